@@ -1,0 +1,73 @@
+"""ctypes binding of libgsd_b200.so (C ABI: include/gsd.h).
+
+There is NO CPU fallback: if the shared library is missing or a call fails the product raises.  Build it with
+``python -c "import __graft_entry__ as g; g.build()"`` (nvcc, sm_100a) — the .so is kept in-tree.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgsd_b200.so")
+
+GSD_STATUS_WORDS = 8
+
+
+class GsdError(RuntimeError):
+    pass
+
+
+class GsdRasterFwd(C.Structure):
+    _fields_ = [
+        ("G", C.c_int32), ("W", C.c_int32), ("H", C.c_int32), ("n_sets", C.c_int32),
+        ("capacity", C.c_int64),
+        ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
+        ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("bg0", C.c_void_p), ("bg1", C.c_void_p),
+        ("means3D", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
+        ("colors0", C.c_void_p), ("colors1", C.c_void_p),
+        ("out_color", C.c_void_p), ("out_depth", C.c_void_p), ("radii", C.c_void_p),
+        ("geom_ws", C.c_void_p), ("binning_ws", C.c_void_p), ("image_ws", C.c_void_p), ("status", C.c_void_p),
+    ]
+
+
+class GsdRasterBwd(C.Structure):
+    _fields_ = [
+        ("fwd", GsdRasterFwd),
+        ("dL_dcolor", C.c_void_p), ("partial_ws", C.c_void_p),
+        ("dL_dmeans3D", C.c_void_p), ("dL_dmeans2D", C.c_void_p), ("dL_dcolors0", C.c_void_p),
+        ("dL_dcolors1", C.c_void_p), ("dL_dopacities", C.c_void_p), ("dL_dscales", C.c_void_p),
+        ("dL_drotations", C.c_void_p),
+    ]
+
+
+_lib = None
+
+# every symbol include/gsd.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "gsd_last_error", "gsd_version",
+    "gsd_raster_workspace_bytes", "gsd_raster_count_instances", "gsd_raster_forward", "gsd_raster_backward",
+    "gsd_raster_mark_visible",
+]
+
+
+def lib():
+    """Loads the shared library; raises GsdError (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GsdError("libgsd_b200.so not built (%s). Run __graft_entry__.build(); there is no CPU fallback." % LIB_PATH)
+    l = C.CDLL(LIB_PATH)
+    l.gsd_last_error.restype = C.c_char_p
+    l.gsd_version.restype = C.c_int
+    l.gsd_raster_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_size_t)]
+    l.gsd_raster_count_instances.argtypes = [C.POINTER(GsdRasterFwd), C.c_void_p]
+    l.gsd_raster_forward.argtypes = [C.POINTER(GsdRasterFwd), C.c_void_p]
+    l.gsd_raster_backward.argtypes = [C.POINTER(GsdRasterBwd), C.c_void_p]
+    l.gsd_raster_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    _lib = l
+    return l
+
+
+def check(rc, what):
+    if rc != 0:
+        raise GsdError("%s failed (%d): %s" % (what, rc, lib().gsd_last_error().decode()))

@@ -1,0 +1,134 @@
+// common.cuh — shared device helpers for libgsd_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gsd.h"
+
+#define GSD_TILE 16
+#define GSD_REC_FLOATS 16  // one packed per-tile-instance record = 64 B
+#define GSD_PART_FLOATS 16 // one backward partial-gradient record = 64 B
+
+void gsd_set_error(const char *fmt, ...);
+
+#define GSD_CUDA_CHECK(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            gsd_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return GSD_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define GSD_LAUNCH_CHECK()                                                                     \
+    do {                                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            gsd_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return GSD_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+static inline size_t gsd_align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---- camera constants passed by value to kernels -------------------------------------------------
+struct GsdCam {
+    const float *view; // device [16]
+    const float *proj; // device [16]
+    float tanfovx, tanfovy, focal_x, focal_y, scale_modifier;
+    int W, H, gx, gy;
+};
+
+// ---- workspace carving (host) ----------------------------------------------------------------------
+struct GsdGeomWs { // per-Gaussian state
+    float2 *xy;        // pixel centre
+    float4 *conic_o;   // conic a,b,c + opacity
+    float2 *ext;       // conservative half extents of the alpha>=1/255 ellipse (pixels)
+    float *depth;      // view-space z
+    uint2 *rect;       // (minx | miny<<16, maxx | maxy<<16) in tiles, max exclusive
+    uint32_t *tiles;   // tiles touched
+    uint32_t *offsets; // inclusive prefix sum of tiles
+    void *scan_tmp;
+    size_t scan_tmp_bytes;
+    size_t total;
+};
+struct GsdBinWs {
+    uint64_t *keys_a, *keys_b;
+    uint32_t *vals_a, *vals_b;
+    uint2 *ranges;  // per tile [start,end)
+    float4 *records; // [capacity][4] packed per-instance records (sorted by tile, depth)
+    void *sort_tmp;
+    size_t sort_tmp_bytes;
+    size_t total;
+};
+struct GsdImgWs {
+    float *final_T;
+    int32_t *n_contrib;
+    size_t total;
+};
+
+int gsd_carve_geom(int G, void *base, GsdGeomWs *ws);
+int gsd_carve_bin(int64_t capacity, int tiles, void *base, GsdBinWs *ws);
+int gsd_carve_img(int W, int H, void *base, GsdImgWs *ws);
+
+struct GsdRenderParams {
+    const uint2 *ranges;
+    const float4 *planes; // 4 planes of [plane_stride] float4
+    int64_t plane_stride;
+    int W, H, gx;
+    const float *bg0, *bg1; // device [3] each; bg1 may be null
+    float *out_color; // [CH,H,W]
+    float *out_depth; // [H,W]
+    float *final_T;
+    int32_t *n_contrib;
+    // backward only
+    const float *dL_dcolor;
+    float *partials; // [capacity][GSD_PART_FLOATS]
+};
+
+#ifdef __CUDACC__
+// ---- mbarrier / bulk async copy (TMA 1-D) -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy (TMA engine), completion counted in bytes on the mbarrier.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// The one place the blend exponent is evaluated: forward and backward must produce bit-identical
+// alpha so that the per-pixel contributor decisions agree. Explicit rn intrinsics stop the compiler from
+// contracting the two kernels differently.
+__device__ __forceinline__ float gsd_power(float A, float B, float C, float dx, float dy) {
+    float a1 = __fmul_rn(A, dx);
+    float c1 = __fmul_rn(C, dy);
+    float s = __fmaf_rn(c1, dy, __fmul_rn(a1, dx));
+    float b1 = __fmul_rn(B, dx);
+    return __fmaf_rn(-0.5f, s, -__fmul_rn(b1, dy));
+}
+__device__ __forceinline__ float gsd_gauss(float power) { return __expf(power); }
+#endif

@@ -1,0 +1,155 @@
+// raster_api.cu — C-ABI entry points of the rasterizer (include/gsd.h, Path A.1).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+// launchers implemented in the other translation units
+int gsd_launch_preprocess(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, cudaStream_t st);
+int gsd_launch_mark_visible(int G, const GsdCam &cam, const float *means3D, uint8_t *vis, cudaStream_t st);
+int gsd_launch_scan(int G, const GsdGeomWs &g, int64_t capacity, int32_t *status, cudaStream_t st);
+int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, const GsdBinWs &b, cudaStream_t st);
+int gsd_launch_render_fwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st);
+int gsd_launch_render_bwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st);
+int gsd_launch_preprocess_bwd(int G, const GsdCam &cam, const GsdRasterBwd *a, const GsdGeomWs &g, cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+
+void gsd_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *gsd_last_error(void) { return g_err; }
+extern "C" int gsd_version(void) { return 100; }
+
+static int make_cam(const GsdRasterFwd *a, GsdCam *cam) {
+    if (!a) { gsd_set_error("null descriptor"); return GSD_ERR_INVALID; }
+    if (a->G < 0 || a->W <= 0 || a->H <= 0 || (a->n_sets != 1 && a->n_sets != 2)) {
+        gsd_set_error("invalid sizes G=%d W=%d H=%d n_sets=%d", a->G, a->W, a->H, a->n_sets);
+        return GSD_ERR_INVALID;
+    }
+    if (a->capacity < 0 || a->capacity > 0x7fffffffLL) { gsd_set_error("capacity out of range"); return GSD_ERR_INVALID; }
+    if (!a->viewmatrix || !a->projmatrix || !a->bg0) { gsd_set_error("null camera pointer"); return GSD_ERR_INVALID; }
+    cam->view = a->viewmatrix;
+    cam->proj = a->projmatrix;
+    cam->tanfovx = a->tanfovx;
+    cam->tanfovy = a->tanfovy;
+    cam->focal_x = a->W / (2.0f * a->tanfovx);
+    cam->focal_y = a->H / (2.0f * a->tanfovy);
+    cam->scale_modifier = a->scale_modifier;
+    cam->W = a->W;
+    cam->H = a->H;
+    cam->gx = (a->W + GSD_TILE - 1) / GSD_TILE;
+    cam->gy = (a->H + GSD_TILE - 1) / GSD_TILE;
+    if (cam->gx > 0xffff || cam->gy > 0xffff) { gsd_set_error("image too large"); return GSD_ERR_INVALID; }
+    return GSD_OK;
+}
+
+extern "C" int gsd_raster_workspace_bytes(int32_t G, int32_t W, int32_t H, int32_t n_sets, int64_t capacity, size_t out[4]) {
+    if (G < 0 || W <= 0 || H <= 0 || capacity < 0 || !out) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
+    (void)n_sets;
+    GsdGeomWs g; GsdBinWs b; GsdImgWs im;
+    int rc;
+    if ((rc = gsd_carve_geom(G, nullptr, &g))) return rc;
+    int tiles = ((W + GSD_TILE - 1) / GSD_TILE) * ((H + GSD_TILE - 1) / GSD_TILE);
+    if ((rc = gsd_carve_bin(capacity, tiles, nullptr, &b))) return rc;
+    if ((rc = gsd_carve_img(W, H, nullptr, &im))) return rc;
+    out[0] = g.total;
+    out[1] = b.total;
+    out[2] = im.total;
+    out[3] = gsd_align_up((size_t)(capacity > 0 ? capacity : 1) * GSD_PART_FLOATS * 4);
+    return GSD_OK;
+}
+
+extern "C" int gsd_raster_count_instances(const GsdRasterFwd *a, void *stream) {
+    GsdCam cam;
+    int rc;
+    if ((rc = make_cam(a, &cam))) return rc;
+    if (!a->geom_ws || !a->status || !a->radii) { gsd_set_error("null workspace"); return GSD_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    GsdGeomWs g;
+    if ((rc = gsd_carve_geom(a->G, a->geom_ws, &g))) return rc;
+    if ((rc = gsd_launch_preprocess(a->G, cam, a, g, st))) return rc;
+    return gsd_launch_scan(a->G, g, 0x7fffffffLL, a->status, st);
+}
+
+extern "C" int gsd_raster_forward(const GsdRasterFwd *a, void *stream) {
+    GsdCam cam;
+    int rc;
+    if ((rc = make_cam(a, &cam))) return rc;
+    if (!a->geom_ws || !a->binning_ws || !a->image_ws || !a->status || !a->radii || !a->out_color || !a->out_depth) {
+        gsd_set_error("null workspace/output pointer");
+        return GSD_ERR_INVALID;
+    }
+    if (a->G > 0 && (!a->means3D || !a->opacities || !a->scales || !a->rotations || !a->colors0 || (a->n_sets == 2 && !a->colors1))) {
+        gsd_set_error("null input pointer");
+        return GSD_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    GsdGeomWs g; GsdBinWs b; GsdImgWs im;
+    const int tiles = cam.gx * cam.gy;
+    if ((rc = gsd_carve_geom(a->G, a->geom_ws, &g))) return rc;
+    if ((rc = gsd_carve_bin(a->capacity, tiles, a->binning_ws, &b))) return rc;
+    if ((rc = gsd_carve_img(a->W, a->H, a->image_ws, &im))) return rc;
+    if ((rc = gsd_launch_preprocess(a->G, cam, a, g, st))) return rc;
+    if ((rc = gsd_launch_scan(a->G, g, a->capacity, a->status, st))) return rc;
+    if ((rc = gsd_launch_binning(a->G, cam, a, g, b, st))) return rc;
+    GsdRenderParams p;
+    memset(&p, 0, sizeof(p));
+    p.ranges = b.ranges;
+    p.planes = b.records;
+    p.plane_stride = a->capacity > 0 ? a->capacity : 1;
+    p.W = a->W; p.H = a->H; p.gx = cam.gx;
+    p.bg0 = a->bg0; p.bg1 = a->n_sets == 2 ? a->bg1 : nullptr;
+    p.out_color = a->out_color;
+    p.out_depth = a->out_depth;
+    p.final_T = im.final_T;
+    p.n_contrib = im.n_contrib;
+    return gsd_launch_render_fwd(p, tiles, a->n_sets, st);
+}
+
+extern "C" int gsd_raster_backward(const GsdRasterBwd *a, void *stream) {
+    if (!a) { gsd_set_error("null descriptor"); return GSD_ERR_INVALID; }
+    const GsdRasterFwd *f = &a->fwd;
+    GsdCam cam;
+    int rc;
+    if ((rc = make_cam(f, &cam))) return rc;
+    if (!f->geom_ws || !f->binning_ws || !f->image_ws || !a->partial_ws || !a->dL_dcolor || !a->dL_dmeans3D ||
+        !a->dL_dopacities || !a->dL_dscales || !a->dL_drotations) {
+        gsd_set_error("null workspace/output pointer");
+        return GSD_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    GsdGeomWs g; GsdBinWs b; GsdImgWs im;
+    const int tiles = cam.gx * cam.gy;
+    if ((rc = gsd_carve_geom(f->G, f->geom_ws, &g))) return rc;
+    if ((rc = gsd_carve_bin(f->capacity, tiles, f->binning_ws, &b))) return rc;
+    if ((rc = gsd_carve_img(f->W, f->H, f->image_ws, &im))) return rc;
+    GsdRenderParams p;
+    memset(&p, 0, sizeof(p));
+    p.ranges = b.ranges;
+    p.planes = b.records;
+    p.plane_stride = f->capacity > 0 ? f->capacity : 1;
+    p.W = f->W; p.H = f->H; p.gx = cam.gx;
+    p.bg0 = f->bg0; p.bg1 = f->n_sets == 2 ? f->bg1 : nullptr;
+    p.out_color = f->out_color;
+    p.out_depth = f->out_depth;
+    p.final_T = im.final_T;
+    p.n_contrib = im.n_contrib;
+    p.dL_dcolor = a->dL_dcolor;
+    p.partials = (float *)a->partial_ws;
+    if (f->G > 0 && f->capacity > 0)
+        if ((rc = gsd_launch_render_bwd(p, tiles, f->n_sets, st))) return rc;
+    return gsd_launch_preprocess_bwd(f->G, cam, a, g, st);
+}
+
+extern "C" int gsd_raster_mark_visible(int32_t G, const float *means3D, const float *viewmatrix, uint8_t *visible, void *stream) {
+    if (G < 0 || !viewmatrix || (G > 0 && (!means3D || !visible))) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
+    GsdCam cam;
+    memset(&cam, 0, sizeof(cam));
+    cam.view = viewmatrix;
+    return gsd_launch_mark_visible(G, cam, means3D, visible, (cudaStream_t)stream);
+}

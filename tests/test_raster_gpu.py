@@ -1,0 +1,214 @@
+"""GPU parity tests of the rasterizer (through the C ABI) against the CPU oracle (oracle/raster_oracle.c).
+
+Tolerances (fp32; north_star: "within a stated fp32 tolerance"):
+  * radii: exact (the preprocess kernel is compiled without FMA contraction to match the oracle's op order);
+  * colour / depth: |diff| <= 1e-4 for >= 99.99 % of pixels; the remaining pixels may differ by at most 1e-2 — a
+    Gaussian whose alpha is within one ulp of the 1/255 threshold can flip in/out because the kernel evaluates
+    exp() with ex2.approx (upstream itself is not reproducible at that level);
+  * gradients: max-abs error <= 1e-3 of the tensor's max-abs value (reduction-order + exp differences).
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import make_camera, make_scene, oracle_backward, oracle_forward, rel_err, settings_from
+
+pytestmark = pytest.mark.gpu
+
+
+def _to_cuda(act):
+    return {k: v.cuda() for k, v in act.items()}
+
+
+def _render(act_c, st, colors1=None, capacity=None, bg1=None):
+    from gs_dynamics_b200 import rasterizer as R
+    return R.raster_forward(st, act_c["means3D"], act_c["opacities"], act_c["colors_precomp"], act_c["scales"],
+                            act_c["rotations"], colors1=colors1, capacity=capacity, bg1=bg1)
+
+
+def _img_close(a, b, atol=1e-4, frac=1e-4, hard=1e-2):
+    d = np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))
+    bad = (d > atol).mean()
+    assert bad <= frac, "fraction of pixels beyond %g: %g (max %g)" % (atol, bad, d.max())
+    assert d.max() <= hard, "max abs diff %g" % d.max()
+
+
+@pytest.mark.parametrize("G,w,h,seed,boost,cam_id", [(2000, 128, 96, 1, 1.2, 0), (5000, 100, 70, 2, 1.0, 1),
+                                                     (20000, 640, 480, 3, 0.0, 2), (50000, 640, 480, 0, 0.0, 3)])
+def test_forward_parity(G, w, h, seed, boost, cam_id):
+    cam = make_camera(cam_id, w, h)
+    sc, act = make_scene(G, seed, scale_boost=boost, box_scale=0.6 if w < 640 else 1.0)
+    bg = [0.1, 0.2, 0.3]
+    fo = oracle_forward(act, cam, torch.tensor(bg))
+    color, radii, depth, state = _render(_to_cuda(act), settings_from(cam, bg))
+    torch.cuda.synchronize()
+    assert int(state.status[0].item()) == fo["R"]
+    assert int(state.status[1].item()) == 0
+    assert np.array_equal(radii.cpu().numpy(), fo["radii"])
+    _img_close(color.cpu().numpy(), fo["color"])
+    _img_close(depth.cpu().numpy(), fo["depth"])
+
+
+@pytest.mark.parametrize("G,w,h,seed,boost", [(2000, 128, 96, 1, 1.2), (3000, 100, 70, 4, 1.0), (20000, 640, 480, 3, 0.0)])
+def test_backward_parity(G, w, h, seed, boost):
+    from gs_dynamics_b200 import rasterizer as R
+    cam = make_camera(0, w, h)
+    sc, act = make_scene(G, seed, scale_boost=boost, box_scale=0.6 if w < 640 else 1.0)
+    bg = [0.3, 0.1, 0.7]
+    g = torch.Generator().manual_seed(seed)
+    dL = torch.randn(3, h, w, generator=g)
+    bo = oracle_backward(act, cam, torch.tensor(bg), dL)
+    color, radii, depth, state = _render(_to_cuda(act), settings_from(cam, bg))
+    gr = R.raster_backward(state, dL.cuda())
+    torch.cuda.synchronize()
+    tol = 1e-3
+    assert rel_err(gr["means3D"].cpu(), bo["means3D"]) < tol
+    assert rel_err(gr["means2D"].cpu(), bo["means2D"]) < tol
+    assert rel_err(gr["colors0"].cpu(), bo["colors"]) < tol
+    assert rel_err(gr["opacities"].cpu().reshape(-1), bo["opacities"]) < tol
+    assert rel_err(gr["scales"].cpu(), bo["scales"]) < tol
+    assert rel_err(gr["rotations"].cpu(), bo["rotations"]) < tol
+
+
+def test_autograd_module_surface():
+    """The reference's call pattern: keyword call, means2D as gradient sink (train_utils.py:174-178)."""
+    from gs_dynamics_b200.rasterizer import GaussianRasterizer
+    cam = make_camera(1, 160, 120)
+    sc, act = make_scene(3000, 5, scale_boost=1.0, box_scale=0.6)
+    bg = [0.0, 0.0, 0.0]
+    st = settings_from(cam, bg)
+    leaves = {k: v.cuda().requires_grad_(True) for k, v in act.items()}
+    means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    im, radius, depth = GaussianRasterizer(raster_settings=st)(
+        means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
+        colors_precomp=leaves["colors_precomp"], scales=leaves["scales"], rotations=leaves["rotations"])
+    assert im.shape == (3, 120, 160) and depth.shape == (1, 120, 160) and radius.dtype == torch.int32
+    target = torch.rand(3, 120, 160, generator=torch.Generator().manual_seed(0)).cuda()
+    loss = (im - target).abs().mean()
+    loss.backward()
+    dL = torch.sign(im.detach() - target).cpu() / im.numel()
+    bo = oracle_backward(act, cam, torch.tensor(bg), dL)
+    assert rel_err(leaves["means3D"].grad.cpu(), bo["means3D"]) < 2e-3
+    assert rel_err(means2D.grad.cpu(), bo["means2D"]) < 2e-3
+    assert rel_err(leaves["opacities"].grad.cpu().reshape(-1), bo["opacities"]) < 2e-3
+    assert leaves["opacities"].grad.shape == leaves["opacities"].shape
+    # error behaviour of upstream's forward()
+    with pytest.raises(Exception):
+        GaussianRasterizer(raster_settings=st)(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"])
+
+
+def test_fused_two_sets_equals_two_renders():
+    """One 6-channel pass == the reference's two 3-channel passes (RGB + seg share geometry, train_utils.py:174-192)."""
+    from gs_dynamics_b200 import rasterizer as R
+    cam = make_camera(2, 320, 240)
+    sc, act = make_scene(8000, 6, scale_boost=0.6, box_scale=0.8)
+    a = _to_cuda(act)
+    seg = sc["seg_colors"].cuda() * torch.rand(8000, 1, device="cuda")
+    bg = [0.2, 0.3, 0.4]
+    st = settings_from(cam, bg)
+    bg1 = torch.tensor([0.5, 0.0, 0.1], device="cuda")
+    c0, r0, d0, s0 = _render(a, st)
+    a_seg = dict(a, colors_precomp=seg)
+    st1 = st._replace(bg=bg1)
+    c1, r1, d1, s1 = _render(a_seg, st1)
+    cf, rf, df, sf = _render(a, st, colors1=seg, bg1=bg1)
+    assert torch.equal(cf[:3], c0) and torch.equal(cf[3:], c1) and torch.equal(df, d0) and torch.equal(rf, r0)
+    dL = torch.randn(6, 240, 320, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    g0 = R.raster_backward(s0, dL[:3].contiguous())
+    g1 = R.raster_backward(s1, dL[3:].contiguous())
+    gf = R.raster_backward(sf, dL)
+    for k in ("means3D", "means2D", "opacities", "scales", "rotations"):
+        ref = g0[k] + g1[k]
+        assert rel_err(gf[k].cpu(), ref.cpu()) < 1e-4, k
+    assert rel_err(gf["colors0"].cpu(), g0["colors0"].cpu()) < 1e-5
+    assert rel_err(gf["colors1"].cpu(), g1["colors0"].cpu()) < 1e-5
+
+
+def test_backward_is_bit_reproducible():
+    from gs_dynamics_b200 import rasterizer as R
+    cam = make_camera(0, 640, 480)
+    sc, act = make_scene(30000, 9)
+    a = _to_cuda(act)
+    st = settings_from(cam, [0, 0, 0])
+    dL = torch.randn(3, 480, 640, device="cuda")
+    outs = []
+    for _ in range(3):
+        c, r, d, s = _render(a, st)
+        outs.append(R.raster_backward(s, dL))
+    for k in ("means3D", "means2D", "colors0", "opacities", "scales", "rotations"):
+        assert torch.equal(outs[0][k], outs[1][k]) and torch.equal(outs[0][k], outs[2][k]), k
+
+
+def test_capacity_modes_and_overflow_flag():
+    cam = make_camera(3, 320, 240)
+    sc, act = make_scene(6000, 11, scale_boost=0.5, box_scale=0.8)
+    a = _to_cuda(act)
+    st = settings_from(cam, [0.1, 0.1, 0.1])
+    c_exact, r_exact, d_exact, s_exact = _render(a, st)
+    R_true = int(s_exact.status[0].item())
+    c_cap, r_cap, d_cap, s_cap = _render(a, st, capacity=int(R_true * 1.5) + 7)
+    assert torch.equal(c_exact, c_cap) and torch.equal(d_exact, d_cap) and torch.equal(r_exact, r_cap)
+    assert int(s_cap.status[1].item()) == 0
+    c_small, _, _, s_small = _render(a, st, capacity=R_true // 2)
+    torch.cuda.synchronize()
+    assert int(s_small.status[0].item()) == R_true and int(s_small.status[1].item()) == 1
+    assert torch.isfinite(c_small).all()
+
+
+def test_edge_cases_empty_culled_ragged():
+    from gs_dynamics_b200 import rasterizer as R
+    cam = make_camera(0, 50, 34)  # not multiples of 16
+    st = settings_from(cam, [0.2, 0.4, 0.6])
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    # G = 0
+    c, r, d, s = R.raster_forward(st, z(0, 3), z(0, 1), z(0, 3), z(0, 3), z(0, 4))
+    assert c.shape == (3, 34, 50) and torch.allclose(c[1], torch.full((34, 50), 0.4, device="cuda")) and (d == 0).all()
+    g = R.raster_backward(s, torch.ones(3, 34, 50, device="cuda"))
+    assert g["means3D"].shape == (0, 3)
+    # everything culled (behind the camera)
+    sc, act = make_scene(64, 0)
+    a = _to_cuda(act)
+    a["means3D"] = a["means3D"] + torch.tensor([0.0, 0.0, 100.0], device="cuda")
+    c, r, d, s = _render(a, st)
+    assert (r == 0).all() and torch.allclose(c[2], torch.full((34, 50), 0.6, device="cuda"))
+    g = R.raster_backward(s, torch.ones(3, 34, 50, device="cuda"))
+    assert all(float(v.abs().max()) == 0.0 for v in g.values() if v is not None)
+    # ragged image vs oracle
+    sc, act = make_scene(1500, 3, scale_boost=1.3, box_scale=0.5)
+    fo = oracle_forward(act, cam, torch.tensor([0.2, 0.4, 0.6]))
+    c, r, d, s = _render(_to_cuda(act), st)
+    _img_close(c.cpu().numpy(), fo["color"])
+    assert np.array_equal(r.cpu().numpy(), fo["radii"])
+
+
+def test_full_size_properties_100k():
+    """BASELINE size (100k Gaussians, 640x480): size-independent properties instead of the slow oracle.
+       * ones-colour/bg0 image + zero-colour/bg1 image == 1 (alpha compositing partition of unity);
+       * linearity of the image in the colours."""
+    cam = make_camera(0, 640, 480)
+    sc, act = make_scene(100000, 0)
+    a = _to_cuda(act)
+    ones = torch.ones_like(a["colors_precomp"])
+    zeros = torch.zeros_like(a["colors_precomp"])
+    st0 = settings_from(cam, [0, 0, 0])
+    st1 = settings_from(cam, [1, 1, 1])
+    m, _, _, s = _render(dict(a, colors_precomp=ones), st0)
+    t, _, _, _ = _render(dict(a, colors_precomp=zeros), st1)
+    assert float((m + t - 1).abs().max()) < 1e-5
+    c1, _, _, _ = _render(a, st0)
+    c2, _, _, _ = _render(dict(a, colors_precomp=ones - a["colors_precomp"]), st0)
+    assert float((c1 + c2 - m).abs().max()) < 1e-5
+    R_true = int(s.status[0].item())
+    assert 300000 < R_true < 420000  # R ~ 353k per camera at G = 100k
+
+
+def test_mark_visible():
+    from gs_dynamics_b200.rasterizer import GaussianRasterizer
+    cam = make_camera(0, 64, 48)
+    st = settings_from(cam, [0, 0, 0])
+    pts = torch.randn(1000, 3, device="cuda")
+    vis = GaussianRasterizer(st).markVisible(pts)
+    V = cam["viewmatrix"].reshape(4, 4).cuda()
+    z = pts @ V[:3, 2] + V[3, 2]
+    borderline = (z - 0.2).abs() < 1e-5
+    assert torch.equal(vis[~borderline], (z > 0.2)[~borderline])
