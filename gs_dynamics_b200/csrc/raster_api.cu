@@ -68,7 +68,7 @@ extern "C" int gsd_raster_count_instances(const GsdRasterFwd *a, void *stream) {
     GsdCam cam;
     int rc;
     if ((rc = make_cam(a, &cam))) return rc;
-    if (!a->geom_ws || !a->status || !a->radii) { gsd_set_error("null workspace"); return GSD_ERR_INVALID; }
+    if (!a->geom_ws || !a->status || (a->G > 0 && !a->radii)) { gsd_set_error("null workspace"); return GSD_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     GsdGeomWs g;
     if ((rc = gsd_carve_geom(a->G, a->geom_ws, &g))) return rc;
@@ -80,7 +80,7 @@ extern "C" int gsd_raster_forward(const GsdRasterFwd *a, void *stream) {
     GsdCam cam;
     int rc;
     if ((rc = make_cam(a, &cam))) return rc;
-    if (!a->geom_ws || !a->binning_ws || !a->image_ws || !a->status || !a->radii || !a->out_color || !a->out_depth) {
+    if (!a->geom_ws || !a->binning_ws || !a->image_ws || !a->status || (a->G > 0 && !a->radii) || !a->out_color || !a->out_depth) {
         gsd_set_error("null workspace/output pointer");
         return GSD_ERR_INVALID;
     }
@@ -117,8 +117,8 @@ extern "C" int gsd_raster_backward(const GsdRasterBwd *a, void *stream) {
     GsdCam cam;
     int rc;
     if ((rc = make_cam(f, &cam))) return rc;
-    if (!f->geom_ws || !f->binning_ws || !f->image_ws || !a->partial_ws || !a->dL_dcolor || !a->dL_dmeans3D ||
-        !a->dL_dopacities || !a->dL_dscales || !a->dL_drotations) {
+    if (!f->geom_ws || !f->binning_ws || !f->image_ws || !a->partial_ws || !a->dL_dcolor ||
+        (f->G > 0 && (!a->dL_dmeans3D || !a->dL_dopacities || !a->dL_dscales || !a->dL_drotations))) {
         gsd_set_error("null workspace/output pointer");
         return GSD_ERR_INVALID;
     }

@@ -125,8 +125,8 @@ __global__ void gsd_fill_sentinel_kernel(int64_t capacity, const int32_t *__rest
 }
 
 // one thread per sorted instance: tile range boundaries + the packed record
-//   rec[0] = (x, y, ext_x, ext_y)   rec[1] = (A, B, C, opacity)
-//   rec[2] = (c0, c1, c2, depth)    rec[3] = (slot bits, c3, c4, c5)
+//   plane0 = (x, y, ext_x, ext_y)   plane1 = (A, B, C, opacity)
+//   plane2 = (c0, c1, c2, depth)    plane3 = (slot bits, c3, c4, c5)
 // slot = position of this instance in the *unsorted* per-Gaussian order (offset + rank of the tile inside the
 // Gaussian's rectangle): the backward writes its partial gradient there so that a Gaussian's partials are
 // contiguous and can be summed in a fixed order without atomics.
@@ -170,11 +170,11 @@ gsd_pack_records_kernel(int64_t capacity, int gx, const int32_t *__restrict__ st
         c4 = colors1[3 * g + 1];
         c5 = colors1[3 * g + 2];
     }
-    float4 *out = records + j * 4;
-    out[0] = make_float4(p.x, p.y, e.x, e.y);
-    out[1] = co;
-    out[2] = make_float4(c0, c1, c2, d);
-    out[3] = make_float4(__uint_as_float(slot), c3, c4, c5);
+    // four SoA planes of [capacity] float4 (each plane is one contiguous bulk-copy source per tile batch)
+    records[j] = make_float4(p.x, p.y, e.x, e.y);
+    records[capacity + j] = co;
+    records[2 * capacity + j] = make_float4(c0, c1, c2, d);
+    records[3 * capacity + j] = make_float4(__uint_as_float(slot), c3, c4, c5);
 }
 
 // ---- host launchers -------------------------------------------------------------------------------------

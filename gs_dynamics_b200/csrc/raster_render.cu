@@ -164,19 +164,20 @@ __device__ __forceinline__ void xreduce(float *v, int lane) {
         xreduce<Hh, BIT / 2>(v, lane);
     }
 }
+// Mirrors xreduce's index bookkeeping: every stage halves the (zero-padded) value range [base, base+n) for all lanes
+// alike; the lane ends up with value `base`, which is real only if it lies inside the unpadded range.
 __device__ __forceinline__ int holder_id(int N, int lane) {
-    int base = 0;
+    int base = 0, n = N, end = N;
     for (int bit = 16; bit >= 1; bit >>= 1) {
-        if (N == 0) break;
-        int Hh = (N + 1) / 2;
+        const int Hh = (n + 1) / 2;
         if (lane & bit) {
             base += Hh;
-            N -= Hh;
         } else {
-            N = Hh;
+            end = min(end, base + Hh);
         }
+        n = Hh;
     }
-    return N == 1 ? base : -1;
+    return base < end ? base : -1;
 }
 
 template <int CH>
