@@ -39,6 +39,31 @@ class GsdRasterBwd(C.Structure):
     ]
 
 
+GSD_ADAM_MAX_TENSORS = 16
+
+
+class GsdTrackLosses(C.Structure):
+    _fields_ = [
+        ("G", C.c_int32), ("Gf", C.c_int32), ("K", C.c_int32), ("Gb", C.c_int32),
+        ("means3D", C.c_void_p), ("rotations", C.c_void_p), ("fg_index", C.c_void_p), ("prev_inv_rot", C.c_void_p),
+        ("neighbor_indices", C.c_void_p), ("neighbor_weight", C.c_void_p), ("neighbor_dist", C.c_void_p),
+        ("prev_offset", C.c_void_p), ("in_ptr", C.c_void_p), ("in_edge", C.c_void_p), ("bg_index", C.c_void_p),
+        ("init_bg_pts", C.c_void_p), ("init_bg_rot", C.c_void_p),
+        ("w_rigid", C.c_float), ("w_rot", C.c_float), ("w_iso", C.c_float), ("w_floor", C.c_float), ("w_bg", C.c_float),
+        ("ws", C.c_void_p), ("losses", C.c_void_p), ("grad_means3D", C.c_void_p), ("grad_rotations", C.c_void_p),
+    ]
+
+
+class GsdAdam(C.Structure):
+    _fields_ = [
+        ("n_tensors", C.c_int32), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("param", C.c_void_p * GSD_ADAM_MAX_TENSORS), ("grad", C.c_void_p * GSD_ADAM_MAX_TENSORS),
+        ("exp_avg", C.c_void_p * GSD_ADAM_MAX_TENSORS), ("exp_avg_sq", C.c_void_p * GSD_ADAM_MAX_TENSORS),
+        ("step", C.c_void_p * GSD_ADAM_MAX_TENSORS), ("lr", C.c_float * GSD_ADAM_MAX_TENSORS),
+        ("numel", C.c_int64 * GSD_ADAM_MAX_TENSORS),
+    ]
+
+
 _lib = None
 
 # every symbol include/gsd.h declares (checked by tests/test_abi.py)
@@ -46,6 +71,8 @@ EXPORTS = [
     "gsd_last_error", "gsd_version",
     "gsd_raster_workspace_bytes", "gsd_raster_count_instances", "gsd_raster_forward", "gsd_raster_backward",
     "gsd_raster_mark_visible",
+    "gsd_photometric_workspace_bytes", "gsd_photometric_forward", "gsd_photometric_backward",
+    "gsd_track_losses_workspace_bytes", "gsd_track_losses_fwd_bwd", "gsd_adam_step", "gsd_track_update_radii",
 ]
 
 
@@ -64,6 +91,15 @@ def lib():
     l.gsd_raster_forward.argtypes = [C.POINTER(GsdRasterFwd), C.c_void_p]
     l.gsd_raster_backward.argtypes = [C.POINTER(GsdRasterBwd), C.c_void_p]
     l.gsd_raster_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.gsd_photometric_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
+    l.gsd_photometric_forward.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]
+    l.gsd_photometric_backward.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                           C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    l.gsd_track_losses_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
+    l.gsd_track_losses_fwd_bwd.argtypes = [C.POINTER(GsdTrackLosses), C.c_void_p]
+    l.gsd_adam_step.argtypes = [C.POINTER(GsdAdam), C.c_void_p]
+    l.gsd_track_update_radii.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = l
     return l
 

@@ -1,0 +1,287 @@
+// track_losses.cu — the physical priors of the tracking iteration, forward + backward in one pass:
+//   rigid  = mean sqrt(w * |R_i^T (x_j - x_i) - prev_offset_ik|^2 + 1e-20)
+//   rot    = mean sqrt(w * |rel_j - rel_i|^2 + 1e-20),   rel = q (x) prev_inv_q
+//   iso    = mean sqrt(w * (sqrt(|x_j - x_i|^2 + 1e-20) - d0_ik)^2 + 1e-20)
+//   floor  = mean clamp(y_fg, min=0);   bg = mean |x_bg - x0|_1 + mean |q_bg - q0|_1
+// Reference: /root/reference/src/tracking/train_utils.py:198-240 (get_loss), helpers.py:79-94
+// (weighted_l2_loss_v1/v2, quat_mult), external.py:25-42 (build_rotation).
+//
+// One thread per foreground point.  Its own gradient (x_i, q_i) is accumulated in registers over its K out-edges;
+// the gradient it receives as somebody's neighbour is accumulated by walking its IN-edges (transposed CSR built once
+// per episode — the kNN graph is static) and recomputing those edges.  No atomics, no [G,K,3] temporaries, fixed
+// summation order (the reference materialises ~15 such temporaries and scatters with index_put atomics).
+// Algorithmic bytes: 56*G*K + 72*G per call; node data is L2-resident.
+#include "common.cuh"
+
+struct TrackArgs {
+    int Gf, K, Gb;
+    const float *x;        // [G,3] means3D
+    const float *q;        // [G,4] normalised rotations
+    const int32_t *fg_index; // [Gf] or null (identity)
+    const float *prev_inv; // [Gf,4]
+    const int32_t *nbr;    // [Gf,K] indices into the fg set
+    const float *nbr_w, *nbr_d; // [Gf,K]
+    const float *prev_off; // [Gf,K,3]
+    const int32_t *in_ptr; // [Gf+1]
+    const int32_t *in_edge;// [Gf*K] edge ids (i*K+k) grouped by neighbour
+    const int32_t *bg_index; // [Gb]
+    const float *bg_x0, *bg_q0; // [Gb,3], [Gb,4]
+    float c_rigid, c_rot, c_iso, c_floor, c_bg; // weight / count
+    float *grad_x, *grad_q; // [G,3], [G,4]
+    float *block_sums;     // [nblocks][5]
+};
+
+struct Quat { float w, x, y, z; };
+
+__device__ __forceinline__ Quat qmul(Quat a, Quat b) {
+    Quat r;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x;
+    r.z = a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w;
+    return r;
+}
+// gradient w.r.t. a of qmul(a, b) given gradient g w.r.t. the product
+__device__ __forceinline__ Quat qmul_bwd_a(Quat g, Quat b) {
+    Quat r;
+    r.w = b.w * g.w + b.x * g.x + b.y * g.y + b.z * g.z;
+    r.x = -b.x * g.w + b.w * g.x - b.z * g.y + b.y * g.z;
+    r.y = -b.y * g.w + b.z * g.x + b.w * g.y - b.x * g.z;
+    r.z = -b.z * g.w - b.y * g.x + b.x * g.y + b.w * g.z;
+    return r;
+}
+__device__ __forceinline__ void rot_from_unit(Quat n, float R[3][3]) {
+    float r = n.w, x = n.x, y = n.y, z = n.z;
+    R[0][0] = 1.f - 2.f * (y * y + z * z); R[0][1] = 2.f * (x * y - r * z); R[0][2] = 2.f * (x * z + r * y);
+    R[1][0] = 2.f * (x * y + r * z); R[1][1] = 1.f - 2.f * (x * x + z * z); R[1][2] = 2.f * (y * z - r * x);
+    R[2][0] = 2.f * (x * z - r * y); R[2][1] = 2.f * (y * z + r * x); R[2][2] = 1.f - 2.f * (x * x + y * y);
+}
+__device__ __forceinline__ Quat load_q(const float *p, int i) {
+    float4 v = *reinterpret_cast<const float4 *>(p + 4 * (size_t)i);
+    return Quat{v.x, v.y, v.z, v.w};
+}
+
+struct EdgeOut { float g_off[3]; float dLde[3]; float g_rel[4]; float s1, s2, s3; };
+
+// evaluates one edge i -> j; g_off = dL/d(x_j - x_i), dLde = dL/d(R_i^T off - prev), g_rel = dL/d rel_j (= -dL/d rel_i)
+__device__ __forceinline__ void eval_edge(const TrackArgs &a, const float xi[3], const float Ri[3][3], Quat rel_i,
+                                          const float xj[3], Quat rel_j, float w, float d0, const float po[3],
+                                          EdgeOut &o) {
+    float off[3] = {xj[0] - xi[0], xj[1] - xi[1], xj[2] - xi[2]};
+    float e[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) e[c] = Ri[0][c] * off[0] + Ri[1][c] * off[1] + Ri[2][c] * off[2] - po[c];
+    float s1 = sqrtf(w * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) + 1e-20f);
+    float cr = a.c_rigid * w / s1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o.dLde[c] = cr * e[c];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) o.g_off[b] = Ri[b][0] * o.dLde[0] + Ri[b][1] * o.dLde[1] + Ri[b][2] * o.dLde[2];
+    float d[4] = {rel_j.w - rel_i.w, rel_j.x - rel_i.x, rel_j.y - rel_i.y, rel_j.z - rel_i.z};
+    float s2 = sqrtf(w * (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]) + 1e-20f);
+    float crot = a.c_rot * w / s2;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o.g_rel[c] = crot * d[c];
+    float m = sqrtf(off[0] * off[0] + off[1] * off[1] + off[2] * off[2] + 1e-20f);
+    float dm = m - d0;
+    float s3 = sqrtf(w * dm * dm + 1e-20f);
+    float ciso = a.c_iso * w * dm / (s3 * m);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o.g_off[c] += ciso * off[c];
+    o.s1 = s1; o.s2 = s2; o.s3 = s3;
+}
+
+__global__ void __launch_bounds__(128)
+gsd_track_fg_kernel(TrackArgs a) {
+    __shared__ float red[4][4];
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    float s_rigid = 0.f, s_rot = 0.f, s_iso = 0.f, s_floor = 0.f;
+    if (f < a.Gf) {
+        const int gi = a.fg_index ? a.fg_index[f] : f;
+        float xi[3] = {a.x[3 * (size_t)gi], a.x[3 * (size_t)gi + 1], a.x[3 * (size_t)gi + 2]};
+        Quat qi = load_q(a.q, gi), pi = load_q(a.prev_inv, f);
+        Quat rel_i = qmul(qi, pi);
+        float nrm = sqrtf(rel_i.w * rel_i.w + rel_i.x * rel_i.x + rel_i.y * rel_i.y + rel_i.z * rel_i.z);
+        float inv_n = 1.f / nrm;
+        Quat n_i = {rel_i.w * inv_n, rel_i.x * inv_n, rel_i.y * inv_n, rel_i.z * inv_n};
+        float Ri[3][3];
+        rot_from_unit(n_i, Ri);
+        float gx[3] = {0.f, 0.f, 0.f}, grel[4] = {0.f, 0.f, 0.f, 0.f};
+        float Gm[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+        // ---- out-edges: f is the centre point
+        for (int k = 0; k < a.K; ++k) {
+            const size_t e = (size_t)f * a.K + k;
+            const int j = a.nbr[e];
+            const int gj = a.fg_index ? a.fg_index[j] : j;
+            float xj[3] = {a.x[3 * (size_t)gj], a.x[3 * (size_t)gj + 1], a.x[3 * (size_t)gj + 2]};
+            Quat rel_j = qmul(load_q(a.q, gj), load_q(a.prev_inv, j));
+            float po[3] = {a.prev_off[3 * e], a.prev_off[3 * e + 1], a.prev_off[3 * e + 2]};
+            EdgeOut o;
+            eval_edge(a, xi, Ri, rel_i, xj, rel_j, a.nbr_w[e], a.nbr_d[e], po, o);
+            float off[3] = {xj[0] - xi[0], xj[1] - xi[1], xj[2] - xi[2]};
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                gx[b] -= o.g_off[b];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Gm[b][c] += off[b] * o.dLde[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) grel[c] -= o.g_rel[c];
+            s_rigid += o.s1; s_rot += o.s2; s_iso += o.s3;
+        }
+        // dL/dR_i -> dL/dn_i -> dL/drel_i (through the normalisation inside build_rotation)
+        {
+            float r = n_i.w, x = n_i.x, y = n_i.y, z = n_i.z;
+            float gn[4];
+            gn[0] = 2.f * (-z * Gm[0][1] + y * Gm[0][2] + z * Gm[1][0] - x * Gm[1][2] - y * Gm[2][0] + x * Gm[2][1]);
+            gn[1] = 2.f * (y * Gm[0][1] + z * Gm[0][2] + y * Gm[1][0] - 2.f * x * Gm[1][1] - r * Gm[1][2] + z * Gm[2][0] + r * Gm[2][1] - 2.f * x * Gm[2][2]);
+            gn[2] = 2.f * (-2.f * y * Gm[0][0] + x * Gm[0][1] + r * Gm[0][2] + x * Gm[1][0] + z * Gm[1][2] - r * Gm[2][0] + z * Gm[2][1] - 2.f * y * Gm[2][2]);
+            gn[3] = 2.f * (-2.f * z * Gm[0][0] - r * Gm[0][1] + x * Gm[0][2] + r * Gm[1][0] - 2.f * z * Gm[1][1] + y * Gm[1][2] + x * Gm[2][0] + y * Gm[2][1]);
+            float dot = r * gn[0] + x * gn[1] + y * gn[2] + z * gn[3];
+            grel[0] += (gn[0] - r * dot) * inv_n;
+            grel[1] += (gn[1] - x * dot) * inv_n;
+            grel[2] += (gn[2] - y * dot) * inv_n;
+            grel[3] += (gn[3] - z * dot) * inv_n;
+        }
+        // ---- in-edges: f is the neighbour of some centre i2
+        const int e0 = a.in_ptr[f], e1 = a.in_ptr[f + 1];
+        for (int t = e0; t < e1; ++t) {
+            const int e = a.in_edge[t];
+            const int i2 = e / a.K;
+            const int g2 = a.fg_index ? a.fg_index[i2] : i2;
+            float x2[3] = {a.x[3 * (size_t)g2], a.x[3 * (size_t)g2 + 1], a.x[3 * (size_t)g2 + 2]};
+            Quat rel_2 = qmul(load_q(a.q, g2), load_q(a.prev_inv, i2));
+            float n2 = rsqrtf(rel_2.w * rel_2.w + rel_2.x * rel_2.x + rel_2.y * rel_2.y + rel_2.z * rel_2.z);
+            Quat u2 = {rel_2.w * n2, rel_2.x * n2, rel_2.y * n2, rel_2.z * n2};
+            float R2[3][3];
+            rot_from_unit(u2, R2);
+            float po[3] = {a.prev_off[3 * (size_t)e], a.prev_off[3 * (size_t)e + 1], a.prev_off[3 * (size_t)e + 2]};
+            EdgeOut o;
+            eval_edge(a, x2, R2, rel_2, xi, rel_i, a.nbr_w[e], a.nbr_d[e], po, o);
+#pragma unroll
+            for (int b = 0; b < 3; ++b) gx[b] += o.g_off[b];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) grel[c] += o.g_rel[c];
+        }
+        // floor
+        if (xi[1] > 0.f) { gx[1] += a.c_floor; s_floor = xi[1]; }
+        Quat gq = qmul_bwd_a(Quat{grel[0], grel[1], grel[2], grel[3]}, pi);
+        a.grad_x[3 * (size_t)gi] = gx[0]; a.grad_x[3 * (size_t)gi + 1] = gx[1]; a.grad_x[3 * (size_t)gi + 2] = gx[2];
+        *reinterpret_cast<float4 *>(a.grad_q + 4 * (size_t)gi) = make_float4(gq.w, gq.x, gq.y, gq.z);
+    }
+    // block partial sums, fixed order
+    float v[4] = {s_rigid, s_rot, s_iso, s_floor};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) red[threadIdx.x >> 5][c] = v[c];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+        a.block_sums[5 * (size_t)blockIdx.x + threadIdx.x] = s;
+    }
+    if (threadIdx.x == 4) a.block_sums[5 * (size_t)blockIdx.x + 4] = 0.f;
+}
+
+__global__ void __launch_bounds__(128)
+gsd_track_bg_kernel(TrackArgs a, int fg_blocks) {
+    __shared__ float red[4];
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    float s = 0.f;
+    if (b < a.Gb) {
+        const int gi = a.bg_index[b];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float d = a.x[3 * (size_t)gi + c] - a.bg_x0[3 * (size_t)b + c];
+            s += fabsf(d);
+            a.grad_x[3 * (size_t)gi + c] = a.c_bg * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float d = a.q[4 * (size_t)gi + c] - a.bg_q0[4 * (size_t)b + c];
+            s += fabsf(d);
+            a.grad_q[4 * (size_t)gi + c] = a.c_bg * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        size_t row = (size_t)fg_blocks + blockIdx.x;
+        a.block_sums[5 * row + 0] = 0.f; a.block_sums[5 * row + 1] = 0.f; a.block_sums[5 * row + 2] = 0.f;
+        a.block_sums[5 * row + 3] = 0.f;
+        a.block_sums[5 * row + 4] = red[0] + red[1] + red[2] + red[3];
+    }
+}
+
+// losses[0..4] = rigid, rot, iso, floor, bg (unweighted means); losses[5] = weighted total
+__global__ void gsd_track_finish_kernel(int nrows, const float *__restrict__ block_sums, float inv_e, float inv_f,
+                                        float inv_b, float w_rigid, float w_rot, float w_iso, float w_floor, float w_bg,
+                                        float *__restrict__ losses) {
+    __shared__ double r[5][128];
+    double v[5] = {0, 0, 0, 0, 0};
+    for (int i = threadIdx.x; i < nrows; i += 128)
+        for (int c = 0; c < 5; ++c) v[c] += block_sums[5 * (size_t)i + c];
+    for (int c = 0; c < 5; ++c) r[c][threadIdx.x] = v[c];
+    __syncthreads();
+    for (int s = 64; s >= 1; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int c = 0; c < 5; ++c) r[c][threadIdx.x] += r[c][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        float l0 = (float)(r[0][0] * inv_e), l1 = (float)(r[1][0] * inv_e), l2 = (float)(r[2][0] * inv_e);
+        float l3 = (float)(r[3][0] * inv_f), l4 = (float)(r[4][0] * inv_b);
+        losses[0] = l0; losses[1] = l1; losses[2] = l2; losses[3] = l3; losses[4] = l4;
+        losses[5] = w_rigid * l0 + w_rot * l1 + w_iso * l2 + w_floor * l3 + w_bg * l4;
+    }
+}
+
+extern "C" int gsd_track_losses_workspace_bytes(int32_t Gf, int32_t Gb, size_t *bytes) {
+    if (Gf < 0 || Gb < 0 || !bytes) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
+    size_t rows = (size_t)(Gf + 127) / 128 + (size_t)(Gb + 127) / 128 + 1;
+    *bytes = gsd_align_up(rows * 5 * 4);
+    return GSD_OK;
+}
+
+extern "C" int gsd_track_losses_fwd_bwd(const GsdTrackLosses *t, void *stream) {
+    if (!t || t->G < 0 || t->Gf < 0 || t->Gb < 0 || t->K < 0 || !t->ws || !t->losses || !t->grad_means3D || !t->grad_rotations) {
+        gsd_set_error("invalid arguments");
+        return GSD_ERR_INVALID;
+    }
+    if (t->Gf > 0 && (!t->means3D || !t->rotations || !t->prev_inv_rot || (t->K > 0 && (!t->neighbor_indices || !t->neighbor_weight ||
+        !t->neighbor_dist || !t->prev_offset || !t->in_ptr || !t->in_edge)))) {
+        gsd_set_error("null foreground input");
+        return GSD_ERR_INVALID;
+    }
+    if (t->Gb > 0 && (!t->bg_index || !t->init_bg_pts || !t->init_bg_rot)) { gsd_set_error("null background input"); return GSD_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    GSD_CUDA_CHECK(cudaMemsetAsync(t->grad_means3D, 0, (size_t)t->G * 3 * 4, st));
+    GSD_CUDA_CHECK(cudaMemsetAsync(t->grad_rotations, 0, (size_t)t->G * 4 * 4, st));
+    TrackArgs a;
+    a.Gf = t->Gf; a.K = t->K; a.Gb = t->Gb;
+    a.x = t->means3D; a.q = t->rotations; a.fg_index = t->fg_index; a.prev_inv = t->prev_inv_rot;
+    a.nbr = t->neighbor_indices; a.nbr_w = t->neighbor_weight; a.nbr_d = t->neighbor_dist; a.prev_off = t->prev_offset;
+    a.in_ptr = t->in_ptr; a.in_edge = t->in_edge;
+    a.bg_index = t->bg_index; a.bg_x0 = t->init_bg_pts; a.bg_q0 = t->init_bg_rot;
+    const double ne = (double)t->Gf * (double)(t->K > 0 ? t->K : 1);
+    a.c_rigid = t->Gf > 0 ? (float)(t->w_rigid / ne) : 0.f;
+    a.c_rot = t->Gf > 0 ? (float)(t->w_rot / ne) : 0.f;
+    a.c_iso = t->Gf > 0 ? (float)(t->w_iso / ne) : 0.f;
+    a.c_floor = t->Gf > 0 ? t->w_floor / (float)t->Gf : 0.f;
+    a.c_bg = t->Gb > 0 ? t->w_bg / (float)t->Gb : 0.f;
+    a.grad_x = t->grad_means3D; a.grad_q = t->grad_rotations;
+    a.block_sums = (float *)t->ws;
+    const int fgb = (t->Gf + 127) / 128, bgb = (t->Gb + 127) / 128;
+    if (fgb > 0) { gsd_track_fg_kernel<<<fgb, 128, 0, st>>>(a); GSD_LAUNCH_CHECK(); }
+    if (bgb > 0) { gsd_track_bg_kernel<<<bgb, 128, 0, st>>>(a, fgb); GSD_LAUNCH_CHECK(); }
+    gsd_track_finish_kernel<<<1, 128, 0, st>>>(fgb + bgb, a.block_sums, t->Gf > 0 ? (float)(1.0 / ne) : 0.f,
+                                               t->Gf > 0 ? 1.f / t->Gf : 0.f, t->Gb > 0 ? 1.f / t->Gb : 0.f, t->w_rigid,
+                                               t->w_rot, t->w_iso, t->w_floor, t->w_bg, t->losses);
+    GSD_LAUNCH_CHECK();
+    return GSD_OK;
+}

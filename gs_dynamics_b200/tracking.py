@@ -1,0 +1,451 @@
+"""Host side of the tracking iteration (path A): the reference's tracking/helpers.py + train_utils.py surface, backed
+by the sm_100a kernels of libgsd_b200.so.
+
+Mirrors (same names, argument meaning, results):
+  setup_camera, params2rendervar            /root/reference/src/tracking/helpers.py:10-45
+  l1_loss_v1, calc_ssim, calc_psnr          helpers.py:71-72, external.py:45-47,101-135
+  get_loss                                  /root/reference/src/tracking/train_utils.py:167-246
+  initialize_optimizer                      train_utils.py:152-164   (-> FusedAdam, one launch for all groups)
+  initialize_per_timestep                   train_utils.py:331-351   (in place: storage stays valid for CUDA graphs)
+  initialize_post_first_timestep            train_utils.py:354-374
+Differences by design: no boolean-mask indexing / host syncs inside get_loss (index lists are built once), the RGB and
+seg renders of one iteration run as ONE 6-channel rasterizer pass when the colour render's means2D gradient is not
+needed (t > 0), and `TrackingStep` captures loss + backward + Adam in a CUDA graph per camera.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import rasterizer as R
+from .rasterizer import GaussianRasterizationSettings as Camera
+from .rasterizer import GaussianRasterizer as Renderer
+
+FLOOR_WEIGHT = 2.0  # hard-coded in the reference (train_utils.py:237)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ----------------------------------------------------------------------------------------------------
+# cameras / activations
+# ----------------------------------------------------------------------------------------------------
+def setup_camera(w, h, k, w2c, near=0.01, far=100, bg=(0, 0, 0), device="cuda"):
+    fx, fy, cx, cy = k[0][0], k[1][1], k[0][2], k[1][2]
+    w2c = torch.tensor(np.asarray(w2c), dtype=torch.float32, device=device)
+    cam_center = torch.inverse(w2c)[:3, 3]
+    w2c = w2c.unsqueeze(0).transpose(1, 2)
+    opengl_proj = torch.tensor([[2 * fx / w, 0.0, -(w - 2 * cx) / w, 0.0],
+                                [0.0, 2 * fy / h, -(h - 2 * cy) / h, 0.0],
+                                [0.0, 0.0, far / (far - near), -(far * near) / (far - near)],
+                                [0.0, 0.0, 1.0, 0.0]], dtype=torch.float32, device=device).unsqueeze(0).transpose(1, 2)
+    full_proj = w2c.bmm(opengl_proj)
+    return Camera(image_height=h, image_width=w, tanfovx=w / (2 * fx), tanfovy=h / (2 * fy),
+                  bg=torch.tensor(bg, dtype=torch.float32, device=device), scale_modifier=1.0,
+                  viewmatrix=w2c.contiguous(), projmatrix=full_proj.contiguous(), sh_degree=0, campos=cam_center,
+                  prefiltered=False)
+
+
+def params2rendervar(params):
+    return {
+        'means3D': params['means3D'],
+        'colors_precomp': params['rgb_colors'],
+        'rotations': torch.nn.functional.normalize(params['unnorm_rotations']),
+        'opacities': torch.sigmoid(params['logit_opacities']),
+        'scales': torch.exp(params['log_scales']),
+        'means2D': torch.zeros_like(params['means3D'], requires_grad=True) + 0,
+    }
+
+
+# ----------------------------------------------------------------------------------------------------
+# photometric loss  (fused L1 + SSIM)
+# ----------------------------------------------------------------------------------------------------
+class _Photometric(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, w_l1, w_ssim):
+        x = R._f32c(x, "x")
+        y = R._f32c(y, "y")
+        if x.shape != y.shape or x.dim() != 3:
+            raise ValueError("photometric loss expects two [C,H,W] tensors")
+        Cc, H, W = x.shape
+        lib = _lib.lib()
+        nbytes = C.c_size_t()
+        _lib.check(lib.gsd_photometric_workspace_bytes(Cc, H, W, C.byref(nbytes)), "gsd_photometric_workspace_bytes")
+        with torch.cuda.device(x.device):
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
+            out = torch.empty(3, dtype=torch.float32, device=x.device)
+            _lib.check(lib.gsd_photometric_forward(Cc, H, W, x.data_ptr(), y.data_ptr(), w_l1, w_ssim, ws.data_ptr(),
+                                                   out.data_ptr(), _stream()), "gsd_photometric_forward")
+        ctx.save_for_backward(x, y, ws)
+        ctx.w = (w_l1, w_ssim)
+        ctx.mark_non_differentiable(out)
+        return out[0], out
+
+    @staticmethod
+    def backward(ctx, g_loss, g_out):
+        x, y, ws = ctx.saved_tensors
+        Cc, H, W = x.shape
+        g_loss = g_loss.contiguous().float()
+        grad = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().gsd_photometric_backward(Cc, H, W, x.data_ptr(), y.data_ptr(), ctx.w[0], ctx.w[1],
+                                                           ws.data_ptr(), g_loss.data_ptr(), 1.0, grad.data_ptr(),
+                                                           _stream()), "gsd_photometric_backward")
+        return grad, None, None, None
+
+
+def photometric_loss(x, y, w_l1=0.8, w_ssim=0.2, return_parts=False):
+    """0.8*l1_loss_v1(x,y) + 0.2*(1-calc_ssim(x,y)) of train_utils.py:185,195 in two kernels."""
+    loss, parts = _Photometric.apply(x, y, float(w_l1), float(w_ssim))
+    return (loss, parts) if return_parts else loss
+
+
+def l1_loss_v1(x, y):
+    return photometric_loss(x, y, 1.0, 0.0)
+
+
+def calc_ssim(img1, img2):
+    return photometric_loss(img1, img2, 0.0, 1.0, return_parts=True)[1][2]
+
+
+def calc_psnr(img1, img2):
+    mse = ((img1 - img2) ** 2).view(img1.shape[0], -1).mean(1, keepdim=True)
+    return 20 * torch.log10(1.0 / torch.sqrt(mse))
+
+
+# ----------------------------------------------------------------------------------------------------
+# physical priors (rigid / rot / iso / floor / bg)
+# ----------------------------------------------------------------------------------------------------
+class _TrackPriors(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, rotations, variables, weights):
+        lib = _lib.lib()
+        x = R._f32c(means3D, "means3D")
+        q = R._f32c(rotations, "rotations")
+        G = x.shape[0]
+        v = variables
+        t = _lib.GsdTrackLosses()
+        fg, bg = v.get("fg_index"), v.get("bg_index")
+        Gf = int(v["prev_inv_rot_fg"].shape[0])
+        K = int(v["neighbor_indices_i32"].shape[1]) if Gf > 0 else 0
+        Gb = int(bg.shape[0]) if bg is not None else 0
+        t.G, t.Gf, t.K, t.Gb = G, Gf, K, Gb
+        ptr = lambda tt: tt.data_ptr() if tt is not None and tt.numel() > 0 else None
+        t.means3D, t.rotations = x.data_ptr(), q.data_ptr()
+        t.fg_index = ptr(fg)
+        t.prev_inv_rot = ptr(v["prev_inv_rot_fg"])
+        t.neighbor_indices, t.neighbor_weight = ptr(v["neighbor_indices_i32"]), ptr(v["neighbor_weight"])
+        t.neighbor_dist, t.prev_offset = ptr(v["neighbor_dist"]), ptr(v["prev_offset"])
+        t.in_ptr, t.in_edge = ptr(v["in_ptr"]), ptr(v["in_edge"])
+        t.bg_index, t.init_bg_pts, t.init_bg_rot = ptr(bg), ptr(v.get("init_bg_pts")), ptr(v.get("init_bg_rot"))
+        t.w_rigid, t.w_rot, t.w_iso, t.w_floor, t.w_bg = [float(w) for w in weights]
+        nbytes = C.c_size_t()
+        _lib.check(lib.gsd_track_losses_workspace_bytes(Gf, Gb, C.byref(nbytes)), "gsd_track_losses_workspace_bytes")
+        with torch.cuda.device(x.device):
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
+            losses = torch.empty(6, dtype=torch.float32, device=x.device)
+            gx = torch.empty_like(x)
+            gq = torch.empty_like(q)
+            t.ws, t.losses, t.grad_means3D, t.grad_rotations = ws.data_ptr(), losses.data_ptr(), gx.data_ptr(), gq.data_ptr()
+            _lib.check(lib.gsd_track_losses_fwd_bwd(C.byref(t), _stream()), "gsd_track_losses_fwd_bwd")
+        ctx.save_for_backward(gx, gq)
+        ctx.mark_non_differentiable(losses)
+        return losses[5], losses
+
+    @staticmethod
+    def backward(ctx, g_total, g_losses):
+        gx, gq = ctx.saved_tensors
+        return gx * g_total, gq * g_total, None, None
+
+
+def track_prior_losses(means3D, rotations, variables, weight_rigid, weight_rot, weight_iso, weight_bg,
+                       weight_floor=FLOOR_WEIGHT):
+    """Returns (weighted total, [rigid, rot, iso, floor, bg, total]) — train_utils.py:198-240."""
+    return _TrackPriors.apply(means3D, rotations, variables, (weight_rigid, weight_rot, weight_iso, weight_floor, weight_bg))
+
+
+# ----------------------------------------------------------------------------------------------------
+# fused two-set rasterization (RGB + seg in one pass)
+# ----------------------------------------------------------------------------------------------------
+class _RasterizeTwoSets(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, opacities, colors0, colors1, scales, rotations, settings, bg1, capacity):
+        color, radii, depth, state = R.raster_forward(settings, means3D, opacities, colors0, scales, rotations,
+                                                       colors1=colors1, bg1=bg1, capacity=capacity)
+        ctx.state = state
+        ctx.opac_shape = opacities.shape
+        ctx.need_m2d = means2D is not None and means2D.requires_grad
+        ctx.mark_non_differentiable(radii, depth)
+        ctx.status = state.status
+        return color, radii, depth
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_depth):
+        g = R.raster_backward(ctx.state, grad_color, need_means2D=ctx.need_m2d)
+        ctx.state = None
+        return (g["means3D"], g["means2D"], g["opacities"].reshape(ctx.opac_shape), g["colors0"], g["colors1"], g["scales"],
+                g["rotations"], None, None, None)
+
+
+def render_two_sets(settings, rendervar, colors1, bg1=None, capacity=None):
+    """One 6-channel pass: channels 0-2 use rendervar['colors_precomp'], 3-5 use colors1 (same geometry)."""
+    return _RasterizeTwoSets.apply(rendervar['means3D'], rendervar.get('means2D'), rendervar['opacities'],
+                                   rendervar['colors_precomp'], colors1, rendervar['scales'], rendervar['rotations'],
+                                   settings, bg1, capacity)
+
+
+# ----------------------------------------------------------------------------------------------------
+# get_loss
+# ----------------------------------------------------------------------------------------------------
+def update_seen(radius, variables):
+    G = radius.shape[0]
+    seen = torch.empty(G, dtype=torch.uint8, device=radius.device)
+    with torch.cuda.device(radius.device):
+        _lib.check(_lib.lib().gsd_track_update_radii(G, radius.data_ptr(), variables['max_2D_radius'].data_ptr(),
+                                                     seen.data_ptr(), _stream()), "gsd_track_update_radii")
+    variables['seen'] = seen.bool()
+    return variables
+
+
+def get_loss(params, curr_data, variables, is_initial_timestep, weight_soft_col_cons=0.01, weight_im=50.0,
+             weight_seg=200.0, weight_rigid=200.0, weight_bg=200.0, weight_iso=1000.0, weight_rot=4.0, fused=None,
+             capacity=None):
+    """Same contract as the reference's get_loss (train_utils.py:167-246): returns (loss, variables) and updates
+    variables['means2D' | 'max_2D_radius' | 'seen'].  `fused` (default: t > 0) renders RGB+seg in one pass; in that mode
+    variables['means2D'].grad holds the gradient of BOTH renders (only the t = 0 densifier reads it, so t = 0 defaults to
+    the reference's two separate passes)."""
+    losses = {}
+    if fused is None:
+        fused = not is_initial_timestep
+    rendervar = params2rendervar(params)
+    rendervar['means2D'].retain_grad()
+    curr_id = curr_data['id']
+    cam = curr_data['cam']
+    if fused:
+        out, radius, _ = render_two_sets(cam, rendervar, params['seg_colors'], capacity=capacity)
+        im, seg = out[:3], out[3:]
+    else:
+        im, radius, _ = Renderer(raster_settings=cam)(**rendervar)
+    im = torch.exp(params['cam_m'][curr_id])[:, None, None] * im + params['cam_c'][curr_id][:, None, None]
+    losses['im'] = photometric_loss(im, curr_data['im'])
+    variables['means2D'] = rendervar['means2D']
+    if not fused:
+        segrendervar = params2rendervar(params)
+        segrendervar['colors_precomp'] = params['seg_colors']
+        seg, _, _ = Renderer(raster_settings=cam)(**segrendervar)
+    losses['seg'] = photometric_loss(seg, curr_data['seg'])
+    loss = weight_im * losses['im'] + weight_seg * losses['seg']
+    if not is_initial_timestep:
+        prior, parts = track_prior_losses(rendervar['means3D'], rendervar['rotations'], variables, weight_rigid, weight_rot,
+                                          weight_iso, weight_bg)
+        variables['prior_losses'] = parts  # rigid, rot, iso, floor, bg, weighted total
+        loss = loss + prior  # soft_col_cons is identically 0.0 in the reference (train_utils.py:230-232)
+    variables = update_seen(radius, variables)
+    return loss, variables
+
+
+# ----------------------------------------------------------------------------------------------------
+# optimiser
+# ----------------------------------------------------------------------------------------------------
+class FusedAdam:
+    """torch.optim.Adam(param_groups, lr=0.0, eps=1e-15) of initialize_optimizer (train_utils.py:152-164) as one kernel
+    launch over every group.  Exposes param_groups / state like torch optimizers so the reference's per-timestep state
+    surgery translates directly; step counters live on the device."""
+
+    def __init__(self, param_groups, lr=0.0, betas=(0.9, 0.999), eps=1e-15):
+        self.param_groups = []
+        for g in param_groups:
+            g = dict(g)
+            g.setdefault('lr', lr)
+            self.param_groups.append(g)
+        self.betas, self.eps = betas, eps
+        self.state = {}
+        for g in self.param_groups:
+            for p in g['params']:
+                self.state[p] = dict(step=torch.zeros((), dtype=torch.float32, device=p.device),
+                                     exp_avg=torch.zeros_like(p), exp_avg_sq=torch.zeros_like(p))
+        if sum(len(g['params']) for g in self.param_groups) > _lib.GSD_ADAM_MAX_TENSORS:
+            raise ValueError("too many tensors for one fused launch")
+
+    def zero_grad(self, set_to_none=True):
+        for g in self.param_groups:
+            for p in g['params']:
+                if set_to_none:
+                    p.grad = None
+                elif p.grad is not None:
+                    p.grad.zero_()
+
+    @torch.no_grad()
+    def step(self):
+        a = _lib.GsdAdam()
+        a.beta1, a.beta2, a.eps = self.betas[0], self.betas[1], self.eps
+        n = 0
+        dev = None
+        for g in self.param_groups:
+            for p in g['params']:
+                if p.grad is None or not p.requires_grad:
+                    continue
+                if g['lr'] == 0.0:
+                    # lr 0: parameter frozen; moments would be updated by torch but never used again unless lr changes.
+                    # Keep exact torch semantics (moments advance) so a later lr change behaves identically.
+                    pass
+                st = self.state[p]
+                grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                a.param[n], a.grad[n] = p.data_ptr(), grad.data_ptr()
+                a.exp_avg[n], a.exp_avg_sq[n], a.step[n] = st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(), st['step'].data_ptr()
+                a.lr[n], a.numel[n] = float(g['lr']), p.numel()
+                dev = p.device
+                n += 1
+        a.n_tensors = n
+        if n:
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().gsd_adam_step(C.byref(a), _stream()), "gsd_adam_step")
+
+
+def initialize_optimizer(params, variables):
+    lrs = {'means3D': 0.00016 * variables['scene_radius'], 'rgb_colors': 0.0, 'seg_colors': 0.0, 'unnorm_rotations': 0.001,
+           'logit_opacities': 0.05, 'log_scales': 0.001, 'cam_m': 1e-4, 'cam_c': 1e-4}
+    param_groups = [{'params': [v], 'name': k, 'lr': lrs[k]} for k, v in params.items()]
+    return FusedAdam(param_groups, lr=0.0, eps=1e-15)
+
+
+# ----------------------------------------------------------------------------------------------------
+# per-timestep state
+# ----------------------------------------------------------------------------------------------------
+def knn(pts, num_knn):
+    """o3d_knn of the reference (helpers.py:97-115): squared distances + indices of the num_knn nearest OTHER points,
+    computed on the host in float64 (the reference uses Open3D's KD-tree on the CPU, once per episode)."""
+    from scipy.spatial import cKDTree
+    pts = np.ascontiguousarray(pts, np.float64)
+    d, i = cKDTree(pts).query(pts, k=num_knn + 1)
+    return (d[:, 1:] ** 2), i[:, 1:]
+
+
+def build_in_edges(neighbor_indices):
+    """Transposed adjacency of the static kNN graph: for every point the ids (i*K+k) of the edges that name it."""
+    Gf, K = neighbor_indices.shape
+    flat = neighbor_indices.reshape(-1).long()
+    order = torch.argsort(flat, stable=True)
+    counts = torch.bincount(flat, minlength=Gf)
+    in_ptr = torch.zeros(Gf + 1, dtype=torch.int32, device=flat.device)
+    in_ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    return in_ptr.contiguous(), order.to(torch.int32).contiguous()
+
+
+def initialize_post_first_timestep(params, variables, optimizer, num_knn=20):
+    is_fg = params['seg_colors'][:, 0] > 0.5
+    fg_index = torch.nonzero(is_fg).reshape(-1)
+    bg_index = torch.nonzero(~is_fg).reshape(-1)
+    init_fg_pts = params['means3D'][fg_index]
+    neighbor_sq_dist, neighbor_indices = knn(init_fg_pts.detach().cpu().numpy(), num_knn)
+    dev = params['means3D'].device
+    variables["neighbor_indices"] = torch.tensor(neighbor_indices, device=dev).long().contiguous()
+    variables["neighbor_indices_i32"] = variables["neighbor_indices"].to(torch.int32).contiguous()
+    variables["neighbor_weight"] = torch.tensor(np.exp(-2000 * neighbor_sq_dist), device=dev).float().contiguous()
+    variables["neighbor_dist"] = torch.tensor(np.sqrt(neighbor_sq_dist), device=dev).float().contiguous()
+    variables["in_ptr"], variables["in_edge"] = build_in_edges(variables["neighbor_indices_i32"])
+    all_fg = bool(fg_index.numel() == is_fg.numel())
+    variables["fg_index"] = None if all_fg else fg_index.to(torch.int32).contiguous()
+    variables["bg_index"] = bg_index.to(torch.int32).contiguous()
+    variables["init_bg_pts"] = params['means3D'][bg_index].detach().clone()
+    variables["init_bg_rot"] = torch.nn.functional.normalize(params['unnorm_rotations'][bg_index]).detach().clone()
+    variables["prev_pts"] = params['means3D'].detach().clone()
+    variables["prev_rot"] = torch.nn.functional.normalize(params['unnorm_rotations']).detach().clone()
+    for group in optimizer.param_groups:
+        if group["name"] in ['logit_opacities', 'log_scales', 'cam_m', 'cam_c', 'rgb_colors']:
+            group['lr'] = 0.0
+    return variables
+
+
+@torch.no_grad()
+def initialize_per_timestep(params, variables, optimizer):
+    """Constant-velocity warm start + Adam moment reset (train_utils.py:331-351), done IN PLACE."""
+    pts = params['means3D']
+    rot = torch.nn.functional.normalize(params['unnorm_rotations'])
+    new_pts = pts + (pts - variables["prev_pts"])
+    new_rot = torch.nn.functional.normalize(rot + (rot - variables["prev_rot"]))
+    fg = variables.get("fg_index")
+    rot_fg = rot if fg is None else rot[fg.long()]
+    pts_fg = pts if fg is None else pts[fg.long()]
+    prev_inv = rot_fg.clone()
+    prev_inv[:, 1:] = -1 * prev_inv[:, 1:]
+    prev_offset = pts_fg[variables["neighbor_indices"]] - pts_fg[:, None]
+
+    def assign(key, value):
+        if key in variables and isinstance(variables[key], torch.Tensor) and variables[key].shape == value.shape:
+            variables[key].copy_(value)
+        else:
+            variables[key] = value.detach().clone().contiguous()
+    assign('prev_inv_rot_fg', prev_inv)
+    assign('prev_offset', prev_offset)
+    assign('prev_col', params['rgb_colors'])
+    assign('prev_pts', pts)
+    assign('prev_rot', rot)
+    for k, v in (('means3D', new_pts), ('unnorm_rotations', new_rot)):
+        p = params[k]
+        p.data.copy_(v)
+        st = optimizer.state[p]
+        st['exp_avg'].zero_()
+        st['exp_avg_sq'].zero_()
+    return params, variables
+
+
+# ----------------------------------------------------------------------------------------------------
+# CUDA-graph fast path: one replay = get_loss + backward + Adam for one camera
+# ----------------------------------------------------------------------------------------------------
+class TrackingStep:
+    """Captures the steady-state (t > 0) iteration of train_gs.py:25-39 per camera. Parameters, Adam state, neighbour
+    tables and targets are static device tensors; `step(cam_id)` replays the graph and returns the device loss scalar."""
+
+    def __init__(self, params, variables, optimizer, dataset, is_initial_timestep=False, loss_kwargs=None,
+                 capacity_margin=1.5, use_graph=True):
+        self.params, self.variables, self.optimizer, self.dataset = params, variables, optimizer, dataset
+        self.is_initial = is_initial_timestep
+        self.kw = dict(loss_kwargs or {})
+        self.margin = capacity_margin
+        self.use_graph = use_graph
+        self.graphs, self.losses, self.capacity, self.status = {}, {}, {}, {}
+
+    def _iteration(self, data, capacity):
+        loss, self.variables = get_loss(self.params, data, self.variables, self.is_initial, capacity=capacity, **self.kw)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def _probe_capacity(self, data):
+        rv = params2rendervar(self.params)
+        with torch.no_grad():
+            _, _, _, st = R.raster_forward(data['cam'], rv['means3D'], rv['opacities'], rv['colors_precomp'], rv['scales'],
+                                           rv['rotations'])
+        return max(1024, int(int(st.status[0].item()) * self.margin))
+
+    def prepare(self, cam_ids=None):
+        """Warm-up (eager, on a side stream) and capture. Warm-up iterations are real optimisation steps."""
+        cam_ids = list(range(len(self.dataset))) if cam_ids is None else list(cam_ids)
+        for c in cam_ids:
+            self.capacity[c] = self._probe_capacity(self.dataset[c])
+        if not self.use_graph:
+            return
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for c in cam_ids:
+                self.optimizer.zero_grad(set_to_none=True)
+                self._iteration(self.dataset[c], self.capacity[c])
+        torch.cuda.current_stream().wait_stream(s)
+        for c in cam_ids:
+            g = torch.cuda.CUDAGraph()
+            self.optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(g):
+                self.losses[c] = self._iteration(self.dataset[c], self.capacity[c])
+            self.graphs[c] = g
+
+    def step(self, cam_id):
+        if self.use_graph:
+            self.graphs[cam_id].replay()
+            return self.losses[cam_id]
+        self.optimizer.zero_grad(set_to_none=True)
+        return self._iteration(self.dataset[cam_id], self.capacity.get(cam_id))

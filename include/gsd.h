@@ -111,6 +111,68 @@ int gsd_raster_backward(const GsdRasterBwd *a, void *stream);
 /* replaces _C.mark_visible: visible[g] = (view-space z > 0.2) */
 int gsd_raster_mark_visible(int32_t G, const float *means3D, const float *viewmatrix, uint8_t *visible, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Path A.2 — per-iteration tracking losses (replace the eager PyTorch graph of get_loss,
+ * /root/reference/src/tracking/train_utils.py:167-246)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* loss = w_l1*mean|x-y| + w_ssim*(1 - mean SSIM_11x11(x,y))   (train_utils.py:185,195; external.py:101-135)
+ * x, y: [C,H,W]. ws keeps three partial-derivative maps between forward and backward.
+ * loss_out[3] = {loss, mean|x-y|, mean SSIM}. */
+int gsd_photometric_workspace_bytes(int32_t C, int32_t H, int32_t W, size_t *bytes);
+int gsd_photometric_forward(int32_t C, int32_t H, int32_t W, const float *x, const float *y, float w_l1, float w_ssim,
+                            void *ws, float *loss_out, void *stream);
+/* grad_x = (gscale_ptr ? *gscale_ptr : 1) * gscale_mul * dloss/dx */
+int gsd_photometric_backward(int32_t C, int32_t H, int32_t W, const float *x, const float *y, float w_l1, float w_ssim,
+                             const void *ws, const float *gscale_ptr, float gscale_mul, float *grad_x, void *stream);
+
+/* rigid / rot / iso / floor / bg priors, forward + gradient in one call (train_utils.py:198-240).
+ * The foreground set is fg_index (NULL = all G points, in order); neighbour tables index into that set.
+ * in_ptr/in_edge: transposed adjacency (CSR over the neighbour id) of the static kNN graph, edge id = i*K+k. */
+typedef struct {
+    int32_t G, Gf, K, Gb;
+    const float *means3D;           /* [G,3] */
+    const float *rotations;         /* [G,4] normalised (what params2rendervar feeds the rasterizer) */
+    const int32_t *fg_index;        /* [Gf] or NULL */
+    const float *prev_inv_rot;      /* [Gf,4]  variables["prev_inv_rot_fg"] */
+    const int32_t *neighbor_indices;/* [Gf,K]  variables["neighbor_indices"] (int32) */
+    const float *neighbor_weight;   /* [Gf,K] */
+    const float *neighbor_dist;     /* [Gf,K] */
+    const float *prev_offset;       /* [Gf,K,3] */
+    const int32_t *in_ptr;          /* [Gf+1] */
+    const int32_t *in_edge;         /* [Gf*K] */
+    const int32_t *bg_index;        /* [Gb] */
+    const float *init_bg_pts;       /* [Gb,3] */
+    const float *init_bg_rot;       /* [Gb,4] */
+    float w_rigid, w_rot, w_iso, w_floor, w_bg; /* loss weights (train_utils.py:236-240) */
+    void *ws;                       /* gsd_track_losses_workspace_bytes() */
+    float *losses;                  /* [6] rigid, rot, iso, floor, bg (unweighted means), weighted total */
+    float *grad_means3D;            /* [G,3] d(weighted total)/d means3D, fully overwritten */
+    float *grad_rotations;          /* [G,4] d(weighted total)/d rotations, fully overwritten */
+} GsdTrackLosses;
+int gsd_track_losses_workspace_bytes(int32_t Gf, int32_t Gb, size_t *bytes);
+int gsd_track_losses_fwd_bwd(const GsdTrackLosses *t, void *stream);
+
+/* Multi-tensor Adam, one launch for every parameter group (torch.optim.Adam semantics, no weight decay /
+ * amsgrad; eps inside the bias-corrected denominator) — initialize_optimizer, train_utils.py:152-164.
+ * step[i] is a device-resident float counter per group, incremented by the kernel (CUDA-graph friendly). */
+#define GSD_ADAM_MAX_TENSORS 16
+typedef struct {
+    int32_t n_tensors;
+    float beta1, beta2, eps;
+    float *param[GSD_ADAM_MAX_TENSORS];
+    const float *grad[GSD_ADAM_MAX_TENSORS];
+    float *exp_avg[GSD_ADAM_MAX_TENSORS];
+    float *exp_avg_sq[GSD_ADAM_MAX_TENSORS];
+    float *step[GSD_ADAM_MAX_TENSORS];
+    float lr[GSD_ADAM_MAX_TENSORS];
+    int64_t numel[GSD_ADAM_MAX_TENSORS];
+} GsdAdam;
+int gsd_adam_step(const GsdAdam *a, void *stream);
+
+/* bookkeeping of get_loss (train_utils.py:243-245): seen = radii > 0; max_2D_radius = max(radii, max_2D_radius)[seen] */
+int gsd_track_update_radii(int32_t G, const int32_t *radii, float *max_2D_radius, uint8_t *seen, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

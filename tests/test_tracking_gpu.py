@@ -1,0 +1,205 @@
+"""GPU parity tests of the tracking-iteration kernels (photometric, priors, Adam, get_loss) through the C ABI.
+
+Tolerances: photometric loss 1e-5 abs, its gradient 1e-3 of max; prior losses 1e-4 rel, gradients 2e-3 of max (fp32 vs the
+float64 autograd oracle; the sqrt(.+1e-20) terms amplify rounding near zero residuals); Adam 1e-6 rel vs torch.optim.Adam.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tracking_oracle as T
+from tests.helpers import make_camera, make_scene, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "tracking_golden.npz"))
+
+
+def _variables_from_case(c, dev="cuda"):
+    from gs_dynamics_b200 import tracking as TR
+    is_fg = c["is_fg"]
+    v = {}
+    v["neighbor_indices"] = c["neighbor_indices"].to(dev)
+    v["neighbor_indices_i32"] = c["neighbor_indices"].to(torch.int32).to(dev).contiguous()
+    v["neighbor_weight"] = c["neighbor_weight"].float().to(dev)
+    v["neighbor_dist"] = c["neighbor_dist"].float().to(dev)
+    v["prev_offset"] = c["prev_offset"].float().to(dev)
+    v["prev_inv_rot_fg"] = c["prev_inv_rot_fg"].float().to(dev)
+    v["in_ptr"], v["in_edge"] = TR.build_in_edges(v["neighbor_indices_i32"])
+    v["fg_index"] = None if bool(is_fg.all()) else torch.nonzero(is_fg).reshape(-1).to(torch.int32).to(dev)
+    v["bg_index"] = torch.nonzero(~is_fg).reshape(-1).to(torch.int32).to(dev)
+    v["init_bg_pts"] = c["init_bg_pts"].float().to(dev)
+    v["init_bg_rot"] = c["init_bg_rot"].float().to(dev)
+    return v
+
+
+def test_photometric_golden_fixture():
+    from gs_dynamics_b200 import tracking as TR
+    x = torch.tensor(GOLD["ph_x"]).cuda().requires_grad_(True)
+    y = torch.tensor(GOLD["ph_y"]).cuda()
+    loss, parts = TR.photometric_loss(x, y, return_parts=True)
+    loss.backward()
+    assert abs(loss.item() - float(GOLD["ph_loss"])) < 1e-5
+    assert abs(parts[1].item() - float(GOLD["ph_l1"])) < 1e-5 and abs(parts[2].item() - float(GOLD["ph_ssim"])) < 1e-5
+    assert rel_err(x.grad.cpu(), GOLD["ph_grad"]) < 1e-3
+
+
+@pytest.mark.parametrize("C,H,W", [(3, 480, 640), (3, 33, 47), (1, 16, 16), (6, 100, 70)])
+def test_photometric_vs_oracle(C, H, W):
+    from gs_dynamics_b200 import tracking as TR
+    g = torch.Generator().manual_seed(C * H)
+    x = torch.rand(C, H, W, generator=g)
+    y = (x + 0.1 * torch.randn(C, H, W, generator=g)).clamp(0, 1)
+    xd = x.double().requires_grad_(True)
+    lo = T.photometric(xd, y.double())
+    lo.backward()
+    xc = x.cuda().requires_grad_(True)
+    loss = TR.photometric_loss(xc, y.cuda())
+    (3.0 * loss).backward()  # non-unit upstream gradient
+    assert abs(loss.item() - lo.item()) < 1e-5
+    assert rel_err(xc.grad.cpu(), 3.0 * xd.grad) < 1e-3
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_priors_golden_fixture(tag):
+    from gs_dynamics_b200 import tracking as TR
+    G, K, seed, fb = GOLD[f"pr_{tag}_cfg"]
+    c = T.make_prior_case(int(G), int(K), int(seed), float(fb))
+    v = _variables_from_case(c)
+    x = c["means3D"].cuda().requires_grad_(True)
+    q = c["rotations"].cuda().requires_grad_(True)
+    total, parts = TR.track_prior_losses(x, q, v, 200.0, 4.0, 1000.0, 200.0)
+    total.backward()
+    for i, k in enumerate(("rigid", "rot", "iso", "floor", "bg")):
+        ref = float(GOLD[f"pr_{tag}_{k}"])
+        assert abs(parts[i].item() - ref) <= 1e-4 * max(1e-3, abs(ref)), k
+    assert abs(total.item() - float(GOLD[f"pr_{tag}_total"])) <= 1e-4 * abs(float(GOLD[f"pr_{tag}_total"]))
+    assert rel_err(x.grad.cpu(), GOLD[f"pr_{tag}_gx"]) < 2e-3
+    assert rel_err(q.grad.cpu(), GOLD[f"pr_{tag}_gq"]) < 2e-3
+
+
+@pytest.mark.parametrize("G,K,fb", [(5000, 20, 0.0), (3000, 20, 0.3), (257, 3, 0.5)])
+def test_priors_vs_float64_oracle(G, K, fb):
+    from gs_dynamics_b200 import tracking as TR
+    c = T.make_prior_case(G, K, 7, fb, dtype=torch.float64)
+    x64 = c["means3D"].clone().requires_grad_(True)
+    q64 = c["rotations"].clone().requires_grad_(True)
+    L = T.prior_losses(x64, q64, c["is_fg"], c["prev_inv_rot_fg"], c["neighbor_indices"], c["neighbor_weight"],
+                       c["neighbor_dist"], c["prev_offset"], c["init_bg_pts"], c["init_bg_rot"])
+    w = dict(rigid=200.0, rot=4.0, iso=1000.0, floor=2.0, bg=200.0)
+    tot = sum(w[k] * L[k] for k in w)
+    tot.backward()
+    v = _variables_from_case(c)
+    x = c["means3D"].float().cuda().requires_grad_(True)
+    q = c["rotations"].float().cuda().requires_grad_(True)
+    total, parts = TR.track_prior_losses(x, q, v, 200.0, 4.0, 1000.0, 200.0)
+    (0.5 * total).backward()
+    for i, k in enumerate(("rigid", "rot", "iso", "floor", "bg")):
+        assert abs(parts[i].item() - L[k].item()) <= 2e-4 * max(1e-3, abs(L[k].item())), k
+    assert rel_err(x.grad.cpu(), 0.5 * x64.grad) < 2e-3
+    assert rel_err(q.grad.cpu(), 0.5 * q64.grad) < 2e-3
+
+
+def test_fused_adam_matches_torch_adam():
+    from gs_dynamics_b200 import tracking as TR
+    g = torch.Generator().manual_seed(0)
+    shapes = [(1000, 3), (1000, 4), (1000, 1), (50, 3), (7,)]
+    lrs = [1.6e-4, 1e-3, 0.05, 1e-4, 0.0]
+    p_ref = [torch.nn.Parameter(torch.randn(*s, generator=g)) for s in shapes]
+    p_gpu = [torch.nn.Parameter(p.detach().clone().cuda()) for p in p_ref]
+    opt_ref = torch.optim.Adam([{'params': [p], 'lr': lr} for p, lr in zip(p_ref, lrs)], lr=0.0, eps=1e-15)
+    opt = TR.FusedAdam([{'params': [p], 'lr': lr, 'name': str(i)} for i, (p, lr) in enumerate(zip(p_gpu, lrs))], lr=0.0, eps=1e-15)
+    for it in range(5):
+        for pr, pg in zip(p_ref, p_gpu):
+            gr = torch.randn(pr.shape, generator=g) * (10.0 ** (it - 2))
+            pr.grad = gr.clone()
+            pg.grad = gr.cuda()
+        opt_ref.step()
+        opt.step()
+    for pr, pg in zip(p_ref, p_gpu):
+        assert rel_err(pg.detach().cpu(), pr.detach()) < 1e-6
+    assert float(opt.state[p_gpu[0]]['step'].item()) == 5.0
+
+
+def _tracking_problem(G, cam_ids=(0, 1), w=160, h=120, boost=1.0, box=0.6, seed=0):
+    """Steady-state (t > 0) tracking set-up on synthetic data: scene S(G, seed) to fit, targets rendered from a slightly
+    moved copy, kNN tables from the initial points (scaled down)."""
+    from gs_dynamics_b200 import tracking as TR, scenes
+    from gs_dynamics_b200 import rasterizer as R
+    W0, H0, cams = scenes.demo_cameras()
+    sc, act = make_scene(G, seed, scale_boost=boost, box_scale=box)
+    params = {k: torch.nn.Parameter(v.cuda().contiguous()) for k, v in sc.items()}
+    params['cam_m'] = torch.nn.Parameter(torch.zeros(50, 3, device="cuda"))
+    params['cam_c'] = torch.nn.Parameter(torch.zeros(50, 3, device="cuda"))
+    params['rgb_colors'].requires_grad = False
+    variables = {'max_2D_radius': torch.zeros(G, device="cuda"), 'scene_radius': 1.0,
+                 'means2D_gradient_accum': torch.zeros(G, device="cuda"), 'denom': torch.zeros(G, device="cuda")}
+    opt = TR.initialize_optimizer(params, variables)
+    variables = TR.initialize_post_first_timestep(params, variables, opt, num_knn=8)
+    dataset = []
+    tgt = {k: v.clone() for k, v in act.items()}
+    tgt['means3D'] = tgt['means3D'] + torch.tensor([0.002, -0.001, 0.001])
+    for cid in cam_ids:
+        k, w2c = cams[cid]
+        k = k.copy(); k[0] *= w / W0; k[1] *= h / H0
+        cam = TR.setup_camera(w, h, k, w2c, near=1.0, far=100)
+        with torch.no_grad():
+            tc = {kk: vv.cuda() for kk, vv in tgt.items()}
+            im, _, _, _ = R.raster_forward(cam, tc['means3D'], tc['opacities'], tc['colors_precomp'], tc['scales'], tc['rotations'])
+            sg, _, _, _ = R.raster_forward(cam, tc['means3D'], tc['opacities'], sc['seg_colors'].cuda(), tc['scales'], tc['rotations'])
+        dataset.append({'cam': cam, 'im': im.clone(), 'seg': sg.clone(), 'id': cid})
+    params, variables = TR.initialize_per_timestep(params, variables, opt)
+    return params, variables, opt, dataset
+
+
+def test_get_loss_fused_equals_two_pass_and_oracle_composition():
+    from gs_dynamics_b200 import tracking as TR
+    params, variables, opt, dataset = _tracking_problem(3000)
+    data = dataset[0]
+    opt.zero_grad()
+    l_f, variables = TR.get_loss(params, data, variables, False, fused=True)
+    l_f.backward()
+    g_f = {k: p.grad.clone() for k, p in params.items() if p.grad is not None}
+    opt.zero_grad()
+    l_2, variables = TR.get_loss(params, data, variables, False, fused=False)
+    l_2.backward()
+    assert abs(l_f.item() - l_2.item()) <= 1e-5 * abs(l_2.item())
+    for k in g_f:
+        assert rel_err(g_f[k].cpu(), params[k].grad.cpu()) < 1e-4, k
+    # loss value against the oracle composition on the same rendered images
+    rv = TR.params2rendervar(params)
+    with torch.no_grad():
+        from gs_dynamics_b200 import rasterizer as R
+        im, radius, _, _ = R.raster_forward(data['cam'], rv['means3D'], rv['opacities'], rv['colors_precomp'], rv['scales'], rv['rotations'])
+        sg, _, _, _ = R.raster_forward(data['cam'], rv['means3D'], rv['opacities'], params['seg_colors'].detach(), rv['scales'], rv['rotations'])
+    ref = 50.0 * T.photometric(im.cpu().double(), data['im'].cpu().double()) + 200.0 * T.photometric(sg.cpu().double(), data['seg'].cpu().double())
+    is_fg = (params['seg_colors'][:, 0] > 0.5).cpu()
+    L = T.prior_losses(rv['means3D'].detach().cpu().double(), rv['rotations'].detach().cpu().double(), is_fg,
+                       variables['prev_inv_rot_fg'].cpu().double(), variables['neighbor_indices'].cpu(),
+                       variables['neighbor_weight'].cpu().double(), variables['neighbor_dist'].cpu().double(),
+                       variables['prev_offset'].cpu().double(), variables['init_bg_pts'].cpu().double(), variables['init_bg_rot'].cpu().double())
+    ref = ref + 200.0 * L['rigid'] + 4.0 * L['rot'] + 1000.0 * L['iso'] + 2.0 * L['floor'] + 200.0 * L['bg']
+    assert abs(l_2.item() - ref.item()) <= 2e-4 * abs(ref.item())
+    assert variables['seen'].dtype == torch.bool and bool((variables['max_2D_radius'] >= radius.float()).all())
+
+
+def test_tracking_step_graph_matches_eager_and_reduces_loss():
+    from gs_dynamics_b200 import tracking as TR
+    pa, va, oa, da = _tracking_problem(2000)
+    pb, vb, ob, db = _tracking_problem(2000)
+    eager = TR.TrackingStep(pa, va, oa, da, use_graph=False)
+    graph = TR.TrackingStep(pb, vb, ob, db, use_graph=True)
+    eager.prepare(); graph.prepare()
+    # the graph path spent len(dataset) warm-up iterations: replay them eagerly to align the two optimisers
+    for c in range(len(da)):
+        eager.step(c)
+    seq = [0, 1, 1, 0, 1, 0, 0, 1]
+    le = [float(eager.step(c)) for c in seq]
+    lg = [float(graph.step(c)) for c in seq]
+    np.testing.assert_allclose(lg, le, rtol=2e-4)
+    assert rel_err(pb['means3D'].detach().cpu(), pa['means3D'].detach().cpu()) < 1e-5
+    first = float(eager.step(0))
+    for _ in range(60):
+        eager.step(0)
+    assert float(eager.step(0)) < first

@@ -1,0 +1,80 @@
+"""Generates tests/golden/*.npz by IMPORTING THE REFERENCE (/root/reference/src) in the build container.
+The GPU box has no /root/reference: tests read only the committed fixtures.  Run:  python tools/make_golden.py
+
+tracking_golden.npz — outputs of the reference's own helpers (tracking/helpers.py: quat_mult, l1_loss_v1/v2,
+weighted_l2_loss_v1/v2; tracking/external.py: calc_ssim, build_rotation) composed exactly as get_loss does at
+train_utils.py:182-228, on seeded inputs built by oracle.tracking_oracle.make_prior_case.
+"""
+import os, sys, types
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+import numpy as np, torch
+
+# ---- stubs for modules the reference imports at module top but that this path never calls
+for name in ("open3d", "diff_gaussian_rasterization", "dgl", "dgl.geometry"):
+    m = types.ModuleType(name)
+    sys.modules[name] = m
+sys.modules["diff_gaussian_rasterization"].GaussianRasterizationSettings = object
+sys.modules["diff_gaussian_rasterization"].GaussianRasterizer = object
+sys.modules["dgl.geometry"].farthest_point_sampler = None
+sys.path.insert(0, os.path.join(REF, "src", "tracking"))
+import helpers as ref_h      # /root/reference/src/tracking/helpers.py
+import external as ref_e     # /root/reference/src/tracking/external.py
+
+# build_rotation hard-codes device='cuda' (external.py:28); run it on the CPU by dropping that kwarg
+_zeros = torch.zeros
+def _zeros_cpu(*a, **k):
+    k.pop("device", None)
+    return _zeros(*a, **k)
+
+def ref_build_rotation(q):
+    torch.zeros = _zeros_cpu
+    try:
+        return ref_e.build_rotation(q)
+    finally:
+        torch.zeros = _zeros
+
+from oracle import tracking_oracle as T
+
+out = {}
+# ---- photometric
+g = torch.Generator().manual_seed(0)
+x = torch.rand(3, 50, 70, generator=g).requires_grad_(True)
+y = torch.rand(3, 50, 70, generator=g)
+loss = 0.8 * ref_h.l1_loss_v1(x, y) + 0.2 * (1.0 - ref_e.calc_ssim(x, y))
+loss.backward()
+out.update(ph_x=x.detach().numpy(), ph_y=y.numpy(), ph_loss=loss.item(), ph_l1=ref_h.l1_loss_v1(x, y).item(),
+           ph_ssim=ref_e.calc_ssim(x, y).item(), ph_grad=x.grad.numpy())
+
+# ---- priors, composed as train_utils.py:200-228
+for tag, (G, K, seed, fb) in dict(a=(96, 6, 1, 0.25), b=(64, 4, 2, 0.0)).items():
+    c = T.make_prior_case(G, K, seed, fb)
+    m3 = c["means3D"].clone().requires_grad_(True)
+    rq = c["rotations"].clone().requires_grad_(True)
+    is_fg = c["is_fg"]
+    fg_pts, fg_rot = m3[is_fg], rq[is_fg]
+    rel_rot = ref_h.quat_mult(fg_rot, c["prev_inv_rot_fg"])
+    rot = ref_build_rotation(rel_rot)
+    neighbor_pts = fg_pts[c["neighbor_indices"]]
+    curr_offset = neighbor_pts - fg_pts[:, None]
+    curr_offset_in_prev_coord = (rot.transpose(2, 1)[:, None] @ curr_offset[:, :, :, None]).squeeze(-1)
+    L = {}
+    L["rigid"] = ref_h.weighted_l2_loss_v2(curr_offset_in_prev_coord, c["prev_offset"], c["neighbor_weight"])
+    L["rot"] = ref_h.weighted_l2_loss_v2(rel_rot[c["neighbor_indices"]], rel_rot[:, None], c["neighbor_weight"])
+    curr_offset_mag = torch.sqrt((curr_offset ** 2).sum(-1) + 1e-20)
+    L["iso"] = ref_h.weighted_l2_loss_v1(curr_offset_mag, c["neighbor_dist"], c["neighbor_weight"])
+    L["floor"] = torch.clamp(fg_pts[:, 1], min=0).mean()
+    if (~is_fg).any():
+        L["bg"] = ref_h.l1_loss_v2(m3[~is_fg], c["init_bg_pts"]) + ref_h.l1_loss_v2(rq[~is_fg], c["init_bg_rot"])
+    else:
+        L["bg"] = m3.sum() * 0.0
+    w = dict(rigid=200.0, rot=4.0, iso=1000.0, floor=2.0, bg=200.0)   # train_gs.py defaults + train_utils.py:237
+    total = sum(w[k] * v for k, v in L.items())
+    total.backward()
+    out.update({f"pr_{tag}_{k}": v.item() for k, v in L.items()})
+    out.update({f"pr_{tag}_total": total.item(), f"pr_{tag}_gx": m3.grad.numpy(), f"pr_{tag}_gq": rq.grad.numpy(),
+                f"pr_{tag}_cfg": np.array([G, K, seed, fb])})
+dst = os.path.join(ROOT, "tests", "golden", "tracking_golden.npz")
+np.savez_compressed(dst, **out)
+print("wrote", dst, os.path.getsize(dst), "bytes")
