@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the gs-dynamics hot path on B200 (contract: see DESIGN.md §Measurement).
+
+Workload (BASELINE.json configs[1]): steady-state tracking iteration of train_gs.py — get_loss (fused RGB+seg render,
+L1+SSIM, rigid/rot/iso/floor/bg priors) + backward + Adam — at G Gaussians on the 4 demo cameras @640x480, one random
+camera per iteration.  A "step" is one such iteration.  metric = tracking iters/sec, whole job.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--gaussians G]
+
+ours      : CUDA-graph replay of the iteration (inputs resident in HBM) -> value;  e2e: the same iteration through the public
+            API with the step's camera image+seg copied from pinned host memory and the loss read back, inside the timed region.
+reference : the reference's iteration on the host cores (oracle port: C rasterizer restatement + CPU PyTorch), bounded sample.
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+HBM_FALLBACK_GBS = 6650.0
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------------------------------
+def build_gpu_problem(G, seed, device):
+    from gs_dynamics_b200 import tracking as TR, workloads, rasterizer as R
+    prob = workloads.tracking_problem(G, seed)
+    params = {k: torch.nn.Parameter(v.to(device).contiguous()) for k, v in prob["params"].items()}
+    params["rgb_colors"].requires_grad = False
+    v = {k: (t.to(device).contiguous() if isinstance(t, torch.Tensor) else t) for k, t in prob["variables"].items()}
+    v["neighbor_indices_i32"] = v["neighbor_indices"].to(torch.int32).contiguous()
+    v["in_ptr"], v["in_edge"] = TR.build_in_edges(v["neighbor_indices_i32"])
+    v["fg_index"] = None
+    v["bg_index"] = torch.zeros(0, dtype=torch.int32, device=device)
+    opt = TR.initialize_optimizer(params, v)
+    for g in opt.param_groups:  # steady state: lrs frozen after t = 0 (train_utils.py:370-373)
+        if g["name"] in ("logit_opacities", "log_scales", "cam_m", "cam_c", "rgb_colors"):
+            g["lr"] = 0.0
+    tgt = {k: t.to(device) for k, t in prob["target"].items()}
+    ones = torch.ones_like(tgt["colors_precomp"])
+    dataset, host = [], []
+    for c in prob["cams"]:
+        cam = TR.setup_camera(c["w"], c["h"], c["k"], c["w2c"], near=1.0, far=100, device=device)
+        with torch.no_grad():
+            out, _, _, _ = R.raster_forward(cam, tgt["means3D"], tgt["opacities"], tgt["colors_precomp"], tgt["scales"],
+                                            tgt["rotations"], colors1=ones)
+        im = out[:3].clone()
+        seg = workloads.seg_target_from_mask(out[3]).contiguous()
+        dataset.append({"cam": cam, "im": im, "seg": seg, "id": c["id"]})
+        host.append((im.cpu().pin_memory(), seg.cpu().pin_memory()))
+    return params, v, opt, dataset, host
+
+
+def time_blend_backward(params, dataset, capacity, flush, iters=10):
+    """CUDA-event duration of the dominant kernel (blend backward, 6 channels) alone, L2 flushed before each launch."""
+    import ctypes as C
+    from gs_dynamics_b200 import tracking as TR, rasterizer as R, _lib
+    data = dataset[0]
+    with torch.no_grad():
+        rv = TR.params2rendervar(params)
+        color, radii, depth, st = R.raster_forward(data["cam"], rv["means3D"], rv["opacities"], rv["colors_precomp"], rv["scales"],
+                                                   rv["rotations"], colors1=params["seg_colors"].detach(), capacity=capacity)
+        dL = torch.randn_like(color)
+        sz = R._workspace_bytes(st.G, st.W, st.H, st.n_sets, st.capacity)
+        partial = torch.empty(sz[3], dtype=torch.uint8, device=color.device)
+        b = _lib.GsdRasterBwd()
+        b.fwd = st.desc
+        b.dL_dcolor, b.partial_ws = dL.data_ptr(), partial.data_ptr()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ts = []
+        for i in range(iters + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(_lib.lib().gsd_raster_backward_stage(C.byref(b), 1, stream), "gsd_raster_backward_stage")
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(e0.elapsed_time(e1) * 1e-3)
+        R_inst = int(st.status[0].item())
+    return float(np.mean(ts)), R_inst
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from gs_dynamics_b200 import tracking as TR, _lib
+    rank, local_rank, world = env_rank()
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    G = args.gaussians
+    params, variables, opt, dataset, host = build_gpu_problem(G, seed=rank, device=device)
+    n_cams = len(dataset)
+    rng = random.Random(0)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    step_obj = TR.TrackingStep(params, variables, opt, dataset, use_graph=True)
+    own0, lib0 = _lib.launch_count()
+    step_obj.prepare()
+    own1, lib1 = _lib.launch_count()
+    # prepare() = capacity probe (1 fwd) + 1 eager warm-up + 1 captured iteration per camera
+    # launches of ONE iteration: measure on an eager replay
+    eager = TR.TrackingStep(params, variables, opt, dataset, use_graph=False)
+    eager.capacity = dict(step_obj.capacity)
+    a0 = _lib.launch_count()
+    eager.step(0)
+    a1 = _lib.launch_count()
+    own_per_iter, lib_per_iter = a1[0] - a0[0], a1[1] - a0[1]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (value)
+    for _ in range(args.warmup):
+        step_obj.step(rng.randrange(n_cams))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = []
+    t_wall0 = time.time()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_obj.step(rng.randrange(n_cams))
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    t_wall = time.time() - t_wall0
+    dev_s = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public API with host buffers
+    stage_im = torch.empty_like(dataset[0]["im"])
+    stage_seg = torch.empty_like(dataset[0]["seg"])
+    e2e_data = [dict(d, im=stage_im, seg=stage_seg) for d in dataset]
+    e2e = TR.TrackingStep(params, variables, opt, e2e_data, use_graph=True)
+    e2e.capacity = dict(step_obj.capacity)
+    e2e.prepare()
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    h2d = stage_im.numel() * 4 + stage_seg.numel() * 4
+
+    def e2e_step(c):
+        stage_im.copy_(host[c][0], non_blocking=True)
+        stage_seg.copy_(host[c][1], non_blocking=True)
+        l = e2e.step(c)
+        loss_host.copy_(l, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller consumes the loss every step
+        return float(loss_host)
+
+    for _ in range(max(3, args.warmup // 4)):
+        e2e_step(rng.randrange(n_cams))
+    barrier()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last_loss = e2e_step(rng.randrange(n_cams))
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_s += e0.elapsed_time(e1) * 1e-3
+    barrier()
+
+    # ---- roofline of the dominant kernel
+    peak, peak_src = measured_peaks()
+    t_blend, R_inst = time_blend_backward(params, dataset, step_obj.capacity[0], flush)
+    P = 640 * 480
+    alg_bytes = 56.0 * R_inst + 32.0 * P + 48.0 * G  # blend backward, 6 channels, per launch
+    achieved = alg_bytes / t_blend / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("blend_backward_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    times = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_s, e2e_s = float(times[0]), float(times[1])
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "tracking iters/sec", "value": world * args.steps / dev_s, "unit": "iters/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "train_gs.py steady-state iteration (t>0), %dk Gaussians, 4 cams @640x480, 1 episode per GPU" % (G // 1000),
+                       "gaussians": G, "cameras": n_cams, "image": "640x480", "knn": 20, "instances_per_camera": R_inst,
+                       "parallelism": "episode-per-gpu x%d" % world, "l2": "256 MiB flush between timed steps (excluded from step time)",
+                       "timing": "CUDA events per step on the launch stream, max over ranks"},
+            "e2e": {"value": world * args.steps / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(own_per_iter * args.steps), "gpu_launches_per_step": int(own_per_iter),
+            "library_launches_per_step": int(lib_per_iter),
+            "roofline": {"bound": "hbm", "kernel": "gsd_render_bwd_kernel<6>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
+                         "kernel_us": t_blend * 1e6},
+            "clocks": clocks, "wall_s": t_wall, "final_loss": last_loss,
+        }
+    return line, rank, world
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (oracle port on the host cores)
+# ------------------------------------------------------------------------------------------------------------------
+def build_cpu_problem(G, seed):
+    from gs_dynamics_b200 import workloads
+    from oracle import raster_c, tracking_cpu
+    prob = workloads.tracking_problem(G, seed)
+    params = {k: torch.nn.Parameter(v.clone().contiguous()) for k, v in prob["params"].items()}
+    params["rgb_colors"].requires_grad = False
+    variables = dict(prob["variables"])
+    tgt = prob["target"]
+    dataset = []
+    for c in prob["cams"]:
+        m = c["mats"]
+        args = (tgt["means3D"], tgt["colors_precomp"], tgt["opacities"], tgt["scales"], tgt["rotations"], m["viewmatrix"],
+                m["projmatrix"], torch.zeros(3), m["tanfovx"], m["tanfovy"], m["image_height"], m["image_width"])
+        im = torch.from_numpy(raster_c.forward(*args)["color"])
+        a2 = list(args); a2[1] = torch.ones_like(tgt["colors_precomp"])
+        mask = torch.from_numpy(raster_c.forward(*a2)["color"][0])
+        from gs_dynamics_b200.workloads import seg_target_from_mask
+        dataset.append({"cam": m, "im": im, "seg": seg_target_from_mask(mask), "id": c["id"]})
+    opt = tracking_cpu.make_optimizer(params, variables["scene_radius"])
+    return params, variables, opt, dataset
+
+
+def cpu_iterations(G, steps, warmup, budget_s):
+    from oracle import tracking_cpu, raster_c
+    torch.set_num_threads(os.cpu_count() or 1)
+    params, variables, opt, dataset = build_cpu_problem(G, 0)
+    rng = random.Random(0)
+    for _ in range(warmup):
+        tracking_cpu.iteration(params, dataset[rng.randrange(len(dataset))], variables, opt)
+    done, t0 = 0, time.time()
+    while done < steps and (done == 0 or time.time() - t0 < budget_s):
+        tracking_cpu.iteration(params, dataset[rng.randrange(len(dataset))], variables, opt)
+        done += 1
+    dt = time.time() - t0
+    return done, dt, max(raster_c.num_threads(), torch.get_num_threads())
+
+
+def run_reference(args):
+    rank, local_rank, world = env_rank()
+    if rank != 0:
+        return None, rank, world
+    G = args.gaussians
+    done, dt, cores = cpu_iterations(G, args.steps, min(args.warmup, 1), budget_s=150.0)
+    val = done / dt
+    sample = "%d of the requested %d iterations (time-bounded), same config as the GPU arm" % (done, args.steps)
+    line = {"impl": "reference", "metric": "tracking iters/sec", "value": val, "unit": "iters/s", "n_gpus": world, "steps": done,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "train_gs.py steady-state iteration (t>0), %dk Gaussians, 4 cams @640x480" % (G // 1000),
+                       "gaussians": G, "cameras": 4, "image": "640x480", "knn": 20,
+                       "note": "reference iteration on host cores: oracle port (C rasterizer restatement + CPU PyTorch); the "
+                               "reference's own rasterizer is CUDA-only and un-vendored"},
+            "cpu_baseline": {"value": val, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    return line, rank, world
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gaussians", type=int, default=50000)
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        line, rank, world = run_reference(args)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device and no CPU fallback in the product path (use --impl reference for the CPU arm)")
+    line, rank, world = run_ours(args)
+    if rank == 0:
+        if world == 1:
+            done, dt, cores = cpu_iterations(args.gaussians, 10 ** 9, 1, budget_s=args.cpu_baseline_seconds)
+            line["cpu_baseline"] = {"value": done / dt, "unit": "iters/s", "cores": cores, "kind": "port",
+                                    "sample": "%d iterations in %.1f s of the same workload (oracle port on host cores)" % (done, dt)}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

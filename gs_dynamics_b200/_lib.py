@@ -68,7 +68,7 @@ _lib = None
 
 # every symbol include/gsd.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "gsd_last_error", "gsd_version",
+    "gsd_last_error", "gsd_version", "gsd_launch_count", "gsd_raster_backward_stage",
     "gsd_raster_workspace_bytes", "gsd_raster_count_instances", "gsd_raster_forward", "gsd_raster_backward",
     "gsd_raster_mark_visible",
     "gsd_photometric_workspace_bytes", "gsd_photometric_forward", "gsd_photometric_backward",
@@ -90,6 +90,9 @@ def lib():
     l.gsd_raster_count_instances.argtypes = [C.POINTER(GsdRasterFwd), C.c_void_p]
     l.gsd_raster_forward.argtypes = [C.POINTER(GsdRasterFwd), C.c_void_p]
     l.gsd_raster_backward.argtypes = [C.POINTER(GsdRasterBwd), C.c_void_p]
+    l.gsd_raster_backward_stage.argtypes = [C.POINTER(GsdRasterBwd), C.c_int32, C.c_void_p]
+    l.gsd_launch_count.argtypes = [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    l.gsd_launch_count.restype = None
     l.gsd_raster_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_photometric_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
     l.gsd_photometric_forward.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
@@ -102,6 +105,13 @@ def lib():
     l.gsd_track_update_radii.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = l
     return l
+
+
+def launch_count():
+    """(own kernels, CUB kernels) launched by the library so far (host-side count; graph replays are not counted)."""
+    a, b = C.c_longlong(), C.c_longlong()
+    lib().gsd_launch_count(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
 
 
 def check(rc, what):

@@ -11,6 +11,7 @@
 #define GSD_PART_FLOATS 16 // one backward partial-gradient record = 64 B
 
 void gsd_set_error(const char *fmt, ...);
+void gsd_count_launch(int own, int library); // host-side launch accounting (gsd_launch_count)
 
 #define GSD_CUDA_CHECK(expr)                                                                   \
     do {                                                                                       \
@@ -28,6 +29,7 @@ void gsd_set_error(const char *fmt, ...);
             gsd_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
             return GSD_ERR_CUDA;                                                               \
         }                                                                                      \
+        gsd_count_launch(1, 0);                                                                \
     } while (0)
 
 static inline size_t gsd_align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }

@@ -13,7 +13,14 @@ int gsd_launch_render_fwd(const GsdRenderParams &p, int tiles, int n_sets, cudaS
 int gsd_launch_render_bwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st);
 int gsd_launch_preprocess_bwd(int G, const GsdCam &cam, const GsdRasterBwd *a, const GsdGeomWs &g, cudaStream_t st);
 
+#include <atomic>
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_own_launches{0}, g_lib_launches{0};
+void gsd_count_launch(int own, int library) { g_own_launches += own; g_lib_launches += library; }
+extern "C" void gsd_launch_count(long long *own_kernels, long long *library_kernels) {
+    if (own_kernels) *own_kernels = g_own_launches.load();
+    if (library_kernels) *library_kernels = g_lib_launches.load();
+}
 
 void gsd_set_error(const char *fmt, ...) {
     va_list ap;
@@ -111,14 +118,21 @@ extern "C" int gsd_raster_forward(const GsdRasterFwd *a, void *stream) {
     return gsd_launch_render_fwd(p, tiles, a->n_sets, st);
 }
 
-extern "C" int gsd_raster_backward(const GsdRasterBwd *a, void *stream) {
+static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages);
+extern "C" int gsd_raster_backward(const GsdRasterBwd *a, void *stream) { return raster_backward_impl(a, stream, 3); }
+// stage 1: blend backward only (the dominant kernel, timed alone for the roofline); stage 2: per-Gaussian backward only
+extern "C" int gsd_raster_backward_stage(const GsdRasterBwd *a, int32_t stage, void *stream) {
+    if (stage != 1 && stage != 2) { gsd_set_error("stage must be 1 or 2"); return GSD_ERR_INVALID; }
+    return raster_backward_impl(a, stream, stage);
+}
+static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages) {
     if (!a) { gsd_set_error("null descriptor"); return GSD_ERR_INVALID; }
     const GsdRasterFwd *f = &a->fwd;
     GsdCam cam;
     int rc;
     if ((rc = make_cam(f, &cam))) return rc;
     if (!f->geom_ws || !f->binning_ws || !f->image_ws || !a->partial_ws || !a->dL_dcolor ||
-        (f->G > 0 && (!a->dL_dmeans3D || !a->dL_dopacities || !a->dL_dscales || !a->dL_drotations))) {
+        ((stages & 2) && f->G > 0 && (!a->dL_dmeans3D || !a->dL_dopacities || !a->dL_dscales || !a->dL_drotations))) {
         gsd_set_error("null workspace/output pointer");
         return GSD_ERR_INVALID;
     }
@@ -141,9 +155,10 @@ extern "C" int gsd_raster_backward(const GsdRasterBwd *a, void *stream) {
     p.n_contrib = im.n_contrib;
     p.dL_dcolor = a->dL_dcolor;
     p.partials = (float *)a->partial_ws;
-    if (f->G > 0 && f->capacity > 0)
+    if ((stages & 1) && f->G > 0 && f->capacity > 0)
         if ((rc = gsd_launch_render_bwd(p, tiles, f->n_sets, st))) return rc;
-    return gsd_launch_preprocess_bwd(f->G, cam, a, g, st);
+    if (stages & 2) return gsd_launch_preprocess_bwd(f->G, cam, a, g, st);
+    return GSD_OK;
 }
 
 extern "C" int gsd_raster_mark_visible(int32_t G, const float *means3D, const float *viewmatrix, uint8_t *visible, void *stream) {

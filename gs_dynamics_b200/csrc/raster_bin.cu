@@ -182,6 +182,7 @@ int gsd_launch_scan(int G, const GsdGeomWs &g, int64_t capacity, int32_t *status
     if (G > 0) {
         size_t tmp = g.scan_tmp_bytes;
         GSD_CUDA_CHECK(cub::DeviceScan::InclusiveSum(g.scan_tmp, tmp, g.tiles, g.offsets, G, st));
+        gsd_count_launch(0, 2);
     }
     gsd_finish_count_kernel<<<1, 1, 0, st>>>(G, g.offsets, capacity, status);
     GSD_LAUNCH_CHECK();
@@ -209,6 +210,7 @@ int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const Gs
     int end_bit = 32 + highest_bit((uint32_t)tiles); // sentinel tile id (all ones) stays above every real tile
     GSD_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(b.sort_tmp, tmp, b.keys_a, b.keys_b, b.vals_a, b.vals_b, (int)cap, 0,
                                                    end_bit, st));
+    gsd_count_launch(0, 2 + (end_bit + 7) / 8);
     gsd_pack_records_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(
         cap, cam.gx, a->status, b.keys_b, b.vals_b, g.xy, g.conic_o, g.ext, g.depth, g.rect, g.offsets, g.tiles,
         a->colors0, a->n_sets == 2 ? a->colors1 : nullptr, b.ranges, b.records);

@@ -42,6 +42,8 @@ typedef enum {
 
 const char *gsd_last_error(void);
 int gsd_version(void);
+/* host-side count of kernels launched by this library since load: own kernels / CUB (library) kernels */
+void gsd_launch_count(long long *own_kernels, long long *library_kernels);
 
 /* ------------------------------------------------------------------------------------------------
  * Path A.1 — rasterizer (replaces _C.rasterize_gaussians / _C.rasterize_gaussians_backward)
@@ -107,6 +109,9 @@ int gsd_raster_forward(const GsdRasterFwd *a, void *stream);
 
 /* blend backward (deterministic, atomic-free) -> cov2D/projection/cov3D backward */
 int gsd_raster_backward(const GsdRasterBwd *a, void *stream);
+
+/* one stage of the backward alone (1 = blend backward, 2 = per-Gaussian backward); bench.py times stage 1 for the roofline */
+int gsd_raster_backward_stage(const GsdRasterBwd *a, int32_t stage, void *stream);
 
 /* replaces _C.mark_visible: visible[g] = (view-space z > 0.2) */
 int gsd_raster_mark_visible(int32_t G, const float *means3D, const float *viewmatrix, uint8_t *visible, void *stream);
