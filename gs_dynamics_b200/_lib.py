@@ -64,6 +64,16 @@ class GsdAdam(C.Structure):
     ]
 
 
+class GsdGnnEdges(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("N", C.c_int32), ("n_tool", C.c_int32), ("topk", C.c_int32), ("connect_all", C.c_int32),
+        ("capacity", C.c_int32),
+        ("states", C.c_void_p), ("mask", C.c_void_p), ("tool_mask", C.c_void_p), ("adj_thresh", C.c_void_p),
+        ("adj_thresh_sq_scalar", C.c_float),
+        ("ws", C.c_void_p), ("row_ptr", C.c_void_p), ("n_edges", C.c_void_p), ("receivers", C.c_void_p), ("senders", C.c_void_p),
+    ]
+
+
 _lib = None
 
 # every symbol include/gsd.h declares (checked by tests/test_abi.py)
@@ -73,6 +83,8 @@ EXPORTS = [
     "gsd_raster_mark_visible",
     "gsd_photometric_workspace_bytes", "gsd_photometric_forward", "gsd_photometric_backward",
     "gsd_track_losses_workspace_bytes", "gsd_track_losses_fwd_bwd", "gsd_adam_step", "gsd_track_update_radii",
+    "gsd_gnn_edges_workspace_bytes", "gsd_gnn_build_edges", "gsd_gnn_edge_inputs", "gsd_gnn_aggregate_workspace_bytes",
+    "gsd_gnn_aggregate", "gsd_fps",
 ]
 
 
@@ -103,6 +115,12 @@ def lib():
     l.gsd_track_losses_fwd_bwd.argtypes = [C.POINTER(GsdTrackLosses), C.c_void_p]
     l.gsd_adam_step.argtypes = [C.POINTER(GsdAdam), C.c_void_p]
     l.gsd_track_update_radii.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.gsd_gnn_edges_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
+    l.gsd_gnn_build_edges.argtypes = [C.POINTER(GsdGnnEdges), C.c_void_p]
+    l.gsd_gnn_edge_inputs.argtypes = [C.c_int32] * 7 + [C.c_void_p] * 7
+    l.gsd_gnn_aggregate_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
+    l.gsd_gnn_aggregate.argtypes = [C.c_int32] * 5 + [C.c_void_p] * 7
+    l.gsd_fps.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = l
     return l
 

@@ -1,0 +1,486 @@
+// gnn.cu — graph kernels of the GNN particle-dynamics step (path B), sm_100a.
+//
+//   gsd_gnn_build_edges   radius AND top-k adjacency + tool edges -> CSR-by-receiver index lists (never N x N one-hots)
+//                         replaces construct_edges_from_states, /root/reference/src/data/dataset.py:88-147
+//   gsd_gnn_edge_inputs   per-edge relation features [attrs_r | attrs_s | group diff | pos_r - pos_s over history]
+//                         replaces the six one-hot bmm of /root/reference/src/gnn/model.py:164-199
+//   gsd_gnn_aggregate     agg[r] = sum_{e: recv(e)=r} ReLU(A[e] + Pr[r] + Ps[send(e)])   (edge MLP epilogue + segment reduce)
+//                         replaces Rr.bmm / Rs.bmm / cat / Linear epilogue / Rr_t.bmm of model.py:212-229 after splitting
+//                         W_rel [enc_e | h_r | h_s] = W1 enc_e + W2 h_r + W3 h_s  (the dense parts stay on cuBLAS)
+//   gsd_fps / gsd_fps_radius   farthest point sampling (dgl.geometry.farthest_point_sampler, data/utils.py:50-65)
+//
+// All of these are gather / scatter-shaped, HBM/L2-bound integer+fp32 work: warp-per-row with float4 lanes, no tensor cores.
+// Algorithmic bytes of gsd_gnn_aggregate per call: 4*E*F (A) + 8*E (indices) + 12*N*F (Pr, Ps, agg)  (SURVEY.md §8d).
+#include "common.cuh"
+
+#define GNN_MAX_SMEM_NODES 4096
+
+__device__ __forceinline__ float dist2_rn(float ax, float ay, float az, float bx, float by, float bz) {
+    // ((dx^2 + dy^2) + dz^2) without FMA contraction, the order torch.sum(s_diff ** 2, -1) uses for 3 elements
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// edge construction.  One warp per receiver row; tools are the last n_tool nodes (dataset.py:120-124).
+//   pass 0: adjacency bit rows + row counts;  (host launches a 1-block scan);  pass 1: expand bits to (recv, send) lists
+// ------------------------------------------------------------------------------------------------------
+struct EdgeArgs {
+    int B, N, n_tool, topk, connect_all;
+    const float *states;     // [B,N,3]
+    const uint8_t *mask;     // [B,N] valid particle
+    const uint8_t *tool_mask;// [B,N]
+    const float *thresh;     // [B] adj_thresh (not squared) or null -> thresh_sq_scalar
+    float thresh_sq_scalar;
+    uint32_t *bits;          // [B*N][words]
+    int words;
+    int32_t *row_count;      // [B*N]
+};
+
+__global__ void __launch_bounds__(128)
+gsd_gnn_adjacency_kernel(EdgeArgs a) {
+    extern __shared__ float spos[]; // [N*3] positions of this batch element
+    const int b = blockIdx.y;
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float *st = a.states + (size_t)b * a.N * 3;
+    for (int i = threadIdx.x; i < a.N * 3; i += blockDim.x) spos[i] = st[i];
+    __syncthreads();
+    const uint8_t *mk = a.mask + (size_t)b * a.N, *tm = a.tool_mask + (size_t)b * a.N;
+    const int n_obj = a.N - a.n_tool;
+    const float thr = a.thresh ? __fmul_rn(a.thresh[b], a.thresh[b]) : a.thresh_sq_scalar;
+    const int r = blockIdx.x * warps + warp;
+    if (r >= a.N) return;
+    const float rx = spos[3 * r], ry = spos[3 * r + 1], rz = spos[3 * r + 2];
+    const bool r_valid = mk[r] != 0, r_tool = tm[r] != 0;
+    uint32_t *row = a.bits + ((size_t)b * a.N + r) * a.words;
+
+    // ---- top-k smallest distances among the object block (only rows of the object block), ties -> lowest index
+    // selected columns are kept as per-lane bit sets: column c is owned by lane c % 32, slot c / 32
+    uint32_t sel[GNN_MAX_SMEM_NODES / 1024]; // slot bits, 32 slots per word
+#pragma unroll
+    for (int w = 0; w < GNN_MAX_SMEM_NODES / 1024; ++w) sel[w] = 0u;
+    const int k_eff = min(a.topk, a.N);
+    if (r < n_obj) {
+        for (int it = 0; it < min(k_eff, n_obj); ++it) {
+            float best = 3.0e38f;
+            int best_c = 0x7fffffff;
+            for (int c = lane, slot = 0; c < n_obj; c += 32, ++slot) {
+                if ((sel[slot >> 5] >> (slot & 31)) & 1u) continue;
+                float d = dist2_rn(rx, ry, rz, spos[3 * c], spos[3 * c + 1], spos[3 * c + 2]);
+                if (!(r_valid && mk[c]) || (r_tool && tm[c])) d = 1e10f;
+                if (d < best) { best = d; best_c = c; }
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+                if (ob < best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+            }
+            if (best_c != 0x7fffffff && (best_c & 31) == lane) {
+                int slot = best_c >> 5;
+                sel[slot >> 5] |= 1u << (slot & 31);
+            }
+        }
+    }
+    // ---- adjacency bits
+    int count = 0;
+    for (int w = 0; w < a.words; ++w) {
+        const int c = w * 32 + lane;
+        bool on = false;
+        if (c < a.N) {
+            const bool c_valid = mk[c] != 0, c_tool = tm[c] != 0;
+            float d = dist2_rn(rx, ry, rz, spos[3 * c], spos[3 * c + 1], spos[3 * c + 2]);
+            if (!(r_valid && c_valid)) d = 1e10f;
+            if (r_tool && c_tool) d = 1e10f;
+            on = __fsub_rn(d, thr) < 0.f;
+            if (r < n_obj && c < n_obj) {
+                const int slot = c >> 5; // lane == c & 31 by construction
+                on = on && ((sel[slot >> 5] >> (slot & 31)) & 1u);
+            }
+            if (a.connect_all) {
+                if (r_tool && c_valid) on = true;
+                if (c_tool && r_valid) on = true;
+                if (r_tool && c_tool) on = false;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) row[w] = m;
+        count += __popc(m);
+    }
+    if (lane == 0) a.row_count[(size_t)b * a.N + r] = count;
+}
+
+// single block: exclusive scan of row counts per batch element -> row_ptr [B][N+1]; n_edges[b]
+__global__ void gsd_gnn_scan_rows_kernel(int B, int N, const int32_t *__restrict__ row_count, int32_t *__restrict__ row_ptr,
+                                         int32_t *__restrict__ n_edges) {
+    __shared__ int sbuf[1024];
+    __shared__ int carry;
+    for (int b = 0; b < B; ++b) {
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (int base = 0; base < N; base += 1024) {
+            int i = base + threadIdx.x;
+            int v = i < N ? row_count[(size_t)b * N + i] : 0;
+            sbuf[threadIdx.x] = v;
+            __syncthreads();
+            for (int o = 1; o < 1024; o <<= 1) {
+                int add = threadIdx.x >= o ? sbuf[threadIdx.x - o] : 0;
+                __syncthreads();
+                sbuf[threadIdx.x] += add;
+                __syncthreads();
+            }
+            if (i < N) row_ptr[(size_t)b * (N + 1) + i] = carry + sbuf[threadIdx.x] - v;
+            __syncthreads();
+            if (threadIdx.x == 1023) carry += sbuf[1023];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            row_ptr[(size_t)b * (N + 1) + N] = carry;
+            n_edges[b] = carry;
+        }
+        __syncthreads();
+    }
+}
+
+// one warp per row: expand adjacency bits to receiver / sender lists (row-major = adj.nonzero() order).
+// Edges of batch element b occupy [b*cap, b*cap + n_edges[b]); the remaining slots get receiver = sender = -1.
+__global__ void __launch_bounds__(128)
+gsd_gnn_expand_kernel(int B, int N, int words, int cap, const uint32_t *__restrict__ bits, const int32_t *__restrict__ row_ptr,
+                      int32_t *__restrict__ recv, int32_t *__restrict__ send) {
+    const int b = blockIdx.y;
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * warps + warp;
+    if (r > N) return;
+    const int32_t *rp = row_ptr + (size_t)b * (N + 1);
+    if (r == N) { // padding
+        for (int e = rp[N] + lane; e < cap; e += 32) {
+            recv[(size_t)b * cap + e] = -1;
+            send[(size_t)b * cap + e] = -1;
+        }
+        return;
+    }
+    int off = rp[r];
+    const uint32_t *row = bits + ((size_t)b * N + r) * words;
+    for (int w = 0; w < words; ++w) {
+        const uint32_t m = row[w];
+        if ((m >> lane) & 1u) {
+            const int e = off + __popc(m & ((1u << lane) - 1u));
+            if (e < cap) {
+                recv[(size_t)b * cap + e] = r;
+                send[(size_t)b * cap + e] = w * 32 + lane;
+            }
+        }
+        off += __popc(m);
+    }
+}
+
+extern "C" int gsd_gnn_edges_workspace_bytes(int32_t B, int32_t N, size_t *bytes) {
+    if (B <= 0 || N <= 0 || !bytes) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
+    size_t words = (size_t)(N + 31) / 32;
+    *bytes = gsd_align_up((size_t)B * N * words * 4) + gsd_align_up((size_t)B * N * 4);
+    return GSD_OK;
+}
+
+extern "C" int gsd_gnn_build_edges(const GsdGnnEdges *g, void *stream) {
+    if (!g || g->B <= 0 || g->N <= 0 || g->n_tool < 0 || g->n_tool > g->N || g->capacity < 0 || !g->states || !g->mask ||
+        !g->tool_mask || !g->ws || !g->row_ptr || !g->n_edges || !g->receivers || !g->senders) {
+        gsd_set_error("invalid arguments");
+        return GSD_ERR_INVALID;
+    }
+    if (g->N > GNN_MAX_SMEM_NODES) { gsd_set_error("N=%d exceeds %d nodes per graph", g->N, GNN_MAX_SMEM_NODES); return GSD_ERR_UNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+    EdgeArgs a;
+    a.B = g->B; a.N = g->N; a.n_tool = g->n_tool; a.topk = g->topk; a.connect_all = g->connect_all;
+    a.states = g->states; a.mask = g->mask; a.tool_mask = g->tool_mask; a.thresh = g->adj_thresh; a.thresh_sq_scalar = g->adj_thresh_sq_scalar;
+    a.words = (g->N + 31) / 32;
+    a.bits = (uint32_t *)g->ws;
+    a.row_count = (int32_t *)((char *)g->ws + gsd_align_up((size_t)g->B * g->N * a.words * 4));
+    const int warps = 4;
+    dim3 grid((g->N + warps - 1) / warps, g->B);
+    size_t smem = (size_t)g->N * 3 * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_gnn_adjacency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GNN_MAX_SMEM_NODES * 12));
+        attr_set = true;
+    }
+    gsd_gnn_adjacency_kernel<<<grid, warps * 32, smem, st>>>(a);
+    GSD_LAUNCH_CHECK();
+    gsd_gnn_scan_rows_kernel<<<1, 1024, 0, st>>>(g->B, g->N, a.row_count, g->row_ptr, g->n_edges);
+    GSD_LAUNCH_CHECK();
+    dim3 grid2((g->N + 1 + warps - 1) / warps, g->B);
+    gsd_gnn_expand_kernel<<<grid2, warps * 32, 0, st>>>(g->B, g->N, a.words, g->capacity, a.bits, g->row_ptr, g->receivers, g->senders);
+    GSD_LAUNCH_CHECK();
+    return GSD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// per-edge relation inputs: [attrs_r(A) | attrs_s(A) | sum|g_r - g_s| (1) | (pos_r - pos_s) for each history frame (3*n_his)]
+// node-major state layout: state_t [B,N,n_his*3] is what the reference builds at model.py:132; here state is [B,n_his,N,3].
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gsd_gnn_edge_inputs_kernel(int B, int N, int cap, int n_his, int attr_dim, int n_inst, int n_p, const float *__restrict__ state,
+                           const float *__restrict__ attrs, const float *__restrict__ p_instance, const int32_t *__restrict__ recv,
+                           const int32_t *__restrict__ send, float *__restrict__ out) {
+    const int width = 2 * attr_dim + 1 + 3 * n_his;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)B * cap) return;
+    const int b = (int)(e / cap);
+    float *o = out + e * width;
+    const int r = recv[e], s = send[e];
+    if (r < 0) {
+        for (int k = 0; k < width; ++k) o[k] = 0.f;
+        return;
+    }
+    const float *at = attrs + (size_t)b * N * attr_dim;
+    for (int k = 0; k < attr_dim; ++k) {
+        o[k] = at[(size_t)r * attr_dim + k];
+        o[attr_dim + k] = at[(size_t)s * attr_dim + k];
+    }
+    float gd = 0.f;
+    const float *pi = p_instance + (size_t)b * n_p * n_inst;
+    for (int k = 0; k < n_inst; ++k) {
+        float gr = r < n_p ? pi[(size_t)r * n_inst + k] : 0.f;
+        float gs = s < n_p ? pi[(size_t)s * n_inst + k] : 0.f;
+        gd += fabsf(gr - gs);
+    }
+    o[2 * attr_dim] = gd;
+    for (int h = 0; h < n_his; ++h) {
+        const float *sp = state + ((size_t)b * n_his + h) * N * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[2 * attr_dim + 1 + 3 * h + c] = sp[(size_t)r * 3 + c] - sp[(size_t)s * 3 + c];
+    }
+}
+
+extern "C" int gsd_gnn_edge_inputs(int32_t B, int32_t N, int32_t capacity, int32_t n_his, int32_t attr_dim, int32_t n_instance,
+                                   int32_t n_p, const float *state, const float *attrs, const float *p_instance,
+                                   const int32_t *receivers, const int32_t *senders, float *rel_inputs, void *stream) {
+    if (B <= 0 || N <= 0 || capacity < 0 || n_his <= 0 || attr_dim < 0 || n_instance < 0 || !state || !attrs || !receivers || !senders || !rel_inputs) {
+        gsd_set_error("invalid arguments");
+        return GSD_ERR_INVALID;
+    }
+    if (capacity == 0) return GSD_OK;
+    long long total = (long long)B * capacity;
+    gsd_gnn_edge_inputs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        B, N, capacity, n_his, attr_dim, n_instance, n_p, state, attrs, p_instance, receivers, senders, rel_inputs);
+    GSD_LAUNCH_CHECK();
+    return GSD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// fused edge epilogue + segment reduce.  Nodes are globally indexed (b*N + n), edges of element b live at [b*cap, ...).
+//   agg[node] = sum over the node's incoming edges of ReLU(A[e] + P[node][0:F] + P[b*N + send(e)][F:2F])
+// One warp per (receiver) row for ordinary rows; rows with many edges (the tool rows: every object is a sender) are split
+// over GNN_SPLIT CTAs writing partials that a second kernel sums in fixed order.
+// ------------------------------------------------------------------------------------------------------
+#define GNN_SPLIT 32
+
+template <int VEC_PER_LANE> // F = 128 * VEC_PER_LANE
+__global__ void __launch_bounds__(128)
+gsd_gnn_aggregate_rows_kernel(int B, int N, int cap, int n_rows_per_b, const int32_t *__restrict__ row_ptr,
+                              const int32_t *__restrict__ send, const float4 *__restrict__ A, const float4 *__restrict__ P,
+                              float4 *__restrict__ agg) {
+    constexpr int F4 = 32 * VEC_PER_LANE; // float4 per feature row
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * warps + warp;
+    if (row >= (long long)B * n_rows_per_b) return;
+    const int b = (int)(row / n_rows_per_b), r = (int)(row % n_rows_per_b);
+    const int32_t *rp = row_ptr + (size_t)b * (N + 1);
+    const int e0 = min(rp[r], cap), e1 = min(rp[r + 1], cap);
+    const size_t node = (size_t)b * N + r;
+    float4 pr[VEC_PER_LANE], acc[VEC_PER_LANE];
+#pragma unroll
+    for (int v = 0; v < VEC_PER_LANE; ++v) {
+        pr[v] = P[node * 2 * F4 + v * 32 + lane];
+        acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int e = e0; e < e1; ++e) {
+        const size_t ge = (size_t)b * cap + e;
+        const size_t snode = (size_t)b * N + send[ge];
+#pragma unroll
+        for (int v = 0; v < VEC_PER_LANE; ++v) {
+            const float4 a4 = A[ge * F4 + v * 32 + lane];
+            const float4 s4 = P[snode * 2 * F4 + F4 + v * 32 + lane];
+            acc[v].x += fmaxf(a4.x + pr[v].x + s4.x, 0.f);
+            acc[v].y += fmaxf(a4.y + pr[v].y + s4.y, 0.f);
+            acc[v].z += fmaxf(a4.z + pr[v].z + s4.z, 0.f);
+            acc[v].w += fmaxf(a4.w + pr[v].w + s4.w, 0.f);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC_PER_LANE; ++v) agg[node * F4 + v * 32 + lane] = acc[v];
+}
+
+template <int VEC_PER_LANE>
+__global__ void __launch_bounds__(128)
+gsd_gnn_aggregate_heavy_kernel(int B, int N, int cap, int first_row, int n_heavy, const int32_t *__restrict__ row_ptr,
+                               const int32_t *__restrict__ send, const float4 *__restrict__ A, const float4 *__restrict__ P,
+                               float4 *__restrict__ partial /* [B*n_heavy][GNN_SPLIT][F4] */) {
+    constexpr int F4 = 32 * VEC_PER_LANE;
+    const int hrow = blockIdx.x, split = blockIdx.y; // hrow in [0, B*n_heavy)
+    const int b = hrow / n_heavy, r = first_row + hrow % n_heavy;
+    const int32_t *rp = row_ptr + (size_t)b * (N + 1);
+    const int e0 = min(rp[r], cap), e1 = min(rp[r + 1], cap);
+    const int n = e1 - e0;
+    const int per = (n + GNN_SPLIT - 1) / GNN_SPLIT;
+    const int s0 = e0 + split * per, s1 = min(e1, s0 + per);
+    const size_t node = (size_t)b * N + r;
+    // 128 threads = one float4 column each for F = 512; generic: loop columns
+    for (int col = threadIdx.x; col < F4; col += blockDim.x) {
+        const float4 pr = P[node * 2 * F4 + col];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = s0; e < s1; ++e) {
+            const size_t ge = (size_t)b * cap + e;
+            const size_t snode = (size_t)b * N + send[ge];
+            const float4 a4 = A[ge * F4 + col];
+            const float4 s4 = P[snode * 2 * F4 + F4 + col];
+            acc.x += fmaxf(a4.x + pr.x + s4.x, 0.f);
+            acc.y += fmaxf(a4.y + pr.y + s4.y, 0.f);
+            acc.z += fmaxf(a4.z + pr.z + s4.z, 0.f);
+            acc.w += fmaxf(a4.w + pr.w + s4.w, 0.f);
+        }
+        partial[((size_t)hrow * GNN_SPLIT + split) * F4 + col] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+gsd_gnn_aggregate_heavy_finish_kernel(int N, int first_row, int n_heavy, int F4, const float4 *__restrict__ partial,
+                                      float4 *__restrict__ agg) {
+    const int hrow = blockIdx.x;
+    const int b = hrow / n_heavy, r = first_row + hrow % n_heavy;
+    for (int col = threadIdx.x; col < F4; col += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < GNN_SPLIT; ++s) {
+            const float4 p = partial[((size_t)hrow * GNN_SPLIT + s) * F4 + col];
+            acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+        }
+        agg[((size_t)b * N + r) * F4 + col] = acc;
+    }
+}
+
+extern "C" int gsd_gnn_aggregate_workspace_bytes(int32_t B, int32_t n_heavy, int32_t F, size_t *bytes) {
+    if (B <= 0 || n_heavy < 0 || F <= 0 || !bytes) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
+    *bytes = gsd_align_up((size_t)B * (n_heavy > 0 ? n_heavy : 1) * GNN_SPLIT * F * 4);
+    return GSD_OK;
+}
+
+// rows [0, N - n_heavy) : warp per row;  rows [N - n_heavy, N) (tool nodes) : split over GNN_SPLIT CTAs
+extern "C" int gsd_gnn_aggregate(int32_t B, int32_t N, int32_t capacity, int32_t F, int32_t n_heavy, const int32_t *row_ptr,
+                                 const int32_t *senders, const float *A, const float *P, void *ws, float *agg, void *stream) {
+    if (B <= 0 || N <= 0 || capacity < 0 || n_heavy < 0 || n_heavy > N || !row_ptr || !senders || !A || !P || !agg || (n_heavy > 0 && !ws)) {
+        gsd_set_error("invalid arguments");
+        return GSD_ERR_INVALID;
+    }
+    if (F % 128 != 0 || F > 512) { gsd_set_error("feature width %d must be a multiple of 128 and <= 512", F); return GSD_ERR_UNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_light = N - n_heavy;
+    const int warps = 4;
+    const long long rows = (long long)B * n_light;
+    if (rows > 0) {
+        unsigned grid = (unsigned)((rows + warps - 1) / warps);
+        // light rows of batch b are rows [0, n_light): pass n_rows_per_b = n_light
+        switch (F / 128) {
+        case 1: gsd_gnn_aggregate_rows_kernel<1><<<grid, 128, 0, st>>>(B, N, capacity, n_light, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)agg); break;
+        case 2: gsd_gnn_aggregate_rows_kernel<2><<<grid, 128, 0, st>>>(B, N, capacity, n_light, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)agg); break;
+        case 3: gsd_gnn_aggregate_rows_kernel<3><<<grid, 128, 0, st>>>(B, N, capacity, n_light, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)agg); break;
+        default: gsd_gnn_aggregate_rows_kernel<4><<<grid, 128, 0, st>>>(B, N, capacity, n_light, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)agg); break;
+        }
+        GSD_LAUNCH_CHECK();
+    }
+    if (n_heavy > 0) {
+        dim3 grid(B * n_heavy, GNN_SPLIT);
+        switch (F / 128) {
+        case 1: gsd_gnn_aggregate_heavy_kernel<1><<<grid, 128, 0, st>>>(B, N, capacity, n_light, n_heavy, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)ws); break;
+        case 2: gsd_gnn_aggregate_heavy_kernel<2><<<grid, 128, 0, st>>>(B, N, capacity, n_light, n_heavy, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)ws); break;
+        case 3: gsd_gnn_aggregate_heavy_kernel<3><<<grid, 128, 0, st>>>(B, N, capacity, n_light, n_heavy, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)ws); break;
+        default: gsd_gnn_aggregate_heavy_kernel<4><<<grid, 128, 0, st>>>(B, N, capacity, n_light, n_heavy, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)ws); break;
+        }
+        GSD_LAUNCH_CHECK();
+        gsd_gnn_aggregate_heavy_finish_kernel<<<B * n_heavy, 128, 0, st>>>(N, n_light, n_heavy, F / 4, (const float4 *)ws, (float4 *)agg);
+        GSD_LAUNCH_CHECK();
+    }
+    return GSD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// farthest point sampling: one CTA per batch element, distances in shared memory, first-max tie break.
+//   radius <= 0 : classic FPS to npoints (dgl.geometry.farthest_point_sampler, squared distances)
+//   radius  > 0 : radius-terminated FPS of fps_rad_idx_torch (data/utils.py:50-65, euclidean distances): stops when the
+//                 largest distance to the picked set is <= radius; count[b] receives the number of picks
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+gsd_fps_kernel(int N, int npoints, float radius, const float *__restrict__ pos, const int64_t *__restrict__ start_idx,
+               int64_t *__restrict__ out, int32_t *__restrict__ count) {
+    extern __shared__ float sdist[]; // [N]
+    __shared__ float rv[32];
+    __shared__ int ri[32];
+    __shared__ int s_cur;
+    const int b = blockIdx.x;
+    const float *p = pos + (size_t)b * N * 3;
+    int64_t *o = out + (size_t)b * npoints;
+    const bool rad = radius > 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sdist[i] = 3.0e38f;
+    if (threadIdx.x == 0) {
+        long long s = start_idx ? start_idx[b] : 0;
+        s_cur = (int)(s < 0 ? 0 : (s >= N ? N - 1 : s));
+    }
+    __syncthreads();
+    int picked = 0;
+    for (int it = 0; it < npoints; ++it) {
+        const int cur = s_cur;
+        if (threadIdx.x == 0) o[it] = cur;
+        picked = it + 1;
+        const float cx = p[3 * cur], cy = p[3 * cur + 1], cz = p[3 * cur + 2];
+        float best = -1.f;
+        int best_i = 0x7fffffff;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            float d = dist2_rn(p[3 * i], p[3 * i + 1], p[3 * i + 2], cx, cy, cz);
+            if (rad) d = sqrtf(d);
+            float m = fminf(sdist[i], d);
+            sdist[i] = m;
+            if (m > best) { best = m; best_i = i; }
+        }
+#pragma unroll
+        for (int of = 16; of >= 1; of >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, of);
+            int oi = __shfl_xor_sync(0xffffffffu, best_i, of);
+            if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { rv[threadIdx.x >> 5] = best; ri[threadIdx.x >> 5] = best_i; }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            best = threadIdx.x < (blockDim.x >> 5) ? rv[threadIdx.x] : -1.f;
+            best_i = threadIdx.x < (blockDim.x >> 5) ? ri[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+            for (int of = 16; of >= 1; of >>= 1) {
+                float ob = __shfl_xor_sync(0xffffffffu, best, of);
+                int oi = __shfl_xor_sync(0xffffffffu, best_i, of);
+                if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+            }
+            if (threadIdx.x == 0) {
+                rv[0] = best;
+                s_cur = best_i;
+            }
+        }
+        __syncthreads();
+        if (rad && !(rv[0] > radius)) break;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && count) count[b] = picked;
+    for (int i = picked + threadIdx.x; i < npoints; i += blockDim.x) o[i] = -1;
+}
+
+extern "C" int gsd_fps(int32_t B, int32_t N, int32_t npoints, float radius, const float *pos, const int64_t *start_idx,
+                       int64_t *out_idx, int32_t *count, void *stream) {
+    if (B <= 0 || N <= 0 || npoints <= 0 || !pos || !out_idx) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
+    if ((size_t)N * 4 > 200 * 1024) { gsd_set_error("N=%d too large for the shared-memory FPS kernel", N); return GSD_ERR_UNSUPPORTED; }
+    if (radius <= 0.f && npoints > N) { gsd_set_error("npoints > N"); return GSD_ERR_INVALID; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    int threads = N >= 1024 ? 1024 : ((N + 31) / 32) * 32;
+    gsd_fps_kernel<<<B, threads, (size_t)N * 4, (cudaStream_t)stream>>>(N, npoints, radius, pos, start_idx, out_idx, count);
+    GSD_LAUNCH_CHECK();
+    return GSD_OK;
+}

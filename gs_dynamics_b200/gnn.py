@@ -1,0 +1,421 @@
+"""Host side of the GNN particle-dynamics step (path B), backed by the sm_100a graph kernels of libgsd_b200.so.
+
+Mirrors (same names, argument meaning, results):
+  DynamicsPredictor(model_config, device).forward(state, attrs, Rr, Rs, p_instance, action=None, **kw)
+                                             /root/reference/src/gnn/model.py:70-246  (state_dict layout identical)
+  construct_edges_from_states[_batch]        /root/reference/src/data/dataset.py:88-216
+  farthest_point_sampler                     dgl.geometry (call sites /root/reference/src/render/dynamics_module.py:46,65)
+  fps_rad_idx_torch                          /root/reference/src/data/utils.py:50-65
+Design: edges are index lists grouped by receiver (CSR), never one-hot matrices; the relation propagator
+Linear([enc_e | h_r | h_s]) is split into W1 enc_e (once per step, cuBLAS) + W2 h_r + W3 h_s (node-level GEMM per pstep), so
+the per-pstep edge work is one fused gather + ReLU + segment-sum kernel.  Dense Linears stay on cuBLAS fp32 (no TF32).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _cuda_f32(t, name):
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (no CPU path)" % name)
+    return t.contiguous().float()
+
+
+# ----------------------------------------------------------------------------------------------------
+# farthest point sampling
+# ----------------------------------------------------------------------------------------------------
+def farthest_point_sampler(pos, npoints, start_idx=None):
+    """dgl.geometry.farthest_point_sampler: pos [B,N,3] -> int64 [B,npoints]. CPU inputs (the reference passes
+    `.cpu()` tensors) are staged to the GPU and the result is returned on the input's device."""
+    src_dev = pos.device
+    p = pos.detach()
+    if not p.is_cuda:
+        p = p.cuda()
+    p = p.contiguous().float()
+    B, N, _ = p.shape
+    if start_idx is None:
+        start = torch.randint(0, N, (B,), device=p.device, dtype=torch.int64)
+    elif isinstance(start_idx, int):
+        start = torch.full((B,), start_idx, device=p.device, dtype=torch.int64)
+    else:
+        start = torch.as_tensor(start_idx, device=p.device, dtype=torch.int64).reshape(B).contiguous()
+    out = torch.empty((B, npoints), dtype=torch.int64, device=p.device)
+    with torch.cuda.device(p.device):
+        _lib.check(_lib.lib().gsd_fps(B, N, npoints, 0.0, p.data_ptr(), start.data_ptr(), out.data_ptr(), None, _stream()), "gsd_fps")
+    return out.to(src_dev)
+
+
+def fps_rad_idx_torch(pcd, radius, start_idx=None):
+    """Radius-terminated FPS of data/utils.py:50-65: returns (pcd_fps, idx_lst). The reference draws the first index
+    with np.random.randint; pass start_idx for reproducibility."""
+    src_dev = pcd.device
+    p = pcd.detach()
+    if not p.is_cuda:
+        p = p.cuda()
+    p = p.contiguous().float()
+    N = p.shape[0]
+    if start_idx is None:
+        start_idx = int(np.random.randint(N))
+    start = torch.tensor([start_idx], device=p.device, dtype=torch.int64)
+    out = torch.empty((1, N), dtype=torch.int64, device=p.device)
+    count = torch.zeros(1, dtype=torch.int32, device=p.device)
+    with torch.cuda.device(p.device):
+        _lib.check(_lib.lib().gsd_fps(1, N, N, float(radius), p.data_ptr(), start.data_ptr(), out.data_ptr(), count.data_ptr(),
+                                      _stream()), "gsd_fps")
+    n = int(count.item())  # the reference's own loop syncs once per pick
+    idx = out[0, :n]
+    return pcd[idx.to(src_dev)], idx.to(src_dev)
+
+
+# ----------------------------------------------------------------------------------------------------
+# edges
+# ----------------------------------------------------------------------------------------------------
+class EdgeIndex:
+    """Edges grouped by receiver. receivers/senders: int32 [B,capacity] (-1 = unused slot); row_ptr: int32 [B,N+1]."""
+    __slots__ = ("B", "N", "capacity", "n_tool", "row_ptr", "n_edges", "receivers", "senders")
+
+    def dense(self):
+        """(Rr, Rs) float32 [B, max_e, N] one-hot matrices exactly as the reference returns them (host sync)."""
+        n = self.n_edges.cpu()
+        E = int(n.max())
+        Rr = torch.zeros((self.B, E, self.N), device=self.receivers.device)
+        Rs = torch.zeros((self.B, E, self.N), device=self.receivers.device)
+        for b in range(self.B):
+            e = int(n[b])
+            ar = torch.arange(e, device=Rr.device)
+            Rr[b, ar, self.receivers[b, :e].long()] = 1
+            Rs[b, ar, self.senders[b, :e].long()] = 1
+        return Rr, Rs
+
+
+def edge_capacity(N, n_tool, topk):
+    n_obj = N - n_tool
+    return n_obj * min(topk, max(n_obj, 1)) + 2 * n_obj * n_tool
+
+
+def construct_edges_index(states, adj_thresh, mask, tool_mask, topk=10, connect_all=False, n_tool=None, capacity=None):
+    """states [N,3] or [B,N,3]; mask/tool_mask bool; tools must be the last n_tool nodes (dataset.py:120-124).
+    n_tool=None reads it from tool_mask (one host sync, as the reference's `.item()` does)."""
+    st = _cuda_f32(states, "states")
+    if st.dim() == 2:
+        st, mask, tool_mask = st[None], mask[None], tool_mask[None]
+    B, N, _ = st.shape
+    dev = st.device
+    if n_tool is None:
+        nt = tool_mask.sum(dim=-1)
+        n_tool = int(nt.max().item())
+        assert n_tool == int(nt.min().item()), 'only support fixed number of tool particles'
+    if capacity is None:
+        capacity = edge_capacity(N, n_tool, topk)
+    m8 = mask.to(torch.uint8).contiguous()
+    t8 = tool_mask.to(torch.uint8).contiguous()
+    g = _lib.GsdGnnEdges()
+    g.B, g.N, g.n_tool, g.topk, g.connect_all, g.capacity = B, N, n_tool, int(topk), int(bool(connect_all)), int(capacity)
+    g.states, g.mask, g.tool_mask = st.data_ptr(), m8.data_ptr(), t8.data_ptr()
+    thr_t = None
+    if isinstance(adj_thresh, torch.Tensor):
+        thr_t = adj_thresh.to(dev).float().reshape(-1)
+        thr_t = (thr_t.expand(B) if thr_t.numel() == 1 else thr_t).contiguous()
+        g.adj_thresh = thr_t.data_ptr()
+    else:
+        g.adj_thresh = None
+        g.adj_thresh_sq_scalar = float(adj_thresh) * float(adj_thresh)
+    nbytes = C.c_size_t()
+    lib = _lib.lib()
+    _lib.check(lib.gsd_gnn_edges_workspace_bytes(B, N, C.byref(nbytes)), "gsd_gnn_edges_workspace_bytes")
+    e = EdgeIndex()
+    e.B, e.N, e.capacity, e.n_tool = B, N, int(capacity), n_tool
+    with torch.cuda.device(dev):
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        e.row_ptr = torch.empty((B, N + 1), dtype=torch.int32, device=dev)
+        e.n_edges = torch.empty(B, dtype=torch.int32, device=dev)
+        e.receivers = torch.empty((B, capacity), dtype=torch.int32, device=dev)
+        e.senders = torch.empty((B, capacity), dtype=torch.int32, device=dev)
+        g.ws, g.row_ptr, g.n_edges = ws.data_ptr(), e.row_ptr.data_ptr(), e.n_edges.data_ptr()
+        g.receivers, g.senders = e.receivers.data_ptr(), e.senders.data_ptr()
+        _lib.check(lib.gsd_gnn_build_edges(C.byref(g), _stream()), "gsd_gnn_build_edges")
+    return e
+
+
+def construct_edges_from_states(states, adj_thresh, mask, tool_mask, topk=10, connect_all=False):
+    """Reference contract: returns dense one-hot (Rr, Rs) of shape [n_rel, N]."""
+    Rr, Rs = construct_edges_index(states, adj_thresh, mask, tool_mask, topk, connect_all).dense()
+    return Rr[0], Rs[0]
+
+
+def construct_edges_from_states_batch(states, adj_thresh, mask, tool_mask, topk=10, connect_all=False):
+    """Reference contract: returns dense one-hot (Rr, Rs) of shape [B, max n_rel, N] (zero rows = padding)."""
+    return construct_edges_index(states, adj_thresh, mask, tool_mask, topk, connect_all).dense()
+
+
+def edge_index_from_dense(Rr, Rs, n_heavy=0):
+    """One-hot (Rr, Rs) [B,n_rel,N] (zero rows = padding, pad_torch of dataset.py:229-238) -> EdgeIndex, no host sync."""
+    B, E, N = Rr.shape
+    valid = Rr.sum(-1) > 0.5
+    recv = torch.where(valid, Rr.argmax(-1), torch.full_like(valid, N, dtype=torch.int64))
+    send = Rs.argmax(-1)
+    order = torch.argsort(recv, dim=1, stable=True)
+    recv_s = torch.gather(recv, 1, order)
+    send_s = torch.gather(send, 1, order)
+    ok = recv_s < N
+    e = EdgeIndex()
+    e.B, e.N, e.capacity, e.n_tool = B, N, E, n_heavy
+    e.receivers = torch.where(ok, recv_s, torch.full_like(recv_s, -1)).to(torch.int32).contiguous()
+    e.senders = torch.where(ok, send_s, torch.full_like(send_s, -1)).to(torch.int32).contiguous()
+    counts = torch.zeros((B, N + 1), dtype=torch.int64, device=Rr.device)
+    counts.scatter_add_(1, recv_s, torch.ones_like(recv_s))
+    rp = torch.zeros((B, N + 1), dtype=torch.int32, device=Rr.device)
+    rp[:, 1:] = torch.cumsum(counts[:, :N], 1).to(torch.int32)
+    e.row_ptr = rp.contiguous()
+    e.n_edges = rp[:, N].contiguous()
+    return e
+
+
+# ----------------------------------------------------------------------------------------------------
+# fused kernels as autograd functions
+# ----------------------------------------------------------------------------------------------------
+def edge_inputs(state, attrs, p_instance, edges, attr_dim_used=True, group=True):
+    """rel_inputs [B, capacity, 2*attr_dim + 1 + 3*n_his] (model.py:164-199)."""
+    B, n_his, N, _ = state.shape
+    attr_dim = attrs.shape[2]
+    n_p, n_inst = p_instance.shape[1], p_instance.shape[2]
+    width = 2 * attr_dim + 1 + 3 * n_his
+    out = torch.empty((B, edges.capacity, width), dtype=torch.float32, device=state.device)
+    with torch.cuda.device(state.device):
+        _lib.check(_lib.lib().gsd_gnn_edge_inputs(B, N, edges.capacity, n_his, attr_dim, n_inst, n_p, state.data_ptr(),
+                                                  attrs.data_ptr(), p_instance.data_ptr(), edges.receivers.data_ptr(),
+                                                  edges.senders.data_ptr(), out.data_ptr(), _stream()), "gsd_gnn_edge_inputs")
+    return out
+
+
+class _Aggregate(torch.autograd.Function):
+    """agg[node] = sum_e ReLU(A[e] + P[node,:F] + P[send(e),F:]).  Backward (for the GNN-training row) recomputes the
+    pre-activation with torch ops; it is not on the rollout path."""
+
+    @staticmethod
+    def forward(ctx, A, P, edges):
+        B, N, cap = edges.B, edges.N, edges.capacity
+        Fd = A.shape[-1]
+        A = A.contiguous()
+        P = P.contiguous()
+        lib = _lib.lib()
+        nbytes = C.c_size_t()
+        _lib.check(lib.gsd_gnn_aggregate_workspace_bytes(B, edges.n_tool, Fd, C.byref(nbytes)), "gsd_gnn_aggregate_workspace_bytes")
+        with torch.cuda.device(A.device):
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=A.device)
+            agg = torch.empty((B * N, Fd), dtype=torch.float32, device=A.device)
+            _lib.check(lib.gsd_gnn_aggregate(B, N, cap, Fd, edges.n_tool, edges.row_ptr.data_ptr(), edges.senders.data_ptr(),
+                                             A.data_ptr(), P.data_ptr(), ws.data_ptr(), agg.data_ptr(), _stream()), "gsd_gnn_aggregate")
+        ctx.save_for_backward(A, P)
+        ctx.edges = edges
+        return agg
+
+    @staticmethod
+    def backward(ctx, g):
+        A, P = ctx.saved_tensors
+        e = ctx.edges
+        B, N, cap = e.B, e.N, e.capacity
+        Fd = A.shape[-1]
+        valid = (e.receivers >= 0).reshape(-1)
+        base = (torch.arange(B, device=A.device) * N)[:, None]
+        r = (e.receivers.long().clamp(min=0) + base).reshape(-1)
+        s = (e.senders.long().clamp(min=0) + base).reshape(-1)
+        pre = A.reshape(-1, Fd) + P[r, :Fd] + P[s, Fd:]
+        gm = g[r] * (pre > 0) * valid[:, None]
+        gP = torch.zeros_like(P)
+        gP[:, :Fd].index_add_(0, r, gm)
+        gP[:, Fd:].index_add_(0, s, gm)
+        return gm.reshape(A.shape), gP, None
+
+
+# ----------------------------------------------------------------------------------------------------
+# model (state_dict identical to the reference: particle_encoder.model.{0,2,4}, relation_encoder.model.{0,2,4},
+# particle_propagator.linear, relation_propagator.linear, non_rigid_predictor.linear_{0,1,2})
+# ----------------------------------------------------------------------------------------------------
+class Encoder(nn.Module):
+    def __init__(self, input_size, hidden_size, output_size):
+        super().__init__()
+        self.model = nn.Sequential(nn.Linear(input_size, hidden_size), nn.ReLU(), nn.Linear(hidden_size, hidden_size), nn.ReLU(),
+                                   nn.Linear(hidden_size, output_size), nn.ReLU())
+        self.output_size = output_size
+
+    def forward(self, x):
+        s = x.size()
+        return self.model(x.reshape(-1, s[-1])).view(list(s[:-1]) + [self.output_size])
+
+
+class Propagator(nn.Module):
+    def __init__(self, input_size, output_size):
+        super().__init__()
+        self.linear = nn.Linear(input_size, output_size)
+        self.relu = nn.ReLU()
+        self.output_size = output_size
+
+
+class ParticlePredictor(nn.Module):
+    def __init__(self, input_size, hidden_size, output_size):
+        super().__init__()
+        self.linear_0 = nn.Linear(input_size, hidden_size)
+        self.linear_1 = nn.Linear(hidden_size, hidden_size)
+        self.linear_2 = nn.Linear(hidden_size, output_size)
+        self.relu = nn.ReLU()
+        self.output_size = output_size
+
+    def forward(self, x):
+        s = x.size()
+        x = x.reshape(-1, s[-1])
+        x = self.relu(self.linear_0(x))
+        x = self.relu(self.linear_1(x))
+        return self.linear_2(x).view(list(s[:-1]) + [self.output_size])
+
+
+class DynamicsPredictor(nn.Module):
+    def __init__(self, model_config, device):
+        super().__init__()
+        self.model_config = model_config
+        self.device = device
+        self.nf_particle = model_config['nf_particle']
+        self.nf_relation = model_config['nf_relation']
+        self.nf_effect = model_config['nf_effect']
+        self.motion_clamp = 100.0
+        self.motion_dim = model_config['motion_dim'] if 'motion_dim' in model_config else 0
+        input_dim = model_config['n_his'] * model_config['state_dim'] + (model_config['n_his'] - 1) * self.motion_dim + \
+            model_config['attr_dim'] + model_config['action_dim']
+        self.particle_encoder = Encoder(input_dim, self.nf_particle, self.nf_effect)
+        rel_input_dim = model_config['rel_attr_dim'] * 2 + model_config['rel_group_dim'] + \
+            model_config['rel_distance_dim'] * model_config['n_his']
+        self.relation_encoder = Encoder(rel_input_dim, self.nf_relation, self.nf_effect)
+        self.particle_propagator = Propagator(self.nf_effect * 2, self.nf_effect)
+        self.relation_propagator = Propagator(self.nf_effect * 3, self.nf_effect)
+        self.non_rigid_predictor = ParticlePredictor(self.nf_effect, self.nf_effect, 3)
+        if model_config.get('verbose', False):
+            print("DynamicsPredictor initialized")
+            print("particle input dim: {}, relation input dim: {}".format(input_dim, rel_input_dim))
+
+    def _particle_inputs(self, state, attrs, action):
+        cfg = self.model_config
+        B, N = attrs.size(0), attrs.size(1)
+        n_his, state_dim = cfg['n_his'], state.size(3)
+        state_t = state.transpose(1, 2).contiguous().view(B, N, n_his * state_dim)
+        p_inputs = attrs
+        if cfg['state_dim'] > 0:
+            if cfg['state_dim'] == 3:
+                p_inputs = torch.cat([p_inputs, state_t], 2)
+            elif cfg['state_dim'] == 1:
+                assert state_dim == 3
+                p_inputs = torch.cat([attrs, state_t.view(B, N, n_his, state_dim)[:, :, :, 2]], 2)
+        if self.motion_dim > 0:
+            assert self.motion_dim == 3
+            xyz = state_t.view(B, N, n_his, state_dim)
+            p_inputs = torch.cat([p_inputs, (xyz[:, :, 1:] - xyz[:, :, :-1]).reshape(B, N, (n_his - 1) * 3)], 2)
+        if cfg['action_dim'] > 0:
+            assert action is not None
+            p_inputs = torch.cat([p_inputs, action], 2)
+        return p_inputs
+
+    def forward(self, state, attrs, Rr, Rs, p_instance, action=None, **kwargs):
+        """Rr may be an EdgeIndex (fast path, Rs ignored) or the reference's dense one-hot matrices."""
+        cfg = self.model_config
+        if cfg['rel_attr_dim'] != attrs.size(2) or cfg['rel_group_dim'] != 1 or cfg['rel_distance_dim'] != 3:
+            raise NotImplementedError("only the reference's relation layout (attr, group diff, 3-d distance) is implemented")
+        state = _cuda_f32(state, "state")
+        attrs = _cuda_f32(attrs, "attrs")
+        p_instance = _cuda_f32(p_instance, "p_instance")
+        edges = Rr if isinstance(Rr, EdgeIndex) else edge_index_from_dense(Rr, Rs)
+        B, N = attrs.size(0), attrs.size(1)
+        n_p = p_instance.size(1)
+        Fd = self.nf_effect
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            p_inputs = self._particle_inputs(state, attrs, action)
+            rel_inputs = edge_inputs(state, attrs, p_instance, edges)
+            particle_encode = self.particle_encoder(p_inputs).reshape(B * N, Fd)
+            relation_encode = self.relation_encoder(rel_inputs).reshape(B * edges.capacity, Fd)
+            Wr, br = self.relation_propagator.linear.weight, self.relation_propagator.linear.bias
+            Wp, bp = self.particle_propagator.linear.weight, self.particle_propagator.linear.bias
+            A = F.linear(relation_encode, Wr[:, :Fd], br)            # pstep-invariant edge term
+            C0 = F.linear(particle_encode, Wp[:, :Fd], bp)           # pstep-invariant node term
+            W23 = torch.cat([Wr[:, Fd:2 * Fd], Wr[:, 2 * Fd:]], 0)   # [2F, F]: receiver | sender projections
+            Wp2_t = Wp[:, Fd:].t()
+            h = particle_encode
+            for _ in range(cfg['pstep']):
+                P = F.linear(h, W23)                                  # [B*N, 2F]
+                agg = _Aggregate.apply(A, P, edges)
+                h = torch.relu(torch.addmm(C0 + h, agg, Wp2_t))
+            h = h.view(B, N, Fd)
+            pred_motion = self.non_rigid_predictor(h[:, :n_p].contiguous())
+            pred_pos = state[:, -1, :n_p] + torch.clamp(pred_motion, max=self.motion_clamp, min=-self.motion_clamp)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+        return pred_pos, pred_motion
+
+
+# ----------------------------------------------------------------------------------------------------
+# rollout step (the loop body of DynamicsModule.rollout, /root/reference/src/render/dynamics_module.py:85-170,
+# without the Gaussian skinning which is a "next" row): edges -> model -> history shift
+# ----------------------------------------------------------------------------------------------------
+class GnnRollout:
+    """Autoregressive rollout with static shapes (CUDA-graph capturable): nobj object particles + 1 tool particle."""
+
+    def __init__(self, model, particle_pos, eef_pos, adj_thresh, topk, connect_all, use_graph=True):
+        self.model = model
+        dev = particle_pos.device
+        n_his = model.model_config['n_his']
+        self.nobj = particle_pos.shape[0]
+        N = self.nobj + 1
+        self.states = torch.zeros((1, n_his, N, 3), device=dev)
+        self.states[:, :, :self.nobj] = particle_pos
+        self.states[:, :, self.nobj:] = eef_pos
+        self.action = torch.zeros((1, N, 3), device=dev)
+        self.attrs = torch.zeros((1, N, 2), device=dev)
+        self.attrs[:, :self.nobj, 0] = 1.
+        self.attrs[:, self.nobj:, 1] = 1.
+        self.p_instance = torch.ones((1, self.nobj, 1), device=dev)
+        self.state_mask = torch.ones((1, N), dtype=torch.bool, device=dev)
+        self.eef_mask = torch.zeros((1, N), dtype=torch.bool, device=dev)
+        self.eef_mask[:, self.nobj] = True
+        self.adj_thresh, self.topk, self.connect_all = adj_thresh, topk, connect_all
+        self.eef_delta = torch.zeros(3, device=dev)
+        self.use_graph, self.graph, self.pred = use_graph, None, None
+
+    @torch.no_grad()
+    def _step_impl(self):
+        # tool moves by eef_delta; history shift of the tool row; action row of the tool
+        new_eef = self.states[0, -1, self.nobj] + self.eef_delta
+        self.action[0, self.nobj] = self.eef_delta
+        edges = construct_edges_index(self.states[:, -1], self.adj_thresh, self.state_mask, self.eef_mask, topk=self.topk,
+                                      connect_all=self.connect_all, n_tool=1)
+        pred, _ = self.model(self.states, self.attrs, edges, None, self.p_instance, action=self.action)
+        nxt = torch.cat([pred[0], new_eef[None]], 0)
+        self.states.copy_(torch.cat([self.states[:, 1:], nxt[None, None]], 1))
+        return pred
+
+    def step(self, eef_delta=None):
+        if eef_delta is not None:
+            self.eef_delta.copy_(eef_delta)
+        if not self.use_graph:
+            return self._step_impl()
+        if self.graph is None:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            keep = self.states.clone()
+            with torch.cuda.stream(s):
+                self._step_impl()
+            torch.cuda.current_stream().wait_stream(s)
+            self.states.copy_(keep)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.pred = self._step_impl()
+            self.states.copy_(keep)
+        self.graph.replay()
+        return self.pred

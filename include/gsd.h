@@ -178,6 +178,52 @@ int gsd_adam_step(const GsdAdam *a, void *stream);
 /* bookkeeping of get_loss (train_utils.py:243-245): seen = radii > 0; max_2D_radius = max(radii, max_2D_radius)[seen] */
 int gsd_track_update_radii(int32_t G, const int32_t *radii, float *max_2D_radius, uint8_t *seen, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Path B — GNN particle-dynamics step (replaces the one-hot torch.bmm formulation of
+ * /root/reference/src/gnn/model.py:112-246 and the dense N x N edge construction of
+ * /root/reference/src/data/dataset.py:88-216)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* construct_edges_from_states[_batch]: adjacency = (d^2 < r^2) AND top-k nearest (object-object block), tool<->object
+ * edges by radius or all (connect_all), no tool-tool edges; edges in adj.nonzero() order = grouped by receiver.
+ * Tools must be the last n_tool nodes (dataset.py:120-124). Outputs are index lists, never one-hot matrices:
+ * edges of batch element b occupy slots [b*capacity, b*capacity + n_edges[b]); unused slots hold -1. */
+typedef struct {
+    int32_t B, N, n_tool, topk, connect_all;
+    int32_t capacity;            /* edge slots per batch element */
+    const float *states;         /* [B,N,3] */
+    const uint8_t *mask;         /* [B,N] valid particle */
+    const uint8_t *tool_mask;    /* [B,N] */
+    const float *adj_thresh;     /* [B] radius per element, or NULL to use adj_thresh_sq_scalar */
+    float adj_thresh_sq_scalar;  /* float32(adj_thresh * adj_thresh) as the reference's scalar path computes it */
+    void *ws;                    /* gsd_gnn_edges_workspace_bytes() */
+    int32_t *row_ptr;            /* [B,N+1] CSR offsets by receiver */
+    int32_t *n_edges;            /* [B] */
+    int32_t *receivers;          /* [B,capacity] */
+    int32_t *senders;            /* [B,capacity] */
+} GsdGnnEdges;
+int gsd_gnn_edges_workspace_bytes(int32_t B, int32_t N, size_t *bytes);
+int gsd_gnn_build_edges(const GsdGnnEdges *g, void *stream);
+
+/* rel_inputs[b,e,:] = [attrs[recv] | attrs[send] | sum_k |g[recv,k]-g[send,k]| | (state[h,recv]-state[h,send]) h=0..n_his-1]
+ * (model.py:164-199); state is [B,n_his,N,3], g = p_instance padded with zeros for the n_s shape particles. */
+int gsd_gnn_edge_inputs(int32_t B, int32_t N, int32_t capacity, int32_t n_his, int32_t attr_dim, int32_t n_instance,
+                        int32_t n_p, const float *state, const float *attrs, const float *p_instance,
+                        const int32_t *receivers, const int32_t *senders, float *rel_inputs, void *stream);
+
+/* agg[b*N+r, :] = sum over incoming edges e of ReLU(A[b*cap+e, :] + P[b*N+r, 0:F] + P[b*N+send(e), F:2F])
+ * (relation propagator epilogue + Rr^T scatter-add of model.py:212-229). The last n_heavy rows of every element
+ * (tool nodes) are split over several CTAs and summed in fixed order. F multiple of 128, <= 512. */
+int gsd_gnn_aggregate_workspace_bytes(int32_t B, int32_t n_heavy, int32_t F, size_t *bytes);
+int gsd_gnn_aggregate(int32_t B, int32_t N, int32_t capacity, int32_t F, int32_t n_heavy, const int32_t *row_ptr,
+                      const int32_t *senders, const float *A, const float *P, void *ws, float *agg, void *stream);
+
+/* farthest point sampling, one CTA per batch element. radius <= 0: dgl.geometry.farthest_point_sampler(pos, npoints,
+ * start_idx) (squared distances, first maximum). radius > 0: fps_rad_idx_torch (data/utils.py:50-65): stops when the
+ * largest euclidean distance to the picked set is <= radius; count[b] = number of picks, unused outputs = -1. */
+int gsd_fps(int32_t B, int32_t N, int32_t npoints, float radius, const float *pos, const int64_t *start_idx,
+            int64_t *out_idx, int32_t *count, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

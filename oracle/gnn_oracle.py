@@ -1,0 +1,186 @@
+"""oracle/gnn_oracle.py — TEST INFRASTRUCTURE / CPU BASELINE, NOT PRODUCT CODE.
+
+CPU restatement (PyTorch, dense one-hot formulation exactly like the reference) of
+  DynamicsPredictor.forward              /root/reference/src/gnn/model.py:112-246
+  construct_edges_from_states            /root/reference/src/data/dataset.py:88-147
+  dgl.geometry.farthest_point_sampler    (DGL is un-vendored and unpinned: requirements.txt:4, README.md:23; restated as
+                                          batched FPS: idx[0]=start, dist=+inf, dist=min(dist,|x-x[idx]|^2), argmax first max)
+  fps_rad_idx_torch                      /root/reference/src/data/utils.py:50-65
+Pinned against the reference itself by tests/golden/gnn_golden.npz (tools/make_golden.py imports /root/reference/src/gnn/model.py
+and src/data/dataset.py).  The model is a pure function of a state_dict so that no nn.Module code is duplicated.
+Only tests/, smoke() and bench.py's cpu legs may import this module.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def model_dims(cfg):
+    motion = cfg.get('motion_dim', 0)
+    in_dim = cfg['n_his'] * cfg['state_dim'] + (cfg['n_his'] - 1) * motion + cfg['attr_dim'] + cfg['action_dim']
+    rel_dim = cfg['rel_attr_dim'] * 2 + cfg['rel_group_dim'] + cfg['rel_distance_dim'] * cfg['n_his']
+    return in_dim, rel_dim
+
+
+def make_state_dict(cfg, seed):
+    """Deterministic weights from numpy's PCG64 stream (stable across versions): U(-1/sqrt(fan_in), 1/sqrt(fan_in))."""
+    rng = np.random.default_rng(seed)
+    in_dim, rel_dim = model_dims(cfg)
+    nf = cfg['nf_effect']
+    shapes = {}
+    for name, d in (("particle_encoder", in_dim), ("relation_encoder", rel_dim)):
+        shapes[f"{name}.model.0"] = (cfg['nf_particle'] if name[0] == 'p' else cfg['nf_relation'], d)
+        h = shapes[f"{name}.model.0"][0]
+        shapes[f"{name}.model.2"] = (h, h)
+        shapes[f"{name}.model.4"] = (nf, h)
+    shapes["particle_propagator.linear"] = (nf, 2 * nf)
+    shapes["relation_propagator.linear"] = (nf, 3 * nf)
+    shapes["non_rigid_predictor.linear_0"] = (nf, nf)
+    shapes["non_rigid_predictor.linear_1"] = (nf, nf)
+    shapes["non_rigid_predictor.linear_2"] = (3, nf)
+    sd = {}
+    for k, (o, i) in shapes.items():
+        b = 1.0 / np.sqrt(i)
+        sd[k + ".weight"] = torch.tensor(rng.uniform(-b, b, size=(o, i)), dtype=torch.float32)
+        sd[k + ".bias"] = torch.tensor(rng.uniform(-b, b, size=(o,)), dtype=torch.float32)
+    return sd
+
+
+def _mlp3(sd, name, x):
+    for i in (0, 2, 4):
+        x = F.relu(F.linear(x, sd[f"{name}.model.{i}.weight"], sd[f"{name}.model.{i}.bias"]))
+    return x
+
+
+def forward(sd, cfg, state, attrs, Rr, Rs, p_instance, action=None):
+    """Dense one-hot forward, op for op as model.py:112-246. Returns (pred_pos, pred_motion)."""
+    n_his = cfg['n_his']
+    B, N = attrs.shape[:2]
+    n_p, n_inst = p_instance.shape[1], p_instance.shape[2]
+    n_s = N - n_p
+    sdim = state.shape[3]
+    Rr_t = Rr.transpose(1, 2).contiguous()
+    state_t = state.transpose(1, 2).contiguous().view(B, N, n_his * sdim)
+    p_inputs = attrs
+    if cfg['state_dim'] == 3:
+        p_inputs = torch.cat([p_inputs, state_t], 2)
+    elif cfg['state_dim'] == 1:
+        p_inputs = torch.cat([attrs, state_t.view(B, N, n_his, sdim)[:, :, :, 2]], 2)
+    if cfg.get('motion_dim', 0) > 0:
+        xyz = state_t.view(B, N, n_his, sdim)
+        p_inputs = torch.cat([p_inputs, (xyz[:, :, 1:] - xyz[:, :, :-1]).reshape(B, N, (n_his - 1) * 3)], 2)
+    if cfg['action_dim'] > 0:
+        p_inputs = torch.cat([p_inputs, action], 2)
+    g = torch.cat([p_instance, torch.zeros(B, n_s, n_inst, dtype=state.dtype)], 1)
+    rel_inputs = torch.cat([Rr.bmm(attrs), Rs.bmm(attrs), torch.sum(torch.abs(Rr.bmm(g) - Rs.bmm(g)), 2, keepdim=True),
+                            Rr.bmm(state_t) - Rs.bmm(state_t)], 2)
+    particle_encode = _mlp3(sd, "particle_encoder", p_inputs)
+    relation_encode = _mlp3(sd, "relation_encoder", rel_inputs)
+    effect = particle_encode
+    for _ in range(cfg['pstep']):
+        er, es = Rr.bmm(effect), Rs.bmm(effect)
+        rel = F.relu(F.linear(torch.cat([relation_encode, er, es], 2), sd["relation_propagator.linear.weight"],
+                              sd["relation_propagator.linear.bias"]))
+        agg = Rr_t.bmm(rel)
+        effect = F.relu(F.linear(torch.cat([particle_encode, agg], 2), sd["particle_propagator.linear.weight"],
+                                 sd["particle_propagator.linear.bias"]) + effect)
+    x = effect[:, :n_p].contiguous()
+    x = F.relu(F.linear(x, sd["non_rigid_predictor.linear_0.weight"], sd["non_rigid_predictor.linear_0.bias"]))
+    x = F.relu(F.linear(x, sd["non_rigid_predictor.linear_1.weight"], sd["non_rigid_predictor.linear_1.bias"]))
+    motion = F.linear(x, sd["non_rigid_predictor.linear_2.weight"], sd["non_rigid_predictor.linear_2.bias"])
+    return state[:, -1, :n_p] + torch.clamp(motion, max=100.0, min=-100.0), motion
+
+
+def construct_edges(states, adj_thresh, mask, tool_mask, topk=10, connect_all=False):
+    """Dense restatement of dataset.py:88-147. Returns (receivers, senders) int64 in adj.nonzero() order."""
+    N = states.shape[0]
+    diff = states[:, None, :] - states[None, :, :]
+    dis = torch.sum(diff ** 2, -1)
+    m12 = mask[:, None] & mask[None, :]
+    dis[~m12] = 1e10
+    t12 = tool_mask[:, None] & tool_mask[None, :]
+    dis[t12] = 1e10
+    adj = ((dis - adj_thresh * adj_thresh) < 0).float()
+    k = min(N, topk)
+    n_tool = int(tool_mask.sum())
+    dis_obj = dis[:-n_tool, :-n_tool] if n_tool > 0 else dis
+    idx = torch.topk(dis_obj, k=k, dim=-1, largest=False)[1]
+    tk = torch.zeros_like(dis_obj)
+    tk.scatter_(-1, idx, 1)
+    if n_tool > 0:
+        adj[:-n_tool, :-n_tool] = adj[:-n_tool, :-n_tool] * tk
+    else:
+        adj = adj * tk
+    if connect_all:
+        adj[tool_mask[:, None] & mask[None, :]] = 1.
+        adj[tool_mask[None, :] & mask[:, None]] = 1.
+        adj[t12] = 0.
+    rels = adj.nonzero()
+    return rels[:, 0], rels[:, 1]
+
+
+def one_hot_edges(recv, send, N):
+    E = recv.shape[0]
+    Rr, Rs = torch.zeros(E, N), torch.zeros(E, N)
+    ar = torch.arange(E)
+    Rr[ar, recv] = 1
+    Rs[ar, send] = 1
+    return Rr, Rs
+
+
+def fps(pos, npoints, start_idx=0):
+    """pos [B,N,3] -> int64 [B,npoints]."""
+    B, N, _ = pos.shape
+    out = torch.zeros(B, npoints, dtype=torch.int64)
+    for b in range(B):
+        dist = torch.full((N,), float("inf"))
+        cur = int(start_idx if isinstance(start_idx, int) else start_idx[b])
+        for i in range(npoints):
+            out[b, i] = cur
+            d = ((pos[b] - pos[b, cur]) ** 2).sum(-1)
+            dist = torch.minimum(dist, d)
+            cur = int(torch.argmax(dist))
+    return out
+
+
+def fps_radius(pcd, radius, start_idx):
+    idx = [int(start_idx)]
+    dist = torch.norm(pcd - pcd[idx[0]], dim=1)
+    while dist.max() > radius:
+        a = int(dist.argmax())
+        idx.append(a)
+        dist = torch.minimum(dist, torch.norm(pcd - pcd[a], dim=1))
+    return torch.tensor(idx)
+
+
+def sloth_cfg(nf=512):
+    return dict(verbose=False, nf_particle=nf, nf_relation=nf, nf_effect=nf, attr_dim=2, state_dim=1, motion_dim=3, action_dim=3,
+                pstep=3, rel_attr_dim=2, rel_group_dim=1, rel_distance_dim=3, n_his=3)
+
+
+def rope_cfg(nf=512):
+    return dict(verbose=False, nf_particle=nf, nf_relation=nf, nf_effect=nf, attr_dim=2, state_dim=0, action_dim=3, pstep=3,
+                rel_attr_dim=2, rel_group_dim=1, rel_distance_dim=3, n_his=3)
+
+
+def make_graph_inputs(n_obj, seed, kind="sloth", n_his=3):
+    """Seeded rollout-style inputs (dynamics_module.py:106-125): n_obj object particles + 1 tool particle (last)."""
+    rng = np.random.default_rng(seed)
+    if kind == "rope":
+        x = np.arange(n_obj) * 0.009
+        base = np.stack([x, np.zeros(n_obj), np.zeros(n_obj)], 1) + rng.normal(scale=0.002, size=(n_obj, 3))
+    else:
+        base = rng.uniform([0, 0, 0], [0.5, 0.5, 0.1], size=(n_obj, 3))
+    N = n_obj + 1
+    states = np.zeros((1, n_his, N, 3), np.float32)
+    for h in range(n_his):
+        states[0, h, :n_obj] = base + rng.normal(scale=0.001, size=(n_obj, 3)) * (n_his - 1 - h)
+        states[0, h, n_obj] = np.array([0.25, 0.25, 0.12]) + 0.005 * h * np.array([1.0, 0, 0])
+    action = np.zeros((1, N, 3), np.float32)
+    action[0, n_obj] = [0.005, 0, 0]
+    attrs = np.zeros((1, N, 2), np.float32)
+    attrs[0, :n_obj, 0] = 1
+    attrs[0, n_obj:, 1] = 1
+    t = torch.tensor
+    return dict(state=t(states), action=t(action), attrs=t(attrs), p_instance=torch.ones(1, n_obj, 1),
+                state_mask=torch.ones(N, dtype=torch.bool), eef_mask=torch.tensor([False] * n_obj + [True]))

@@ -1,0 +1,170 @@
+"""GPU parity tests of the GNN path (edge builder, FPS, fused forward) through the C ABI.
+
+Tolerances: edge lists and FPS indices are integer work -> bit-exact; pred_pos abs <= 1e-5 (fp32 with the
+relation-propagator weights split, TF32 off)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gnn_oracle as GO
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "gnn_golden.npz"))
+
+
+def _model(cfg, seed):
+    from gs_dynamics_b200.gnn import DynamicsPredictor
+    m = DynamicsPredictor(dict(cfg), torch.device("cuda")).cuda().eval()
+    m.load_state_dict(GO.make_state_dict(cfg, seed))  # the reference's state_dict layout loads unchanged
+    return m
+
+
+@pytest.mark.parametrize("tag", ["sloth", "rope"])
+def test_golden_fixture_edges_and_forward(tag):
+    from gs_dynamics_b200 import gnn
+    n_obj, topk, adj, conn, seed = GOLD[f"{tag}_cfg"]
+    n_obj, topk, seed = int(n_obj), int(topk), int(seed)
+    cfg = GO.sloth_cfg(128) if tag == "sloth" else GO.rope_cfg(128)
+    gi = GO.make_graph_inputs(n_obj, seed, tag)
+    e = gnn.construct_edges_index(gi["state"][0, -1].cuda(), float(adj), gi["state_mask"].cuda(), gi["eef_mask"].cuda(), topk=topk,
+                                  connect_all=bool(conn))
+    E = int(e.n_edges[0])
+    assert E == len(GOLD[f"{tag}_recv"])
+    assert np.array_equal(e.receivers[0, :E].cpu().numpy(), GOLD[f"{tag}_recv"])
+    assert np.array_equal(e.senders[0, :E].cpu().numpy(), GOLD[f"{tag}_send"])
+    assert bool((e.receivers[0, E:] == -1).all())
+    m = _model(cfg, seed)
+    with torch.no_grad():
+        pos, mot = m(gi["state"].cuda(), gi["attrs"].cuda(), e, None, gi["p_instance"].cuda(), action=gi["action"].cuda())
+    np.testing.assert_allclose(pos.cpu().numpy(), GOLD[f"{tag}_pred_pos"], atol=1e-5)
+    np.testing.assert_allclose(mot.cpu().numpy(), GOLD[f"{tag}_pred_motion"], atol=1e-5)
+    # reference calling convention: dense one-hot Rr / Rs (with zero padding rows, dataset.py:491-492)
+    Rr, Rs = gnn.construct_edges_from_states(gi["state"][0, -1].cuda(), float(adj), gi["state_mask"].cuda(), gi["eef_mask"].cuda(),
+                                             topk=topk, connect_all=bool(conn))
+    pad = torch.zeros(7, n_obj + 1, device="cuda")
+    with torch.no_grad():
+        pos2, _ = m(state=gi["state"].cuda(), attrs=gi["attrs"].cuda(), Rr=torch.cat([Rr, pad])[None], Rs=torch.cat([Rs, pad])[None],
+                    p_instance=gi["p_instance"].cuda(), action=gi["action"].cuda())
+    np.testing.assert_allclose(pos2.cpu().numpy(), GOLD[f"{tag}_pred_pos"], atol=1e-5)
+
+
+@pytest.mark.parametrize("kind,n_obj,topk,adj,conn", [("sloth", 2000, 8, 0.075, True), ("rope", 500, 8, 0.08, False),
+                                                       ("sloth", 37, 50, 0.2, True), ("rope", 1, 5, 0.08, True)])
+def test_edges_vs_oracle_full_size(kind, n_obj, topk, adj, conn):
+    from gs_dynamics_b200 import gnn
+    gi = GO.make_graph_inputs(n_obj, 5, kind)
+    recv, send = GO.construct_edges(gi["state"][0, -1], adj, gi["state_mask"], gi["eef_mask"], topk, conn)
+    e = gnn.construct_edges_index(gi["state"][0, -1].cuda(), adj, gi["state_mask"].cuda(), gi["eef_mask"].cuda(), topk=topk, connect_all=conn)
+    E = int(e.n_edges[0])
+    assert E == recv.numel()
+    assert np.array_equal(e.receivers[0, :E].cpu().numpy(), recv.numpy()) and np.array_equal(e.senders[0, :E].cpu().numpy(), send.numpy())
+    rp = e.row_ptr[0].cpu().numpy()
+    assert rp[-1] == E and np.array_equal(np.diff(rp), np.bincount(recv.numpy(), minlength=n_obj + 1))
+
+
+def test_edges_batch_masks_and_per_element_radius():
+    from gs_dynamics_b200 import gnn
+    g = torch.Generator().manual_seed(3)
+    B, N = 3, 64
+    states = torch.rand(B, N, 3, generator=g) * 0.3
+    mask = torch.ones(B, N, dtype=torch.bool)
+    mask[1, 40:60] = False          # padded (invalid) particles inside the object block
+    tool = torch.zeros(B, N, dtype=torch.bool)
+    tool[:, -2:] = True
+    thr = torch.tensor([0.08, 0.1, 0.06])
+    e = gnn.construct_edges_index(states.cuda(), thr.cuda(), mask.cuda(), tool.cuda(), topk=5, connect_all=False)
+    for b in range(B):
+        recv, send = GO.construct_edges(states[b], thr[b], mask[b], tool[b], 5, False)
+        E = int(e.n_edges[b])
+        assert E == recv.numel()
+        assert np.array_equal(e.receivers[b, :E].cpu().numpy(), recv.numpy()) and np.array_equal(e.senders[b, :E].cpu().numpy(), send.numpy())
+
+
+@pytest.mark.parametrize("kind,n_obj,topk,adj,conn", [("sloth", 2000, 8, 0.075, True), ("rope", 500, 8, 0.08, False)])
+def test_forward_vs_oracle_benchmark_sizes(kind, n_obj, topk, adj, conn):
+    """BASELINE configs: rope-500 / sloth-2k, nf = 512, seeded weights; oracle = dense one-hot formulation on the CPU."""
+    from gs_dynamics_b200 import gnn
+    cfg = GO.sloth_cfg(512) if kind == "sloth" else GO.rope_cfg(512)
+    gi = GO.make_graph_inputs(n_obj, 1, kind)
+    recv, send = GO.construct_edges(gi["state"][0, -1], adj, gi["state_mask"], gi["eef_mask"], topk, conn)
+    Rr, Rs = GO.one_hot_edges(recv, send, n_obj + 1)
+    sd = GO.make_state_dict(cfg, 0)
+    with torch.no_grad():
+        pos_o, mot_o = GO.forward(sd, cfg, gi["state"], gi["attrs"], Rr[None], Rs[None], gi["p_instance"], gi["action"])
+    m = _model(cfg, 0)
+    e = gnn.construct_edges_index(gi["state"][0, -1].cuda(), adj, gi["state_mask"].cuda(), gi["eef_mask"].cuda(), topk=topk,
+                                  connect_all=conn, n_tool=1)
+    with torch.no_grad():
+        pos, mot = m(gi["state"].cuda(), gi["attrs"].cuda(), e, None, gi["p_instance"].cuda(), action=gi["action"].cuda())
+    assert float((pos.cpu() - pos_o).abs().max()) <= 1e-5
+    assert float((mot.cpu() - mot_o).abs().max()) <= 1e-5
+
+
+def test_padding_rows_do_not_change_prediction_and_batching():
+    from gs_dynamics_b200 import gnn
+    cfg = GO.sloth_cfg(128)
+    m = _model(cfg, 3)
+    gis = [GO.make_graph_inputs(150, s, "sloth") for s in (1, 2)]
+    outs = []
+    for gi in gis:
+        e = gnn.construct_edges_index(gi["state"][0, -1].cuda(), 0.075, gi["state_mask"].cuda(), gi["eef_mask"].cuda(), topk=6, connect_all=True)
+        with torch.no_grad():
+            outs.append(m(gi["state"].cuda(), gi["attrs"].cuda(), e, None, gi["p_instance"].cuda(), action=gi["action"].cuda())[0])
+    cat = lambda k: torch.cat([g[k] for g in gis]).cuda()
+    st = cat("state")
+    eb = gnn.construct_edges_index(st[:, -1], 0.075, torch.stack([g["state_mask"] for g in gis]).cuda(),
+                                   torch.stack([g["eef_mask"] for g in gis]).cuda(), topk=6, connect_all=True)
+    with torch.no_grad():
+        pb, _ = m(st, cat("attrs"), eb, None, cat("p_instance"), action=cat("action"))
+    for b in range(2):
+        assert float((pb[b] - outs[b][0]).abs().max()) <= 2e-6
+
+
+def test_aggregate_backward_matches_autograd_reference():
+    from gs_dynamics_b200 import gnn
+    gi = GO.make_graph_inputs(60, 4, "sloth")
+    e = gnn.construct_edges_index(gi["state"][0, -1].cuda(), 0.1, gi["state_mask"].cuda(), gi["eef_mask"].cuda(), topk=5, connect_all=True)
+    Fd = 128
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randn(e.capacity, Fd, device="cuda", generator=g, requires_grad=True)
+    P = torch.randn(61, 2 * Fd, device="cuda", generator=g, requires_grad=True)
+    agg = gnn._Aggregate.apply(A, P, e)
+    w = torch.randn_like(agg)
+    (agg * w).sum().backward()
+    E = int(e.n_edges[0])
+    r, s = e.receivers[0, :E].long(), e.senders[0, :E].long()
+    A2, P2 = A.detach().clone().requires_grad_(True), P.detach().clone().requires_grad_(True)
+    ref = torch.zeros(61, Fd, device="cuda").index_add(0, r, torch.relu(A2[:E] + P2[r, :Fd] + P2[s, Fd:]))
+    (ref * w).sum().backward()
+    assert float((agg - ref).abs().max()) < 1e-4
+    assert float((A.grad - A2.grad).abs().max()) < 1e-5 and float((P.grad - P2.grad).abs().max()) < 1e-4
+
+
+def test_fps_matches_oracle_bit_exact():
+    from gs_dynamics_b200 import gnn
+    g = torch.Generator().manual_seed(1)
+    pos = torch.rand(2, 1000, 3, generator=g)
+    idx = gnn.farthest_point_sampler(pos.cuda(), 150, start_idx=0)
+    assert torch.equal(idx.cpu(), GO.fps(pos, 150, 0))
+    idx_cpu_in = gnn.farthest_point_sampler(pos, 20, start_idx=5)      # the reference passes CPU tensors
+    assert idx_cpu_in.device.type == "cpu" and torch.equal(idx_cpu_in, GO.fps(pos, 20, 5))
+    sub, ridx = gnn.fps_rad_idx_torch(pos[0].cuda(), 0.12, start_idx=7)
+    ref = GO.fps_radius(pos[0], 0.12, 7)
+    assert torch.equal(ridx.cpu(), ref) and torch.equal(sub.cpu(), pos[0][ref])
+
+
+def test_rollout_graph_matches_eager():
+    from gs_dynamics_b200 import gnn
+    cfg = GO.sloth_cfg(128)
+    m = _model(cfg, 2)
+    gi = GO.make_graph_inputs(400, 9, "sloth")
+    p0, eef = gi["state"][0, :, :400].cuda(), gi["state"][0, :, 400:].cuda()
+    ra = gnn.GnnRollout(m, p0, eef, 0.075, 6, True, use_graph=False)
+    rb = gnn.GnnRollout(m, p0, eef, 0.075, 6, True, use_graph=True)
+    d = torch.tensor([0.005, 0.0, 0.0], device="cuda")
+    for _ in range(5):
+        pa = ra.step(d).clone()
+        pb = rb.step(d).clone()
+    assert float((pa - pb).abs().max()) <= 1e-6 and float((ra.states - rb.states).abs().max()) <= 1e-6

@@ -78,3 +78,30 @@ for tag, (G, K, seed, fb) in dict(a=(96, 6, 1, 0.25), b=(64, 4, 2, 0.0)).items()
 dst = os.path.join(ROOT, "tests", "golden", "tracking_golden.npz")
 np.savez_compressed(dst, **out)
 print("wrote", dst, os.path.getsize(dst), "bytes")
+
+# =====================================================================================================================
+# gnn_golden.npz — the reference's DynamicsPredictor.forward (src/gnn/model.py) and construct_edges_from_states
+# (src/data/dataset.py) on seeded inputs (oracle.gnn_oracle.make_graph_inputs) with seeded weights
+# (oracle.gnn_oracle.make_state_dict, numpy PCG64), nf = 128 so that the fixture stays small.
+# =====================================================================================================================
+sys.path.insert(0, os.path.join(REF, "src"))
+from gnn.model import DynamicsPredictor as RefPredictor          # /root/reference/src/gnn/model.py:70
+from data.dataset import construct_edges_from_states as ref_edges  # /root/reference/src/data/dataset.py:88
+from oracle import gnn_oracle as GO
+
+gout = {}
+for tag, (kind, n_obj, topk, adj, conn, seed) in dict(sloth=("sloth", 300, 6, 0.075, True, 11), rope=("rope", 200, 5, 0.08, False, 12)).items():
+    cfg = GO.sloth_cfg(128) if kind == "sloth" else GO.rope_cfg(128)
+    model = RefPredictor(dict(cfg), torch.device("cpu"))
+    model.load_state_dict(GO.make_state_dict(cfg, seed))
+    model.eval()
+    gi = GO.make_graph_inputs(n_obj, seed, kind)
+    Rr, Rs = ref_edges(gi["state"][0, -1], adj, mask=gi["state_mask"], tool_mask=gi["eef_mask"], topk=topk, connect_all=conn)
+    with torch.no_grad():
+        pos, mot = model(state=gi["state"], attrs=gi["attrs"], Rr=Rr[None], Rs=Rs[None], p_instance=gi["p_instance"], action=gi["action"])
+    gout.update({f"{tag}_recv": Rr.argmax(-1).numpy().astype(np.int32), f"{tag}_send": Rs.argmax(-1).numpy().astype(np.int32),
+                 f"{tag}_pred_pos": pos.numpy(), f"{tag}_pred_motion": mot.numpy(),
+                 f"{tag}_cfg": np.array([n_obj, topk, adj, float(conn), seed])})
+dst = os.path.join(ROOT, "tests", "golden", "gnn_golden.npz")
+np.savez_compressed(dst, **gout)
+print("wrote", dst, os.path.getsize(dst), "bytes")
