@@ -374,8 +374,11 @@ class GnnRollout:
         self.nobj = particle_pos.shape[0]
         N = self.nobj + 1
         self.states = torch.zeros((1, n_his, N, 3), device=dev)
-        self.states[:, :, :self.nobj] = particle_pos
-        self.states[:, :, self.nobj:] = eef_pos
+        self.nobj = particle_pos.shape[-2]
+        N = self.nobj + 1
+        self.states = torch.zeros((1, n_his, N, 3), device=dev)
+        self.states[0, :, :self.nobj] = particle_pos          # [nobj,3] or a history [n_his,nobj,3]
+        self.states[0, :, self.nobj:] = eef_pos.reshape(-1, 1, 3) if eef_pos.dim() > 1 else eef_pos
         self.action = torch.zeros((1, N, 3), device=dev)
         self.attrs = torch.zeros((1, N, 2), device=dev)
         self.attrs[:, :self.nobj, 0] = 1.
