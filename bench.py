@@ -337,6 +337,63 @@ def run_reference(args):
     return line, rank, world
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# secondary metric: GNN rollout steps/sec (BASELINE.json configs[3]: sloth cfg, 2k particles, 8-NN, 50-step horizon)
+# ------------------------------------------------------------------------------------------------------------------
+def run_gnn_ours(device, steps=50, warmup=5, n_obj=2000, seed=1):
+    from gs_dynamics_b200 import gnn, workloads as GO
+    cfg = GO.sloth_cfg(512)
+    model = gnn.DynamicsPredictor(dict(cfg), device).to(device).eval()
+    model.load_state_dict(GO.make_state_dict(cfg, 0))
+    gi = GO.make_graph_inputs(n_obj, seed, "sloth")
+    p0, eef = gi["state"][0, :, :n_obj].to(device), gi["state"][0, :, n_obj:].to(device)
+    ro = gnn.GnnRollout(model, p0, eef, 0.075, 8, True, use_graph=True)
+    delta = torch.tensor([0.005, 0.0, 0.0], device=device)
+    for _ in range(warmup):
+        ro.step(delta)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ro.step(delta)
+    e1.record()
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) * 1e-3
+    # end to end: tool displacement comes from the host every step, predicted particle positions are read back
+    host_delta = torch.tensor([0.005, 0.0, 0.0]).pin_memory()
+    host_pred = torch.empty((1, n_obj, 3)).pin_memory()
+    t0 = time.time()
+    for _ in range(steps):
+        ro.eef_delta.copy_(host_delta, non_blocking=True)
+        pred = ro.step()
+        host_pred.copy_(pred, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    dt_e2e = time.time() - t0
+    return {"metric": "GNN steps/sec", "value": steps / dt, "unit": "steps/s", "ms_per_step": 1e3 * dt / steps, "steps": steps,
+            "config": {"workload": "predict.py GNN rollout step (edge build + forward + history shift), sloth cfg nf=512, "
+                                   "%d particles + 1 tool, 8-NN, connect_all, %d-step horizon" % (n_obj, steps)},
+            "e2e": {"value": steps / dt_e2e, "unit": "steps/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": n_obj * 12}}
+
+
+def run_gnn_cpu(budget_s=8.0, n_obj=2000, seed=1):
+    """The reference formulation (dense one-hot bmm, oracle/gnn_oracle.py) on the host cores, bounded sample."""
+    from oracle import gnn_oracle as GO
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = GO.sloth_cfg(512)
+    sd = GO.make_state_dict(cfg, 0)
+    gi = GO.make_graph_inputs(n_obj, seed, "sloth")
+    done, t0 = 0, time.time()
+    with torch.no_grad():
+        while done == 0 or time.time() - t0 < budget_s:
+            recv, send = GO.construct_edges(gi["state"][0, -1], 0.075, gi["state_mask"], gi["eef_mask"], 8, True)
+            Rr, Rs = GO.one_hot_edges(recv, send, n_obj + 1)
+            GO.forward(sd, cfg, gi["state"], gi["attrs"], Rr[None], Rs[None], gi["p_instance"], gi["action"])
+            done += 1
+    dt = time.time() - t0
+    return {"value": done / dt, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d steps in %.1f s (dense one-hot reference formulation on host cores)" % (done, dt)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -345,6 +402,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gaussians", type=int, default=50000)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
+    ap.add_argument("--no-gnn", action="store_true", help="skip the secondary GNN steps/sec measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -360,6 +418,13 @@ def main():
             done, dt, cores = cpu_iterations(args.gaussians, 10 ** 9, 1, budget_s=args.cpu_baseline_seconds)
             line["cpu_baseline"] = {"value": done / dt, "unit": "iters/s", "cores": cores, "kind": "port",
                                     "sample": "%d iterations in %.1f s of the same workload (oracle port on host cores)" % (done, dt)}
+            if not args.no_gnn:
+                try:
+                    g = run_gnn_ours(torch.device("cuda", 0))
+                    g["cpu_baseline"] = run_gnn_cpu()
+                    line["gnn"] = g
+                except Exception as ex:  # the secondary metric must never take the headline line down
+                    line["gnn"] = {"error": repr(ex)}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)

@@ -46,3 +46,71 @@ def tracking_problem(G, seed=0, num_knn=20, n_cams=4, width=640, height=480):
 def seg_target_from_mask(mask):
     """(seg, 0, 1-seg) colour coding of the reference's dataset loader (train_utils.py:71-75)."""
     return torch.stack((mask, torch.zeros_like(mask), 1 - mask))
+
+
+# ----------------------------------------------------------------------------------------------------
+# GNN workloads (configs 1 and 4 of SURVEY.md §8d): model configs of src/config/{rope,sloth}.yaml, seeded weights and
+# rollout-style graph inputs (dynamics_module.py:106-125)
+# ----------------------------------------------------------------------------------------------------
+def model_dims(cfg):
+    motion = cfg.get('motion_dim', 0)
+    in_dim = cfg['n_his'] * cfg['state_dim'] + (cfg['n_his'] - 1) * motion + cfg['attr_dim'] + cfg['action_dim']
+    rel_dim = cfg['rel_attr_dim'] * 2 + cfg['rel_group_dim'] + cfg['rel_distance_dim'] * cfg['n_his']
+    return in_dim, rel_dim
+
+
+def make_state_dict(cfg, seed):
+    """Deterministic weights from numpy's PCG64 stream (stable across versions): U(-1/sqrt(fan_in), 1/sqrt(fan_in))."""
+    rng = np.random.default_rng(seed)
+    in_dim, rel_dim = model_dims(cfg)
+    nf = cfg['nf_effect']
+    shapes = {}
+    for name, d in (("particle_encoder", in_dim), ("relation_encoder", rel_dim)):
+        shapes[f"{name}.model.0"] = (cfg['nf_particle'] if name[0] == 'p' else cfg['nf_relation'], d)
+        h = shapes[f"{name}.model.0"][0]
+        shapes[f"{name}.model.2"] = (h, h)
+        shapes[f"{name}.model.4"] = (nf, h)
+    shapes["particle_propagator.linear"] = (nf, 2 * nf)
+    shapes["relation_propagator.linear"] = (nf, 3 * nf)
+    shapes["non_rigid_predictor.linear_0"] = (nf, nf)
+    shapes["non_rigid_predictor.linear_1"] = (nf, nf)
+    shapes["non_rigid_predictor.linear_2"] = (3, nf)
+    sd = {}
+    for k, (o, i) in shapes.items():
+        b = 1.0 / np.sqrt(i)
+        sd[k + ".weight"] = torch.tensor(rng.uniform(-b, b, size=(o, i)), dtype=torch.float32)
+        sd[k + ".bias"] = torch.tensor(rng.uniform(-b, b, size=(o,)), dtype=torch.float32)
+    return sd
+
+
+def sloth_cfg(nf=512):
+    return dict(verbose=False, nf_particle=nf, nf_relation=nf, nf_effect=nf, attr_dim=2, state_dim=1, motion_dim=3, action_dim=3,
+                pstep=3, rel_attr_dim=2, rel_group_dim=1, rel_distance_dim=3, n_his=3)
+
+
+def rope_cfg(nf=512):
+    return dict(verbose=False, nf_particle=nf, nf_relation=nf, nf_effect=nf, attr_dim=2, state_dim=0, action_dim=3, pstep=3,
+                rel_attr_dim=2, rel_group_dim=1, rel_distance_dim=3, n_his=3)
+
+
+def make_graph_inputs(n_obj, seed, kind="sloth", n_his=3):
+    """Seeded rollout-style inputs (dynamics_module.py:106-125): n_obj object particles + 1 tool particle (last)."""
+    rng = np.random.default_rng(seed)
+    if kind == "rope":
+        x = np.arange(n_obj) * 0.009
+        base = np.stack([x, np.zeros(n_obj), np.zeros(n_obj)], 1) + rng.normal(scale=0.002, size=(n_obj, 3))
+    else:
+        base = rng.uniform([0, 0, 0], [0.5, 0.5, 0.1], size=(n_obj, 3))
+    N = n_obj + 1
+    states = np.zeros((1, n_his, N, 3), np.float32)
+    for h in range(n_his):
+        states[0, h, :n_obj] = base + rng.normal(scale=0.001, size=(n_obj, 3)) * (n_his - 1 - h)
+        states[0, h, n_obj] = np.array([0.25, 0.25, 0.12]) + 0.005 * h * np.array([1.0, 0, 0])
+    action = np.zeros((1, N, 3), np.float32)
+    action[0, n_obj] = [0.005, 0, 0]
+    attrs = np.zeros((1, N, 2), np.float32)
+    attrs[0, :n_obj, 0] = 1
+    attrs[0, n_obj:, 1] = 1
+    t = torch.tensor
+    return dict(state=t(states), action=t(action), attrs=t(attrs), p_instance=torch.ones(1, n_obj, 1),
+                state_mask=torch.ones(N, dtype=torch.bool), eef_mask=torch.tensor([False] * n_obj + [True]))
