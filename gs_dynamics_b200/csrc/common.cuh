@@ -50,18 +50,17 @@ struct GsdGeomWs { // per-Gaussian state
     float *depth;      // view-space z
     uint2 *rect;       // (minx | miny<<16, maxx | maxy<<16) in tiles, max exclusive
     uint32_t *tiles;   // tiles touched
-    uint32_t *offsets; // inclusive prefix sum of tiles
-    void *scan_tmp;
-    size_t scan_tmp_bytes;
+    uint32_t *slot_base; // first partial-gradient slot of this Gaussian's instances (disjoint ranges, arbitrary order)
     size_t total;
 };
 struct GsdBinWs {
-    uint64_t *keys_a, *keys_b;
-    uint32_t *vals_a, *vals_b;
-    uint2 *ranges;  // per tile [start,end)
-    float4 *records; // [capacity][4] packed per-instance records (sorted by tile, depth)
-    void *sort_tmp;
-    size_t sort_tmp_bytes;
+    uint64_t *keys;      // [capacity] (depth bits << 32 | gaussian id), grouped by tile, unsorted inside a tile
+    int32_t *tile_count; // [tiles] instances per tile (pass 1)
+    int32_t *tile_fill;  // [tiles] fill cursors (pass 2)
+    int32_t *tile_order; // [tiles] tile ids by descending instance count (longest-processing-time-first schedule)
+    int32_t *counters;   // [8] 0: next tile (sort/pack) 1: next tile (blend fwd) 2: next tile (blend bwd)
+    uint2 *ranges;       // per tile [start,end) clipped to capacity
+    float4 *records;     // 4 SoA planes of [capacity] float4: packed per-instance records sorted by (tile, depth, id)
     size_t total;
 };
 struct GsdImgWs {
@@ -78,7 +77,9 @@ struct GsdRenderParams {
     const uint2 *ranges;
     const float4 *planes; // 4 planes of [plane_stride] float4
     int64_t plane_stride;
-    int W, H, gx;
+    int W, H, gx, n_tiles;
+    const int32_t *tile_order; // LPT schedule
+    int32_t *next_tile;        // work-queue cursor of this launch (zero on entry)
     const float *bg0, *bg1; // device [3] each; bg1 may be null
     float *out_color; // [CH,H,W]
     float *out_depth; // [H,W]

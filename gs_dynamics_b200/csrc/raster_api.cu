@@ -5,9 +5,8 @@
 #include "common.cuh"
 
 // launchers implemented in the other translation units
-int gsd_launch_preprocess(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, cudaStream_t st);
+int gsd_launch_preprocess(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, int32_t *tile_count, cudaStream_t st);
 int gsd_launch_mark_visible(int G, const GsdCam &cam, const float *means3D, uint8_t *vis, cudaStream_t st);
-int gsd_launch_scan(int G, const GsdGeomWs &g, int64_t capacity, int32_t *status, cudaStream_t st);
 int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, const GsdBinWs &b, cudaStream_t st);
 int gsd_launch_render_fwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st);
 int gsd_launch_render_bwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st);
@@ -79,8 +78,8 @@ extern "C" int gsd_raster_count_instances(const GsdRasterFwd *a, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GsdGeomWs g;
     if ((rc = gsd_carve_geom(a->G, a->geom_ws, &g))) return rc;
-    if ((rc = gsd_launch_preprocess(a->G, cam, a, g, st))) return rc;
-    return gsd_launch_scan(a->G, g, 0x7fffffffLL, a->status, st);
+    GSD_CUDA_CHECK(cudaMemsetAsync(a->status, 0, GSD_STATUS_WORDS * 4, st));
+    return gsd_launch_preprocess(a->G, cam, a, g, nullptr, st);
 }
 
 extern "C" int gsd_raster_forward(const GsdRasterFwd *a, void *stream) {
@@ -101,15 +100,18 @@ extern "C" int gsd_raster_forward(const GsdRasterFwd *a, void *stream) {
     if ((rc = gsd_carve_geom(a->G, a->geom_ws, &g))) return rc;
     if ((rc = gsd_carve_bin(a->capacity, tiles, a->binning_ws, &b))) return rc;
     if ((rc = gsd_carve_img(a->W, a->H, a->image_ws, &im))) return rc;
-    if ((rc = gsd_launch_preprocess(a->G, cam, a, g, st))) return rc;
-    if ((rc = gsd_launch_scan(a->G, g, a->capacity, a->status, st))) return rc;
+    GSD_CUDA_CHECK(cudaMemsetAsync(a->status, 0, GSD_STATUS_WORDS * 4, st));
+    // tile_count | tile_fill | counters are contiguous: one memset
+    GSD_CUDA_CHECK(cudaMemsetAsync(b.tile_count, 0, (size_t)((char *)(b.counters + 8) - (char *)b.tile_count), st));
+    if ((rc = gsd_launch_preprocess(a->G, cam, a, g, b.tile_count, st))) return rc;
     if ((rc = gsd_launch_binning(a->G, cam, a, g, b, st))) return rc;
     GsdRenderParams p;
     memset(&p, 0, sizeof(p));
     p.ranges = b.ranges;
     p.planes = b.records;
     p.plane_stride = a->capacity > 0 ? a->capacity : 1;
-    p.W = a->W; p.H = a->H; p.gx = cam.gx;
+    p.W = a->W; p.H = a->H; p.gx = cam.gx; p.n_tiles = tiles;
+    p.tile_order = b.tile_order; p.next_tile = b.counters + 1;
     p.bg0 = a->bg0; p.bg1 = a->n_sets == 2 ? a->bg1 : nullptr;
     p.out_color = a->out_color;
     p.out_depth = a->out_depth;
@@ -147,7 +149,8 @@ static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages)
     p.ranges = b.ranges;
     p.planes = b.records;
     p.plane_stride = f->capacity > 0 ? f->capacity : 1;
-    p.W = f->W; p.H = f->H; p.gx = cam.gx;
+    p.W = f->W; p.H = f->H; p.gx = cam.gx; p.n_tiles = tiles;
+    p.tile_order = b.tile_order; p.next_tile = b.counters + 2;
     p.bg0 = f->bg0; p.bg1 = f->n_sets == 2 ? f->bg1 : nullptr;
     p.out_color = f->out_color;
     p.out_depth = f->out_depth;
@@ -155,8 +158,10 @@ static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages)
     p.n_contrib = im.n_contrib;
     p.dL_dcolor = a->dL_dcolor;
     p.partials = (float *)a->partial_ws;
-    if ((stages & 1) && f->G > 0 && f->capacity > 0)
+    if ((stages & 1) && f->G > 0 && f->capacity > 0) {
+        GSD_CUDA_CHECK(cudaMemsetAsync(b.counters + 2, 0, 4, st));
         if ((rc = gsd_launch_render_bwd(p, tiles, f->n_sets, st))) return rc;
+    }
     if (stages & 2) return gsd_launch_preprocess_bwd(f->G, cam, a, g, st);
     return GSD_OK;
 }

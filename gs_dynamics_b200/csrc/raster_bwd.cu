@@ -10,7 +10,7 @@ template <int CH>
 __global__ void __launch_bounds__(256)
 gsd_preprocess_bwd_kernel(int G, GsdCam cam, int64_t capacity, const float *__restrict__ means3D,
                           const float *__restrict__ scales, const float *__restrict__ rotations,
-                          const int32_t *__restrict__ radii, const uint32_t *__restrict__ offsets,
+                          const int32_t *__restrict__ radii, const uint32_t *__restrict__ slot_base,
                           const uint32_t *__restrict__ tiles, const float4 *__restrict__ partials,
                           float *__restrict__ dmeans3D, float *__restrict__ dmeans2D, float *__restrict__ dcolors0,
                           float *__restrict__ dcolors1, float *__restrict__ dopac, float *__restrict__ dscales,
@@ -27,7 +27,7 @@ gsd_preprocess_bwd_kernel(int G, GsdCam cam, int64_t capacity, const float *__re
     const bool vis = radii[i] > 0;
     if (vis) {
         uint32_t nt = tiles[i];
-        int64_t s0 = (int64_t)offsets[i] - nt;
+        int64_t s0 = (int64_t)slot_base[i];
         for (uint32_t k = 0; k < nt; ++k) {
             int64_t s = s0 + k;
             if (s >= capacity) break;
@@ -159,11 +159,11 @@ int gsd_launch_preprocess_bwd(int G, const GsdCam &cam, const GsdRasterBwd *a, c
     int blocks = (G + 255) / 256;
     if (f.n_sets == 1)
         gsd_preprocess_bwd_kernel<3><<<blocks, 256, 0, st>>>(
-            G, cam, f.capacity, f.means3D, f.scales, f.rotations, f.radii, g.offsets, g.tiles, (const float4 *)a->partial_ws,
+            G, cam, f.capacity, f.means3D, f.scales, f.rotations, f.radii, g.slot_base, g.tiles, (const float4 *)a->partial_ws,
             a->dL_dmeans3D, a->dL_dmeans2D, a->dL_dcolors0, a->dL_dcolors1, a->dL_dopacities, a->dL_dscales, a->dL_drotations);
     else
         gsd_preprocess_bwd_kernel<6><<<blocks, 256, 0, st>>>(
-            G, cam, f.capacity, f.means3D, f.scales, f.rotations, f.radii, g.offsets, g.tiles, (const float4 *)a->partial_ws,
+            G, cam, f.capacity, f.means3D, f.scales, f.rotations, f.radii, g.slot_base, g.tiles, (const float4 *)a->partial_ws,
             a->dL_dmeans3D, a->dL_dmeans2D, a->dL_dcolors0, a->dL_dcolors1, a->dL_dopacities, a->dL_dscales, a->dL_drotations);
     GSD_LAUNCH_CHECK();
     return GSD_OK;

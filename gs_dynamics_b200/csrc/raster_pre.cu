@@ -15,17 +15,18 @@ __global__ void __launch_bounds__(256)
 gsd_preprocess_kernel(int G, GsdCam cam, const float *__restrict__ means3D, const float *__restrict__ opacities,
                       const float *__restrict__ scales, const float *__restrict__ rotations, float2 *__restrict__ xy,
                       float4 *__restrict__ conic_o, float2 *__restrict__ ext, float *__restrict__ depth,
-                      uint2 *__restrict__ rect, uint32_t *__restrict__ tiles, int32_t *__restrict__ radii) {
+                      uint2 *__restrict__ rect, uint32_t *__restrict__ tiles, uint32_t *__restrict__ slot_base,
+                      int32_t *__restrict__ radii, int32_t *__restrict__ tile_count, uint32_t *__restrict__ counter) {
     __shared__ float sVP[32];
     if (threadIdx.x < 16) sVP[threadIdx.x] = cam.view[threadIdx.x];
     else if (threadIdx.x < 32) sVP[threadIdx.x] = cam.proj[threadIdx.x - 16];
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G) return;
+    const bool in_range = i < G;
     int rad_out = 0;
     uint32_t tiles_out = 0;
     uint2 rect_out = make_uint2(0u, 0u);
-    do {
+    if (in_range) do {
         float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
         const float *V = sVP, *P = sVP + 16;
         float3 pv = xform4x3(V, p);
@@ -115,10 +116,29 @@ gsd_preprocess_kernel(int G, GsdCam cam, const float *__restrict__ means3D, cons
         rad_out = (int)rad;
         rect_out = make_uint2((uint32_t)minx | ((uint32_t)miny << 16), (uint32_t)maxx | ((uint32_t)maxy << 16));
         tiles_out = (uint32_t)((maxx - minx) * (maxy - miny));
+        // per-tile instance counts (binning pass 1)
+        if (tile_count)
+            for (int ty = miny; ty < maxy; ++ty)
+                for (int tx = minx; tx < maxx; ++tx) atomicAdd(&tile_count[ty * cam.gx + tx], 1);
     } while (0);
-    radii[i] = rad_out;
-    tiles[i] = tiles_out;
-    rect[i] = rect_out;
+    // slot range of this Gaussian's instances: warp-aggregated claim on the global instance counter. The assignment
+    // order is arbitrary, the ranges are disjoint and the per-Gaussian order inside a range is fixed (tile rank).
+    const int lane = threadIdx.x & 31;
+    uint32_t incl = tiles_out;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    uint32_t base = 0;
+    if (lane == 31 && incl > 0) base = atomicAdd(counter, incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (in_range) {
+        radii[i] = rad_out;
+        tiles[i] = tiles_out;
+        rect[i] = rect_out;
+        slot_base[i] = base + incl - tiles_out;
+    }
 }
 
 __global__ void gsd_mark_visible_kernel(int G, GsdCam cam, const float *__restrict__ means3D, uint8_t *__restrict__ vis) {
@@ -132,11 +152,14 @@ __global__ void gsd_mark_visible_kernel(int G, GsdCam cam, const float *__restri
     vis[i] = pv.z > 0.2f ? 1 : 0;
 }
 
-int gsd_launch_preprocess(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, cudaStream_t st) {
+// tile_count may be null (count-only call). status[0] must be zero on entry: it accumulates the instance count R.
+int gsd_launch_preprocess(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, int32_t *tile_count,
+                          cudaStream_t st) {
     if (G == 0) return GSD_OK;
     int blocks = (G + 255) / 256;
     gsd_preprocess_kernel<<<blocks, 256, 0, st>>>(G, cam, a->means3D, a->opacities, a->scales, a->rotations, g.xy,
-                                                   g.conic_o, g.ext, g.depth, g.rect, g.tiles, a->radii);
+                                                   g.conic_o, g.ext, g.depth, g.rect, g.tiles, g.slot_base, a->radii,
+                                                   tile_count, (uint32_t *)a->status);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
