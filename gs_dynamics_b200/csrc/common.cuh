@@ -50,36 +50,50 @@ struct GsdGeomWs { // per-Gaussian state
     float *depth;      // view-space z
     uint2 *rect;       // (minx | miny<<16, maxx | maxy<<16) in tiles, max exclusive
     uint32_t *tiles;   // tiles touched
-    uint32_t *slot_base; // first partial-gradient slot of this Gaussian's instances (disjoint ranges, arbitrary order)
+    uint32_t *slot_base; // first partial-gradient slot of this Gaussian's instances (= its position in Gaussian order)
+    uint32_t *block_sum; // [ceil(G/256)] instances per preprocess block
+    uint32_t *block_base;// [ceil(G/256)] exclusive scan of block_sum
     size_t total;
 };
+#define GSD_CHUNK 256      // records per blend work item (tile lists are split into chunks processed in parallel)
+#define GSD_BIN_BLOCK 1024 // Gaussians per binning block
 struct GsdBinWs {
-    uint64_t *keys;      // [capacity] (depth bits << 32 | gaussian id), grouped by tile, unsorted inside a tile
-    int32_t *tile_count; // [tiles] instances per tile (pass 1)
-    int32_t *tile_fill;  // [tiles] fill cursors (pass 2)
-    int32_t *tile_order; // [tiles] tile ids by descending instance count (longest-processing-time-first schedule)
-    int32_t *counters;   // [8] 0: next tile (sort/pack) 1: next tile (blend fwd) 2: next tile (blend bwd)
+    int n_bb;            // binning blocks = ceil(G / GSD_BIN_BLOCK)
+    int max_items;       // upper bound of blend work items = capacity / GSD_CHUNK + tiles
+    int32_t *table;      // [tiles][n_bb] per (tile, binning block) instance counts -> exclusive scan (tile-major)
     uint2 *ranges;       // per tile [start,end) clipped to capacity
+    int32_t *chunk_ptr;  // [tiles+1] exclusive scan of chunks per tile
+    int32_t *item_tile;  // [max_items] tile of each work item
+    int32_t *counters;   // [8] 0: n_items
+    uint64_t *keys;      // [capacity] (depth bits << 32 | gaussian id), grouped by tile, unsorted inside a tile
     float4 *records;     // 4 SoA planes of [capacity] float4: packed per-instance records sorted by (tile, depth, id)
     size_t total;
 };
 struct GsdImgWs {
     float *final_T;
     int32_t *n_contrib;
+    float *chunk_state; // [max_items][5 + 3 n_sets][256]
+    float *term_state;  // [tiles][4 + 3 n_sets][256]
     size_t total;
 };
+size_t gsd_chunk_state_floats(int n_sets, int max_items);
+size_t gsd_term_state_floats(int n_sets, int tiles);
 
 int gsd_carve_geom(int G, void *base, GsdGeomWs *ws);
-int gsd_carve_bin(int64_t capacity, int tiles, void *base, GsdBinWs *ws);
-int gsd_carve_img(int W, int H, void *base, GsdImgWs *ws);
+int gsd_carve_bin(int G, int64_t capacity, int tiles, void *base, GsdBinWs *ws);
+int gsd_carve_img(int W, int H, int n_sets, int max_items, void *base, GsdImgWs *ws);
 
 struct GsdRenderParams {
     const uint2 *ranges;
     const float4 *planes; // 4 planes of [plane_stride] float4
     int64_t plane_stride;
     int W, H, gx, n_tiles;
-    const int32_t *tile_order; // LPT schedule
-    int32_t *next_tile;        // work-queue cursor of this launch (zero on entry)
+    const int32_t *chunk_ptr;  // [tiles+1]
+    const int32_t *item_tile;  // [n_items]
+    const int32_t *n_items;    // device scalar
+    float *chunk_state;        // per work item: SoA fields x 256 pixels (see raster_render.cu)
+    float *term_state;         // per tile: terminal record of each pixel
+    int max_items;
     const float *bg0, *bg1; // device [3] each; bg1 may be null
     float *out_color; // [CH,H,W]
     float *out_depth; // [H,W]

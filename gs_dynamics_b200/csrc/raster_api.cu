@@ -5,7 +5,8 @@
 #include "common.cuh"
 
 // launchers implemented in the other translation units
-int gsd_launch_preprocess(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, int32_t *tile_count, cudaStream_t st);
+int gsd_launch_preprocess(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, cudaStream_t st);
+int gsd_launch_count(int G, const GsdGeomWs &g, int32_t *status, cudaStream_t st);
 int gsd_launch_mark_visible(int G, const GsdCam &cam, const float *means3D, uint8_t *vis, cudaStream_t st);
 int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, const GsdBinWs &b, cudaStream_t st);
 int gsd_launch_render_fwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st);
@@ -56,13 +57,13 @@ static int make_cam(const GsdRasterFwd *a, GsdCam *cam) {
 
 extern "C" int gsd_raster_workspace_bytes(int32_t G, int32_t W, int32_t H, int32_t n_sets, int64_t capacity, size_t out[4]) {
     if (G < 0 || W <= 0 || H <= 0 || capacity < 0 || !out) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
-    (void)n_sets;
+    if (n_sets != 1 && n_sets != 2) { gsd_set_error("n_sets must be 1 or 2"); return GSD_ERR_INVALID; }
     GsdGeomWs g; GsdBinWs b; GsdImgWs im;
     int rc;
     if ((rc = gsd_carve_geom(G, nullptr, &g))) return rc;
     int tiles = ((W + GSD_TILE - 1) / GSD_TILE) * ((H + GSD_TILE - 1) / GSD_TILE);
-    if ((rc = gsd_carve_bin(capacity, tiles, nullptr, &b))) return rc;
-    if ((rc = gsd_carve_img(W, H, nullptr, &im))) return rc;
+    if ((rc = gsd_carve_bin(G, capacity, tiles, nullptr, &b))) return rc;
+    if ((rc = gsd_carve_img(W, H, n_sets, b.max_items, nullptr, &im))) return rc;
     out[0] = g.total;
     out[1] = b.total;
     out[2] = im.total;
@@ -79,7 +80,8 @@ extern "C" int gsd_raster_count_instances(const GsdRasterFwd *a, void *stream) {
     GsdGeomWs g;
     if ((rc = gsd_carve_geom(a->G, a->geom_ws, &g))) return rc;
     GSD_CUDA_CHECK(cudaMemsetAsync(a->status, 0, GSD_STATUS_WORDS * 4, st));
-    return gsd_launch_preprocess(a->G, cam, a, g, nullptr, st);
+    if ((rc = gsd_launch_preprocess(a->G, cam, a, g, st))) return rc;
+    return gsd_launch_count(a->G, g, a->status, st);
 }
 
 extern "C" int gsd_raster_forward(const GsdRasterFwd *a, void *stream) {
@@ -98,12 +100,10 @@ extern "C" int gsd_raster_forward(const GsdRasterFwd *a, void *stream) {
     GsdGeomWs g; GsdBinWs b; GsdImgWs im;
     const int tiles = cam.gx * cam.gy;
     if ((rc = gsd_carve_geom(a->G, a->geom_ws, &g))) return rc;
-    if ((rc = gsd_carve_bin(a->capacity, tiles, a->binning_ws, &b))) return rc;
-    if ((rc = gsd_carve_img(a->W, a->H, a->image_ws, &im))) return rc;
+    if ((rc = gsd_carve_bin(a->G, a->capacity, tiles, a->binning_ws, &b))) return rc;
+    if ((rc = gsd_carve_img(a->W, a->H, a->n_sets, b.max_items, a->image_ws, &im))) return rc;
     GSD_CUDA_CHECK(cudaMemsetAsync(a->status, 0, GSD_STATUS_WORDS * 4, st));
-    // tile_count | tile_fill | counters are contiguous: one memset
-    GSD_CUDA_CHECK(cudaMemsetAsync(b.tile_count, 0, (size_t)((char *)(b.counters + 8) - (char *)b.tile_count), st));
-    if ((rc = gsd_launch_preprocess(a->G, cam, a, g, b.tile_count, st))) return rc;
+    if ((rc = gsd_launch_preprocess(a->G, cam, a, g, st))) return rc;
     if ((rc = gsd_launch_binning(a->G, cam, a, g, b, st))) return rc;
     GsdRenderParams p;
     memset(&p, 0, sizeof(p));
@@ -111,7 +111,8 @@ extern "C" int gsd_raster_forward(const GsdRasterFwd *a, void *stream) {
     p.planes = b.records;
     p.plane_stride = a->capacity > 0 ? a->capacity : 1;
     p.W = a->W; p.H = a->H; p.gx = cam.gx; p.n_tiles = tiles;
-    p.tile_order = b.tile_order; p.next_tile = b.counters + 1;
+    p.chunk_ptr = b.chunk_ptr; p.item_tile = b.item_tile; p.n_items = b.counters + 0; p.max_items = b.max_items;
+    p.chunk_state = im.chunk_state; p.term_state = im.term_state;
     p.bg0 = a->bg0; p.bg1 = a->n_sets == 2 ? a->bg1 : nullptr;
     p.out_color = a->out_color;
     p.out_depth = a->out_depth;
@@ -142,15 +143,16 @@ static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages)
     GsdGeomWs g; GsdBinWs b; GsdImgWs im;
     const int tiles = cam.gx * cam.gy;
     if ((rc = gsd_carve_geom(f->G, f->geom_ws, &g))) return rc;
-    if ((rc = gsd_carve_bin(f->capacity, tiles, f->binning_ws, &b))) return rc;
-    if ((rc = gsd_carve_img(f->W, f->H, f->image_ws, &im))) return rc;
+    if ((rc = gsd_carve_bin(f->G, f->capacity, tiles, f->binning_ws, &b))) return rc;
+    if ((rc = gsd_carve_img(f->W, f->H, f->n_sets, b.max_items, f->image_ws, &im))) return rc;
     GsdRenderParams p;
     memset(&p, 0, sizeof(p));
     p.ranges = b.ranges;
     p.planes = b.records;
     p.plane_stride = f->capacity > 0 ? f->capacity : 1;
     p.W = f->W; p.H = f->H; p.gx = cam.gx; p.n_tiles = tiles;
-    p.tile_order = b.tile_order; p.next_tile = b.counters + 2;
+    p.chunk_ptr = b.chunk_ptr; p.item_tile = b.item_tile; p.n_items = b.counters + 0; p.max_items = b.max_items;
+    p.chunk_state = im.chunk_state; p.term_state = im.term_state;
     p.bg0 = f->bg0; p.bg1 = f->n_sets == 2 ? f->bg1 : nullptr;
     p.out_color = f->out_color;
     p.out_depth = f->out_depth;
@@ -158,10 +160,8 @@ static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages)
     p.n_contrib = im.n_contrib;
     p.dL_dcolor = a->dL_dcolor;
     p.partials = (float *)a->partial_ws;
-    if ((stages & 1) && f->G > 0 && f->capacity > 0) {
-        GSD_CUDA_CHECK(cudaMemsetAsync(b.counters + 2, 0, 4, st));
+    if ((stages & 1) && f->G > 0 && f->capacity > 0)
         if ((rc = gsd_launch_render_bwd(p, tiles, f->n_sets, st))) return rc;
-    }
     if (stages & 2) return gsd_launch_preprocess_bwd(f->G, cam, a, g, st);
     return GSD_OK;
 }

@@ -1,20 +1,26 @@
-// raster_bin.cu — tile binning without a global sort:
-//   pass 1 (in the preprocess kernel)  per-tile instance counts + per-Gaussian slot ranges
-//   tile_scan     one CTA: exclusive scan of the tile counts -> per-tile ranges, and the tile schedule sorted by
-//                 descending count (longest-processing-time-first) for the persistent blend kernels
-//   fill          one thread per Gaussian: append (depth bits << 32 | id) to each touched tile's segment
-//   sort_pack     one CTA per tile: bitonic sort of the segment in shared memory (ties by Gaussian id, i.e. exactly the
-//                 order of the reference's stable (tile | depth) radix sort), then gather the Gaussian data into the four
-//                 SoA record planes that the blend kernels stream with 1-D bulk (TMA) copies
+// raster_bin.cu — tile binning without a global sort and without global atomics:
+//   (preprocess)  per-Gaussian tile rectangles + per-256-block instance sums
+//   hist          one CTA per 1024 Gaussians: shared-memory histogram of touched tiles -> table[tile][block]
+//   scan          one CTA: exclusive scans of the block sums (slot bases, R), of the tile-major table (scatter bases, per-tile
+//                 ranges) and of the chunks per tile (blend work items)
+//   scatter       one CTA per 1024 Gaussians: append (depth bits << 32 | id) to each touched tile's segment at
+//                 base[tile][block] + shared-memory cursor
+//   sort_pack     one CTA per tile: bitonic sort of the segment (ties by Gaussian id, i.e. exactly the order of the reference's
+//                 stable (tile | depth) radix sort), then gather the Gaussian data into the four SoA record planes that the blend
+//                 kernels stream with 1-D bulk (TMA) copies
 //
 // Replaces InclusiveSum / duplicateWithKeys / 6-pass SortPairs / identifyTileRanges of the upstream rasterizer
-// (SURVEY.md §2.1): the R-element 43-bit global radix sort (75 us at R = 181k on B200, profiles/r1_*) becomes
-// per-tile sorts of ~150 keys that run concurrently in shared memory, and the instance count never leaves the device.
+// (SURVEY.md §2.1).  Measured on B200 (profiles/): the 43-bit CUB radix sort of R = 181k keys costs 75 us; per-tile atomic
+// cursors are worse (a returning atomic on one address retires every ~18 ns and the benchmark scene puts up to 1900 instances
+// on one tile), hence the two-level counting sort with shared-memory histograms.  The instance count never leaves the device.
 #include "common.cuh"
+
+#define MAX_TILES_SMEM 12288 // 48 KB of 32-bit bins
 
 // ---- workspace carving -----------------------------------------------------------------------------
 int gsd_carve_geom(int G, void *base, GsdGeomWs *ws) {
     size_t n = (size_t)(G > 0 ? G : 1);
+    size_t nblk = (n + 255) / 256;
     char *p = (char *)base;
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -29,11 +35,13 @@ int gsd_carve_geom(int G, void *base, GsdGeomWs *ws) {
     ws->rect = (uint2 *)take(n * sizeof(uint2));
     ws->tiles = (uint32_t *)take(n * sizeof(uint32_t));
     ws->slot_base = (uint32_t *)take(n * sizeof(uint32_t));
+    ws->block_sum = (uint32_t *)take(nblk * 4);
+    ws->block_base = (uint32_t *)take(nblk * 4);
     ws->total = off;
     return GSD_OK;
 }
 
-int gsd_carve_bin(int64_t capacity, int tiles, void *base, GsdBinWs *ws) {
+int gsd_carve_bin(int G, int64_t capacity, int tiles, void *base, GsdBinWs *ws) {
     size_t n = (size_t)(capacity > 0 ? capacity : 1);
     char *p = (char *)base;
     size_t off = 0;
@@ -42,20 +50,23 @@ int gsd_carve_bin(int64_t capacity, int tiles, void *base, GsdBinWs *ws) {
         off += gsd_align_up(bytes);
         return r;
     };
-    // the three small integer arrays are contiguous so that one memset clears them
-    ws->tile_count = (int32_t *)take((size_t)tiles * 4);
-    ws->tile_fill = (int32_t *)take((size_t)tiles * 4);
-    ws->counters = (int32_t *)take(8 * 4);
-    ws->tile_order = (int32_t *)take((size_t)tiles * 4);
+    ws->n_bb = (G + GSD_BIN_BLOCK - 1) / GSD_BIN_BLOCK;
+    if (ws->n_bb < 1) ws->n_bb = 1;
+    ws->max_items = (int)(n / GSD_CHUNK) + tiles;
+    ws->table = (int32_t *)take((size_t)tiles * ws->n_bb * 4);
     ws->ranges = (uint2 *)take((size_t)tiles * sizeof(uint2));
+    ws->chunk_ptr = (int32_t *)take((size_t)(tiles + 1) * 4);
+    ws->item_tile = (int32_t *)take((size_t)ws->max_items * 4);
+    ws->counters = (int32_t *)take(8 * 4);
     ws->keys = (uint64_t *)take(n * 8);
     ws->records = (float4 *)take(n * GSD_REC_FLOATS * 4);
     ws->total = off;
     return GSD_OK;
 }
 
-int gsd_carve_img(int W, int H, void *base, GsdImgWs *ws) {
+int gsd_carve_img(int W, int H, int n_sets, int max_items, void *base, GsdImgWs *ws) {
     size_t n = (size_t)W * H;
+    const int tiles = ((W + GSD_TILE - 1) / GSD_TILE) * ((H + GSD_TILE - 1) / GSD_TILE);
     char *p = (char *)base;
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -65,91 +76,124 @@ int gsd_carve_img(int W, int H, void *base, GsdImgWs *ws) {
     };
     ws->final_T = (float *)take(n * 4);
     ws->n_contrib = (int32_t *)take(n * 4);
+    ws->chunk_state = (float *)take(gsd_chunk_state_floats(n_sets, max_items) * 4);
+    ws->term_state = (float *)take(gsd_term_state_floats(n_sets, tiles) * 4);
     ws->total = off;
     return GSD_OK;
 }
 
-// ---- tile scan + schedule ----------------------------------------------------------------------------
-// One CTA of 1024 threads. status[0] already holds R (accumulated by the preprocess kernel).
-#define SCAN_THREADS 1024
-#define ORDER_MAX 8192 // tiles sortable in shared memory (64 KB of keys); larger images keep the natural order
-
-__global__ void __launch_bounds__(SCAN_THREADS)
-gsd_tile_scan_kernel(int n_tiles, int64_t capacity, const int32_t *__restrict__ tile_count, uint2 *__restrict__ ranges,
-                     int32_t *__restrict__ tile_order, int32_t *__restrict__ status) {
-    extern __shared__ unsigned long long skey[]; // [pow2 >= n_tiles] when n_tiles <= ORDER_MAX
-    __shared__ int sbuf[SCAN_THREADS];
-    __shared__ int carry;
-    const int t = threadIdx.x;
-    if (t == 0) carry = 0;
+// ---- hist / scatter: one CTA per GSD_BIN_BLOCK Gaussians ------------------------------------------------------
+template <bool SCATTER>
+__global__ void __launch_bounds__(GSD_BIN_BLOCK)
+gsd_bin_kernel(int G, int gx, int n_tiles, int n_bb, const uint32_t *__restrict__ tiles, const uint2 *__restrict__ rect,
+               const float *__restrict__ depth, int32_t *__restrict__ table, const uint2 *__restrict__ ranges,
+               uint64_t *__restrict__ keys, uint32_t *__restrict__ slot_base, const uint32_t *__restrict__ block_base) {
+    extern __shared__ int bins[]; // [n_tiles] counts (hist) or cursors (scatter)
+    const int bb = blockIdx.x;
+    for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) bins[i] = 0;
     __syncthreads();
-    for (int base = 0; base < n_tiles; base += SCAN_THREADS) {
-        const int i = base + t;
-        const int v = i < n_tiles ? tile_count[i] : 0;
-        sbuf[t] = v;
-        __syncthreads();
-        for (int o = 1; o < SCAN_THREADS; o <<= 1) {
-            int add = t >= o ? sbuf[t - o] : 0;
-            __syncthreads();
-            sbuf[t] += add;
-            __syncthreads();
-        }
-        if (i < n_tiles) {
-            long long s = (long long)carry + sbuf[t] - v, e = s + v;
-            if (s > capacity) s = capacity;
-            if (e > capacity) e = capacity;
-            ranges[i] = make_uint2((uint32_t)s, (uint32_t)e);
-        }
-        __syncthreads();
-        if (t == SCAN_THREADS - 1) carry += sbuf[SCAN_THREADS - 1];
-        __syncthreads();
-    }
-    if (t == 0) status[1] = ((long long)(uint32_t)status[0] > capacity) ? 1 : 0;
-
-    // schedule: tiles by descending count (ties by tile id) — bitonic sort of (~count << 32 | tile)
-    if (n_tiles <= ORDER_MAX) {
-        int P = 1;
-        while (P < n_tiles) P <<= 1;
-        for (int i = t; i < P; i += SCAN_THREADS)
-            skey[i] = i < n_tiles ? (((unsigned long long)(0xffffffffu - (uint32_t)tile_count[i]) << 32) | (uint32_t)i) : ~0ull;
-        __syncthreads();
-        for (int k = 2; k <= P; k <<= 1) {
-            for (int j = k >> 1; j >= 1; j >>= 1) {
-                for (int i = t; i < P; i += SCAN_THREADS) {
-                    int ixj = i ^ j;
-                    if (ixj > i) {
-                        unsigned long long a = skey[i], b = skey[ixj];
-                        bool up = (i & k) == 0;
-                        if ((a > b) == up) { skey[i] = b; skey[ixj] = a; }
+    const int i = bb * GSD_BIN_BLOCK + threadIdx.x;
+    if (i < G) {
+        const uint32_t n = tiles[i];
+        if (SCATTER) slot_base[i] += block_base[i >> 8]; // block-local offset -> global slot
+        if (n) {
+            const uint2 rc = rect[i];
+            const int minx = rc.x & 0xffff, miny = rc.x >> 16, maxx = rc.y & 0xffff, maxy = rc.y >> 16;
+            const uint64_t key = SCATTER ? (((uint64_t)__float_as_uint(depth[i]) << 32) | (uint32_t)i) : 0ull;
+            for (int y = miny; y < maxy; ++y)
+                for (int x = minx; x < maxx; ++x) {
+                    const int tile = y * gx + x;
+                    if (SCATTER) {
+                        const uint32_t pos = (uint32_t)table[(size_t)tile * n_bb + bb] + (uint32_t)atomicAdd(&bins[tile], 1);
+                        if (pos < ranges[tile].y) keys[pos] = key; // ranges are clipped to capacity
+                    } else {
+                        atomicAdd(&bins[tile], 1);
                     }
                 }
-                __syncthreads();
-            }
         }
-        for (int i = t; i < n_tiles; i += SCAN_THREADS) tile_order[i] = (int32_t)(skey[i] & 0xffffffffu);
-    } else {
-        for (int i = t; i < n_tiles; i += SCAN_THREADS) tile_order[i] = i;
+    }
+    if (!SCATTER) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) table[(size_t)t * n_bb + bb] = bins[t];
     }
 }
 
-// ---- fill ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-gsd_fill_keys_kernel(int G, int gx, int64_t capacity, const uint32_t *__restrict__ tiles, const uint2 *__restrict__ rect,
-                     const float *__restrict__ depth, const uint2 *__restrict__ ranges, int32_t *__restrict__ tile_fill,
-                     uint64_t *__restrict__ keys) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G) return;
-    if (tiles[i] == 0) return;
-    uint2 rc = rect[i];
-    int minx = rc.x & 0xffff, miny = rc.x >> 16, maxx = rc.y & 0xffff, maxy = rc.y >> 16;
-    const uint64_t key = ((uint64_t)__float_as_uint(depth[i]) << 32) | (uint32_t)i;
-    for (int y = miny; y < maxy; ++y)
-        for (int x = minx; x < maxx; ++x) {
-            const int tile = y * gx + x;
-            const uint2 r = ranges[tile];
-            const uint32_t pos = r.x + (uint32_t)atomicAdd(&tile_fill[tile], 1);
-            if (pos < r.y) keys[pos] = key; // r.y is clipped to capacity
+// ---- scans (one CTA) -------------------------------------------------------------------------------------------
+#define SCAN_THREADS 1024
+// exclusive scan of `n` ints in place; each thread owns a contiguous run. Returns the total (valid in all threads).
+__device__ int cta_exclusive_scan(int *data, int n, int *s_warp /* [33] */) {
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int beg = min(n, t * per), end = min(n, beg + per);
+    int sum = 0;
+    for (int i = beg; i < end; ++i) sum += data[i];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
         }
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    int run = s_warp[wid] + incl - sum;
+    for (int i = beg; i < end; ++i) {
+        int v = data[i];
+        data[i] = run;
+        run += v;
+    }
+    const int total = s_warp[32];
+    __syncthreads();
+    return total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+gsd_bin_scan_kernel(int n_pre_blocks, int n_tiles, int n_bb, int64_t capacity, int max_items, uint32_t *__restrict__ block_sum,
+                    uint32_t *__restrict__ block_base, int32_t *__restrict__ table, uint2 *__restrict__ ranges,
+                    int32_t *__restrict__ chunk_ptr, int32_t *__restrict__ item_tile, int32_t *__restrict__ counters,
+                    int32_t *__restrict__ status) {
+    __shared__ int s_warp[33];
+    const int t = threadIdx.x;
+    // (a) slot bases of the preprocess blocks, R
+    for (int i = t; i < n_pre_blocks; i += SCAN_THREADS) block_base[i] = block_sum[i];
+    __syncthreads();
+    const int R = cta_exclusive_scan((int *)block_base, n_pre_blocks, s_warp);
+    if (t == 0) {
+        status[0] = R;
+        status[1] = ((long long)R > capacity) ? 1 : 0;
+    }
+    // (b) tile-major table -> scatter bases; per-tile ranges
+    const int total = cta_exclusive_scan(table, n_tiles * n_bb, s_warp);
+    for (int i = t; i < n_tiles; i += SCAN_THREADS) {
+        long long s = table[(size_t)i * n_bb];
+        long long e = (i + 1 < n_tiles) ? table[(size_t)(i + 1) * n_bb] : total;
+        if (s > capacity) s = capacity;
+        if (e > capacity) e = capacity;
+        ranges[i] = make_uint2((uint32_t)s, (uint32_t)e);
+        chunk_ptr[i] = (int)((e - s + GSD_CHUNK - 1) / GSD_CHUNK);
+    }
+    __syncthreads();
+    // (c) work items: one per GSD_CHUNK records of a tile
+    const int n_items = cta_exclusive_scan(chunk_ptr, n_tiles, s_warp);
+    if (t == 0) {
+        chunk_ptr[n_tiles] = n_items;
+        counters[0] = n_items < max_items ? n_items : max_items;
+    }
+    __syncthreads();
+    for (int i = t; i < n_tiles; i += SCAN_THREADS) {
+        const int c0 = chunk_ptr[i], c1 = (i + 1 < n_tiles) ? chunk_ptr[i + 1] : n_items;
+        for (int c = c0; c < c1 && c < max_items; ++c) item_tile[c] = i;
+    }
 }
 
 // ---- per-tile sort + pack ----------------------------------------------------------------------------------
@@ -185,88 +229,116 @@ __device__ __forceinline__ void cta_bitonic_sort(KeyPtr key, int n, int tid, int
 }
 
 #define SORT_THREADS 256
-#define SORT_SMEM_KEYS 6000 // 48 KB static limit; longer tile lists are sorted in place in global memory
+#define SORT_SMEM_KEYS 2048 // 16 KB: every tile's CTA is resident at once; longer lists are sorted in place in global memory (L2)
 
 // plane0 = (x, y, ext_x, ext_y)   plane1 = (A, B, C, opacity)   plane2 = (c0, c1, c2, depth)   plane3 = (slot bits, c3, c4, c5)
 // slot = slot_base[g] + rank of the tile inside the Gaussian's rectangle: the blend backward writes this instance's
 // partial gradient there, so a Gaussian's partials are contiguous and are summed in a fixed order without atomics.
 __global__ void __launch_bounds__(SORT_THREADS)
-gsd_tile_sort_pack_kernel(int n_tiles, int gx, int64_t capacity, const int32_t *__restrict__ tile_order,
-                          int32_t *__restrict__ next_tile, const uint2 *__restrict__ ranges, uint64_t *__restrict__ keys,
+gsd_tile_sort_pack_kernel(int gx, int64_t capacity, const uint2 *__restrict__ ranges, uint64_t *__restrict__ keys,
                           const float2 *__restrict__ xy, const float4 *__restrict__ conic_o, const float2 *__restrict__ ext,
                           const float *__restrict__ depth, const uint2 *__restrict__ rect, const uint32_t *__restrict__ slot_base,
                           const float *__restrict__ colors0, const float *__restrict__ colors1, float4 *__restrict__ records) {
     __shared__ unsigned long long skeys[SORT_SMEM_KEYS];
-    __shared__ int s_next;
     const int t = threadIdx.x;
-    for (;;) {
-        if (t == 0) s_next = atomicAdd(next_tile, 1);
+    const int tile = blockIdx.x;
+    const uint2 r = ranges[tile];
+    const int n = (int)(r.y - r.x);
+    if (n == 0) return;
+    unsigned long long *gk = reinterpret_cast<unsigned long long *>(keys) + r.x;
+    const bool in_smem = n <= SORT_SMEM_KEYS;
+    if (in_smem) {
+        for (int i = t; i < n; i += SORT_THREADS) skeys[i] = gk[i];
         __syncthreads();
-        const int q = s_next;
-        __syncthreads();
-        if (q >= n_tiles) break;
-        const int tile = tile_order[q];
-        const uint2 r = ranges[tile];
-        const int n = (int)(r.y - r.x);
-        if (n == 0) continue; // (with the LPT schedule everything after is empty too; natural order needs the scan)
-        unsigned long long *gk = reinterpret_cast<unsigned long long *>(keys) + r.x;
-        const bool in_smem = n <= SORT_SMEM_KEYS;
-        if (in_smem) {
-            for (int i = t; i < n; i += SORT_THREADS) skeys[i] = gk[i];
-            __syncthreads();
-            cta_bitonic_sort(skeys, n, t, SORT_THREADS);
-        } else {
-            cta_bitonic_sort(gk, n, t, SORT_THREADS);
-        }
-        const int tx = tile % gx, ty = tile / gx;
-        for (int i = t; i < n; i += SORT_THREADS) {
-            const uint32_t g = (uint32_t)((in_smem ? skeys[i] : gk[i]) & 0xffffffffull);
-            const uint2 rc = rect[g];
-            const int minx = rc.x & 0xffff, miny = rc.x >> 16, maxx = rc.y & 0xffff;
-            const uint32_t slot = slot_base[g] + (uint32_t)((ty - miny) * (maxx - minx) + (tx - minx));
-            const float2 p = xy[g];
-            const float2 e = ext[g];
-            const float4 co = conic_o[g];
-            const float d = depth[g];
-            const float c0 = colors0[3 * g], c1 = colors0[3 * g + 1], c2 = colors0[3 * g + 2];
-            float c3 = 0.f, c4 = 0.f, c5 = 0.f;
-            if (colors1) { c3 = colors1[3 * g]; c4 = colors1[3 * g + 1]; c5 = colors1[3 * g + 2]; }
-            const int64_t j = (int64_t)r.x + i;
-            records[j] = make_float4(p.x, p.y, e.x, e.y);
-            records[capacity + j] = co;
-            records[2 * capacity + j] = make_float4(c0, c1, c2, d);
-            records[3 * capacity + j] = make_float4(__uint_as_float(slot), c3, c4, c5);
-        }
-        __syncthreads();
+        cta_bitonic_sort(skeys, n, t, SORT_THREADS);
+    } else {
+        cta_bitonic_sort(gk, n, t, SORT_THREADS);
+    }
+    const int tx = tile % gx, ty = tile / gx;
+    for (int i = t; i < n; i += SORT_THREADS) {
+        const uint32_t g = (uint32_t)((in_smem ? skeys[i] : gk[i]) & 0xffffffffull);
+        const uint2 rc = rect[g];
+        const int minx = rc.x & 0xffff, miny = rc.x >> 16, maxx = rc.y & 0xffff;
+        const uint32_t slot = slot_base[g] + (uint32_t)((ty - miny) * (maxx - minx) + (tx - minx));
+        const float2 p = xy[g];
+        const float2 e = ext[g];
+        const float4 co = conic_o[g];
+        const float d = depth[g];
+        const float c0 = colors0[3 * g], c1 = colors0[3 * g + 1], c2 = colors0[3 * g + 2];
+        float c3 = 0.f, c4 = 0.f, c5 = 0.f;
+        if (colors1) { c3 = colors1[3 * g]; c4 = colors1[3 * g + 1]; c5 = colors1[3 * g + 2]; }
+        const int64_t j = (int64_t)r.x + i;
+        records[j] = make_float4(p.x, p.y, e.x, e.y);
+        records[capacity + j] = co;
+        records[2 * capacity + j] = make_float4(c0, c1, c2, d);
+        records[3 * capacity + j] = make_float4(__uint_as_float(slot), c3, c4, c5);
     }
 }
 
 // ---- host launchers -------------------------------------------------------------------------------------
-// b.tile_count / tile_fill / counters must be zero on entry (one memset by the caller); status[0] holds R.
+static int set_bin_attrs() {
+    static bool done = false;
+    if (!done) {
+        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_TILES_SMEM * 4));
+        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_TILES_SMEM * 4));
+        done = true;
+    }
+    return GSD_OK;
+}
+
+// count only: scan of the block sums -> status[0] = R  (what upstream copies to the host before binning)
+__global__ void __launch_bounds__(SCAN_THREADS)
+gsd_count_kernel(int n_pre_blocks, const uint32_t *__restrict__ block_sum, int32_t *__restrict__ status) {
+    __shared__ long long red[SCAN_THREADS / 32];
+    long long s = 0;
+    for (int i = threadIdx.x; i < n_pre_blocks; i += SCAN_THREADS) s += block_sum[i];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long tot = 0;
+        for (int k = 0; k < SCAN_THREADS / 32; ++k) tot += red[k];
+        status[0] = (int32_t)tot;
+        status[1] = 0;
+    }
+}
+
+int gsd_launch_count(int G, const GsdGeomWs &g, int32_t *status, cudaStream_t st) {
+    gsd_count_kernel<<<1, SCAN_THREADS, 0, st>>>(G > 0 ? (G + 255) / 256 : 0, g.block_sum, status);
+    GSD_LAUNCH_CHECK();
+    return GSD_OK;
+}
+
 int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, const GsdBinWs &b,
                        cudaStream_t st) {
     const int64_t cap = a->capacity;
     const int tiles = cam.gx * cam.gy;
-    size_t smem = 0;
-    if (tiles <= ORDER_MAX) {
-        int P = 1;
-        while (P < tiles) P <<= 1;
-        smem = (size_t)P * 8;
+    if (tiles > MAX_TILES_SMEM) {
+        gsd_set_error("image has %d tiles; the binning histogram supports up to %d (e.g. 2048x1536)", tiles, MAX_TILES_SMEM);
+        return GSD_ERR_UNSUPPORTED;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_tile_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ORDER_MAX * 8));
-        attr_set = true;
+    int rc;
+    if ((rc = set_bin_attrs())) return rc;
+    const int n_pre = G > 0 ? (G + 255) / 256 : 0;
+    const size_t smem = (size_t)tiles * 4;
+    if (G > 0) {
+        gsd_bin_kernel<false><<<b.n_bb, GSD_BIN_BLOCK, smem, st>>>(G, cam.gx, tiles, b.n_bb, g.tiles, g.rect, g.depth, b.table,
+                                                                    b.ranges, b.keys, g.slot_base, g.block_base);
+        GSD_LAUNCH_CHECK();
+    } else {
+        GSD_CUDA_CHECK(cudaMemsetAsync(b.table, 0, (size_t)tiles * b.n_bb * 4, st));
     }
-    gsd_tile_scan_kernel<<<1, SCAN_THREADS, smem, st>>>(tiles, cap, b.tile_count, b.ranges, b.tile_order, a->status);
+    gsd_bin_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(n_pre, tiles, b.n_bb, cap, b.max_items, g.block_sum, g.block_base, b.table,
+                                                     b.ranges, b.chunk_ptr, b.item_tile, b.counters, a->status);
     GSD_LAUNCH_CHECK();
     if (G == 0 || cap == 0) return GSD_OK;
-    gsd_fill_keys_kernel<<<(G + 255) / 256, 256, 0, st>>>(G, cam.gx, cap, g.tiles, g.rect, g.depth, b.ranges, b.tile_fill, b.keys);
+    gsd_bin_kernel<true><<<b.n_bb, GSD_BIN_BLOCK, smem, st>>>(G, cam.gx, tiles, b.n_bb, g.tiles, g.rect, g.depth, b.table, b.ranges,
+                                                               b.keys, g.slot_base, g.block_base);
     GSD_LAUNCH_CHECK();
-    int grid = tiles < 148 * 8 ? tiles : 148 * 8;
-    gsd_tile_sort_pack_kernel<<<grid, SORT_THREADS, 0, st>>>(tiles, cam.gx, cap, b.tile_order, b.counters + 0, b.ranges, b.keys,
-                                                              g.xy, g.conic_o, g.ext, g.depth, g.rect, g.slot_base, a->colors0,
-                                                              a->n_sets == 2 ? a->colors1 : nullptr, b.records);
+    gsd_tile_sort_pack_kernel<<<tiles, SORT_THREADS, 0, st>>>(cam.gx, cap, b.ranges, b.keys, g.xy, g.conic_o, g.ext, g.depth,
+                                                               g.rect, g.slot_base, a->colors0,
+                                                               a->n_sets == 2 ? a->colors1 : nullptr, b.records);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }

@@ -16,7 +16,7 @@ gsd_preprocess_kernel(int G, GsdCam cam, const float *__restrict__ means3D, cons
                       const float *__restrict__ scales, const float *__restrict__ rotations, float2 *__restrict__ xy,
                       float4 *__restrict__ conic_o, float2 *__restrict__ ext, float *__restrict__ depth,
                       uint2 *__restrict__ rect, uint32_t *__restrict__ tiles, uint32_t *__restrict__ slot_base,
-                      int32_t *__restrict__ radii, int32_t *__restrict__ tile_count, uint32_t *__restrict__ counter) {
+                      int32_t *__restrict__ radii, uint32_t *__restrict__ block_sum) {
     __shared__ float sVP[32];
     if (threadIdx.x < 16) sVP[threadIdx.x] = cam.view[threadIdx.x];
     else if (threadIdx.x < 32) sVP[threadIdx.x] = cam.proj[threadIdx.x - 16];
@@ -116,28 +116,31 @@ gsd_preprocess_kernel(int G, GsdCam cam, const float *__restrict__ means3D, cons
         rad_out = (int)rad;
         rect_out = make_uint2((uint32_t)minx | ((uint32_t)miny << 16), (uint32_t)maxx | ((uint32_t)maxy << 16));
         tiles_out = (uint32_t)((maxx - minx) * (maxy - miny));
-        // per-tile instance counts (binning pass 1)
-        if (tile_count)
-            for (int ty = miny; ty < maxy; ++ty)
-                for (int tx = minx; tx < maxx; ++tx) atomicAdd(&tile_count[ty * cam.gx + tx], 1);
     } while (0);
-    // slot range of this Gaussian's instances: warp-aggregated claim on the global instance counter. The assignment
-    // order is arbitrary, the ranges are disjoint and the per-Gaussian order inside a range is fixed (tile rank).
-    const int lane = threadIdx.x & 31;
+    // block-local exclusive scan of tiles touched: slot_base[i] = offset inside this block (the binning scatter adds the
+    // block's base). No atomics: slots are deterministic and in Gaussian order.
+    __shared__ uint32_t wsum[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t incl = tiles_out;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
     }
-    uint32_t base = 0;
-    if (lane == 31 && incl > 0) base = atomicAdd(counter, incl);
-    base = __shfl_sync(0xffffffffu, base, 31);
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k < wid) wbase += wsum[k];
+        total += wsum[k];
+    }
+    if (threadIdx.x == 0) block_sum[blockIdx.x] = total;
     if (in_range) {
         radii[i] = rad_out;
         tiles[i] = tiles_out;
         rect[i] = rect_out;
-        slot_base[i] = base + incl - tiles_out;
+        slot_base[i] = wbase + incl - tiles_out;
     }
 }
 
@@ -152,14 +155,13 @@ __global__ void gsd_mark_visible_kernel(int G, GsdCam cam, const float *__restri
     vis[i] = pv.z > 0.2f ? 1 : 0;
 }
 
-// tile_count may be null (count-only call). status[0] must be zero on entry: it accumulates the instance count R.
-int gsd_launch_preprocess(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, int32_t *tile_count,
-                          cudaStream_t st) {
+// block_sum[b] receives the number of tile instances of Gaussians [256 b, 256 b + 256)
+int gsd_launch_preprocess(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, cudaStream_t st) {
     if (G == 0) return GSD_OK;
     int blocks = (G + 255) / 256;
     gsd_preprocess_kernel<<<blocks, 256, 0, st>>>(G, cam, a->means3D, a->opacities, a->scales, a->rotations, g.xy,
                                                    g.conic_o, g.ext, g.depth, g.rect, g.tiles, g.slot_base, a->radii,
-                                                   tile_count, (uint32_t *)a->status);
+                                                   g.block_sum);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }

@@ -3,176 +3,360 @@
 // Replaces renderCUDA<3> forward/backward of the upstream rasterizer, reached from
 // /root/reference/src/tracking/train_utils.py:178,192 (forward) and train_gs.py:31 (backward).
 //
-// Design (B200-first, not a translation):
-//   * persistent CTAs pull 16x16 tiles from a work queue ordered by descending instance count (LPT schedule written by
-//     the binning pass), so the heaviest tiles start first and the tail is short;
-//   * warp-specialised: one PRODUCER warp streams the tile's depth-sorted record planes into a ring of shared-memory
-//     stages with the TMA engine (cp.async.bulk + mbarrier full/empty pairs); 8 CONSUMER warps each own an 8x4 pixel
-//     rectangle and never meet at a CTA-wide barrier inside a tile; (backward) one FLUSHER warp sums the per-warp
-//     partials of a finished stage in fixed order and writes one 64-byte record per instance;
-//   * every 32 records the lanes of a consumer warp test one record each against the warp's rectangle (conservative
-//     extents of the alpha >= 1/255 ellipse) and only the survivors of the ballot are blended — exact, ~2.3x fewer pairs;
-//   * survivors are processed GSD_ILP at a time: the alpha evaluations (the long dependent chains: LDS -> FMA x6 ->
-//     MUFU.EX2) are independent and overlap; only the short transmittance recurrence is serial;
-//   * backward runs FRONT-TO-BACK like the forward (suffix colour = final colour - prefix), so T is rebuilt by the same
-//     multiplications as in the forward; the per-pixel partials of a Gaussian are summed across the warp with a transposed
-//     butterfly (13 shuffles for 12 values): no atomics anywhere, bit-reproducible gradients.
+// Design (B200-first, not a translation).  A pixel's front-to-back recurrence is serial in the length of its tile list, and
+// real scenes concentrate the instances on few tiles (benchmark scene: 317 of 1200 tiles, up to 1900 instances; a tracked
+// object: tens of tiles with thousands).  One CTA per tile therefore leaves most SMs idle behind a few long serial chains
+// (profiles/r1_*).  Here every tile list is cut into CHUNKS of 256 records and each (tile, chunk) is an independent work item:
+//   fwd A1  per item   local composite of the chunk (transmittance product P, colour/depth sums with T starting at 1)
+//   fwd A2  per item   exact termination: T_in = prod of the preceding chunks' P; if T_in*P < 1e-4 some Gaussian inside this
+//                      chunk is the reference's stopping point — that pixel is replayed sequentially with the true T_in
+//   fwd B   per tile   combine the chunk composites in order -> colour, depth, final_T, n_contrib
+//   bwd B'  per tile   per chunk and pixel: T_in and Q_in = dL/dC . (colour still to come), from the stored chunk composites
+//   bwd A'  per item   gradients of the chunk's Gaussians from (T_in, Q_in): front-to-back like the forward (T rebuilt by
+//                      multiplication, not division); per-pixel partials summed across the warp with a transposed butterfly
+//                      (13 shuffles for 12 values), across warps in fixed order by a flusher warp, one 64-byte record per
+//                      instance: no atomics, bit-reproducible gradients
+// Inside an item the chunk's records are one TMA bulk copy per SoA plane (cp.async.bulk + mbarrier); 8 warps own 8x4 pixel
+// rectangles; every 32 records the lanes test one record each against the rectangle (conservative extents of the
+// alpha >= 1/255 ellipse) and only ballot survivors are blended, GSD_ILP at a time.
 #include "common.cuh"
 
-#define GSD_BATCH 32     // records per pipeline stage
-#define GSD_STAGES_F 6   // forward ring depth
-#define GSD_STAGES_B 3   // backward ring depth (each stage also carries the per-warp partial sums)
-#define GSD_CWARPS 8     // consumer warps
+#define GSD_SUB 32     // records per cull group / backward sub-batch
+#define GSD_CWARPS 8   // consumer warps = 8x4 pixel rectangles of a 16x16 tile
 #define GSD_ILP 4
+#define T_EPS 0.0001f
+#define TERMINAL_NONE (-1)
+
+// per-item state (floats, SoA over the 256 pixels): P, D, C[CH], last(int) | bwd: T_in, Q_in
+template <int CH> struct ItemState {
+    static constexpr int P = 0, D = 1, C = 2, LAST = 2 + CH, TIN = 3 + CH, QIN = 4 + CH, NF = 5 + CH;
+};
+// per-tile terminal record (written by the one chunk that terminates a pixel): T_stop, D_abs, C_abs[CH], last(int), cstar(int)
+template <int CH> struct TermState {
+    static constexpr int T = 0, D = 1, C = 2, LAST = 2 + CH, CSTAR = 3 + CH, NF = 4 + CH;
+};
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+struct ItemInfo { int tile, chunk, start, cnt, px, py, pix; bool inside; float rx0, rx1, ry0, ry1; };
+
+__device__ __forceinline__ bool item_setup(const GsdRenderParams &p, int item, int warp, int lane, ItemInfo &I) {
+    if (item >= *p.n_items) return false;
+    I.tile = p.item_tile[item];
+    I.chunk = item - p.chunk_ptr[I.tile];
+    const uint2 r = p.ranges[I.tile];
+    I.start = (int)r.x + I.chunk * GSD_CHUNK;
+    I.cnt = min(GSD_CHUNK, (int)r.y - I.start);
+    const int tx = I.tile % p.gx, ty = I.tile / p.gx;
+    const int wx0 = tx * GSD_TILE + (warp & 1) * 8, wy0 = ty * GSD_TILE + (warp >> 1) * 4;
+    I.px = wx0 + (lane & 7);
+    I.py = wy0 + (lane >> 3);
+    I.inside = I.px < p.W && I.py < p.H;
+    I.pix = warp * 32 + lane;
+    I.rx0 = (float)wx0; I.rx1 = (float)(wx0 + 7); I.ry0 = (float)wy0; I.ry1 = (float)(wy0 + 3);
+    return true;
+}
+
 template <int NPLANES>
-__device__ __forceinline__ void issue_batch(const GsdRenderParams &p, float4 (*stage)[GSD_BATCH], uint64_t *bar,
-                                            uint32_t start, int cnt) {
+__device__ __forceinline__ void load_chunk(const GsdRenderParams &p, float4 (*planes)[GSD_CHUNK], uint64_t *bar, int start, int cnt) {
     const uint32_t bytes = (uint32_t)cnt * 16u;
     mbar_expect_tx(bar, bytes * NPLANES);
 #pragma unroll
-    for (int k = 0; k < NPLANES; ++k) bulk_g2s(&stage[k][0], p.planes + (int64_t)k * p.plane_stride + start, bytes, bar);
+    for (int k = 0; k < NPLANES; ++k) bulk_g2s(&planes[k][0], p.planes + (int64_t)k * p.plane_stride + start, bytes, bar);
 }
 
 // ------------------------------------------------------------------------------------------------------
-// forward
+// forward A1: local composite of one chunk
 // ------------------------------------------------------------------------------------------------------
 template <int CH>
-__global__ void __launch_bounds__((GSD_CWARPS + 1) * 32)
-gsd_render_fwd_kernel(GsdRenderParams p) {
+__global__ void __launch_bounds__(GSD_CWARPS * 32)
+gsd_blend_fwd_chunk_kernel(GsdRenderParams p) {
     constexpr int NPL = (CH == 3) ? 3 : 4;
-    constexpr int S = GSD_STAGES_F;
-    __shared__ __align__(128) float4 stage[S][NPL][GSD_BATCH];
-    __shared__ __align__(8) uint64_t full[S], empty[S];
-    __shared__ int s_tile;
-
+    using IS = ItemState<CH>;
+    __shared__ __align__(128) float4 planes[NPL][GSD_CHUNK];
+    __shared__ __align__(8) uint64_t bar;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    if (t == 0) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GSD_CWARPS); }
-        mbar_fence_init();
-    }
+    ItemInfo I;
+    if (!item_setup(p, blockIdx.x, warp, lane, I)) return;
+    if (t == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     __syncthreads();
-    uint32_t gb = 0; // batches streamed so far by this CTA (identical in every warp): stage = gb % S, use = gb / S
-
-    for (;;) {
-        if (t == 0) s_tile = atomicAdd(p.next_tile, 1);
-        __syncthreads();
-        const int q = s_tile;
-        __syncthreads();
-        if (q >= p.n_tiles) break;
-        const int tile = p.tile_order[q];
-        const uint2 range = p.ranges[tile];
-        const int n = (int)(range.y - range.x);
-        const int nb = (n + GSD_BATCH - 1) / GSD_BATCH;
-
-        if (warp == GSD_CWARPS) {
-            // ===== producer =====
-            if (lane == 0) {
-                for (int b = 0; b < nb; ++b) {
-                    const uint32_t g = gb + b;
-                    const int s = g % S;
-                    if (g >= S) mbar_wait(&empty[s], ((g / S) - 1) & 1);
-                    issue_batch<NPL>(p, stage[s], &full[s], range.x + b * GSD_BATCH, min(GSD_BATCH, n - b * GSD_BATCH));
-                }
+    if (t == 0) load_chunk<NPL>(p, planes, &bar, I.start, I.cnt);
+    float *st = p.chunk_state + (size_t)blockIdx.x * IS::NF * 256;
+    if (I.chunk == 0) // first chunk of the tile resets the tile's terminal record
+        reinterpret_cast<int *>(p.term_state + (size_t)I.tile * TermState<CH>::NF * 256)[TermState<CH>::CSTAR * 256 + I.pix] = TERMINAL_NONE;
+    const float pxf = (float)I.px, pyf = (float)I.py;
+    float T = 1.0f, D = 0.f;
+    float C[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) C[c] = 0.f;
+    int last = 0;
+    bool dead = !I.inside; // beyond T_EPS nothing of this chunk can be used (A2 replays the chunk for such pixels)
+    mbar_wait(&bar, 0);
+    for (int grp = 0; grp < I.cnt; grp += GSD_SUB) {
+        if (__all_sync(0xffffffffu, dead)) break;
+        const int idx = grp + lane;
+        bool pass = false;
+        if (idx < I.cnt) {
+            const float4 g0 = planes[0][idx];
+            pass = (g0.x + g0.z >= I.rx0) && (g0.x - g0.z <= I.rx1) && (g0.y + g0.w >= I.ry0) && (g0.y - g0.w <= I.ry1);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, pass);
+        while (m) {
+            int j[GSD_ILP];
+            bool valid[GSD_ILP];
+            float alpha[GSD_ILP], power[GSD_ILP];
+            float4 col[GSD_ILP];
+#pragma unroll
+            for (int u = 0; u < GSD_ILP; ++u) {
+                valid[u] = m != 0;
+                j[u] = valid[u] ? (grp + __ffs(m) - 1) : grp;
+                m &= m - 1;
             }
-        } else {
-            // ===== consumers =====
-            const int tx = tile % p.gx, ty = tile / p.gx;
-            const int wx0 = tx * GSD_TILE + (warp & 1) * 8, wy0 = ty * GSD_TILE + (warp >> 1) * 4;
-            const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
-            const float pxf = (float)px, pyf = (float)py;
-            const bool inside = px < p.W && py < p.H;
-            const float rx0 = (float)wx0, rx1 = (float)(wx0 + 7), ry0 = (float)wy0, ry1 = (float)(wy0 + 3);
-            bool done = !inside;
-            float T = 1.0f, D = 0.f;
-            float C[CH];
 #pragma unroll
-            for (int c = 0; c < CH; ++c) C[c] = 0.f;
-            int last = 0;
-            for (int b = 0; b < nb; ++b) {
-                const uint32_t g = gb + b;
-                const int s = g % S;
-                mbar_wait(&full[s], (g / S) & 1);
-                const int cnt = min(GSD_BATCH, n - b * GSD_BATCH);
-                if (!__all_sync(0xffffffffu, done)) {
-                    bool pass = false;
-                    if (lane < cnt) {
-                        const float4 g0 = stage[s][0][lane];
-                        pass = (g0.x + g0.z >= rx0) && (g0.x - g0.z <= rx1) && (g0.y + g0.w >= ry0) && (g0.y - g0.w <= ry1);
-                    }
-                    unsigned m = __ballot_sync(0xffffffffu, pass);
-                    while (m) {
-                        int j[GSD_ILP];
-                        bool valid[GSD_ILP];
-                        float alpha[GSD_ILP], power[GSD_ILP];
-                        float4 col[GSD_ILP];
-#pragma unroll
-                        for (int u = 0; u < GSD_ILP; ++u) {
-                            valid[u] = m != 0;
-                            j[u] = valid[u] ? (__ffs(m) - 1) : 0;
-                            m &= m - 1;
-                        }
-#pragma unroll
-                        for (int u = 0; u < GSD_ILP; ++u) {
-                            const float4 g0 = stage[s][0][j[u]];
-                            const float4 g1 = stage[s][1][j[u]];
-                            col[u] = stage[s][2][j[u]];
-                            power[u] = gsd_power(g1.x, g1.y, g1.z, g0.x - pxf, g0.y - pyf);
-                            alpha[u] = fminf(0.99f, __fmul_rn(g1.w, gsd_gauss(power[u])));
-                        }
-#pragma unroll
-                        for (int u = 0; u < GSD_ILP; ++u) {
-                            bool ok = valid[u] && (!done) && (power[u] <= 0.0f) && (alpha[u] >= 1.0f / 255.0f);
-                            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha[u]));
-                            if (ok && test_T < 0.0001f) {
-                                done = true;
-                                ok = false;
-                            }
-                            if (ok) {
-                                const float w = alpha[u] * T;
-                                C[0] += col[u].x * w;
-                                C[1] += col[u].y * w;
-                                C[2] += col[u].z * w;
-                                if (CH == 6) {
-                                    const float4 g3 = stage[s][NPL - 1][j[u]];
-                                    C[3 % CH] += g3.y * w;
-                                    C[4 % CH] += g3.z * w;
-                                    C[5 % CH] += g3.w * w;
-                                }
-                                D += col[u].w * w;
-                                T = test_T;
-                                last = b * GSD_BATCH + j[u] + 1;
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
+            for (int u = 0; u < GSD_ILP; ++u) {
+                const float4 g0 = planes[0][j[u]];
+                const float4 g1 = planes[1][j[u]];
+                col[u] = planes[2][j[u]];
+                power[u] = gsd_power(g1.x, g1.y, g1.z, g0.x - pxf, g0.y - pyf);
+                alpha[u] = fminf(0.99f, __fmul_rn(g1.w, gsd_gauss(power[u])));
             }
-            if (inside) {
-                const size_t pid = (size_t)py * p.W + px;
-                const size_t plane = (size_t)p.W * p.H;
-                p.final_T[pid] = T;
-                p.n_contrib[pid] = last;
 #pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const float bgc = (c < 3) ? __ldg(p.bg0 + c) : (p.bg1 ? __ldg(p.bg1 + (c % 3)) : 0.f);
-                    p.out_color[c * plane + pid] = C[c] + T * bgc;
+            for (int u = 0; u < GSD_ILP; ++u) {
+                const bool ok = valid[u] && (power[u] <= 0.0f) && (alpha[u] >= 1.0f / 255.0f);
+                if (ok) {
+                    const float w = alpha[u] * T;
+                    C[0] += col[u].x * w;
+                    C[1] += col[u].y * w;
+                    C[2] += col[u].z * w;
+                    if (CH == 6) {
+                        const float4 g3 = planes[NPL - 1][j[u]];
+                        C[3 % CH] += g3.y * w;
+                        C[4 % CH] += g3.z * w;
+                        C[5 % CH] += g3.w * w;
+                    }
+                    D += col[u].w * w;
+                    T = __fmul_rn(T, __fsub_rn(1.0f, alpha[u]));
+                    last = j[u] + 1;
                 }
-                p.out_depth[pid] = D;
             }
         }
-        gb += nb;
+        dead = dead || (T < T_EPS);
+    }
+    st[IS::P * 256 + I.pix] = T;
+    st[IS::D * 256 + I.pix] = D;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) st[(IS::C + c) * 256 + I.pix] = C[c];
+    reinterpret_cast<int *>(st)[IS::LAST * 256 + I.pix] = last;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// forward A2: find the terminating chunk of each pixel and replay it with the reference's exact sequential rule
+// ------------------------------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(GSD_CWARPS * 32)
+gsd_blend_fwd_term_kernel(GsdRenderParams p) {
+    constexpr int NPL = (CH == 3) ? 3 : 4;
+    using IS = ItemState<CH>;
+    using TS = TermState<CH>;
+    __shared__ __align__(128) float4 planes[NPL][GSD_CHUNK];
+    __shared__ __align__(8) uint64_t bar;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    ItemInfo I;
+    if (!item_setup(p, blockIdx.x, warp, lane, I)) return;
+    const int item0 = blockIdx.x - I.chunk;
+    // T_in = product of the preceding chunks' P (same order and ops in every kernel that rebuilds it)
+    float T = 1.0f;
+    bool dead = !I.inside;
+    for (int c = 0; c < I.chunk && !dead; ++c) {
+        const float Pc = p.chunk_state[(size_t)(item0 + c) * IS::NF * 256 + IS::P * 256 + I.pix];
+        const float Tn = __fmul_rn(T, Pc);
+        if (Tn < T_EPS) dead = true; // terminated in an earlier chunk
+        T = Tn;
+    }
+    const float Pme = p.chunk_state[(size_t)blockIdx.x * IS::NF * 256 + IS::P * 256 + I.pix];
+    const bool crossing = !dead && (__fmul_rn(T, Pme) < T_EPS);
+    if (!__syncthreads_or(crossing ? 1 : 0)) return;
+    if (t == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (t == 0) load_chunk<NPL>(p, planes, &bar, I.start, I.cnt);
+    mbar_wait(&bar, 0);
+    if (!__any_sync(0xffffffffu, crossing)) return;
+    // sequential replay for the crossing lanes: the reference's loop (renderCUDA forward) with the true incoming T
+    const float pxf = (float)I.px, pyf = (float)I.py;
+    float D = 0.f;
+    float C[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) C[c] = 0.f;
+    int last = 0;
+    bool done = !crossing;
+    for (int grp = 0; grp < I.cnt; grp += GSD_SUB) {
+        if (__all_sync(0xffffffffu, done)) break;
+        const int idx = grp + lane;
+        bool pass = false;
+        if (idx < I.cnt) {
+            const float4 g0 = planes[0][idx];
+            pass = (g0.x + g0.z >= I.rx0) && (g0.x - g0.z <= I.rx1) && (g0.y + g0.w >= I.ry0) && (g0.y - g0.w <= I.ry1);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, pass);
+        while (m) {
+            const int j = grp + __ffs(m) - 1;
+            m &= m - 1;
+            const float4 g0 = planes[0][j];
+            const float4 g1 = planes[1][j];
+            const float power = gsd_power(g1.x, g1.y, g1.z, g0.x - pxf, g0.y - pyf);
+            const float alpha = fminf(0.99f, __fmul_rn(g1.w, gsd_gauss(power)));
+            bool ok = (!done) && (power <= 0.0f) && (alpha >= 1.0f / 255.0f);
+            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+            if (ok && test_T < T_EPS) {
+                done = true;
+                ok = false;
+            }
+            if (ok) {
+                const float4 g2 = planes[2][j];
+                const float w = alpha * T;
+                C[0] += g2.x * w;
+                C[1] += g2.y * w;
+                C[2] += g2.z * w;
+                if (CH == 6) {
+                    const float4 g3 = planes[NPL - 1][j];
+                    C[3 % CH] += g3.y * w;
+                    C[4 % CH] += g3.z * w;
+                    C[5 % CH] += g3.w * w;
+                }
+                D += g2.w * w;
+                T = test_T;
+                last = j + 1;
+            }
+        }
+    }
+    if (crossing) {
+        float *ts = p.term_state + (size_t)I.tile * TS::NF * 256;
+        ts[TS::T * 256 + I.pix] = T;
+        ts[TS::D * 256 + I.pix] = D;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) ts[(TS::C + c) * 256 + I.pix] = C[c];
+        reinterpret_cast<int *>(ts)[TS::LAST * 256 + I.pix] = last; // 0: nothing of this chunk contributed before the stop
+        reinterpret_cast<int *>(ts)[TS::CSTAR * 256 + I.pix] = I.chunk;
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
-// backward
+// forward B: combine the chunks of a tile in order
+// ------------------------------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(GSD_CWARPS * 32)
+gsd_blend_fwd_combine_kernel(GsdRenderParams p) {
+    using IS = ItemState<CH>;
+    using TS = TermState<CH>;
+    const int tile = blockIdx.x;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int tx = tile % p.gx, ty = tile / p.gx;
+    const int px = tx * GSD_TILE + (warp & 1) * 8 + (lane & 7), py = ty * GSD_TILE + (warp >> 1) * 4 + (lane >> 3);
+    if (px >= p.W || py >= p.H) return;
+    const int item0 = p.chunk_ptr[tile];
+    const int nc = min(p.chunk_ptr[tile + 1], p.max_items) - item0;
+    float T = 1.0f, D = 0.f;
+    float C[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) C[c] = 0.f;
+    int last = 0;
+    if (nc > 0) {
+        const float *ts = p.term_state + (size_t)tile * TS::NF * 256;
+        const int cstar = reinterpret_cast<const int *>(ts)[TS::CSTAR * 256 + t];
+        for (int c = 0; c < nc; ++c) {
+            if (c == cstar) {
+                const int lc = reinterpret_cast<const int *>(ts)[TS::LAST * 256 + t];
+#pragma unroll
+                for (int k = 0; k < CH; ++k) C[k] += ts[(TS::C + k) * 256 + t];
+                D += ts[TS::D * 256 + t];
+                T = ts[TS::T * 256 + t];
+                if (lc > 0) last = c * GSD_CHUNK + lc;
+                break;
+            }
+            const float *st = p.chunk_state + (size_t)(item0 + c) * IS::NF * 256;
+            const int lc = reinterpret_cast<const int *>(st)[IS::LAST * 256 + t];
+            if (lc > 0) {
+#pragma unroll
+                for (int k = 0; k < CH; ++k) C[k] += T * st[(IS::C + k) * 256 + t];
+                D += T * st[IS::D * 256 + t];
+                T = __fmul_rn(T, st[IS::P * 256 + t]);
+                last = c * GSD_CHUNK + lc;
+            }
+        }
+    }
+    const size_t pid = (size_t)py * p.W + px;
+    const size_t plane = (size_t)p.W * p.H;
+    p.final_T[pid] = T;
+    p.n_contrib[pid] = last;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const float bgc = (c < 3) ? __ldg(p.bg0 + c) : (p.bg1 ? __ldg(p.bg1 + (c % 3)) : 0.f);
+        p.out_color[c * plane + pid] = C[c] + T * bgc;
+    }
+    p.out_depth[pid] = D;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward B': per chunk and pixel, the incoming transmittance and Q = dL/dC . (colour composited after this point)
+// ------------------------------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(GSD_CWARPS * 32)
+gsd_blend_bwd_prefix_kernel(GsdRenderParams p) {
+    using IS = ItemState<CH>;
+    const int tile = blockIdx.x;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int tx = tile % p.gx, ty = tile / p.gx;
+    const int px = tx * GSD_TILE + (warp & 1) * 8 + (lane & 7), py = ty * GSD_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const int item0 = p.chunk_ptr[tile];
+    const int nc = min(p.chunk_ptr[tile + 1], p.max_items) - item0;
+    if (nc <= 0) return;
+    const bool inside = px < p.W && py < p.H;
+    float dLdC[CH];
+    float Q = 0.f;
+    int last = 0;
+    if (inside) {
+        const size_t pid = (size_t)py * p.W + px;
+        const size_t plane = (size_t)p.W * p.H;
+        const float Tfin = p.final_T[pid];
+        last = p.n_contrib[pid];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const float bgc = (c < 3) ? __ldg(p.bg0 + c) : (p.bg1 ? __ldg(p.bg1 + (c % 3)) : 0.f);
+            dLdC[c] = p.dL_dcolor[c * plane + pid];
+            Q += dLdC[c] * (p.out_color[c * plane + pid] - Tfin * bgc);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) dLdC[c] = 0.f;
+    }
+    float T = 1.0f;
+    for (int c = 0; c < nc; ++c) {
+        float *st = p.chunk_state + (size_t)(item0 + c) * IS::NF * 256;
+        st[IS::TIN * 256 + t] = T;
+        st[IS::QIN * 256 + t] = Q;
+        if (c * GSD_CHUNK >= last) { // nothing of this or later chunks contributed to the pixel
+            for (int c2 = c + 1; c2 < nc; ++c2) {
+                float *s2 = p.chunk_state + (size_t)(item0 + c2) * IS::NF * 256;
+                s2[IS::TIN * 256 + t] = 0.f;
+                s2[IS::QIN * 256 + t] = 0.f;
+            }
+            break;
+        }
+        const int lc = reinterpret_cast<const int *>(st)[IS::LAST * 256 + t];
+        if (lc > 0) {
+            float cd = 0.f;
+#pragma unroll
+            for (int k = 0; k < CH; ++k) cd += dLdC[k] * st[(IS::C + k) * 256 + t];
+            Q -= T * cd;
+            T = __fmul_rn(T, st[IS::P * 256 + t]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward A': gradients of one chunk
 // ------------------------------------------------------------------------------------------------------
 // Transposed butterfly: N per-lane values are summed over the 32 lanes with ~N shuffles; afterwards the lane with
 // holder_id() == k holds the warp total of value k in v[0].
@@ -208,208 +392,181 @@ __device__ __forceinline__ int holder_id(int N, int lane) {
 }
 
 template <int CH>
-__global__ void __launch_bounds__((GSD_CWARPS + 2) * 32, 3)
-gsd_render_bwd_kernel(GsdRenderParams p) {
+__global__ void __launch_bounds__((GSD_CWARPS + 1) * 32)
+gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
     constexpr int NV = CH + 6; // colours, mean2D(2), conic(3), opacity(1)
-    constexpr int S = GSD_STAGES_B;
-    __shared__ __align__(128) float4 stage[S][4][GSD_BATCH];
-    __shared__ float acc[S][GSD_CWARPS][GSD_BATCH][NV];
+    constexpr int S = (CH == 3) ? 3 : 2; // ring of per-warp partial-sum stages (static shared memory budget)
+    using IS = ItemState<CH>;
+    __shared__ __align__(128) float4 planes[4][GSD_CHUNK];
+    __shared__ float acc[S][GSD_CWARPS][GSD_SUB][NV];
     __shared__ unsigned wmask[S][GSD_CWARPS];
-    __shared__ __align__(8) uint64_t full[S], done_bar[S], empty[S];
-    __shared__ int s_tile;
-
+    __shared__ __align__(8) uint64_t bar, done_bar[S], empty[S];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    ItemInfo I;
+    if (!item_setup(p, blockIdx.x, warp < GSD_CWARPS ? warp : 0, lane, I)) return;
     if (t == 0) {
+        mbar_init(&bar, 1);
 #pragma unroll
-        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&done_bar[s], GSD_CWARPS); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(&done_bar[s], GSD_CWARPS); mbar_init(&empty[s], 1); }
         mbar_fence_init();
     }
     __syncthreads();
-    uint32_t gb = 0;
-    const int my_val = holder_id(NV, lane);
+    if (t == 0) load_chunk<4>(p, planes, &bar, I.start, I.cnt);
+    const int nsub = (I.cnt + GSD_SUB - 1) / GSD_SUB;
+
+    if (warp == GSD_CWARPS) {
+        // ===== flusher: fixed-order sum over the consumer warps, one 64-byte partial record per instance =====
+        mbar_wait(&bar, 0);
+        for (int sb = 0; sb < nsub; ++sb) {
+            const int s = sb % S;
+            mbar_wait(&done_bar[s], (sb / S) & 1);
+            const int cnt = min(GSD_SUB, I.cnt - sb * GSD_SUB);
+            unsigned wm[GSD_CWARPS];
+#pragma unroll
+            for (int w2 = 0; w2 < GSD_CWARPS; ++w2) wm[w2] = wmask[s][w2];
+            for (int idx = lane; idx < cnt * GSD_PART_FLOATS; idx += 32) {
+                const int j = idx / GSD_PART_FLOATS, vv = idx % GSD_PART_FLOATS;
+                float sum = 0.f;
+                if (vv < NV) {
+#pragma unroll
+                    for (int w2 = 0; w2 < GSD_CWARPS; ++w2)
+                        if ((wm[w2] >> j) & 1u) sum += acc[s][w2][j][vv];
+                }
+                const uint32_t slot = __float_as_uint(planes[3][sb * GSD_SUB + j].x);
+                if ((int64_t)slot < p.plane_stride) p.partials[(size_t)slot * GSD_PART_FLOATS + vv] = sum;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        return;
+    }
+    // ===== consumers =====
+    const float pxf = (float)I.px, pyf = (float)I.py;
     const float ddelx_dx = 0.5f * p.W, ddely_dy = 0.5f * p.H;
-
-    for (;;) {
-        if (t == 0) s_tile = atomicAdd(p.next_tile, 1);
-        __syncthreads();
-        const int q = s_tile;
-        __syncthreads();
-        if (q >= p.n_tiles) break;
-        const int tile = p.tile_order[q];
-        const uint2 range = p.ranges[tile];
-        const int n = (int)(range.y - range.x);
-        const int nb = (n + GSD_BATCH - 1) / GSD_BATCH;
-
-        if (warp == GSD_CWARPS) {
-            // ===== producer =====
-            if (lane == 0) {
-                for (int b = 0; b < nb; ++b) {
-                    const uint32_t g = gb + b;
-                    const int s = g % S;
-                    if (g >= S) mbar_wait(&empty[s], ((g / S) - 1) & 1);
-                    issue_batch<4>(p, stage[s], &full[s], range.x + b * GSD_BATCH, min(GSD_BATCH, n - b * GSD_BATCH));
-                }
+    const int my_val = holder_id(NV, lane);
+    const int base = I.chunk * GSD_CHUNK; // index of the chunk's first record in the tile list
+    float T = 0.f, Q = 0.f, tail = 0.f;
+    float dLdC[CH];
+    int last = 0;
+    if (I.inside) {
+        const size_t pid = (size_t)I.py * p.W + I.px;
+        const size_t plane = (size_t)p.W * p.H;
+        const float *st = p.chunk_state + (size_t)blockIdx.x * IS::NF * 256;
+        T = st[IS::TIN * 256 + I.pix];
+        Q = st[IS::QIN * 256 + I.pix];
+        last = p.n_contrib[pid];
+        const float Tfin = p.final_T[pid];
+        float bgdot = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const float bgc = (c < 3) ? __ldg(p.bg0 + c) : (p.bg1 ? __ldg(p.bg1 + (c % 3)) : 0.f);
+            dLdC[c] = p.dL_dcolor[c * plane + pid];
+            bgdot += bgc * dLdC[c];
+        }
+        tail = Tfin * bgdot;
+    } else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) dLdC[c] = 0.f;
+    }
+    int wlast = last;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) wlast = max(wlast, __shfl_xor_sync(0xffffffffu, wlast, o));
+    mbar_wait(&bar, 0);
+    for (int sb = 0; sb < nsub; ++sb) {
+        const int s = sb % S;
+        if (sb >= S) mbar_wait(&empty[s], ((sb / S) - 1) & 1);
+        const int grp = sb * GSD_SUB;
+        unsigned touched = 0u;
+        if (base + grp < wlast) {
+            const int idx = grp + lane;
+            bool pass = false;
+            if (idx < I.cnt && base + idx < wlast) {
+                const float4 g0 = planes[0][idx];
+                pass = (g0.x + g0.z >= I.rx0) && (g0.x - g0.z <= I.rx1) && (g0.y + g0.w >= I.ry0) && (g0.y - g0.w <= I.ry1);
             }
-        } else if (warp == GSD_CWARPS + 1) {
-            // ===== flusher: fixed-order sum over the consumer warps, one 64-byte partial record per instance =====
-            for (int b = 0; b < nb; ++b) {
-                const uint32_t g = gb + b;
-                const int s = g % S;
-                mbar_wait(&done_bar[s], (g / S) & 1);
-                const int cnt = min(GSD_BATCH, n - b * GSD_BATCH);
-                unsigned wm[GSD_CWARPS];
-#pragma unroll
-                for (int w2 = 0; w2 < GSD_CWARPS; ++w2) wm[w2] = wmask[s][w2];
-                for (int idx = lane; idx < cnt * GSD_PART_FLOATS; idx += 32) {
-                    const int j = idx / GSD_PART_FLOATS, vv = idx % GSD_PART_FLOATS;
-                    float sum = 0.f;
-                    if (vv < NV) {
-#pragma unroll
-                        for (int w2 = 0; w2 < GSD_CWARPS; ++w2)
-                            if ((wm[w2] >> j) & 1u) sum += acc[s][w2][j][vv];
-                    }
-                    const uint32_t slot = __float_as_uint(stage[s][3][j].x);
-                    if ((int64_t)slot < p.plane_stride) p.partials[(size_t)slot * GSD_PART_FLOATS + vv] = sum;
+            unsigned m = __ballot_sync(0xffffffffu, pass);
+            while (m) {
+                const int jl = __ffs(m) - 1;
+                m &= m - 1;
+                const int j = grp + jl;
+                const float4 g0 = planes[0][j];
+                const float4 g1 = planes[1][j];
+                const float dx = g0.x - pxf, dy = g0.y - pyf;
+                const float power = gsd_power(g1.x, g1.y, g1.z, dx, dy);
+                const float Gr = gsd_gauss(power);
+                const float alpha = fminf(0.99f, __fmul_rn(g1.w, Gr));
+                const bool ok = (base + j < last) && (power <= 0.0f) && (alpha >= 1.0f / 255.0f);
+                if (!__any_sync(0xffffffffu, ok)) continue;
+                const float4 g2 = planes[2][j];
+                float col[CH];
+                col[0] = g2.x; col[1] = g2.y; col[2] = g2.z;
+                if (CH == 6) {
+                    const float4 g3 = planes[3][j];
+                    col[3 % CH] = g3.y; col[4 % CH] = g3.z; col[5 % CH] = g3.w;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
-            }
-        } else {
-            // ===== consumers =====
-            const int tx = tile % p.gx, ty = tile / p.gx;
-            const int wx0 = tx * GSD_TILE + (warp & 1) * 8, wy0 = ty * GSD_TILE + (warp >> 1) * 4;
-            const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
-            const float pxf = (float)px, pyf = (float)py;
-            const bool inside = px < p.W && py < p.H;
-            float T = 1.0f, Tfin = 0.f, Q = 0.f, bgdot = 0.f;
-            float dLdC[CH];
-            int last = 0;
-            if (inside && n > 0) {
-                const size_t pid = (size_t)py * p.W + px;
-                const size_t plane = (size_t)p.W * p.H;
-                Tfin = p.final_T[pid];
-                last = p.n_contrib[pid];
+                const float one_m = __fsub_rn(1.0f, alpha);
+                const float w = ok ? alpha * T : 0.f;
+                float cd = 0.f;
 #pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const float bgc = (c < 3) ? __ldg(p.bg0 + c) : (p.bg1 ? __ldg(p.bg1 + (c % 3)) : 0.f);
-                    dLdC[c] = p.dL_dcolor[c * plane + pid];
-                    Q += dLdC[c] * (p.out_color[c * plane + pid] - Tfin * bgc);
-                    bgdot += bgc * dLdC[c];
+                for (int c = 0; c < CH; ++c) cd += col[c] * dLdC[c];
+                const float Qn = Q - cd * w;
+                const float dL_dalpha = ok ? (T * cd - __fdividef(Qn + tail, one_m)) : 0.f;
+                const float Ge = ok ? Gr : 0.f;
+                float v[NV];
+#pragma unroll
+                for (int c = 0; c < CH; ++c) v[c] = w * dLdC[c];
+                const float dL_dG = g1.w * dL_dalpha;
+                const float gdx = Ge * dx, gdy = Ge * dy;
+                v[CH + 0] = dL_dG * (-gdx * g1.x - gdy * g1.y) * ddelx_dx;
+                v[CH + 1] = dL_dG * (-gdy * g1.z - gdx * g1.y) * ddely_dy;
+                v[CH + 2] = -0.5f * gdx * dx * dL_dG;
+                v[CH + 3] = -0.5f * gdx * dy * dL_dG;
+                v[CH + 4] = -0.5f * gdy * dy * dL_dG;
+                v[CH + 5] = Ge * dL_dalpha;
+                if (ok) {
+                    Q = Qn;
+                    T = __fmul_rn(T, one_m);
                 }
-            } else {
-#pragma unroll
-                for (int c = 0; c < CH; ++c) dLdC[c] = 0.f;
-            }
-            const float tail = Tfin * bgdot;
-            int wlast = last;
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) wlast = max(wlast, __shfl_xor_sync(0xffffffffu, wlast, o));
-            const float rx0 = (float)wx0, rx1 = (float)(wx0 + 7), ry0 = (float)wy0, ry1 = (float)(wy0 + 3);
-
-            for (int b = 0; b < nb; ++b) {
-                const uint32_t g = gb + b;
-                const int s = g % S;
-                mbar_wait(&full[s], (g / S) & 1);
-                const int cnt = min(GSD_BATCH, n - b * GSD_BATCH);
-                unsigned touched = 0u;
-                if (b * GSD_BATCH < wlast) {
-                    bool pass = false;
-                    if (lane < cnt && b * GSD_BATCH + lane < wlast) {
-                        const float4 g0 = stage[s][0][lane];
-                        pass = (g0.x + g0.z >= rx0) && (g0.x - g0.z <= rx1) && (g0.y + g0.w >= ry0) && (g0.y - g0.w <= ry1);
-                    }
-                    unsigned m = __ballot_sync(0xffffffffu, pass);
-                    while (m) {
-                        const int j = __ffs(m) - 1;
-                        m &= m - 1;
-                        const float4 g0 = stage[s][0][j];
-                        const float4 g1 = stage[s][1][j];
-                        const float dx = g0.x - pxf, dy = g0.y - pyf;
-                        const float power = gsd_power(g1.x, g1.y, g1.z, dx, dy);
-                        const float Gr = gsd_gauss(power);
-                        const float alpha = fminf(0.99f, __fmul_rn(g1.w, Gr));
-                        const bool ok = (b * GSD_BATCH + j < last) && (power <= 0.0f) && (alpha >= 1.0f / 255.0f);
-                        if (!__any_sync(0xffffffffu, ok)) continue;
-                        const float4 g2 = stage[s][2][j];
-                        float col[CH];
-                        col[0] = g2.x; col[1] = g2.y; col[2] = g2.z;
-                        if (CH == 6) {
-                            const float4 g3 = stage[s][3][j];
-                            col[3 % CH] = g3.y; col[4 % CH] = g3.z; col[5 % CH] = g3.w;
-                        }
-                        const float one_m = __fsub_rn(1.0f, alpha);
-                        const float w = ok ? alpha * T : 0.f;
-                        float cd = 0.f;
-#pragma unroll
-                        for (int c = 0; c < CH; ++c) cd += col[c] * dLdC[c];
-                        const float Qn = Q - cd * w;
-                        const float dL_dalpha = ok ? (T * cd - __fdividef(Qn + tail, one_m)) : 0.f;
-                        const float Ge = ok ? Gr : 0.f;
-                        float v[NV];
-#pragma unroll
-                        for (int c = 0; c < CH; ++c) v[c] = w * dLdC[c];
-                        const float dL_dG = g1.w * dL_dalpha;
-                        const float gdx = Ge * dx, gdy = Ge * dy;
-                        v[CH + 0] = dL_dG * (-gdx * g1.x - gdy * g1.y) * ddelx_dx;
-                        v[CH + 1] = dL_dG * (-gdy * g1.z - gdx * g1.y) * ddely_dy;
-                        v[CH + 2] = -0.5f * gdx * dx * dL_dG;
-                        v[CH + 3] = -0.5f * gdx * dy * dL_dG;
-                        v[CH + 4] = -0.5f * gdy * dy * dL_dG;
-                        v[CH + 5] = Ge * dL_dalpha;
-                        if (ok) {
-                            Q = Qn;
-                            T = __fmul_rn(T, one_m);
-                        }
-                        xreduce<NV, 16>(v, lane);
-                        if (my_val >= 0) acc[s][warp][j][my_val] = v[0];
-                        touched |= 1u << j;
-                    }
-                }
-                if (lane == 0) wmask[s][warp] = touched;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&done_bar[s]);
+                xreduce<NV, 16>(v, lane);
+                if (my_val >= 0) acc[s][warp][jl][my_val] = v[0];
+                touched |= 1u << jl;
             }
         }
-        gb += nb;
+        if (lane == 0) wmask[s][warp] = touched;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done_bar[s]);
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
-template <typename K>
-static int blend_grid(K kernel, int threads, int tiles) {
-    int dev = 0, sms = 148, per_sm = 1;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-    int g = sms * per_sm;
-    return tiles < g ? tiles : g;
-}
+size_t gsd_chunk_state_floats(int n_sets, int max_items) { return (size_t)(5 + 3 * n_sets) * 256 * (size_t)max_items; }
+size_t gsd_term_state_floats(int n_sets, int tiles) { return (size_t)(4 + 3 * n_sets) * 256 * (size_t)tiles; }
 
 int gsd_launch_render_fwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st) {
     if (tiles == 0) return GSD_OK;
-    const int threads = (GSD_CWARPS + 1) * 32;
-    static int grid3 = 0, grid6 = 0;
-    if (n_sets == 1) {
-        if (!grid3) grid3 = blend_grid(gsd_render_fwd_kernel<3>, threads, 1 << 30);
-        gsd_render_fwd_kernel<3><<<tiles < grid3 ? tiles : grid3, threads, 0, st>>>(p);
-    } else {
-        if (!grid6) grid6 = blend_grid(gsd_render_fwd_kernel<6>, threads, 1 << 30);
-        gsd_render_fwd_kernel<6><<<tiles < grid6 ? tiles : grid6, threads, 0, st>>>(p);
+    const int threads = GSD_CWARPS * 32;
+    if (p.max_items > 0) {
+        if (n_sets == 1) gsd_blend_fwd_chunk_kernel<3><<<p.max_items, threads, 0, st>>>(p);
+        else gsd_blend_fwd_chunk_kernel<6><<<p.max_items, threads, 0, st>>>(p);
+        GSD_LAUNCH_CHECK();
+        if (n_sets == 1) gsd_blend_fwd_term_kernel<3><<<p.max_items, threads, 0, st>>>(p);
+        else gsd_blend_fwd_term_kernel<6><<<p.max_items, threads, 0, st>>>(p);
+        GSD_LAUNCH_CHECK();
     }
+    if (n_sets == 1) gsd_blend_fwd_combine_kernel<3><<<tiles, threads, 0, st>>>(p);
+    else gsd_blend_fwd_combine_kernel<6><<<tiles, threads, 0, st>>>(p);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
 
 int gsd_launch_render_bwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st) {
-    if (tiles == 0) return GSD_OK;
-    const int threads = (GSD_CWARPS + 2) * 32;
-    static int grid3 = 0, grid6 = 0;
-    if (n_sets == 1) {
-        if (!grid3) grid3 = blend_grid(gsd_render_bwd_kernel<3>, threads, 1 << 30);
-        gsd_render_bwd_kernel<3><<<tiles < grid3 ? tiles : grid3, threads, 0, st>>>(p);
-    } else {
-        if (!grid6) grid6 = blend_grid(gsd_render_bwd_kernel<6>, threads, 1 << 30);
-        gsd_render_bwd_kernel<6><<<tiles < grid6 ? tiles : grid6, threads, 0, st>>>(p);
-    }
+    if (tiles == 0 || p.max_items == 0) return GSD_OK;
+    if (n_sets == 1) gsd_blend_bwd_prefix_kernel<3><<<tiles, GSD_CWARPS * 32, 0, st>>>(p);
+    else gsd_blend_bwd_prefix_kernel<6><<<tiles, GSD_CWARPS * 32, 0, st>>>(p);
+    GSD_LAUNCH_CHECK();
+    const int threads = (GSD_CWARPS + 1) * 32;
+    if (n_sets == 1) gsd_blend_bwd_chunk_kernel<3><<<p.max_items, threads, 0, st>>>(p);
+    else gsd_blend_bwd_chunk_kernel<6><<<p.max_items, threads, 0, st>>>(p);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
