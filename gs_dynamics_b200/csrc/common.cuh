@@ -55,17 +55,19 @@ struct GsdGeomWs { // per-Gaussian state
     uint32_t *block_base;// [ceil(G/256)] exclusive scan of block_sum
     size_t total;
 };
-#define GSD_CHUNK 256      // records per blend work item (tile lists are split into chunks processed in parallel)
+#define GSD_CHUNK 128      // records per blend work item (tile lists are split into chunks processed in parallel)
 #define GSD_BIN_BLOCK 1024 // Gaussians per binning block
 struct GsdBinWs {
     int n_bb;            // binning blocks = ceil(G / GSD_BIN_BLOCK)
     int max_items;       // upper bound of blend work items = capacity / GSD_CHUNK + tiles
     int32_t *table;      // [tiles][n_bb] per (tile, binning block) instance counts -> exclusive scan (tile-major)
+    int32_t *tile_base;  // [tiles] row totals -> exclusive scan (first slot of the tile's segment)
     uint2 *ranges;       // per tile [start,end) clipped to capacity
     int32_t *chunk_ptr;  // [tiles+1] exclusive scan of chunks per tile
     int32_t *item_tile;  // [max_items] tile of each work item
     int32_t *counters;   // [8] 0: n_items
     uint64_t *keys;      // [capacity] (depth bits << 32 | gaussian id), grouped by tile, unsorted inside a tile
+    uint64_t *keys_tmp;  // [capacity] merge-sort ping-pong buffer for tile lists that do not fit shared memory
     float4 *records;     // 4 SoA planes of [capacity] float4: packed per-instance records sorted by (tile, depth, id)
     size_t total;
 };
@@ -91,6 +93,10 @@ struct GsdRenderParams {
     const int32_t *chunk_ptr;  // [tiles+1]
     const int32_t *item_tile;  // [n_items]
     const int32_t *n_items;    // device scalar
+    // forward A1 gathers the per-Gaussian data by sorted key and writes the record planes
+    const uint64_t *keys; const float2 *g_xy; const float4 *g_conic_o; const float2 *g_ext; const float *g_depth;
+    const uint2 *g_rect; const uint32_t *g_slot_base; const float *colors0; const float *colors1;
+    float4 *planes_w;
     float *chunk_state;        // per work item: SoA fields x 256 pixels (see raster_render.cu)
     float *term_state;         // per tile: terminal record of each pixel
     int max_items;

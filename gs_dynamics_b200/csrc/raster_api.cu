@@ -118,6 +118,9 @@ extern "C" int gsd_raster_forward(const GsdRasterFwd *a, void *stream) {
     p.out_depth = a->out_depth;
     p.final_T = im.final_T;
     p.n_contrib = im.n_contrib;
+    p.keys = b.keys; p.g_xy = g.xy; p.g_conic_o = g.conic_o; p.g_ext = g.ext; p.g_depth = g.depth; p.g_rect = g.rect;
+    p.g_slot_base = g.slot_base; p.colors0 = a->colors0; p.colors1 = a->n_sets == 2 ? a->colors1 : nullptr;
+    p.planes_w = b.records;
     return gsd_launch_render_fwd(p, tiles, a->n_sets, st);
 }
 

@@ -96,19 +96,11 @@ gsd_preprocess_kernel(int G, GsdCam cam, const float *__restrict__ means3D, cons
         if ((maxx - minx) * (maxy - miny) == 0) break;
 
         float o = opacities[i];
-        // conservative half extents of {alpha >= 1/255}: d^T Q d <= 2*ln(255 o), from the conic actually blended
-        float ex = -1.f, ey = -1.f; // o < 1/255: can never contribute
-        float tau = logf(255.0f * o);
-        if (tau >= 0.f) {
-            float dq = A * C - B * B;
-            if (dq > 1e-4f * A * C && A > 0.f && C > 0.f) {
-                float t2 = 2.0f * tau * 1.002f + 1e-3f;
-                ex = sqrtf(t2 * C / dq) * 1.001f + 0.01f;
-                ey = sqrtf(t2 * A / dq) * 1.001f + 0.01f;
-            } else {
-                ex = ey = 1e30f; // ill-conditioned conic: never cull
-            }
-        }
+        // contribution bound used by the blend kernels' exact rectangle cull: a pixel at offset d contributes iff
+        // d^T Q d <= 2 ln(255 o); stored with a safety margin (o < 1/255 gives a negative bound: never contributes)
+        float ex = 2.0f * logf(255.0f * o);
+        ex = ex * (ex > 0.f ? 1.0005f : 0.9995f) + 1e-3f;
+        float ey = 0.f;
         depth[i] = pv.z;
         xy[i] = make_float2(px, py);
         conic_o[i] = make_float4(A, B, C, o);

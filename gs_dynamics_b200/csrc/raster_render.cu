@@ -23,7 +23,7 @@
 
 #define GSD_SUB 32     // records per cull group / backward sub-batch
 #define GSD_CWARPS 8   // consumer warps = 8x4 pixel rectangles of a 16x16 tile
-#define GSD_ILP 4
+#define GSD_ILP 2
 #define T_EPS 0.0001f
 #define TERMINAL_NONE (-1)
 
@@ -38,6 +38,31 @@ template <int CH> struct TermState {
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Exact test "does any pixel of the warp's 8x4 rectangle receive alpha >= 1/255 from this Gaussian": minimum of the
+// quadratic form q(d) = A dx^2 + 2 B dx dy + C dy^2 over the rectangle (in offset space) against the bound 2 ln(255 o).
+// Evaluated by ONE lane per record (32 records per warp instruction), so even ~40 flops here are ~1 warp instruction per
+// record, while every false survivor costs ~30. Anything non-finite or degenerate passes (conservative).
+__device__ __forceinline__ bool cull_pass(const float4 g0, const float4 g1, float rx0, float rx1, float ry0, float ry1) {
+    const float x0 = g0.x - rx1, x1 = g0.x - rx0, y0 = g0.y - ry1, y1 = g0.y - ry0; // offsets d = centre - pixel
+    const float A = g1.x, B = g1.y, C = g1.z;
+    if (!(A > 0.f) || !(C > 0.f)) return true;
+    const bool in_x = x0 <= 0.f && x1 >= 0.f, in_y = y0 <= 0.f && y1 >= 0.f;
+    float qmin = 0.f;
+    if (!(in_x && in_y)) {
+        const float nBA = -B / A, nBC = -B / C;
+        float ys = fminf(fmaxf(nBC * x0, y0), y1);
+        float q1 = A * x0 * x0 + 2.f * B * x0 * ys + C * ys * ys;
+        ys = fminf(fmaxf(nBC * x1, y0), y1);
+        float q2 = A * x1 * x1 + 2.f * B * x1 * ys + C * ys * ys;
+        float xs = fminf(fmaxf(nBA * y0, x0), x1);
+        float q3 = A * xs * xs + 2.f * B * xs * y0 + C * y0 * y0;
+        xs = fminf(fmaxf(nBA * y1, x0), x1);
+        float q4 = A * xs * xs + 2.f * B * xs * y1 + C * y1 * y1;
+        qmin = fminf(fminf(q1, q2), fminf(q3, q4));
+    }
+    return !(qmin * 0.9999f > g0.z);
 }
 
 struct ItemInfo { int tile, chunk, start, cnt, px, py, pix; bool inside; float rx0, rx1, ry0, ry1; };
@@ -71,21 +96,43 @@ __device__ __forceinline__ void load_chunk(const GsdRenderParams &p, float4 (*pl
 // forward A1: local composite of one chunk
 // ------------------------------------------------------------------------------------------------------
 template <int CH>
-__global__ void __launch_bounds__(GSD_CWARPS * 32)
+__global__ void __launch_bounds__(GSD_CWARPS * 32, 8)
 gsd_blend_fwd_chunk_kernel(GsdRenderParams p) {
     constexpr int NPL = (CH == 3) ? 3 : 4;
     using IS = ItemState<CH>;
     __shared__ __align__(128) float4 planes[NPL][GSD_CHUNK];
-    __shared__ __align__(8) uint64_t bar;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     ItemInfo I;
     if (!item_setup(p, blockIdx.x, warp, lane, I)) return;
-    if (t == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-    __syncthreads();
-    if (t == 0) load_chunk<NPL>(p, planes, &bar, I.start, I.cnt);
+    // gather the chunk's records by sorted key into shared memory AND into the global record planes (the backward and
+    // the termination pass stream them with TMA). One record per thread; the gathers of 8 CTAs per SM overlap.
+    for (int i = t; i < I.cnt; i += GSD_CWARPS * 32) {
+        const uint32_t g = (uint32_t)(p.keys[I.start + i] & 0xffffffffull);
+        const uint2 rc = p.g_rect[g];
+        const int minx = rc.x & 0xffff, miny = rc.x >> 16, maxx = rc.y & 0xffff;
+        const int tx = I.tile % p.gx, ty = I.tile / p.gx;
+        const uint32_t slot = p.g_slot_base[g] + (uint32_t)((ty - miny) * (maxx - minx) + (tx - minx));
+        const float2 pc = p.g_xy[g];
+        const float2 e = p.g_ext[g];
+        const float4 co = p.g_conic_o[g];
+        const float d = p.g_depth[g];
+        const float c0 = p.colors0[3 * g], c1 = p.colors0[3 * g + 1], c2 = p.colors0[3 * g + 2];
+        float c3 = 0.f, c4 = 0.f, c5 = 0.f;
+        if (CH == 6) { c3 = p.colors1[3 * g]; c4 = p.colors1[3 * g + 1]; c5 = p.colors1[3 * g + 2]; }
+        const float4 r0 = make_float4(pc.x, pc.y, e.x, e.y), r2 = make_float4(c0, c1, c2, d);
+        const float4 r3 = make_float4(__uint_as_float(slot), c3, c4, c5);
+        const int64_t j = (int64_t)I.start + i;
+        planes[0][i] = r0; planes[1][i] = co; planes[2][i] = r2;
+        if (NPL == 4) planes[NPL - 1][i] = r3;
+        p.planes_w[j] = r0;
+        p.planes_w[p.plane_stride + j] = co;
+        p.planes_w[2 * p.plane_stride + j] = r2;
+        p.planes_w[3 * p.plane_stride + j] = r3;
+    }
     float *st = p.chunk_state + (size_t)blockIdx.x * IS::NF * 256;
-    if (I.chunk == 0) // first chunk of the tile resets the tile's terminal record
-        reinterpret_cast<int *>(p.term_state + (size_t)I.tile * TermState<CH>::NF * 256)[TermState<CH>::CSTAR * 256 + I.pix] = TERMINAL_NONE;
+    int *term_i = reinterpret_cast<int *>(p.term_state + (size_t)I.tile * TermState<CH>::NF * 256);
+    const bool first = I.chunk == 0; // T_in = 1 is known: the reference's termination rule is applied right here
+    __syncthreads();
     const float pxf = (float)I.px, pyf = (float)I.py;
     float T = 1.0f, D = 0.f;
     float C[CH];
@@ -93,14 +140,13 @@ gsd_blend_fwd_chunk_kernel(GsdRenderParams p) {
     for (int c = 0; c < CH; ++c) C[c] = 0.f;
     int last = 0;
     bool dead = !I.inside; // beyond T_EPS nothing of this chunk can be used (A2 replays the chunk for such pixels)
-    mbar_wait(&bar, 0);
+    bool stopped = false;  // first chunk only: the reference's "done"
     for (int grp = 0; grp < I.cnt; grp += GSD_SUB) {
         if (__all_sync(0xffffffffu, dead)) break;
         const int idx = grp + lane;
         bool pass = false;
         if (idx < I.cnt) {
-            const float4 g0 = planes[0][idx];
-            pass = (g0.x + g0.z >= I.rx0) && (g0.x - g0.z <= I.rx1) && (g0.y + g0.w >= I.ry0) && (g0.y - g0.w <= I.ry1);
+            pass = cull_pass(planes[0][idx], planes[1][idx], I.rx0, I.rx1, I.ry0, I.ry1);
         }
         unsigned m = __ballot_sync(0xffffffffu, pass);
         while (m) {
@@ -124,7 +170,11 @@ gsd_blend_fwd_chunk_kernel(GsdRenderParams p) {
             }
 #pragma unroll
             for (int u = 0; u < GSD_ILP; ++u) {
-                const bool ok = valid[u] && (power[u] <= 0.0f) && (alpha[u] >= 1.0f / 255.0f);
+                bool ok = valid[u] && (!stopped) && (power[u] <= 0.0f) && (alpha[u] >= 1.0f / 255.0f);
+                if (first && ok && __fmul_rn(T, __fsub_rn(1.0f, alpha[u])) < T_EPS) {
+                    stopped = true;
+                    ok = false;
+                }
                 if (ok) {
                     const float w = alpha[u] * T;
                     C[0] += col[u].x * w;
@@ -142,7 +192,20 @@ gsd_blend_fwd_chunk_kernel(GsdRenderParams p) {
                 }
             }
         }
-        dead = dead || (T < T_EPS);
+        dead = dead || stopped || (T < T_EPS);
+    }
+    if (first) {
+        using TS = TermState<CH>;
+        float *ts = p.term_state + (size_t)I.tile * TS::NF * 256;
+        if (stopped) {
+            ts[TS::T * 256 + I.pix] = T;
+            ts[TS::D * 256 + I.pix] = D;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) ts[(TS::C + c) * 256 + I.pix] = C[c];
+            term_i[TS::LAST * 256 + I.pix] = last;
+        }
+        term_i[TS::CSTAR * 256 + I.pix] = stopped ? 0 : TERMINAL_NONE;
+        if (stopped) T = 0.f; // later chunks see a dead pixel
     }
     st[IS::P * 256 + I.pix] = T;
     st[IS::D * 256 + I.pix] = D;
@@ -165,15 +228,24 @@ gsd_blend_fwd_term_kernel(GsdRenderParams p) {
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     ItemInfo I;
     if (!item_setup(p, blockIdx.x, warp, lane, I)) return;
+    if (I.chunk == 0) return; // handled exactly by A1
     const int item0 = blockIdx.x - I.chunk;
     // T_in = product of the preceding chunks' P (same order and ops in every kernel that rebuilds it)
     float T = 1.0f;
     bool dead = !I.inside;
-    for (int c = 0; c < I.chunk && !dead; ++c) {
-        const float Pc = p.chunk_state[(size_t)(item0 + c) * IS::NF * 256 + IS::P * 256 + I.pix];
-        const float Tn = __fmul_rn(T, Pc);
-        if (Tn < T_EPS) dead = true; // terminated in an earlier chunk
-        T = Tn;
+    for (int c0 = 0; c0 < I.chunk && !dead; c0 += 8) {
+        float Pc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) // independent loads in flight
+            Pc[u] = (c0 + u < I.chunk) ? p.chunk_state[(size_t)(item0 + c0 + u) * IS::NF * 256 + IS::P * 256 + I.pix] : 1.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (c0 + u < I.chunk && !dead) {
+                const float Tn = __fmul_rn(T, Pc[u]);
+                if (Tn < T_EPS) dead = true; // terminated in an earlier chunk
+                T = Tn;
+            }
+        }
     }
     const float Pme = p.chunk_state[(size_t)blockIdx.x * IS::NF * 256 + IS::P * 256 + I.pix];
     const bool crossing = !dead && (__fmul_rn(T, Pme) < T_EPS);
@@ -196,8 +268,7 @@ gsd_blend_fwd_term_kernel(GsdRenderParams p) {
         const int idx = grp + lane;
         bool pass = false;
         if (idx < I.cnt) {
-            const float4 g0 = planes[0][idx];
-            pass = (g0.x + g0.z >= I.rx0) && (g0.x - g0.z <= I.rx1) && (g0.y + g0.w >= I.ry0) && (g0.y - g0.w <= I.ry1);
+            pass = cull_pass(planes[0][idx], planes[1][idx], I.rx0, I.rx1, I.ry0, I.ry1);
         }
         unsigned m = __ballot_sync(0xffffffffu, pass);
         while (m) {
@@ -392,7 +463,7 @@ __device__ __forceinline__ int holder_id(int N, int lane) {
 }
 
 template <int CH>
-__global__ void __launch_bounds__((GSD_CWARPS + 1) * 32)
+__global__ void __launch_bounds__((GSD_CWARPS + 1) * 32, 5)
 gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
     constexpr int NV = CH + 6; // colours, mean2D(2), conic(3), opacity(1)
     constexpr int S = (CH == 3) ? 3 : 2; // ring of per-warp partial-sum stages (static shared memory budget)
@@ -481,8 +552,7 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
             const int idx = grp + lane;
             bool pass = false;
             if (idx < I.cnt && base + idx < wlast) {
-                const float4 g0 = planes[0][idx];
-                pass = (g0.x + g0.z >= I.rx0) && (g0.x - g0.z <= I.rx1) && (g0.y + g0.w >= I.ry0) && (g0.y - g0.w <= I.ry1);
+                pass = cull_pass(planes[0][idx], planes[1][idx], I.rx0, I.rx1, I.ry0, I.ry1);
             }
             unsigned m = __ballot_sync(0xffffffffu, pass);
             while (m) {

@@ -70,6 +70,25 @@ def test_backward_parity(G, w, h, seed, boost):
     assert rel_err(gr["rotations"].cpu(), bo["rotations"]) < tol
 
 
+def test_long_tile_lists_global_merge_path():
+    """Tiles with more instances than the shared-memory sort holds (> 2048) and many chunks per tile."""
+    from gs_dynamics_b200 import rasterizer as R
+    cam = make_camera(1, 64, 48)
+    sc, act = make_scene(30000, 12, scale_boost=0.3, box_scale=0.5)
+    bg = [0.05, 0.1, 0.15]
+    fo = oracle_forward(act, cam, torch.tensor(bg))
+    assert fo["R"] / 12 > 2500
+    color, radii, depth, state = _render(_to_cuda(act), settings_from(cam, bg))
+    assert np.array_equal(radii.cpu().numpy(), fo["radii"])
+    _img_close(color.cpu().numpy(), fo["color"])
+    _img_close(depth.cpu().numpy(), fo["depth"])
+    dL = torch.randn(3, 48, 64, generator=torch.Generator().manual_seed(0))
+    bo = oracle_backward(act, cam, torch.tensor(bg), dL)
+    gr = R.raster_backward(state, dL.cuda())
+    for k, ko in (("means3D", "means3D"), ("colors0", "colors"), ("rotations", "rotations"), ("scales", "scales")):
+        assert rel_err(gr[k].cpu(), bo[ko]) < 1e-3, k
+
+
 def test_autograd_module_surface():
     """The reference's call pattern: keyword call, means2D as gradient sink (train_utils.py:174-178)."""
     from gs_dynamics_b200.rasterizer import GaussianRasterizer
