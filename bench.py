@@ -165,13 +165,13 @@ def run_ours(args):
     rng = random.Random(0)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
 
-    step_obj = TR.TrackingStep(params, variables, opt, dataset, use_graph=True)
+    step_obj = TR.FusedTrackingStep(params, variables, opt, dataset, use_graph=True)
     own0, lib0 = _lib.launch_count()
     step_obj.prepare()
     own1, lib1 = _lib.launch_count()
     # prepare() = capacity probe (1 fwd) + 1 eager warm-up + 1 captured iteration per camera
     # launches of ONE iteration: measure on an eager replay
-    eager = TR.TrackingStep(params, variables, opt, dataset, use_graph=False)
+    eager = TR.FusedTrackingStep(params, variables, opt, dataset, use_graph=False)
     eager.capacity = dict(step_obj.capacity)
     a0 = _lib.launch_count()
     eager.step(0)
@@ -204,20 +204,14 @@ def run_ours(args):
     dev_s = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end to end through the public API with host buffers
-    stage_im = torch.empty_like(dataset[0]["im"])
-    stage_seg = torch.empty_like(dataset[0]["seg"])
-    e2e_data = [dict(d, im=stage_im, seg=stage_seg) for d in dataset]
-    e2e = TR.TrackingStep(params, variables, opt, e2e_data, use_graph=True)
-    e2e.capacity = dict(step_obj.capacity)
-    e2e.prepare()
+    # ---- end to end through the public API with host buffers: the step's camera image + seg come from pinned host memory
+    # into the step's target buffers, the loss is read back and consumed on the host, every step
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-    h2d = stage_im.numel() * 4 + stage_seg.numel() * 4
+    h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4
 
     def e2e_step(c):
-        stage_im.copy_(host[c][0], non_blocking=True)
-        stage_seg.copy_(host[c][1], non_blocking=True)
-        l = e2e.step(c)
+        step_obj.set_target(c, host[c][0], host[c][1])
+        l = step_obj.step(c)
         loss_host.copy_(l, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller consumes the loss every step
         return float(loss_host)
@@ -269,7 +263,7 @@ def run_ours(args):
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(own_per_iter * args.steps), "gpu_launches_per_step": int(own_per_iter),
             "library_launches_per_step": int(lib_per_iter),
-            "roofline": {"bound": "hbm", "kernel": "gsd_render_bwd_kernel<6>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "gsd_blend_bwd_chunk_kernel<6> (+ prefix kernel)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
                          "kernel_us": t_blend * 1e6},
             "clocks": clocks, "wall_s": t_wall, "final_loss": last_loss,

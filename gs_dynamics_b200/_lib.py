@@ -54,6 +54,24 @@ class GsdTrackLosses(C.Structure):
     ]
 
 
+class GsdPhotometric(C.Structure):
+    _fields_ = [
+        ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("n_sets", C.c_int32),
+        ("x", C.c_void_p), ("y", C.c_void_p), ("affine_log_scale", C.c_void_p), ("affine_shift", C.c_void_p),
+        ("w_l1", C.c_float), ("w_ssim", C.c_float), ("set_weight", C.c_float * 2), ("ws", C.c_void_p),
+    ]
+
+
+class GsdTrackUpdate(C.Structure):
+    _fields_ = [
+        ("G", C.c_int32), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("lr_means", C.c_float),
+        ("lr_rot", C.c_float),
+        ("means3D", C.c_void_p), ("unnorm_rotations", C.c_void_p), ("g_means_a", C.c_void_p), ("g_means_b", C.c_void_p),
+        ("g_rot_a", C.c_void_p), ("g_rot_b", C.c_void_p), ("m_means", C.c_void_p), ("v_means", C.c_void_p),
+        ("m_rot", C.c_void_p), ("v_rot", C.c_void_p), ("step_means", C.c_void_p), ("step_rot", C.c_void_p),
+    ]
+
+
 class GsdAdam(C.Structure):
     _fields_ = [
         ("n_tensors", C.c_int32), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
@@ -83,6 +101,7 @@ EXPORTS = [
     "gsd_raster_mark_visible",
     "gsd_photometric_workspace_bytes", "gsd_photometric_forward", "gsd_photometric_backward",
     "gsd_track_losses_workspace_bytes", "gsd_track_losses_fwd_bwd", "gsd_adam_step", "gsd_track_update_radii",
+    "gsd_track_normalize_rotations", "gsd_track_update",
     "gsd_gnn_edges_workspace_bytes", "gsd_gnn_build_edges", "gsd_gnn_edge_inputs", "gsd_gnn_aggregate_workspace_bytes",
     "gsd_gnn_aggregate", "gsd_fps",
 ]
@@ -107,10 +126,10 @@ def lib():
     l.gsd_launch_count.restype = None
     l.gsd_raster_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_photometric_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
-    l.gsd_photometric_forward.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
-                                          C.c_void_p, C.c_void_p, C.c_void_p]
-    l.gsd_photometric_backward.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
-                                           C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    l.gsd_photometric_forward.argtypes = [C.POINTER(GsdPhotometric), C.c_void_p, C.c_void_p]
+    l.gsd_photometric_backward.argtypes = [C.POINTER(GsdPhotometric), C.c_void_p, C.c_void_p, C.c_void_p]
+    l.gsd_track_normalize_rotations.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.gsd_track_update.argtypes = [C.POINTER(GsdTrackUpdate), C.c_void_p]
     l.gsd_track_losses_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
     l.gsd_track_losses_fwd_bwd.argtypes = [C.POINTER(GsdTrackLosses), C.c_void_p]
     l.gsd_adam_step.argtypes = [C.POINTER(GsdAdam), C.c_void_p]

@@ -88,3 +88,82 @@ extern "C" int gsd_track_update_radii(int32_t G, const int32_t *radii, float *ma
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// steady-state fast path: F.normalize forward, and (normalize backward + gradient sum + Adam) for the two live groups
+// ------------------------------------------------------------------------------------------------------
+__global__ void gsd_normalize_rot_kernel(int G, const float4 *__restrict__ q, float4 *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G) return;
+    float4 v = q[i];
+    float n = fmaxf(sqrtf(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w), 1e-12f); // F.normalize eps
+    out[i] = make_float4(v.x / n, v.y / n, v.z / n, v.w / n);
+}
+
+extern "C" int gsd_track_normalize_rotations(int32_t G, const float *unnorm, float *rot, void *stream) {
+    if (G < 0 || (G > 0 && (!unnorm || !rot))) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
+    if (G == 0) return GSD_OK;
+    gsd_normalize_rot_kernel<<<(G + 255) / 256, 256, 0, (cudaStream_t)stream>>>(G, (const float4 *)unnorm, (float4 *)rot);
+    GSD_LAUNCH_CHECK();
+    return GSD_OK;
+}
+
+__device__ __forceinline__ float adam_1(float p, float g, float &m, float &v, float b1, float b2, float eps, float lr_bc1, float inv_sqrt_bc2) {
+    m = b1 * m + (1.f - b1) * g;
+    v = b2 * v + (1.f - b2) * g * g;
+    return p - lr_bc1 * (m / (sqrtf(v) * inv_sqrt_bc2 + eps));
+}
+
+__global__ void __launch_bounds__(256)
+gsd_track_update_kernel(GsdTrackUpdate u) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= u.G) return;
+    const float sm = *u.step_means + 1.f, sr = *u.step_rot + 1.f;
+    const float lrm = u.lr_means / (1.f - powf(u.beta1, sm)), ism = 1.f / sqrtf(1.f - powf(u.beta2, sm));
+    const float lrr = u.lr_rot / (1.f - powf(u.beta1, sr)), isr = 1.f / sqrtf(1.f - powf(u.beta2, sr));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const size_t k = 3 * (size_t)i + c;
+        float g = u.g_means_a[k] + (u.g_means_b ? u.g_means_b[k] : 0.f);
+        float m = u.m_means[k], v = u.v_means[k];
+        u.means3D[k] = adam_1(u.means3D[k], g, m, v, u.beta1, u.beta2, u.eps, lrm, ism);
+        u.m_means[k] = m; u.v_means[k] = v;
+    }
+    float4 q = reinterpret_cast<const float4 *>(u.unnorm_rotations)[i];
+    float4 ga = reinterpret_cast<const float4 *>(u.g_rot_a)[i];
+    if (u.g_rot_b) {
+        float4 gb = reinterpret_cast<const float4 *>(u.g_rot_b)[i];
+        ga.x += gb.x; ga.y += gb.y; ga.z += gb.z; ga.w += gb.w;
+    }
+    const float n = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+    const float4 qn = make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
+    const float dot = qn.x * ga.x + qn.y * ga.y + qn.z * ga.z + qn.w * ga.w;
+    const float gq[4] = {(ga.x - qn.x * dot) / n, (ga.y - qn.y * dot) / n, (ga.z - qn.z * dot) / n, (ga.w - qn.w * dot) / n};
+    float4 m4 = reinterpret_cast<float4 *>(u.m_rot)[i], v4 = reinterpret_cast<float4 *>(u.v_rot)[i];
+    float qo[4] = {q.x, q.y, q.z, q.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) qo[c] = adam_1(qo[c], gq[c], mm[c], vv[c], u.beta1, u.beta2, u.eps, lrr, isr);
+    reinterpret_cast<float4 *>(u.unnorm_rotations)[i] = make_float4(qo[0], qo[1], qo[2], qo[3]);
+    reinterpret_cast<float4 *>(u.m_rot)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4 *>(u.v_rot)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+}
+__global__ void gsd_track_update_advance_kernel(float *a, float *b) {
+    *a += 1.0f;
+    if (b != a) *b += 1.0f;
+}
+
+extern "C" int gsd_track_update(const GsdTrackUpdate *u, void *stream) {
+    if (!u || u->G < 0) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
+    if (u->G == 0) return GSD_OK;
+    if (!u->means3D || !u->unnorm_rotations || !u->g_means_a || !u->g_rot_a || !u->m_means || !u->v_means || !u->m_rot || !u->v_rot ||
+        !u->step_means || !u->step_rot) {
+        gsd_set_error("null pointer in GsdTrackUpdate");
+        return GSD_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    gsd_track_update_kernel<<<(u->G + 255) / 256, 256, 0, st>>>(*u);
+    GSD_LAUNCH_CHECK();
+    gsd_track_update_advance_kernel<<<1, 1, 0, st>>>(u->step_means, u->step_rot);
+    GSD_LAUNCH_CHECK();
+    return GSD_OK;
+}

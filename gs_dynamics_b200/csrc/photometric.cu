@@ -1,29 +1,41 @@
 // photometric.cu — fused photometric loss of the tracking iteration:
-//     loss = w_l1 * mean|x - y| + w_ssim * (1 - mean SSIM_11x11,sigma=1.5(x, y))
-// and its gradient w.r.t. x, in two kernels (statistics + gradient) instead of the reference's 5 depthwise
+//     loss = w_l1 * mean|x - y| + w_ssim * (1 - mean SSIM_11x11,sigma=1.5(x, y)),   x = scale_c * rendered + shift_c
+// and its gradient w.r.t. the rendered image, in two kernels (statistics + gradient) instead of the reference's 5 depthwise
 // cuDNN convolutions forward + their backward per call, with the window rebuilt on the host every call
 // (/root/reference/src/tracking/external.py:101-135 calc_ssim/_ssim, src/tracking/helpers.py:71-72 l1_loss_v1,
-//  called at /root/reference/src/tracking/train_utils.py:185,195).
+//  called at /root/reference/src/tracking/train_utils.py:182-185,195; the affine is the cam_m / cam_c correction of :182).
+// Channels are grouped in sets of 3 (RGB render, seg render) with their own loss weight so that both losses of an
+// iteration are one launch.
 //
 // Both kernels are separable 11-tap stencils over 32x32 tiles staged in shared memory (halo 5, zero padding like
-// conv2d(padding=5)); HBM traffic per call: read x,y + write 3 partial maps (kernel 1), read 3 maps + x,y, write
-// the gradient (kernel 2) = 40 B/pixel/channel.  Block partial sums are written to a buffer and reduced in fixed
-// order (deterministic).
+// conv2d(padding=5)); each thread produces 4 consecutive outputs per pass from a 14-value register window (8x fewer
+// shared-memory reads than one output per thread).  HBM traffic per call: read x,y + write 3 partial maps (kernel 1),
+// read 3 maps + x,y, write the gradient (kernel 2) = 40 B/pixel/channel.  Block partial sums are written to a buffer and
+// reduced in fixed order (deterministic).
 #include "common.cuh"
 
 #define PH_T 32          // tile edge
 #define PH_R 5           // window radius
 #define PH_E (PH_T + 2 * PH_R)
+#define PH_MAXC 6
 
 struct PhWin { float g[11]; };
+struct PhAffine { float scale[PH_MAXC], shift[PH_MAXC]; int on; };
 
 __device__ __forceinline__ float ph_load(const float *img, int W, int H, int x, int y) {
     return (x >= 0 && x < W && y >= 0 && y < H) ? img[(size_t)y * W + x] : 0.f;
 }
 
+// affine parameters may live on the device (cam_m / cam_c rows): scale = exp(m[c]), shift = c[c]
+__device__ __forceinline__ void ph_affine(const float *log_scale, const float *shift, int c, float &s, float &b) {
+    s = log_scale ? __expf(log_scale[c % 3]) : 1.0f;
+    b = shift ? shift[c % 3] : 0.0f;
+}
+
 // kernel 1: per pixel SSIM partials dS/dmu1, dS/ds11, dS/ds12 + block sums of |x-y| and SSIM
 __global__ void __launch_bounds__(256)
 gsd_ssim_stats_kernel(int C, int H, int W, PhWin win, const float *__restrict__ X, const float *__restrict__ Y,
+                      const float *__restrict__ log_scale, const float *__restrict__ shift, int affine_channels,
                       float *__restrict__ dmu, float *__restrict__ ds11, float *__restrict__ ds12,
                       float *__restrict__ block_sums /* [nblocks][2] */) {
     __shared__ float sx[PH_E][PH_E + 1], sy[PH_E][PH_E + 1];
@@ -33,53 +45,73 @@ gsd_ssim_stats_kernel(int C, int H, int W, PhWin win, const float *__restrict__ 
     const int x0 = blockIdx.x * PH_T, y0 = blockIdx.y * PH_T;
     const float *Xc = X + (size_t)c * H * W, *Yc = Y + (size_t)c * H * W;
     const int t = threadIdx.x;
+    float as = 1.f, ab = 0.f;
+    if (c < affine_channels) ph_affine(log_scale, shift, c, as, ab);
     for (int i = t; i < PH_E * PH_E; i += 256) {
         int ly = i / PH_E, lx = i % PH_E;
-        sx[ly][lx] = ph_load(Xc, W, H, x0 + lx - PH_R, y0 + ly - PH_R);
-        sy[ly][lx] = ph_load(Yc, W, H, x0 + lx - PH_R, y0 + ly - PH_R);
+        const int gx = x0 + lx - PH_R, gy = y0 + ly - PH_R;
+        const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
+        sx[ly][lx] = in ? as * Xc[(size_t)gy * W + gx] + ab : 0.f;
+        sy[ly][lx] = in ? Yc[(size_t)gy * W + gx] : 0.f;
     }
     __syncthreads();
-    for (int i = t; i < PH_E * PH_T; i += 256) {
-        int ly = i / PH_T, lx = i % PH_T;
-        float a = 0.f, b = 0.f, aa = 0.f, bb = 0.f, ab = 0.f;
+    // horizontal pass: unit = (row, segment of 4 outputs); consecutive lanes take consecutive rows (pitch 43: no conflicts)
+    for (int u = t; u < PH_E * (PH_T / 4); u += 256) {
+        const int ly = u % PH_E, seg = u / PH_E;
+        float xv[14], yv[14];
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            float xv = sx[ly][lx + k], yv = sy[ly][lx + k], w = win.g[k];
-            a += w * xv; b += w * yv; aa += w * xv * xv; bb += w * yv * yv; ab += w * xv * yv;
+        for (int k = 0; k < 14; ++k) { xv[k] = sx[ly][seg * 4 + k]; yv[k] = sy[ly][seg * 4 + k]; }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float a = 0.f, b = 0.f, aa = 0.f, bb = 0.f, ab2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) {
+                const float w = win.g[k], xx = xv[o + k], yy = yv[o + k];
+                a += w * xx; b += w * yy; aa += w * xx * xx; bb += w * yy * yy; ab2 += w * xx * yy;
+            }
+            const int lx = seg * 4 + o;
+            h[0][ly][lx] = a; h[1][ly][lx] = b; h[2][ly][lx] = aa; h[3][ly][lx] = bb; h[4][ly][lx] = ab2;
         }
-        h[0][ly][lx] = a; h[1][ly][lx] = b; h[2][ly][lx] = aa; h[3][ly][lx] = bb; h[4][ly][lx] = ab;
     }
     __syncthreads();
+    // vertical pass: thread = (column, segment of 4 rows)
     float l1 = 0.f, ss = 0.f;
-    for (int i = t; i < PH_T * PH_T; i += 256) {
-        int ly = i / PH_T, lx = i % PH_T;
-        int gx = x0 + lx, gy = y0 + ly;
-        if (gx >= W || gy >= H) continue;
-        float mu1 = 0.f, mu2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+    {
+        const int lx = t % PH_T, seg = t / PH_T; // 32 columns x 8 segments
+        float v[5][14];
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            float w = win.g[k];
-            mu1 += w * h[0][ly + k][lx]; mu2 += w * h[1][ly + k][lx];
-            s11 += w * h[2][ly + k][lx]; s22 += w * h[3][ly + k][lx]; s12 += w * h[4][ly + k][lx];
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+            for (int k = 0; k < 14; ++k) v[q][k] = h[q][seg * 4 + k][lx];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int ly = seg * 4 + o;
+            const int gx = x0 + lx, gy = y0 + ly;
+            float mu1 = 0.f, mu2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) {
+                const float w = win.g[k];
+                mu1 += w * v[0][o + k]; mu2 += w * v[1][o + k]; s11 += w * v[2][o + k]; s22 += w * v[3][o + k]; s12 += w * v[4][o + k];
+            }
+            if (gx < W && gy < H) {
+                const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+                const float mu1sq = mu1 * mu1, mu2sq = mu2 * mu2, mu12 = mu1 * mu2;
+                const float sig1 = s11 - mu1sq, sig2 = s22 - mu2sq, sig12 = s12 - mu12;
+                const float A1 = 2.f * mu12 + C1, A2 = 2.f * sig12 + C2;
+                const float B1 = mu1sq + mu2sq + C1, B2 = sig1 + sig2 + C2;
+                const float inv = 1.f / (B1 * B2);
+                const float S = A1 * A2 * inv;
+                const float dS_dA1 = A2 * inv, dS_dA2 = A1 * inv, dS_dB1 = -S / B1, dS_dB2 = -S / B2;
+                const float d_mu1 = dS_dA1 * 2.f * mu2 + dS_dA2 * (-2.f * mu2) + dS_dB1 * 2.f * mu1 + dS_dB2 * (-2.f * mu1);
+                const size_t pid = (size_t)c * H * W + (size_t)gy * W + gx;
+                dmu[pid] = d_mu1;
+                ds11[pid] = dS_dB2;
+                ds12[pid] = 2.f * dS_dA2;
+                ss += S;
+                l1 += fabsf(sx[ly + PH_R][lx + PH_R] - sy[ly + PH_R][lx + PH_R]);
+            }
         }
-        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-        float mu1sq = mu1 * mu1, mu2sq = mu2 * mu2, mu12 = mu1 * mu2;
-        float sig1 = s11 - mu1sq, sig2 = s22 - mu2sq, sig12 = s12 - mu12;
-        float A1 = 2.f * mu12 + C1, A2 = 2.f * sig12 + C2;
-        float B1 = mu1sq + mu2sq + C1, B2 = sig1 + sig2 + C2;
-        float inv = 1.f / (B1 * B2);
-        float S = A1 * A2 * inv;
-        // dS/dmu1 (through A1, A2, B1, B2), dS/ds11 (through B2), dS/ds12 (through A2)
-        float dS_dA1 = A2 * inv, dS_dA2 = A1 * inv, dS_dB1 = -S / B1, dS_dB2 = -S / B2;
-        float d_mu1 = dS_dA1 * 2.f * mu2 + dS_dA2 * (-2.f * mu2) + dS_dB1 * 2.f * mu1 + dS_dB2 * (-2.f * mu1);
-        size_t pid = (size_t)c * H * W + (size_t)gy * W + gx;
-        dmu[pid] = d_mu1;
-        ds11[pid] = dS_dB2;
-        ds12[pid] = 2.f * dS_dA2;
-        ss += S;
-        l1 += fabsf(sx[ly + PH_R][lx + PH_R] - sy[ly + PH_R][lx + PH_R]);
     }
-    // block reduce (fixed order)
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
         l1 += __shfl_xor_sync(0xffffffffu, l1, o);
@@ -96,31 +128,41 @@ gsd_ssim_stats_kernel(int C, int H, int W, PhWin win, const float *__restrict__ 
     }
 }
 
-// fixed-order final reduction: out[0] = loss, out[1] = mean|x-y|, out[2] = mean SSIM
-__global__ void gsd_ssim_finish_kernel(int nblocks, const float *__restrict__ block_sums, float inv_n, float w_l1,
-                                       float w_ssim, float *__restrict__ out) {
+// fixed-order final reduction per set of 3 channels: out[3*s + 0] = loss_s, [1] = mean|x-y|, [2] = mean SSIM;
+// out[3*n_sets] = sum_s set_weight[s] * loss_s
+__global__ void gsd_ssim_finish_kernel(int n_sets, int blocks_per_set, const float *__restrict__ block_sums, float inv_n,
+                                       float w_l1, float w_ssim, float sw0, float sw1, float *__restrict__ out) {
     __shared__ double r0[256], r1[256];
-    double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < nblocks; i += 256) { a += block_sums[2 * i]; b += block_sums[2 * i + 1]; }
-    r0[threadIdx.x] = a; r1[threadIdx.x] = b;
-    __syncthreads();
-    for (int s = 128; s >= 1; s >>= 1) {
-        if (threadIdx.x < s) { r0[threadIdx.x] += r0[threadIdx.x + s]; r1[threadIdx.x] += r1[threadIdx.x + s]; }
+    float total = 0.f;
+    for (int s = 0; s < n_sets; ++s) {
+        double a = 0.0, b = 0.0;
+        for (int i = threadIdx.x; i < blocks_per_set; i += 256) {
+            a += block_sums[2 * ((size_t)s * blocks_per_set + i)];
+            b += block_sums[2 * ((size_t)s * blocks_per_set + i) + 1];
+        }
+        r0[threadIdx.x] = a; r1[threadIdx.x] = b;
+        __syncthreads();
+        for (int k = 128; k >= 1; k >>= 1) {
+            if (threadIdx.x < k) { r0[threadIdx.x] += r0[threadIdx.x + k]; r1[threadIdx.x] += r1[threadIdx.x + k]; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            float ml1 = (float)(r0[0] * inv_n), ms = (float)(r1[0] * inv_n);
+            float l = w_l1 * ml1 + w_ssim * (1.0f - ms);
+            out[3 * s] = l; out[3 * s + 1] = ml1; out[3 * s + 2] = ms;
+            total += (s == 0 ? sw0 : sw1) * l;
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        float ml1 = (float)(r0[0] * inv_n), ms = (float)(r1[0] * inv_n);
-        out[0] = w_l1 * ml1 + w_ssim * (1.0f - ms);
-        out[1] = ml1;
-        out[2] = ms;
-    }
+    if (threadIdx.x == 0) out[3 * n_sets] = total;
 }
 
-// kernel 2: grad_x = gscale * ( w_l1*sign(x-y)/N - w_ssim/N * (conv(dmu) + 2x*conv(ds11) + y*conv(ds12)) )
+// kernel 2: d loss / d rendered = gscale * set_weight * scale_c * ( w_l1*sign(x-y)/N - w_ssim/N * (conv(dmu) + 2x*conv(ds11) + y*conv(ds12)) )
 __global__ void __launch_bounds__(256)
 gsd_ssim_grad_kernel(int C, int H, int W, PhWin win, const float *__restrict__ X, const float *__restrict__ Y,
+                     const float *__restrict__ log_scale, const float *__restrict__ shift, int affine_channels,
                      const float *__restrict__ dmu, const float *__restrict__ ds11, const float *__restrict__ ds12,
-                     const float *__restrict__ gscale_ptr, float gscale_mul, float w_l1, float w_ssim, float inv_n,
+                     const float *__restrict__ gscale_ptr, float sw0, float sw1, float w_l1, float w_ssim, float inv_n,
                      float *__restrict__ grad) {
     __shared__ float sm[3][PH_E][PH_E + 1];
     __shared__ float h[3][PH_E][PH_T + 1];
@@ -136,32 +178,47 @@ gsd_ssim_grad_kernel(int C, int H, int W, PhWin win, const float *__restrict__ X
         sm[2][ly][lx] = ph_load(ds12 + coff, W, H, gx, gy);
     }
     __syncthreads();
-    for (int i = t; i < PH_E * PH_T; i += 256) {
-        int ly = i / PH_T, lx = i % PH_T;
-        float a = 0.f, b = 0.f, d = 0.f;
+    for (int u = t; u < PH_E * (PH_T / 4); u += 256) {
+        const int ly = u % PH_E, seg = u / PH_E;
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            float w = win.g[k];
-            a += w * sm[0][ly][lx + k]; b += w * sm[1][ly][lx + k]; d += w * sm[2][ly][lx + k];
+        for (int q = 0; q < 3; ++q) {
+            float v[14];
+#pragma unroll
+            for (int k = 0; k < 14; ++k) v[k] = sm[q][ly][seg * 4 + k];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 11; ++k) a += win.g[k] * v[o + k];
+                h[q][ly][seg * 4 + o] = a;
+            }
         }
-        h[0][ly][lx] = a; h[1][ly][lx] = b; h[2][ly][lx] = d;
     }
     __syncthreads();
-    const float gs = (gscale_ptr ? *gscale_ptr : 1.0f) * gscale_mul;
-    for (int i = t; i < PH_T * PH_T; i += 256) {
-        int ly = i / PH_T, lx = i % PH_T;
-        int gx = x0 + lx, gy = y0 + ly;
+    float as = 1.f, ab = 0.f;
+    if (c < affine_channels) ph_affine(log_scale, shift, c, as, ab);
+    const float gs = (gscale_ptr ? *gscale_ptr : 1.0f) * (c < 3 ? sw0 : sw1) * as;
+    const int lx = t % PH_T, seg = t / PH_T;
+    float v[3][14];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int k = 0; k < 14; ++k) v[q][k] = h[q][seg * 4 + k][lx];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        const int ly = seg * 4 + o;
+        const int gx = x0 + lx, gy = y0 + ly;
         if (gx >= W || gy >= H) continue;
         float a = 0.f, b = 0.f, d = 0.f;
 #pragma unroll
         for (int k = 0; k < 11; ++k) {
-            float w = win.g[k];
-            a += w * h[0][ly + k][lx]; b += w * h[1][ly + k][lx]; d += w * h[2][ly + k][lx];
+            const float w = win.g[k];
+            a += w * v[0][o + k]; b += w * v[1][o + k]; d += w * v[2][o + k];
         }
-        size_t pid = coff + (size_t)gy * W + gx;
-        float xv = X[pid], yv = Y[pid];
-        float df = xv - yv;
-        float sgn = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+        const size_t pid = coff + (size_t)gy * W + gx;
+        const float xv = as * X[pid] + ab, yv = Y[pid];
+        const float df = xv - yv;
+        const float sgn = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
         grad[pid] = gs * inv_n * (w_l1 * sgn - w_ssim * (a + 2.f * xv * b + yv * d));
     }
 }
@@ -187,42 +244,60 @@ extern "C" int gsd_photometric_workspace_bytes(int32_t C, int32_t H, int32_t W, 
     return GSD_OK;
 }
 
-// loss_out[3] = {loss, mean|x-y|, mean SSIM}; ws keeps the partial maps for the backward call
-extern "C" int gsd_photometric_forward(int32_t C, int32_t H, int32_t W, const float *x, const float *y, float w_l1,
-                                       float w_ssim, void *ws, float *loss_out, void *stream) {
-    if (C <= 0 || H <= 0 || W <= 0 || !x || !y || !ws || !loss_out) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
+static int ph_check(const GsdPhotometric *p) {
+    if (!p || p->H <= 0 || p->W <= 0 || (p->n_sets != 1 && p->n_sets != 2) || p->C != (p->n_sets == 2 ? 6 : p->C) || p->C <= 0 ||
+        p->C > PH_MAXC || !p->x || !p->y || !p->ws) {
+        gsd_set_error("invalid photometric descriptor");
+        return GSD_ERR_INVALID;
+    }
+    return GSD_OK;
+}
+
+// loss_out: per set {loss, mean|x-y|, mean SSIM}, then the weighted total  (3*n_sets + 1 floats)
+extern "C" int gsd_photometric_forward(const GsdPhotometric *p, float *loss_out, void *stream) {
+    int rc;
+    if ((rc = ph_check(p))) return rc;
+    if (!loss_out) { gsd_set_error("null loss_out"); return GSD_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
+    const int C = p->C, H = p->H, W = p->W;
     size_t n = (size_t)C * H * W;
-    char *p = (char *)ws;
-    float *dmu = (float *)p; p += gsd_align_up(n * 4);
-    float *ds11 = (float *)p; p += gsd_align_up(n * 4);
-    float *ds12 = (float *)p; p += gsd_align_up(n * 4);
-    float *bs = (float *)p;
+    char *q = (char *)p->ws;
+    float *dmu = (float *)q; q += gsd_align_up(n * 4);
+    float *ds11 = (float *)q; q += gsd_align_up(n * 4);
+    float *ds12 = (float *)q; q += gsd_align_up(n * 4);
+    float *bs = (float *)q;
     dim3 grid((W + PH_T - 1) / PH_T, (H + PH_T - 1) / PH_T, C);
     PhWin win = make_window();
-    gsd_ssim_stats_kernel<<<grid, 256, 0, st>>>(C, H, W, win, x, y, dmu, ds11, ds12, bs);
+    gsd_ssim_stats_kernel<<<grid, 256, 0, st>>>(C, H, W, win, p->x, p->y, p->affine_log_scale, p->affine_shift,
+                                                 (p->affine_log_scale || p->affine_shift) ? 3 : 0, dmu, ds11, ds12, bs);
     GSD_LAUNCH_CHECK();
-    int nb = (int)(grid.x * grid.y * grid.z);
-    gsd_ssim_finish_kernel<<<1, 256, 0, st>>>(nb, bs, 1.0f / (float)n, w_l1, w_ssim, loss_out);
+    const int per_set_c = C / p->n_sets;
+    const int blocks_per_set = (int)(grid.x * grid.y) * per_set_c;
+    gsd_ssim_finish_kernel<<<1, 256, 0, st>>>(p->n_sets, blocks_per_set, bs, 1.0f / (float)((size_t)per_set_c * H * W), p->w_l1,
+                                              p->w_ssim, p->set_weight[0], p->set_weight[1], loss_out);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
 
-// grad_x = (*gscale_ptr or 1) * gscale_mul * dloss/dx
-extern "C" int gsd_photometric_backward(int32_t C, int32_t H, int32_t W, const float *x, const float *y, float w_l1,
-                                        float w_ssim, const void *ws, const float *gscale_ptr, float gscale_mul,
-                                        float *grad_x, void *stream) {
-    if (C <= 0 || H <= 0 || W <= 0 || !x || !y || !ws || !grad_x) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
+// grad = (gscale_ptr ? *gscale_ptr : 1) * set_weight[set] * d loss_set / d rendered
+extern "C" int gsd_photometric_backward(const GsdPhotometric *p, const float *gscale_ptr, float *grad, void *stream) {
+    int rc;
+    if ((rc = ph_check(p))) return rc;
+    if (!grad) { gsd_set_error("null grad"); return GSD_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
+    const int C = p->C, H = p->H, W = p->W;
     size_t n = (size_t)C * H * W;
-    const char *p = (const char *)ws;
-    const float *dmu = (const float *)p; p += gsd_align_up(n * 4);
-    const float *ds11 = (const float *)p; p += gsd_align_up(n * 4);
-    const float *ds12 = (const float *)p;
+    const char *q = (const char *)p->ws;
+    const float *dmu = (const float *)q; q += gsd_align_up(n * 4);
+    const float *ds11 = (const float *)q; q += gsd_align_up(n * 4);
+    const float *ds12 = (const float *)q;
     dim3 grid((W + PH_T - 1) / PH_T, (H + PH_T - 1) / PH_T, C);
     PhWin win = make_window();
-    gsd_ssim_grad_kernel<<<grid, 256, 0, st>>>(C, H, W, win, x, y, dmu, ds11, ds12, gscale_ptr, gscale_mul, w_l1, w_ssim,
-                                               1.0f / (float)n, grad_x);
+    const int per_set_c = C / p->n_sets;
+    gsd_ssim_grad_kernel<<<grid, 256, 0, st>>>(C, H, W, win, p->x, p->y, p->affine_log_scale, p->affine_shift,
+                                               (p->affine_log_scale || p->affine_shift) ? 3 : 0, dmu, ds11, ds12, gscale_ptr,
+                                               p->set_weight[0], p->set_weight[1], p->w_l1, p->w_ssim,
+                                               1.0f / (float)((size_t)per_set_c * H * W), grad);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }

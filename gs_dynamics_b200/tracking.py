@@ -63,22 +63,37 @@ def params2rendervar(params):
 # ----------------------------------------------------------------------------------------------------
 # photometric loss  (fused L1 + SSIM)
 # ----------------------------------------------------------------------------------------------------
+def _ph_desc(x, y, n_sets, w_l1, w_ssim, set_weight, ws, affine=None):
+    d = _lib.GsdPhotometric()
+    d.C, d.H, d.W, d.n_sets = x.shape[0], x.shape[1], x.shape[2], n_sets
+    d.x, d.y = x.data_ptr(), y.data_ptr()
+    d.affine_log_scale = affine[0].data_ptr() if affine is not None else None
+    d.affine_shift = affine[1].data_ptr() if affine is not None else None
+    d.w_l1, d.w_ssim = float(w_l1), float(w_ssim)
+    d.set_weight[0], d.set_weight[1] = float(set_weight[0]), float(set_weight[1])
+    d.ws = ws.data_ptr()
+    return d
+
+
+def _ph_workspace(x):
+    nbytes = C.c_size_t()
+    _lib.check(_lib.lib().gsd_photometric_workspace_bytes(x.shape[0], x.shape[1], x.shape[2], C.byref(nbytes)),
+               "gsd_photometric_workspace_bytes")
+    return torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
+
+
 class _Photometric(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, w_l1, w_ssim):
         x = R._f32c(x, "x")
         y = R._f32c(y, "y")
-        if x.shape != y.shape or x.dim() != 3:
-            raise ValueError("photometric loss expects two [C,H,W] tensors")
-        Cc, H, W = x.shape
-        lib = _lib.lib()
-        nbytes = C.c_size_t()
-        _lib.check(lib.gsd_photometric_workspace_bytes(Cc, H, W, C.byref(nbytes)), "gsd_photometric_workspace_bytes")
+        if x.shape != y.shape or x.dim() != 3 or x.shape[0] > 6:
+            raise ValueError("photometric loss expects two [C<=6,H,W] tensors")
         with torch.cuda.device(x.device):
-            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
-            out = torch.empty(3, dtype=torch.float32, device=x.device)
-            _lib.check(lib.gsd_photometric_forward(Cc, H, W, x.data_ptr(), y.data_ptr(), w_l1, w_ssim, ws.data_ptr(),
-                                                   out.data_ptr(), _stream()), "gsd_photometric_forward")
+            ws = _ph_workspace(x)
+            out = torch.empty(4, dtype=torch.float32, device=x.device)
+            d = _ph_desc(x, y, 1, w_l1, w_ssim, (1.0, 1.0), ws)
+            _lib.check(_lib.lib().gsd_photometric_forward(C.byref(d), out.data_ptr(), _stream()), "gsd_photometric_forward")
         ctx.save_for_backward(x, y, ws)
         ctx.w = (w_l1, w_ssim)
         ctx.mark_non_differentiable(out)
@@ -87,13 +102,12 @@ class _Photometric(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, g_out):
         x, y, ws = ctx.saved_tensors
-        Cc, H, W = x.shape
         g_loss = g_loss.contiguous().float()
         grad = torch.empty_like(x)
         with torch.cuda.device(x.device):
-            _lib.check(_lib.lib().gsd_photometric_backward(Cc, H, W, x.data_ptr(), y.data_ptr(), ctx.w[0], ctx.w[1],
-                                                           ws.data_ptr(), g_loss.data_ptr(), 1.0, grad.data_ptr(),
-                                                           _stream()), "gsd_photometric_backward")
+            d = _ph_desc(x, y, 1, ctx.w[0], ctx.w[1], (1.0, 1.0), ws)
+            _lib.check(_lib.lib().gsd_photometric_backward(C.byref(d), g_loss.data_ptr(), grad.data_ptr(), _stream()),
+                       "gsd_photometric_backward")
         return grad, None, None, None
 
 
@@ -449,3 +463,90 @@ class TrackingStep:
             return self.losses[cam_id]
         self.optimizer.zero_grad(set_to_none=True)
         return self._iteration(self.dataset[cam_id], self.capacity.get(cam_id))
+
+
+class FusedTrackingStep(TrackingStep):
+    """Steady-state (t > 0) iteration without any PyTorch op in the loop: after the first frame only means3D and
+    unnorm_rotations have a non-zero learning rate (train_utils.py:370-373), so opacities / scales / colours are constants
+    and the whole iteration is
+
+        normalize -> rasterize (RGB+seg, one pass) -> photometric (both sets, affine colour fix fused) -> priors
+                  -> rasterize backward -> (normalize backward + gradient sum + Adam) for the two live groups
+
+    = ~24 launches of this library.  Same loss and parameter trajectory as get_loss + backward + FusedAdam.step (frozen groups
+    are skipped: their values cannot change; their unused Adam moments are not advanced).  Requires every group other than
+    means3D / unnorm_rotations to have lr == 0; use TrackingStep otherwise."""
+
+    def __init__(self, params, variables, optimizer, dataset, loss_kwargs=None, capacity_margin=1.5, use_graph=True):
+        super().__init__(params, variables, optimizer, dataset, False, loss_kwargs, capacity_margin, use_graph)
+        live = {g['name'] for g in optimizer.param_groups if g['lr'] != 0.0}
+        if not live <= {'means3D', 'unnorm_rotations'}:
+            raise ValueError("FusedTrackingStep needs lr == 0 for every group except means3D / unnorm_rotations; live: %s" % live)
+        kw = dict(weight_im=50.0, weight_seg=200.0, weight_rigid=200.0, weight_bg=200.0, weight_iso=1000.0, weight_rot=4.0)
+        kw.update({k: v for k, v in self.kw.items() if k in kw})
+        self.w = kw
+        with torch.no_grad():
+            self.opac = torch.sigmoid(params['logit_opacities']).reshape(-1).contiguous()
+            self.scales = torch.exp(params['log_scales']).contiguous()
+            self.rgb = params['rgb_colors'].detach().contiguous()
+            self.seg = params['seg_colors'].detach().contiguous()
+            self.targets = [torch.cat([d['im'], d['seg']], 0).contiguous() for d in dataset]
+            self.rot = torch.empty_like(params['unnorm_rotations'])
+        self.lr = {g['name']: float(g['lr']) for g in optimizer.param_groups}
+
+    def set_target(self, cam_id, im, seg):
+        self.targets[cam_id][:3].copy_(im, non_blocking=True)
+        self.targets[cam_id][3:].copy_(seg, non_blocking=True)
+
+    @torch.no_grad()
+    def _iteration(self, data, capacity):
+        lib = _lib.lib()
+        P, V = self.params, self.variables
+        x, uq = P['means3D'], P['unnorm_rotations']
+        G = x.shape[0]
+        cid = data['id']
+        idx = next((i for i, d_ in enumerate(self.dataset) if d_ is data), None)
+        tgt = self.targets[idx] if idx is not None else torch.cat([data['im'], data['seg']], 0).contiguous()
+        with torch.cuda.device(x.device):
+            st = _stream()
+            _lib.check(lib.gsd_track_normalize_rotations(G, uq.data_ptr(), self.rot.data_ptr(), st), "gsd_track_normalize_rotations")
+            color, radii, _, state = R.raster_forward(data['cam'], x.detach(), self.opac, self.rgb, self.scales, self.rot,
+                                                      colors1=self.seg, capacity=capacity)
+            ws = _ph_workspace(color)
+            ph = torch.empty(7, dtype=torch.float32, device=x.device)
+            d = _ph_desc(color, tgt, 2, 0.8, 0.2, (self.w['weight_im'], self.w['weight_seg']), ws,
+                         affine=(P['cam_m'][cid], P['cam_c'][cid]))
+            _lib.check(lib.gsd_photometric_forward(C.byref(d), ph.data_ptr(), st), "gsd_photometric_forward")
+            dL = torch.empty_like(color)
+            _lib.check(lib.gsd_photometric_backward(C.byref(d), None, dL.data_ptr(), st), "gsd_photometric_backward")
+            prior, parts = _TrackPriors.forward(_NullCtx(), x.detach(), self.rot, V, (self.w['weight_rigid'], self.w['weight_rot'],
+                                                self.w['weight_iso'], FLOOR_WEIGHT, self.w['weight_bg']))
+            gx_p, gq_p = _NullCtx.saved
+            g = R.raster_backward(state, dL, need_means2D=False)
+            u = _lib.GsdTrackUpdate()
+            u.G = G
+            u.beta1, u.beta2, u.eps = self.optimizer.betas[0], self.optimizer.betas[1], self.optimizer.eps
+            u.lr_means, u.lr_rot = self.lr['means3D'], self.lr['unnorm_rotations']
+            sm, sr = self.optimizer.state[x], self.optimizer.state[uq]
+            u.means3D, u.unnorm_rotations = x.data_ptr(), uq.data_ptr()
+            u.g_means_a, u.g_means_b = g['means3D'].data_ptr(), gx_p.data_ptr()
+            u.g_rot_a, u.g_rot_b = g['rotations'].data_ptr(), gq_p.data_ptr()
+            u.m_means, u.v_means = sm['exp_avg'].data_ptr(), sm['exp_avg_sq'].data_ptr()
+            u.m_rot, u.v_rot = sr['exp_avg'].data_ptr(), sr['exp_avg_sq'].data_ptr()
+            u.step_means, u.step_rot = sm['step'].data_ptr(), sr['step'].data_ptr()
+            _lib.check(lib.gsd_track_update(C.byref(u), st), "gsd_track_update")
+            self.variables = update_seen(radii, V)
+            V['prior_losses'] = parts
+            V['photometric_losses'] = ph
+        return ph[6] + prior
+
+
+class _NullCtx:
+    """Stand-in autograd context so that _TrackPriors.forward can be called directly (no graph) in the fused step."""
+    saved = None
+
+    def save_for_backward(self, *t):
+        _NullCtx.saved = t
+
+    def mark_non_differentiable(self, *t):
+        pass

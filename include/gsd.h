@@ -121,15 +121,24 @@ int gsd_raster_mark_visible(int32_t G, const float *means3D, const float *viewma
  * /root/reference/src/tracking/train_utils.py:167-246)
  * ------------------------------------------------------------------------------------------------ */
 
-/* loss = w_l1*mean|x-y| + w_ssim*(1 - mean SSIM_11x11(x,y))   (train_utils.py:185,195; external.py:101-135)
- * x, y: [C,H,W]. ws keeps three partial-derivative maps between forward and backward.
- * loss_out[3] = {loss, mean|x-y|, mean SSIM}. */
+/* loss_set = w_l1*mean|x-y| + w_ssim*(1 - mean SSIM_11x11(x,y))   (train_utils.py:185,195; external.py:101-135)
+ * x, y: [C,H,W]; channels come in sets of 3 (n_sets = 2: RGB render + seg render of one iteration in one launch, C = 6;
+ * n_sets = 1: any C <= 6). Optionally the first set is colour-corrected on the fly, x = exp(affine_log_scale[c]) * x +
+ * affine_shift[c] (the cam_m / cam_c rows of train_utils.py:182; device pointers to 3 floats, or NULL).
+ * ws keeps three partial-derivative maps between forward and backward.
+ * loss_out: per set {loss, mean|x-y|, mean SSIM}, then sum_s set_weight[s]*loss_s  (3*n_sets + 1 floats). */
+typedef struct {
+    int32_t C, H, W, n_sets;
+    const float *x, *y;
+    const float *affine_log_scale, *affine_shift;
+    float w_l1, w_ssim;
+    float set_weight[2];
+    void *ws;
+} GsdPhotometric;
 int gsd_photometric_workspace_bytes(int32_t C, int32_t H, int32_t W, size_t *bytes);
-int gsd_photometric_forward(int32_t C, int32_t H, int32_t W, const float *x, const float *y, float w_l1, float w_ssim,
-                            void *ws, float *loss_out, void *stream);
-/* grad_x = (gscale_ptr ? *gscale_ptr : 1) * gscale_mul * dloss/dx */
-int gsd_photometric_backward(int32_t C, int32_t H, int32_t W, const float *x, const float *y, float w_l1, float w_ssim,
-                             const void *ws, const float *gscale_ptr, float gscale_mul, float *grad_x, void *stream);
+int gsd_photometric_forward(const GsdPhotometric *p, float *loss_out, void *stream);
+/* grad = (gscale_ptr ? *gscale_ptr : 1) * set_weight[set] * d loss_set / d x_rendered (before the affine) */
+int gsd_photometric_backward(const GsdPhotometric *p, const float *gscale_ptr, float *grad, void *stream);
 
 /* rigid / rot / iso / floor / bg priors, forward + gradient in one call (train_utils.py:198-240).
  * The foreground set is fg_index (NULL = all G points, in order); neighbour tables index into that set.
@@ -174,6 +183,23 @@ typedef struct {
     int64_t numel[GSD_ADAM_MAX_TENSORS];
 } GsdAdam;
 int gsd_adam_step(const GsdAdam *a, void *stream);
+
+/* Steady-state (t > 0) fast path of the tracker, where only means3D and unnorm_rotations have a non-zero learning rate
+ * (train_utils.py:370-373): rotations = F.normalize(unnorm_rotations) (helpers.py:40), and the fused update
+ *   g_means = ga + gb;  g_unnorm = normalize_backward(ga_rot + gb_rot);  Adam step on both groups
+ * (the two gradient sources are the rasterizer backward and the physical priors). Step counters are device floats,
+ * read as (*step + 1) and advanced by a trailing 1-thread kernel. */
+int gsd_track_normalize_rotations(int32_t G, const float *unnorm_rotations, float *rotations, void *stream);
+typedef struct {
+    int32_t G;
+    float beta1, beta2, eps, lr_means, lr_rot;
+    float *means3D, *unnorm_rotations;
+    const float *g_means_a, *g_means_b;   /* [G,3] each; b may be NULL */
+    const float *g_rot_a, *g_rot_b;       /* [G,4] each, w.r.t. the NORMALISED rotations; b may be NULL */
+    float *m_means, *v_means, *m_rot, *v_rot;
+    float *step_means, *step_rot;
+} GsdTrackUpdate;
+int gsd_track_update(const GsdTrackUpdate *u, void *stream);
 
 /* bookkeeping of get_loss (train_utils.py:243-245): seen = radii > 0; max_2D_radius = max(radii, max_2D_radius)[seen] */
 int gsd_track_update_radii(int32_t G, const int32_t *radii, float *max_2D_radius, uint8_t *seen, void *stream);
