@@ -102,6 +102,7 @@ def build_gpu_problem(G, seed, device):
     v["in_ptr"], v["in_edge"] = TR.build_in_edges(v["neighbor_indices_i32"])
     v["fg_index"] = None
     v["bg_index"] = torch.zeros(0, dtype=torch.int32, device=device)
+    TR.pack_edge_records(v)
     opt = TR.initialize_optimizer(params, v)
     for g in opt.param_groups:  # steady state: lrs frozen after t = 0 (train_utils.py:370-373)
         if g["name"] in ("logit_opacities", "log_scales", "cam_m", "cam_c", "rgb_colors"):

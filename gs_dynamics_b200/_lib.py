@@ -47,7 +47,8 @@ class GsdTrackLosses(C.Structure):
         ("G", C.c_int32), ("Gf", C.c_int32), ("K", C.c_int32), ("Gb", C.c_int32),
         ("means3D", C.c_void_p), ("rotations", C.c_void_p), ("fg_index", C.c_void_p), ("prev_inv_rot", C.c_void_p),
         ("neighbor_indices", C.c_void_p), ("neighbor_weight", C.c_void_p), ("neighbor_dist", C.c_void_p),
-        ("prev_offset", C.c_void_p), ("in_ptr", C.c_void_p), ("in_edge", C.c_void_p), ("bg_index", C.c_void_p),
+        ("prev_offset", C.c_void_p), ("in_ptr", C.c_void_p), ("in_edge", C.c_void_p), ("edge_records", C.c_void_p),
+        ("bg_index", C.c_void_p),
         ("init_bg_pts", C.c_void_p), ("init_bg_rot", C.c_void_p),
         ("w_rigid", C.c_float), ("w_rot", C.c_float), ("w_iso", C.c_float), ("w_floor", C.c_float), ("w_bg", C.c_float),
         ("ws", C.c_void_p), ("losses", C.c_void_p), ("grad_means3D", C.c_void_p), ("grad_rotations", C.c_void_p),
@@ -59,6 +60,7 @@ class GsdPhotometric(C.Structure):
         ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("n_sets", C.c_int32),
         ("x", C.c_void_p), ("y", C.c_void_p), ("affine_log_scale", C.c_void_p), ("affine_shift", C.c_void_p),
         ("w_l1", C.c_float), ("w_ssim", C.c_float), ("set_weight", C.c_float * 2), ("ws", C.c_void_p),
+        ("y_mu", C.c_void_p), ("y_s22", C.c_void_p),
     ]
 
 
@@ -100,8 +102,8 @@ EXPORTS = [
     "gsd_raster_workspace_bytes", "gsd_raster_count_instances", "gsd_raster_forward", "gsd_raster_backward",
     "gsd_raster_mark_visible",
     "gsd_photometric_workspace_bytes", "gsd_photometric_forward", "gsd_photometric_backward",
-    "gsd_track_losses_workspace_bytes", "gsd_track_losses_fwd_bwd", "gsd_adam_step", "gsd_track_update_radii",
-    "gsd_track_normalize_rotations", "gsd_track_update",
+    "gsd_track_losses_workspace_bytes", "gsd_track_losses_fwd_bwd", "gsd_track_pack_edges", "gsd_adam_step", "gsd_track_update_radii",
+    "gsd_track_normalize_rotations", "gsd_track_update", "gsd_photometric_target_stats",
     "gsd_gnn_edges_workspace_bytes", "gsd_gnn_build_edges", "gsd_gnn_edge_inputs", "gsd_gnn_aggregate_workspace_bytes",
     "gsd_gnn_aggregate", "gsd_fps",
 ]
@@ -128,10 +130,12 @@ def lib():
     l.gsd_photometric_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
     l.gsd_photometric_forward.argtypes = [C.POINTER(GsdPhotometric), C.c_void_p, C.c_void_p]
     l.gsd_photometric_backward.argtypes = [C.POINTER(GsdPhotometric), C.c_void_p, C.c_void_p, C.c_void_p]
+    l.gsd_photometric_target_stats.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_track_normalize_rotations.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_track_update.argtypes = [C.POINTER(GsdTrackUpdate), C.c_void_p]
     l.gsd_track_losses_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
     l.gsd_track_losses_fwd_bwd.argtypes = [C.POINTER(GsdTrackLosses), C.c_void_p]
+    l.gsd_track_pack_edges.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 6
     l.gsd_adam_step.argtypes = [C.POINTER(GsdAdam), C.c_void_p]
     l.gsd_track_update_radii.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_gnn_edges_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]

@@ -154,4 +154,39 @@ __device__ __forceinline__ float gsd_power(float A, float B, float C, float dx, 
     return __fmaf_rn(-0.5f, s, -__fmul_rn(b1, dy));
 }
 __device__ __forceinline__ float gsd_gauss(float power) { return __expf(power); }
+
+// Transposed butterfly: N per-lane values are summed over the 32 lanes with ~N shuffles; afterwards the lane with
+// holder_id() == k holds the warp total of value k in v[0].
+template <int N, int BIT>
+__device__ __forceinline__ void xreduce(float *v, int lane) {
+    if constexpr (BIT >= 1) {
+        constexpr int Hh = (N + 1) / 2;
+        const bool upper = (lane & BIT) != 0;
+#pragma unroll
+        for (int k = 0; k < Hh; ++k) {
+            const float lo = v[k];
+            const float hi = (Hh + k < N) ? v[Hh + k] : 0.f;
+            const float recv = __shfl_xor_sync(0xffffffffu, upper ? lo : hi, BIT);
+            v[k] = (upper ? hi : lo) + recv;
+        }
+        xreduce<Hh, BIT / 2>(v, lane);
+    }
+}
+// Mirrors xreduce's index bookkeeping: every stage halves the (zero-padded) value range [base, base+n) for all lanes
+// alike; the lane ends up with value `base`, which is real only if it lies inside the unpadded range.
+__device__ __forceinline__ int holder_id(int N, int lane) {
+    int base = 0, n = N, end = N;
+    for (int bit = 16; bit >= 1; bit >>= 1) {
+        const int Hh = (n + 1) / 2;
+        if (lane & bit) {
+            base += Hh;
+        } else {
+            end = min(end, base + Hh);
+        }
+        n = Hh;
+    }
+    return base < end ? base : -1;
+}
+
+
 #endif

@@ -32,45 +32,58 @@ __device__ __forceinline__ void ph_affine(const float *log_scale, const float *s
     b = shift ? shift[c % 3] : 0.0f;
 }
 
-// kernel 1: per pixel SSIM partials dS/dmu1, dS/ds11, dS/ds12 + block sums of |x-y| and SSIM
-__global__ void __launch_bounds__(256)
+// kernel 1: per pixel SSIM partials dS/dmu1, dS/ds11, dS/ds12 + block sums of |x-y| and SSIM.
+// MODE 0: everything from x and y.  MODE 1: the target's window statistics (mu2 = conv(y), s22 = conv(y*y)) are read from
+// maps precomputed once per target image (they do not change during an episode frame).  MODE 2: write those maps.
+template <int MODE>
+__global__ void __launch_bounds__(256, 3)
 gsd_ssim_stats_kernel(int C, int H, int W, PhWin win, const float *__restrict__ X, const float *__restrict__ Y,
                       const float *__restrict__ log_scale, const float *__restrict__ shift, int affine_channels,
+                      float *__restrict__ y_mu, float *__restrict__ y_s22,
                       float *__restrict__ dmu, float *__restrict__ ds11, float *__restrict__ ds12,
                       float *__restrict__ block_sums /* [nblocks][2] */) {
+    constexpr int NQ = (MODE == 0) ? 5 : (MODE == 1 ? 3 : 2); // x, xx, xy (, y, yy)   |   MODE 2: y, yy
     __shared__ float sx[PH_E][PH_E + 1], sy[PH_E][PH_E + 1];
-    __shared__ float h[5][PH_E][PH_T + 1]; // horizontally filtered x, y, xx, yy, xy
+    __shared__ float h[NQ][PH_E][PH_T + 1];
     __shared__ float red[2][8];
     const int c = blockIdx.z;
     const int x0 = blockIdx.x * PH_T, y0 = blockIdx.y * PH_T;
     const float *Xc = X + (size_t)c * H * W, *Yc = Y + (size_t)c * H * W;
     const int t = threadIdx.x;
     float as = 1.f, ab = 0.f;
-    if (c < affine_channels) ph_affine(log_scale, shift, c, as, ab);
+    if (MODE != 2 && c < affine_channels) ph_affine(log_scale, shift, c, as, ab);
     for (int i = t; i < PH_E * PH_E; i += 256) {
         int ly = i / PH_E, lx = i % PH_E;
         const int gx = x0 + lx - PH_R, gy = y0 + ly - PH_R;
         const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
-        sx[ly][lx] = in ? as * Xc[(size_t)gy * W + gx] + ab : 0.f;
+        if (MODE != 2) sx[ly][lx] = in ? as * Xc[(size_t)gy * W + gx] + ab : 0.f;
         sy[ly][lx] = in ? Yc[(size_t)gy * W + gx] : 0.f;
     }
     __syncthreads();
     // horizontal pass: unit = (row, segment of 4 outputs); consecutive lanes take consecutive rows (pitch 43: no conflicts)
     for (int u = t; u < PH_E * (PH_T / 4); u += 256) {
         const int ly = u % PH_E, seg = u / PH_E;
-        float xv[14], yv[14];
+        float q[NQ][14];
 #pragma unroll
-        for (int k = 0; k < 14; ++k) { xv[k] = sx[ly][seg * 4 + k]; yv[k] = sy[ly][seg * 4 + k]; }
+        for (int k = 0; k < 14; ++k) {
+            const float yy = sy[ly][seg * 4 + k];
+            if (MODE == 2) {
+                q[0][k] = yy; q[1][k] = yy * yy;
+            } else {
+                const float xx = sx[ly][seg * 4 + k];
+                q[0][k] = xx; q[1][k] = xx * xx; q[2][k] = xx * yy;
+                if (MODE == 0) { q[3 % NQ][k] = yy; q[4 % NQ][k] = yy * yy; }
+            }
+        }
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
-            float a = 0.f, b = 0.f, aa = 0.f, bb = 0.f, ab2 = 0.f;
 #pragma unroll
-            for (int k = 0; k < 11; ++k) {
-                const float w = win.g[k], xx = xv[o + k], yy = yv[o + k];
-                a += w * xx; b += w * yy; aa += w * xx * xx; bb += w * yy * yy; ab2 += w * xx * yy;
+            for (int n = 0; n < NQ; ++n) {
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 11; ++k) a += win.g[k] * q[n][o + k];
+                h[n][ly][seg * 4 + o] = a;
             }
-            const int lx = seg * 4 + o;
-            h[0][ly][lx] = a; h[1][ly][lx] = b; h[2][ly][lx] = aa; h[3][ly][lx] = bb; h[4][ly][lx] = ab2;
         }
     }
     __syncthreads();
@@ -78,40 +91,50 @@ gsd_ssim_stats_kernel(int C, int H, int W, PhWin win, const float *__restrict__ 
     float l1 = 0.f, ss = 0.f;
     {
         const int lx = t % PH_T, seg = t / PH_T; // 32 columns x 8 segments
-        float v[5][14];
+        float v[NQ][14];
 #pragma unroll
-        for (int q = 0; q < 5; ++q)
+        for (int n = 0; n < NQ; ++n)
 #pragma unroll
-            for (int k = 0; k < 14; ++k) v[q][k] = h[q][seg * 4 + k][lx];
+            for (int k = 0; k < 14; ++k) v[n][k] = h[n][seg * 4 + k][lx];
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
             const int ly = seg * 4 + o;
             const int gx = x0 + lx, gy = y0 + ly;
-            float mu1 = 0.f, mu2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+            float r[NQ];
 #pragma unroll
-            for (int k = 0; k < 11; ++k) {
-                const float w = win.g[k];
-                mu1 += w * v[0][o + k]; mu2 += w * v[1][o + k]; s11 += w * v[2][o + k]; s22 += w * v[3][o + k]; s12 += w * v[4][o + k];
+            for (int n = 0; n < NQ; ++n) {
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 11; ++k) a += win.g[k] * v[n][o + k];
+                r[n] = a;
             }
             if (gx < W && gy < H) {
-                const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-                const float mu1sq = mu1 * mu1, mu2sq = mu2 * mu2, mu12 = mu1 * mu2;
-                const float sig1 = s11 - mu1sq, sig2 = s22 - mu2sq, sig12 = s12 - mu12;
-                const float A1 = 2.f * mu12 + C1, A2 = 2.f * sig12 + C2;
-                const float B1 = mu1sq + mu2sq + C1, B2 = sig1 + sig2 + C2;
-                const float inv = 1.f / (B1 * B2);
-                const float S = A1 * A2 * inv;
-                const float dS_dA1 = A2 * inv, dS_dA2 = A1 * inv, dS_dB1 = -S / B1, dS_dB2 = -S / B2;
-                const float d_mu1 = dS_dA1 * 2.f * mu2 + dS_dA2 * (-2.f * mu2) + dS_dB1 * 2.f * mu1 + dS_dB2 * (-2.f * mu1);
                 const size_t pid = (size_t)c * H * W + (size_t)gy * W + gx;
-                dmu[pid] = d_mu1;
-                ds11[pid] = dS_dB2;
-                ds12[pid] = 2.f * dS_dA2;
-                ss += S;
-                l1 += fabsf(sx[ly + PH_R][lx + PH_R] - sy[ly + PH_R][lx + PH_R]);
+                if (MODE == 2) {
+                    y_mu[pid] = r[0];
+                    y_s22[pid] = r[1];
+                } else {
+                    const float mu1 = r[0], s11 = r[1], s12 = r[2];
+                    const float mu2 = (MODE == 0) ? r[3 % NQ] : y_mu[pid];
+                    const float s22 = (MODE == 0) ? r[4 % NQ] : y_s22[pid];
+                    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+                    const float mu1sq = mu1 * mu1, mu2sq = mu2 * mu2, mu12 = mu1 * mu2;
+                    const float sig1 = s11 - mu1sq, sig2 = s22 - mu2sq, sig12 = s12 - mu12;
+                    const float A1 = 2.f * mu12 + C1, A2 = 2.f * sig12 + C2;
+                    const float B1 = mu1sq + mu2sq + C1, B2 = sig1 + sig2 + C2;
+                    const float inv = 1.f / (B1 * B2);
+                    const float S = A1 * A2 * inv;
+                    const float dS_dA1 = A2 * inv, dS_dA2 = A1 * inv, dS_dB1 = -S / B1, dS_dB2 = -S / B2;
+                    dmu[pid] = dS_dA1 * 2.f * mu2 + dS_dA2 * (-2.f * mu2) + dS_dB1 * 2.f * mu1 + dS_dB2 * (-2.f * mu1);
+                    ds11[pid] = dS_dB2;
+                    ds12[pid] = 2.f * dS_dA2;
+                    ss += S;
+                    l1 += fabsf(sx[ly + PH_R][lx + PH_R] - sy[ly + PH_R][lx + PH_R]);
+                }
             }
         }
     }
+    if (MODE == 2) return;
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
         l1 += __shfl_xor_sync(0xffffffffu, l1, o);
@@ -158,7 +181,7 @@ __global__ void gsd_ssim_finish_kernel(int n_sets, int blocks_per_set, const flo
 }
 
 // kernel 2: d loss / d rendered = gscale * set_weight * scale_c * ( w_l1*sign(x-y)/N - w_ssim/N * (conv(dmu) + 2x*conv(ds11) + y*conv(ds12)) )
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gsd_ssim_grad_kernel(int C, int H, int W, PhWin win, const float *__restrict__ X, const float *__restrict__ Y,
                      const float *__restrict__ log_scale, const float *__restrict__ shift, int affine_channels,
                      const float *__restrict__ dmu, const float *__restrict__ ds11, const float *__restrict__ ds12,
@@ -268,13 +291,29 @@ extern "C" int gsd_photometric_forward(const GsdPhotometric *p, float *loss_out,
     float *bs = (float *)q;
     dim3 grid((W + PH_T - 1) / PH_T, (H + PH_T - 1) / PH_T, C);
     PhWin win = make_window();
-    gsd_ssim_stats_kernel<<<grid, 256, 0, st>>>(C, H, W, win, p->x, p->y, p->affine_log_scale, p->affine_shift,
-                                                 (p->affine_log_scale || p->affine_shift) ? 3 : 0, dmu, ds11, ds12, bs);
+    const int aff = (p->affine_log_scale || p->affine_shift) ? 3 : 0;
+    if (p->y_mu && p->y_s22)
+        gsd_ssim_stats_kernel<1><<<grid, 256, 0, st>>>(C, H, W, win, p->x, p->y, p->affine_log_scale, p->affine_shift, aff,
+                                                        (float *)p->y_mu, (float *)p->y_s22, dmu, ds11, ds12, bs);
+    else
+        gsd_ssim_stats_kernel<0><<<grid, 256, 0, st>>>(C, H, W, win, p->x, p->y, p->affine_log_scale, p->affine_shift, aff,
+                                                        nullptr, nullptr, dmu, ds11, ds12, bs);
     GSD_LAUNCH_CHECK();
     const int per_set_c = C / p->n_sets;
     const int blocks_per_set = (int)(grid.x * grid.y) * per_set_c;
     gsd_ssim_finish_kernel<<<1, 256, 0, st>>>(p->n_sets, blocks_per_set, bs, 1.0f / (float)((size_t)per_set_c * H * W), p->w_l1,
                                               p->w_ssim, p->set_weight[0], p->set_weight[1], loss_out);
+    GSD_LAUNCH_CHECK();
+    return GSD_OK;
+}
+
+// window statistics of a target image, computed once and passed as GsdPhotometric.y_mu / y_s22 on later calls
+extern "C" int gsd_photometric_target_stats(int32_t C, int32_t H, int32_t W, const float *y, float *y_mu, float *y_s22, void *stream) {
+    if (C <= 0 || H <= 0 || W <= 0 || !y || !y_mu || !y_s22) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
+    dim3 grid((W + PH_T - 1) / PH_T, (H + PH_T - 1) / PH_T, C);
+    PhWin win = make_window();
+    gsd_ssim_stats_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(C, H, W, win, y, y, nullptr, nullptr, 0, y_mu, y_s22, nullptr,
+                                                                     nullptr, nullptr, nullptr);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }

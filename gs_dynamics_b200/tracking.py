@@ -63,7 +63,7 @@ def params2rendervar(params):
 # ----------------------------------------------------------------------------------------------------
 # photometric loss  (fused L1 + SSIM)
 # ----------------------------------------------------------------------------------------------------
-def _ph_desc(x, y, n_sets, w_l1, w_ssim, set_weight, ws, affine=None):
+def _ph_desc(x, y, n_sets, w_l1, w_ssim, set_weight, ws, affine=None, y_stats=None):
     d = _lib.GsdPhotometric()
     d.C, d.H, d.W, d.n_sets = x.shape[0], x.shape[1], x.shape[2], n_sets
     d.x, d.y = x.data_ptr(), y.data_ptr()
@@ -72,7 +72,19 @@ def _ph_desc(x, y, n_sets, w_l1, w_ssim, set_weight, ws, affine=None):
     d.w_l1, d.w_ssim = float(w_l1), float(w_ssim)
     d.set_weight[0], d.set_weight[1] = float(set_weight[0]), float(set_weight[1])
     d.ws = ws.data_ptr()
+    d.y_mu = y_stats[0].data_ptr() if y_stats is not None else None
+    d.y_s22 = y_stats[1].data_ptr() if y_stats is not None else None
     return d
+
+
+def target_stats(y):
+    """Window statistics (conv(y), conv(y*y)) of a target image: constant while the target does not change."""
+    y = R._f32c(y, "y")
+    mu, s22 = torch.empty_like(y), torch.empty_like(y)
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.lib().gsd_photometric_target_stats(y.shape[0], y.shape[1], y.shape[2], y.data_ptr(), mu.data_ptr(),
+                                                           s22.data_ptr(), _stream()), "gsd_photometric_target_stats")
+    return mu, s22
 
 
 def _ph_workspace(x):
@@ -154,6 +166,9 @@ class _TrackPriors(torch.autograd.Function):
         t.neighbor_indices, t.neighbor_weight = ptr(v["neighbor_indices_i32"]), ptr(v["neighbor_weight"])
         t.neighbor_dist, t.prev_offset = ptr(v["neighbor_dist"]), ptr(v["prev_offset"])
         t.in_ptr, t.in_edge = ptr(v["in_ptr"]), ptr(v["in_edge"])
+        er = v.get("edge_records")
+        if er is not None and er.get("src") is v["prev_offset"] and er.get("ver") == v["prev_offset"]._version:
+            t.edge_records = er["data"].data_ptr()
         t.bg_index, t.init_bg_pts, t.init_bg_rot = ptr(bg), ptr(v.get("init_bg_pts")), ptr(v.get("init_bg_rot"))
         t.w_rigid, t.w_rot, t.w_iso, t.w_floor, t.w_bg = [float(w) for w in weights]
         nbytes = C.c_size_t()
@@ -173,6 +188,20 @@ class _TrackPriors(torch.autograd.Function):
     def backward(ctx, g_total, g_losses):
         gx, gq = ctx.saved_tensors
         return gx * g_total, gq * g_total, None, None
+
+
+def pack_edge_records(variables):
+    """Packs the per-edge tables into 32-byte records for the priors kernel. Call after prev_offset changed (once per
+    timestep); a stale pack is detected (tensor identity + version) and ignored."""
+    v = variables
+    Gf, K = v["neighbor_indices_i32"].shape
+    out = torch.empty((Gf * K, 8), dtype=torch.float32, device=v["prev_offset"].device)
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().gsd_track_pack_edges(Gf, K, v["neighbor_indices_i32"].data_ptr(), v["neighbor_weight"].data_ptr(),
+                                                   v["neighbor_dist"].data_ptr(), v["prev_offset"].data_ptr(), out.data_ptr(),
+                                                   _stream()), "gsd_track_pack_edges")
+    v["edge_records"] = dict(data=out, src=v["prev_offset"], ver=v["prev_offset"]._version)
+    return v
 
 
 def track_prior_losses(means3D, rotations, variables, weight_rigid, weight_rot, weight_iso, weight_bg,
@@ -398,6 +427,7 @@ def initialize_per_timestep(params, variables, optimizer):
     assign('prev_col', params['rgb_colors'])
     assign('prev_pts', pts)
     assign('prev_rot', rot)
+    pack_edge_records(variables)
     for k, v in (('means3D', new_pts), ('unnorm_rotations', new_rot)):
         p = params[k]
         p.data.copy_(v)
@@ -492,11 +522,19 @@ class FusedTrackingStep(TrackingStep):
             self.seg = params['seg_colors'].detach().contiguous()
             self.targets = [torch.cat([d['im'], d['seg']], 0).contiguous() for d in dataset]
             self.rot = torch.empty_like(params['unnorm_rotations'])
+            self.tstats = [target_stats(tg) for tg in self.targets]
         self.lr = {g['name']: float(g['lr']) for g in optimizer.param_groups}
 
     def set_target(self, cam_id, im, seg):
-        self.targets[cam_id][:3].copy_(im, non_blocking=True)
-        self.targets[cam_id][3:].copy_(seg, non_blocking=True)
+        """New target images for a camera (e.g. the next frame's, from pinned host memory): copies them into the static
+        buffers the captured graph reads and refreshes their window statistics."""
+        tg = self.targets[cam_id]
+        tg[:3].copy_(im, non_blocking=True)
+        tg[3:].copy_(seg, non_blocking=True)
+        mu, s22 = self.tstats[cam_id]
+        with torch.cuda.device(tg.device):
+            _lib.check(_lib.lib().gsd_photometric_target_stats(6, tg.shape[1], tg.shape[2], tg.data_ptr(), mu.data_ptr(),
+                                                               s22.data_ptr(), _stream()), "gsd_photometric_target_stats")
 
     @torch.no_grad()
     def _iteration(self, data, capacity):
@@ -507,6 +545,7 @@ class FusedTrackingStep(TrackingStep):
         cid = data['id']
         idx = next((i for i, d_ in enumerate(self.dataset) if d_ is data), None)
         tgt = self.targets[idx] if idx is not None else torch.cat([data['im'], data['seg']], 0).contiguous()
+        tst = self.tstats[idx] if idx is not None else None
         with torch.cuda.device(x.device):
             st = _stream()
             _lib.check(lib.gsd_track_normalize_rotations(G, uq.data_ptr(), self.rot.data_ptr(), st), "gsd_track_normalize_rotations")
@@ -515,7 +554,7 @@ class FusedTrackingStep(TrackingStep):
             ws = _ph_workspace(color)
             ph = torch.empty(7, dtype=torch.float32, device=x.device)
             d = _ph_desc(color, tgt, 2, 0.8, 0.2, (self.w['weight_im'], self.w['weight_seg']), ws,
-                         affine=(P['cam_m'][cid], P['cam_c'][cid]))
+                         affine=(P['cam_m'][cid], P['cam_c'][cid]), y_stats=tst)
             _lib.check(lib.gsd_photometric_forward(C.byref(d), ph.data_ptr(), st), "gsd_photometric_forward")
             dL = torch.empty_like(color)
             _lib.check(lib.gsd_photometric_backward(C.byref(d), None, dL.data_ptr(), st), "gsd_photometric_backward")

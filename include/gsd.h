@@ -134,9 +134,12 @@ typedef struct {
     float w_l1, w_ssim;
     float set_weight[2];
     void *ws;
+    const float *y_mu, *y_s22; /* optional [C,H,W] window statistics of y from gsd_photometric_target_stats (or NULL) */
 } GsdPhotometric;
 int gsd_photometric_workspace_bytes(int32_t C, int32_t H, int32_t W, size_t *bytes);
 int gsd_photometric_forward(const GsdPhotometric *p, float *loss_out, void *stream);
+/* conv(y), conv(y*y) with the SSIM window: constant per target image, computed once per camera and frame */
+int gsd_photometric_target_stats(int32_t C, int32_t H, int32_t W, const float *y, float *y_mu, float *y_s22, void *stream);
 /* grad = (gscale_ptr ? *gscale_ptr : 1) * set_weight[set] * d loss_set / d x_rendered (before the affine) */
 int gsd_photometric_backward(const GsdPhotometric *p, const float *gscale_ptr, float *grad, void *stream);
 
@@ -155,6 +158,7 @@ typedef struct {
     const float *prev_offset;       /* [Gf,K,3] */
     const int32_t *in_ptr;          /* [Gf+1] */
     const int32_t *in_edge;         /* [Gf*K] */
+    const float *edge_records;      /* optional [Gf*K,8] from gsd_track_pack_edges (32-byte records: 4x fewer L1 sectors) */
     const int32_t *bg_index;        /* [Gb] */
     const float *init_bg_pts;       /* [Gb,3] */
     const float *init_bg_rot;       /* [Gb,4] */
@@ -165,6 +169,10 @@ typedef struct {
     float *grad_rotations;          /* [G,4] d(weighted total)/d rotations, fully overwritten */
 } GsdTrackLosses;
 int gsd_track_losses_workspace_bytes(int32_t Gf, int32_t Gb, size_t *bytes);
+/* packs (neighbour id, weight, rest distance, previous offset) of every edge into one 32-byte record; call once per
+ * timestep (initialize_per_timestep changes prev_offset, train_utils.py:331-351) */
+int gsd_track_pack_edges(int32_t Gf, int32_t K, const int32_t *neighbor_indices, const float *neighbor_weight,
+                         const float *neighbor_dist, const float *prev_offset, float *edge_records, void *stream);
 int gsd_track_losses_fwd_bwd(const GsdTrackLosses *t, void *stream);
 
 /* Multi-tensor Adam, one launch for every parameter group (torch.optim.Adam semantics, no weight decay /

@@ -101,6 +101,26 @@ def test_priors_vs_float64_oracle(G, K, fb):
     assert rel_err(q.grad.cpu(), 0.5 * q64.grad) < 2e-3
 
 
+def test_priors_packed_edge_records_match_unpacked_tables():
+    from gs_dynamics_b200 import tracking as TR
+    c = T.make_prior_case(4000, 20, 11, 0.2)
+    v = _variables_from_case(c)
+    x = c["means3D"].cuda().requires_grad_(True)
+    q = c["rotations"].cuda().requires_grad_(True)
+    t0, p0 = TR.track_prior_losses(x, q, v, 200.0, 4.0, 1000.0, 200.0)
+    t0.backward()
+    gx0, gq0 = x.grad.clone(), q.grad.clone()
+    x.grad = None; q.grad = None
+    TR.pack_edge_records(v)
+    t1, p1 = TR.track_prior_losses(x, q, v, 200.0, 4.0, 1000.0, 200.0)
+    t1.backward()
+    assert float((p1 - p0).abs().max()) <= 1e-6 * float(p0.abs().max())
+    assert rel_err(x.grad.cpu(), gx0.cpu()) < 1e-5 and rel_err(q.grad.cpu(), gq0.cpu()) < 1e-5
+    # a stale pack (prev_offset modified afterwards) must not be used
+    v["prev_offset"].mul_(1.0)
+    assert v["edge_records"]["ver"] != v["prev_offset"]._version
+
+
 def test_fused_adam_matches_torch_adam():
     from gs_dynamics_b200 import tracking as TR
     g = torch.Generator().manual_seed(0)
