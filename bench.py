@@ -154,12 +154,11 @@ def time_blend_backward(params, dataset, capacity, flush, iters=10):
 
 def run_ours(args):
     import torch.distributed as dist
-    from gs_dynamics_b200 import tracking as TR, _lib
+    from gs_dynamics_b200 import tracking as TR, _lib, dist as gdist
     rank, local_rank, world = env_rank()
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+    gdist.init(backend="nccl", device=device)  # NCCL: barrier + max-over-ranks timing only; episodes share nothing
     G = args.gaussians
     params, variables, opt, dataset, host = build_gpu_problem(G, seed=rank, device=device)
     n_cams = len(dataset)

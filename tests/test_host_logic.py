@@ -1,0 +1,59 @@
+"""CPU: host-side logic of the product (no kernels): workloads, camera conventions, graph bookkeeping, sharding."""
+import numpy as np
+import torch
+
+from gs_dynamics_b200 import dist as gdist
+from gs_dynamics_b200 import gnn, scenes, workloads
+
+
+def test_camera_matrices_follow_reference_conventions():
+    w, h, cams = scenes.demo_cameras()
+    assert (w, h) == (640, 480) and len(cams) == 4
+    k, w2c = cams[0]
+    m = scenes.camera_matrices(w, h, k, w2c, near=1.0, far=100.0)
+    assert m["viewmatrix"].shape == (1, 4, 4) and m["projmatrix"].shape == (1, 4, 4)
+    np.testing.assert_allclose(m["viewmatrix"][0].numpy(), np.asarray(w2c, np.float32).T, atol=1e-6)   # viewmatrix = w2c^T
+    assert abs(m["tanfovx"] - w / (2 * k[0][0])) < 1e-9
+    # campos = camera centre in world coordinates
+    np.testing.assert_allclose(m["campos"].numpy(), np.linalg.inv(w2c)[:3, 3], atol=1e-5)
+    # a world point in front of the camera projects inside NDC [-1, 1]
+    p = np.linalg.inv(w2c) @ np.array([0, 0, 0.7, 1.0])
+    hom = torch.tensor(p, dtype=torch.float32) @ m["projmatrix"][0]
+    assert abs(hom[0] / hom[3]) < 1 and abs(hom[1] / hom[3]) < 1
+
+
+def test_tracking_workload_is_seeded_and_consistent():
+    a = workloads.tracking_problem(500, seed=3, num_knn=5)
+    b = workloads.tracking_problem(500, seed=3, num_knn=5)
+    assert torch.equal(a["params"]["means3D"], b["params"]["means3D"])
+    v = a["variables"]
+    assert v["neighbor_indices"].shape == (500, 5) and v["prev_offset"].shape == (500, 5, 3)
+    assert int((v["neighbor_indices"] == torch.arange(500)[:, None]).sum()) == 0   # self excluded (o3d_knn drops index 0)
+    np.testing.assert_allclose(v["neighbor_weight"].numpy(), np.exp(-2000 * v["neighbor_dist"].numpy() ** 2), rtol=1e-4)
+    m = torch.rand(4, 6)
+    s = workloads.seg_target_from_mask(m)
+    assert s.shape == (3, 4, 6) and torch.equal(s[2], 1 - m) and float(s[1].abs().max()) == 0
+
+
+def test_edge_index_from_dense_handles_padding_and_order():
+    N = 6
+    recv = torch.tensor([0, 0, 2, 5, 5, 5])
+    send = torch.tensor([1, 2, 0, 0, 1, 3])
+    Rr = torch.zeros(1, 9, N); Rs = torch.zeros(1, 9, N)
+    perm = torch.tensor([3, 0, 5, 1, 4, 2])                 # unsorted input rows + 3 zero padding rows
+    for slot, e in enumerate(perm):
+        Rr[0, slot, recv[e]] = 1; Rs[0, slot, send[e]] = 1
+    e = gnn.edge_index_from_dense(Rr, Rs)
+    assert e.capacity == 9 and int(e.n_edges[0]) == 6
+    assert e.row_ptr[0].tolist() == [0, 2, 2, 3, 3, 3, 6]
+    got = sorted(zip(e.receivers[0, :6].tolist(), e.senders[0, :6].tolist()))
+    assert got == sorted(zip(recv.tolist(), send.tolist()))
+    assert e.receivers[0, 6:].tolist() == [-1, -1, -1]
+    assert gnn.edge_capacity(2001, 1, 8) == 2000 * 8 + 2 * 2000
+
+
+def test_shard_partitions_units_evenly():
+    for n, w in ((8, 8), (8, 3), (5, 2), (3, 4)):
+        parts = [gdist.shard(n, r, w) for r in range(w)]
+        assert sorted(sum(parts, [])) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
