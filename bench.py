@@ -204,31 +204,55 @@ def run_ours(args):
     dev_s = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end to end through the public API with host buffers: the step's camera image + seg come from pinned host memory
-    # into the step's target buffers, the loss is read back and consumed on the host, every step
+    # ---- end to end through the public API with host buffers: every step its camera image + seg are copied from pinned host
+    # memory into the step's target buffers (plus their SSIM window statistics), and the loss is read back and consumed on the
+    # host.  The copy for step i+1 is issued on a side stream while step i computes (double buffering per camera; when the next
+    # step uses the same camera the copy waits for the running step).  All of it is inside the timed region.
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4
+    copy_stream = torch.cuda.Stream(device=device)
+    main = torch.cuda.current_stream()
 
-    def e2e_step(c):
-        step_obj.set_target(c, host[c][0], host[c][1])
-        l = step_obj.step(c)
-        loss_host.copy_(l, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller consumes the loss every step
-        return float(loss_host)
+    def prefetch(c, after=None):
+        with torch.cuda.stream(copy_stream):
+            if after is not None:
+                copy_stream.wait_event(after)
+            step_obj.set_target(c, host[c][0], host[c][1])
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
 
-    for _ in range(max(3, args.warmup // 4)):
-        e2e_step(rng.randrange(n_cams))
+    def run_e2e(n_steps, timed):
+        seq = [rng.randrange(n_cams) for _ in range(n_steps + 1)]
+        total = 0.0
+        last = None
+        copy_ev = prefetch(seq[0])
+        torch.cuda.synchronize()
+        for i in range(n_steps):
+            if timed:
+                flush.zero_()
+                torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            l = step_obj.step(seq[i])                      # inputs of this step landed inside the previous timed region
+            done = torch.cuda.Event()
+            done.record(main)
+            # next step's inputs: overlap with this step unless it reads the same camera buffers; the timed region of this
+            # step ends only when that copy has landed too, so every H2D byte is paid for inside a timed region
+            copy_ev = prefetch(seq[i + 1], after=done if seq[i + 1] == seq[i] else None)
+            main.wait_event(copy_ev)
+            loss_host.copy_(l, non_blocking=True)
+            e1.record()
+            main.synchronize()                             # the caller consumes the loss every step
+            last = float(loss_host)
+            if timed:
+                total += e0.elapsed_time(e1) * 1e-3
+        torch.cuda.synchronize()
+        return total, last
+
+    run_e2e(max(3, args.warmup // 4), False)
     barrier()
-    e2e_s = 0.0
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        last_loss = e2e_step(rng.randrange(n_cams))
-        e1.record()
-        torch.cuda.synchronize()
-        e2e_s += e0.elapsed_time(e1) * 1e-3
+    e2e_s, last_loss = run_e2e(args.steps, True)
     barrier()
 
     # ---- roofline of the dominant kernel
