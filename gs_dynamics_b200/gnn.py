@@ -360,6 +360,16 @@ class DynamicsPredictor(nn.Module):
         return pred_pos, pred_motion
 
 
+def downsample_vertices(xyz, max_nobj, fps_radius, start_idx=None):
+    """DynamicsModule.downsample_vertices (/root/reference/src/render/dynamics_module.py:44-51): FPS to max_nobj points
+    (start index 0), then radius-terminated FPS. Returns (points, indices into xyz)."""
+    idx1 = farthest_point_sampler(xyz[None], min(max_nobj, xyz.shape[0]), start_idx=0)[0]
+    sub = xyz[idx1]
+    _, idx2 = fps_rad_idx_torch(sub, fps_radius, start_idx=start_idx)
+    idx = idx1[idx2]
+    return xyz[idx], idx
+
+
 # ----------------------------------------------------------------------------------------------------
 # rollout step (the loop body of DynamicsModule.rollout, /root/reference/src/render/dynamics_module.py:85-170,
 # without the Gaussian skinning which is a "next" row): edges -> model -> history shift

@@ -589,3 +589,172 @@ class _NullCtx:
 
     def mark_non_differentiable(self, *t):
         pass
+
+
+# ----------------------------------------------------------------------------------------------------
+# t = 0 path: densification statistics and parameter/optimizer surgery (A9, A12: /root/reference/src/tracking/external.py:138-299).
+# Host-side PyTorch logic on top of FusedAdam's state; the kernels above do the per-iteration work.  Variable G is
+# incompatible with CUDA-graph capture, so t = 0 runs eagerly through get_loss(..., fused=False).
+# ----------------------------------------------------------------------------------------------------
+PER_POINT_KEYS = ('means3D', 'rgb_colors', 'seg_colors', 'unnorm_rotations', 'logit_opacities', 'log_scales')
+
+
+def _group(optimizer, name):
+    for g in optimizer.param_groups:
+        if g['name'] == name:
+            return g
+    raise KeyError(name)
+
+
+def _replace_param(optimizer, params, name, value, exp_avg=None, exp_avg_sq=None, keep_step=True):
+    """Swap the tensor of a parameter group for `value`, carrying over / installing its Adam moments."""
+    g = _group(optimizer, name)
+    old = g['params'][0]
+    st = optimizer.state.pop(old, None)
+    new = torch.nn.Parameter(value.detach().clone().contiguous(), requires_grad=old.requires_grad)
+    g['params'][0] = new
+    params[name] = new
+    step = st['step'] if (st is not None and keep_step) else torch.zeros((), dtype=torch.float32, device=new.device)
+    optimizer.state[new] = dict(step=step,
+                                exp_avg=torch.zeros_like(new) if exp_avg is None else exp_avg.contiguous(),
+                                exp_avg_sq=torch.zeros_like(new) if exp_avg_sq is None else exp_avg_sq.contiguous())
+    return new
+
+
+def update_params_and_optimizer(new_params, params, optimizer):
+    """external.py:145-157: new values, Adam moments reset to zero (step counter kept)."""
+    for k, v in new_params.items():
+        _replace_param(optimizer, params, k, v)
+    return params
+
+
+def cat_params_to_optimizer(new_params, params, optimizer):
+    """external.py:160-174: append rows; the appended rows start with zero Adam moments."""
+    for k, v in new_params.items():
+        st = optimizer.state[_group(optimizer, k)['params'][0]]
+        _replace_param(optimizer, params, k, torch.cat((params[k].detach(), v), 0),
+                       torch.cat((st['exp_avg'], torch.zeros_like(v)), 0), torch.cat((st['exp_avg_sq'], torch.zeros_like(v)), 0))
+    return params
+
+
+def remove_points(to_remove, params, variables, optimizer):
+    """external.py:177-222: drop rows (parameters, Adam moments and the densification statistics)."""
+    keep = ~to_remove
+    for k in [k for k in params.keys() if k not in ('cam_m', 'cam_c')]:
+        st = optimizer.state[_group(optimizer, k)['params'][0]]
+        _replace_param(optimizer, params, k, params[k].detach()[keep], st['exp_avg'][keep], st['exp_avg_sq'][keep])
+    for k in ('means2D_gradient_accum', 'denom', 'max_2D_radius'):
+        variables[k] = variables[k][keep]
+    return params, variables
+
+
+def accumulate_mean2d_gradient(variables):
+    """external.py:138-142 without boolean-mask indexing (no host sync)."""
+    seen = variables['seen']
+    gnorm = torch.norm(variables['means2D'].grad[:, :2], dim=-1)
+    variables['means2D_gradient_accum'] += torch.where(seen, gnorm, torch.zeros_like(gnorm))
+    variables['denom'] += seen.to(variables['denom'].dtype)
+    return variables
+
+
+def _rotation_matrices(q):
+    q = torch.nn.functional.normalize(q)
+    r, x, y, z = q.unbind(-1)
+    return torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                        2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                        2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], -1).reshape(-1, 3, 3)
+
+
+@torch.no_grad()
+def densify(params, variables, optimizer, i, remove_thresh, remove_thresh_5k, scale_scene_radius, grad_thresh=0.0002):
+    """Clone / split / prune schedule of external.py:229-299 (t = 0 only): every 100 iterations for 500 <= i <= 5000 points
+    with a large screen-space gradient are cloned (small) or split in two (large, sampled from the Gaussian, scale / 1.6);
+    transparent (and, after 3000, oversized) points are pruned; opacities are reset to 0.01 every 3000 iterations."""
+    if i <= 5000:
+        variables = accumulate_mean2d_gradient(variables)
+        if i >= 500 and i % 100 == 0:
+            grads = variables['means2D_gradient_accum'] / variables['denom']
+            grads[grads.isnan()] = 0.0
+            limit = scale_scene_radius * variables['scene_radius']
+            big = torch.exp(params['log_scales']).max(dim=1).values > limit
+            hot = grads >= grad_thresh
+            # clone the small hot points
+            to_clone = hot & ~big
+            params = cat_params_to_optimizer({k: params[k].detach()[to_clone] for k in PER_POINT_KEYS}, params, optimizer)
+            n_now = params['means3D'].shape[0]
+            hot_pad = torch.zeros(n_now, dtype=torch.bool, device=hot.device)
+            hot_pad[:hot.shape[0]] = hot
+            to_split = hot_pad & (torch.exp(params['log_scales']).max(dim=1).values > limit)
+            n = 2
+            new = {k: params[k].detach()[to_split].repeat(n, 1) for k in PER_POINT_KEYS}
+            stds = torch.exp(params['log_scales'].detach())[to_split].repeat(n, 1)
+            samples = torch.normal(mean=torch.zeros_like(stds), std=stds)
+            rots = _rotation_matrices(params['unnorm_rotations'].detach()[to_split]).repeat(n, 1, 1)
+            new['means3D'] = new['means3D'] + torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1)
+            new['log_scales'] = torch.log(torch.exp(new['log_scales']) / (0.8 * n))
+            params = cat_params_to_optimizer(new, params, optimizer)
+            n_now = params['means3D'].shape[0]
+            for k in ('means2D_gradient_accum', 'denom', 'max_2D_radius'):
+                variables[k] = torch.zeros(n_now, device=hot.device)
+            drop = torch.cat((to_split, torch.zeros(n * int(to_split.sum()), dtype=torch.bool, device=hot.device)))
+            params, variables = remove_points(drop, params, variables, optimizer)
+            thr = remove_thresh_5k if i == 5000 else remove_thresh
+            drop = (torch.sigmoid(params['logit_opacities']) < thr).squeeze(-1)
+            if i >= 3000:
+                drop = drop | (torch.exp(params['log_scales']).max(dim=1).values > 0.1 * variables['scene_radius'])
+            params, variables = remove_points(drop, params, variables, optimizer)
+        if i > 0 and i % 3000 == 0:
+            reset = torch.full_like(params['logit_opacities'], math.log(0.01 / 0.99))   # inverse_sigmoid(0.01)
+            params = update_params_and_optimizer({'logit_opacities': reset}, params, optimizer)
+    return params, variables, params['means3D'].shape[0]
+
+
+def initialize_params_from_point_cloud(init_pt_cld, cam_centers, device="cuda", max_cams=50):
+    """initialize_params of train_utils.py:89-149 from an in-memory [n,7] array (xyz, rgb, seg) instead of the .npz path."""
+    pts = np.asarray(init_pt_cld, np.float64)
+    seg = pts[:, 6]
+    sq, _ = knn(pts[:, :3], 3)
+    mean3 = sq.mean(-1).clip(min=1e-7)
+    raw = {'means3D': pts[:, :3], 'rgb_colors': pts[:, 3:6], 'seg_colors': np.stack((seg, np.zeros_like(seg), 1 - seg), -1),
+           'unnorm_rotations': np.tile([1, 0, 0, 0], (seg.shape[0], 1)), 'logit_opacities': np.zeros((seg.shape[0], 1)),
+           'log_scales': np.tile(np.log(np.sqrt(mean3))[..., None], (1, 3)), 'cam_m': np.zeros((max_cams, 3)),
+           'cam_c': np.zeros((max_cams, 3))}
+    params = {k: torch.nn.Parameter(torch.tensor(v, dtype=torch.float32, device=device).contiguous()) for k, v in raw.items()}
+    params['rgb_colors'].requires_grad = False
+    cam_centers = np.asarray(cam_centers, np.float64)
+    scene_radius = 1.1 * np.max(np.linalg.norm(cam_centers - np.mean(cam_centers, 0)[None], axis=-1))
+    n = params['means3D'].shape[0]
+    z = lambda: torch.zeros(n, device=device)
+    variables = {'max_2D_radius': z(), 'scene_radius': float(scene_radius), 'means2D_gradient_accum': z(), 'denom': z()}
+    return params, variables
+
+
+def train_frames(params, variables, optimizer, datasets, iters_first=10000, iters_next=2000, num_knn=20, densify_args=None,
+                 loss_kwargs=None, seed=0):
+    """The episode loop of train_gs.py:10-46 on in-memory per-frame datasets (lists of {'cam','im','seg','id'}): 10 000
+    iterations with densification at t = 0, then FusedTrackingStep graphs for every later frame. Returns per-frame snapshots of
+    (means3D, rgb_colors, unnorm_rotations) like params2cpu (helpers.py:141-147)."""
+    import random
+    rnd = random.Random(seed)
+    out = []
+    for t, dataset in enumerate(datasets):
+        if t == 0:
+            for i in range(iters_first):
+                data = dataset[rnd.randrange(len(dataset))]
+                loss, variables = get_loss(params, data, variables, True, fused=False, **(loss_kwargs or {}))
+                loss.backward()
+                with torch.no_grad():
+                    if densify_args is not None:
+                        params, variables, _ = densify(params, variables, optimizer, i, *densify_args)
+                    optimizer.step()
+                    optimizer.zero_grad(set_to_none=True)
+            variables = initialize_post_first_timestep(params, variables, optimizer, num_knn)
+        else:
+            params, variables = initialize_per_timestep(params, variables, optimizer)
+            step = FusedTrackingStep(params, variables, optimizer, dataset, loss_kwargs=loss_kwargs)
+            step.prepare()
+            for i in range(iters_next):
+                step.step(rnd.randrange(len(dataset)))
+            variables = step.variables
+        out.append({k: params[k].detach().cpu().numpy().copy() for k in ('means3D', 'rgb_colors', 'unnorm_rotations')})
+    return params, variables, out

@@ -293,3 +293,65 @@ def test_fused_tracking_step_matches_autograd_path():
     lg = [float(fg.step(c)) for c in seq]
     l2 = [float(fe.step(c)) for c in seq]
     np.testing.assert_allclose(lg, l2, rtol=1e-4)
+
+
+def test_t0_densification_surgery_and_short_episode():
+    """A9/A12 + episode loop: densify bookkeeping (clone / split / prune, Adam state surgery) and a 2-frame episode."""
+    from gs_dynamics_b200 import tracking as TR, scenes, rasterizer as R
+    W0, H0, cams = scenes.demo_cameras()
+    rng = np.random.default_rng(0)
+    n = 1200
+    pts = np.concatenate([rng.uniform([-0.1, -0.1, -0.05], [0.1, 0.1, 0.0], (n, 3)) + [0.28, 0.073, 0.0], rng.uniform(size=(n, 3)),
+                          np.ones((n, 1))], 1)
+    cam_centers = np.stack([np.linalg.inv(c[1])[:3, 3] for c in cams])
+    params, variables = TR.initialize_params_from_point_cloud(pts, cam_centers)
+    opt = TR.initialize_optimizer(params, variables)
+    # targets: the same cloud rendered with slightly different colours
+    datasets = []
+    for t in range(2):
+        ds = []
+        for cid in (0, 1):
+            k, w2c = cams[cid]
+            k = k.copy(); k[0] *= 160 / W0; k[1] *= 120 / H0
+            cam = TR.setup_camera(160, 120, k, w2c, near=1.0, far=100)
+            with torch.no_grad():
+                rv = TR.params2rendervar(params)
+                shift = torch.tensor([0.002 * t, 0.0, 0.0], device="cuda")
+                im, _, _, _ = R.raster_forward(cam, rv['means3D'] + shift, rv['opacities'], (rv['colors_precomp'] * 0.9).contiguous(),
+                                               rv['scales'] * 1.2, rv['rotations'])
+                sg, _, _, _ = R.raster_forward(cam, rv['means3D'] + shift, rv['opacities'], params['seg_colors'].detach(),
+                                               rv['scales'] * 1.2, rv['rotations'])
+            ds.append({'cam': cam, 'im': im.clone(), 'seg': sg.clone(), 'id': cid})
+        datasets.append(ds)
+    # a few t = 0 iterations, then force one densification round
+    for i in range(6):
+        loss, variables = TR.get_loss(params, datasets[0][i % 2], variables, True)
+        loss.backward()
+        with torch.no_grad():
+            params, variables, npts = TR.densify(params, variables, opt, i, 0.005, 0.25, 0.05)
+            opt.step(); opt.zero_grad(set_to_none=True)
+    assert npts == n and float(variables['denom'].max()) == 6.0
+    loss, variables = TR.get_loss(params, datasets[0][0], variables, True)
+    loss.backward()
+    g_before = (variables['means2D_gradient_accum'] + torch.norm(variables['means2D'].grad[:, :2], dim=-1) * variables['seen']) / \
+               (variables['denom'] + variables['seen'])
+    limit = 0.05 * variables['scene_radius']
+    big = torch.exp(params['log_scales']).max(1).values > limit
+    n_clone = int(((g_before >= 1e-6) & ~big).sum()); n_split = int(((g_before >= 1e-6) & big).sum())
+    n_transparent = 0  # opacities start at sigmoid(0) = 0.5 > thresholds
+    with torch.no_grad():
+        params, variables, npts = TR.densify(params, variables, opt, 500, 0.005, 0.25, 0.05, grad_thresh=1e-6)
+        opt.step(); opt.zero_grad(set_to_none=True)
+    assert npts == n + n_clone + n_split - n_transparent and n_clone + n_split > 0
+    for k in TR.PER_POINT_KEYS:
+        p = params[k]
+        st = opt.state[p]
+        assert p.shape[0] == npts and st['exp_avg'].shape == p.shape and st['exp_avg_sq'].shape == p.shape
+    assert variables['denom'].shape[0] == npts and float(variables['denom'].abs().max()) == 0.0
+    # the episode loop: a short t = 0 and one tracked frame through the fused graph path
+    l0 = float(TR.get_loss(params, datasets[0][0], variables, True)[0])
+    params, variables, snaps = TR.train_frames(params, variables, opt, datasets, iters_first=25, iters_next=40, num_knn=6)
+    assert len(snaps) == 2 and snaps[1]['means3D'].shape == (npts, 3)
+    l1 = float(TR.get_loss(params, datasets[0][0], variables, True)[0])
+    assert np.isfinite(l1) and l1 < l0
+    assert "edge_records" in variables and variables['prior_losses'].shape == (6,)
