@@ -100,6 +100,7 @@ struct GsdRenderParams {
     float *chunk_state;        // per work item: SoA fields x 256 pixels (see raster_render.cu)
     float *term_state;         // per tile: terminal record of each pixel
     int max_items;
+    int geom_only;             // backward: only mean2D / conic partials (colours and opacities frozen)
     const float *bg0, *bg1; // device [3] each; bg1 may be null
     float *out_color; // [CH,H,W]
     float *out_depth; // [H,W]

@@ -36,7 +36,7 @@ __device__ __forceinline__ void ph_affine(const float *log_scale, const float *s
 // MODE 0: everything from x and y.  MODE 1: the target's window statistics (mu2 = conv(y), s22 = conv(y*y)) are read from
 // maps precomputed once per target image (they do not change during an episode frame).  MODE 2: write those maps.
 template <int MODE>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 gsd_ssim_stats_kernel(int C, int H, int W, PhWin win, const float *__restrict__ X, const float *__restrict__ Y,
                       const float *__restrict__ log_scale, const float *__restrict__ shift, int affine_channels,
                       float *__restrict__ y_mu, float *__restrict__ y_s22,
@@ -134,7 +134,7 @@ gsd_ssim_stats_kernel(int C, int H, int W, PhWin win, const float *__restrict__ 
             }
         }
     }
-    if (MODE == 2) return;
+    if (MODE != 2) {
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
         l1 += __shfl_xor_sync(0xffffffffu, l1, o);
@@ -148,6 +148,7 @@ gsd_ssim_stats_kernel(int C, int H, int W, PhWin win, const float *__restrict__ 
         size_t bid = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
         block_sums[2 * bid] = a;
         block_sums[2 * bid + 1] = b;
+    }
     }
 }
 
@@ -181,7 +182,7 @@ __global__ void gsd_ssim_finish_kernel(int n_sets, int blocks_per_set, const flo
 }
 
 // kernel 2: d loss / d rendered = gscale * set_weight * scale_c * ( w_l1*sign(x-y)/N - w_ssim/N * (conv(dmu) + 2x*conv(ds11) + y*conv(ds12)) )
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 gsd_ssim_grad_kernel(int C, int H, int W, PhWin win, const float *__restrict__ X, const float *__restrict__ Y,
                      const float *__restrict__ log_scale, const float *__restrict__ shift, int affine_channels,
                      const float *__restrict__ dmu, const float *__restrict__ ds11, const float *__restrict__ ds12,

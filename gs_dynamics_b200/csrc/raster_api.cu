@@ -11,7 +11,7 @@ int gsd_launch_mark_visible(int G, const GsdCam &cam, const float *means3D, uint
 int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, const GsdBinWs &b, cudaStream_t st);
 int gsd_launch_render_fwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st);
 int gsd_launch_render_bwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st);
-int gsd_launch_preprocess_bwd(int G, const GsdCam &cam, const GsdRasterBwd *a, const GsdGeomWs &g, cudaStream_t st);
+int gsd_launch_preprocess_bwd(int G, const GsdCam &cam, const GsdRasterBwd *a, const GsdGeomWs &g, int geom_only, cudaStream_t st);
 
 #include <atomic>
 static thread_local char g_err[512] = "";
@@ -138,7 +138,7 @@ static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages)
     int rc;
     if ((rc = make_cam(f, &cam))) return rc;
     if (!f->geom_ws || !f->binning_ws || !f->image_ws || !a->partial_ws || !a->dL_dcolor ||
-        ((stages & 2) && f->G > 0 && (!a->dL_dmeans3D || !a->dL_dopacities || !a->dL_dscales || !a->dL_drotations))) {
+        ((stages & 2) && f->G > 0 && (!a->dL_dmeans3D || !a->dL_dscales || !a->dL_drotations))) {
         gsd_set_error("null workspace/output pointer");
         return GSD_ERR_INVALID;
     }
@@ -163,9 +163,12 @@ static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages)
     p.n_contrib = im.n_contrib;
     p.dL_dcolor = a->dL_dcolor;
     p.partials = (float *)a->partial_ws;
+    // colours and opacities frozen (no output requested): geometry-only partials
+    const int geom_only = (!a->dL_dcolors0 && !a->dL_dcolors1 && !a->dL_dopacities) ? 1 : 0;
+    p.geom_only = geom_only;
     if ((stages & 1) && f->G > 0 && f->capacity > 0)
         if ((rc = gsd_launch_render_bwd(p, tiles, f->n_sets, st))) return rc;
-    if (stages & 2) return gsd_launch_preprocess_bwd(f->G, cam, a, g, st);
+    if (stages & 2) return gsd_launch_preprocess_bwd(f->G, cam, a, g, geom_only, st);
     return GSD_OK;
 }
 

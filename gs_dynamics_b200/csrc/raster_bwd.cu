@@ -6,7 +6,7 @@
 // means2D.grad at /root/reference/src/tracking/external.py:138-142). dL/ddepth is ignored as upstream does.
 #include "common.cuh"
 
-template <int CH>
+template <int CH, bool GEOM>
 __global__ void __launch_bounds__(256)
 gsd_preprocess_bwd_kernel(int G, GsdCam cam, int64_t capacity, const float *__restrict__ means3D,
                           const float *__restrict__ scales, const float *__restrict__ rotations,
@@ -32,18 +32,24 @@ gsd_preprocess_bwd_kernel(int G, GsdCam cam, int64_t capacity, const float *__re
             int64_t s = s0 + k;
             if (s >= capacity) break;
             const float4 *r = partials + s * 4;
-            float4 a = r[0], b = r[1], c = r[2];
+            float4 a = r[0], b = r[1];
             acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
             acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-            acc[8] += c.x; acc[9] += c.y; acc[10] += c.z; acc[11] += c.w;
+            if (!GEOM) {
+                float4 c = r[2];
+                acc[8] += c.x; acc[9] += c.y; acc[10] += c.z; acc[11] += c.w;
+            }
         }
     }
     // layout of a partial record: colours[CH], mean2D.x, mean2D.y, conic.a, conic.b(half), conic.c, opacity
-    float dm2x = acc[CH], dm2y = acc[CH + 1];
-    float dca = acc[CH + 2], dcb = acc[CH + 3], dcc = acc[CH + 4];
-    if (dcolors0) { dcolors0[3 * i] = acc[0]; dcolors0[3 * i + 1] = acc[1]; dcolors0[3 * i + 2] = acc[2]; }
-    if (CH == 6 && dcolors1) { dcolors1[3 * i] = acc[3]; dcolors1[3 * i + 1] = acc[4]; dcolors1[3 * i + 2] = acc[5]; }
-    dopac[i] = acc[CH + 5];
+    constexpr int OG = GEOM ? 0 : CH;
+    float dm2x = acc[OG], dm2y = acc[OG + 1];
+    float dca = acc[OG + 2], dcb = acc[OG + 3], dcc = acc[OG + 4];
+    if (!GEOM) {
+        if (dcolors0) { dcolors0[3 * i] = acc[0]; dcolors0[3 * i + 1] = acc[1]; dcolors0[3 * i + 2] = acc[2]; }
+        if (CH == 6 && dcolors1) { dcolors1[3 * i] = acc[3]; dcolors1[3 * i + 1] = acc[4]; dcolors1[3 * i + 2] = acc[5]; }
+        if (dopac) dopac[i] = acc[(CH + 5) % 12];
+    }
     if (dmeans2D) { dmeans2D[3 * i] = dm2x; dmeans2D[3 * i + 1] = dm2y; dmeans2D[3 * i + 2] = 0.f; }
     float dmean[3] = {0.f, 0.f, 0.f}, dsc[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
     if (vis) {
@@ -153,18 +159,20 @@ gsd_preprocess_bwd_kernel(int G, GsdCam cam, int64_t capacity, const float *__re
     for (int k = 0; k < 4; ++k) drot[4 * i + k] = dq[k];
 }
 
-int gsd_launch_preprocess_bwd(int G, const GsdCam &cam, const GsdRasterBwd *a, const GsdGeomWs &g, cudaStream_t st) {
+int gsd_launch_preprocess_bwd(int G, const GsdCam &cam, const GsdRasterBwd *a, const GsdGeomWs &g, int geom_only, cudaStream_t st) {
     if (G == 0) return GSD_OK;
     const GsdRasterFwd &f = a->fwd;
     int blocks = (G + 255) / 256;
-    if (f.n_sets == 1)
-        gsd_preprocess_bwd_kernel<3><<<blocks, 256, 0, st>>>(
-            G, cam, f.capacity, f.means3D, f.scales, f.rotations, f.radii, g.slot_base, g.tiles, (const float4 *)a->partial_ws,
-            a->dL_dmeans3D, a->dL_dmeans2D, a->dL_dcolors0, a->dL_dcolors1, a->dL_dopacities, a->dL_dscales, a->dL_drotations);
-    else
-        gsd_preprocess_bwd_kernel<6><<<blocks, 256, 0, st>>>(
-            G, cam, f.capacity, f.means3D, f.scales, f.rotations, f.radii, g.slot_base, g.tiles, (const float4 *)a->partial_ws,
-            a->dL_dmeans3D, a->dL_dmeans2D, a->dL_dcolors0, a->dL_dcolors1, a->dL_dopacities, a->dL_dscales, a->dL_drotations);
+#define GSD_PB_ARGS G, cam, f.capacity, f.means3D, f.scales, f.rotations, f.radii, g.slot_base, g.tiles, (const float4 *)a->partial_ws, \
+        a->dL_dmeans3D, a->dL_dmeans2D, a->dL_dcolors0, a->dL_dcolors1, a->dL_dopacities, a->dL_dscales, a->dL_drotations
+    if (geom_only) {
+        if (f.n_sets == 1) gsd_preprocess_bwd_kernel<3, true><<<blocks, 256, 0, st>>>(GSD_PB_ARGS);
+        else gsd_preprocess_bwd_kernel<6, true><<<blocks, 256, 0, st>>>(GSD_PB_ARGS);
+    } else {
+        if (f.n_sets == 1) gsd_preprocess_bwd_kernel<3, false><<<blocks, 256, 0, st>>>(GSD_PB_ARGS);
+        else gsd_preprocess_bwd_kernel<6, false><<<blocks, 256, 0, st>>>(GSD_PB_ARGS);
+    }
+#undef GSD_PB_ARGS
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }

@@ -96,7 +96,7 @@ __device__ __forceinline__ void load_chunk(const GsdRenderParams &p, float4 (*pl
 // forward A1: local composite of one chunk
 // ------------------------------------------------------------------------------------------------------
 template <int CH>
-__global__ void __launch_bounds__(GSD_CWARPS * 32, 8)
+__global__ void __launch_bounds__(GSD_CWARPS * 32, 6)
 gsd_blend_fwd_chunk_kernel(GsdRenderParams p) {
     constexpr int NPL = (CH == 3) ? 3 : 4;
     using IS = ItemState<CH>;
@@ -336,6 +336,18 @@ gsd_blend_fwd_combine_kernel(GsdRenderParams p) {
     if (nc > 0) {
         const float *ts = p.term_state + (size_t)tile * TS::NF * 256;
         const int cstar = reinterpret_cast<const int *>(ts)[TS::CSTAR * 256 + t];
+        // the loads of chunk c+1 are issued before chunk c is folded in (the loop is otherwise a chain of dependent L2 round trips)
+        float nP = 0.f, nD = 0.f, nC[CH];
+        int nl = 0;
+        auto fetch = [&](int c) {
+            const float *st = p.chunk_state + (size_t)(item0 + c) * IS::NF * 256;
+            nl = reinterpret_cast<const int *>(st)[IS::LAST * 256 + t];
+            nP = st[IS::P * 256 + t];
+            nD = st[IS::D * 256 + t];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) nC[k] = st[(IS::C + k) * 256 + t];
+        };
+        if (cstar != 0) fetch(0);
         for (int c = 0; c < nc; ++c) {
             if (c == cstar) {
                 const int lc = reinterpret_cast<const int *>(ts)[TS::LAST * 256 + t];
@@ -346,13 +358,17 @@ gsd_blend_fwd_combine_kernel(GsdRenderParams p) {
                 if (lc > 0) last = c * GSD_CHUNK + lc;
                 break;
             }
-            const float *st = p.chunk_state + (size_t)(item0 + c) * IS::NF * 256;
-            const int lc = reinterpret_cast<const int *>(st)[IS::LAST * 256 + t];
+            const float cP = nP, cD = nD;
+            const int lc = nl;
+            float cC[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) cC[k] = nC[k];
+            if (c + 1 < nc && c + 1 != cstar) fetch(c + 1);
             if (lc > 0) {
 #pragma unroll
-                for (int k = 0; k < CH; ++k) C[k] += T * st[(IS::C + k) * 256 + t];
-                D += T * st[IS::D * 256 + t];
-                T = __fmul_rn(T, st[IS::P * 256 + t]);
+                for (int k = 0; k < CH; ++k) C[k] += T * cC[k];
+                D += T * cD;
+                T = __fmul_rn(T, cP);
                 last = c * GSD_CHUNK + lc;
             }
         }
@@ -403,6 +419,16 @@ gsd_blend_bwd_prefix_kernel(GsdRenderParams p) {
         for (int c = 0; c < CH; ++c) dLdC[c] = 0.f;
     }
     float T = 1.0f;
+    float nP = 0.f, nC[CH];
+    int nl = 0;
+    auto fetch = [&](int c) {
+        const float *st = p.chunk_state + (size_t)(item0 + c) * IS::NF * 256;
+        nl = reinterpret_cast<const int *>(st)[IS::LAST * 256 + t];
+        nP = st[IS::P * 256 + t];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) nC[k] = st[(IS::C + k) * 256 + t];
+    };
+    fetch(0);
     for (int c = 0; c < nc; ++c) {
         float *st = p.chunk_state + (size_t)(item0 + c) * IS::NF * 256;
         st[IS::TIN * 256 + t] = T;
@@ -415,13 +441,18 @@ gsd_blend_bwd_prefix_kernel(GsdRenderParams p) {
             }
             break;
         }
-        const int lc = reinterpret_cast<const int *>(st)[IS::LAST * 256 + t];
+        const float cP = nP;
+        const int lc = nl;
+        float cC[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) cC[k] = nC[k];
+        if (c + 1 < nc) fetch(c + 1);
         if (lc > 0) {
             float cd = 0.f;
 #pragma unroll
-            for (int k = 0; k < CH; ++k) cd += dLdC[k] * st[(IS::C + k) * 256 + t];
+            for (int k = 0; k < CH; ++k) cd += dLdC[k] * cC[k];
             Q -= T * cd;
-            T = __fmul_rn(T, st[IS::P * 256 + t]);
+            T = __fmul_rn(T, cP);
         }
     }
 }
@@ -429,11 +460,14 @@ gsd_blend_bwd_prefix_kernel(GsdRenderParams p) {
 // ------------------------------------------------------------------------------------------------------
 // backward A': gradients of one chunk
 // ------------------------------------------------------------------------------------------------------
-template <int CH>
+// GEOM: only the geometry gradients (mean2D, conic) are produced — the steady state of the tracker freezes colours and
+// opacities (train_utils.py:370-373), which shrinks the per-Gaussian warp reduction from 12 to 5 values.
+template <int CH, bool GEOM>
 __global__ void __launch_bounds__((GSD_CWARPS + 1) * 32, 5)
 gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
-    constexpr int NV = CH + 6; // colours, mean2D(2), conic(3), opacity(1)
-    constexpr int S = (CH == 3) ? 3 : 2; // ring of per-warp partial-sum stages (static shared memory budget)
+    constexpr int NV = GEOM ? 5 : CH + 6; // [colours,] mean2D(2), conic(3) [, opacity(1)]
+    constexpr int OG = GEOM ? 0 : CH;     // offset of the geometry values inside a partial record
+    constexpr int S = (GEOM || CH == 3) ? 3 : 2; // ring of per-warp partial-sum stages (static shared memory budget)
     using IS = ItemState<CH>;
     __shared__ __align__(128) float4 planes[4][GSD_CHUNK];
     __shared__ float acc[S][GSD_CWARPS][GSD_SUB][NV];
@@ -550,16 +584,18 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
                 const float dL_dalpha = ok ? (T * cd - __fdividef(Qn + tail, one_m)) : 0.f;
                 const float Ge = ok ? Gr : 0.f;
                 float v[NV];
+                if (!GEOM) {
 #pragma unroll
-                for (int c = 0; c < CH; ++c) v[c] = w * dLdC[c];
+                    for (int c = 0; c < CH; ++c) v[c % NV] = w * dLdC[c];
+                    v[(CH + 5) % NV] = Ge * dL_dalpha;
+                }
                 const float dL_dG = g1.w * dL_dalpha;
                 const float gdx = Ge * dx, gdy = Ge * dy;
-                v[CH + 0] = dL_dG * (-gdx * g1.x - gdy * g1.y) * ddelx_dx;
-                v[CH + 1] = dL_dG * (-gdy * g1.z - gdx * g1.y) * ddely_dy;
-                v[CH + 2] = -0.5f * gdx * dx * dL_dG;
-                v[CH + 3] = -0.5f * gdx * dy * dL_dG;
-                v[CH + 4] = -0.5f * gdy * dy * dL_dG;
-                v[CH + 5] = Ge * dL_dalpha;
+                v[OG + 0] = dL_dG * (-gdx * g1.x - gdy * g1.y) * ddelx_dx;
+                v[OG + 1] = dL_dG * (-gdy * g1.z - gdx * g1.y) * ddely_dy;
+                v[OG + 2] = -0.5f * gdx * dx * dL_dG;
+                v[OG + 3] = -0.5f * gdx * dy * dL_dG;
+                v[OG + 4] = -0.5f * gdy * dy * dL_dG;
                 if (ok) {
                     Q = Qn;
                     T = __fmul_rn(T, one_m);
@@ -602,8 +638,13 @@ int gsd_launch_render_bwd(const GsdRenderParams &p, int tiles, int n_sets, cudaS
     else gsd_blend_bwd_prefix_kernel<6><<<tiles, GSD_CWARPS * 32, 0, st>>>(p);
     GSD_LAUNCH_CHECK();
     const int threads = (GSD_CWARPS + 1) * 32;
-    if (n_sets == 1) gsd_blend_bwd_chunk_kernel<3><<<p.max_items, threads, 0, st>>>(p);
-    else gsd_blend_bwd_chunk_kernel<6><<<p.max_items, threads, 0, st>>>(p);
+    if (p.geom_only) {
+        if (n_sets == 1) gsd_blend_bwd_chunk_kernel<3, true><<<p.max_items, threads, 0, st>>>(p);
+        else gsd_blend_bwd_chunk_kernel<6, true><<<p.max_items, threads, 0, st>>>(p);
+    } else {
+        if (n_sets == 1) gsd_blend_bwd_chunk_kernel<3, false><<<p.max_items, threads, 0, st>>>(p);
+        else gsd_blend_bwd_chunk_kernel<6, false><<<p.max_items, threads, 0, st>>>(p);
+    }
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }

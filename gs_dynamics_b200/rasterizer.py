@@ -141,8 +141,9 @@ def raster_forward(settings, means3D, opacities, colors0, scales, rotations, col
     return color, radii, depth, state
 
 
-def raster_backward(state, grad_color, need_means2D=True):
-    """Runs the backward kernels. Returns dict of gradients (float32 CUDA tensors)."""
+def raster_backward(state, grad_color, need_means2D=True, geom_only=False):
+    """Runs the backward kernels. Returns dict of gradients (float32 CUDA tensors). geom_only: colours and opacities are
+    frozen (steady-state tracking) — their gradients are not produced and the blend backward reduces 5 values per instance."""
     lib = _lib.lib()
     G, n_sets = state.G, state.n_sets
     dev = grad_color.device
@@ -154,9 +155,9 @@ def raster_backward(state, grad_color, need_means2D=True):
         partial = torch.empty(sz[3], dtype=torch.uint8, device=dev)
         g = dict(means3D=torch.empty((G, 3), dtype=torch.float32, device=dev),
                  means2D=torch.empty((G, 3), dtype=torch.float32, device=dev) if need_means2D else None,
-                 colors0=torch.empty((G, 3), dtype=torch.float32, device=dev),
-                 colors1=torch.empty((G, 3), dtype=torch.float32, device=dev) if n_sets == 2 else None,
-                 opacities=torch.empty((G, 1), dtype=torch.float32, device=dev),
+                 colors0=torch.empty((G, 3), dtype=torch.float32, device=dev) if not geom_only else None,
+                 colors1=torch.empty((G, 3), dtype=torch.float32, device=dev) if (n_sets == 2 and not geom_only) else None,
+                 opacities=torch.empty((G, 1), dtype=torch.float32, device=dev) if not geom_only else None,
                  scales=torch.empty((G, 3), dtype=torch.float32, device=dev),
                  rotations=torch.empty((G, 4), dtype=torch.float32, device=dev))
         b = _lib.GsdRasterBwd()

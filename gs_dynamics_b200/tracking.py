@@ -561,7 +561,7 @@ class FusedTrackingStep(TrackingStep):
             prior, parts = _TrackPriors.forward(_NullCtx(), x.detach(), self.rot, V, (self.w['weight_rigid'], self.w['weight_rot'],
                                                 self.w['weight_iso'], FLOOR_WEIGHT, self.w['weight_bg']))
             gx_p, gq_p = _NullCtx.saved
-            g = R.raster_backward(state, dL, need_means2D=False)
+            g = R.raster_backward(state, dL, need_means2D=False, geom_only=True)
             u = _lib.GsdTrackUpdate()
             u.G = G
             u.beta1, u.beta2, u.eps = self.optimizer.betas[0], self.optimizer.betas[1], self.optimizer.eps

@@ -92,7 +92,8 @@ typedef struct {
     float *dL_dmeans2D;   /* [G,3] NDC-scaled screen-space gradient (xy), z = 0; may be NULL */
     float *dL_dcolors0;   /* [G,3]; may be NULL */
     float *dL_dcolors1;   /* [G,3]; may be NULL */
-    float *dL_dopacities; /* [G] */
+    float *dL_dopacities; /* [G]; may be NULL. dL_dcolors0 = dL_dcolors1 = dL_dopacities = NULL selects the geometry-only
+                           * backward (colours / opacities frozen): 5 instead of 9-12 partials per instance */
     float *dL_dscales;    /* [G,3] */
     float *dL_drotations; /* [G,4] */
 } GsdRasterBwd;

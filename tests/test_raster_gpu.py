@@ -143,6 +143,25 @@ def test_fused_two_sets_equals_two_renders():
     assert rel_err(gf["colors1"].cpu(), g1["colors0"].cpu()) < 1e-5
 
 
+def test_geometry_only_backward_equals_full_backward():
+    """Steady-state mode (colours / opacities frozen): same means3D / rotations / scales / means2D gradients, bit for bit in
+    the per-instance partials' geometry part up to summation order inside the warp reduce."""
+    from gs_dynamics_b200 import rasterizer as R
+    for n_sets in (1, 2):
+        cam = make_camera(1, 320, 240)
+        sc, act = make_scene(9000, 21, scale_boost=0.5, box_scale=0.8)
+        a = _to_cuda(act)
+        seg = sc["seg_colors"].cuda() if n_sets == 2 else None
+        st = settings_from(cam, [0.1, 0.2, 0.3])
+        c, r, d, s = _render(a, st, colors1=seg)
+        dL = torch.randn(3 * n_sets, 240, 320, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+        full = R.raster_backward(s, dL)
+        geom = R.raster_backward(s, dL, geom_only=True)
+        assert geom["colors0"] is None and geom["opacities"] is None
+        for k in ("means3D", "means2D", "scales", "rotations"):
+            assert rel_err(geom[k].cpu(), full[k].cpu()) < 1e-5, (n_sets, k)
+
+
 def test_backward_is_bit_reproducible():
     from gs_dynamics_b200 import rasterizer as R
     cam = make_camera(0, 640, 480)
