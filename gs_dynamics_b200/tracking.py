@@ -523,6 +523,7 @@ class FusedTrackingStep(TrackingStep):
             self.targets = [torch.cat([d['im'], d['seg']], 0).contiguous() for d in dataset]
             self.rot = torch.empty_like(params['unnorm_rotations'])
             self.tstats = [target_stats(tg) for tg in self.targets]
+        self.side = torch.cuda.Stream(device=params['means3D'].device)
         self.lr = {g['name']: float(g['lr']) for g in optimizer.param_groups}
 
     def set_target(self, cam_id, im, seg):
@@ -549,6 +550,20 @@ class FusedTrackingStep(TrackingStep):
         with torch.cuda.device(x.device):
             st = _stream()
             _lib.check(lib.gsd_track_normalize_rotations(G, uq.data_ptr(), self.rot.data_ptr(), st), "gsd_track_normalize_rotations")
+            # the physical priors depend only on the parameters, not on the render: they run on a side stream concurrently
+            # with binning / sorting / blending (fork-join, captured as parallel branches of the CUDA graph)
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(fork)
+                prior, parts = _TrackPriors.forward(_NullCtx(), x.detach(), self.rot, V, (self.w['weight_rigid'], self.w['weight_rot'],
+                                                    self.w['weight_iso'], FLOOR_WEIGHT, self.w['weight_bg']))
+                gx_p, gq_p = _NullCtx.saved
+                join = torch.cuda.Event()
+                join.record(self.side)
+            for tns in (prior, parts, gx_p, gq_p):
+                tns.record_stream(main)
             color, radii, _, state = R.raster_forward(data['cam'], x.detach(), self.opac, self.rgb, self.scales, self.rot,
                                                       colors1=self.seg, capacity=capacity)
             ws = _ph_workspace(color)
@@ -558,10 +573,8 @@ class FusedTrackingStep(TrackingStep):
             _lib.check(lib.gsd_photometric_forward(C.byref(d), ph.data_ptr(), st), "gsd_photometric_forward")
             dL = torch.empty_like(color)
             _lib.check(lib.gsd_photometric_backward(C.byref(d), None, dL.data_ptr(), st), "gsd_photometric_backward")
-            prior, parts = _TrackPriors.forward(_NullCtx(), x.detach(), self.rot, V, (self.w['weight_rigid'], self.w['weight_rot'],
-                                                self.w['weight_iso'], FLOOR_WEIGHT, self.w['weight_bg']))
-            gx_p, gq_p = _NullCtx.saved
             g = R.raster_backward(state, dL, need_means2D=False, geom_only=True)
+            main.wait_event(join)
             u = _lib.GsdTrackUpdate()
             u.G = G
             u.beta1, u.beta2, u.eps = self.optimizer.betas[0], self.optimizer.betas[1], self.optimizer.eps
