@@ -362,7 +362,7 @@ def run_gnn_ours(device, steps=50, warmup=5, n_obj=2000, seed=1):
     from gs_dynamics_b200 import gnn, workloads as GO
     cfg = GO.sloth_cfg(512)
     model = gnn.DynamicsPredictor(dict(cfg), device).to(device).eval()
-    model.load_state_dict(GO.make_state_dict(cfg, 0))
+    model.load_state_dict(GO.make_state_dict(cfg, 0, head_scale=1e-3))
     gi = GO.make_graph_inputs(n_obj, seed, "sloth")
     p0, eef = gi["state"][0, :, :n_obj].to(device), gi["state"][0, :, n_obj:].to(device)
     ro = gnn.GnnRollout(model, p0, eef, 0.075, 8, True, use_graph=True)
@@ -389,7 +389,7 @@ def run_gnn_ours(device, steps=50, warmup=5, n_obj=2000, seed=1):
     dt_e2e = time.time() - t0
     return {"metric": "GNN steps/sec", "value": steps / dt, "unit": "steps/s", "ms_per_step": 1e3 * dt / steps, "steps": steps,
             "config": {"workload": "predict.py GNN rollout step (edge build + forward + history shift), sloth cfg nf=512, "
-                                   "%d particles + 1 tool, 8-NN, connect_all, %d-step horizon" % (n_obj, steps)},
+                                   "%d particles + 1 tool, 8-NN, connect_all, %d-step horizon, random-init weights with the motion head scaled 1e-3 so the cloud keeps its 8-NN graph" % (n_obj, steps)},
             "e2e": {"value": steps / dt_e2e, "unit": "steps/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": n_obj * 12}}
 
 
@@ -398,7 +398,7 @@ def run_gnn_cpu(budget_s=8.0, n_obj=2000, seed=1):
     from oracle import gnn_oracle as GO
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = GO.sloth_cfg(512)
-    sd = GO.make_state_dict(cfg, 0)
+    sd = GO.make_state_dict(cfg, 0, head_scale=1e-3)
     gi = GO.make_graph_inputs(n_obj, seed, "sloth")
     done, t0 = 0, time.time()
     with torch.no_grad():

@@ -14,6 +14,7 @@
 #include "common.cuh"
 
 #define GNN_MAX_SMEM_NODES 4096
+#define GNN_CAND 256 // within-radius candidates per row kept in shared memory
 
 __device__ __forceinline__ float dist2_rn(float ax, float ay, float az, float bx, float by, float bz) {
     // ((dx^2 + dy^2) + dz^2) without FMA contraction, the order torch.sum(s_diff ** 2, -1) uses for 3 elements
@@ -37,66 +38,128 @@ struct EdgeArgs {
     int32_t *row_count;      // [B*N]
 };
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 gsd_gnn_adjacency_kernel(EdgeArgs a) {
-    extern __shared__ float spos[]; // [N*3] positions of this batch element
-    const int b = blockIdx.y;
+    // shared: positions [N*3] | per warp: candidates [GNN_CAND] u64 | per warp: row distances [N] | per warp: selected bits [words]
+    // | node flags [N] (bit 0 valid, bit 1 tool)
+    extern __shared__ float spos[];
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long *cand_all = reinterpret_cast<unsigned long long *>(spos + ((a.N * 3 + 1) & ~1));
+    float *sd_all = reinterpret_cast<float *>(cand_all + (size_t)warps * GNN_CAND);
+    uint32_t *sel_all = reinterpret_cast<uint32_t *>(sd_all + (size_t)warps * a.N);
+    uint8_t *sflag = reinterpret_cast<uint8_t *>(sel_all + (size_t)warps * a.words);
+    unsigned long long *cand = cand_all + (size_t)warp * GNN_CAND;
+    float *sd = sd_all + (size_t)warp * a.N;
+    uint32_t *selbits = sel_all + (size_t)warp * a.words;
+    const int b = blockIdx.y;
     const float *st = a.states + (size_t)b * a.N * 3;
-    for (int i = threadIdx.x; i < a.N * 3; i += blockDim.x) spos[i] = st[i];
-    __syncthreads();
     const uint8_t *mk = a.mask + (size_t)b * a.N, *tm = a.tool_mask + (size_t)b * a.N;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < a.N * 3; i += blockDim.x) spos[i] = st[i];
+#pragma unroll 4
+    for (int i = threadIdx.x; i < a.N; i += blockDim.x) sflag[i] = (mk[i] ? 1 : 0) | (tm[i] ? 2 : 0);
+    __syncthreads();
     const int n_obj = a.N - a.n_tool;
     const float thr = a.thresh ? __fmul_rn(a.thresh[b], a.thresh[b]) : a.thresh_sq_scalar;
-    const int r = blockIdx.x * warps + warp;
-    if (r >= a.N) return;
+    for (int r = blockIdx.x * warps + warp; r < a.N; r += gridDim.x * warps) {
     const float rx = spos[3 * r], ry = spos[3 * r + 1], rz = spos[3 * r + 2];
-    const bool r_valid = mk[r] != 0, r_tool = tm[r] != 0;
+    const bool r_valid = (sflag[r] & 1) != 0, r_tool = (sflag[r] & 2) != 0;
     uint32_t *row = a.bits + ((size_t)b * a.N + r) * a.words;
+    __syncwarp(); // previous row's readers of sd / selbits / cand are done
 
-    // ---- top-k smallest distances among the object block (only rows of the object block), ties -> lowest index
-    // selected columns are kept as per-lane bit sets: column c is owned by lane c % 32, slot c / 32
-    uint32_t sel[GNN_MAX_SMEM_NODES / 1024]; // slot bits, 32 slots per word
-#pragma unroll
-    for (int w = 0; w < GNN_MAX_SMEM_NODES / 1024; ++w) sel[w] = 0u;
-    const int k_eff = min(a.topk, a.N);
-    if (r < n_obj) {
-        for (int it = 0; it < min(k_eff, n_obj); ++it) {
-            float best = 3.0e38f;
-            int best_c = 0x7fffffff;
-            for (int c = lane, slot = 0; c < n_obj; c += 32, ++slot) {
-                if ((sel[slot >> 5] >> (slot & 31)) & 1u) continue;
-                float d = dist2_rn(rx, ry, rz, spos[3 * c], spos[3 * c + 1], spos[3 * c + 2]);
-                if (!(r_valid && mk[c]) || (r_tool && tm[c])) d = 1e10f;
-                if (d < best) { best = d; best_c = c; }
-            }
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
-                if (ob < best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
-            }
-            if (best_c != 0x7fffffff && (best_c & 31) == lane) {
-                int slot = best_c >> 5;
-                sel[slot >> 5] |= 1u << (slot & 31);
+    // ---- distances of this row, cached per warp (masked pairs -> 1e10 like the reference's dis[mask] = 1e10)
+    int cnt = 0; // object columns within the radius
+    for (int c = lane; c < a.N; c += 32) {
+        float d = dist2_rn(rx, ry, rz, spos[3 * c], spos[3 * c + 1], spos[3 * c + 2]);
+        const int fc = sflag[c];
+        if (!(r_valid && (fc & 1)) || (r_tool && (fc & 2))) d = 1e10f;
+        sd[c] = d;
+        cnt += (c < n_obj && __fsub_rn(d, thr) < 0.f) ? 1 : 0;
+    }
+    for (int w = lane; w < a.words; w += 32) selbits[w] = 0u;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    __syncwarp();
+
+    // ---- object block: adj = (d < r^2) AND (column among the k nearest of the row).  Every column nearer than a
+    // within-radius column is itself within the radius, so only within-radius columns need ranking; and once at least k
+    // columns lie strictly inside a smaller bound t, every column at or beyond t is outside the k nearest.  So: shrink t by
+    // bisection until a small candidate set (>= k columns) lies inside it, compact that set into shared memory, rank the
+    // candidates against each other (ties -> lowest index) and set the bits of those ranked below k.  If bisection cannot
+    // separate (hundreds of equal distances, or k larger than the buffer) fall back to k rounds of warp arg-min.
+    if (r < n_obj && cnt > 0) {
+        const int k_eff = min(a.topk, a.N);
+        const int want = min(GNN_CAND, max(64, 2 * k_eff)); // candidate-set size the bisection aims below
+        float t = thr;
+        bool exact_thr = true, fallback = false;
+        if (cnt > want) {
+            fallback = true;
+            if (k_eff <= want) {
+                float lo = 0.f, hi = thr;
+                for (int it = 0; it < 48; ++it) {
+                    const float mid = 0.5f * (lo + hi);
+                    if (!(mid > lo && mid < hi)) break;
+                    int c_mid = 0;
+                    for (int c = lane; c < n_obj; c += 32) c_mid += sd[c] < mid ? 1 : 0;
+                    c_mid = __reduce_add_sync(0xffffffffu, c_mid);
+                    if (c_mid > want) hi = mid;
+                    else if (c_mid < k_eff) lo = mid;
+                    else { t = mid; exact_thr = false; fallback = false; break; }
+                }
             }
         }
+        if (!fallback) {
+            int n_cand = 0;
+            for (int c0 = 0; c0 < n_obj; c0 += 32) {
+                const int c = c0 + lane;
+                const float d = c < n_obj ? sd[c] : 3.0e38f;
+                const bool in = exact_thr ? (__fsub_rn(d, thr) < 0.f) : (d < t);
+                const unsigned m = __ballot_sync(0xffffffffu, in);
+                const int pos = n_cand + __popc(m & ((1u << lane) - 1u));
+                if (in) cand[pos] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)c; // d >= 0: bit order = value order
+                n_cand += __popc(m);
+            }
+            __syncwarp();
+            for (int q = lane; q < n_cand; q += 32) {
+                const unsigned long long me = cand[q];
+                int rank = 0;
+                for (int j = 0; j < n_cand; ++j) rank += cand[j] < me ? 1 : 0;
+                if (rank < k_eff) {
+                    const unsigned c = (unsigned)(me & 0xffffffffull);
+                    atomicOr(&selbits[c >> 5], 1u << (c & 31));
+                }
+            }
+        } else {
+            for (int it = 0; it < min(k_eff, n_obj); ++it) {
+                float best = 3.0e38f;
+                int best_c = 0x7fffffff;
+                for (int c = lane; c < n_obj; c += 32) { // column c is always visited by lane c % 32: selbits[c/32] bit lane
+                    if ((selbits[c >> 5] >> lane) & 1u) continue;
+                    const float d = sd[c];
+                    if (d < best) { best = d; best_c = c; }
+                }
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) {
+                    float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+                    if (ob < best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+                }
+                if (best_c == 0x7fffffff) break;
+                if ((best_c & 31) == lane) selbits[best_c >> 5] |= 1u << lane;
+                __syncwarp();
+            }
+        }
+        __syncwarp();
     }
+
     // ---- adjacency bits
     int count = 0;
     for (int w = 0; w < a.words; ++w) {
         const int c = w * 32 + lane;
         bool on = false;
         if (c < a.N) {
-            const bool c_valid = mk[c] != 0, c_tool = tm[c] != 0;
-            float d = dist2_rn(rx, ry, rz, spos[3 * c], spos[3 * c + 1], spos[3 * c + 2]);
-            if (!(r_valid && c_valid)) d = 1e10f;
-            if (r_tool && c_tool) d = 1e10f;
-            on = __fsub_rn(d, thr) < 0.f;
-            if (r < n_obj && c < n_obj) {
-                const int slot = c >> 5; // lane == c & 31 by construction
-                on = on && ((sel[slot >> 5] >> (slot & 31)) & 1u);
-            }
+            const bool c_valid = (sflag[c] & 1) != 0, c_tool = (sflag[c] & 2) != 0;
+            on = __fsub_rn(sd[c], thr) < 0.f;
+            if (r < n_obj && c < n_obj) on = on && ((selbits[w] >> lane) & 1u);
             if (a.connect_all) {
                 if (r_tool && c_valid) on = true;
                 if (c_tool && r_valid) on = true;
@@ -108,6 +171,7 @@ gsd_gnn_adjacency_kernel(EdgeArgs a) {
         count += __popc(m);
     }
     if (lane == 0) a.row_count[(size_t)b * a.N + r] = count;
+    } // rows
 }
 
 // single block: exclusive scan of row counts per batch element -> row_ptr [B][N+1]; n_edges[b]
@@ -195,15 +259,22 @@ extern "C" int gsd_gnn_build_edges(const GsdGnnEdges *g, void *stream) {
     a.words = (g->N + 31) / 32;
     a.bits = (uint32_t *)g->ws;
     a.row_count = (int32_t *)((char *)g->ws + gsd_align_up((size_t)g->B * g->N * a.words * 4));
-    const int warps = 4;
-    dim3 grid((g->N + warps - 1) / warps, g->B);
-    size_t smem = (size_t)g->N * 3 * 4;
+    const int warps = 4, adj_warps = 8;
+    // persistent CTAs (8 rows in flight each, 2 CTAs per SM at N = 2000): one wave, the position table is staged once per CTA
+    int ctas = (g->N + adj_warps - 1) / adj_warps;
+    const int max_ctas = (2 * 148 + g->B - 1) / g->B;
+    if (ctas > max_ctas) ctas = max_ctas;
+    dim3 grid(ctas, g->B);
+    size_t smem = (size_t)((g->N * 3 + 1) & ~1) * 4 + (size_t)adj_warps * GNN_CAND * 8 + (size_t)adj_warps * g->N * 4 +
+                  (size_t)adj_warps * a.words * 4 + (size_t)g->N;
     static bool attr_set = false;
     if (!attr_set) {
-        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_gnn_adjacency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GNN_MAX_SMEM_NODES * 12));
+        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_gnn_adjacency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            GNN_MAX_SMEM_NODES * 12 + 8 + 8 * GNN_CAND * 8 + 8 * GNN_MAX_SMEM_NODES * 4 +
+                                                8 * (GNN_MAX_SMEM_NODES / 32) * 4 + GNN_MAX_SMEM_NODES));
         attr_set = true;
     }
-    gsd_gnn_adjacency_kernel<<<grid, warps * 32, smem, st>>>(a);
+    gsd_gnn_adjacency_kernel<<<grid, adj_warps * 32, smem, st>>>(a);
     GSD_LAUNCH_CHECK();
     gsd_gnn_scan_rows_kernel<<<1, 1024, 0, st>>>(g->B, g->N, a.row_count, g->row_ptr, g->n_edges);
     GSD_LAUNCH_CHECK();
@@ -272,7 +343,7 @@ extern "C" int gsd_gnn_edge_inputs(int32_t B, int32_t N, int32_t capacity, int32
 // One warp per (receiver) row for ordinary rows; rows with many edges (the tool rows: every object is a sender) are split
 // over GNN_SPLIT CTAs writing partials that a second kernel sums in fixed order.
 // ------------------------------------------------------------------------------------------------------
-#define GNN_SPLIT 32
+#define GNN_SPLIT 128
 
 template <int VEC_PER_LANE> // F = 128 * VEC_PER_LANE
 __global__ void __launch_bounds__(128)
@@ -328,29 +399,52 @@ gsd_gnn_aggregate_heavy_kernel(int B, int N, int cap, int first_row, int n_heavy
     for (int col = threadIdx.x; col < F4; col += blockDim.x) {
         const float4 pr = P[node * 2 * F4 + col];
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int e = s0; e < s1; ++e) {
-            const size_t ge = (size_t)b * cap + e;
-            const size_t snode = (size_t)b * N + send[ge];
-            const float4 a4 = A[ge * F4 + col];
-            const float4 s4 = P[snode * 2 * F4 + F4 + col];
-            acc.x += fmaxf(a4.x + pr.x + s4.x, 0.f);
-            acc.y += fmaxf(a4.y + pr.y + s4.y, 0.f);
-            acc.z += fmaxf(a4.z + pr.z + s4.z, 0.f);
-            acc.w += fmaxf(a4.w + pr.w + s4.w, 0.f);
+        for (int e = s0; e < s1; e += 4) { // 4 independent gathers in flight
+            float4 a4[4], s4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ee = min(e + u, s1 - 1);
+                const size_t ge = (size_t)b * cap + ee;
+                const size_t snode = (size_t)b * N + send[ge];
+                a4[u] = A[ge * F4 + col];
+                s4[u] = P[snode * 2 * F4 + F4 + col];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (e + u < s1) {
+                    acc.x += fmaxf(a4[u].x + pr.x + s4[u].x, 0.f);
+                    acc.y += fmaxf(a4[u].y + pr.y + s4[u].y, 0.f);
+                    acc.z += fmaxf(a4[u].z + pr.z + s4[u].z, 0.f);
+                    acc.w += fmaxf(a4[u].w + pr.w + s4[u].w, 0.f);
+                }
+            }
         }
         partial[((size_t)hrow * GNN_SPLIT + split) * F4 + col] = acc;
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 gsd_gnn_aggregate_heavy_finish_kernel(int N, int first_row, int n_heavy, int F4, const float4 *__restrict__ partial,
                                       float4 *__restrict__ agg) {
+    __shared__ float4 red[8][32];
     const int hrow = blockIdx.x;
     const int b = hrow / n_heavy, r = first_row + hrow % n_heavy;
-    for (int col = threadIdx.x; col < F4; col += blockDim.x) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < GNN_SPLIT; ++s) {
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int col = blockIdx.y * 32 + lane;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < F4) {
+#pragma unroll 4
+        for (int s = grp * (GNN_SPLIT / 8); s < (grp + 1) * (GNN_SPLIT / 8); ++s) {
             const float4 p = partial[((size_t)hrow * GNN_SPLIT + s) * F4 + col];
+            acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+        }
+    }
+    red[grp][lane] = acc;
+    __syncthreads();
+    if (grp == 0 && col < F4) {
+#pragma unroll
+        for (int g = 1; g < 8; ++g) { // fixed order: deterministic
+            const float4 p = red[g][lane];
             acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
         }
         agg[((size_t)b * N + r) * F4 + col] = acc;
@@ -395,7 +489,7 @@ extern "C" int gsd_gnn_aggregate(int32_t B, int32_t N, int32_t capacity, int32_t
         default: gsd_gnn_aggregate_heavy_kernel<4><<<grid, 128, 0, st>>>(B, N, capacity, n_light, n_heavy, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)ws); break;
         }
         GSD_LAUNCH_CHECK();
-        gsd_gnn_aggregate_heavy_finish_kernel<<<B * n_heavy, 128, 0, st>>>(N, n_light, n_heavy, F / 4, (const float4 *)ws, (float4 *)agg);
+        gsd_gnn_aggregate_heavy_finish_kernel<<<dim3(B * n_heavy, (F / 4 + 31) / 32), 256, 0, st>>>(N, n_light, n_heavy, F / 4, (const float4 *)ws, (float4 *)agg);
         GSD_LAUNCH_CHECK();
     }
     return GSD_OK;
@@ -481,6 +575,47 @@ extern "C" int gsd_fps(int32_t B, int32_t N, int32_t npoints, float radius, cons
     }
     int threads = N >= 1024 ? 1024 : ((N + 31) / 32) * 32;
     gsd_fps_kernel<<<B, threads, (size_t)N * 4, (cudaStream_t)stream>>>(N, npoints, radius, pos, start_idx, out_idx, count);
+    GSD_LAUNCH_CHECK();
+    return GSD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// error-compensated TF32 operands for the dense layers: fp32 accuracy on the tensor cores from ONE TF32 GEMM over a
+// 3x longer K.  With t = relu?(x + add), hi = t rounded to 10 explicit mantissa bits and lo = t - hi, the activation row
+// becomes [lo | hi | hi] and the weight row [w_hi | w_lo | w_hi]:  lo.w_hi + hi.w_lo + hi.w_hi = t.w up to the dropped
+// lo.w_lo term (2^-22 relative).  The small products come first in K so they are summed before the accumulator is large.
+// One pass also applies the previous layer's ReLU / residual add and optionally writes t itself.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_hi(float t) { return __uint_as_float((__float_as_uint(t) + 0x1000u) & 0xffffe000u); }
+
+__global__ void __launch_bounds__(256)
+gsd_tf32_pack_kernel(long long rows, int F4, int relu, int weight_layout, const float4 *__restrict__ x, const float4 *__restrict__ add,
+                     float4 *__restrict__ full, float4 *__restrict__ out) {
+    const long long n4 = rows * F4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = x[i];
+        if (add) { const float4 a = add[i]; v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (full) full[i] = v;
+        const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+        const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        const long long r = i / F4;
+        const int c = (int)(i - r * F4);
+        float4 *o = out + r * 3 * F4 + c;
+        if (weight_layout) { o[0] = h; o[F4] = l; o[2 * F4] = h; }
+        else { o[0] = l; o[F4] = h; o[2 * F4] = h; }
+    }
+}
+
+extern "C" int gsd_tf32_pack(int64_t rows, int32_t F, int32_t relu, int32_t weight_layout, const float *x, const float *add, float *full,
+                             float *out, void *stream) {
+    if (rows < 0 || F <= 0 || (F % 4) != 0 || (rows > 0 && (!x || !out))) { gsd_set_error("invalid arguments (F must be a multiple of 4)"); return GSD_ERR_INVALID; }
+    if (rows == 0) return GSD_OK;
+    long long n4 = rows * (F / 4);
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    gsd_tf32_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rows, F / 4, relu, weight_layout, (const float4 *)x, (const float4 *)add,
+                                                                              (float4 *)full, (float4 *)out);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }

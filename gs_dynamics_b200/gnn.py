@@ -181,6 +181,26 @@ def edge_index_from_dense(Rr, Rs, n_heavy=0):
 
 
 # ----------------------------------------------------------------------------------------------------
+# dense layers: fp32 accuracy on the tensor cores by error-compensated TF32 splitting (x = x_hi + x_lo, three TF32 GEMMs:
+# hi*hi + hi*lo + lo*hi; the dropped lo*lo term is ~2^-22 relative).  The GEMMs themselves are cuBLAS (library code);
+# "ieee" keeps plain fp32 SIMT GEMMs.
+# ----------------------------------------------------------------------------------------------------
+def _tf32_pack(x, relu=False, add=None, want_full=False, weight=False):
+    """Error-compensated TF32 operand of t = relu?(x + add) (gsd_tf32_pack): activations -> [rows, 3F] = [lo | hi | hi],
+    weights -> [out, 3K] = [hi | lo | hi], so that one TF32 GEMM over K = 3F gives the fp32 product.  Returns (packed, t or None)."""
+    x = x.contiguous()
+    rows, Fd = x.shape
+    out = torch.empty((rows, 3 * Fd), device=x.device, dtype=torch.float32)
+    full = torch.empty_like(x) if want_full else None
+    if add is not None:
+        add = add.contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().gsd_tf32_pack(rows, Fd, int(relu), int(weight), x.data_ptr(), add.data_ptr() if add is not None else None,
+                                            full.data_ptr() if want_full else None, out.data_ptr(), _stream()), "gsd_tf32_pack")
+    return out, full
+
+
+# ----------------------------------------------------------------------------------------------------
 # fused kernels as autograd functions
 # ----------------------------------------------------------------------------------------------------
 def edge_inputs(state, attrs, p_instance, edges, attr_dim_used=True, group=True):
@@ -279,10 +299,11 @@ class ParticlePredictor(nn.Module):
 
 
 class DynamicsPredictor(nn.Module):
-    def __init__(self, model_config, device):
+    def __init__(self, model_config, device, matmul="3xtf32"):
         super().__init__()
         self.model_config = model_config
         self.device = device
+        self.matmul = matmul   # "3xtf32": error-compensated TF32 tensor-core GEMMs for the edge-row layers; "ieee": fp32 SIMT
         self.nf_particle = model_config['nf_particle']
         self.nf_relation = model_config['nf_relation']
         self.nf_effect = model_config['nf_effect']
@@ -322,6 +343,73 @@ class DynamicsPredictor(nn.Module):
             p_inputs = torch.cat([p_inputs, action], 2)
         return p_inputs
 
+    def _forward_ieee(self, p_inputs, rel_inputs, edges, B, N, n_p):
+        """fp32 SIMT GEMMs, differentiable (training and the bit-tight parity tests)."""
+        cfg, Fd = self.model_config, self.nf_effect
+        particle_encode = self.particle_encoder(p_inputs).reshape(B * N, Fd)
+        relation_encode = self.relation_encoder(rel_inputs).reshape(B * edges.capacity, Fd)
+        Wr, br = self.relation_propagator.linear.weight, self.relation_propagator.linear.bias
+        Wp, bp = self.particle_propagator.linear.weight, self.particle_propagator.linear.bias
+        A = F.linear(relation_encode, Wr[:, :Fd], br)                 # pstep-invariant edge term
+        C0 = F.linear(particle_encode, Wp[:, :Fd], bp)                # pstep-invariant node term
+        W23 = torch.cat([Wr[:, Fd:2 * Fd], Wr[:, 2 * Fd:]], 0)        # [2F, F]: receiver | sender projections
+        Wp2_t = Wp[:, Fd:].t()
+        h = particle_encode
+        for _ in range(cfg['pstep']):
+            P = F.linear(h, W23)                                      # [B*N, 2F]
+            agg = _Aggregate.apply(A, P, edges)
+            h = torch.relu(torch.addmm(C0 + h, agg, Wp2_t))
+        return self.non_rigid_predictor(h.view(B, N, Fd)[:, :n_p].contiguous())
+
+    def _packed_weights(self):
+        """[w_hi | w_lo | w_hi] operands of every F-wide layer, rebuilt when a parameter changes (version counters)."""
+        ps = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, "_wkey", None) != key:
+            Fd = self.nf_effect
+            Wr, Wp = self.relation_propagator.linear.weight.detach(), self.particle_propagator.linear.weight.detach()
+            pk = lambda w: _tf32_pack(w.detach(), weight=True)[0].t()
+            pe, re, nr = self.particle_encoder.model, self.relation_encoder.model, self.non_rigid_predictor
+            self._wpk = dict(pe2=pk(pe[2].weight), pe4=pk(pe[4].weight), re2=pk(re[2].weight), re4=pk(re[4].weight),
+                             A=pk(Wr[:, :Fd]), C0=pk(Wp[:, :Fd]), W23=pk(torch.cat([Wr[:, Fd:2 * Fd], Wr[:, 2 * Fd:]], 0)),
+                             Wp2=pk(Wp[:, Fd:]), nr0=pk(nr.linear_0.weight), nr1=pk(nr.linear_1.weight))
+            self._wkey = key
+        return self._wpk
+
+    def _forward_3xtf32(self, p_inputs, rel_inputs, edges, B, N, n_p):
+        """Inference path: every F-wide layer is one TF32 tensor-core GEMM over the error-compensated K = 3F operands
+        (gsd_tf32_pack), which also carries the ReLU / residual add between layers.  Same results as the fp32 path to ~1e-6."""
+        cfg, Fd = self.model_config, self.nf_effect
+        W = self._packed_weights()
+        pe, re, nr = self.particle_encoder.model, self.relation_encoder.model, self.non_rigid_predictor
+        br, bp = self.relation_propagator.linear.bias, self.particle_propagator.linear.bias
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        y = F.linear(p_inputs.reshape(B * N, -1), pe[0].weight, pe[0].bias)        # K = 5..14: fp32
+        e = F.linear(rel_inputs.reshape(B * edges.capacity, -1), re[0].weight, re[0].bias)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            y = torch.addmm(pe[2].bias, _tf32_pack(y, relu=True)[0], W["pe2"])
+            y = torch.addmm(pe[4].bias, _tf32_pack(y, relu=True)[0], W["pe4"])
+            hp, h = _tf32_pack(y, relu=True, want_full=True)                        # particle_encode
+            C0 = torch.addmm(bp, hp, W["C0"])
+            e = torch.addmm(re[2].bias, _tf32_pack(e, relu=True)[0], W["re2"])
+            e = torch.addmm(re[4].bias, _tf32_pack(e, relu=True)[0], W["re4"])
+            A = torch.addmm(br, _tf32_pack(e, relu=True)[0], W["A"])
+            for _ in range(cfg['pstep']):
+                P = hp @ W["W23"]
+                agg = _Aggregate.apply(A, P, edges)
+                y = torch.addmm(C0, _tf32_pack(agg)[0], W["Wp2"])
+                hp, h = _tf32_pack(y, relu=True, add=h, want_full=True)
+            if n_p != N:
+                hp = hp.view(B, N, 3 * Fd)[:, :n_p].reshape(B * n_p, 3 * Fd)
+            y = torch.addmm(nr.linear_0.bias, hp, W["nr0"])
+            y = torch.addmm(nr.linear_1.bias, _tf32_pack(y, relu=True)[0], W["nr1"])
+            torch.backends.cuda.matmul.allow_tf32 = False
+            return F.linear(torch.relu(y), nr.linear_2.weight, nr.linear_2.bias).view(B, n_p, 3)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+
     def forward(self, state, attrs, Rr, Rs, p_instance, action=None, **kwargs):
         """Rr may be an EdgeIndex (fast path, Rs ignored) or the reference's dense one-hot matrices."""
         cfg = self.model_config
@@ -339,21 +427,10 @@ class DynamicsPredictor(nn.Module):
         try:
             p_inputs = self._particle_inputs(state, attrs, action)
             rel_inputs = edge_inputs(state, attrs, p_instance, edges)
-            particle_encode = self.particle_encoder(p_inputs).reshape(B * N, Fd)
-            relation_encode = self.relation_encoder(rel_inputs).reshape(B * edges.capacity, Fd)
-            Wr, br = self.relation_propagator.linear.weight, self.relation_propagator.linear.bias
-            Wp, bp = self.particle_propagator.linear.weight, self.particle_propagator.linear.bias
-            A = F.linear(relation_encode, Wr[:, :Fd], br)            # pstep-invariant edge term
-            C0 = F.linear(particle_encode, Wp[:, :Fd], bp)           # pstep-invariant node term
-            W23 = torch.cat([Wr[:, Fd:2 * Fd], Wr[:, 2 * Fd:]], 0)   # [2F, F]: receiver | sender projections
-            Wp2_t = Wp[:, Fd:].t()
-            h = particle_encode
-            for _ in range(cfg['pstep']):
-                P = F.linear(h, W23)                                  # [B*N, 2F]
-                agg = _Aggregate.apply(A, P, edges)
-                h = torch.relu(torch.addmm(C0 + h, agg, Wp2_t))
-            h = h.view(B, N, Fd)
-            pred_motion = self.non_rigid_predictor(h[:, :n_p].contiguous())
+            if self.matmul == "3xtf32" and not torch.is_grad_enabled() and B * N >= 256 and Fd % 4 == 0:
+                pred_motion = self._forward_3xtf32(p_inputs, rel_inputs, edges, B, N, n_p)
+            else:
+                pred_motion = self._forward_ieee(p_inputs, rel_inputs, edges, B, N, n_p)
             pred_pos = state[:, -1, :n_p] + torch.clamp(pred_motion, max=self.motion_clamp, min=-self.motion_clamp)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev_tf32

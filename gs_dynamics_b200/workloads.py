@@ -59,8 +59,11 @@ def model_dims(cfg):
     return in_dim, rel_dim
 
 
-def make_state_dict(cfg, seed):
-    """Deterministic weights from numpy's PCG64 stream (stable across versions): U(-1/sqrt(fan_in), 1/sqrt(fan_in))."""
+def make_state_dict(cfg, seed, head_scale=1.0):
+    """Deterministic weights from numpy's PCG64 stream (stable across versions): U(-1/sqrt(fan_in), 1/sqrt(fan_in)).
+    head_scale multiplies the last layer of the motion head: an untrained head moves particles by ~0.1 m per step, which
+    empties the neighbour graph within a few rollout steps; the rollout benchmark uses 1e-3 (mm-scale motion, like a
+    trained model) so that all 50 steps run on a realistic 8-NN graph."""
     rng = np.random.default_rng(seed)
     in_dim, rel_dim = model_dims(cfg)
     nf = cfg['nf_effect']
@@ -80,6 +83,9 @@ def make_state_dict(cfg, seed):
         b = 1.0 / np.sqrt(i)
         sd[k + ".weight"] = torch.tensor(rng.uniform(-b, b, size=(o, i)), dtype=torch.float32)
         sd[k + ".bias"] = torch.tensor(rng.uniform(-b, b, size=(o,)), dtype=torch.float32)
+    if head_scale != 1.0:
+        sd["non_rigid_predictor.linear_2.weight"] *= head_scale
+        sd["non_rigid_predictor.linear_2.bias"] *= head_scale
     return sd
 
 

@@ -253,6 +253,13 @@ int gsd_gnn_aggregate_workspace_bytes(int32_t B, int32_t n_heavy, int32_t F, siz
 int gsd_gnn_aggregate(int32_t B, int32_t N, int32_t capacity, int32_t F, int32_t n_heavy, const int32_t *row_ptr,
                       const int32_t *senders, const float *A, const float *P, void *ws, float *agg, void *stream);
 
+/* Operands for the error-compensated TF32 GEMMs of the dense layers (nn.Linear in src/gnn/model.py:16-108 computed as one
+ * tensor-core GEMM over K = 3F).  t = relu ? max(x + add, 0) : x + add  (add may be NULL), hi = round_to_tf32(t), lo = t - hi.
+ * out [rows, 3F]: activation layout (weight_layout = 0) [lo | hi | hi], weight layout (1) [hi | lo | hi].
+ * full (nullable) [rows, F] receives t. */
+int gsd_tf32_pack(int64_t rows, int32_t F, int32_t relu, int32_t weight_layout, const float *x, const float *add, float *full,
+                  float *out, void *stream);
+
 /* farthest point sampling, one CTA per batch element. radius <= 0: dgl.geometry.farthest_point_sampler(pos, npoints,
  * start_idx) (squared distances, first maximum). radius > 0: fps_rad_idx_torch (data/utils.py:50-65): stops when the
  * largest euclidean distance to the picked set is <= radius; count[b] = number of picks, unused outputs = -1. */

@@ -64,6 +64,34 @@ def test_edges_vs_oracle_full_size(kind, n_obj, topk, adj, conn):
     assert rp[-1] == E and np.array_equal(np.diff(rp), np.bincount(recv.numpy(), minlength=n_obj + 1))
 
 
+def test_edges_dense_cloud_topk_is_the_binding_constraint():
+    """every particle within the radius of every other (bisection path of the adjacency kernel): bit-exact edge list."""
+    from gs_dynamics_b200 import gnn
+    gi = GO.make_graph_inputs(1500, 7, "sloth")
+    recv, send = GO.construct_edges(gi["state"][0, -1], 5.0, gi["state_mask"], gi["eef_mask"], 8, True)
+    e = gnn.construct_edges_index(gi["state"][0, -1].cuda(), 5.0, gi["state_mask"].cuda(), gi["eef_mask"].cuda(), topk=8, connect_all=True)
+    E = int(e.n_edges[0])
+    assert E == recv.numel()
+    assert np.array_equal(e.receivers[0, :E].cpu().numpy(), recv.numpy()) and np.array_equal(e.senders[0, :E].cpu().numpy(), send.numpy())
+
+
+def test_edges_many_equal_distances_fall_back_to_selection():
+    """600 coincident particles: all distances tie (the reference's torch.topk order is unspecified there), so only the
+    degree is checked: every object row keeps exactly topk neighbours."""
+    from gs_dynamics_b200 import gnn
+    N = 601
+    states = torch.zeros(N, 3)
+    states[-1] = 10.0
+    mask = torch.ones(N, dtype=torch.bool)
+    tool = torch.zeros(N, dtype=torch.bool)
+    tool[-1] = True
+    e = gnn.construct_edges_index(states.cuda(), 0.1, mask.cuda(), tool.cuda(), topk=6, connect_all=False)
+    deg = np.diff(e.row_ptr[0].cpu().numpy())
+    assert np.all(deg[:-1] == 6) and deg[-1] == 0
+    E = int(e.n_edges[0])
+    assert E == 600 * 6 and int(e.senders[0, :E].max()) < 600
+
+
 def test_edges_batch_masks_and_per_element_radius():
     from gs_dynamics_b200 import gnn
     g = torch.Generator().manual_seed(3)
