@@ -458,9 +458,6 @@ class GnnRollout:
         self.model = model
         dev = particle_pos.device
         n_his = model.model_config['n_his']
-        self.nobj = particle_pos.shape[0]
-        N = self.nobj + 1
-        self.states = torch.zeros((1, n_his, N, 3), device=dev)
         self.nobj = particle_pos.shape[-2]
         N = self.nobj + 1
         self.states = torch.zeros((1, n_his, N, 3), device=dev)
@@ -477,6 +474,14 @@ class GnnRollout:
         self.adj_thresh, self.topk, self.connect_all = adj_thresh, topk, connect_all
         self.eef_delta = torch.zeros(3, device=dev)
         self.use_graph, self.graph, self.pred = use_graph, None, None
+        self.gs_xyz = self.gs_quat = None
+
+    def attach_gaussians(self, xyz, quat):
+        """Skin these Gaussians (positions [n,3], rotations [n,4] wxyz) from the particles after every step
+        (interpolate_motions, dynamics_module.py:150-156); `gs_xyz` / `gs_quat` hold the current values.  Call before the first step."""
+        if self.graph is not None:
+            raise RuntimeError("attach_gaussians must be called before the first step")
+        self.gs_xyz, self.gs_quat = xyz.detach().clone().float().contiguous(), quat.detach().clone().float().contiguous()
 
     @torch.no_grad()
     def _step_impl(self):
@@ -486,6 +491,12 @@ class GnnRollout:
         edges = construct_edges_index(self.states[:, -1], self.adj_thresh, self.state_mask, self.eef_mask, topk=self.topk,
                                       connect_all=self.connect_all, n_tool=1)
         pred, _ = self.model(self.states, self.attrs, edges, None, self.p_instance, action=self.action)
+        if self.gs_xyz is not None:
+            from .skinning import interpolate_motions
+            bones = self.states[0, -1, :self.nobj]
+            x, q, _ = interpolate_motions(bones, pred[0] - bones, edges, self.gs_xyz, quat=self.gs_quat, return_weights=False)
+            self.gs_xyz.copy_(x)
+            self.gs_quat.copy_(q)
         nxt = torch.cat([pred[0], new_eef[None]], 0)
         self.states.copy_(torch.cat([self.states[:, 1:], nxt[None, None]], 1))
         return pred
@@ -499,13 +510,20 @@ class GnnRollout:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             keep = self.states.clone()
+            keep_gs = (self.gs_xyz.clone(), self.gs_quat.clone()) if self.gs_xyz is not None else None
+
+            def restore():
+                self.states.copy_(keep)
+                if keep_gs is not None:
+                    self.gs_xyz.copy_(keep_gs[0])
+                    self.gs_quat.copy_(keep_gs[1])
             with torch.cuda.stream(s):
                 self._step_impl()
             torch.cuda.current_stream().wait_stream(s)
-            self.states.copy_(keep)
+            restore()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.pred = self._step_impl()
-            self.states.copy_(keep)
+            restore()
         self.graph.replay()
         return self.pred

@@ -260,6 +260,24 @@ int gsd_gnn_aggregate(int32_t B, int32_t N, int32_t capacity, int32_t F, int32_t
 int gsd_tf32_pack(int64_t rows, int32_t F, int32_t relu, int32_t weight_layout, const float *x, const float *add, float *full,
                   float *out, void *stream);
 
+/* ---- linear-blend skinning of the Gaussians from the GNN particles -------------------------------
+ * Replaces interpolate_motions, /root/reference/src/render/utils.py:129-243, called once per rollout step from
+ * /root/reference/src/render/dynamics_module.py:150-156.
+ *
+ * gsd_skin_bone_transforms: per bone i, neighbours = columns j < n_bones of CSR row i (row_ptr [n_bones+1], cols); Procrustes
+ * rotation R_i of the neighbourhood (utils.py:150-204, incl. the rank-1 construction and the identity fallbacks).
+ * bone_tf [n_bones, 20] floats: R (9, row-major) | c = motion + b - R b (3) | normalised mat2quat(R) (4, wxyz) | b (3) | pad.
+ * rot_out (nullable) [n_bones, 9] receives R. */
+int gsd_skin_bone_transforms(int32_t n_bones, const float *bones, const float *motions, const int32_t *row_ptr,
+                             const int32_t *cols, float *bone_tf, float *rot_out, void *stream);
+
+/* gsd_skin_apply: per particle p, w_b = 1 / max(|xyz_p - b|, 1e-4) normalised over all bones (utils.py:206-213), or the rows
+ * of weights_in [n_particles, n_bones] used as they are; xyz_out = sum_b w_b (R_b xyz_p + c_b); when quat is given,
+ * quat_out = normalize(sum_b w_b q_b) (x) quat_p (utils.py:216-237).  weights_out (nullable) [n_particles, n_bones] receives the
+ * dense normalised weights the reference returns. */
+int gsd_skin_apply(int32_t n_particles, int32_t n_bones, const float *xyz, const float *quat, const float *bone_tf,
+                   const float *weights_in, float *xyz_out, float *quat_out, float *weights_out, void *stream);
+
 /* farthest point sampling, one CTA per batch element. radius <= 0: dgl.geometry.farthest_point_sampler(pos, npoints,
  * start_idx) (squared distances, first maximum). radius > 0: fps_rad_idx_torch (data/utils.py:50-65): stops when the
  * largest euclidean distance to the picked set is <= radius; count[b] = number of picks, unused outputs = -1. */

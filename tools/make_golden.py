@@ -105,3 +105,41 @@ for tag, (kind, n_obj, topk, adj, conn, seed) in dict(sloth=("sloth", 300, 6, 0.
 dst = os.path.join(ROOT, "tests", "golden", "gnn_golden.npz")
 np.savez_compressed(dst, **gout)
 print("wrote", dst, os.path.getsize(dst), "bytes")
+
+# ------------------------------------------------------------------------------------------------------------------
+# skinning_golden.npz — the reference's render/utils.py (interpolate_motions, mat2quat, quat2mat, relations_to_matrix)
+# run on the CPU (its `device` argument) on the seeded scenes of oracle.skinning_oracle.make_skinning_inputs, which
+# include an isolated bone (rank 0), a two-bone pair (rank 1) and a coplanar neighbourhood (rank 2).
+# ------------------------------------------------------------------------------------------------------------------
+import warnings
+warnings.filterwarnings("ignore")
+sys.path.insert(0, os.path.join(REF, "src"))
+from render.utils import interpolate_motions as ref_interp, mat2quat as ref_m2q, quat2mat as ref_q2m, relations_to_matrix as ref_r2m
+from oracle import skinning_oracle as SO
+
+sout = {}
+for tag, (nb, npart, seed) in {"a": (40, 300, 0), "b": (150, 1000, 1)}.items():
+    d = SO.make_skinning_inputs(nb, npart, seed)
+    x, q, w = ref_interp(d["bones"], d["motions"], d["relations"], d["xyz"], quat=d["quat"], device="cpu")
+    for k, v in d.items():
+        sout[f"{tag}_{k}"] = v.numpy()
+    sout[f"{tag}_xyz_out"], sout[f"{tag}_quat_out"], sout[f"{tag}_weights"] = x.numpy(), q.numpy(), w.numpy()
+    # caller-supplied weights variant (utils.py:207 skipped)
+    g = torch.Generator().manual_seed(seed)
+    wg = torch.rand(npart, nb, generator=g)
+    wg = wg / wg.sum(1, keepdim=True)
+    x2, q2, _ = ref_interp(d["bones"], d["motions"], d["relations"], d["xyz"], quat=d["quat"], weights=wg, device="cpu")
+    sout[f"{tag}_weights_given"], sout[f"{tag}_xyz_out_given"], sout[f"{tag}_quat_out_given"] = wg.numpy(), x2.numpy(), q2.numpy()
+g = torch.Generator().manual_seed(5)
+qq = torch.nn.functional.normalize(torch.randn(64, 4, generator=g), dim=-1)
+qq[0] = torch.tensor([0., 1., 0., 0.]); qq[1] = torch.tensor([0., 0., 1., 0.]); qq[2] = torch.tensor([0., 0., 0., 1.])  # trace = -1 branches
+Rm = ref_q2m(qq)
+sout["m2q_quat_in"], sout["m2q_rot"], sout["m2q_quat_out"] = qq.numpy(), Rm.numpy(), ref_m2q(Rm).numpy()
+# relations_to_matrix on a small one-hot pair
+recv = torch.tensor([0, 0, 1, 2, 2, 3]); send = torch.tensor([0, 1, 1, 2, 0, 3])
+Rr = torch.zeros(1, 6, 4); Rs = torch.zeros(1, 6, 4)
+Rr[0, torch.arange(6), recv] = 1; Rs[0, torch.arange(6), send] = 1
+sout["r2m_Rr"], sout["r2m_Rs"], sout["r2m_rel"] = Rr.numpy(), Rs.numpy(), ref_r2m(Rr, Rs).numpy()
+dst = os.path.join(ROOT, "tests", "golden", "skinning_golden.npz")
+np.savez_compressed(dst, **sout)
+print("wrote", dst, os.path.getsize(dst), "bytes")
