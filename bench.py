@@ -387,10 +387,48 @@ def run_gnn_ours(device, steps=50, warmup=5, n_obj=2000, seed=1):
         host_pred.copy_(pred, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     dt_e2e = time.time() - t0
-    return {"metric": "GNN steps/sec", "value": steps / dt, "unit": "steps/s", "ms_per_step": 1e3 * dt / steps, "steps": steps,
+    skin = time_skinning(device, model, ro)
+    return {"skinning": skin, "metric": "GNN steps/sec", "value": steps / dt, "unit": "steps/s", "ms_per_step": 1e3 * dt / steps, "steps": steps,
             "config": {"workload": "predict.py GNN rollout step (edge build + forward + history shift), sloth cfg nf=512, "
                                    "%d particles + 1 tool, 8-NN, connect_all, %d-step horizon, random-init weights with the motion head scaled 1e-3 so the cloud keeps its 8-NN graph" % (n_obj, steps)},
             "e2e": {"value": steps / dt_e2e, "unit": "steps/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": n_obj * 12}}
+
+
+def time_skinning(device, model, ro, n_gauss=100000, iters=20):
+    """The step after the GNN (interpolate_motions): 100k Gaussians skinned from the 2000 particles of the
+    rollout graph.  Device time per call, L2 flushed between calls; CPU: the oracle restatement on a 5k-Gaussian sample."""
+    from gs_dynamics_b200 import gnn, skinning as SK
+    g = torch.Generator().manual_seed(0)
+    xyz = (torch.rand(n_gauss, 3, generator=g) * torch.tensor([0.5, 0.5, 0.1])).to(device)
+    quat = torch.nn.functional.normalize(torch.randn(n_gauss, 4, generator=g), dim=-1).to(device)
+    bones = ro.states[0, -1, :ro.nobj].clone()
+    motions = torch.randn(ro.nobj, 3, generator=g).to(device) * 0.003
+    edges = gnn.construct_edges_index(ro.states[:, -1], ro.adj_thresh, ro.state_mask, ro.eef_mask, topk=ro.topk, connect_all=ro.connect_all, n_tool=1)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    ts = []
+    for i in range(iters + 3):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        SK.interpolate_motions(bones, motions, edges, xyz, quat=quat, return_weights=False)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1) * 1e3)
+    out = {"us_per_call": float(np.median(ts)), "gaussians": n_gauss, "bones": int(ro.nobj),
+           "pairs_per_s": n_gauss * ro.nobj / (float(np.median(ts)) * 1e-6)}
+    try:
+        from oracle import skinning_oracle as SO
+        Rr, Rs = edges.dense()
+        rel = SK.relations_to_matrix(Rr, Rs)[:ro.nobj, :ro.nobj].cpu()
+        sample = 5000
+        t0 = time.time()
+        SO.interpolate_motions(bones.cpu(), motions.cpu(), rel, xyz[:sample].cpu(), quat=quat[:sample].cpu(), dtype=torch.float32)
+        out["cpu_baseline"] = {"seconds": time.time() - t0, "kind": "port", "cores": torch.get_num_threads(),
+                               "sample": "%d Gaussians x %d bones (reference formulation: per-bone Python loop + dense weights)" % (sample, ro.nobj)}
+    except Exception as ex:  # the CPU leg is a reported baseline only
+        out["cpu_baseline"] = {"error": repr(ex)}
+    return out
 
 
 def run_gnn_cpu(budget_s=8.0, n_obj=2000, seed=1):
