@@ -105,7 +105,7 @@ EXPORTS = [
     "gsd_track_losses_workspace_bytes", "gsd_track_losses_fwd_bwd", "gsd_track_pack_edges", "gsd_adam_step", "gsd_track_update_radii",
     "gsd_track_normalize_rotations", "gsd_track_update", "gsd_photometric_target_stats",
     "gsd_gnn_edges_workspace_bytes", "gsd_gnn_build_edges", "gsd_gnn_edge_inputs", "gsd_gnn_aggregate_workspace_bytes",
-    "gsd_gnn_aggregate", "gsd_fps", "gsd_tf32_pack", "gsd_skin_bone_transforms", "gsd_skin_apply",
+    "gsd_gnn_aggregate", "gsd_fps", "gsd_tf32_pack", "gsd_skin_bone_transforms", "gsd_skin_apply", "gsd_knn",
 ]
 
 
@@ -146,6 +146,7 @@ def lib():
     l.gsd_tf32_pack.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_skin_bone_transforms.argtypes = [C.c_int32] + [C.c_void_p] * 7
     l.gsd_skin_apply.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 8
+    l.gsd_knn.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_fps.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = l
     return l

@@ -358,13 +358,22 @@ def initialize_optimizer(params, variables):
 # ----------------------------------------------------------------------------------------------------
 # per-timestep state
 # ----------------------------------------------------------------------------------------------------
-def knn(pts, num_knn):
-    """o3d_knn of the reference (helpers.py:97-115): squared distances + indices of the num_knn nearest OTHER points,
-    computed on the host in float64 (the reference uses Open3D's KD-tree on the CPU, once per episode)."""
-    from scipy.spatial import cKDTree
-    pts = np.ascontiguousarray(pts, np.float64)
-    d, i = cKDTree(pts).query(pts, k=num_knn + 1)
-    return (d[:, 1:] ** 2), i[:, 1:]
+def knn(pts, num_knn, device="cuda"):
+    """o3d_knn of the reference (helpers.py:97-115): squared distances + indices of the num_knn nearest OTHER points.
+    The reference walks an Open3D KD-tree on the CPU with one Python iteration per point; here gsd_knn does the exact search
+    on the device in float64.  numpy in -> (float64 [n,k], int64 [n,k]) numpy out; CUDA tensor in -> CUDA tensors out."""
+    is_np = not torch.is_tensor(pts)
+    p = torch.as_tensor(np.ascontiguousarray(pts, np.float32), device=device) if is_np else pts.detach().float().contiguous()
+    if not p.is_cuda:
+        raise ValueError("knn needs a CUDA device (no CPU path)")
+    n = p.shape[0]
+    sq = torch.empty((n, num_knn), dtype=torch.float64, device=p.device)
+    idx = torch.empty((n, num_knn), dtype=torch.int32, device=p.device)
+    with torch.cuda.device(p.device):
+        _lib.check(_lib.lib().gsd_knn(n, num_knn, p.data_ptr(), sq.data_ptr(), idx.data_ptr(), _stream()), "gsd_knn")
+    if is_np:
+        return sq.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
+    return sq, idx.long()
 
 
 def build_in_edges(neighbor_indices):
@@ -383,12 +392,11 @@ def initialize_post_first_timestep(params, variables, optimizer, num_knn=20):
     fg_index = torch.nonzero(is_fg).reshape(-1)
     bg_index = torch.nonzero(~is_fg).reshape(-1)
     init_fg_pts = params['means3D'][fg_index]
-    neighbor_sq_dist, neighbor_indices = knn(init_fg_pts.detach().cpu().numpy(), num_knn)
-    dev = params['means3D'].device
-    variables["neighbor_indices"] = torch.tensor(neighbor_indices, device=dev).long().contiguous()
+    neighbor_sq_dist, neighbor_indices = knn(init_fg_pts, num_knn)         # on the device, float64 like Open3D
+    variables["neighbor_indices"] = neighbor_indices.contiguous()
     variables["neighbor_indices_i32"] = variables["neighbor_indices"].to(torch.int32).contiguous()
-    variables["neighbor_weight"] = torch.tensor(np.exp(-2000 * neighbor_sq_dist), device=dev).float().contiguous()
-    variables["neighbor_dist"] = torch.tensor(np.sqrt(neighbor_sq_dist), device=dev).float().contiguous()
+    variables["neighbor_weight"] = torch.exp(-2000 * neighbor_sq_dist).float().contiguous()
+    variables["neighbor_dist"] = torch.sqrt(neighbor_sq_dist).float().contiguous()
     variables["in_ptr"], variables["in_edge"] = build_in_edges(variables["neighbor_indices_i32"])
     all_fg = bool(fg_index.numel() == is_fg.numel())
     variables["fg_index"] = None if all_fg else fg_index.to(torch.int32).contiguous()

@@ -260,6 +260,11 @@ int gsd_gnn_aggregate(int32_t B, int32_t N, int32_t capacity, int32_t F, int32_t
 int gsd_tf32_pack(int64_t rows, int32_t F, int32_t relu, int32_t weight_layout, const float *x, const float *add, float *full,
                   float *out, void *stream);
 
+/* Exact k nearest neighbours of every point among the OTHER points (self excluded), brute force in float64.
+ * Replaces o3d_knn, /root/reference/src/tracking/helpers.py:97-115 (Open3D KD-tree + Python loop over points on the CPU).
+ * pts float32 [n,3]; sq_dist float64 [n,k] squared distances ascending; idx int32 [n,k].  k <= 64, k <= n-1. */
+int gsd_knn(int32_t n, int32_t k, const float *pts, double *sq_dist, int32_t *idx, void *stream);
+
 /* ---- linear-blend skinning of the Gaussians from the GNN particles -------------------------------
  * Replaces interpolate_motions, /root/reference/src/render/utils.py:129-243, called once per rollout step from
  * /root/reference/src/render/dynamics_module.py:150-156.

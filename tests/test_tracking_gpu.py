@@ -355,3 +355,27 @@ def test_t0_densification_surgery_and_short_episode():
     l1 = float(TR.get_loss(params, datasets[0][0], variables, True)[0])
     assert np.isfinite(l1) and l1 < l0
     assert "edge_records" in variables and variables['prior_losses'].shape == (6,)
+
+
+@pytest.mark.parametrize("n,k", [(50000, 20), (3000, 3), (65, 64), (2, 1)])
+def test_device_knn_matches_kdtree(n, k):
+    """gsd_knn (exact, float64) vs scipy's KD-tree in float64 on the same float32 points: squared distances to 1e-12
+    relative, indices identical wherever the distance is not tied with the next one."""
+    from scipy.spatial import cKDTree
+    from gs_dynamics_b200 import tracking as TR
+    rng = np.random.default_rng(n)
+    pts = rng.uniform([-0.25, -0.25, -0.1], [0.25, 0.25, 0.0], size=(n, 3)).astype(np.float32)
+    sq, idx = TR.knn(pts, k)
+    d, ref = cKDTree(pts.astype(np.float64)).query(pts.astype(np.float64), k=k + 1)
+    ref_sq, ref_idx = d[:, 1:].reshape(n, k) ** 2, ref[:, 1:].reshape(n, k)
+    assert sq.dtype == np.float64 and idx.dtype == np.int64 and sq.shape == (n, k)
+    assert np.allclose(sq, ref_sq, rtol=1e-12, atol=1e-18)
+    untied = np.ones((n, k), bool)
+    if k > 1:
+        gap = np.diff(ref_sq, axis=1) > 1e-15
+        untied[:, 1:] &= gap
+        untied[:, :-1] &= gap
+    assert np.array_equal(idx[untied], ref_idx[untied])
+    assert not np.any(idx == np.arange(n)[:, None])          # self excluded
+    t_sq, t_idx = TR.knn(torch.tensor(pts).cuda(), k)         # tensor in -> tensors out
+    assert t_sq.is_cuda and np.array_equal(t_idx.cpu().numpy(), idx)

@@ -143,3 +143,44 @@ sout["r2m_Rr"], sout["r2m_Rs"], sout["r2m_rel"] = Rr.numpy(), Rs.numpy(), ref_r2
 dst = os.path.join(ROOT, "tests", "golden", "skinning_golden.npz")
 np.savez_compressed(dst, **sout)
 print("wrote", dst, os.path.getsize(dst), "bytes")
+
+# ------------------------------------------------------------------------------------------------------------------
+# formats_golden.npz — on-disk formats: the reference's .splat writer (real_world/gs/convert.py), save_params / params2cpu
+# (tracking/helpers.py:122-140) and the path mapping of train_utils.py:10-29, run as they are on seeded inputs.
+# ------------------------------------------------------------------------------------------------------------------
+import importlib.util, tempfile
+spec = importlib.util.spec_from_file_location("ref_convert", os.path.join(REF, "src", "real_world", "gs", "convert.py"))
+ref_convert = importlib.util.module_from_spec(spec); spec.loader.exec_module(ref_convert)
+rng = np.random.default_rng(7)
+n = 64
+fin = dict(pts=rng.normal(size=(n, 3)), colors=rng.uniform(-0.1, 1.1, size=(n, 3)), scales=rng.uniform(0.001, 0.02, size=(n, 3)),
+           quats=rng.normal(size=(n, 4)), opacities=rng.uniform(0, 1, size=(n, 1)))
+fout = {f"splat_{k}": v for k, v in fin.items()}
+with tempfile.TemporaryDirectory() as td:
+    ref_convert.save_to_splat(fin["pts"], fin["colors"], fin["scales"], fin["quats"], fin["opacities"], os.path.join(td, "a.splat"))
+    fout["splat_bytes"] = np.frombuffer(open(os.path.join(td, "a.splat"), "rb").read(), dtype=np.uint8)
+    # save_params: frame 0 holds every key, later frames only means3D / rgb_colors / unnorm_rotations
+    frames = []
+    for t in range(3):
+        p = {k: torch.tensor(rng.normal(size=s)).float() for k, s in dict(means3D=(n, 3), rgb_colors=(n, 3), seg_colors=(n, 3), unnorm_rotations=(n, 4),
+                                                                           logit_opacities=(n, 1), log_scales=(n, 3), cam_m=(50, 3), cam_c=(50, 3)).items()}
+        for k, v in p.items():
+            fout[f"params_in_{t}_{k}"] = v.numpy()
+        frames.append(ref_h.params2cpu(p, t == 0))
+    cwd = os.getcwd(); os.chdir(td)
+    try:
+        ref_h.save_params(frames, "seqA", "expA")
+        saved = dict(np.load(os.path.join(td, "output", "expA", "seqA", "params.npz")))
+    finally:
+        os.chdir(cwd)
+    for k, v in saved.items():
+        fout[f"params_saved_{k}"] = v
+sys.path.insert(0, os.path.join(REF, "src", "tracking"))
+import train_utils as ref_tu   # /root/reference/src/tracking/train_utils.py (stubs above satisfy its imports)
+paths = ["camera_1/foreground/foreground_000012.png", "camera_3/color/color_7.png", "a/b/camera_0/foreground/foreground_000100.png"]
+fout["paths_in"] = np.array(paths)
+fout["paths_seg"] = np.array([ref_tu.map_to_segmentation_path(p) for p in paths])
+fout["paths_depth"] = np.array([ref_tu.map_to_depth_path(p) for p in ["camera_1/color_12.png", "x/y/im_000003.png"]])
+dst = os.path.join(ROOT, "tests", "golden", "formats_golden.npz")
+np.savez_compressed(dst, **fout)
+print("wrote", dst, os.path.getsize(dst), "bytes")
