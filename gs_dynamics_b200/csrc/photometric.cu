@@ -7,24 +7,23 @@
 // Channels are grouped in sets of 3 (RGB render, seg render) with their own loss weight so that both losses of an
 // iteration are one launch.
 //
-// Both kernels are separable 11-tap stencils over 32x32 tiles staged in shared memory (halo 5, zero padding like
-// conv2d(padding=5)); each thread produces 4 consecutive outputs per pass from a 14-value register window (8x fewer
-// shared-memory reads than one output per thread).  HBM traffic per call: read x,y + write 3 partial maps (kernel 1),
-// read 3 maps + x,y, write the gradient (kernel 2) = 40 B/pixel/channel.  Block partial sums are written to a buffer and
-// reduced in fixed order (deterministic).
+// Both kernels are separable 11-tap stencils written as ROW-STREAMING warps: a warp owns a strip of 32*NCOL output columns
+// and a segment of `seg_rows` output rows of one channel and marches down the rows.  Rows are fetched PH_D-1 rows ahead by
+// asynchronous 4-byte copies (LDGSTS, zero-filled outside the image like conv2d(padding=5)) into a per-warp shared-memory
+// ring (one commit group per row, one __syncwarp per row, no block barrier), filtered horizontally from a register window and
+// scattered into a 10-slot ring of vertical accumulators held in registers (the ring shift is folded into the
+// destination registers of the update FMAs, so the row loop is compact: no unrolling, no moves).  There is no vertical halo recompute inside a segment (10 rows at its ends only), the
+// work unit is one warp (fine-grained tail), and global latency is hidden by the depth of the ring instead of by
+// co-resident blocks.  HBM traffic per call: read x,y + write 3 partial maps (kernel 1), read 3 maps + x,y, write the
+// gradient (kernel 2) = 40 B/pixel/channel.  Per-warp partial sums are written to a buffer and reduced in fixed order.
 #include "common.cuh"
 
-#define PH_T 32          // tile edge
 #define PH_R 5           // window radius
-#define PH_E (PH_T + 2 * PH_R)
 #define PH_MAXC 6
+#define PH_WARPS 1       // warps per CTA (adjacent strips of one channel / segment)
+#define PH_MIN_SEG 8     // smallest segment the launcher picks (bounds the partial-sum buffer)
 
 struct PhWin { float g[11]; };
-struct PhAffine { float scale[PH_MAXC], shift[PH_MAXC]; int on; };
-
-__device__ __forceinline__ float ph_load(const float *img, int W, int H, int x, int y) {
-    return (x >= 0 && x < W && y >= 0 && y < H) ? img[(size_t)y * W + x] : 0.f;
-}
 
 // affine parameters may live on the device (cam_m / cam_c rows): scale = exp(m[c]), shift = c[c]
 __device__ __forceinline__ void ph_affine(const float *log_scale, const float *shift, int c, float &s, float &b) {
@@ -32,123 +31,239 @@ __device__ __forceinline__ void ph_affine(const float *log_scale, const float *s
     b = shift ? shift[c % 3] : 0.0f;
 }
 
-// kernel 1: per pixel SSIM partials dS/dmu1, dS/ds11, dS/ds12 + block sums of |x-y| and SSIM.
+template <int NCOL> struct PhGeom {
+    static constexpr int OUT = 32 * NCOL;            // output columns per strip
+    static constexpr int LC = OUT + 2 * PH_R;        // loaded columns
+    static constexpr int NL = (LC + 31) / 32;        // loads per lane per row
+    static constexpr int PITCH = 32 * NL + 4;        // staged line (floats)
+    static constexpr int WN = 10 + NCOL;             // register window
+};
+
+#define PH_D 4           // depth of the per-warp row ring (rows in flight: PH_D - 1)
+
+// 4-byte asynchronous global -> shared copy, zero-filled when !pred (LDGSTS; the address is not dereferenced then)
+__device__ __forceinline__ void ph_cp4(unsigned dst_saddr, const float *src, bool pred) {
+    const int sz = pred ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_saddr), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void ph_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void ph_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Per-warp streaming state shared by both kernels: NA staged input arrays (LC columns from column xl, rows [rs, re)) and NB
+// per-output arrays (the lane's own NCOL pixels of the output row completed PH_R rows later) ride in one commit group per
+// streamed row.  Pointers advance by W per row; column predicates are per-lane constants.
+template <int NCOL, int NA, int NB>
+struct PhStream {
+    using Gm = PhGeom<NCOL>;
+    static constexpr int SLOT = NA * Gm::PITCH + NB * 32 * NCOL;   // floats per ring slot
+    const float *in[NA];      // next row to issue, at column xl + lane
+    const float *out[NB ? NB : 1];  // output row of the next row to issue, at column x0 + NCOL*lane
+    const float *safe;        // valid address for zero-filled (not dereferenced) copies
+    unsigned base;            // shared address of the warp's ring
+    int row, W, H, r0;
+    unsigned colmask;         // bit i: column xl + i*32 + lane inside the image and the strip; bit 8+j: output column j inside
+    __device__ __forceinline__ void init(float *ring, const float *const *src, const float *const *osrc, int W_, int H_, int rs,
+                                         int r0_, int xl, int x0, int lane) {
+        base = (unsigned)__cvta_generic_to_shared(ring);
+        safe = src[0];
+        row = rs; W = W_; H = H_; r0 = r0_;
+        colmask = 0;
+#pragma unroll
+        for (int i = 0; i < Gm::NL; ++i) {
+            const int j = i * 32 + lane, gx = xl + j;
+            if (j < Gm::LC && gx >= 0 && gx < W) colmask |= 1u << i;
+        }
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j)
+            if (x0 + NCOL * lane + j < W) colmask |= 1u << (8 + j);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) in[a] = src[a] + (ptrdiff_t)rs * W + xl + lane;
+#pragma unroll
+        for (int a = 0; a < NB; ++a) out[a] = osrc[a] + (ptrdiff_t)(rs - PH_R) * W + x0 + NCOL * lane;
+    }
+    __device__ __forceinline__ void issue(int lane) {
+        const unsigned slot = base + (unsigned)(row & (PH_D - 1)) * (SLOT * 4u) + lane * 4u;
+        const bool rin = (unsigned)row < (unsigned)H;
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int i = 0; i < Gm::NL; ++i) {
+                const bool ok = rin && ((colmask >> i) & 1u);
+                ph_cp4(slot + (a * Gm::PITCH + i * 32) * 4u, ok ? in[a] + i * 32 : safe, ok);
+            }
+        const bool oin = row - PH_R >= r0 && row - PH_R < H;
+#pragma unroll
+        for (int a = 0; a < NB; ++a)
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+                const bool ok = oin && ((colmask >> (8 + j)) & 1u);
+                ph_cp4(slot + (NA * Gm::PITCH + a * 32 * NCOL + (NCOL - 1) * lane + j) * 4u, ok ? out[a] + j : safe, ok);
+            }
+        ph_commit();
+#pragma unroll
+        for (int a = 0; a < NA; ++a) in[a] += W;
+#pragma unroll
+        for (int a = 0; a < NB; ++a) out[a] += W;
+        ++row;
+    }
+};
+
+template <int NCOL>
+__device__ __forceinline__ void ph_window(float (&w)[PhGeom<NCOL>::WN], const float *line, int lane) {
+    if (NCOL == 1) {
+#pragma unroll
+        for (int k = 0; k < 11; ++k) w[k] = line[lane + k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < PhGeom<NCOL>::WN / 2; ++k) {
+            const float2 t = *reinterpret_cast<const float2 *>(line + 2 * lane + 2 * k);
+            w[2 * k] = t.x; w[2 * k + 1] = t.y;
+        }
+    }
+}
+
+// kernel 1: per pixel SSIM partials dS/dmu1, dS/ds11, dS/ds12 + per-warp sums of |x-y| and SSIM.
 // MODE 0: everything from x and y.  MODE 1: the target's window statistics (mu2 = conv(y), s22 = conv(y*y)) are read from
 // maps precomputed once per target image (they do not change during an episode frame).  MODE 2: write those maps.
-template <int MODE>
-__global__ void __launch_bounds__(256, 4)
-gsd_ssim_stats_kernel(int C, int H, int W, PhWin win, const float *__restrict__ X, const float *__restrict__ Y,
-                      const float *__restrict__ log_scale, const float *__restrict__ shift, int affine_channels,
-                      float *__restrict__ y_mu, float *__restrict__ y_s22,
-                      float *__restrict__ dmu, float *__restrict__ ds11, float *__restrict__ ds12,
-                      float *__restrict__ block_sums /* [nblocks][2] */) {
+template <int MODE, int NCOL>
+__global__ void __launch_bounds__(32 * PH_WARPS)
+gsd_ssim_stats_kernel(int C, int H, int W, int seg_rows, int n_seg, int n_strip, PhWin win, const float *__restrict__ X,
+                      const float *__restrict__ Y, const float *__restrict__ log_scale, const float *__restrict__ shift,
+                      int affine_channels, float *__restrict__ y_mu, float *__restrict__ y_s22, float *__restrict__ dmu,
+                      float *__restrict__ ds11, float *__restrict__ ds12, float *__restrict__ unit_sums /* [units][2] */) {
+    using Gm = PhGeom<NCOL>;
     constexpr int NQ = (MODE == 0) ? 5 : (MODE == 1 ? 3 : 2); // x, xx, xy (, y, yy)   |   MODE 2: y, yy
-    __shared__ float sx[PH_E][PH_E + 1], sy[PH_E][PH_E + 1];
-    __shared__ float h[NQ][PH_E][PH_T + 1];
-    __shared__ float red[2][8];
-    const int c = blockIdx.z;
-    const int x0 = blockIdx.x * PH_T, y0 = blockIdx.y * PH_T;
-    const float *Xc = X + (size_t)c * H * W, *Yc = Y + (size_t)c * H * W;
-    const int t = threadIdx.x;
+    constexpr int NA = (MODE == 2) ? 1 : 2;                    // staged arrays: (x,) y
+    constexpr int NB = (MODE == 1) ? 2 : 0;                    // per-output arrays: y_mu, y_s22 (MODE 1 only)
+    using St = PhStream<NCOL, NA, NB>;
+    __shared__ __align__(16) float ring_s[PH_WARPS][PH_D][St::SLOT];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int unit = blockIdx.x * PH_WARPS + wid;
+    if (unit >= C * n_seg * n_strip) return;
+    const int sx = unit % n_strip, sy = (unit / n_strip) % n_seg, c = unit / (n_strip * n_seg);
+    const int x0 = sx * Gm::OUT, xl = x0 - PH_R;
+    const int r0 = sy * seg_rows, r1 = min(r0 + seg_rows, H);
+    const size_t coff = (size_t)c * H * W;
+    const float *src[NA];
+    src[0] = (MODE == 2 ? Y : X) + coff;
+    src[NA - 1] = Y + coff;
+    const float *osrc[2] = {MODE == 1 ? y_mu + coff : nullptr, MODE == 1 ? y_s22 + coff : nullptr};
     float as = 1.f, ab = 0.f;
     if (MODE != 2 && c < affine_channels) ph_affine(log_scale, shift, c, as, ab);
-    for (int i = t; i < PH_E * PH_E; i += 256) {
-        int ly = i / PH_E, lx = i % PH_E;
-        const int gx = x0 + lx - PH_R, gy = y0 + ly - PH_R;
-        const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
-        if (MODE != 2) sx[ly][lx] = in ? as * Xc[(size_t)gy * W + gx] + ab : 0.f;
-        sy[ly][lx] = in ? Yc[(size_t)gy * W + gx] : 0.f;
-    }
-    __syncthreads();
-    // horizontal pass: unit = (row, segment of 4 outputs); consecutive lanes take consecutive rows (pitch 43: no conflicts)
-    for (int u = t; u < PH_E * (PH_T / 4); u += 256) {
-        const int ly = u % PH_E, seg = u / PH_E;
-        float q[NQ][14];
+    const bool affine = (as != 1.f) || (ab != 0.f);
+
+    // vertical ring: acc[.][.][i] = partial sum of output row (current input row - 4 + i); the shift is folded into the
+    // destination register of the update FMAs, so the row loop needs no unrolling and no moves
+    float acc[NQ][NCOL][10];
 #pragma unroll
-        for (int k = 0; k < 14; ++k) {
-            const float yy = sy[ly][seg * 4 + k];
-            if (MODE == 2) {
-                q[0][k] = yy; q[1][k] = yy * yy;
-            } else {
-                const float xx = sx[ly][seg * 4 + k];
-                q[0][k] = xx; q[1][k] = xx * xx; q[2][k] = xx * yy;
-                if (MODE == 0) { q[3 % NQ][k] = yy; q[4 % NQ][k] = yy * yy; }
-            }
-        }
+    for (int q = 0; q < NQ; ++q)
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
+        for (int j = 0; j < NCOL; ++j)
 #pragma unroll
-            for (int n = 0; n < NQ; ++n) {
-                float a = 0.f;
-#pragma unroll
-                for (int k = 0; k < 11; ++k) a += win.g[k] * q[n][o + k];
-                h[n][ly][seg * 4 + o] = a;
-            }
-        }
-    }
-    __syncthreads();
-    // vertical pass: thread = (column, segment of 4 rows)
+            for (int s = 0; s < 10; ++s) acc[q][j][s] = 0.f;
     float l1 = 0.f, ss = 0.f;
-    {
-        const int lx = t % PH_T, seg = t / PH_T; // 32 columns x 8 segments
-        float v[NQ][14];
+    float (*ring)[St::SLOT] = ring_s[wid];
+    const int rs = r0 - PH_R, re = r1 + PH_R;  // rows streamed: [rs, re)
+    St stm;
+    stm.init(&ring[0][0], src, osrc, W, H, rs, r0, xl, x0, lane);
+
+    // a landed row: affine in place on the elements this lane copied (zero padding stays zero), L1 term on owned pixels
+    auto finish_row = [&](int row) {
+        if (MODE == 2) return;
+        const bool own_row = row >= r0 && row < r1;
+        if (!own_row && !affine) return;
+        float *sl = ring[row & (PH_D - 1)];
+        const bool rin = (unsigned)row < (unsigned)H;
 #pragma unroll
-        for (int n = 0; n < NQ; ++n)
-#pragma unroll
-            for (int k = 0; k < 14; ++k) v[n][k] = h[n][seg * 4 + k][lx];
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            const int ly = seg * 4 + o;
-            const int gx = x0 + lx, gy = y0 + ly;
-            float r[NQ];
-#pragma unroll
-            for (int n = 0; n < NQ; ++n) {
-                float a = 0.f;
-#pragma unroll
-                for (int k = 0; k < 11; ++k) a += win.g[k] * v[n][o + k];
-                r[n] = a;
+        for (int i = 0; i < Gm::NL; ++i) {
+            const int j = i * 32 + lane;
+            if (rin && ((stm.colmask >> i) & 1u)) {
+                float xv = sl[j];
+                if (affine) { xv = as * xv + ab; sl[j] = xv; }
+                if (own_row && j >= PH_R && j < PH_R + Gm::OUT) l1 += fabsf(xv - sl[Gm::PITCH + j]);
             }
-            if (gx < W && gy < H) {
-                const size_t pid = (size_t)c * H * W + (size_t)gy * W + gx;
+        }
+    };
+
+#pragma unroll
+    for (int k = 0; k < PH_D - 1; ++k) stm.issue(lane);
+    ph_wait<PH_D - 2>();
+    finish_row(rs);
+#pragma unroll 1
+    for (int rr = rs; rr < re; ++rr) {
+        __syncwarp();                       // row rr (finished last iteration) visible; slot of row rr-1 free
+        stm.issue(lane);                    // row rr + PH_D - 1
+        const float *sl = ring[rr & (PH_D - 1)];
+        // rows outside the image are staged as zeros: the same arithmetic handles them
+        float wx[Gm::WN], wy[Gm::WN];
+        if (MODE != 2) ph_window<NCOL>(wx, sl, lane);
+        ph_window<NCOL>(wy, sl + (NA - 1) * Gm::PITCH, lane);
+        float done[NQ][NCOL];
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            float hq[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) hq[q] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) {
+                const float g = win.g[k], yy = wy[j + k];
                 if (MODE == 2) {
-                    y_mu[pid] = r[0];
-                    y_s22[pid] = r[1];
+                    hq[0] += g * yy; hq[1] += g * (yy * yy);
                 } else {
-                    const float mu1 = r[0], s11 = r[1], s12 = r[2];
-                    const float mu2 = (MODE == 0) ? r[3 % NQ] : y_mu[pid];
-                    const float s22 = (MODE == 0) ? r[4 % NQ] : y_s22[pid];
-                    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-                    const float mu1sq = mu1 * mu1, mu2sq = mu2 * mu2, mu12 = mu1 * mu2;
-                    const float sig1 = s11 - mu1sq, sig2 = s22 - mu2sq, sig12 = s12 - mu12;
-                    const float A1 = 2.f * mu12 + C1, A2 = 2.f * sig12 + C2;
-                    const float B1 = mu1sq + mu2sq + C1, B2 = sig1 + sig2 + C2;
-                    const float inv = 1.f / (B1 * B2);
-                    const float S = A1 * A2 * inv;
-                    const float dS_dA1 = A2 * inv, dS_dA2 = A1 * inv, dS_dB1 = -S / B1, dS_dB2 = -S / B2;
-                    dmu[pid] = dS_dA1 * 2.f * mu2 + dS_dA2 * (-2.f * mu2) + dS_dB1 * 2.f * mu1 + dS_dB2 * (-2.f * mu1);
-                    ds11[pid] = dS_dB2;
-                    ds12[pid] = 2.f * dS_dA2;
-                    ss += S;
-                    l1 += fabsf(sx[ly + PH_R][lx + PH_R] - sy[ly + PH_R][lx + PH_R]);
+                    const float xx = wx[j + k];
+                    hq[0] += g * xx; hq[1] += g * (xx * xx); hq[2] += g * (xx * yy);
+                    if (MODE == 0) { hq[3 % NQ] += g * yy; hq[4 % NQ] += g * (yy * yy); }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                done[q][j] = acc[q][j][0] + win.g[0] * hq[q];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) acc[q][j][i] = acc[q][j][i + 1] + win.g[i + 1] * hq[q];
+                acc[q][j][9] = win.g[10] * hq[q];
+            }
+        }
+        const int o = rr - PH_R;            // output row completed by this input row
+        if (o >= r0) {
+            float *gp0 = (MODE == 2 ? y_mu : dmu) + coff + (size_t)o * W + x0 + NCOL * lane;
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+                if ((stm.colmask >> (8 + j)) & 1u) {
+                    if (MODE == 2) {
+                        gp0[j] = done[0][j];
+                        (y_s22 + (gp0 - y_mu))[j] = done[1][j];
+                    } else {
+                        const float mu1 = done[0][j], s11 = done[1][j], s12 = done[2][j];
+                        const float mu2 = (MODE == 0) ? done[3 % NQ][j] : sl[NA * Gm::PITCH + NCOL * lane + j];
+                        const float s22v = (MODE == 0) ? done[4 % NQ][j] : sl[NA * Gm::PITCH + 32 * NCOL + NCOL * lane + j];
+                        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+                        const float mu1sq = mu1 * mu1, mu2sq = mu2 * mu2, mu12 = mu1 * mu2;
+                        const float sig1 = s11 - mu1sq, sig2 = s22v - mu2sq, sig12 = s12 - mu12;
+                        const float A1 = 2.f * mu12 + C1, A2 = 2.f * sig12 + C2;
+                        const float B1 = mu1sq + mu2sq + C1, B2 = sig1 + sig2 + C2;   // both >= C1, C2 > 0
+                        const float i1 = __fdividef(1.f, B1), i2 = __fdividef(1.f, B2);
+                        const float inv = i1 * i2;
+                        const float S = A1 * A2 * inv;
+                        const float dS_dA1 = A2 * inv, dS_dA2 = A1 * inv, dS_dB1 = -S * i1, dS_dB2 = -S * i2;
+                        gp0[j] = 2.f * (mu2 * (dS_dA1 - dS_dA2) + mu1 * (dS_dB1 - dS_dB2));
+                        (ds11 + (gp0 - dmu))[j] = dS_dB2;
+                        (ds12 + (gp0 - dmu))[j] = 2.f * dS_dA2;
+                        ss += S;
+                    }
                 }
             }
         }
+        ph_wait<PH_D - 2>();                // row rr + 1 has landed (this lane's copies)
+        finish_row(rr + 1);
     }
+    ph_wait<0>();
     if (MODE != 2) {
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        l1 += __shfl_xor_sync(0xffffffffu, l1, o);
-        ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    }
-    if ((t & 31) == 0) { red[0][t >> 5] = l1; red[1][t >> 5] = ss; }
-    __syncthreads();
-    if (t == 0) {
-        float a = 0.f, b = 0.f;
-        for (int k = 0; k < 8; ++k) { a += red[0][k]; b += red[1][k]; }
-        size_t bid = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-        block_sums[2 * bid] = a;
-        block_sums[2 * bid + 1] = b;
-    }
+        for (int o = 16; o >= 1; o >>= 1) {
+            l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        }
+        if (lane == 0) { unit_sums[2 * (size_t)unit] = l1; unit_sums[2 * (size_t)unit + 1] = ss; }
     }
 }
 
@@ -182,69 +297,80 @@ __global__ void gsd_ssim_finish_kernel(int n_sets, int blocks_per_set, const flo
 }
 
 // kernel 2: d loss / d rendered = gscale * set_weight * scale_c * ( w_l1*sign(x-y)/N - w_ssim/N * (conv(dmu) + 2x*conv(ds11) + y*conv(ds12)) )
-__global__ void __launch_bounds__(256, 4)
-gsd_ssim_grad_kernel(int C, int H, int W, PhWin win, const float *__restrict__ X, const float *__restrict__ Y,
-                     const float *__restrict__ log_scale, const float *__restrict__ shift, int affine_channels,
-                     const float *__restrict__ dmu, const float *__restrict__ ds11, const float *__restrict__ ds12,
-                     const float *__restrict__ gscale_ptr, float sw0, float sw1, float w_l1, float w_ssim, float inv_n,
-                     float *__restrict__ grad) {
-    __shared__ float sm[3][PH_E][PH_E + 1];
-    __shared__ float h[3][PH_E][PH_T + 1];
-    const int c = blockIdx.z;
-    const int x0 = blockIdx.x * PH_T, y0 = blockIdx.y * PH_T;
+// (same row-streaming structure; three staged maps, x and y of the completed output row ride in the same commit group)
+template <int NCOL>
+__global__ void __launch_bounds__(32 * PH_WARPS)
+gsd_ssim_grad_kernel(int C, int H, int W, int seg_rows, int n_seg, int n_strip, PhWin win, const float *__restrict__ X,
+                     const float *__restrict__ Y, const float *__restrict__ log_scale, const float *__restrict__ shift,
+                     int affine_channels, const float *__restrict__ dmu, const float *__restrict__ ds11,
+                     const float *__restrict__ ds12, const float *__restrict__ gscale_ptr, float sw0, float sw1, float w_l1,
+                     float w_ssim, float inv_n, float *__restrict__ grad) {
+    using Gm = PhGeom<NCOL>;
+    using St = PhStream<NCOL, 3, 2>;
+    __shared__ __align__(16) float ring_s[PH_WARPS][PH_D][St::SLOT];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int unit = blockIdx.x * PH_WARPS + wid;
+    if (unit >= C * n_seg * n_strip) return;
+    const int sx = unit % n_strip, sy = (unit / n_strip) % n_seg, c = unit / (n_strip * n_seg);
+    const int x0 = sx * Gm::OUT, xl = x0 - PH_R;
+    const int r0 = sy * seg_rows, r1 = min(r0 + seg_rows, H);
     const size_t coff = (size_t)c * H * W;
-    const int t = threadIdx.x;
-    for (int i = t; i < PH_E * PH_E; i += 256) {
-        int ly = i / PH_E, lx = i % PH_E;
-        int gx = x0 + lx - PH_R, gy = y0 + ly - PH_R;
-        sm[0][ly][lx] = ph_load(dmu + coff, W, H, gx, gy);
-        sm[1][ly][lx] = ph_load(ds11 + coff, W, H, gx, gy);
-        sm[2][ly][lx] = ph_load(ds12 + coff, W, H, gx, gy);
-    }
-    __syncthreads();
-    for (int u = t; u < PH_E * (PH_T / 4); u += 256) {
-        const int ly = u % PH_E, seg = u / PH_E;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            float v[14];
-#pragma unroll
-            for (int k = 0; k < 14; ++k) v[k] = sm[q][ly][seg * 4 + k];
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                float a = 0.f;
-#pragma unroll
-                for (int k = 0; k < 11; ++k) a += win.g[k] * v[o + k];
-                h[q][ly][seg * 4 + o] = a;
-            }
-        }
-    }
-    __syncthreads();
+    const float *src[3] = {dmu + coff, ds11 + coff, ds12 + coff};
+    const float *osrc[2] = {X + coff, Y + coff};
     float as = 1.f, ab = 0.f;
     if (c < affine_channels) ph_affine(log_scale, shift, c, as, ab);
-    const float gs = (gscale_ptr ? *gscale_ptr : 1.0f) * (c < 3 ? sw0 : sw1) * as;
-    const int lx = t % PH_T, seg = t / PH_T;
-    float v[3][14];
+    const float gs = (gscale_ptr ? *gscale_ptr : 1.0f) * (c < 3 ? sw0 : sw1) * as * inv_n;
+
+    float acc[3][NCOL][10];
 #pragma unroll
     for (int q = 0; q < 3; ++q)
 #pragma unroll
-        for (int k = 0; k < 14; ++k) v[q][k] = h[q][seg * 4 + k][lx];
+        for (int j = 0; j < NCOL; ++j)
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-        const int ly = seg * 4 + o;
-        const int gx = x0 + lx, gy = y0 + ly;
-        if (gx >= W || gy >= H) continue;
-        float a = 0.f, b = 0.f, d = 0.f;
+            for (int s = 0; s < 10; ++s) acc[q][j][s] = 0.f;
+    float (*ring)[St::SLOT] = ring_s[wid];
+    const int rs = r0 - PH_R, re = r1 + PH_R;
+    St stm;
+    stm.init(&ring[0][0], src, osrc, W, H, rs, r0, xl, x0, lane);
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            const float w = win.g[k];
-            a += w * v[0][o + k]; b += w * v[1][o + k]; d += w * v[2][o + k];
+    for (int k = 0; k < PH_D - 1; ++k) stm.issue(lane);
+#pragma unroll 1
+    for (int rr = rs; rr < re; ++rr) {
+        ph_wait<PH_D - 2>();                // row rr has landed (this lane's copies) ...
+        __syncwarp();                       // ... and everybody's; slot of row rr-1 free
+        stm.issue(lane);
+        const float *sl = ring[rr & (PH_D - 1)];
+        float done[3][NCOL];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            float w[Gm::WN];
+            ph_window<NCOL>(w, sl + q * Gm::PITCH, lane);
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+                float h = 0.f;
+#pragma unroll
+                for (int k = 0; k < 11; ++k) h += win.g[k] * w[j + k];
+                done[q][j] = acc[q][j][0] + win.g[0] * h;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) acc[q][j][i] = acc[q][j][i + 1] + win.g[i + 1] * h;
+                acc[q][j][9] = win.g[10] * h;
+            }
         }
-        const size_t pid = coff + (size_t)gy * W + gx;
-        const float xv = as * X[pid] + ab, yv = Y[pid];
-        const float df = xv - yv;
-        const float sgn = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
-        grad[pid] = gs * inv_n * (w_l1 * sgn - w_ssim * (a + 2.f * xv * b + yv * d));
+        const int o = rr - PH_R;
+        if (o >= r0) {
+            float *gp = grad + coff + (size_t)o * W + x0 + NCOL * lane;
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+                if ((stm.colmask >> (8 + j)) & 1u) {
+                    const float xv = as * sl[3 * Gm::PITCH + NCOL * lane + j] + ab, yv = sl[3 * Gm::PITCH + 32 * NCOL + NCOL * lane + j];
+                    const float df = xv - yv;
+                    const float sgn = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+                    gp[j] = gs * (w_l1 * sgn - w_ssim * (done[0][j] + 2.f * xv * done[1][j] + yv * done[2][j]));
+                }
+            }
+        }
     }
+    ph_wait<0>();
 }
 
 static PhWin make_window() {
@@ -260,10 +386,49 @@ static PhWin make_window() {
     return w;
 }
 
+// launch geometry: strips of 32*NCOL columns, segments of seg_rows rows; one warp per (channel, segment, strip)
+struct PhPlan { int ncol, seg_rows, n_seg, n_strip, units, ctas; };
+
+static int ph_env(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+static PhPlan ph_plan(int C, int H, int W) {
+    static const int env_ncol = ph_env("GSD_PH_NCOL", 0), env_seg = ph_env("GSD_PH_SEG", 0);
+    PhPlan pl;
+    pl.ncol = env_ncol == 1 || env_ncol == 2 ? env_ncol : 2;
+    pl.n_strip = (W + 32 * pl.ncol - 1) / (32 * pl.ncol);
+    // One warp per unit, all units resident at once.  Pick the number of row segments that maximises
+    //   (SM load balance) x (useful rows / streamed rows: 10 halo rows are recomputed per segment)
+    // among the choices that keep 7..16 warps per SM (fewer: the per-warp dependency chains are exposed; measured).
+    const int n_sm = 148;
+    int best_seg = H;
+    double best = -1.0;
+    for (int n_seg = 1; n_seg <= (H + PH_MIN_SEG - 1) / PH_MIN_SEG; ++n_seg) {
+        const int seg = (H + n_seg - 1) / n_seg;
+        if ((H + seg - 1) / seg != n_seg) continue;
+        const long long units = (long long)C * pl.n_strip * n_seg;
+        const int waves = (int)((units + n_sm - 1) / n_sm);
+        double eff = ((double)units / n_sm / waves) * ((double)seg / (seg + 2 * PH_R));
+        if (waves < 7) eff *= waves / 7.0;
+        if (waves > 16) eff *= 16.0 / waves;
+        if (eff > best) { best = eff; best_seg = seg; }
+    }
+    int seg = env_seg > 0 ? env_seg : best_seg;
+    if (seg < PH_MIN_SEG) seg = PH_MIN_SEG;
+    if (seg > H) seg = H;
+    pl.seg_rows = seg;
+    pl.n_seg = (H + seg - 1) / seg;
+    pl.units = C * pl.n_seg * pl.n_strip;
+    pl.ctas = (pl.units + PH_WARPS - 1) / PH_WARPS;
+    return pl;
+}
+
 extern "C" int gsd_photometric_workspace_bytes(int32_t C, int32_t H, int32_t W, size_t *bytes) {
     if (C <= 0 || H <= 0 || W <= 0 || !bytes) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
     size_t n = (size_t)C * H * W;
-    size_t nb = (size_t)C * ((H + PH_T - 1) / PH_T) * ((W + PH_T - 1) / PH_T);
+    size_t nb = (size_t)C * ((H + PH_MIN_SEG - 1) / PH_MIN_SEG) * ((W + 31) / 32);  // upper bound on the work units
     *bytes = gsd_align_up(n * 4) * 3 + gsd_align_up(nb * 8);
     return GSD_OK;
 }
@@ -275,6 +440,18 @@ static int ph_check(const GsdPhotometric *p) {
         return GSD_ERR_INVALID;
     }
     return GSD_OK;
+}
+
+template <int MODE>
+static void ph_launch_stats(const PhPlan &pl, cudaStream_t st, int C, int H, int W, const PhWin &win, const float *x, const float *y,
+                            const float *ls, const float *sh, int aff, float *y_mu, float *y_s22, float *dmu, float *ds11,
+                            float *ds12, float *us) {
+    if (pl.ncol == 2)
+        gsd_ssim_stats_kernel<MODE, 2><<<pl.ctas, 32 * PH_WARPS, 0, st>>>(C, H, W, pl.seg_rows, pl.n_seg, pl.n_strip, win, x, y, ls, sh,
+                                                                         aff, y_mu, y_s22, dmu, ds11, ds12, us);
+    else
+        gsd_ssim_stats_kernel<MODE, 1><<<pl.ctas, 32 * PH_WARPS, 0, st>>>(C, H, W, pl.seg_rows, pl.n_seg, pl.n_strip, win, x, y, ls, sh,
+                                                                         aff, y_mu, y_s22, dmu, ds11, ds12, us);
 }
 
 // loss_out: per set {loss, mean|x-y|, mean SSIM}, then the weighted total  (3*n_sets + 1 floats)
@@ -290,19 +467,19 @@ extern "C" int gsd_photometric_forward(const GsdPhotometric *p, float *loss_out,
     float *ds11 = (float *)q; q += gsd_align_up(n * 4);
     float *ds12 = (float *)q; q += gsd_align_up(n * 4);
     float *bs = (float *)q;
-    dim3 grid((W + PH_T - 1) / PH_T, (H + PH_T - 1) / PH_T, C);
+    const PhPlan pl = ph_plan(C, H, W);
     PhWin win = make_window();
     const int aff = (p->affine_log_scale || p->affine_shift) ? 3 : 0;
     if (p->y_mu && p->y_s22)
-        gsd_ssim_stats_kernel<1><<<grid, 256, 0, st>>>(C, H, W, win, p->x, p->y, p->affine_log_scale, p->affine_shift, aff,
-                                                        (float *)p->y_mu, (float *)p->y_s22, dmu, ds11, ds12, bs);
+        ph_launch_stats<1>(pl, st, C, H, W, win, p->x, p->y, p->affine_log_scale, p->affine_shift, aff, (float *)p->y_mu,
+                           (float *)p->y_s22, dmu, ds11, ds12, bs);
     else
-        gsd_ssim_stats_kernel<0><<<grid, 256, 0, st>>>(C, H, W, win, p->x, p->y, p->affine_log_scale, p->affine_shift, aff,
-                                                        nullptr, nullptr, dmu, ds11, ds12, bs);
+        ph_launch_stats<0>(pl, st, C, H, W, win, p->x, p->y, p->affine_log_scale, p->affine_shift, aff, nullptr, nullptr, dmu, ds11,
+                           ds12, bs);
     GSD_LAUNCH_CHECK();
     const int per_set_c = C / p->n_sets;
-    const int blocks_per_set = (int)(grid.x * grid.y) * per_set_c;
-    gsd_ssim_finish_kernel<<<1, 256, 0, st>>>(p->n_sets, blocks_per_set, bs, 1.0f / (float)((size_t)per_set_c * H * W), p->w_l1,
+    const int units_per_set = pl.n_seg * pl.n_strip * per_set_c;
+    gsd_ssim_finish_kernel<<<1, 256, 0, st>>>(p->n_sets, units_per_set, bs, 1.0f / (float)((size_t)per_set_c * H * W), p->w_l1,
                                               p->w_ssim, p->set_weight[0], p->set_weight[1], loss_out);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
@@ -311,10 +488,10 @@ extern "C" int gsd_photometric_forward(const GsdPhotometric *p, float *loss_out,
 // window statistics of a target image, computed once and passed as GsdPhotometric.y_mu / y_s22 on later calls
 extern "C" int gsd_photometric_target_stats(int32_t C, int32_t H, int32_t W, const float *y, float *y_mu, float *y_s22, void *stream) {
     if (C <= 0 || H <= 0 || W <= 0 || !y || !y_mu || !y_s22) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
-    dim3 grid((W + PH_T - 1) / PH_T, (H + PH_T - 1) / PH_T, C);
+    const PhPlan pl = ph_plan(C, H, W);
     PhWin win = make_window();
-    gsd_ssim_stats_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(C, H, W, win, y, y, nullptr, nullptr, 0, y_mu, y_s22, nullptr,
-                                                                     nullptr, nullptr, nullptr);
+    ph_launch_stats<2>(pl, (cudaStream_t)stream, C, H, W, win, y, y, nullptr, nullptr, 0, y_mu, y_s22, nullptr, nullptr, nullptr,
+                       nullptr);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
@@ -331,13 +508,21 @@ extern "C" int gsd_photometric_backward(const GsdPhotometric *p, const float *gs
     const float *dmu = (const float *)q; q += gsd_align_up(n * 4);
     const float *ds11 = (const float *)q; q += gsd_align_up(n * 4);
     const float *ds12 = (const float *)q;
-    dim3 grid((W + PH_T - 1) / PH_T, (H + PH_T - 1) / PH_T, C);
+    const PhPlan pl = ph_plan(C, H, W);
     PhWin win = make_window();
     const int per_set_c = C / p->n_sets;
-    gsd_ssim_grad_kernel<<<grid, 256, 0, st>>>(C, H, W, win, p->x, p->y, p->affine_log_scale, p->affine_shift,
-                                               (p->affine_log_scale || p->affine_shift) ? 3 : 0, dmu, ds11, ds12, gscale_ptr,
-                                               p->set_weight[0], p->set_weight[1], p->w_l1, p->w_ssim,
-                                               1.0f / (float)((size_t)per_set_c * H * W), grad);
+    const int aff = (p->affine_log_scale || p->affine_shift) ? 3 : 0;
+    const float inv_n = 1.0f / (float)((size_t)per_set_c * H * W);
+    if (pl.ncol == 2)
+        gsd_ssim_grad_kernel<2><<<pl.ctas, 32 * PH_WARPS, 0, st>>>(C, H, W, pl.seg_rows, pl.n_seg, pl.n_strip, win, p->x, p->y,
+                                                                  p->affine_log_scale, p->affine_shift, aff, dmu, ds11, ds12,
+                                                                  gscale_ptr, p->set_weight[0], p->set_weight[1], p->w_l1,
+                                                                  p->w_ssim, inv_n, grad);
+    else
+        gsd_ssim_grad_kernel<1><<<pl.ctas, 32 * PH_WARPS, 0, st>>>(C, H, W, pl.seg_rows, pl.n_seg, pl.n_strip, win, p->x, p->y,
+                                                                  p->affine_log_scale, p->affine_shift, aff, dmu, ds11, ds12,
+                                                                  gscale_ptr, p->set_weight[0], p->set_weight[1], p->w_l1,
+                                                                  p->w_ssim, inv_n, grad);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
