@@ -105,7 +105,7 @@ EXPORTS = [
     "gsd_track_losses_workspace_bytes", "gsd_track_losses_fwd_bwd", "gsd_track_pack_edges", "gsd_adam_step", "gsd_track_update_radii",
     "gsd_track_normalize_rotations", "gsd_track_update", "gsd_photometric_target_stats",
     "gsd_gnn_edges_workspace_bytes", "gsd_gnn_build_edges", "gsd_gnn_edge_inputs", "gsd_gnn_aggregate_workspace_bytes",
-    "gsd_gnn_aggregate", "gsd_fps", "gsd_tf32_pack", "gsd_skin_bone_transforms", "gsd_skin_apply", "gsd_knn",
+    "gsd_gnn_aggregate", "gsd_gnn_aggregate_bwd_workspace_bytes", "gsd_gnn_aggregate_bwd", "gsd_gnn_edge_inputs_bwd", "gsd_fps", "gsd_tf32_pack", "gsd_skin_bone_transforms", "gsd_skin_apply", "gsd_knn",
 ]
 
 
@@ -143,6 +143,9 @@ def lib():
     l.gsd_gnn_edge_inputs.argtypes = [C.c_int32] * 7 + [C.c_void_p] * 7
     l.gsd_gnn_aggregate_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
     l.gsd_gnn_aggregate.argtypes = [C.c_int32] * 5 + [C.c_void_p] * 7
+    l.gsd_gnn_aggregate_bwd_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
+    l.gsd_gnn_aggregate_bwd.argtypes = [C.c_int32] * 5 + [C.c_void_p] * 11
+    l.gsd_gnn_edge_inputs_bwd.argtypes = [C.c_int32] * 6 + [C.c_void_p] * 6
     l.gsd_tf32_pack.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_skin_bone_transforms.argtypes = [C.c_int32] + [C.c_void_p] * 7
     l.gsd_skin_apply.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 8

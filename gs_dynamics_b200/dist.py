@@ -24,6 +24,10 @@ def init(backend=None, device=None):
     return rank, local_rank, world
 
 
+def world_size():
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
 def shard(n_units, rank, world):
     """Units (episodes, rollouts) of this rank: contiguous blocks, sizes differing by at most one."""
     base, rem = divmod(n_units, world)

@@ -81,7 +81,23 @@ def fps_rad_idx_torch(pcd, radius, start_idx=None):
 # ----------------------------------------------------------------------------------------------------
 class EdgeIndex:
     """Edges grouped by receiver. receivers/senders: int32 [B,capacity] (-1 = unused slot); row_ptr: int32 [B,N+1]."""
-    __slots__ = ("B", "N", "capacity", "n_tool", "row_ptr", "n_edges", "receivers", "senders")
+    __slots__ = ("B", "N", "capacity", "n_tool", "row_ptr", "n_edges", "receivers", "senders", "_tr")
+
+    def transposed(self):
+        """(col_ptr int32 [B,N+1], order int32 [B,capacity]): the same edges grouped by SENDER (order = edge slots sorted by
+        sender, stable; unused slots last) — what the backward kernels walk.  Built once per graph with device ops, no host sync."""
+        tr = getattr(self, "_tr", None)
+        if tr is None:
+            N = self.N
+            key = torch.where(self.senders >= 0, self.senders, torch.full_like(self.senders, N)).long()
+            order = torch.argsort(key, dim=1, stable=True)
+            counts = torch.zeros((self.B, N + 1), dtype=torch.int64, device=key.device)
+            counts.scatter_add_(1, key, torch.ones_like(key))
+            cp = torch.zeros((self.B, N + 1), dtype=torch.int32, device=key.device)
+            cp[:, 1:] = torch.cumsum(counts[:, :N], 1).to(torch.int32)
+            tr = (cp.contiguous(), order.to(torch.int32).contiguous())
+            self._tr = tr
+        return tr
 
     def dense(self):
         """(Rr, Rs) float32 [B, max_e, N] one-hot matrices exactly as the reference returns them (host sync)."""
@@ -203,23 +219,49 @@ def _tf32_pack(x, relu=False, add=None, want_full=False, weight=False):
 # ----------------------------------------------------------------------------------------------------
 # fused kernels as autograd functions
 # ----------------------------------------------------------------------------------------------------
+class _EdgeInputs(torch.autograd.Function):
+    """rel_inputs of model.py:164-199 (gsd_gnn_edge_inputs); differentiable w.r.t. state (the position differences)."""
+
+    @staticmethod
+    def forward(ctx, state, attrs, p_instance, edges):
+        B, n_his, N, _ = state.shape
+        attr_dim = attrs.shape[2]
+        n_p, n_inst = p_instance.shape[1], p_instance.shape[2]
+        width = 2 * attr_dim + 1 + 3 * n_his
+        state = state.contiguous()
+        out = torch.empty((B, edges.capacity, width), dtype=torch.float32, device=state.device)
+        with torch.cuda.device(state.device):
+            _lib.check(_lib.lib().gsd_gnn_edge_inputs(B, N, edges.capacity, n_his, attr_dim, n_inst, n_p, state.data_ptr(),
+                                                      attrs.data_ptr(), p_instance.data_ptr(), edges.receivers.data_ptr(),
+                                                      edges.senders.data_ptr(), out.data_ptr(), _stream()), "gsd_gnn_edge_inputs")
+        ctx.edges = edges
+        ctx.dims = (B, n_his, N, width, 2 * attr_dim + 1)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        e = ctx.edges
+        B, n_his, N, width, off = ctx.dims
+        g = g.contiguous().float()
+        col_ptr, order = e.transposed()
+        gs = torch.empty((B, n_his, N, 3), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().gsd_gnn_edge_inputs_bwd(B, N, e.capacity, n_his, width, off, e.row_ptr.data_ptr(), col_ptr.data_ptr(),
+                                                          order.data_ptr(), g.data_ptr(), gs.data_ptr(), _stream()),
+                       "gsd_gnn_edge_inputs_bwd")
+        return gs, None, None, None
+
+
 def edge_inputs(state, attrs, p_instance, edges, attr_dim_used=True, group=True):
     """rel_inputs [B, capacity, 2*attr_dim + 1 + 3*n_his] (model.py:164-199)."""
-    B, n_his, N, _ = state.shape
-    attr_dim = attrs.shape[2]
-    n_p, n_inst = p_instance.shape[1], p_instance.shape[2]
-    width = 2 * attr_dim + 1 + 3 * n_his
-    out = torch.empty((B, edges.capacity, width), dtype=torch.float32, device=state.device)
-    with torch.cuda.device(state.device):
-        _lib.check(_lib.lib().gsd_gnn_edge_inputs(B, N, edges.capacity, n_his, attr_dim, n_inst, n_p, state.data_ptr(),
-                                                  attrs.data_ptr(), p_instance.data_ptr(), edges.receivers.data_ptr(),
-                                                  edges.senders.data_ptr(), out.data_ptr(), _stream()), "gsd_gnn_edge_inputs")
-    return out
+    if state.shape[3] != 3:
+        raise ValueError("state must be [B, n_his, N, 3]")
+    return _EdgeInputs.apply(state, attrs.contiguous(), p_instance.contiguous(), edges)
 
 
 class _Aggregate(torch.autograd.Function):
-    """agg[node] = sum_e ReLU(A[e] + P[node,:F] + P[send(e),F:]).  Backward (for the GNN-training row) recomputes the
-    pre-activation with torch ops; it is not on the rollout path."""
+    """agg[node] = sum_e ReLU(A[e] + P[node,:F] + P[send(e),F:]).  Backward (GNN training): gsd_gnn_aggregate_bwd recomputes
+    the pre-activation sign, so the forward saves nothing but its inputs."""
 
     @staticmethod
     def forward(ctx, A, P, edges):
@@ -245,16 +287,19 @@ class _Aggregate(torch.autograd.Function):
         e = ctx.edges
         B, N, cap = e.B, e.N, e.capacity
         Fd = A.shape[-1]
-        valid = (e.receivers >= 0).reshape(-1)
-        base = (torch.arange(B, device=A.device) * N)[:, None]
-        r = (e.receivers.long().clamp(min=0) + base).reshape(-1)
-        s = (e.senders.long().clamp(min=0) + base).reshape(-1)
-        pre = A.reshape(-1, Fd) + P[r, :Fd] + P[s, Fd:]
-        gm = g[r] * (pre > 0) * valid[:, None]
-        gP = torch.zeros_like(P)
-        gP[:, :Fd].index_add_(0, r, gm)
-        gP[:, Fd:].index_add_(0, s, gm)
-        return gm.reshape(A.shape), gP, None
+        g = g.contiguous().float()
+        col_ptr, order = e.transposed()
+        lib = _lib.lib()
+        nbytes = C.c_size_t()
+        _lib.check(lib.gsd_gnn_aggregate_bwd_workspace_bytes(B, e.n_tool, Fd, C.byref(nbytes)), "gsd_gnn_aggregate_bwd_workspace_bytes")
+        with torch.cuda.device(A.device):
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=A.device)
+            gA = torch.zeros_like(A)       # unused edge slots keep a zero gradient
+            gP = torch.empty_like(P)
+            _lib.check(lib.gsd_gnn_aggregate_bwd(B, N, cap, Fd, e.n_tool, e.row_ptr.data_ptr(), e.senders.data_ptr(), col_ptr.data_ptr(),
+                                                 order.data_ptr(), A.data_ptr(), P.data_ptr(), g.data_ptr(), ws.data_ptr(),
+                                                 gA.data_ptr(), gP.data_ptr(), _stream()), "gsd_gnn_aggregate_bwd")
+        return gA, gP, None
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -120,3 +120,43 @@ def make_graph_inputs(n_obj, seed, kind="sloth", n_his=3):
     t = torch.tensor
     return dict(state=t(states), action=t(action), attrs=t(attrs), p_instance=torch.ones(1, n_obj, 1),
                 state_mask=torch.ones(N, dtype=torch.bool), eef_mask=torch.tensor([False] * n_obj + [True]))
+
+
+def make_training_batch(B, n_obj, seed, kind="sloth", n_future=3, n_his=3, n_pad=2):
+    """Seeded training-style batch (the dict DynDataset yields, /root/reference/src/data/dataset.py:240-420, without graph
+    matrices): B elements of n_obj object particles + n_pad padding particles (state_mask False, as the dataset pads to
+    max_nobj) + 1 tool particle (last).  Futures: the objects drift by a smooth seeded field, the tool advances 5 mm per step."""
+    rng = np.random.default_rng(seed)
+    N = n_obj + n_pad + 1
+    n_p = n_obj + n_pad
+    out = {k: [] for k in ("state", "action", "attrs", "p_instance", "state_mask", "eef_mask", "state_future", "tool_future",
+                           "action_future")}
+    for b in range(B):
+        gi = make_graph_inputs(n_obj, seed * 1000 + b, kind, n_his)
+        st = torch.zeros(n_his, N, 3)
+        st[:, :n_obj] = gi["state"][0, :, :n_obj]
+        st[:, -1] = gi["state"][0, :, n_obj]
+        act = torch.zeros(N, 3)
+        act[-1] = gi["action"][0, n_obj]
+        attrs = torch.zeros(N, 2)
+        attrs[:n_obj, 0] = 1
+        attrs[-1, 1] = 1
+        p_inst = torch.zeros(n_p, 1)
+        p_inst[:n_obj] = 1
+        smask = torch.zeros(N, dtype=torch.bool)
+        smask[:n_obj] = True
+        smask[-1] = True
+        emask = torch.zeros(N, dtype=torch.bool)
+        emask[-1] = True
+        drift = torch.tensor(rng.normal(scale=0.002, size=(n_future, 1, 3)), dtype=torch.float32).cumsum(0)
+        sf = torch.zeros(n_future, n_p, 3)
+        sf[:, :n_obj] = st[-1, :n_obj][None] + drift + torch.tensor(rng.normal(scale=0.0005, size=(n_future, n_obj, 3)), dtype=torch.float32)
+        tf = torch.zeros(max(n_future - 1, 1), N, 3)
+        af = torch.zeros(max(n_future - 1, 1), N, 3)
+        for f in range(n_future - 1):
+            tf[f, -1] = st[-1, -1] + act[-1] * (f + 1)
+            af[f, -1] = act[-1]
+        for k, v in (("state", st), ("action", act), ("attrs", attrs), ("p_instance", p_inst), ("state_mask", smask),
+                     ("eef_mask", emask), ("state_future", sf), ("tool_future", tf), ("action_future", af)):
+            out[k].append(v)
+    return {k: torch.stack(v) for k, v in out.items()}

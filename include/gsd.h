@@ -253,6 +253,21 @@ int gsd_gnn_aggregate_workspace_bytes(int32_t B, int32_t n_heavy, int32_t F, siz
 int gsd_gnn_aggregate(int32_t B, int32_t N, int32_t capacity, int32_t F, int32_t n_heavy, const int32_t *row_ptr,
                       const int32_t *senders, const float *A, const float *P, void *ws, float *agg, void *stream);
 
+/* Backward of gsd_gnn_aggregate / gsd_gnn_edge_inputs for GNN training (replaces what autograd derives from the one-hot
+ * bmm gathers/scatters of /root/reference/src/gnn/model.py:164-229 under /root/reference/src/train.py:183-211).
+ * col_ptr [B,N+1] / order [B,capacity]: the forward's edges grouped by SENDER (order = edge ids sorted by sender, stable).
+ *   gA[e]     = g_agg[recv(e)] where A[e] + P[recv,0:F] + P[send,F:2F] > 0, else 0     [B*capacity, F]
+ *   gP[n]     = [ sum_{e: recv=n} gA[e] | sum_{e: send=n} gA[e] ]                        [B*N, 2F]
+ *   g_state[b,h,n,:] = sum_{e: recv=n} g_rel[b,e,off+3h:off+3h+3] - sum_{e: send=n} (same)  [B,n_his,N,3]
+ * No atomics; fixed summation order. */
+int gsd_gnn_aggregate_bwd_workspace_bytes(int32_t B, int32_t n_heavy, int32_t F, size_t *bytes);
+int gsd_gnn_aggregate_bwd(int32_t B, int32_t N, int32_t capacity, int32_t F, int32_t n_heavy, const int32_t *row_ptr,
+                          const int32_t *senders, const int32_t *col_ptr, const int32_t *order, const float *A, const float *P,
+                          const float *g_agg, void *ws, float *gA, float *gP, void *stream);
+int gsd_gnn_edge_inputs_bwd(int32_t B, int32_t N, int32_t capacity, int32_t n_his, int32_t width, int32_t offset,
+                            const int32_t *row_ptr, const int32_t *col_ptr, const int32_t *order, const float *g_rel,
+                            float *g_state, void *stream);
+
 /* Operands for the error-compensated TF32 GEMMs of the dense layers (nn.Linear in src/gnn/model.py:16-108 computed as one
  * tensor-core GEMM over K = 3F).  t = relu ? max(x + add, 0) : x + add  (add may be NULL), hi = round_to_tf32(t), lo = t - hi.
  * out [rows, 3F]: activation layout (weight_layout = 0) [lo | hi | hi], weight layout (1) [hi | lo | hi].

@@ -15,7 +15,8 @@ import torch
 import torch.nn.functional as F
 
 # seeded input / weight builders are plain data generators shared with bench.py; they live in the product package
-from gs_dynamics_b200.workloads import (model_dims, make_state_dict, sloth_cfg, rope_cfg, make_graph_inputs)  # noqa: F401
+from gs_dynamics_b200.workloads import (model_dims, make_state_dict, sloth_cfg, rope_cfg, make_graph_inputs,  # noqa: F401
+                                        make_training_batch)
 
 
 def _mlp3(sd, name, x):
@@ -125,3 +126,63 @@ def fps_radius(pcd, radius, start_idx):
     return torch.tensor(idx)
 
 
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GNN training: losses and the n_future-step unroll of /root/reference/src/train.py, dense one-hots
+# ---------------------------------------------------------------------------------------------------------------------
+def length_loss(pred, state, Rr, Rs):
+    """/root/reference/src/train.py:66-83"""
+    n_p = pred.shape[1]
+    pos = state[:, 0, :n_p].detach()
+    Rr, Rs = Rr[:, :, :n_p], Rs[:, :, :n_p]
+    pos_diff = Rr.bmm(pos) - Rs.bmm(pos)
+    pred_diff = Rr.bmm(pred) - Rs.bmm(pred)
+    return F.mse_loss(torch.norm(pred_diff, dim=-1), torch.norm(pos_diff, dim=-1))
+
+
+def local_rigid_loss(pred, state, Rr, Rs):
+    """/root/reference/src/train.py:85-102"""
+    n_p = pred.shape[1]
+    pos = state[:, 0, :n_p].detach()
+    Rr, Rs = Rr[:, :, :n_p], Rs[:, :, :n_p]
+    diff_r = torch.norm(Rr.bmm(pred) - Rr.bmm(pos), dim=-1)
+    diff_s = torch.norm(Rs.bmm(pred) - Rs.bmm(pos), dim=-1)
+    return F.mse_loss(diff_r, diff_s)
+
+
+def batch_edges(batch, adj_thresh, topk, connect_all):
+    """Per-element construct_edges on the newest frame, one-hots padded with zero rows to a common n_rel
+    (pad_torch, /root/reference/src/data/dataset.py:229-238)."""
+    B, _, N, _ = batch["state"].shape
+    rs = [construct_edges(batch["state"][b, -1], adj_thresh, batch["state_mask"][b], batch["eef_mask"][b], topk, connect_all)
+          for b in range(B)]
+    n_rel = max(r.numel() for r, _ in rs)
+    Rr = torch.zeros(B, n_rel, N, dtype=batch["state"].dtype)
+    Rs = torch.zeros(B, n_rel, N, dtype=batch["state"].dtype)
+    for b, (r, s) in enumerate(rs):
+        ar = torch.arange(r.numel())
+        Rr[b, ar, r] = 1
+        Rs[b, ar, s] = 1
+    return Rr, Rs
+
+
+def unrolled_loss(sd, cfg, batch, Rr, Rs, n_future, w_mse=1.0, w_len=0.01):
+    """/root/reference/src/train.py:183-211 with loss_funcs = [(mse_loss, w_mse), (length_loss, w_len)].
+    Returns (loss_sum, [[mse_i, len_i] per step])."""
+    state, action = batch["state"], batch["action"]
+    loss_sum, parts = 0, []
+    for fi in range(n_future):
+        gt = batch["state_future"][:, fi].clone()
+        pred, _ = forward(sd, cfg, state, batch["attrs"], Rr, Rs, batch["p_instance"], action)
+        pred_p = pred[:, :gt.shape[1], :3].clone()
+        l_mse = w_mse * F.mse_loss(pred_p, gt)
+        l_len = w_len * length_loss(pred_p, state, Rr, Rs)
+        loss_sum = loss_sum + l_mse + l_len
+        parts.append([l_mse, l_len])
+        if fi < n_future - 1:
+            next_state = batch["tool_future"][:, fi].clone().unsqueeze(1)
+            next_state[:, -1, :pred_p.shape[1]] = pred_p
+            state = torch.cat([state[:, 1:], next_state], dim=1)
+            action = batch["action_future"][:, fi].clone()
+    return loss_sum, parts

@@ -206,3 +206,114 @@ def test_rollout_graph_matches_eager():
         pa = ra.step(d).clone()
         pb = rb.step(d).clone()
     assert float((pa - pb).abs().max()) <= 1e-6 and float((ra.states - rb.states).abs().max()) <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GNN training row: backward kernels, losses, the train.py unroll
+# Tolerances: gradients of a 2-3 step unroll through three propagation steps, fp32 with different summation orders:
+# 2e-4 of the tensor max vs the reference fixture (the fp32 oracle itself differs from a float64 run by ~1e-5).
+# ---------------------------------------------------------------------------------------------------------------------
+TGOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "gnn_train_golden.npz"))
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+@pytest.mark.parametrize("n_tool_rows", [0, 1])
+def test_aggregate_backward_kernel_vs_torch(n_tool_rows):
+    """gsd_gnn_aggregate_bwd vs autograd through the index formulation (heavy split rows on and off)."""
+    from gs_dynamics_b200 import gnn
+    gi = GO.make_graph_inputs(150, 5, "sloth")
+    e = gnn.construct_edges_index(gi["state"][0, -1].cuda(), 0.075, gi["state_mask"].cuda(), gi["eef_mask"].cuda(), topk=6, connect_all=True)
+    e.n_tool = n_tool_rows
+    Fd, N, cap = 128, e.N, e.capacity
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randn(cap, Fd, device="cuda", generator=g).requires_grad_(True)
+    P = torch.randn(N, 2 * Fd, device="cuda", generator=g).requires_grad_(True)
+    out = gnn._Aggregate.apply(A, P, e)
+    go = torch.randn_like(out)
+    out.backward(go)
+    gA, gP = A.grad.clone(), P.grad.clone()
+    A2, P2 = A.detach().double().requires_grad_(True), P.detach().double().requires_grad_(True)
+    E = int(e.n_edges[0])
+    r, s = e.receivers[0, :E].long(), e.senders[0, :E].long()
+    pre = torch.relu(A2[:E] + P2[r, :Fd] + P2[s, Fd:])
+    ref = torch.zeros(N, Fd, device="cuda", dtype=torch.float64).index_add_(0, r, pre)
+    assert _rel(out.detach().cpu(), ref.detach().cpu()) < 1e-5
+    ref.backward(go.double())
+    assert float(gA[E:].abs().max()) == 0.0
+    assert _rel(gA[:E].cpu(), A2.grad[:E].cpu()) < 1e-6
+    assert _rel(gP.cpu(), P2.grad.cpu()) < 1e-5
+    # bit-reproducible (no atomics)
+    A.grad = None; P.grad = None
+    gnn._Aggregate.apply(A, P, e).backward(go)
+    assert torch.equal(A.grad, gA) and torch.equal(P.grad, gP)
+
+
+def test_edge_inputs_backward_kernel_vs_torch():
+    from gs_dynamics_b200 import gnn
+    gi = GO.make_graph_inputs(120, 6, "sloth")
+    e = gnn.construct_edges_index(gi["state"][0, -1].cuda(), 0.075, gi["state_mask"].cuda(), gi["eef_mask"].cuda(), topk=5, connect_all=True)
+    st = gi["state"].cuda().requires_grad_(True)
+    rel = gnn.edge_inputs(st, gi["attrs"].cuda(), gi["p_instance"].cuda(), e)
+    go = torch.randn_like(rel)
+    rel.backward(go)
+    E = int(e.n_edges[0])
+    r, s = e.receivers[0, :E].long(), e.senders[0, :E].long()
+    st2 = gi["state"].cuda().double().requires_grad_(True)
+    diff = (st2[0][:, r] - st2[0][:, s]).permute(1, 0, 2).reshape(E, -1)            # [E, 3*n_his]
+    np.testing.assert_allclose(rel[0, :E, 5:].detach().cpu().numpy(), diff.detach().cpu().numpy(), atol=1e-7)
+    diff.backward(go[0, :E, 5:].double())
+    assert _rel(st.grad.cpu(), st2.grad.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["sloth", "rope"])
+def test_training_unroll_gradients_match_reference(tag):
+    """train.py:183-211 through gnn_train.unrolled_loss on the CUDA kernels vs the fixture generated from the reference's
+    model and loss functions; both calling conventions (dense Rr/Rs of the dataset, EdgeIndex)."""
+    from gs_dynamics_b200 import gnn, gnn_train
+    B, n_obj, topk, adj, conn, seed, n_future = TGOLD[f"{tag}_cfg"]
+    B, n_obj, topk, seed, n_future = int(B), int(n_obj), int(topk), int(seed), int(n_future)
+    cfg = GO.sloth_cfg(128) if tag == "sloth" else GO.rope_cfg(128)
+    batch = GO.make_training_batch(B, n_obj, seed, tag, n_future)
+    Rr, Rs = GO.batch_edges(batch, float(adj), topk, bool(conn))
+    keys = [k.split("_grad_", 1)[1] for k in TGOLD.files if k.startswith(f"{tag}_grad_") and not k.endswith("abs_sum")]
+    for mode in ("dense", "index"):
+        m = gnn.DynamicsPredictor(dict(cfg), torch.device("cuda")).cuda().train()
+        m.load_state_dict(GO.make_state_dict(cfg, seed, head_scale=0.05))
+        data = {k: v.cuda() for k, v in batch.items()}
+        if mode == "dense":
+            data["Rr"], data["Rs"] = Rr.cuda(), Rs.cuda()
+        else:
+            data["Rr"] = gnn.construct_edges_index(data["state"][:, -1], float(adj), data["state_mask"], data["eef_mask"], topk=topk,
+                                                   connect_all=bool(conn), capacity=Rr.shape[1])
+            data["Rs"] = None
+        loss, parts = gnn_train.unrolled_loss(m, data, n_future, [(gnn_train.mse_loss, 1.0), (gnn_train.length_loss, 0.01)])
+        loss.backward()
+        gold = float(TGOLD[f"{tag}_loss"])
+        assert abs(loss.item() - gold) <= 2e-5 * max(1.0, abs(gold)), (mode, loss.item(), gold)
+        np.testing.assert_allclose(np.array([[float(p) for p in ps] for ps in parts]), TGOLD[f"{tag}_items"], rtol=2e-4, atol=1e-9)
+        named = dict(m.named_parameters())
+        for k in keys:
+            assert _rel(named[k].grad.cpu().numpy(), TGOLD[f"{tag}_grad_{k}"]) < 2e-4, (mode, k)
+        sums = np.array([float(p.grad.abs().sum()) for _, p in m.named_parameters()])
+        np.testing.assert_allclose(sums, TGOLD[f"{tag}_grad_abs_sum"], rtol=1e-3)
+
+
+def test_train_iteration_decreases_loss_and_bucket_aliases_grads():
+    from gs_dynamics_b200 import gnn, gnn_train
+    cfg = GO.sloth_cfg(128)
+    m = gnn.DynamicsPredictor(dict(cfg), torch.device("cuda")).cuda().train()
+    m.load_state_dict(GO.make_state_dict(cfg, 3, head_scale=0.05))
+    batch = {k: v.cuda() for k, v in GO.make_training_batch(4, 50, 3, "sloth", 3).items()}
+    batch["Rr"] = gnn.construct_edges_index(batch["state"][:, -1], 0.075, batch["state_mask"], batch["eef_mask"], topk=5, connect_all=True)
+    batch["Rs"] = None
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    bucket = gnn_train.GradientBucket(m.parameters())
+    funcs = gnn_train.default_loss_funcs({"mse_loss": 1.0, "length_loss": 0.05})
+    losses = [float(gnn_train.train_iteration(m, opt, batch, 3, funcs, bucket)[0]) for _ in range(8)]
+    assert losses[-1] < losses[0]
+    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in m.parameters())
+    assert float(bucket.flat.abs().sum()) > 0

@@ -184,3 +184,59 @@ fout["paths_depth"] = np.array([ref_tu.map_to_depth_path(p) for p in ["camera_1/
 dst = os.path.join(ROOT, "tests", "golden", "formats_golden.npz")
 np.savez_compressed(dst, **fout)
 print("wrote", dst, os.path.getsize(dst), "bytes")
+
+# ------------------------------------------------------------------------------------------------------------------
+# gnn_train_golden.npz — the reference's training unroll (src/train.py:183-211) composed from ITS model and ITS loss
+# functions (train.mse_loss, train.length_loss) on a seeded batch (workloads.make_training_batch), nf = 128:
+# loss, per-step loss terms, and gradients of selected parameters after loss_sum.backward().
+# ------------------------------------------------------------------------------------------------------------------
+for name in ("matplotlib", "matplotlib.pyplot"):
+    sys.modules[name] = types.ModuleType(name)
+sys.modules["matplotlib"].use = lambda *a, **k: None
+import train as ref_train                                          # /root/reference/src/train.py
+
+GRAD_KEYS = ["particle_encoder.model.0.weight", "relation_encoder.model.0.weight", "relation_encoder.model.4.bias",
+             "relation_propagator.linear.bias", "particle_propagator.linear.bias", "non_rigid_predictor.linear_2.weight"]
+tout = {}
+for tag, (kind, B, n_obj, topk, adj, conn, seed, n_future) in dict(sloth=("sloth", 2, 60, 5, 0.075, True, 21, 3),
+                                                                    rope=("rope", 3, 40, 4, 0.08, False, 22, 2)).items():
+    cfg = GO.sloth_cfg(128) if kind == "sloth" else GO.rope_cfg(128)
+    model = RefPredictor(dict(cfg), torch.device("cpu"))
+    model.load_state_dict(GO.make_state_dict(cfg, seed, head_scale=0.05))
+    model.train()
+    batch = GO.make_training_batch(B, n_obj, seed, kind, n_future)
+    Rr, Rs = GO.batch_edges(batch, adj, topk, conn)
+    # cross-check the padded one-hots against the reference's own edge builder
+    for b in range(B):
+        rr, rs_ = ref_edges(batch["state"][b, -1], adj, mask=batch["state_mask"][b], tool_mask=batch["eef_mask"][b], topk=topk, connect_all=conn)
+        assert torch.equal(rr, Rr[b, :rr.shape[0]]) and torch.equal(rs_, Rs[b, :rs_.shape[0]]) and Rr[b, rr.shape[0]:].abs().sum() == 0
+    data = dict(batch)
+    data["Rr"], data["Rs"] = Rr, Rs
+    loss_funcs = [(ref_train.mse_loss, 1.0), (ref_train.length_loss, 0.01)]
+    loss_sum, items = 0, []
+    future_state, future_tool, future_action = data['state_future'], data['tool_future'], data['action_future']
+    for fi in range(n_future):                                      # train.py:183-211, line for line
+        gt_state = future_state[:, fi].clone()
+        pred_state, pred_motion = model(**data)
+        pred_state_p = pred_state[:, :gt_state.shape[1], :3].clone()
+        loss = [weight * func(pred_state_p, gt_state, **data) for func, weight in loss_funcs]
+        loss_sum += sum(loss)
+        items.append([l.item() for l in loss])
+        if fi < n_future - 1:
+            next_tool = future_tool[:, fi].clone()
+            next_action = future_action[:, fi].clone()
+            next_state = next_tool.unsqueeze(1)
+            next_state[:, -1, :pred_state_p.shape[1]] = pred_state_p
+            next_state = torch.cat([data['state'][:, 1:], next_state], dim=1)
+            data["state"] = next_state
+            data["action"] = next_action
+    loss_sum.backward()
+    grads = dict(model.named_parameters())
+    tout.update({f"{tag}_cfg": np.array([B, n_obj, topk, adj, float(conn), seed, n_future]), f"{tag}_loss": loss_sum.item(),
+                 f"{tag}_items": np.array(items), f"{tag}_pred_last": pred_state_p.detach().numpy(),
+                 f"{tag}_grad_abs_sum": np.array([float(p.grad.abs().sum()) for _, p in model.named_parameters()])})
+    for k in GRAD_KEYS:
+        tout[f"{tag}_grad_{k}"] = grads[k].grad.numpy()
+dst = os.path.join(ROOT, "tests", "golden", "gnn_train_golden.npz")
+np.savez_compressed(dst, **tout)
+print("wrote", dst, os.path.getsize(dst), "bytes")
