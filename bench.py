@@ -450,6 +450,63 @@ def run_gnn_cpu(budget_s=8.0, n_obj=2000, seed=1):
             "sample": "%d steps in %.1f s (dense one-hot reference formulation on host cores)" % (done, dt)}
 
 
+def run_gnn_train(device, world, steps=10, warmup=3, B=64, n_obj=100, n_future=5):
+    """GNN training iteration (train.py:176-218 at the reference's batch_size 64 / n_future 5, nf = 512,
+    ~100 object particles, topk 5): zero_grad + 5-step unroll + backward + gradient-bucket all-reduce (N > 1) + Adam.
+    Every rank trains on its own batch (weak scaling); device time per step, max over ranks."""
+    import torch.distributed as dist
+    from gs_dynamics_b200 import gnn, gnn_train, workloads as GO
+    rank = int(os.environ.get("RANK", "0"))
+    cfg = GO.sloth_cfg(512)
+    model = gnn.DynamicsPredictor(dict(cfg), device).to(device).train()
+    model.load_state_dict(GO.make_state_dict(cfg, 0, head_scale=0.05))
+    batch = {k: v.to(device) for k, v in GO.make_training_batch(B, n_obj, 100 + rank, "sloth", n_future).items()}
+    batch["Rr"] = gnn.construct_edges_index(batch["state"][:, -1], 0.075, batch["state_mask"], batch["eef_mask"], topk=5, connect_all=True)
+    batch["Rs"] = None
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    bucket = gnn_train.GradientBucket(model.parameters())
+    funcs = gnn_train.default_loss_funcs({"mse_loss": 1.0, "length_loss": 0.05})
+    losses = []
+    for _ in range(warmup):
+        losses.append(float(gnn_train.train_iteration(model, opt, batch, n_future, funcs, bucket)[0]))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, _ = gnn_train.train_iteration(model, opt, batch, n_future, funcs, bucket)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t[0])
+    E = int(batch["Rr"].n_edges.sum())
+    return {"metric": "GNN training samples/sec", "value": world * B * steps / dt, "unit": "samples/s", "ms_per_iteration": 1e3 * dt / steps,
+            "steps": steps, "n_gpus": world, "allreduce_bytes_per_step": int(bucket.flat.numel() * 4) if world > 1 else 0,
+            "loss_first": losses[0], "loss_last": float(loss),
+            "config": {"workload": "train.py iteration: batch %d x (%d particles + pad + tool), %d edges/batch, n_future %d, nf 512, "
+                                   "mse + 0.05 length loss, Adam; DP = one batch per GPU + one flat-bucket all-reduce" % (B, n_obj, E, n_future)}}
+
+
+def run_gnn_train_cpu(B=4, n_obj=100, n_future=5):
+    """The reference formulation (dense one-hot bmm, autograd) of the same iteration on the host cores: one fwd+bwd of a
+    B = 4 sample of the batch (the oracle is a pure function of the state_dict; Adam is negligible)."""
+    from oracle import gnn_oracle as GO
+    torch.set_num_threads(os.cpu_count())
+    cfg = GO.sloth_cfg(512)
+    sd = {k: v.clone().requires_grad_(True) for k, v in GO.make_state_dict(cfg, 0, head_scale=0.05).items()}
+    batch = GO.make_training_batch(B, n_obj, 100, "sloth", n_future)
+    Rr, Rs = GO.batch_edges(batch, 0.075, 5, True)
+    t0 = time.time()
+    loss, _ = GO.unrolled_loss(sd, cfg, batch, Rr, Rs, n_future, 1.0, 0.05)
+    loss.backward()
+    dt = time.time() - t0
+    return {"value": B / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "1 forward+backward of a %d-sample batch in %.1f s (dense one-hot reference formulation, autograd, host cores)" % (B, dt)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -469,7 +526,15 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device and no CPU fallback in the product path (use --impl reference for the CPU arm)")
     line, rank, world = run_ours(args)
+    gtrain = None
+    if not args.no_gnn:
+        try:   # every rank takes part (N > 1: the gradient all-reduce is a real NCCL collective)
+            gtrain = run_gnn_train(torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))), world)
+        except Exception as ex:
+            gtrain = {"error": repr(ex)}
     if rank == 0:
+        if gtrain is not None:
+            line["gnn_train"] = gtrain
         if world == 1:
             done, dt, cores = cpu_iterations(args.gaussians, 10 ** 9, 1, budget_s=args.cpu_baseline_seconds)
             line["cpu_baseline"] = {"value": done / dt, "unit": "iters/s", "cores": cores, "kind": "port",
@@ -479,6 +544,8 @@ def main():
                     g = run_gnn_ours(torch.device("cuda", 0))
                     g["cpu_baseline"] = run_gnn_cpu()
                     line["gnn"] = g
+                    if "error" not in line.get("gnn_train", {"error": 1}):
+                        line["gnn_train"]["cpu_baseline"] = run_gnn_train_cpu()
                 except Exception as ex:  # the secondary metric must never take the headline line down
                     line["gnn"] = {"error": repr(ex)}
         else:

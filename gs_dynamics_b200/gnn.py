@@ -216,6 +216,60 @@ def _tf32_pack(x, relu=False, add=None, want_full=False, weight=False):
     return out, full
 
 
+class _Linear3x(torch.autograd.Function):
+    """y = x W^T + b with fp32 accuracy on the TF32 tensor cores, forward AND backward (GNN training):
+    forward / grad-input are one GEMM over the K-concatenated error-compensated operands of gsd_tf32_pack; grad-weight
+    contracts over the rows, so it is three TF32 GEMMs on the hi / lo halves (strided views of the packed operands, small
+    products first).  cuBLAS does the GEMMs (library code); the split/pack is this repo's kernel."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        xp, _ = _tf32_pack(x)                                        # [rows, 3K] = [lo | hi | hi]
+        Wp, _ = _tf32_pack(W.detach(), weight=True)                  # [out, 3K]  = [hi | lo | hi]
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            y = torch.addmm(b, xp, Wp.t()) if b is not None else xp @ Wp.t()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        ctx.save_for_backward(xp, W)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xp, W = ctx.saved_tensors
+        K = W.shape[1]
+        gy = gy.contiguous()
+        gp, _ = _tf32_pack(gy)                                       # [rows, 3*out] = [lo | hi | hi]
+        O = gy.shape[1]
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            gx = gW = None
+            if ctx.needs_input_grad[0]:
+                Wtp, _ = _tf32_pack(W.detach().t().contiguous(), weight=True)   # [K, 3*out]
+                gx = gp @ Wtp.t()
+            if ctx.needs_input_grad[1]:
+                g_lo, g_hi = gp[:, :O], gp[:, O:2 * O]
+                x_lo, x_hi = xp[:, :K], xp[:, K:2 * K]
+                gW = g_lo.t() @ x_hi
+                gW.addmm_(g_hi.t(), x_lo)
+                gW.addmm_(g_hi.t(), x_hi)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        gb = gy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return gx, gW, gb
+
+
+def _linear(x, W, b, fast):
+    """F.linear, or its 3xTF32 tensor-core twin when `fast` and the shape suits the pack kernel."""
+    if fast and x.is_cuda and x.dim() == 2 and x.shape[0] >= 256 and W.shape[1] % 4 == 0 and W.shape[1] >= 128 and W.shape[0] % 4 == 0 \
+            and W.shape[0] >= 128:
+        return _Linear3x.apply(x, W, b)
+    return F.linear(x, W, b)
+
+
 # ----------------------------------------------------------------------------------------------------
 # fused kernels as autograd functions
 # ----------------------------------------------------------------------------------------------------
@@ -388,23 +442,30 @@ class DynamicsPredictor(nn.Module):
             p_inputs = torch.cat([p_inputs, action], 2)
         return p_inputs
 
-    def _forward_ieee(self, p_inputs, rel_inputs, edges, B, N, n_p):
-        """fp32 SIMT GEMMs, differentiable (training and the bit-tight parity tests)."""
+    def _forward_ieee(self, p_inputs, rel_inputs, edges, B, N, n_p, fast=False):
+        """Differentiable path (training and the bit-tight parity tests).  fast=False: fp32 SIMT GEMMs; fast=True: the F-wide
+        layers run as error-compensated TF32 tensor-core GEMMs in forward and backward (_Linear3x), same results to ~1e-6."""
         cfg, Fd = self.model_config, self.nf_effect
-        particle_encode = self.particle_encoder(p_inputs).reshape(B * N, Fd)
-        relation_encode = self.relation_encoder(rel_inputs).reshape(B * edges.capacity, Fd)
+        pe, re, nr = self.particle_encoder.model, self.relation_encoder.model, self.non_rigid_predictor
+        mlp3 = lambda m, x: torch.relu(_linear(torch.relu(_linear(torch.relu(F.linear(x, m[0].weight, m[0].bias)), m[2].weight,
+                                                                      m[2].bias, fast)), m[4].weight, m[4].bias, fast))
+        particle_encode = mlp3(pe, p_inputs.reshape(B * N, -1))
+        relation_encode = mlp3(re, rel_inputs.reshape(B * edges.capacity, -1))
         Wr, br = self.relation_propagator.linear.weight, self.relation_propagator.linear.bias
         Wp, bp = self.particle_propagator.linear.weight, self.particle_propagator.linear.bias
-        A = F.linear(relation_encode, Wr[:, :Fd], br)                 # pstep-invariant edge term
-        C0 = F.linear(particle_encode, Wp[:, :Fd], bp)                # pstep-invariant node term
+        A = _linear(relation_encode, Wr[:, :Fd].contiguous() if fast else Wr[:, :Fd], br, fast)   # pstep-invariant edge term
+        C0 = _linear(particle_encode, Wp[:, :Fd].contiguous() if fast else Wp[:, :Fd], bp, fast)  # pstep-invariant node term
         W23 = torch.cat([Wr[:, Fd:2 * Fd], Wr[:, 2 * Fd:]], 0)        # [2F, F]: receiver | sender projections
-        Wp2_t = Wp[:, Fd:].t()
+        Wp2 = Wp[:, Fd:].contiguous() if fast else Wp[:, Fd:]
         h = particle_encode
         for _ in range(cfg['pstep']):
-            P = F.linear(h, W23)                                      # [B*N, 2F]
+            P = _linear(h, W23, None, fast)                           # [B*N, 2F]
             agg = _Aggregate.apply(A, P, edges)
-            h = torch.relu(torch.addmm(C0 + h, agg, Wp2_t))
-        return self.non_rigid_predictor(h.view(B, N, Fd)[:, :n_p].contiguous())
+            h = torch.relu(C0 + h + _linear(agg, Wp2, None, fast))
+        x = h.view(B, N, Fd)[:, :n_p].reshape(B * n_p, Fd)
+        x = torch.relu(_linear(x, nr.linear_0.weight, nr.linear_0.bias, fast))
+        x = torch.relu(_linear(x, nr.linear_1.weight, nr.linear_1.bias, fast))
+        return F.linear(x, nr.linear_2.weight, nr.linear_2.bias).view(B, n_p, 3)
 
     def _packed_weights(self):
         """[w_hi | w_lo | w_hi] operands of every F-wide layer, rebuilt when a parameter changes (version counters)."""
@@ -475,7 +536,8 @@ class DynamicsPredictor(nn.Module):
             if self.matmul == "3xtf32" and not torch.is_grad_enabled() and B * N >= 256 and Fd % 4 == 0:
                 pred_motion = self._forward_3xtf32(p_inputs, rel_inputs, edges, B, N, n_p)
             else:
-                pred_motion = self._forward_ieee(p_inputs, rel_inputs, edges, B, N, n_p)
+                pred_motion = self._forward_ieee(p_inputs, rel_inputs, edges, B, N, n_p,
+                                                 fast=self.matmul == "3xtf32" and torch.is_grad_enabled() and Fd % 4 == 0)
             pred_pos = state[:, -1, :n_p] + torch.clamp(pred_motion, max=self.motion_clamp, min=-self.motion_clamp)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev_tf32
