@@ -71,6 +71,7 @@ class GsdTrackUpdate(C.Structure):
         ("means3D", C.c_void_p), ("unnorm_rotations", C.c_void_p), ("g_means_a", C.c_void_p), ("g_means_b", C.c_void_p),
         ("g_rot_a", C.c_void_p), ("g_rot_b", C.c_void_p), ("m_means", C.c_void_p), ("v_means", C.c_void_p),
         ("m_rot", C.c_void_p), ("v_rot", C.c_void_p), ("step_means", C.c_void_p), ("step_rot", C.c_void_p),
+        ("radii", C.c_void_p), ("max_2D_radius", C.c_void_p), ("seen", C.c_void_p), ("block_counter", C.c_void_p),
     ]
 
 

@@ -114,9 +114,7 @@ __device__ __forceinline__ float adam_1(float p, float g, float &m, float &v, fl
     return p - lr_bc1 * (m / (sqrtf(v) * inv_sqrt_bc2 + eps));
 }
 
-__global__ void __launch_bounds__(256)
-gsd_track_update_kernel(GsdTrackUpdate u) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void gsd_track_update_body(const GsdTrackUpdate &u, int i) {
     if (i >= u.G) return;
     const float sm = *u.step_means + 1.f, sr = *u.step_rot + 1.f;
     const float lrm = u.lr_means / (1.f - powf(u.beta1, sm)), ism = 1.f / sqrtf(1.f - powf(u.beta2, sm));
@@ -147,6 +145,31 @@ gsd_track_update_kernel(GsdTrackUpdate u) {
     reinterpret_cast<float4 *>(u.m_rot)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
     reinterpret_cast<float4 *>(u.v_rot)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
 }
+
+// the per-Gaussian update + (optionally) the radii bookkeeping and the step advance in ONE launch: the last CTA to retire
+// advances the step counters (every thread has read them by then) and re-arms the counter
+__global__ void __launch_bounds__(256)
+gsd_track_update_fused_kernel(GsdTrackUpdate u) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < u.G && u.radii) {
+        const int r = u.radii[i];
+        const bool s = r > 0;
+        if (u.seen) u.seen[i] = s ? 1 : 0;
+        if (s) u.max_2D_radius[i] = fmaxf((float)r, u.max_2D_radius[i]);
+    }
+    gsd_track_update_body(u, i);
+    if (u.block_counter) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(u.block_counter, 1u) == gridDim.x - 1) {
+                *u.step_means += 1.0f;
+                if (u.step_rot != u.step_means) *u.step_rot += 1.0f;
+                *u.block_counter = 0u;
+            }
+        }
+    }
+}
 __global__ void gsd_track_update_advance_kernel(float *a, float *b) {
     *a += 1.0f;
     if (b != a) *b += 1.0f;
@@ -160,10 +183,13 @@ extern "C" int gsd_track_update(const GsdTrackUpdate *u, void *stream) {
         gsd_set_error("null pointer in GsdTrackUpdate");
         return GSD_ERR_INVALID;
     }
+    if (u->radii && !u->max_2D_radius) { gsd_set_error("radii given without max_2D_radius"); return GSD_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    gsd_track_update_kernel<<<(u->G + 255) / 256, 256, 0, st>>>(*u);
+    gsd_track_update_fused_kernel<<<(u->G + 255) / 256, 256, 0, st>>>(*u);
     GSD_LAUNCH_CHECK();
-    gsd_track_update_advance_kernel<<<1, 1, 0, st>>>(u->step_means, u->step_rot);
-    GSD_LAUNCH_CHECK();
+    if (!u->block_counter) {
+        gsd_track_update_advance_kernel<<<1, 1, 0, st>>>(u->step_means, u->step_rot);
+        GSD_LAUNCH_CHECK();
+    }
     return GSD_OK;
 }

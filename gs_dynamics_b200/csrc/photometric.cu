@@ -269,31 +269,34 @@ gsd_ssim_stats_kernel(int C, int H, int W, int seg_rows, int n_seg, int n_strip,
 
 // fixed-order final reduction per set of 3 channels: out[3*s + 0] = loss_s, [1] = mean|x-y|, [2] = mean SSIM;
 // out[3*n_sets] = sum_s set_weight[s] * loss_s
-__global__ void gsd_ssim_finish_kernel(int n_sets, int blocks_per_set, const float *__restrict__ block_sums, float inv_n,
-                                       float w_l1, float w_ssim, float sw0, float sw1, float *__restrict__ out) {
-    __shared__ double r0[256], r1[256];
-    float total = 0.f;
-    for (int s = 0; s < n_sets; ++s) {
+__global__ void __launch_bounds__(64)
+gsd_ssim_finish_kernel(int n_sets, int blocks_per_set, const float *__restrict__ block_sums, float inv_n,
+                       float w_l1, float w_ssim, float sw0, float sw1, float *__restrict__ out) {
+    // one warp per set: lane-strided double sums, fixed butterfly -> deterministic
+    __shared__ float set_loss[2];
+    const int s = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (s < n_sets) {
         double a = 0.0, b = 0.0;
-        for (int i = threadIdx.x; i < blocks_per_set; i += 256) {
-            a += block_sums[2 * ((size_t)s * blocks_per_set + i)];
-            b += block_sums[2 * ((size_t)s * blocks_per_set + i) + 1];
+        const float2 *bs = reinterpret_cast<const float2 *>(block_sums) + (size_t)s * blocks_per_set;
+#pragma unroll 4
+        for (int i = lane; i < blocks_per_set; i += 32) {
+            const float2 v = bs[i];
+            a += v.x; b += v.y;
         }
-        r0[threadIdx.x] = a; r1[threadIdx.x] = b;
-        __syncthreads();
-        for (int k = 128; k >= 1; k >>= 1) {
-            if (threadIdx.x < k) { r0[threadIdx.x] += r0[threadIdx.x + k]; r1[threadIdx.x] += r1[threadIdx.x + k]; }
-            __syncthreads();
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
         }
-        if (threadIdx.x == 0) {
-            float ml1 = (float)(r0[0] * inv_n), ms = (float)(r1[0] * inv_n);
-            float l = w_l1 * ml1 + w_ssim * (1.0f - ms);
+        if (lane == 0) {
+            const float ml1 = (float)(a * inv_n), ms = (float)(b * inv_n);
+            const float l = w_l1 * ml1 + w_ssim * (1.0f - ms);
             out[3 * s] = l; out[3 * s + 1] = ml1; out[3 * s + 2] = ms;
-            total += (s == 0 ? sw0 : sw1) * l;
+            set_loss[s] = l;
         }
-        __syncthreads();
     }
-    if (threadIdx.x == 0) out[3 * n_sets] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) out[3 * n_sets] = sw0 * set_loss[0] + (n_sets > 1 ? sw1 * set_loss[1] : 0.f);
 }
 
 // kernel 2: d loss / d rendered = gscale * set_weight * scale_c * ( w_l1*sign(x-y)/N - w_ssim/N * (conv(dmu) + 2x*conv(ds11) + y*conv(ds12)) )
@@ -479,7 +482,7 @@ extern "C" int gsd_photometric_forward(const GsdPhotometric *p, float *loss_out,
     GSD_LAUNCH_CHECK();
     const int per_set_c = C / p->n_sets;
     const int units_per_set = pl.n_seg * pl.n_strip * per_set_c;
-    gsd_ssim_finish_kernel<<<1, 256, 0, st>>>(p->n_sets, units_per_set, bs, 1.0f / (float)((size_t)per_set_c * H * W), p->w_l1,
+    gsd_ssim_finish_kernel<<<1, 64, 0, st>>>(p->n_sets, units_per_set, bs, 1.0f / (float)((size_t)per_set_c * H * W), p->w_l1,
                                               p->w_ssim, p->set_weight[0], p->set_weight[1], loss_out);
     GSD_LAUNCH_CHECK();
     return GSD_OK;

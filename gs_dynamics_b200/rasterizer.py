@@ -102,7 +102,7 @@ def raster_forward(settings, means3D, opacities, colors0, scales, rotations, col
 
     with torch.cuda.device(dev):
         st = _stream()
-        status = torch.zeros(_lib.GSD_STATUS_WORDS, dtype=torch.int32, device=dev)
+        status = torch.empty(_lib.GSD_STATUS_WORDS, dtype=torch.int32, device=dev)   # zeroed by the library (memset node)
         radii = torch.empty(G, dtype=torch.int32, device=dev)
         d = _lib.GsdRasterFwd()
         d.G, d.W, d.H, d.n_sets = G, W, H, n_sets

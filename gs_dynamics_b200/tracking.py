@@ -249,7 +249,7 @@ def update_seen(radius, variables):
     with torch.cuda.device(radius.device):
         _lib.check(_lib.lib().gsd_track_update_radii(G, radius.data_ptr(), variables['max_2D_radius'].data_ptr(),
                                                      seen.data_ptr(), _stream()), "gsd_track_update_radii")
-    variables['seen'] = seen.bool()
+    variables['seen'] = seen.view(torch.bool)
     return variables
 
 
@@ -532,6 +532,7 @@ class FusedTrackingStep(TrackingStep):
             self.rot = torch.empty_like(params['unnorm_rotations'])
             self.tstats = [target_stats(tg) for tg in self.targets]
         self.side = torch.cuda.Stream(device=params['means3D'].device)
+        self.block_counter = torch.zeros(1, dtype=torch.int32, device=params['means3D'].device)   # self-resetting (gsd_track_update)
         self.lr = {g['name']: float(g['lr']) for g in optimizer.param_groups}
 
     def set_target(self, cam_id, im, seg):
@@ -594,8 +595,12 @@ class FusedTrackingStep(TrackingStep):
             u.m_means, u.v_means = sm['exp_avg'].data_ptr(), sm['exp_avg_sq'].data_ptr()
             u.m_rot, u.v_rot = sr['exp_avg'].data_ptr(), sr['exp_avg_sq'].data_ptr()
             u.step_means, u.step_rot = sm['step'].data_ptr(), sr['step'].data_ptr()
+            # bookkeeping of get_loss (seen / max_2D_radius, train_utils.py:243-245) and the step advance ride in the same launch
+            seen = torch.empty(G, dtype=torch.uint8, device=x.device)
+            u.radii, u.max_2D_radius, u.seen = radii.data_ptr(), V['max_2D_radius'].data_ptr(), seen.data_ptr()
+            u.block_counter = self.block_counter.data_ptr()
             _lib.check(lib.gsd_track_update(C.byref(u), st), "gsd_track_update")
-            self.variables = update_seen(radii, V)
+            V['seen'] = seen.view(torch.bool)
             V['prior_losses'] = parts
             V['photometric_losses'] = ph
         return ph[6] + prior

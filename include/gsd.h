@@ -197,7 +197,9 @@ int gsd_adam_step(const GsdAdam *a, void *stream);
  * (train_utils.py:370-373): rotations = F.normalize(unnorm_rotations) (helpers.py:40), and the fused update
  *   g_means = ga + gb;  g_unnorm = normalize_backward(ga_rot + gb_rot);  Adam step on both groups
  * (the two gradient sources are the rasterizer backward and the physical priors). Step counters are device floats,
- * read as (*step + 1) and advanced by a trailing 1-thread kernel. */
+ * read as (*step + 1) and advanced once per call: by the last CTA to finish when block_counter (a zero-initialised,
+ * self-resetting device word owned by the caller) is given, else by a trailing 1-thread kernel.  radii / max_2D_radius /
+ * seen (all or none; seen may be NULL) fold the bookkeeping of gsd_track_update_radii into the same launch. */
 int gsd_track_normalize_rotations(int32_t G, const float *unnorm_rotations, float *rotations, void *stream);
 typedef struct {
     int32_t G;
@@ -207,6 +209,10 @@ typedef struct {
     const float *g_rot_a, *g_rot_b;       /* [G,4] each, w.r.t. the NORMALISED rotations; b may be NULL */
     float *m_means, *v_means, *m_rot, *v_rot;
     float *step_means, *step_rot;
+    const int32_t *radii;                 /* optional [G] */
+    float *max_2D_radius;                 /* optional [G] */
+    uint8_t *seen;                        /* optional [G] */
+    uint32_t *block_counter;              /* optional, see above */
 } GsdTrackUpdate;
 int gsd_track_update(const GsdTrackUpdate *u, void *stream);
 
