@@ -299,20 +299,69 @@ __device__ __forceinline__ Ptr cta_merge_sort(Ptr src, Ptr dst, int n, int tid, 
     return src;
 }
 
+// shared-memory variant: buffers addressed as sk[cur] / sk[cur ^ 1] (the compiler keeps LDS/STS instead of generic accesses),
+// four keys per thread searched in lockstep with a fixed-trip branchless lower bound (the searches of a round are independent,
+// so their shared-memory latencies overlap instead of adding up).  Returns the index of the buffer holding the result.
+__device__ __forceinline__ int cta_merge_sort_smem(unsigned long long (*sk)[SORT_SMEM_KEYS], int n, int tid) {
+    constexpr int KPT = 4;
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int g = wid; g * 32 < n; g += SORT_THREADS / 32) {
+        const int i = g * 32 + lane;
+        unsigned long long k = i < n ? sk[0][i] : ~0ull;
+        k = warp_sort32(k, lane);
+        if (i < n) sk[0][i] = k;
+    }
+    __syncthreads();
+    int cur = 0;
+    for (int run = 32; run < n; run <<= 1) {
+        for (int i0 = tid; i0 < n; i0 += KPT * SORT_THREADS) {
+            unsigned long long key[KPT];
+            int sib[KPT], len[KPT], lo[KPT], out[KPT];
+#pragma unroll
+            for (int u = 0; u < KPT; ++u) {
+                const int i = i0 + u * SORT_THREADS;
+                const bool v = i < n;
+                key[u] = v ? sk[cur][i] : 0ull;
+                const int r = i / run, base_self = r * run;
+                sib[u] = (r ^ 1) * run;
+                len[u] = v ? max(0, min(run, n - sib[u])) : 0;
+                out[u] = min(base_self, sib[u]) + (i - base_self);
+                lo[u] = 0;
+            }
+            for (int step = run; step >= 1; step >>= 1) {
+#pragma unroll
+                for (int u = 0; u < KPT; ++u) {
+                    const int idx = lo[u] + step - 1;
+                    if (idx < len[u] && sk[cur][sib[u] + idx] < key[u]) lo[u] += step;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < KPT; ++u)
+                if (i0 + u * SORT_THREADS < n) sk[cur ^ 1][out[u] + lo[u]] = key[u];
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    return cur;
+}
+
 // one CTA per tile: sort the tile's keys in place (the blend forward gathers the Gaussian data by sorted key)
 __global__ void __launch_bounds__(SORT_THREADS)
-gsd_tile_sort_kernel(const uint2 *__restrict__ ranges, uint64_t *__restrict__ keys, uint64_t *__restrict__ keys_tmp) {
+gsd_tile_sort_kernel(const uint2 *__restrict__ ranges, uint64_t *__restrict__ keys, uint64_t *__restrict__ keys_tmp, int n_tiles,
+                     int stride) {
     __shared__ unsigned long long sk[2][SORT_SMEM_KEYS];
     const int t = threadIdx.x;
-    const uint2 r = ranges[blockIdx.x];
+    // CTAs are dispatched in blockIdx order and the long lists sit on neighbouring tiles (the object): a stride permutation
+    // (stride coprime to n_tiles) spreads them over the SMs and over the waves instead of stacking four of them on one SM
+    const uint2 r = ranges[(int)(((long long)blockIdx.x * stride) % n_tiles)];
     const int n = (int)(r.y - r.x);
     if (n <= 1) return;
     unsigned long long *gk = reinterpret_cast<unsigned long long *>(keys) + r.x;
     if (n <= SORT_SMEM_KEYS) {
         for (int i = t; i < n; i += SORT_THREADS) sk[0][i] = gk[i];
         __syncthreads();
-        const unsigned long long *sorted = cta_merge_sort((unsigned long long *)sk[0], (unsigned long long *)sk[1], n, t, SORT_THREADS);
-        for (int i = t; i < n; i += SORT_THREADS) gk[i] = sorted[i];
+        const int res = cta_merge_sort_smem(sk, n, t);
+        for (int i = t; i < n; i += SORT_THREADS) gk[i] = sk[res][i];
     } else {
         unsigned long long *tmp = reinterpret_cast<unsigned long long *>(keys_tmp) + r.x;
         const unsigned long long *sorted = cta_merge_sort(gk, tmp, n, t, SORT_THREADS);
@@ -386,7 +435,11 @@ int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const Gs
     gsd_bin_kernel<true><<<b.n_bb, GSD_BIN_BLOCK, smem, st>>>(G, cam.gx, tiles, b.n_bb, g.tiles, g.rect, g.depth, b.table, b.ranges,
                                                                b.keys, g.slot_base, g.block_base);
     GSD_LAUNCH_CHECK();
-    gsd_tile_sort_kernel<<<tiles, SORT_THREADS, 0, st>>>(b.ranges, b.keys, b.keys_tmp);
+    int stride = (int)(0.6180339887 * tiles) | 1;
+    auto gcd = [](int a, int c) { while (c) { int t2 = a % c; a = c; c = t2; } return a; };
+    while (stride > 1 && gcd(stride, tiles) != 1) stride += 2;
+    if (tiles < 4 || gcd(stride, tiles) != 1) stride = 1;
+    gsd_tile_sort_kernel<<<tiles, SORT_THREADS, 0, st>>>(b.ranges, b.keys, b.keys_tmp, tiles, stride);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
