@@ -394,6 +394,33 @@ def run_gnn_ours(device, steps=50, warmup=5, n_obj=2000, seed=1):
             "e2e": {"value": steps / dt_e2e, "unit": "steps/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": n_obj * 12}}
 
 
+def run_gnn_batched(device, B=1000, n_obj=100, steps=10, warmup=3):
+    """MPPI-style batched rollout (plan.py:25-154: bsz = 1000 perturbed action samples, ~100 particles + tool, graph rebuilt
+    every step): sample-steps per second of one CUDA-graph step over the whole batch."""
+    from gs_dynamics_b200 import gnn, workloads as GO
+    cfg = GO.sloth_cfg(512)
+    model = gnn.DynamicsPredictor(dict(cfg), device).to(device).eval()
+    model.load_state_dict(GO.make_state_dict(cfg, 0, head_scale=1e-3))
+    gi = GO.make_graph_inputs(n_obj, 7, "sloth")
+    p0, eef = gi["state"][0, :, :n_obj].to(device), gi["state"][0, :, n_obj:].to(device)
+    ro = gnn.GnnRollout(model, p0, eef, 0.075, 5, True, use_graph=True, batch=B)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    deltas = (0.005 * torch.randn(B, 3, generator=g)).to(device)
+    deltas[:, 2] = 0
+    for _ in range(warmup):
+        ro.step(deltas)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ro.step(deltas)
+    e1.record()
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) * 1e-3
+    return {"metric": "MPPI batched rollout sample-steps/sec", "value": B * steps / dt, "unit": "sample-steps/s", "ms_per_step": 1e3 * dt / steps,
+            "config": {"workload": "plan.py dynamics(): %d action samples x (%d particles + tool), topk 5, connect_all, nf 512, graph rebuilt every step" % (B, n_obj)}}
+
+
 def time_skinning(device, model, ro, n_gauss=100000, iters=20):
     """The step after the GNN (interpolate_motions): 100k Gaussians skinned from the 2000 particles of the
     rollout graph.  Device time per call, L2 flushed between calls; CPU: the oracle restatement on a 5k-Gaussian sample."""
@@ -543,6 +570,7 @@ def main():
                 try:
                     g = run_gnn_ours(torch.device("cuda", 0))
                     g["cpu_baseline"] = run_gnn_cpu()
+                    g["mppi_batch"] = run_gnn_batched(torch.device("cuda", 0))
                     line["gnn"] = g
                     if "error" not in line.get("gnn_train", {"error": 1}):
                         line["gnn_train"]["cpu_baseline"] = run_gnn_train_cpu()

@@ -559,27 +559,30 @@ def downsample_vertices(xyz, max_nobj, fps_radius, start_idx=None):
 # without the Gaussian skinning which is a "next" row): edges -> model -> history shift
 # ----------------------------------------------------------------------------------------------------
 class GnnRollout:
-    """Autoregressive rollout with static shapes (CUDA-graph capturable): nobj object particles + 1 tool particle."""
+    """Autoregressive rollout with static shapes (CUDA-graph capturable): nobj object particles + 1 tool particle.
+    batch > 1 rolls `batch` action samples out of the same initial state at once (the MPPI planner's inner loop,
+    /root/reference/src/real_world/plan.py:25-154: bsz perturbed action sequences, graph rebuilt every step)."""
 
-    def __init__(self, model, particle_pos, eef_pos, adj_thresh, topk, connect_all, use_graph=True):
+    def __init__(self, model, particle_pos, eef_pos, adj_thresh, topk, connect_all, use_graph=True, batch=1):
         self.model = model
         dev = particle_pos.device
         n_his = model.model_config['n_his']
         self.nobj = particle_pos.shape[-2]
+        self.B = B = int(batch)
         N = self.nobj + 1
-        self.states = torch.zeros((1, n_his, N, 3), device=dev)
-        self.states[0, :, :self.nobj] = particle_pos          # [nobj,3] or a history [n_his,nobj,3]
-        self.states[0, :, self.nobj:] = eef_pos.reshape(-1, 1, 3) if eef_pos.dim() > 1 else eef_pos
-        self.action = torch.zeros((1, N, 3), device=dev)
-        self.attrs = torch.zeros((1, N, 2), device=dev)
+        self.states = torch.zeros((B, n_his, N, 3), device=dev)
+        self.states[:, :, :self.nobj] = particle_pos          # [nobj,3] or a history [n_his,nobj,3]
+        self.states[:, :, self.nobj:] = eef_pos.reshape(-1, 1, 3) if eef_pos.dim() > 1 else eef_pos
+        self.action = torch.zeros((B, N, 3), device=dev)
+        self.attrs = torch.zeros((B, N, 2), device=dev)
         self.attrs[:, :self.nobj, 0] = 1.
         self.attrs[:, self.nobj:, 1] = 1.
-        self.p_instance = torch.ones((1, self.nobj, 1), device=dev)
-        self.state_mask = torch.ones((1, N), dtype=torch.bool, device=dev)
-        self.eef_mask = torch.zeros((1, N), dtype=torch.bool, device=dev)
+        self.p_instance = torch.ones((B, self.nobj, 1), device=dev)
+        self.state_mask = torch.ones((B, N), dtype=torch.bool, device=dev)
+        self.eef_mask = torch.zeros((B, N), dtype=torch.bool, device=dev)
         self.eef_mask[:, self.nobj] = True
         self.adj_thresh, self.topk, self.connect_all = adj_thresh, topk, connect_all
-        self.eef_delta = torch.zeros(3, device=dev)
+        self.eef_delta = torch.zeros(3, device=dev) if B == 1 else torch.zeros((B, 3), device=dev)
         self.use_graph, self.graph, self.pred = use_graph, None, None
         self.gs_xyz = self.gs_quat = None
 
@@ -588,13 +591,15 @@ class GnnRollout:
         (interpolate_motions, dynamics_module.py:150-156); `gs_xyz` / `gs_quat` hold the current values.  Call before the first step."""
         if self.graph is not None:
             raise RuntimeError("attach_gaussians must be called before the first step")
+        if self.B != 1:
+            raise ValueError("Gaussian skinning follows a single rollout (batch == 1)")
         self.gs_xyz, self.gs_quat = xyz.detach().clone().float().contiguous(), quat.detach().clone().float().contiguous()
 
     @torch.no_grad()
     def _step_impl(self):
         # tool moves by eef_delta; history shift of the tool row; action row of the tool
-        new_eef = self.states[0, -1, self.nobj] + self.eef_delta
-        self.action[0, self.nobj] = self.eef_delta
+        new_eef = self.states[:, -1, self.nobj] + self.eef_delta          # [B,3]
+        self.action[:, self.nobj] = self.eef_delta
         edges = construct_edges_index(self.states[:, -1], self.adj_thresh, self.state_mask, self.eef_mask, topk=self.topk,
                                       connect_all=self.connect_all, n_tool=1)
         pred, _ = self.model(self.states, self.attrs, edges, None, self.p_instance, action=self.action)
@@ -604,8 +609,8 @@ class GnnRollout:
             x, q, _ = interpolate_motions(bones, pred[0] - bones, edges, self.gs_xyz, quat=self.gs_quat, return_weights=False)
             self.gs_xyz.copy_(x)
             self.gs_quat.copy_(q)
-        nxt = torch.cat([pred[0], new_eef[None]], 0)
-        self.states.copy_(torch.cat([self.states[:, 1:], nxt[None, None]], 1))
+        nxt = torch.cat([pred, new_eef[:, None]], 1)                      # [B,N,3]
+        self.states.copy_(torch.cat([self.states[:, 1:], nxt[:, None]], 1))
         return pred
 
     def step(self, eef_delta=None):

@@ -317,3 +317,37 @@ def test_train_iteration_decreases_loss_and_bucket_aliases_grads():
     assert losses[-1] < losses[0]
     assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in m.parameters())
     assert float(bucket.flat.abs().sum()) > 0
+
+
+def test_batched_rollout_matches_single_rollouts_and_oracle():
+    """MPPI-style batch (plan.py:25-154): B action samples from one initial state, graph rebuilt every step, vs B separate
+    single rollouts (same kernels, different batch shapes: fp32 GEMM tiling may differ -> 1e-5) and vs the dense oracle."""
+    from gs_dynamics_b200 import gnn
+    cfg = GO.sloth_cfg(128)
+    m = _model(cfg, 4)
+    sd = GO.make_state_dict(cfg, 4)
+    gi = GO.make_graph_inputs(90, 4, "sloth")
+    n_obj = 90
+    p0, eef = gi["state"][0, :, :n_obj].cuda(), gi["state"][0, :, n_obj:].cuda()
+    deltas = torch.tensor([[0.005, 0.0, 0.0], [0.0, 0.004, 0.0], [-0.003, 0.002, 0.0]], device="cuda")
+    B, steps = deltas.shape[0], 3
+    ro = gnn.GnnRollout(m, p0, eef, 0.075, 5, True, use_graph=True, batch=B)
+    batched = [ro.step(deltas).clone() for _ in range(steps)]
+    for b in range(B):
+        r1 = gnn.GnnRollout(m, p0, eef, 0.075, 5, True, use_graph=False)
+        for t in range(steps):
+            single = r1.step(deltas[b])
+            assert float((batched[t][b] - single[0]).abs().max()) < 1e-5
+    # oracle: dense one-hot formulation, step by step on the CPU for sample 1
+    b = 1
+    state = gi["state"].clone()
+    for t in range(steps):
+        action = torch.zeros(1, n_obj + 1, 3)
+        action[0, n_obj] = deltas[b].cpu()
+        recv, send = GO.construct_edges(state[0, -1], 0.075, gi["state_mask"], gi["eef_mask"], 5, True)
+        Rr, Rs = GO.one_hot_edges(recv, send, n_obj + 1)
+        with torch.no_grad():
+            pos, _ = GO.forward(sd, cfg, state, gi["attrs"], Rr[None], Rs[None], gi["p_instance"], action)
+        assert float((batched[t][b].cpu() - pos[0]).abs().max()) < 2e-5
+        nxt = torch.cat([pos[0], (state[0, -1, n_obj] + deltas[b].cpu())[None]], 0)
+        state = torch.cat([state[:, 1:], nxt[None, None]], 1)
