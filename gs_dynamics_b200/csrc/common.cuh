@@ -65,7 +65,8 @@ struct GsdBinWs {
     uint2 *ranges;       // per tile [start,end) clipped to capacity
     int32_t *chunk_ptr;  // [tiles+1] exclusive scan of chunks per tile
     int32_t *item_tile;  // [max_items] tile of each work item
-    int32_t *counters;   // [8] 0: n_items
+    int32_t *counters;   // [8] 0: n_items, 1: tiles that need sorting
+    int32_t *sort_order; // [tiles] tiles with >= 2 instances, longest lists first (three length classes)
     uint64_t *keys;      // [capacity] (depth bits << 32 | gaussian id), grouped by tile, unsorted inside a tile
     uint64_t *keys_tmp;  // [capacity] merge-sort ping-pong buffer for tile lists that do not fit shared memory
     float4 *records;     // 4 SoA planes of [capacity] float4: packed per-instance records sorted by (tile, depth, id)

@@ -59,6 +59,7 @@ int gsd_carve_bin(int G, int64_t capacity, int tiles, void *base, GsdBinWs *ws) 
     ws->chunk_ptr = (int32_t *)take((size_t)(tiles + 1) * 4);
     ws->item_tile = (int32_t *)take((size_t)ws->max_items * 4);
     ws->counters = (int32_t *)take(8 * 4);
+    ws->sort_order = (int32_t *)take((size_t)tiles * 4);
     ws->keys = (uint64_t *)take(n * 8);
     ws->keys_tmp = (uint64_t *)take(n * 8);
     ws->records = (float4 *)take(n * GSD_REC_FLOATS * 4);
@@ -176,8 +177,9 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 gsd_bin_scan_kernel(int n_pre_blocks, int n_tiles, int64_t capacity, int max_items, uint32_t *__restrict__ block_sum,
                     uint32_t *__restrict__ block_base, int32_t *__restrict__ tile_base, uint2 *__restrict__ ranges,
                     int32_t *__restrict__ chunk_ptr, int32_t *__restrict__ item_tile, int32_t *__restrict__ counters,
-                    int32_t *__restrict__ status) {
+                    int32_t *__restrict__ sort_order, int32_t *__restrict__ status) {
     __shared__ int s_warp[33];
+    __shared__ int s_cls[3], s_fill[3];
     const int t = threadIdx.x;
     for (int i = t; i < n_pre_blocks; i += SCAN_THREADS) block_base[i] = block_sum[i];
     __syncthreads();
@@ -196,10 +198,28 @@ gsd_bin_scan_kernel(int n_pre_blocks, int n_tiles, int64_t capacity, int max_ite
         ranges[i] = make_uint2((uint32_t)s, (uint32_t)e);
     }
     __syncthreads();
+    if (t < 3) { s_cls[t] = 0; s_fill[t] = 0; }
+    __syncthreads();
+    // work list of the per-tile sort: only tiles with >= 2 instances, the longest lists first (the sort of a 2000-key tile
+    // is the critical path of that kernel; the order inside a class only affects scheduling, never results)
+    auto cls_of = [](int n) { return n > 1024 ? 0 : (n > 256 ? 1 : 2); };
     for (int i = t; i < n_tiles; i += SCAN_THREADS) {
         const uint2 r = ranges[i];
-        chunk_ptr[i] = (int)((r.y - r.x + GSD_CHUNK - 1) / GSD_CHUNK);
+        const int n = (int)(r.y - r.x);
+        chunk_ptr[i] = (n + GSD_CHUNK - 1) / GSD_CHUNK;
+        if (n >= 2) atomicAdd(&s_cls[cls_of(n)], 1);
     }
+    __syncthreads();
+    for (int i = t; i < n_tiles; i += SCAN_THREADS) {
+        const uint2 r = ranges[i];
+        const int n = (int)(r.y - r.x);
+        if (n >= 2) {
+            const int c = cls_of(n);
+            const int base = (c > 0 ? s_cls[0] : 0) + (c > 1 ? s_cls[1] : 0);
+            sort_order[base + atomicAdd(&s_fill[c], 1)] = i;
+        }
+    }
+    if (t == 0) counters[1] = s_cls[0] + s_cls[1] + s_cls[2];
     __syncthreads();
     const int n_items = cta_exclusive_scan(chunk_ptr, n_tiles, s_warp);
     if (t == 0) {
@@ -347,13 +367,13 @@ __device__ __forceinline__ int cta_merge_sort_smem(unsigned long long (*sk)[SORT
 
 // one CTA per tile: sort the tile's keys in place (the blend forward gathers the Gaussian data by sorted key)
 __global__ void __launch_bounds__(SORT_THREADS)
-gsd_tile_sort_kernel(const uint2 *__restrict__ ranges, uint64_t *__restrict__ keys, uint64_t *__restrict__ keys_tmp, int n_tiles,
-                     int stride) {
+gsd_tile_sort_kernel(const uint2 *__restrict__ ranges, uint64_t *__restrict__ keys, uint64_t *__restrict__ keys_tmp,
+                     const int32_t *__restrict__ sort_order, const int32_t *__restrict__ counters) {
     __shared__ unsigned long long sk[2][SORT_SMEM_KEYS];
     const int t = threadIdx.x;
-    // CTAs are dispatched in blockIdx order and the long lists sit on neighbouring tiles (the object): a stride permutation
-    // (stride coprime to n_tiles) spreads them over the SMs and over the waves instead of stacking four of them on one SM
-    const uint2 r = ranges[(int)(((long long)blockIdx.x * stride) % n_tiles)];
+    // static grid (CUDA-graph friendly); only the first counters[1] CTAs have work: the tiles with >= 2 keys, longest first
+    if ((int)blockIdx.x >= counters[1]) return;
+    const uint2 r = ranges[sort_order[blockIdx.x]];
     const int n = (int)(r.y - r.x);
     if (n <= 1) return;
     unsigned long long *gk = reinterpret_cast<unsigned long long *>(keys) + r.x;
@@ -427,7 +447,7 @@ int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const Gs
     gsd_bin_tile_sum_kernel<<<(tiles + 7) / 8, 256, 0, st>>>(tiles, b.n_bb, b.table, b.tile_base);
     GSD_LAUNCH_CHECK();
     gsd_bin_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(n_pre, tiles, cap, b.max_items, g.block_sum, g.block_base, b.tile_base,
-                                                     b.ranges, b.chunk_ptr, b.item_tile, b.counters, a->status);
+                                                     b.ranges, b.chunk_ptr, b.item_tile, b.counters, b.sort_order, a->status);
     GSD_LAUNCH_CHECK();
     gsd_bin_tile_scan_kernel<<<(tiles + 7) / 8, 256, 0, st>>>(tiles, b.n_bb, b.table, b.tile_base);
     GSD_LAUNCH_CHECK();
@@ -435,11 +455,7 @@ int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const Gs
     gsd_bin_kernel<true><<<b.n_bb, GSD_BIN_BLOCK, smem, st>>>(G, cam.gx, tiles, b.n_bb, g.tiles, g.rect, g.depth, b.table, b.ranges,
                                                                b.keys, g.slot_base, g.block_base);
     GSD_LAUNCH_CHECK();
-    int stride = (int)(0.6180339887 * tiles) | 1;
-    auto gcd = [](int a, int c) { while (c) { int t2 = a % c; a = c; c = t2; } return a; };
-    while (stride > 1 && gcd(stride, tiles) != 1) stride += 2;
-    if (tiles < 4 || gcd(stride, tiles) != 1) stride = 1;
-    gsd_tile_sort_kernel<<<tiles, SORT_THREADS, 0, st>>>(b.ranges, b.keys, b.keys_tmp, tiles, stride);
+    gsd_tile_sort_kernel<<<tiles, SORT_THREADS, 0, st>>>(b.ranges, b.keys, b.keys_tmp, b.sort_order, b.counters);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
