@@ -44,17 +44,19 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  nvidia-smi needs ~a second before its first line, so
+    the process is started before the warm-up; mark() / stop() bracket the timed region and only the lines read between them
+    are used (if the region was shorter than one sampling period, the closest line on either side is used and flagged)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.proc, self.lines, self.t0 = gpu_index, None, [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -62,19 +64,35 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def wait_first(self, timeout=5.0):
+        t = time.time()
+        while self.proc and not self.lines and time.time() - t < timeout:
+            time.sleep(0.05)
+
+    def mark(self):
+        self.t0 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        t1 = time.time()
+        time.sleep(0.06)   # let the line that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [ln for ts, ln in self.lines if t0 <= ts <= t1 + 0.06]
+        note = None
+        if not inside and self.lines:
+            inside = [min(self.lines, key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))[1]]
+            note = "timed region shorter than one sampling period: closest sample"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -85,8 +103,11 @@ class ClockSampler:
             for n, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -184,12 +205,15 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (value)
-    for _ in range(args.warmup):
-        step_obj.step(rng.randrange(n_cams))
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_obj.step(rng.randrange(n_cams))
+    if rank == 0:
+        sampler.wait_first()
+    barrier()
+    sampler.mark()
     evs = []
     t_wall0 = time.time()
     for _ in range(args.steps):
@@ -537,7 +561,7 @@ def run_gnn_train_cpu(B=4, n_obj=100, n_future=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)  # one reference frame = 2000 iterations (train_gs.py:25)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gaussians", type=int, default=50000)
