@@ -102,7 +102,8 @@ EXPORTS = [
     "gsd_last_error", "gsd_version", "gsd_launch_count", "gsd_raster_backward_stage",
     "gsd_raster_workspace_bytes", "gsd_raster_count_instances", "gsd_raster_forward", "gsd_raster_backward",
     "gsd_raster_mark_visible",
-    "gsd_photometric_workspace_bytes", "gsd_photometric_forward", "gsd_photometric_backward",
+    "gsd_photometric_workspace_bytes", "gsd_photometric_forward", "gsd_photometric_backward", "gsd_photometric_stats",
+    "gsd_photometric_reduce",
     "gsd_track_losses_workspace_bytes", "gsd_track_losses_fwd_bwd", "gsd_track_pack_edges", "gsd_adam_step", "gsd_track_update_radii",
     "gsd_track_normalize_rotations", "gsd_track_update", "gsd_photometric_target_stats",
     "gsd_gnn_edges_workspace_bytes", "gsd_gnn_build_edges", "gsd_gnn_edge_inputs", "gsd_gnn_aggregate_workspace_bytes",
@@ -130,6 +131,8 @@ def lib():
     l.gsd_raster_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_photometric_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
     l.gsd_photometric_forward.argtypes = [C.POINTER(GsdPhotometric), C.c_void_p, C.c_void_p]
+    l.gsd_photometric_stats.argtypes = [C.POINTER(GsdPhotometric), C.c_void_p]
+    l.gsd_photometric_reduce.argtypes = [C.POINTER(GsdPhotometric), C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_photometric_backward.argtypes = [C.POINTER(GsdPhotometric), C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_photometric_target_stats.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_track_normalize_rotations.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -271,7 +271,7 @@ gsd_ssim_stats_kernel(int C, int H, int W, int seg_rows, int n_seg, int n_strip,
 // out[3*n_sets] = sum_s set_weight[s] * loss_s
 __global__ void __launch_bounds__(64)
 gsd_ssim_finish_kernel(int n_sets, int blocks_per_set, const float *__restrict__ block_sums, float inv_n,
-                       float w_l1, float w_ssim, float sw0, float sw1, float *__restrict__ out) {
+                       float w_l1, float w_ssim, float sw0, float sw1, const float *__restrict__ add, float *__restrict__ out) {
     // one warp per set: lane-strided double sums, fixed butterfly -> deterministic
     __shared__ float set_loss[2];
     const int s = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -296,7 +296,11 @@ gsd_ssim_finish_kernel(int n_sets, int blocks_per_set, const float *__restrict__
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) out[3 * n_sets] = sw0 * set_loss[0] + (n_sets > 1 ? sw1 * set_loss[1] : 0.f);
+    if (threadIdx.x == 0) {
+        const float total = sw0 * set_loss[0] + (n_sets > 1 ? sw1 * set_loss[1] : 0.f);
+        out[3 * n_sets] = total;
+        if (add) out[3 * n_sets + 1] = total + *add;
+    }
 }
 
 // kernel 2: d loss / d rendered = gscale * set_weight * scale_c * ( w_l1*sign(x-y)/N - w_ssim/N * (conv(dmu) + 2x*conv(ds11) + y*conv(ds12)) )
@@ -457,11 +461,10 @@ static void ph_launch_stats(const PhPlan &pl, cudaStream_t st, int C, int H, int
                                                                          aff, y_mu, y_s22, dmu, ds11, ds12, us);
 }
 
-// loss_out: per set {loss, mean|x-y|, mean SSIM}, then the weighted total  (3*n_sets + 1 floats)
-extern "C" int gsd_photometric_forward(const GsdPhotometric *p, float *loss_out, void *stream) {
+// statistics pass only: per-pixel SSIM partial maps + per-warp partial sums into ws (what the gradient pass needs)
+extern "C" int gsd_photometric_stats(const GsdPhotometric *p, void *stream) {
     int rc;
     if ((rc = ph_check(p))) return rc;
-    if (!loss_out) { gsd_set_error("null loss_out"); return GSD_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     const int C = p->C, H = p->H, W = p->W;
     size_t n = (size_t)C * H * W;
@@ -480,12 +483,34 @@ extern "C" int gsd_photometric_forward(const GsdPhotometric *p, float *loss_out,
         ph_launch_stats<0>(pl, st, C, H, W, win, p->x, p->y, p->affine_log_scale, p->affine_shift, aff, nullptr, nullptr, dmu, ds11,
                            ds12, bs);
     GSD_LAUNCH_CHECK();
+    return GSD_OK;
+}
+
+// fixed-order reduction of the partial sums left by gsd_photometric_stats.  loss_out: per set {loss, mean|x-y|, mean SSIM},
+// then the weighted total (3*n_sets + 1 floats); with add != NULL one more float: total + *add (e.g. the prior losses, so
+// that the iteration's loss needs no further kernel).  May run on another stream than the gradient pass: it only reads ws.
+extern "C" int gsd_photometric_reduce(const GsdPhotometric *p, const float *add, float *loss_out, void *stream) {
+    int rc;
+    if ((rc = ph_check(p))) return rc;
+    if (!loss_out) { gsd_set_error("null loss_out"); return GSD_ERR_INVALID; }
+    const int C = p->C, H = p->H, W = p->W;
+    size_t n = (size_t)C * H * W;
+    const float *bs = (const float *)((const char *)p->ws + 3 * gsd_align_up(n * 4));
+    const PhPlan pl = ph_plan(C, H, W);
     const int per_set_c = C / p->n_sets;
     const int units_per_set = pl.n_seg * pl.n_strip * per_set_c;
-    gsd_ssim_finish_kernel<<<1, 64, 0, st>>>(p->n_sets, units_per_set, bs, 1.0f / (float)((size_t)per_set_c * H * W), p->w_l1,
-                                              p->w_ssim, p->set_weight[0], p->set_weight[1], loss_out);
+    gsd_ssim_finish_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(p->n_sets, units_per_set, bs, 1.0f / (float)((size_t)per_set_c * H * W),
+                                                                 p->w_l1, p->w_ssim, p->set_weight[0], p->set_weight[1], add, loss_out);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
+}
+
+// loss_out: per set {loss, mean|x-y|, mean SSIM}, then the weighted total  (3*n_sets + 1 floats)
+extern "C" int gsd_photometric_forward(const GsdPhotometric *p, float *loss_out, void *stream) {
+    int rc;
+    if (!loss_out) { gsd_set_error("null loss_out"); return GSD_ERR_INVALID; }
+    if ((rc = gsd_photometric_stats(p, stream))) return rc;
+    return gsd_photometric_reduce(p, nullptr, loss_out, stream);
 }
 
 // window statistics of a target image, computed once and passed as GsdPhotometric.y_mu / y_s22 on later calls

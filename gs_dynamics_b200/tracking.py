@@ -576,10 +576,22 @@ class FusedTrackingStep(TrackingStep):
             color, radii, _, state = R.raster_forward(data['cam'], x.detach(), self.opac, self.rgb, self.scales, self.rot,
                                                       colors1=self.seg, capacity=capacity)
             ws = _ph_workspace(color)
-            ph = torch.empty(7, dtype=torch.float32, device=x.device)
+            ph = torch.empty(8, dtype=torch.float32, device=x.device)
             d = _ph_desc(color, tgt, 2, 0.8, 0.2, (self.w['weight_im'], self.w['weight_seg']), ws,
                          affine=(P['cam_m'][cid], P['cam_c'][cid]), y_stats=tst)
-            _lib.check(lib.gsd_photometric_forward(C.byref(d), ph.data_ptr(), st), "gsd_photometric_forward")
+            _lib.check(lib.gsd_photometric_stats(C.byref(d), st), "gsd_photometric_stats")
+            # the scalar reduction (and the addition of the prior losses: ph[7] is the iteration's loss) is not needed by the
+            # gradient pass: it joins the side branch instead of sitting on the critical path
+            stats_done = torch.cuda.Event()
+            stats_done.record(main)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(stats_done)
+                _lib.check(lib.gsd_photometric_reduce(C.byref(d), prior.data_ptr(), ph.data_ptr(), C.c_void_p(self.side.cuda_stream)),
+                           "gsd_photometric_reduce")
+                loss_done = torch.cuda.Event()
+                loss_done.record(self.side)
+            for tns in (ph, ws, color, tgt):
+                tns.record_stream(self.side)
             dL = torch.empty_like(color)
             _lib.check(lib.gsd_photometric_backward(C.byref(d), None, dL.data_ptr(), st), "gsd_photometric_backward")
             g = R.raster_backward(state, dL, need_means2D=False, geom_only=True)
@@ -600,10 +612,11 @@ class FusedTrackingStep(TrackingStep):
             u.radii, u.max_2D_radius, u.seen = radii.data_ptr(), V['max_2D_radius'].data_ptr(), seen.data_ptr()
             u.block_counter = self.block_counter.data_ptr()
             _lib.check(lib.gsd_track_update(C.byref(u), st), "gsd_track_update")
+            main.wait_event(loss_done)
             V['seen'] = seen.view(torch.bool)
             V['prior_losses'] = parts
-            V['photometric_losses'] = ph
-        return ph[6] + prior
+            V['photometric_losses'] = ph[:7]
+        return ph[7]
 
 
 class _NullCtx:

@@ -139,6 +139,10 @@ typedef struct {
 } GsdPhotometric;
 int gsd_photometric_workspace_bytes(int32_t C, int32_t H, int32_t W, size_t *bytes);
 int gsd_photometric_forward(const GsdPhotometric *p, float *loss_out, void *stream);
+/* the two halves of gsd_photometric_forward: the statistics pass the gradient needs, and the scalar reduction, which only
+ * reads ws and may run on another stream.  add (nullable device scalar): loss_out gets one more float, total + *add. */
+int gsd_photometric_stats(const GsdPhotometric *p, void *stream);
+int gsd_photometric_reduce(const GsdPhotometric *p, const float *add, float *loss_out, void *stream);
 /* conv(y), conv(y*y) with the SSIM window: constant per target image, computed once per camera and frame */
 int gsd_photometric_target_stats(int32_t C, int32_t H, int32_t W, const float *y, float *y_mu, float *y_s22, void *stream);
 /* grad = (gscale_ptr ? *gscale_ptr : 1) * set_weight[set] * d loss_set / d x_rendered (before the affine) */
