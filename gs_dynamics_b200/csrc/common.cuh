@@ -156,6 +156,12 @@ __device__ __forceinline__ float gsd_power(float A, float B, float C, float dx, 
     return __fmaf_rn(-0.5f, s, -__fmul_rn(b1, dy));
 }
 __device__ __forceinline__ float gsd_gauss(float power) { return __expf(power); }
+// MUFU.RCP without the range fix-ups of __fdividef (callers guarantee a normal, non-huge argument)
+__device__ __forceinline__ float gsd_rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 // Transposed butterfly: N per-lane values are summed over the 32 lanes with ~N shuffles; afterwards the lane with
 // holder_id() == k holds the warp total of value k in v[0].

@@ -11,8 +11,8 @@ __global__ void __launch_bounds__(256)
 gsd_preprocess_bwd_kernel(int G, GsdCam cam, int64_t capacity, const float *__restrict__ means3D,
                           const float *__restrict__ scales, const float *__restrict__ rotations,
                           const int32_t *__restrict__ radii, const uint32_t *__restrict__ slot_base,
-                          const uint32_t *__restrict__ tiles, const float4 *__restrict__ partials,
-                          float *__restrict__ dmeans3D, float *__restrict__ dmeans2D, float *__restrict__ dcolors0,
+                          const uint32_t *__restrict__ tiles, const float4 *__restrict__ conic_o,
+                          const float4 *__restrict__ partials, float *__restrict__ dmeans3D, float *__restrict__ dmeans2D, float *__restrict__ dcolors0,
                           float *__restrict__ dcolors1, float *__restrict__ dopac, float *__restrict__ dscales,
                           float *__restrict__ drot) {
     __shared__ float sVP[32];
@@ -41,10 +41,19 @@ gsd_preprocess_bwd_kernel(int G, GsdCam cam, int64_t capacity, const float *__re
             }
         }
     }
-    // layout of a partial record: colours[CH], mean2D.x, mean2D.y, conic.a, conic.b(half), conic.c, opacity
+    // layout of a partial record: colours[CH], five geometry MOMENTS, opacity.  With s = dL/dG * G per (pixel, instance) and
+    // d = centre - pixel, the blend backward accumulates M1 = sum s dx, M2 = sum s dy, M3 = sum s dx^2, M4 = sum s dx dy,
+    // M5 = sum s dy^2; the conic is per Gaussian, so the map to dL/dmean2D and dL/dconic is applied once here instead of
+    // per (pixel, instance) there:  dL/dmean2D = -(W/2) (A M1 + B M2), -(H/2) (C M2 + B M1);  dL/dconic = -1/2 (M3, M4, M5)
     constexpr int OG = GEOM ? 0 : CH;
-    float dm2x = acc[OG], dm2y = acc[OG + 1];
-    float dca = acc[OG + 2], dcb = acc[OG + 3], dcc = acc[OG + 4];
+    float dm2x = 0.f, dm2y = 0.f, dca = 0.f, dcb = 0.f, dcc = 0.f;
+    if (vis) {
+        const float4 co = conic_o[i];
+        const float M1 = acc[OG], M2 = acc[OG + 1];
+        dm2x = -(0.5f * cam.W) * (co.x * M1 + co.y * M2);
+        dm2y = -(0.5f * cam.H) * (co.z * M2 + co.y * M1);
+        dca = -0.5f * acc[OG + 2]; dcb = -0.5f * acc[OG + 3]; dcc = -0.5f * acc[OG + 4];
+    }
     if (!GEOM) {
         if (dcolors0) { dcolors0[3 * i] = acc[0]; dcolors0[3 * i + 1] = acc[1]; dcolors0[3 * i + 2] = acc[2]; }
         if (CH == 6 && dcolors1) { dcolors1[3 * i] = acc[3]; dcolors1[3 * i + 1] = acc[4]; dcolors1[3 * i + 2] = acc[5]; }
@@ -163,7 +172,7 @@ int gsd_launch_preprocess_bwd(int G, const GsdCam &cam, const GsdRasterBwd *a, c
     if (G == 0) return GSD_OK;
     const GsdRasterFwd &f = a->fwd;
     int blocks = (G + 255) / 256;
-#define GSD_PB_ARGS G, cam, f.capacity, f.means3D, f.scales, f.rotations, f.radii, g.slot_base, g.tiles, (const float4 *)a->partial_ws, \
+#define GSD_PB_ARGS G, cam, f.capacity, f.means3D, f.scales, f.rotations, f.radii, g.slot_base, g.tiles, g.conic_o, (const float4 *)a->partial_ws, \
         a->dL_dmeans3D, a->dL_dmeans2D, a->dL_dcolors0, a->dL_dcolors1, a->dL_dopacities, a->dL_dscales, a->dL_drotations
     if (geom_only) {
         if (f.n_sets == 1) gsd_preprocess_bwd_kernel<3, true><<<blocks, 256, 0, st>>>(GSD_PB_ARGS);

@@ -477,7 +477,7 @@ __global__ void __launch_bounds__((GSD_CWARPS + 1) * 32, 5)
 gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
     constexpr int NV = GEOM ? 5 : CH + 6; // [colours,] mean2D(2), conic(3) [, opacity(1)]
     constexpr int OG = GEOM ? 0 : CH;     // offset of the geometry values inside a partial record
-    constexpr int S = (GEOM || CH == 3) ? 3 : 2; // ring of per-warp partial-sum stages (static shared memory budget)
+    constexpr int S = GEOM ? 4 : (CH == 3 ? 3 : 2); // ring of per-warp partial-sum stages (static shared memory budget); 4 = a whole chunk: consumers never wait for the flusher
     using IS = ItemState<CH>;
     __shared__ __align__(128) float4 planes[4][GSD_CHUNK];
     __shared__ float acc[S][GSD_CWARPS][GSD_SUB][NV];
@@ -503,19 +503,34 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
             const int s = sb % S;
             mbar_wait(&done_bar[s], (sb / S) & 1);
             const int cnt = min(GSD_SUB, I.cnt - sb * GSD_SUB);
-            unsigned wm[GSD_CWARPS];
+            unsigned wm[GSD_CWARPS], any = 0u;
 #pragma unroll
-            for (int w2 = 0; w2 < GSD_CWARPS; ++w2) wm[w2] = wmask[s][w2];
-            for (int idx = lane; idx < cnt * GSD_PART_FLOATS; idx += 32) {
-                const int j = idx / GSD_PART_FLOATS, vv = idx % GSD_PART_FLOATS;
-                float sum = 0.f;
-                if (vv < NV) {
+            for (int w2 = 0; w2 < GSD_CWARPS; ++w2) { wm[w2] = wmask[s][w2]; any |= wm[w2]; }
+            // the preprocess backward reads the first NVP floats of a record (8 in geometry-only mode, 12 otherwise)
+            constexpr int NVP = GEOM ? 8 : 12;
+            if (any == 0u) {
+                // nothing of this sub-batch reached any pixel (e.g. a chunk behind the termination depth): zero records
+                if (lane < cnt) {
+                    const uint32_t slot = __float_as_uint(planes[3][sb * GSD_SUB + lane].x);
+                    if ((int64_t)slot < p.plane_stride) {
+                        float4 *r = reinterpret_cast<float4 *>(p.partials + (size_t)slot * GSD_PART_FLOATS);
+                        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int w2 = 0; w2 < GSD_CWARPS; ++w2)
-                        if ((wm[w2] >> j) & 1u) sum += acc[s][w2][j][vv];
+                        for (int k = 0; k < NVP / 4; ++k) r[k] = z;
+                    }
                 }
-                const uint32_t slot = __float_as_uint(planes[3][sb * GSD_SUB + j].x);
-                if ((int64_t)slot < p.plane_stride) p.partials[(size_t)slot * GSD_PART_FLOATS + vv] = sum;
+            } else {
+                for (int idx = lane; idx < cnt * NVP; idx += 32) {
+                    const int j = idx / NVP, vv = idx % NVP;
+                    float sum = 0.f;
+                    if (vv < NV) {
+#pragma unroll
+                        for (int w2 = 0; w2 < GSD_CWARPS; ++w2)
+                            if ((wm[w2] >> j) & 1u) sum += acc[s][w2][j][vv];
+                    }
+                    const uint32_t slot = __float_as_uint(planes[3][sb * GSD_SUB + j].x);
+                    if ((int64_t)slot < p.plane_stride) p.partials[(size_t)slot * GSD_PART_FLOATS + vv] = sum;
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
@@ -524,7 +539,6 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
     }
     // ===== consumers =====
     const float pxf = (float)I.px, pyf = (float)I.py;
-    const float ddelx_dx = 0.5f * p.W, ddely_dy = 0.5f * p.H;
     const int my_val = holder_id(NV, lane);
     const int base = I.chunk * GSD_CHUNK; // index of the chunk's first record in the tile list
     float T = 0.f, Q = 0.f, tail = 0.f;
@@ -591,7 +605,7 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
 #pragma unroll
                 for (int c = 0; c < CH; ++c) cd += col[c] * dLdC[c];
                 const float Qn = Q - cd * w;
-                const float dL_dalpha = ok ? (T * cd - __fdividef(Qn + tail, one_m)) : 0.f;
+                const float dL_dalpha = ok ? (T * cd - (Qn + tail) * gsd_rcp_approx(one_m)) : 0.f;   // one_m in [0.01, 1]
                 const float Ge = ok ? Gr : 0.f;
                 float v[NV];
                 if (!GEOM) {
@@ -599,13 +613,14 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
                     for (int c = 0; c < CH; ++c) v[c % NV] = w * dLdC[c];
                     v[(CH + 5) % NV] = Ge * dL_dalpha;
                 }
-                const float dL_dG = g1.w * dL_dalpha;
-                const float gdx = Ge * dx, gdy = Ge * dy;
-                v[OG + 0] = dL_dG * (-gdx * g1.x - gdy * g1.y) * ddelx_dx;
-                v[OG + 1] = dL_dG * (-gdy * g1.z - gdx * g1.y) * ddely_dy;
-                v[OG + 2] = -0.5f * gdx * dx * dL_dG;
-                v[OG + 3] = -0.5f * gdx * dy * dL_dG;
-                v[OG + 4] = -0.5f * gdy * dy * dL_dG;
+                // geometry: raw moments of s = dL/dG * G; the (per-Gaussian) conic is applied once in the preprocess backward
+                const float sg = g1.w * dL_dalpha * Ge;
+                const float sdx = sg * dx, sdy = sg * dy;
+                v[OG + 0] = sdx;
+                v[OG + 1] = sdy;
+                v[OG + 2] = sdx * dx;
+                v[OG + 3] = sdx * dy;
+                v[OG + 4] = sdy * dy;
                 if (ok) {
                     Q = Qn;
                     T = __fmul_rn(T, one_m);
