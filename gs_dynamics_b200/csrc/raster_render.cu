@@ -20,6 +20,7 @@
 // rectangles; every 32 records the lanes test one record each against the rectangle (conservative extents of the
 // alpha >= 1/255 ellipse) and only ballot survivors are blended, GSD_ILP at a time.
 #include "common.cuh"
+#include <type_traits>
 
 #define GSD_SUB 32     // records per cull group / backward sub-batch
 #define GSD_CWARPS 8   // consumer warps = 8x4 pixel rectangles of a 16x16 tile
@@ -51,7 +52,7 @@ __device__ __forceinline__ bool cull_pass(const float4 g0, const float4 g1, floa
     const bool in_x = x0 <= 0.f && x1 >= 0.f, in_y = y0 <= 0.f && y1 >= 0.f;
     float qmin = 0.f;
     if (!(in_x && in_y)) {
-        const float nBA = -B / A, nBC = -B / C;
+        const float nBA = -B * gsd_rcp_approx(A), nBC = -B * gsd_rcp_approx(C);   // A, C > 0; the 1e-4 margin below absorbs the ulp
         float ys = fminf(fmaxf(nBC * x0, y0), y1);
         float q1 = A * x0 * x0 + 2.f * B * x0 * ys + C * ys * ys;
         ys = fminf(fmaxf(nBC * x1, y0), y1);
@@ -148,62 +149,68 @@ gsd_blend_fwd_chunk_kernel(GsdRenderParams p) {
     bool off = gone;        // pixel outside the image, or (chunk 0) stopped here
     bool stopped = false;   // chunk 0 only: the reference's "done"
     bool dead = gone;       // nothing of this chunk can be used any more (A2 replays the terminating chunk of a pixel)
-    for (int grp = 0; grp < I.cnt; grp += GSD_SUB) {
-        if (__all_sync(0xffffffffu, dead)) break;
-        const int idx = grp + lane;
-        bool pass = false;
-        if (idx < I.cnt) {
-            pass = cull_pass(planes[0][idx], planes[1][idx], I.rx0, I.rx1, I.ry0, I.ry1);
-        }
-        unsigned m = __ballot_sync(0xffffffffu, pass);
-        while (m) {
-            int j[GSD_ILP];
-            bool valid[GSD_ILP];
-            float alpha[GSD_ILP], power[GSD_ILP];
-            float4 col[GSD_ILP], ext[GSD_ILP];
-#pragma unroll
-            for (int u = 0; u < GSD_ILP; ++u) {
-                valid[u] = m != 0;
-                j[u] = valid[u] ? (grp + __ffs(m) - 1) : grp;
-                m &= m - 1;
+    // two instantiations of the chunk loop: only chunk 0 carries the termination rule
+    auto run = [&](auto first_tag) {
+        constexpr bool FIRST = decltype(first_tag)::value;
+        for (int grp = 0; grp < I.cnt; grp += GSD_SUB) {
+            if (__all_sync(0xffffffffu, dead)) break;
+            const int idx = grp + lane;
+            bool pass = false;
+            if (idx < I.cnt) {
+                pass = cull_pass(planes[0][idx], planes[1][idx], I.rx0, I.rx1, I.ry0, I.ry1);
             }
-#pragma unroll
-            for (int u = 0; u < GSD_ILP; ++u) {
-                const float4 g0 = planes[0][j[u]];
-                const float4 g1 = planes[1][j[u]];
-                col[u] = planes[2][j[u]];
-                if (CH == 6) ext[u] = planes[NPL - 1][j[u]];
-                power[u] = gsd_power(g1.x, g1.y, g1.z, g0.x - pxf, g0.y - pyf);
-                alpha[u] = fminf(0.99f, __fmul_rn(g1.w, gsd_gauss(power[u])));
-            }
-#pragma unroll
-            for (int u = 0; u < GSD_ILP; ++u) {
-                // straight-line (predicated) update: a rejected Gaussian contributes with weight 0
-                bool ok = valid[u] && (!off) && (power[u] <= 0.0f) && (alpha[u] >= 1.0f / 255.0f);
-                const float om = __fsub_rn(1.0f, alpha[u]);
-                const float Tn = __fmul_rn(T, om);
-                if (first) {
-                    const bool stop = ok && Tn < T_EPS;
-                    stopped = stopped || stop;
-                    off = off || stop;
-                    ok = ok && !stop;
+            unsigned m = __ballot_sync(0xffffffffu, pass);
+            while (m) {
+                int j[GSD_ILP];
+                bool valid[GSD_ILP];
+                float alpha[GSD_ILP], power[GSD_ILP];
+                float4 col[GSD_ILP], ext[GSD_ILP];
+    #pragma unroll
+                for (int u = 0; u < GSD_ILP; ++u) {
+                    valid[u] = m != 0;
+                    j[u] = valid[u] ? (grp + __ffs(m) - 1) : grp;
+                    m &= m - 1;
                 }
-                const float w = ok ? alpha[u] * T : 0.f;
-                C[0] += col[u].x * w;
-                C[1] += col[u].y * w;
-                C[2] += col[u].z * w;
-                if (CH == 6) {
-                    C[3 % CH] += ext[u].y * w;
-                    C[4 % CH] += ext[u].z * w;
-                    C[5 % CH] += ext[u].w * w;
+    #pragma unroll
+                for (int u = 0; u < GSD_ILP; ++u) {
+                    const float4 g0 = planes[0][j[u]];
+                    const float4 g1 = planes[1][j[u]];
+                    col[u] = planes[2][j[u]];
+                    if (CH == 6) ext[u] = planes[NPL - 1][j[u]];
+                    power[u] = gsd_power(g1.x, g1.y, g1.z, g0.x - pxf, g0.y - pyf);
+                    alpha[u] = fminf(0.99f, __fmul_rn(g1.w, gsd_gauss(power[u])));
                 }
-                D += col[u].w * w;
-                T = ok ? Tn : T;
-                last = ok ? j[u] + 1 : last;
+    #pragma unroll
+                for (int u = 0; u < GSD_ILP; ++u) {
+                    // straight-line (predicated) update: a rejected Gaussian contributes with weight 0
+                    bool ok = valid[u] && (!off) && (power[u] <= 0.0f) && (alpha[u] >= 1.0f / 255.0f);
+                    const float om = __fsub_rn(1.0f, alpha[u]);
+                    const float Tn = __fmul_rn(T, om);
+                    if (FIRST) {
+                        const bool stop = ok && Tn < T_EPS;
+                        stopped = stopped || stop;
+                        off = off || stop;
+                        ok = ok && !stop;
+                    }
+                    const float w = ok ? alpha[u] * T : 0.f;
+                    C[0] += col[u].x * w;
+                    C[1] += col[u].y * w;
+                    C[2] += col[u].z * w;
+                    if (CH == 6) {
+                        C[3 % CH] += ext[u].y * w;
+                        C[4 % CH] += ext[u].z * w;
+                        C[5 % CH] += ext[u].w * w;
+                    }
+                    D += col[u].w * w;
+                    T = ok ? Tn : T;
+                    last = ok ? j[u] + 1 : last;
+                }
             }
+            dead = off || (T < T_EPS);
         }
-        dead = off || (T < T_EPS);
-    }
+    };
+    if (first) run(std::true_type{});
+    else run(std::false_type{});
     if (first) {
         using TS = TermState<CH>;
         float *ts = p.term_state + (size_t)I.tile * TS::NF * 256;
