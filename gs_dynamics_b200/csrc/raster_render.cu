@@ -293,30 +293,29 @@ gsd_blend_fwd_term_kernel(GsdRenderParams p) {
             m &= m - 1;
             const float4 g0 = planes[0][j];
             const float4 g1 = planes[1][j];
+            const float4 g2 = planes[2][j];
+            float4 g3 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (CH == 6) g3 = planes[NPL - 1][j];
             const float power = gsd_power(g1.x, g1.y, g1.z, g0.x - pxf, g0.y - pyf);
             const float alpha = fminf(0.99f, __fmul_rn(g1.w, gsd_gauss(power)));
+            // straight-line (predicated) update, as in A1
             bool ok = (!done) && (power <= 0.0f) && (alpha >= 1.0f / 255.0f);
             const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-            if (ok && test_T < T_EPS) {
-                done = true;
-                ok = false;
+            const bool stop = ok && test_T < T_EPS;
+            done = done || stop;
+            ok = ok && !stop;
+            const float w = ok ? alpha * T : 0.f;
+            C[0] += g2.x * w;
+            C[1] += g2.y * w;
+            C[2] += g2.z * w;
+            if (CH == 6) {
+                C[3 % CH] += g3.y * w;
+                C[4 % CH] += g3.z * w;
+                C[5 % CH] += g3.w * w;
             }
-            if (ok) {
-                const float4 g2 = planes[2][j];
-                const float w = alpha * T;
-                C[0] += g2.x * w;
-                C[1] += g2.y * w;
-                C[2] += g2.z * w;
-                if (CH == 6) {
-                    const float4 g3 = planes[NPL - 1][j];
-                    C[3 % CH] += g3.y * w;
-                    C[4 % CH] += g3.z * w;
-                    C[5 % CH] += g3.w * w;
-                }
-                D += g2.w * w;
-                T = test_T;
-                last = j + 1;
-            }
+            D += g2.w * w;
+            T = ok ? test_T : T;
+            last = ok ? j + 1 : last;
         }
     }
     if (crossing) {
