@@ -33,6 +33,10 @@ gsd_preprocess_bwd_kernel(int G, GsdCam cam, int64_t capacity, const float *__re
             if (s >= capacity) break;
             const float4 *r = partials + s * 4;
             float4 a = r[0], b = r[1];
+            if (GEOM) {   // two half-tile partial sums per record: floats [0,5) and [8,13), added in fixed order
+                const float4 c = r[2], d = r[3];
+                a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; b.x += d.x;
+            }
             acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
             acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
             if (!GEOM) {

@@ -478,40 +478,45 @@ gsd_blend_bwd_prefix_kernel(GsdRenderParams p) {
 // ------------------------------------------------------------------------------------------------------
 // GEOM: only the geometry gradients (mean2D, conic) are produced — the steady state of the tracker freezes colours and
 // opacities (train_utils.py:370-373), which shrinks the per-Gaussian warp reduction from 12 to 5 values.
-template <int CH, bool GEOM>
-__global__ void __launch_bounds__((GSD_CWARPS + 1) * 32, 5)
+// HALVES = 2 (geometry mode): an item is processed by two CTAs of four consumer warps + flusher, one per half tile; their
+// five sums go to floats [0,5) and [8,13) of the same 64-byte record (summed by the preprocess backward).  A CTA lives as long
+// as its slowest rectangle, so half-tile CTAs idle less behind uneven rectangles and pack twice as finely.
+template <int CH, bool GEOM, int HALVES>
+__global__ void __launch_bounds__((GSD_CWARPS / HALVES + 1) * 32, HALVES == 2 ? 8 : 5)
 gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
+    constexpr int NW = GSD_CWARPS / HALVES; // consumer warps of this CTA
     constexpr int NV = GEOM ? 5 : CH + 6; // [colours,] mean2D(2), conic(3) [, opacity(1)]
     constexpr int OG = GEOM ? 0 : CH;     // offset of the geometry values inside a partial record
     constexpr int S = GEOM ? 4 : (CH == 3 ? 3 : 2); // ring of per-warp partial-sum stages (static shared memory budget); 4 = a whole chunk: consumers never wait for the flusher
     using IS = ItemState<CH>;
     __shared__ __align__(128) float4 planes[4][GSD_CHUNK];
-    __shared__ float acc[S][GSD_CWARPS][GSD_SUB][NV];
-    __shared__ unsigned wmask[S][GSD_CWARPS];
+    __shared__ float acc[S][NW][GSD_SUB][NV];
+    __shared__ unsigned wmask[S][NW];
     __shared__ __align__(8) uint64_t bar, done_bar[S], empty[S];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     ItemInfo I;
-    if (!item_setup(p, blockIdx.x, warp < GSD_CWARPS ? warp : 0, lane, I)) return;
+    const int item = blockIdx.x / HALVES, half = blockIdx.x % HALVES;
+    if (!item_setup(p, item, half * NW + (warp < NW ? warp : 0), lane, I)) return;
     if (t == 0) {
         mbar_init(&bar, 1);
 #pragma unroll
-        for (int s = 0; s < S; ++s) { mbar_init(&done_bar[s], GSD_CWARPS); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(&done_bar[s], NW); mbar_init(&empty[s], 1); }
         mbar_fence_init();
     }
     __syncthreads();
     if (t == 0) load_chunk<4>(p, planes, &bar, I.start, I.cnt);
     const int nsub = (I.cnt + GSD_SUB - 1) / GSD_SUB;
 
-    if (warp == GSD_CWARPS) {
+    if (warp == NW) {
         // ===== flusher: fixed-order sum over the consumer warps, one 64-byte partial record per instance =====
         mbar_wait(&bar, 0);
         for (int sb = 0; sb < nsub; ++sb) {
             const int s = sb % S;
             mbar_wait(&done_bar[s], (sb / S) & 1);
             const int cnt = min(GSD_SUB, I.cnt - sb * GSD_SUB);
-            unsigned wm[GSD_CWARPS], any = 0u;
+            unsigned wm[NW], any = 0u;
 #pragma unroll
-            for (int w2 = 0; w2 < GSD_CWARPS; ++w2) { wm[w2] = wmask[s][w2]; any |= wm[w2]; }
+            for (int w2 = 0; w2 < NW; ++w2) { wm[w2] = wmask[s][w2]; any |= wm[w2]; }
             // the preprocess backward reads the first NVP floats of a record (8 in geometry-only mode, 12 otherwise)
             constexpr int NVP = GEOM ? 8 : 12;
             if (any == 0u) {
@@ -519,7 +524,7 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
                 if (lane < cnt) {
                     const uint32_t slot = __float_as_uint(planes[3][sb * GSD_SUB + lane].x);
                     if ((int64_t)slot < p.plane_stride) {
-                        float4 *r = reinterpret_cast<float4 *>(p.partials + (size_t)slot * GSD_PART_FLOATS);
+                        float4 *r = reinterpret_cast<float4 *>(p.partials + (size_t)slot * GSD_PART_FLOATS + half * NVP);
                         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                         for (int k = 0; k < NVP / 4; ++k) r[k] = z;
@@ -531,11 +536,11 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
                     float sum = 0.f;
                     if (vv < NV) {
 #pragma unroll
-                        for (int w2 = 0; w2 < GSD_CWARPS; ++w2)
+                        for (int w2 = 0; w2 < NW; ++w2)
                             if ((wm[w2] >> j) & 1u) sum += acc[s][w2][j][vv];
                     }
                     const uint32_t slot = __float_as_uint(planes[3][sb * GSD_SUB + j].x);
-                    if ((int64_t)slot < p.plane_stride) p.partials[(size_t)slot * GSD_PART_FLOATS + vv] = sum;
+                    if ((int64_t)slot < p.plane_stride) p.partials[(size_t)slot * GSD_PART_FLOATS + half * NVP + vv] = sum;
                 }
             }
             __syncwarp();
@@ -553,7 +558,7 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
     if (I.inside) {
         const size_t pid = (size_t)I.py * p.W + I.px;
         const size_t plane = (size_t)p.W * p.H;
-        const float *st = p.chunk_state + (size_t)blockIdx.x * IS::NF * 256;
+        const float *st = p.chunk_state + (size_t)item * IS::NF * 256;
         T = st[IS::TIN * 256 + I.pix];
         Q = st[IS::QIN * 256 + I.pix];
         last = p.n_contrib[pid];
@@ -669,12 +674,13 @@ int gsd_launch_render_bwd(const GsdRenderParams &p, int tiles, int n_sets, cudaS
     else gsd_blend_bwd_prefix_kernel<6><<<tiles, GSD_CWARPS * 32, 0, st>>>(p);
     GSD_LAUNCH_CHECK();
     const int threads = (GSD_CWARPS + 1) * 32;
-    if (p.geom_only) {
-        if (n_sets == 1) gsd_blend_bwd_chunk_kernel<3, true><<<p.max_items, threads, 0, st>>>(p);
-        else gsd_blend_bwd_chunk_kernel<6, true><<<p.max_items, threads, 0, st>>>(p);
+    if (p.geom_only) {   // half-tile CTAs (see the kernel)
+        const int th2 = (GSD_CWARPS / 2 + 1) * 32;
+        if (n_sets == 1) gsd_blend_bwd_chunk_kernel<3, true, 2><<<2 * p.max_items, th2, 0, st>>>(p);
+        else gsd_blend_bwd_chunk_kernel<6, true, 2><<<2 * p.max_items, th2, 0, st>>>(p);
     } else {
-        if (n_sets == 1) gsd_blend_bwd_chunk_kernel<3, false><<<p.max_items, threads, 0, st>>>(p);
-        else gsd_blend_bwd_chunk_kernel<6, false><<<p.max_items, threads, 0, st>>>(p);
+        if (n_sets == 1) gsd_blend_bwd_chunk_kernel<3, false, 1><<<p.max_items, threads, 0, st>>>(p);
+        else gsd_blend_bwd_chunk_kernel<6, false, 1><<<p.max_items, threads, 0, st>>>(p);
     }
     GSD_LAUNCH_CHECK();
     return GSD_OK;
