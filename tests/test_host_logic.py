@@ -57,3 +57,29 @@ def test_shard_partitions_units_evenly():
         parts = [gdist.shard(n, r, w) for r in range(w)]
         assert sorted(sum(parts, [])) == list(range(n))
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_gnn_training_losses_match_reference_formulation_cpu():
+    """gnn_train.length_loss / local_rigid_loss (index gathers on an EdgeIndex built from the dataset's dense one-hots, pure torch:
+    runs on the CPU) vs the one-hot bmm formulation of train.py:66-102 restated in the oracle — values and gradients, including
+    zero padding rows and a tool node outside the first n_p columns."""
+    import torch
+    from gs_dynamics_b200 import gnn_train
+    from oracle import gnn_oracle as GO
+    batch = GO.make_training_batch(3, 30, 5, "sloth", 2)
+    Rr, Rs = GO.batch_edges(batch, 0.075, 4, True)
+    Rr = torch.cat([Rr, torch.zeros(3, 6, Rr.shape[2])], 1)      # padded rows as the dataset pads to max_nR
+    Rs = torch.cat([Rs, torch.zeros(3, 6, Rs.shape[2])], 1)
+    n_p = batch["p_instance"].shape[1]
+    g = torch.Generator().manual_seed(0)
+    pred0 = batch["state"][:, -1, :n_p] + 0.01 * torch.randn(3, n_p, 3, generator=g)
+    for ours, ref in ((gnn_train.length_loss, GO.length_loss), (gnn_train.local_rigid_loss, GO.local_rigid_loss)):
+        pa = pred0.clone().requires_grad_(True)
+        pb = pred0.clone().requires_grad_(True)
+        la = ours(pa, None, state=batch["state"], Rr=Rr, Rs=Rs)
+        lb = ref(pb, batch["state"], Rr, Rs)
+        la.backward()
+        lb.backward()
+        assert abs(la.item() - lb.item()) <= 1e-6 * max(1.0, abs(lb.item())) + 1e-12
+        assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-9)
+        assert torch.isfinite(pa.grad).all()
