@@ -74,10 +74,46 @@ def local_rigid_loss(pred, gt, **kwargs):
     return F.mse_loss(_safe_norm(pred_r - pos_r), _safe_norm(pred_s - pos_s))
 
 
+def umeyama_algorithm(X, Y, mask, fixed_scale=True):
+    """Least-squares similarity transform Y ~ c R X + t over the masked points (gnn/utils.py:7-40; Umeyama 1991).
+    X, Y [B,N,3], mask [B,N] -> c [B], R [B,3,3], t [B,1,3]."""
+    w = mask.to(X.dtype)
+    n = w.sum(1)
+    mean = lambda P: torch.einsum('bn,bnk->bk', w, P)[:, None, :] / n[:, None, None]
+    mu_x, mu_y = mean(X), mean(Y)
+    Xc, Yc = (X - mu_x) * w[..., None], (Y - mu_y) * w[..., None]
+    cov = torch.einsum('bni,bnj->bij', Yc, Xc) / n[:, None, None]
+    U, D, Vh = torch.linalg.svd(cov)
+    flip = (torch.linalg.det(U) * torch.linalg.det(Vh) < 0).to(X.dtype)
+    sign = torch.ones_like(D)
+    sign[:, -1] = 1.0 - 2.0 * flip                                   # reflect the last singular direction when det < 0
+    U = U * sign[:, None, :]
+    if fixed_scale:
+        c = torch.ones_like(n)
+    else:
+        var_x = torch.einsum('bn,bn->b', w, ((X - mu_x) ** 2).sum(-1)) / n
+        c = (D * sign).sum(1) / var_x
+    R = U @ Vh
+    t = mu_y - c[:, None, None] * (mu_x @ R.transpose(1, 2))
+    return c, R, t
+
+
+def rigid_loss(pred, gt, **kwargs):
+    """MSE between the prediction and the best rigid motion of the oldest history frame (train.py:30-38); the aligned
+    target is detached.  Masked mean instead of boolean indexing (no host sync); same value."""
+    n_p = pred.shape[1]
+    orig = kwargs['state'][:, 0, :n_p]
+    mask = kwargs['obj_mask']
+    _, R, t = umeyama_algorithm(orig, pred, mask, fixed_scale=True)
+    target = (orig @ R.transpose(1, 2) + t).detach()
+    w = mask.to(pred.dtype)[..., None]
+    return (((pred - target) ** 2) * w).sum() / (w.sum() * pred.shape[-1])
+
+
 def default_loss_funcs(train_config):
-    """train.py:141-155 (the rigid_loss branch needs gnn.utils.umeyama_algorithm and is not part of this path)."""
+    """train.py:141-155"""
     if train_config.get('rigid_loss'):
-        raise NotImplementedError("rigid_loss (umeyama alignment) is outside the ported path")
+        return [(mse_loss, 1.0), (length_loss, 0.05), (rigid_loss, 0.05)]
     funcs = [(mse_loss, train_config['mse_loss'] if train_config.get('mse_loss', 0) > 0 else 1.0)]
     funcs.append((length_loss, train_config['length_loss'] if train_config.get('length_loss', 0) > 0 else 0.01))
     return funcs

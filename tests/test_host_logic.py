@@ -83,3 +83,24 @@ def test_gnn_training_losses_match_reference_formulation_cpu():
         assert abs(la.item() - lb.item()) <= 1e-6 * max(1.0, abs(lb.item())) + 1e-12
         assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-9)
         assert torch.isfinite(pa.grad).all()
+
+
+def test_rigid_loss_and_umeyama_match_reference_fixture():
+    """gnn_train.rigid_loss / umeyama_algorithm vs outputs of the reference's train.rigid_loss and gnn.utils.umeyama_algorithm
+    (tests/golden/gnn_rigid_golden.npz, tools/make_golden.py)."""
+    import os
+    import numpy as np
+    import torch
+    from gs_dynamics_b200 import gnn_train
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "gnn_rigid_golden.npz"))
+    X, mask = torch.tensor(G["rig_X"]), torch.tensor(G["rig_mask"])
+    Y = torch.tensor(G["rig_Y"]).requires_grad_(True)
+    loss = gnn_train.rigid_loss(Y, None, state=X[:, None].repeat(1, 3, 1, 1), obj_mask=mask)
+    loss.backward()
+    assert abs(loss.item() - float(G["rig_loss"])) <= 1e-6 * max(1.0, float(G["rig_loss"])) + 1e-10
+    assert np.abs(Y.grad.numpy() - G["rig_grad"]).max() <= 1e-5 * np.abs(G["rig_grad"]).max() + 1e-12
+    c, R, t = gnn_train.umeyama_algorithm(X, Y.detach(), mask.float(), fixed_scale=False)
+    np.testing.assert_allclose(c.numpy(), G["ume_c"], rtol=1e-5)
+    np.testing.assert_allclose(R.numpy(), G["ume_R"], atol=1e-5)
+    np.testing.assert_allclose(t.numpy(), G["ume_t"], atol=1e-5)
+    assert gnn_train.default_loss_funcs({"rigid_loss": True})[2][0] is gnn_train.rigid_loss

@@ -240,3 +240,23 @@ for tag, (kind, B, n_obj, topk, adj, conn, seed, n_future) in dict(sloth=("sloth
 dst = os.path.join(ROOT, "tests", "golden", "gnn_train_golden.npz")
 np.savez_compressed(dst, **tout)
 print("wrote", dst, os.path.getsize(dst), "bytes")
+
+# rigid_loss / umeyama (train.py:30-38, gnn/utils.py:7-40) on a seeded case: value, gradient, R, t
+g = torch.Generator().manual_seed(5)
+Bq, Nq = 3, 25
+X = torch.rand(Bq, Nq, 3, generator=g)
+ang = torch.tensor([0.3, -0.2, 0.5])
+Rz = torch.stack([torch.stack([torch.cos(ang), -torch.sin(ang), torch.zeros(3)], 1), torch.stack([torch.sin(ang), torch.cos(ang), torch.zeros(3)], 1),
+                  torch.tensor([[0., 0., 1.]]).repeat(3, 1)], 1)
+Y = (X @ Rz.transpose(1, 2) + torch.tensor([0.1, -0.05, 0.02]) + 0.01 * torch.randn(Bq, Nq, 3, generator=g)).requires_grad_(True)
+qmask = torch.rand(Bq, Nq, generator=g) > 0.2
+stq = X[:, None].repeat(1, 3, 1, 1)
+lq = ref_train.rigid_loss(Y, None, state=stq, obj_mask=qmask)
+lq.backward()
+from gnn.utils import umeyama_algorithm as ref_umeyama          # /root/reference/src/gnn/utils.py:7
+cq, Rq, tq = ref_umeyama(X, Y.detach(), qmask.float(), fixed_scale=False)
+rout = dict(rig_X=X.numpy(), rig_Y=Y.detach().numpy(), rig_mask=qmask.numpy(), rig_loss=lq.item(), rig_grad=Y.grad.numpy(),
+            ume_c=cq.numpy(), ume_R=Rq.numpy(), ume_t=tq.numpy())
+dst = os.path.join(ROOT, "tests", "golden", "gnn_rigid_golden.npz")
+np.savez_compressed(dst, **rout)
+print("wrote", dst, os.path.getsize(dst), "bytes")
