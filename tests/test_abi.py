@@ -40,3 +40,43 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.GsdError):
         _lib.lib()
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """Every struct of include/gsd.h compiled by gcc (plain C) has the size and field offsets of its ctypes mirror in _lib.py:
+    the header is the contract, the Python binding must not drift from it."""
+    import ctypes as C
+    import subprocess
+    header = open(os.path.join(ROOT, "include", "gsd.h")).read()
+    clean = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    structs = {}
+    for body, name in re.findall(r"typedef struct\s*\{(.*?)\}\s*(Gsd\w+)\s*;", clean, flags=re.S):
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            # "const float *a, *b" / "float w[2]" / "int32_t G, W" / "GsdRasterFwd fwd"
+            first, *rest = [d.strip() for d in decl.split(",")]
+            fields.append(re.sub(r"\[.*\]", "", first.split()[-1]).lstrip("*"))
+            fields += [re.sub(r"\[.*\]", "", r).lstrip("*").strip() for r in rest]
+        structs[name] = fields
+    mirrored = {n: getattr(_lib, n) for n in structs if hasattr(_lib, n)}
+    assert {"GsdRasterFwd", "GsdRasterBwd", "GsdPhotometric", "GsdTrackLosses", "GsdTrackUpdate", "GsdAdam", "GsdGnnEdges"} <= set(mirrored)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gsd.h"', 'int main(void) {']
+    for n, cls in mirrored.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (n, n))
+        for f in structs[n]:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (n, f, n, f))
+    lines += ['return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for n, cls in mirrored.items():
+        assert int(out[n]) == C.sizeof(cls), (n, out[n], C.sizeof(cls))
+        py_fields = [f[0] for f in cls._fields_]
+        assert py_fields == structs[n], (n, py_fields, structs[n])
+        for f in py_fields:
+            assert int(out["%s.%s" % (n, f)]) == getattr(cls, f).offset, (n, f)
