@@ -347,6 +347,7 @@ def build_cpu_problem(G, seed):
 def cpu_iterations(G, steps, warmup, budget_s):
     from oracle import tracking_cpu, raster_c
     torch.set_num_threads(os.cpu_count() or 1)
+    raster_c.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1 to its workers
     params, variables, opt, dataset = build_cpu_problem(G, 0)
     rng = random.Random(0)
     for _ in range(warmup):

@@ -29,6 +29,11 @@ def num_threads():
     return int(lib().gsd_oracle_num_threads())
 
 
+def set_num_threads(n):
+    """OpenMP team size of the C oracle (torchrun sets OMP_NUM_THREADS=1 for its workers)."""
+    lib().gsd_oracle_set_num_threads(int(n))
+
+
 def _f32(x):
     if hasattr(x, "detach"):
         x = x.detach().cpu().numpy()

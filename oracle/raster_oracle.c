@@ -506,3 +506,12 @@ int gsd_oracle_num_threads(void) {
     return 1;
 #endif
 }
+
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the timed CPU arm asks for the host's cores explicitly */
+void gsd_oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
