@@ -122,13 +122,12 @@ def default_loss_funcs(train_config):
 def unrolled_loss(model, data, n_future, loss_funcs):
     """The n_future-step unroll of train.py:183-211 on one batch.  ``data``: dict with state [B,n_his,N,3], attrs, Rr (EdgeIndex
     or dense) / Rs, p_instance, action, state_future [B,n_future,n_p,3], tool_future / action_future [B,n_future-1,N,3].
-    Returns (loss_sum, per-function float sums); ``data`` is not modified."""
+    Returns (loss_sum, [per-function weighted losses of every step]); ``data`` is not modified."""
     data = dict(data)
     if not isinstance(data['Rr'], EdgeIndex):
         data['Rr'] = edge_index_from_dense(data['Rr'], data['Rs'])
     data['edges'] = data['Rr']
     loss_sum = 0
-    items = [0.0 for _ in loss_funcs]
     parts = []
     for fi in range(n_future):
         gt_state = data['state_future'][:, fi]

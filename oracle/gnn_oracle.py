@@ -10,7 +10,6 @@ Pinned against the reference itself by tests/golden/gnn_golden.npz (tools/make_g
 and src/data/dataset.py).  The model is a pure function of a state_dict so that no nn.Module code is duplicated.
 Only tests/, smoke() and bench.py's cpu legs may import this module.
 """
-import numpy as np
 import torch
 import torch.nn.functional as F
 

@@ -20,7 +20,6 @@ Conventions reproduced so autograd matches the upstream hand-written backward:
 
 Only tests/ may import this module.  Sizes must stay small (P*G dense).
 """
-import math
 import torch
 
 TILE = 16
