@@ -455,6 +455,11 @@ class TrackingStep:
     def __init__(self, params, variables, optimizer, dataset, is_initial_timestep=False, loss_kwargs=None,
                  capacity_margin=1.5, use_graph=True):
         self.params, self.variables, self.optimizer, self.dataset = params, variables, optimizer, dataset
+        if is_initial_timestep and use_graph:
+            # the first-frame loss renders RGB and seg separately through the autograd rasterizer, which reads the instance
+            # count back to size its buffers (the one sync upstream also performs): not capturable, and densification
+            # changes G between iterations anyway
+            raise ValueError("the first-frame (t = 0) iteration cannot be captured in a CUDA graph: pass use_graph=False")
         self.is_initial = is_initial_timestep
         self.kw = dict(loss_kwargs or {})
         self.margin = capacity_margin

@@ -105,3 +105,12 @@ def test_rigid_loss_and_umeyama_match_reference_fixture():
     np.testing.assert_allclose(R.numpy(), G["ume_R"], atol=1e-5)
     np.testing.assert_allclose(t.numpy(), G["ume_t"], atol=1e-5)
     assert gnn_train.default_loss_funcs({"rigid_loss": True})[2][0] is gnn_train.rigid_loss
+
+
+def test_first_frame_step_refuses_graph_capture():
+    """TrackingStep(is_initial_timestep=True, use_graph=True) must fail loudly in Python, not as a CUDA capture error."""
+    import pytest
+    from gs_dynamics_b200 import tracking as TR
+    with pytest.raises(ValueError, match="use_graph=False"):
+        TR.TrackingStep({}, {}, None, [], is_initial_timestep=True, use_graph=True)
+    TR.TrackingStep({}, {}, None, [], is_initial_timestep=True, use_graph=False)
