@@ -221,14 +221,15 @@ def _rel(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
 
 
-@pytest.mark.parametrize("n_tool_rows", [0, 1])
-def test_aggregate_backward_kernel_vs_torch(n_tool_rows):
-    """gsd_gnn_aggregate_bwd vs autograd through the index formulation (heavy split rows on and off)."""
+@pytest.mark.parametrize("n_tool_rows,Fd", [(0, 128), (1, 128), (1, 512)])
+def test_aggregate_backward_kernel_vs_torch(n_tool_rows, Fd):
+    """gsd_gnn_aggregate_bwd vs autograd through the index formulation (heavy split rows on and off; the benchmark's feature
+    width 512 = four float4 per lane)."""
     from gs_dynamics_b200 import gnn
     gi = GO.make_graph_inputs(150, 5, "sloth")
     e = gnn.construct_edges_index(gi["state"][0, -1].cuda(), 0.075, gi["state_mask"].cuda(), gi["eef_mask"].cuda(), topk=6, connect_all=True)
     e.n_tool = n_tool_rows
-    Fd, N, cap = 128, e.N, e.capacity
+    N, cap = e.N, e.capacity
     g = torch.Generator(device="cuda").manual_seed(0)
     A = torch.randn(cap, Fd, device="cuda", generator=g).requires_grad_(True)
     P = torch.randn(N, 2 * Fd, device="cuda", generator=g).requires_grad_(True)
