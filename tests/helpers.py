@@ -50,3 +50,42 @@ def rel_err(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def analytic_two_gaussians(w=64, h=64, f=100.0):
+    """Known-answer case computable by hand from the published splatting formulas (Kerbl et al. 2023, EWA splatting; the
+    constants of SURVEY.md §2.1): camera at the origin looking down +z with the principal point at the image centre, two
+    ISOTROPIC Gaussians on the optical axis at depths z0 < z1.  Then J = diag(f/z), cov2D = ((f s / z)^2 + 0.3) I, the
+    projected centre is pixel (w-1)/2, (h-1)/2 and for a pixel at squared distance d2 from it
+        alpha_i = min(0.99, o_i * exp(-d2 / (2 ((f s_i / z_i)^2 + 0.3)))),   dropped when < 1/255
+        colour  = a0 c0 + (1 - a0) a1 c1 + (1 - a0)(1 - a1) bg,   depth = a0 z0 + (1 - a0) a1 z1,   T = (1 - a0)(1 - a1)
+    (no pixel gets near the 1e-4 termination).  Returns the inputs and the expected maps, with a validity mask that leaves out
+    the pixels within 2 % of the 1/255 threshold."""
+    import numpy as np
+    import torch
+    from gs_dynamics_b200 import scenes
+    k = [[f, 0.0, w / 2.0], [0.0, f, h / 2.0], [0.0, 0.0, 1.0]]
+    cam = scenes.camera_matrices(w, h, k, np.eye(4), near=0.01)
+    z = np.array([1.0, 1.5])
+    s = np.array([0.03, 0.06])
+    o = np.array([0.7, 0.9])
+    c = np.array([[0.9, 0.2, 0.1], [0.1, 0.5, 0.8]])
+    bg = np.array([0.05, 0.10, 0.15])
+    act = dict(means3D=torch.tensor([[0.0, 0.0, z[0]], [0.0, 0.0, z[1]]], dtype=torch.float32),
+               colors_precomp=torch.tensor(c, dtype=torch.float32), opacities=torch.tensor(o[:, None], dtype=torch.float32),
+               scales=torch.tensor(np.repeat(s[:, None], 3, 1), dtype=torch.float32),
+               rotations=torch.tensor([[1.0, 0, 0, 0], [1.0, 0, 0, 0]], dtype=torch.float32))
+    ys, xs = np.mgrid[0:h, 0:w]
+    d2 = (xs - (w - 1) / 2.0) ** 2 + (ys - (h - 1) / 2.0) ** 2
+    var = (f * s / z) ** 2 + 0.3
+    a = [np.minimum(0.99, o[i] * np.exp(-d2 / (2 * var[i]))) for i in range(2)]
+    near_thr = np.zeros_like(d2, dtype=bool)
+    for i in range(2):
+        near_thr |= np.abs(a[i] - 1 / 255.0) < 0.02 / 255.0
+        a[i] = np.where(a[i] >= 1 / 255.0, a[i], 0.0)
+    T = (1 - a[0]) * (1 - a[1])
+    color = a[0][None] * c[0][:, None, None] + ((1 - a[0]) * a[1])[None] * c[1][:, None, None] + T[None] * bg[:, None, None]
+    depth = a[0] * z[0] + (1 - a[0]) * a[1] * z[1]
+    radii = np.ceil(3.0 * np.sqrt(var)).astype(np.int32)
+    return dict(cam=cam, act=act, bg=torch.tensor(bg, dtype=torch.float32), color=color, depth=depth, final_T=T, radii=radii,
+                valid=~near_thr)

@@ -64,3 +64,23 @@ def test_empty_and_culled_inputs():
     fo = oracle_forward(act, cam, torch.tensor([0.2, 0.4, 0.6]))
     assert fo["R"] == 0 and (fo["radii"] == 0).all()
     np.testing.assert_allclose(fo["color"][1], 0.4)
+
+
+def test_known_answer_two_gaussians_on_the_optical_axis():
+    """Closed-form known-answer test (tests/helpers.py::analytic_two_gaussians): both oracles against values computed by hand
+    from the published formulas — an anchor that does not depend on either restatement."""
+    from tests.helpers import analytic_two_gaussians
+    K = analytic_two_gaussians()
+    fo = oracle_forward(K["act"], K["cam"], K["bg"])
+    v = K["valid"]
+    assert np.array_equal(fo["radii"], K["radii"])
+    assert np.abs(fo["color"] - K["color"])[:, v].max() < 2e-6
+    assert np.abs(fo["depth"][0] - K["depth"])[v].max() < 2e-6
+    assert np.abs(fo["final_T"] - K["final_T"])[v].max() < 2e-6
+    a = K["act"]
+    to = raster_torch.rasterize_dense(a["means3D"].double(), torch.zeros(2, 3, dtype=torch.float64), a["opacities"].double(),
+                                      a["colors_precomp"].double(), a["scales"].double(), a["rotations"].double(),
+                                      K["cam"]["viewmatrix"], K["cam"]["projmatrix"], K["cam"]["tanfovx"], K["cam"]["tanfovy"],
+                                      64, 64, K["bg"])
+    assert np.abs(to["color"].numpy() - K["color"])[:, v].max() < 1e-6
+    assert np.abs(to["depth"].numpy()[0] - K["depth"])[v].max() < 1e-6

@@ -250,3 +250,17 @@ def test_mark_visible():
     z = pts @ V[:3, 2] + V[3, 2]
     borderline = (z - 0.2).abs() < 1e-5
     assert torch.equal(vis[~borderline], (z > 0.2)[~borderline])
+
+
+def test_known_answer_two_gaussians_on_the_optical_axis():
+    """The CUDA rasterizer against the closed-form known-answer case (tests/helpers.py::analytic_two_gaussians): values computed
+    by hand from the published formulas, no oracle in between.  1e-4 abs (ex2.approx), pixels within 2 % of the 1/255
+    threshold left out."""
+    from tests.helpers import analytic_two_gaussians
+    K = analytic_two_gaussians()
+    color, radii, depth, state = _render(_to_cuda(K["act"]), settings_from(K["cam"], K["bg"].tolist()))
+    torch.cuda.synchronize()
+    v = K["valid"]
+    assert np.array_equal(radii.cpu().numpy(), K["radii"])
+    assert np.abs(color.cpu().numpy() - K["color"])[:, v].max() < 1e-4
+    assert np.abs(depth.cpu().numpy()[0] - K["depth"])[v].max() < 1e-4
