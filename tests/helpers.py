@@ -89,3 +89,39 @@ def analytic_two_gaussians(w=64, h=64, f=100.0):
     radii = np.ceil(3.0 * np.sqrt(var)).astype(np.int32)
     return dict(cam=cam, act=act, bg=torch.tensor(bg, dtype=torch.float32), color=color, depth=depth, final_T=T, radii=radii,
                 valid=~near_thr)
+
+
+def analytic_one_gaussian_gradients(w=48, h=48, f=90.0, seed=0):
+    """Closed-form GRADIENTS for one isotropic Gaussian on the optical axis (camera as in analytic_two_gaussians) and a seeded
+    upstream gradient dL/dC.  With G = exp(-(dx^2/vx + dy^2/vy)/2), v. = (f s./z)^2 + 0.3, a = o G < 0.99 and
+    C = a c + (1 - a) bg on the pixels with a >= 1/255 (E = sum_ch dL (c - bg) restricted to them):
+        dL/dc   = sum_px a dL                      dL/do  = sum_px G E
+        dL/dX   = (f/z) sum_px a E dx / vx          (dx = px - centre; cov2D is stationary in X, Y on the axis)
+        dL/dsx  = sum_px a E (dx^2 / (2 vx^2)) * 2 (f/z)^2 sx,   same for y;   dL/dsz = 0  (J's third column vanishes on the axis)
+    Pixels within 2 % of the 1/255 threshold get dL = 0 so that the contributor set is unambiguous."""
+    import numpy as np
+    import torch
+    from gs_dynamics_b200 import scenes
+    k = [[f, 0.0, w / 2.0], [0.0, f, h / 2.0], [0.0, 0.0, 1.0]]
+    cam = scenes.camera_matrices(w, h, k, np.eye(4), near=0.01)
+    z, s, o = 1.2, 0.05, 0.6
+    c = np.array([0.8, 0.3, 0.2])
+    bg = np.array([0.1, 0.4, 0.05])
+    act = dict(means3D=torch.tensor([[0.0, 0.0, z]], dtype=torch.float32), colors_precomp=torch.tensor(c[None], dtype=torch.float32),
+               opacities=torch.tensor([[o]], dtype=torch.float32), scales=torch.tensor([[s, s, s]], dtype=torch.float32),
+               rotations=torch.tensor([[1.0, 0, 0, 0]], dtype=torch.float32))
+    ys, xs = np.mgrid[0:h, 0:w]
+    dx, dy = xs - (w - 1) / 2.0, ys - (h - 1) / 2.0
+    v = (f * s / z) ** 2 + 0.3
+    Gs = np.exp(-(dx * dx + dy * dy) / (2 * v))
+    a = o * Gs
+    on = a >= 1 / 255.0
+    rng = np.random.default_rng(seed)
+    dL = rng.normal(size=(3, h, w))
+    dL[:, np.abs(a - 1 / 255.0) < 0.02 / 255.0] = 0.0
+    E = (dL * (c - bg)[:, None, None]).sum(0) * on
+    g = dict(colors=(dL * (a * on)[None]).sum((1, 2)), opacity=(Gs * E).sum(),
+             mean=np.array([(f / z) * (a * E * dx / v).sum(), (f / z) * (a * E * dy / v).sum()]),
+             scales=np.array([(a * E * dx * dx / (2 * v * v)).sum() * 2 * (f / z) ** 2 * s,
+                              (a * E * dy * dy / (2 * v * v)).sum() * 2 * (f / z) ** 2 * s, 0.0]))
+    return dict(cam=cam, act=act, bg=torch.tensor(bg, dtype=torch.float32), dL=torch.tensor(dL, dtype=torch.float32), grads=g)

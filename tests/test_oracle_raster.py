@@ -84,3 +84,17 @@ def test_known_answer_two_gaussians_on_the_optical_axis():
                                       64, 64, K["bg"])
     assert np.abs(to["color"].numpy() - K["color"])[:, v].max() < 1e-6
     assert np.abs(to["depth"].numpy()[0] - K["depth"])[v].max() < 1e-6
+
+
+def test_known_answer_gradients_one_gaussian():
+    """The C oracle's hand-derived backward against closed-form gradients (tests/helpers.py::analytic_one_gaussian_gradients):
+    colour, opacity, mean x/y and scale gradients of one on-axis Gaussian, independent of the autograd cross-check."""
+    from tests.helpers import analytic_one_gaussian_gradients
+    K = analytic_one_gaussian_gradients()
+    bo = oracle_backward(K["act"], K["cam"], K["bg"], K["dL"])
+    g = K["grads"]
+    tol = lambda ref: 2e-5 * np.abs(ref).max() + 1e-7
+    assert np.abs(bo["colors"][0] - g["colors"]).max() < tol(g["colors"])
+    assert abs(bo["opacities"][0] - g["opacity"]) < tol(np.array([g["opacity"]]))
+    assert np.abs(bo["means3D"][0, :2] - g["mean"]).max() < tol(g["mean"])
+    assert np.abs(bo["scales"][0] - g["scales"]).max() < tol(g["scales"])

@@ -264,3 +264,20 @@ def test_known_answer_two_gaussians_on_the_optical_axis():
     assert np.array_equal(radii.cpu().numpy(), K["radii"])
     assert np.abs(color.cpu().numpy() - K["color"])[:, v].max() < 1e-4
     assert np.abs(depth.cpu().numpy()[0] - K["depth"])[v].max() < 1e-4
+
+
+def test_known_answer_gradients_one_gaussian():
+    """The CUDA backward against closed-form gradients (tests/helpers.py::analytic_one_gaussian_gradients): colour, opacity,
+    mean x/y and scale gradients of one on-axis Gaussian; 1e-3 of the largest component of each (fp32, ex2.approx)."""
+    from gs_dynamics_b200 import rasterizer as R
+    from tests.helpers import analytic_one_gaussian_gradients
+    K = analytic_one_gaussian_gradients()
+    color, radii, depth, state = _render(_to_cuda(K["act"]), settings_from(K["cam"], K["bg"].tolist()))
+    gr = R.raster_backward(state, K["dL"].cuda())
+    torch.cuda.synchronize()
+    g = K["grads"]
+    tol = lambda ref: 1e-3 * np.abs(ref).max() + 1e-6
+    assert np.abs(gr["colors0"][0].cpu().numpy() - g["colors"]).max() < tol(g["colors"])
+    assert abs(float(gr["opacities"].reshape(-1)[0]) - g["opacity"]) < tol(np.array([g["opacity"]]))
+    assert np.abs(gr["means3D"][0, :2].cpu().numpy() - g["mean"]).max() < tol(g["mean"])
+    assert np.abs(gr["scales"][0].cpu().numpy() - g["scales"]).max() < tol(g["scales"])
