@@ -1,15 +1,21 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the gs-dynamics hot path on B200 (contract: see DESIGN.md §Measurement).
 
-Workload (BASELINE.json configs[1]): steady-state tracking iteration of train_gs.py — get_loss (fused RGB+seg render,
-L1+SSIM, rigid/rot/iso/floor/bg priors) + backward + Adam — at G Gaussians on the 4 demo cameras @640x480, one random
-camera per iteration.  A "step" is one such iteration.  metric = tracking iters/sec, whole job.
+Workload (BASELINE.json configs[2], the size the north-star target names): steady-state tracking iteration of train_gs.py —
+get_loss (fused RGB+seg render, L1+SSIM, rigid/rot/iso/floor/bg priors) + backward + Adam — at G = 100 000 Gaussians on the
+4 demo cameras @640x480, one random camera per iteration.  A "step" is one such iteration.  metric = tracking iters/sec.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--gaussians G]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|upstream_structure] [--gaussians G]
 
-ours      : CUDA-graph replay of the iteration (inputs resident in HBM) -> value;  e2e: the same iteration through the public
-            API with the step's camera image+seg copied from pinned host memory and the loss read back, inside the timed region.
-reference : the reference's iteration on the host cores (oracle port: C rasterizer restatement + CPU PyTorch), bounded sample.
+ours               : CUDA-graph replay of the iteration (inputs resident in HBM) -> value;  e2e: the same iteration through the
+                     public API with the step's camera image+seg copied from pinned host memory and the loss read back, inside
+                     the timed region.  Side objects (N = 1): roofline (dominant kernel vs HBM and issue-slot peaks, the §8(d)
+                     aggregate, per-stage table), episode (configs[2]: frames of 2 000 iterations with per-frame target upload and
+                     initialize_per_timestep), secondary_50k (configs[1]), render_1280x720 (A13), gpu_reference (the reference's
+                     eager iteration on an upstream-structure CUDA rasterizer, same box), cpu_baseline, gnn / gnn_train.
+reference          : the reference's iteration on the host cores (oracle port: C rasterizer restatement + CPU PyTorch).
+upstream_structure : the reference's eager iteration on this GPU (baseline/upstream_structure) — the "reference CUDA
+                     rasterizer on 1 GPU" baseline of the north-star, as a clearly-labelled structural re-creation.
 """
 import argparse
 import json
@@ -27,6 +33,15 @@ import numpy as np
 import torch
 
 HBM_FALLBACK_GBS = 6650.0
+
+
+def make_config(G, world, n_cams=4):
+    """The SAME dict for every arm (ours / reference / upstream_structure): the driver compares them."""
+    return {"workload": "train_gs.py steady-state iteration (t>0), %dk Gaussians, 4 cams @640x480, 1 episode per GPU" % (G // 1000),
+            "gaussians": G, "cameras": n_cams, "image": "640x480", "knn": 20,
+            "parallelism": "episode-per-gpu x%d" % world,
+            "l2": "GPU arms: 256 MiB L2 flush between timed steps (excluded from step time)",
+            "timing": "GPU arms: CUDA events per step on the launch stream, max over ranks; CPU arm: wall clock"}
 
 
 def env_rank():
@@ -114,44 +129,21 @@ class ClockSampler:
 # ours
 # ------------------------------------------------------------------------------------------------------------------
 def build_gpu_problem(G, seed, device):
-    from gs_dynamics_b200 import tracking as TR, workloads, rasterizer as R
-    prob = workloads.tracking_problem(G, seed)
-    params = {k: torch.nn.Parameter(v.to(device).contiguous()) for k, v in prob["params"].items()}
-    params["rgb_colors"].requires_grad = False
-    v = {k: (t.to(device).contiguous() if isinstance(t, torch.Tensor) else t) for k, t in prob["variables"].items()}
-    v["neighbor_indices_i32"] = v["neighbor_indices"].to(torch.int32).contiguous()
-    v["in_ptr"], v["in_edge"] = TR.build_in_edges(v["neighbor_indices_i32"])
-    v["fg_index"] = None
-    v["bg_index"] = torch.zeros(0, dtype=torch.int32, device=device)
-    TR.pack_edge_records(v)
-    opt = TR.initialize_optimizer(params, v)
-    for g in opt.param_groups:  # steady state: lrs frozen after t = 0 (train_utils.py:370-373)
-        if g["name"] in ("logit_opacities", "log_scales", "cam_m", "cam_c", "rgb_colors"):
-            g["lr"] = 0.0
-    tgt = {k: t.to(device) for k, t in prob["target"].items()}
-    ones = torch.ones_like(tgt["colors_precomp"])
-    dataset, host = [], []
-    for c in prob["cams"]:
-        cam = TR.setup_camera(c["w"], c["h"], c["k"], c["w2c"], near=1.0, far=100, device=device)
-        with torch.no_grad():
-            out, _, _, _ = R.raster_forward(cam, tgt["means3D"], tgt["opacities"], tgt["colors_precomp"], tgt["scales"],
-                                            tgt["rotations"], colors1=ones)
-        im = out[:3].clone()
-        seg = workloads.seg_target_from_mask(out[3]).contiguous()
-        dataset.append({"cam": cam, "im": im, "seg": seg, "id": c["id"]})
-        host.append((im.cpu().pin_memory(), seg.cpu().pin_memory()))
-    return params, v, opt, dataset, host
+    from gs_dynamics_b200 import workloads
+    return workloads.tracking_problem_gpu(G, seed, device)
 
 
 def time_blend_backward(params, dataset, capacity, flush, iters=10):
-    """CUDA-event duration of the dominant kernel (blend backward, 6 channels) alone, L2 flushed before each launch."""
+    """CUDA-event duration of (a) the dominant kernel (blend backward, 6 channels, geometry-only) alone and (b) the whole
+    rasterizer forward + backward of one camera, L2 flushed before each measurement."""
     import ctypes as C
     from gs_dynamics_b200 import tracking as TR, rasterizer as R, _lib
     data = dataset[0]
     with torch.no_grad():
         rv = TR.params2rendervar(params)
-        color, radii, depth, st = R.raster_forward(data["cam"], rv["means3D"], rv["opacities"], rv["colors_precomp"], rv["scales"],
-                                                   rv["rotations"], colors1=params["seg_colors"].detach(), capacity=capacity)
+        seg = params["seg_colors"].detach()
+        args = (data["cam"], rv["means3D"], rv["opacities"], rv["colors_precomp"], rv["scales"], rv["rotations"])
+        color, radii, depth, st = R.raster_forward(*args, colors1=seg, capacity=capacity)
         dL = torch.randn_like(color)
         sz = R._workspace_bytes(st.G, st.W, st.H, st.n_sets, st.capacity)
         partial = torch.empty(sz[3], dtype=torch.uint8, device=color.device)
@@ -159,7 +151,7 @@ def time_blend_backward(params, dataset, capacity, flush, iters=10):
         b.fwd = st.desc
         b.dL_dcolor, b.partial_ws = dL.data_ptr(), partial.data_ptr()  # no colour/opacity outputs: the steady-state (geometry-only) kernel
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        ts = []
+        ts, tr = [], []
         for i in range(iters + 2):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -169,8 +161,153 @@ def time_blend_backward(params, dataset, capacity, flush, iters=10):
             torch.cuda.synchronize()
             if i >= 2:
                 ts.append(e0.elapsed_time(e1) * 1e-3)
+        for i in range(iters + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            c2, _, _, st2 = R.raster_forward(*args, colors1=seg, capacity=capacity)
+            R.raster_backward(st2, dL, need_means2D=False, geom_only=True)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                tr.append(e0.elapsed_time(e1) * 1e-3)
         R_inst = int(st.status[0].item())
-    return float(np.mean(ts)), R_inst
+    return float(np.mean(ts)), float(np.mean(tr)), R_inst
+
+
+def load_profile_json(name):
+    p = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+def time_device_steps(step_obj, n_cams, rng, steps, warmup, flush, barrier=None):
+    for _ in range(warmup):
+        step_obj.step(rng.randrange(n_cams))
+    if barrier:
+        barrier()
+    evs = []
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_obj.step(rng.randrange(n_cams))
+        e1.record()
+        evs.append((e0, e1))
+    if barrier:
+        barrier()
+    else:
+        torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+
+
+def run_episode(device, G, frames, iters, seed=0):
+    """BASELINE configs[2] (train_gs.py:19-46 for t > 0): per frame — target images uploaded from pinned host memory,
+    initialize_per_timestep (constant-velocity warm start, Adam reset, prev_* tables, edge-record pack), exactly `iters`
+    iterations through the per-camera graphs captured ONCE, one capacity check.  Targets drift by 0.5 mm per frame
+    (SURVEY.md §8d config 3).  Everything between the first frame's start and the last frame's end is inside the timed region
+    (wall clock with a device sync at both ends); graph capture happens before it and is reported separately."""
+    from gs_dynamics_b200 import tracking as TR, workloads, rasterizer as R
+    prob = workloads.tracking_problem(G, seed)
+    params, variables, opt, dataset, _ = workloads.tracking_problem_gpu(G, seed, device, prob=prob)
+    tgt = {k: t.to(device) for k, t in prob["target"].items()}
+    ones = torch.ones_like(tgt["colors_precomp"])
+    host_frames = []
+    with torch.no_grad():
+        for f in range(frames):   # the "dataset on disk": per-frame images in pinned host memory
+            shift = torch.tensor([0.0005 * (f + 1), 0.0, 0.0], device=device)
+            fr = []
+            for d in dataset:
+                out, _, _, _ = R.raster_forward(d["cam"], tgt["means3D"] + shift, tgt["opacities"], tgt["colors_precomp"], tgt["scales"],
+                                                tgt["rotations"], colors1=ones)
+                fr.append((out[:3].cpu().pin_memory(), workloads.seg_target_from_mask(out[3]).cpu().pin_memory()))
+            host_frames.append(fr)
+    rng = random.Random(seed)
+    t0 = time.time()
+    params, variables = TR.initialize_per_timestep(params, variables, opt)
+    step = TR.FusedTrackingStep(params, variables, opt, dataset)
+    step.prepare()
+    torch.cuda.synchronize()
+    t_capture = time.time() - t0
+    hw_max, recaptures = 0, 0
+    t1 = time.time()
+    for f in range(frames):
+        if f > 0:
+            params, variables = TR.initialize_per_timestep(params, variables, opt)
+        for c, (im, seg) in enumerate(host_frames[f]):
+            step.set_target(c, im, seg)
+        cap0 = dict(step.capacity)
+        hw = TR.run_frame(step, [rng.randint(0, len(dataset) - 1) for _ in range(iters)])
+        hw_max = max(hw_max, hw)
+        recaptures += int(cap0 != step.capacity)
+    torch.cuda.synchronize()
+    dt = time.time() - t1
+    h2d = sum(im.numel() * 4 + seg.numel() * 4 for im, seg in host_frames[0])
+    return {"metric": "tracked frames/sec (2 000 iterations each)", "value": frames / dt, "unit": "frames/s", "iters_per_s": frames * iters / dt,
+            "frames": frames, "iters_per_frame": iters, "seconds": dt, "graph_capture_seconds_once": t_capture, "recaptures": recaptures,
+            "max_instances_seen": hw_max, "capacity": min(step.capacity.values()), "h2d_bytes_per_frame": h2d,
+            "config": {"workload": "train_gs.py episode, frames t>0: %dk Gaussians, 4 cams @640x480, per-frame target upload + "
+                                   "initialize_per_timestep + %d iterations + 1 capacity check; graphs captured once" % (G // 1000, iters)}}
+
+
+def run_render_720p(device, G, iters=20):
+    """A13: Renderer.render + the ones-colour mask render of predict.py:116-123 at 1280x720 (3 600 tiles), per frame."""
+    from gs_dynamics_b200 import render as RD, scenes
+    W0, H0, cams = scenes.demo_cameras()
+    k, w2c = cams[0]
+    k = k.copy(); k[0] *= 1280 / W0; k[1] *= 720 / H0
+    act = {kk: v.to(device) for kk, v in scenes.activate(scenes.synthetic_scene(G, 0)).items()}
+    act["means2D"] = torch.zeros_like(act["means3D"])
+    r = RD.Renderer(device)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    ts = []
+    for i in range(iters + 3):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r.render(w2c, k, act)
+        r.render_mask(w2c, k, act)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1))
+    return {"metric": "predict.py render leg: image + mask render per frame", "ms_per_frame": float(np.median(ts)),
+            "value": 1e3 / float(np.median(ts)), "unit": "frames/s", "config": {"workload": "Renderer.render + render_mask, %dk Gaussians, 1280x720 (incl. the reference's exact-size num_rendered sync per call)" % (G // 1000)}}
+
+
+def run_upstream_structure(G, steps, warmup, device, seed=0):
+    """The reference's eager iteration on this GPU (baseline/upstream_structure).  Device time per step incl. its host syncs
+    (CUDA events around each iteration, L2 flushed between iterations like the other GPU arm)."""
+    from baseline import upstream_structure as U
+    from gs_dynamics_b200 import workloads
+    prob = workloads.tracking_problem(G, seed)
+    _, _, _, dataset, _ = workloads.tracking_problem_gpu(G, seed, device, prob=prob)   # same targets / cameras as our arm
+    params = {k: torch.nn.Parameter(v.to(device).contiguous()) for k, v in prob["params"].items()}
+    params["rgb_colors"].requires_grad = False
+    variables = {k: (t.to(device) if isinstance(t, torch.Tensor) else t) for k, t in prob["variables"].items()}
+    opt = U.make_optimizer(params, variables["scene_radius"])
+    Ras, label = U.rasterizer_module(prefer_real=True)
+    rng = random.Random(0)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    for _ in range(warmup):
+        U.iteration(Ras, params, dataset[rng.randrange(len(dataset))], variables, opt)
+    torch.cuda.synchronize()
+    total, t0 = 0.0, time.time()
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = U.iteration(Ras, params, dataset[rng.randrange(len(dataset))], variables, opt)
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1) * 1e-3
+    return {"value": steps / total, "unit": "iters/s", "ms_per_step": 1e3 * total / steps, "steps": steps, "warmup": warmup,
+            "rasterizer": label, "final_loss": float(loss), "wall_s": time.time() - t0,
+            "kind": "reference's eager get_loss + backward + torch.optim.Adam (train_utils.py:167-246, train_gs.py:31-39) on 1 GPU"}
 
 
 def run_ours(args):
@@ -187,16 +324,15 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
 
     step_obj = TR.FusedTrackingStep(params, variables, opt, dataset, use_graph=True)
-    own0, lib0 = _lib.launch_count()
     step_obj.prepare()
-    own1, lib1 = _lib.launch_count()
-    # prepare() = capacity probe (1 fwd) + 1 eager warm-up + 1 captured iteration per camera
-    # launches of ONE iteration: measure on an eager replay
+    # launches of ONE iteration: counted on an eager run of the same code (graph replays are not seen by the host counter)
     eager = TR.FusedTrackingStep(params, variables, opt, dataset, use_graph=False)
     eager.capacity = dict(step_obj.capacity)
+    snap = eager.snapshot()
     a0 = _lib.launch_count()
     eager.step(0)
     a1 = _lib.launch_count()
+    eager.restore(snap)
     own_per_iter, lib_per_iter = a1[0] - a0[0], a1[1] - a0[1]
 
     def barrier():
@@ -214,19 +350,11 @@ def run_ours(args):
         sampler.wait_first()
     barrier()
     sampler.mark()
-    evs = []
     t_wall0 = time.time()
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step_obj.step(rng.randrange(n_cams))
-        e1.record()
-        evs.append((e0, e1))
-    barrier()
+    dev_s = time_device_steps(step_obj, n_cams, rng, args.steps, 0, flush, barrier)
     t_wall = time.time() - t_wall0
-    dev_s = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
+    hw, n_over = step_obj.check_capacity(raise_on_overflow=True)   # one 8-byte read: no replay dropped instances
 
     # ---- end to end through the public API with host buffers: every step its camera image + seg are copied from pinned host
     # memory into the step's target buffers (plus their SSIM window statistics), and the loss is read back and consumed on the
@@ -254,9 +382,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         for i in range(n_steps):
             if timed:
-                flush.zero_()
-                torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                flush.zero_()                              # stream-ordered before e0: no host sync needed (and none wanted —
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)   # it would starve the GPU)
             e0.record()
             l = step_obj.step(seq[i])                      # inputs of this step landed inside the previous timed region
             done = torch.cuda.Event()
@@ -279,19 +406,32 @@ def run_ours(args):
     e2e_s, last_loss = run_e2e(args.steps, True)
     barrier()
 
-    # ---- roofline of the dominant kernel
+    # ---- rooflines
     peak, peak_src = measured_peaks()
-    t_blend, R_inst = time_blend_backward(params, dataset, step_obj.capacity[0], flush)
+    t_blend, t_raster, R_inst = time_blend_backward(params, dataset, step_obj.capacity[0], flush)
     P = 640 * 480
     alg_bytes = 56.0 * R_inst + 32.0 * P + 20.0 * G  # blend backward, 6 channels, geometry-only partials, per launch
     achieved = alg_bytes / t_blend / 1e9
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(prof):
-        try:
-            traffic = json.load(open(prof)).get("blend_backward_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    prof = load_profile_json("roofline_traffic.json") or {}
+    pk = prof.get(str(G), {}) if isinstance(prof.get(str(G)), dict) else {}
+    traffic = pk.get("blend_backward_dram_bytes_per_launch", prof.get("blend_backward_dram_bytes_per_launch") if G == 50000 else None)
+    warp_insts = pk.get("blend_backward_warp_instructions_per_launch")
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak = 148 * 4 * sm_mhz * 1e6            # warp instructions / s: 148 SMs x 4 schedulers x 1 per clock
+    agg_bytes = 260.0 * G + 124.0 * R_inst + 44.0 * P   # one 3-channel fwd+bwd of one camera, every byte once
+    roofline = {"bound": "hbm", "kernel": "gsd_blend_bwd_chunk_kernel<6,geom> (+ prefix kernel)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
+                "kernel_us": t_blend * 1e6, "instances_per_camera": R_inst,
+                "issue_slot": {"note": "the blend kernels are instruction-issue bound, not HBM bound (DESIGN.md §6): this is the binding roof",
+                               "warp_instructions_per_launch": warp_insts, "source": "profiles/roofline_traffic.json (ncu smsp__inst_executed.sum)" if warp_insts else None,
+                               "peak_warp_inst_per_s": issue_peak, "sm_mhz": sm_mhz,
+                               "frac": (warp_insts / t_blend / issue_peak) if warp_insts else None},
+                "aggregate": {"what": "SURVEY.md §8(d) rasterizer unit (260 G + 124 R + 44 P bytes: one 3-channel forward+backward of one camera) "
+                                      "over the time of OUR fused 6-channel forward+backward (which replaces TWO such reference passes)",
+                              "bytes": agg_bytes, "raster_fwd_bwd_us": t_raster * 1e6, "achieved": agg_bytes / t_raster / 1e9,
+                              "frac": agg_bytes / t_raster / 1e9 / peak, "frac_counting_both_replaced_passes": 2 * agg_bytes / t_raster / 1e9 / peak,
+                              "whole_step_frac": 2 * agg_bytes / (dev_s / args.steps) / 1e9 / peak},
+                "stages": load_profile_json("r2_stage_table_%dk.json" % (G // 1000))}
 
     times = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device=device)
     if world > 1:
@@ -303,19 +443,16 @@ def run_ours(args):
             "metric": "tracking iters/sec", "value": world * args.steps / dev_s, "unit": "iters/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "train_gs.py steady-state iteration (t>0), %dk Gaussians, 4 cams @640x480, 1 episode per GPU" % (G // 1000),
-                       "gaussians": G, "cameras": n_cams, "image": "640x480", "knn": 20, "instances_per_camera": R_inst,
-                       "parallelism": "episode-per-gpu x%d" % world, "l2": "256 MiB flush between timed steps (excluded from step time)",
-                       "timing": "CUDA events per step on the launch stream, max over ranks"},
+            "config": make_config(G, world, n_cams),
             "e2e": {"value": world * args.steps / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(own_per_iter * args.steps), "gpu_launches_per_step": int(own_per_iter),
             "library_launches_per_step": int(lib_per_iter),
-            "roofline": {"bound": "hbm", "kernel": "gsd_blend_bwd_chunk_kernel<6,geom> (+ prefix kernel)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
-                         "kernel_us": t_blend * 1e6},
+            "roofline": roofline,
+            "capacity_check": {"max_instances_seen": hw, "overflowed_calls": n_over, "capacity": min(step_obj.capacity.values())},
             "clocks": clocks, "wall_s": t_wall, "final_loss": last_loss,
         }
+    del step_obj, eager
     return line, rank, world
 
 
@@ -365,18 +502,31 @@ def run_reference(args):
     if rank != 0:
         return None, rank, world
     G = args.gaussians
-    done, dt, cores = cpu_iterations(G, args.steps, min(args.warmup, 1), budget_s=150.0)
+    done, dt, cores = cpu_iterations(G, args.steps, args.warmup, budget_s=150.0)
     val = done / dt
     sample = "%d of the requested %d iterations (time-bounded), same config as the GPU arm" % (done, args.steps)
     line = {"impl": "reference", "metric": "tracking iters/sec", "value": val, "unit": "iters/s", "n_gpus": world, "steps": done,
-            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "train_gs.py steady-state iteration (t>0), %dk Gaussians, 4 cams @640x480" % (G // 1000),
-                       "gaussians": G, "cameras": 4, "image": "640x480", "knn": 20,
-                       "note": "reference iteration on host cores: oracle port (C rasterizer restatement + CPU PyTorch); the "
-                               "reference's own rasterizer is CUDA-only and un-vendored"},
+            "config": make_config(G, world),
+            "note": "reference iteration on host cores: oracle port (C rasterizer restatement + CPU PyTorch); the reference's own "
+                    "rasterizer is CUDA-only and un-vendored.  A CPU process does not scale with --gpus: rank 0 alone runs it, so at "
+                    "N > 1 the driver's ratio compares N GPUs with this one process",
             "cpu_baseline": {"value": val, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    return line, rank, world
+
+
+def run_upstream_arm(args):
+    rank, local_rank, world = env_rank()
+    if rank != 0:
+        return None, rank, world
+    torch.cuda.set_device(local_rank)
+    r = run_upstream_structure(args.gaussians, min(args.steps, 200), min(args.warmup, 10), torch.device("cuda", local_rank))
+    line = {"impl": "upstream_structure", "metric": "tracking iters/sec", "value": r["value"], "unit": "iters/s", "n_gpus": 1, "steps": r["steps"],
+            "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": make_config(args.gaussians, world), "gpu_reference": r,
+            "e2e": {"value": r["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     return line, rank, world
 
 
@@ -413,10 +563,49 @@ def run_gnn_ours(device, steps=50, warmup=5, n_obj=2000, seed=1):
         torch.cuda.current_stream().synchronize()
     dt_e2e = time.time() - t0
     skin = time_skinning(device, model, ro)
-    return {"skinning": skin, "metric": "GNN steps/sec", "value": steps / dt, "unit": "steps/s", "ms_per_step": 1e3 * dt / steps, "steps": steps,
+    roof = gnn_roofline(device, model, ro, dt / steps)
+    return {"roofline": roof, "skinning": skin, "metric": "GNN steps/sec", "value": steps / dt, "unit": "steps/s", "ms_per_step": 1e3 * dt / steps, "steps": steps,
             "config": {"workload": "predict.py GNN rollout step (edge build + forward + history shift), sloth cfg nf=512, "
                                    "%d particles + 1 tool, 8-NN, connect_all, %d-step horizon, random-init weights with the motion head scaled 1e-3 so the cloud keeps its 8-NN graph" % (n_obj, steps)},
             "e2e": {"value": steps / dt_e2e, "unit": "steps/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": n_obj * 12}}
+
+
+def gnn_roofline(device, model, ro, step_s, iters=20):
+    """(i) the north-star's scatter-reduce (gsd_gnn_aggregate) timed alone against the HBM roof: algorithmic bytes
+    4 E F (A_e) + 8 E (indices) + 12 N F (P_r | P_s read, agg written); (ii) the step's real FLOPs (weight-split
+    formulation, 3 error-compensated TF32 products each) against the dense TF32 tensor peak (= half the measured bf16 peak)."""
+    from gs_dynamics_b200 import gnn
+    peak, src = measured_peaks()
+    edges = gnn.construct_edges_index(ro.states[:, -1], ro.adj_thresh, ro.state_mask, ro.eef_mask, topk=ro.topk, connect_all=ro.connect_all, n_tool=1)
+    E, N, Fd = int(edges.n_edges[0]), edges.N, 512
+    A = torch.randn(1, edges.capacity, Fd, device=device)
+    P = torch.randn(N, 2 * Fd, device=device)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    ts = []
+    with torch.no_grad():
+        for i in range(iters + 3):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gnn._Aggregate.apply(A, P, edges)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1) * 1e-3)
+    t = float(np.median(ts))
+    alg = 4.0 * E * Fd + 8.0 * E + 12.0 * N * Fd
+    in_dim = 14
+    flops = N * 2 * (in_dim * Fd + 2 * Fd * Fd) + E * 2 * (14 * Fd + 2 * Fd * Fd) + E * 2 * Fd * Fd + 3 * (N * 2 * Fd * 2 * Fd + N * 2 * 2 * Fd * Fd) + N * 2 * (2 * Fd * Fd + 3 * Fd)
+    tf32_peak = None
+    pj = load_profile_json("../MEASURED_PEAKS.json")
+    if pj and "bf16_tflops" in pj:
+        tf32_peak = 0.5 * float(pj["bf16_tflops"])
+    return {"bound": "hbm", "kernel": "gsd_gnn_aggregate (rows + heavy tool row)", "achieved": alg / t / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": alg / t / 1e9 / peak, "kernel_us": t * 1e6, "algorithmic_bytes": alg, "edges": E, "nodes": N, "peak_source": src,
+            "note": "flushed L2: in the step the operands are L2-resident (written by the preceding GEMM), so the in-step time is lower",
+            "dense_layers": {"real_flops_per_step": flops, "x3_compensated_tf32_flops": 3 * flops, "achieved_tflops_whole_step": 3 * flops / step_s / 1e12,
+                             "tf32_peak_tflops": tf32_peak, "frac_whole_step": (3 * flops / step_s / 1e12 / tf32_peak) if tf32_peak else None,
+                             "peak_source": "0.5 x MEASURED_PEAKS.json bf16_tflops (dense TF32 = half of bf16)"}}
 
 
 def run_gnn_batched(device, B=1000, n_obj=100, steps=10, warmup=3):
@@ -564,14 +753,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)  # one reference frame = 2000 iterations (train_gs.py:25)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gaussians", type=int, default=50000)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "upstream_structure"])
+    ap.add_argument("--gaussians", type=int, default=100000)   # BASELINE configs[2] / the north-star's target size
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
-    ap.add_argument("--no-gnn", action="store_true", help="skip the secondary GNN steps/sec measurement")
+    ap.add_argument("--episode-frames", type=int, default=20)
+    ap.add_argument("--no-gnn", action="store_true", help="skip the secondary GNN measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip episode / 50k / render / gpu_reference side objects")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
-        line, rank, world = run_reference(args)
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl in ("reference", "upstream_structure"):
+        line, rank, world = run_reference(args) if args.impl == "reference" else run_upstream_arm(args)
         if line is not None:
             print(json.dumps(line), flush=True)
         return
@@ -588,14 +779,29 @@ def main():
         if gtrain is not None:
             line["gnn_train"] = gtrain
         if world == 1:
+            dev0 = torch.device("cuda", 0)
+
+            def side(name, fn):   # a side object must never take the headline line down
+                try:
+                    line[name] = fn()
+                except Exception as ex:
+                    line[name] = {"error": repr(ex)}
+            if not args.no_extras:
+                side("gpu_reference", lambda: run_upstream_structure(args.gaussians, 100, 5, dev0))
+                if "value" in line.get("gpu_reference", {}):
+                    line["gpu_reference"]["ours_over_reference_e2e"] = line["e2e"]["value"] / line["gpu_reference"]["value"]
+                    line["gpu_reference"]["ours_over_reference_device"] = line["value"] / line["gpu_reference"]["value"]
+                side("episode", lambda: run_episode(dev0, args.gaussians, args.episode_frames, 2000))
+                side("secondary_50k", lambda: secondary_50k(dev0))
+                side("render_1280x720", lambda: run_render_720p(dev0, args.gaussians))
             done, dt, cores = cpu_iterations(args.gaussians, 10 ** 9, 1, budget_s=args.cpu_baseline_seconds)
             line["cpu_baseline"] = {"value": done / dt, "unit": "iters/s", "cores": cores, "kind": "port",
                                     "sample": "%d iterations in %.1f s of the same workload (oracle port on host cores)" % (done, dt)}
             if not args.no_gnn:
                 try:
-                    g = run_gnn_ours(torch.device("cuda", 0))
+                    g = run_gnn_ours(dev0)
                     g["cpu_baseline"] = run_gnn_cpu()
-                    g["mppi_batch"] = run_gnn_batched(torch.device("cuda", 0))
+                    g["mppi_batch"] = run_gnn_batched(dev0)
                     line["gnn"] = g
                     if "error" not in line.get("gnn_train", {"error": 1}):
                         line["gnn_train"]["cpu_baseline"] = run_gnn_train_cpu()
@@ -608,6 +814,19 @@ def main():
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+
+
+def secondary_50k(device, steps=500, warmup=20):
+    """BASELINE configs[1] (single frame, 50k Gaussians): device-resident iterations/s, same method as the headline."""
+    from gs_dynamics_b200 import tracking as TR
+    params, variables, opt, dataset, host = build_gpu_problem(50000, 0, device)
+    step = TR.FusedTrackingStep(params, variables, opt, dataset, use_graph=True)
+    step.prepare()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    dt = time_device_steps(step, len(dataset), random.Random(0), steps, warmup, flush)
+    step.check_capacity()
+    return {"metric": "tracking iters/sec", "value": steps / dt, "unit": "iters/s", "ms_per_step": 1e3 * dt / steps, "steps": steps,
+            "config": make_config(50000, 1)}
 
 
 if __name__ == "__main__":

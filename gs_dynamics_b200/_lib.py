@@ -26,6 +26,7 @@ class GsdRasterFwd(C.Structure):
         ("colors0", C.c_void_p), ("colors1", C.c_void_p),
         ("out_color", C.c_void_p), ("out_depth", C.c_void_p), ("radii", C.c_void_p),
         ("geom_ws", C.c_void_p), ("binning_ws", C.c_void_p), ("image_ws", C.c_void_p), ("status", C.c_void_p),
+        ("sticky", C.c_void_p),
     ]
 
 

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 gsd_bin_scan_kernel(int n_pre_blocks, int n_tiles, int64_t capacity, int max_items, uint32_t *__restrict__ block_sum,
                     uint32_t *__restrict__ block_base, int32_t *__restrict__ tile_base, uint2 *__restrict__ ranges,
                     int32_t *__restrict__ chunk_ptr, int32_t *__restrict__ item_tile, int32_t *__restrict__ counters,
-                    int32_t *__restrict__ sort_order, int32_t *__restrict__ status) {
+                    int32_t *__restrict__ sort_order, int32_t *__restrict__ status, int32_t *__restrict__ sticky) {
     __shared__ int s_warp[33];
     __shared__ int s_cls[3], s_fill[3];
     const int t = threadIdx.x;
@@ -187,6 +187,10 @@ gsd_bin_scan_kernel(int n_pre_blocks, int n_tiles, int64_t capacity, int max_ite
     if (t == 0) {
         status[0] = R;
         status[1] = ((long long)R > capacity) ? 1 : 0;
+        if (sticky) {   // single writer (this thread of this one-CTA kernel; forward calls on one stream are ordered)
+            sticky[0] = max(sticky[0], R);
+            if ((long long)R > capacity) sticky[1] += 1;
+        }
     }
     for (int i = t; i < n_tiles; i += SCAN_THREADS) chunk_ptr[i] = tile_base[i]; // keep the totals: chunk_ptr is scratch here
     __syncthreads();
@@ -447,7 +451,7 @@ int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const Gs
     gsd_bin_tile_sum_kernel<<<(tiles + 7) / 8, 256, 0, st>>>(tiles, b.n_bb, b.table, b.tile_base);
     GSD_LAUNCH_CHECK();
     gsd_bin_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(n_pre, tiles, cap, b.max_items, g.block_sum, g.block_base, b.tile_base,
-                                                     b.ranges, b.chunk_ptr, b.item_tile, b.counters, b.sort_order, a->status);
+                                                     b.ranges, b.chunk_ptr, b.item_tile, b.counters, b.sort_order, a->status, a->sticky);
     GSD_LAUNCH_CHECK();
     gsd_bin_tile_scan_kernel<<<(tiles + 7) / 8, 256, 0, st>>>(tiles, b.n_bb, b.table, b.tile_base);
     GSD_LAUNCH_CHECK();

@@ -55,10 +55,11 @@ def get_custom_dataset(t, md, seq, data_root="./data", device="cuda"):
 
 
 def get_batch(todo_dataset, dataset):
-    """train_utils.py:81-85: cameras are drawn without replacement until the list is empty, then refilled."""
-    if not todo_dataset:
-        todo_dataset.extend(dataset)
-    return todo_dataset.pop(randint(0, len(todo_dataset) - 1))
+    """train_utils.py:81-85.  The reference refills by REBINDING its local (`todo_dataset = dataset.copy()`), so the caller's
+    list stays empty and every call draws one camera uniformly WITH replacement using one randint(0, len - 1): reproduced
+    exactly (same draws for the same random.seed), the caller's list is left untouched."""
+    todo = todo_dataset if todo_dataset else list(dataset)
+    return todo.pop(randint(0, len(todo) - 1))
 
 
 def initialize_params(seq, md, init_pt_cld_path, data_root="./data", device="cuda"):
@@ -137,6 +138,7 @@ def train(seq, exp, remove_threshold=0.005, remove_thresh_5k=0.25, weight_soft_c
     loss_kwargs = dict(weight_soft_col_cons=weight_soft_col_cons, weight_im=weight_im, weight_seg=weight_seg, weight_rigid=weight_rigid,
                        weight_bg=weight_bg, weight_iso=weight_iso, weight_rot=weight_rot)
     output_params, path = [], None
+    step = None
     for t in range(num_timesteps):
         dataset = get_custom_dataset(t, md, seq, data_root, device)
         todo_dataset = []
@@ -154,11 +156,13 @@ def train(seq, exp, remove_threshold=0.005, remove_thresh_5k=0.25, weight_soft_c
                 f.write(f"Number of points: {params['means3D'].shape[0]}\n")
         else:
             params, variables = TR.initialize_per_timestep(params, variables, optimizer)
-            step = TR.FusedTrackingStep(params, variables, optimizer, dataset, loss_kwargs=loss_kwargs)
-            step.prepare()
-            for i in range(iters_next):
-                curr_data = get_batch(todo_dataset, dataset)
-                step.step(next(j for j, d in enumerate(dataset) if d is curr_data))
+            if step is None:   # graphs captured once, reused for every later frame (only the targets change)
+                step = TR.FusedTrackingStep(params, variables, optimizer, dataset, loss_kwargs=loss_kwargs)
+                step.prepare()
+            else:
+                step.set_targets(dataset)
+            draws = [get_batch(todo_dataset, dataset) for _ in range(iters_next)]
+            TR.run_frame(step, [next(j for j, d in enumerate(dataset) if d is cd) for cd in draws])
             variables = step.variables
         output_params.append(params2cpu(params, t == 0))
         if t == 0:

@@ -68,12 +68,13 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def raster_forward(settings, means3D, opacities, colors0, scales, rotations, colors1=None, bg1=None, capacity=None):
+def raster_forward(settings, means3D, opacities, colors0, scales, rotations, colors1=None, bg1=None, capacity=None, sticky=None):
     """Runs the forward kernels. Returns (color [3*n_sets,H,W], radii [G] int32, depth [1,H,W], state).
 
     capacity=None reproduces upstream behaviour: the instance count R is read back once (one D2H sync, what
     upstream's num_rendered copy does) and buffers are sized exactly.  Passing a capacity >= R makes the call
-    fully asynchronous; state.status[1] is set on the device if it was too small."""
+    fully asynchronous; state.status[1] is set on the device if it was too small, and `sticky` (int32[2] CUDA tensor, zeroed
+    by the caller) accumulates max R / number of overflowed calls across calls (read it once per frame, not per call)."""
     lib = _lib.lib()
     means3D = _f32c(means3D, "means3D")
     dev = means3D.device
@@ -113,6 +114,10 @@ def raster_forward(settings, means3D, opacities, colors0, scales, rotations, col
         d.colors0 = colors0.data_ptr()
         d.colors1 = colors1.data_ptr() if colors1 is not None else None
         d.radii, d.status = radii.data_ptr(), status.data_ptr()
+        if sticky is not None:
+            if sticky.dtype != torch.int32 or not sticky.is_cuda or sticky.numel() < 2:
+                raise ValueError("sticky must be a CUDA int32 tensor with 2 elements")
+            d.sticky = sticky.data_ptr()
 
         if capacity is None:
             sz = _workspace_bytes(G, W, H, n_sets, 0)
@@ -136,7 +141,7 @@ def raster_forward(settings, means3D, opacities, colors0, scales, rotations, col
     state = RasterState()
     state.desc = d
     state.keep = (means3D, opacities, colors0, colors1, scales, rotations, view, proj, bg0, bg1, geom, binning, image,
-                  color, depth, radii, status)
+                  color, depth, radii, status, sticky)
     state.capacity, state.G, state.W, state.H, state.n_sets, state.status = capacity, G, W, H, n_sets, status
     return color, radii, depth, state
 

@@ -145,41 +145,48 @@ def calc_psnr(img1, img2):
 # ----------------------------------------------------------------------------------------------------
 # physical priors (rigid / rot / iso / floor / bg)
 # ----------------------------------------------------------------------------------------------------
+def _track_priors_launch(means3D, rotations, variables, weights):
+    """One launch of gsd_track_losses_fwd_bwd: returns (losses[6] = rigid, rot, iso, floor, bg, weighted total; dL/dmeans3D;
+    dL/drotations).  Plain function: the autograd wrapper below and the fused step both call it (no shared state)."""
+    lib = _lib.lib()
+    x = R._f32c(means3D, "means3D")
+    q = R._f32c(rotations, "rotations")
+    G = x.shape[0]
+    v = variables
+    t = _lib.GsdTrackLosses()
+    fg, bg = v.get("fg_index"), v.get("bg_index")
+    Gf = int(v["prev_inv_rot_fg"].shape[0])
+    K = int(v["neighbor_indices_i32"].shape[1]) if Gf > 0 else 0
+    Gb = int(bg.shape[0]) if bg is not None else 0
+    t.G, t.Gf, t.K, t.Gb = G, Gf, K, Gb
+    ptr = lambda tt: tt.data_ptr() if tt is not None and tt.numel() > 0 else None
+    t.means3D, t.rotations = x.data_ptr(), q.data_ptr()
+    t.fg_index = ptr(fg)
+    t.prev_inv_rot = ptr(v["prev_inv_rot_fg"])
+    t.neighbor_indices, t.neighbor_weight = ptr(v["neighbor_indices_i32"]), ptr(v["neighbor_weight"])
+    t.neighbor_dist, t.prev_offset = ptr(v["neighbor_dist"]), ptr(v["prev_offset"])
+    t.in_ptr, t.in_edge = ptr(v["in_ptr"]), ptr(v["in_edge"])
+    er = v.get("edge_records")
+    if er is not None and er.get("src") is v["prev_offset"] and er.get("ver") == v["prev_offset"]._version:
+        t.edge_records = er["data"].data_ptr()
+    t.bg_index, t.init_bg_pts, t.init_bg_rot = ptr(bg), ptr(v.get("init_bg_pts")), ptr(v.get("init_bg_rot"))
+    t.w_rigid, t.w_rot, t.w_iso, t.w_floor, t.w_bg = [float(w) for w in weights]
+    nbytes = C.c_size_t()
+    _lib.check(lib.gsd_track_losses_workspace_bytes(Gf, Gb, C.byref(nbytes)), "gsd_track_losses_workspace_bytes")
+    with torch.cuda.device(x.device):
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
+        losses = torch.empty(6, dtype=torch.float32, device=x.device)
+        gx = torch.empty_like(x)
+        gq = torch.empty_like(q)
+        t.ws, t.losses, t.grad_means3D, t.grad_rotations = ws.data_ptr(), losses.data_ptr(), gx.data_ptr(), gq.data_ptr()
+        _lib.check(lib.gsd_track_losses_fwd_bwd(C.byref(t), _stream()), "gsd_track_losses_fwd_bwd")
+    return losses, gx, gq
+
+
 class _TrackPriors(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, rotations, variables, weights):
-        lib = _lib.lib()
-        x = R._f32c(means3D, "means3D")
-        q = R._f32c(rotations, "rotations")
-        G = x.shape[0]
-        v = variables
-        t = _lib.GsdTrackLosses()
-        fg, bg = v.get("fg_index"), v.get("bg_index")
-        Gf = int(v["prev_inv_rot_fg"].shape[0])
-        K = int(v["neighbor_indices_i32"].shape[1]) if Gf > 0 else 0
-        Gb = int(bg.shape[0]) if bg is not None else 0
-        t.G, t.Gf, t.K, t.Gb = G, Gf, K, Gb
-        ptr = lambda tt: tt.data_ptr() if tt is not None and tt.numel() > 0 else None
-        t.means3D, t.rotations = x.data_ptr(), q.data_ptr()
-        t.fg_index = ptr(fg)
-        t.prev_inv_rot = ptr(v["prev_inv_rot_fg"])
-        t.neighbor_indices, t.neighbor_weight = ptr(v["neighbor_indices_i32"]), ptr(v["neighbor_weight"])
-        t.neighbor_dist, t.prev_offset = ptr(v["neighbor_dist"]), ptr(v["prev_offset"])
-        t.in_ptr, t.in_edge = ptr(v["in_ptr"]), ptr(v["in_edge"])
-        er = v.get("edge_records")
-        if er is not None and er.get("src") is v["prev_offset"] and er.get("ver") == v["prev_offset"]._version:
-            t.edge_records = er["data"].data_ptr()
-        t.bg_index, t.init_bg_pts, t.init_bg_rot = ptr(bg), ptr(v.get("init_bg_pts")), ptr(v.get("init_bg_rot"))
-        t.w_rigid, t.w_rot, t.w_iso, t.w_floor, t.w_bg = [float(w) for w in weights]
-        nbytes = C.c_size_t()
-        _lib.check(lib.gsd_track_losses_workspace_bytes(Gf, Gb, C.byref(nbytes)), "gsd_track_losses_workspace_bytes")
-        with torch.cuda.device(x.device):
-            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
-            losses = torch.empty(6, dtype=torch.float32, device=x.device)
-            gx = torch.empty_like(x)
-            gq = torch.empty_like(q)
-            t.ws, t.losses, t.grad_means3D, t.grad_rotations = ws.data_ptr(), losses.data_ptr(), gx.data_ptr(), gq.data_ptr()
-            _lib.check(lib.gsd_track_losses_fwd_bwd(C.byref(t), _stream()), "gsd_track_losses_fwd_bwd")
+        losses, gx, gq = _track_priors_launch(means3D, rotations, variables, weights)
         ctx.save_for_backward(gx, gq)
         ctx.mark_non_differentiable(losses)
         return losses[5], losses
@@ -192,10 +199,14 @@ class _TrackPriors(torch.autograd.Function):
 
 def pack_edge_records(variables):
     """Packs the per-edge tables into 32-byte records for the priors kernel. Call after prev_offset changed (once per
-    timestep); a stale pack is detected (tensor identity + version) and ignored."""
+    timestep); a stale pack is detected (tensor identity + version) and ignored.  The record buffer is reused across calls."""
     v = variables
     Gf, K = v["neighbor_indices_i32"].shape
-    out = torch.empty((Gf * K, 8), dtype=torch.float32, device=v["prev_offset"].device)
+    old = v.get("edge_records")
+    if old is not None and old["data"].shape == (Gf * K, 8) and old["data"].device == v["prev_offset"].device:
+        out = old["data"]   # in place: a captured CUDA graph keeps reading this buffer on the following frames
+    else:
+        out = torch.empty((Gf * K, 8), dtype=torch.float32, device=v["prev_offset"].device)
     with torch.cuda.device(out.device):
         _lib.check(_lib.lib().gsd_track_pack_edges(Gf, K, v["neighbor_indices_i32"].data_ptr(), v["neighbor_weight"].data_ptr(),
                                                    v["neighbor_dist"].data_ptr(), v["prev_offset"].data_ptr(), out.data_ptr(),
@@ -215,9 +226,9 @@ def track_prior_losses(means3D, rotations, variables, weight_rigid, weight_rot, 
 # ----------------------------------------------------------------------------------------------------
 class _RasterizeTwoSets(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, means3D, means2D, opacities, colors0, colors1, scales, rotations, settings, bg1, capacity):
+    def forward(ctx, means3D, means2D, opacities, colors0, colors1, scales, rotations, settings, bg1, capacity, sticky):
         color, radii, depth, state = R.raster_forward(settings, means3D, opacities, colors0, scales, rotations,
-                                                       colors1=colors1, bg1=bg1, capacity=capacity)
+                                                       colors1=colors1, bg1=bg1, capacity=capacity, sticky=sticky)
         ctx.state = state
         ctx.opac_shape = opacities.shape
         ctx.need_m2d = means2D is not None and means2D.requires_grad
@@ -230,14 +241,14 @@ class _RasterizeTwoSets(torch.autograd.Function):
         g = R.raster_backward(ctx.state, grad_color, need_means2D=ctx.need_m2d)
         ctx.state = None
         return (g["means3D"], g["means2D"], g["opacities"].reshape(ctx.opac_shape), g["colors0"], g["colors1"], g["scales"],
-                g["rotations"], None, None, None)
+                g["rotations"], None, None, None, None)
 
 
-def render_two_sets(settings, rendervar, colors1, bg1=None, capacity=None):
+def render_two_sets(settings, rendervar, colors1, bg1=None, capacity=None, sticky=None):
     """One 6-channel pass: channels 0-2 use rendervar['colors_precomp'], 3-5 use colors1 (same geometry)."""
     return _RasterizeTwoSets.apply(rendervar['means3D'], rendervar.get('means2D'), rendervar['opacities'],
                                    rendervar['colors_precomp'], colors1, rendervar['scales'], rendervar['rotations'],
-                                   settings, bg1, capacity)
+                                   settings, bg1, capacity, sticky)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -255,7 +266,7 @@ def update_seen(radius, variables):
 
 def get_loss(params, curr_data, variables, is_initial_timestep, weight_soft_col_cons=0.01, weight_im=50.0,
              weight_seg=200.0, weight_rigid=200.0, weight_bg=200.0, weight_iso=1000.0, weight_rot=4.0, fused=None,
-             capacity=None):
+             capacity=None, sticky=None):
     """Same contract as the reference's get_loss (train_utils.py:167-246): returns (loss, variables) and updates
     variables['means2D' | 'max_2D_radius' | 'seen'].  `fused` (default: t > 0) renders RGB+seg in one pass; in that mode
     variables['means2D'].grad holds the gradient of BOTH renders (only the t = 0 densifier reads it, so t = 0 defaults to
@@ -268,7 +279,7 @@ def get_loss(params, curr_data, variables, is_initial_timestep, weight_soft_col_
     curr_id = curr_data['id']
     cam = curr_data['cam']
     if fused:
-        out, radius, _ = render_two_sets(cam, rendervar, params['seg_colors'], capacity=capacity)
+        out, radius, _ = render_two_sets(cam, rendervar, params['seg_colors'], capacity=capacity, sticky=sticky)
         im, seg = out[:3], out[3:]
     else:
         im, radius, _ = Renderer(raster_settings=cam)(**rendervar)
@@ -448,9 +459,18 @@ def initialize_per_timestep(params, variables, optimizer):
 # ----------------------------------------------------------------------------------------------------
 # CUDA-graph fast path: one replay = get_loss + backward + Adam for one camera
 # ----------------------------------------------------------------------------------------------------
+class CapacityOverflow(RuntimeError):
+    """Raised when a replayed iteration produced more tile instances than the captured buffers hold."""
+
+
 class TrackingStep:
     """Captures the steady-state (t > 0) iteration of train_gs.py:25-39 per camera. Parameters, Adam state, neighbour
-    tables and targets are static device tensors; `step(cam_id)` replays the graph and returns the device loss scalar."""
+    tables and targets are static device tensors; `step(cam_id)` replays the graph and returns the device loss scalar.
+
+    The rasterizer buffers of a captured graph have a fixed instance capacity (probe x capacity_margin) where the reference
+    sizes them exactly from num_rendered on every call (train_utils.py:178).  Every forward call therefore records its
+    instance count in `self.sticky` (device int32[2]: high-water R, number of overflowed calls); `check_capacity()` reads it
+    with ONE 8-byte copy — call it once per frame.  train_frames / io.train redo a frame whose replays overflowed."""
 
     def __init__(self, params, variables, optimizer, dataset, is_initial_timestep=False, loss_kwargs=None,
                  capacity_margin=1.5, use_graph=True):
@@ -464,10 +484,12 @@ class TrackingStep:
         self.kw = dict(loss_kwargs or {})
         self.margin = capacity_margin
         self.use_graph = use_graph
-        self.graphs, self.losses, self.capacity, self.status = {}, {}, {}, {}
+        self.graphs, self.losses, self.capacity = {}, {}, {}
+        self.sticky = torch.zeros(2, dtype=torch.int32, device=params['means3D'].device) if 'means3D' in params else None
 
     def _iteration(self, data, capacity):
-        loss, self.variables = get_loss(self.params, data, self.variables, self.is_initial, capacity=capacity, **self.kw)
+        loss, self.variables = get_loss(self.params, data, self.variables, self.is_initial, capacity=capacity,
+                                        sticky=self.sticky if capacity is not None else None, **self.kw)
         loss.backward()
         self.optimizer.step()
         return loss.detach()
@@ -479,13 +501,33 @@ class TrackingStep:
                                            rv['rotations'])
         return max(1024, int(int(st.status[0].item()) * self.margin))
 
+    # ---- optimisation state that an iteration modifies: saved / restored IN PLACE (captured pointers stay valid)
+    def snapshot(self):
+        snap = {'max_2D_radius': self.variables['max_2D_radius'].clone(), 'opt': []}
+        for g in self.optimizer.param_groups:
+            for p in g['params']:
+                st = self.optimizer.state[p]
+                snap['opt'].append((p, p.detach().clone(), st['exp_avg'].clone(), st['exp_avg_sq'].clone(), st['step'].clone()))
+        return snap
+
+    @torch.no_grad()
+    def restore(self, snap):
+        self.variables['max_2D_radius'].copy_(snap['max_2D_radius'])
+        for p, val, m, v, step in snap['opt']:
+            st = self.optimizer.state[p]
+            p.data.copy_(val)
+            st['exp_avg'].copy_(m); st['exp_avg_sq'].copy_(v); st['step'].copy_(step)
+
     def prepare(self, cam_ids=None):
-        """Warm-up (eager, on a side stream) and capture. Warm-up iterations are real optimisation steps."""
+        """Capacity probe, one eager warm-up iteration per camera on a side stream, capture.  The warm-up iterations are undone
+        (parameters, Adam moments, step counters, max_2D_radius restored), so a frame is exactly the iterations the caller
+        asks for (train_gs.py:25: 2 000), not 2 000 + n_cams."""
         cam_ids = list(range(len(self.dataset))) if cam_ids is None else list(cam_ids)
         for c in cam_ids:
             self.capacity[c] = self._probe_capacity(self.dataset[c])
         if not self.use_graph:
             return
+        snap = self.snapshot()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -493,12 +535,29 @@ class TrackingStep:
                 self.optimizer.zero_grad(set_to_none=True)
                 self._iteration(self.dataset[c], self.capacity[c])
         torch.cuda.current_stream().wait_stream(s)
+        self.restore(snap)
         for c in cam_ids:
             g = torch.cuda.CUDAGraph()
             self.optimizer.zero_grad(set_to_none=True)
             with torch.cuda.graph(g):
                 self.losses[c] = self._iteration(self.dataset[c], self.capacity[c])
             self.graphs[c] = g
+        self.sticky.zero_()
+
+    def check_capacity(self, raise_on_overflow=True):
+        """One 8-byte D2H read: (high-water instance count, overflowed forward calls) since the last call; clears both."""
+        hw, n_over = [int(x) for x in self.sticky.tolist()]
+        self.sticky.zero_()
+        if n_over and raise_on_overflow:
+            raise CapacityOverflow("%d rasterizer call(s) exceeded the captured capacity (max R = %d, capacities %s)"
+                                   % (n_over, hw, sorted(self.capacity.values())))
+        return hw, n_over
+
+    def grow(self, factor=1.5):
+        """Re-probe at the current state with a larger margin and re-capture (after an overflow)."""
+        self.margin *= factor
+        self.graphs, self.losses = {}, {}
+        self.prepare(list(self.capacity.keys()) or None)
 
     def step(self, cam_id):
         if self.use_graph:
@@ -540,6 +599,11 @@ class FusedTrackingStep(TrackingStep):
         self.block_counter = torch.zeros(1, dtype=torch.int32, device=params['means3D'].device)   # self-resetting (gsd_track_update)
         self.lr = {g['name']: float(g['lr']) for g in optimizer.param_groups}
 
+    def set_targets(self, dataset):
+        """Next frame of the episode: same cameras, new images (train_utils.py:10-29 loads them per frame)."""
+        for c, d in enumerate(dataset):
+            self.set_target(c, d['im'], d['seg'])
+
     def set_target(self, cam_id, im, seg):
         """New target images for a camera (e.g. the next frame's, from pinned host memory): copies them into the static
         buffers the captured graph reads and refreshes their window statistics."""
@@ -571,15 +635,16 @@ class FusedTrackingStep(TrackingStep):
             fork.record(main)
             with torch.cuda.stream(self.side):
                 self.side.wait_event(fork)
-                prior, parts = _TrackPriors.forward(_NullCtx(), x.detach(), self.rot, V, (self.w['weight_rigid'], self.w['weight_rot'],
-                                                    self.w['weight_iso'], FLOOR_WEIGHT, self.w['weight_bg']))
-                gx_p, gq_p = _NullCtx.saved
+                parts, gx_p, gq_p = _track_priors_launch(x.detach(), self.rot, V, (self.w['weight_rigid'], self.w['weight_rot'],
+                                                         self.w['weight_iso'], FLOOR_WEIGHT, self.w['weight_bg']))
+                prior = parts[5]
                 join = torch.cuda.Event()
                 join.record(self.side)
             for tns in (prior, parts, gx_p, gq_p):
                 tns.record_stream(main)
             color, radii, _, state = R.raster_forward(data['cam'], x.detach(), self.opac, self.rgb, self.scales, self.rot,
-                                                      colors1=self.seg, capacity=capacity)
+                                                      colors1=self.seg, capacity=capacity,
+                                                      sticky=self.sticky if capacity is not None else None)
             ws = _ph_workspace(color)
             ph = torch.empty(8, dtype=torch.float32, device=x.device)
             d = _ph_desc(color, tgt, 2, 0.8, 0.2, (self.w['weight_im'], self.w['weight_seg']), ws,
@@ -622,17 +687,6 @@ class FusedTrackingStep(TrackingStep):
             V['prior_losses'] = parts
             V['photometric_losses'] = ph[:7]
         return ph[7]
-
-
-class _NullCtx:
-    """Stand-in autograd context so that _TrackPriors.forward can be called directly (no graph) in the fused step."""
-    saved = None
-
-    def save_for_backward(self, *t):
-        _NullCtx.saved = t
-
-    def mark_non_differentiable(self, *t):
-        pass
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -710,7 +764,7 @@ def _rotation_matrices(q):
 
 
 @torch.no_grad()
-def densify(params, variables, optimizer, i, remove_thresh, remove_thresh_5k, scale_scene_radius, grad_thresh=0.0002):
+def densify(params, variables, optimizer, i, remove_thresh, remove_thresh_5k, scale_scene_radius, grad_thresh=0.0002, normal_sampler=None):
     """Clone / split / prune schedule of external.py:229-299 (t = 0 only): every 100 iterations for 500 <= i <= 5000 points
     with a large screen-space gradient are cloned (small) or split in two (large, sampled from the Gaussian, scale / 1.6);
     transparent (and, after 3000, oversized) points are pruned; opacities are reset to 0.01 every 3000 iterations."""
@@ -732,7 +786,7 @@ def densify(params, variables, optimizer, i, remove_thresh, remove_thresh_5k, sc
             n = 2
             new = {k: params[k].detach()[to_split].repeat(n, 1) for k in PER_POINT_KEYS}
             stds = torch.exp(params['log_scales'].detach())[to_split].repeat(n, 1)
-            samples = torch.normal(mean=torch.zeros_like(stds), std=stds)
+            samples = torch.normal(mean=torch.zeros_like(stds), std=stds) if normal_sampler is None else normal_sampler(stds)
             rots = _rotation_matrices(params['unnorm_rotations'].detach()[to_split]).repeat(n, 1, 1)
             new['means3D'] = new['means3D'] + torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1)
             new['log_scales'] = torch.log(torch.exp(new['log_scales']) / (0.8 * n))
@@ -773,18 +827,41 @@ def initialize_params_from_point_cloud(init_pt_cld, cam_centers, device="cuda", 
     return params, variables
 
 
+def run_frame(step, cam_sequence, max_retries=3):
+    """One tracked frame (train_gs.py:25-39): step.step(c) for every c of cam_sequence — exactly len(cam_sequence) optimiser
+    iterations — then ONE capacity check.  If any replay overflowed the captured rasterizer buffers the frame is redone from
+    its start state with larger buffers (re-probe + re-capture) instead of keeping iterations that dropped instances."""
+    cam_sequence = list(cam_sequence)
+    for attempt in range(max_retries + 1):
+        snap = step.snapshot()
+        for c in cam_sequence:
+            step.step(c)
+        hw, n_over = step.check_capacity(raise_on_overflow=False)
+        if n_over == 0:
+            return hw
+        if attempt == max_retries:
+            raise CapacityOverflow("frame still overflows after %d re-captures (max R = %d)" % (max_retries, hw))
+        step.restore(snap)
+        step.grow(max(1.5, 1.25 * hw / max(1, min(step.capacity.values()))))
+    return hw
+
+
 def train_frames(params, variables, optimizer, datasets, iters_first=10000, iters_next=2000, num_knn=20, densify_args=None,
                  loss_kwargs=None, seed=0):
     """The episode loop of train_gs.py:10-46 on in-memory per-frame datasets (lists of {'cam','im','seg','id'}): 10 000
-    iterations with densification at t = 0, then FusedTrackingStep graphs for every later frame. Returns per-frame snapshots of
-    (means3D, rgb_colors, unnorm_rotations) like params2cpu (helpers.py:141-147)."""
+    iterations with densification at t = 0, then ONE FusedTrackingStep whose per-camera CUDA graphs are captured at the first
+    tracked frame and reused for every later frame (only the target images change; all other buffers are updated in place).
+    Cameras are drawn like the reference's get_batch (train_utils.py:81-85: uniform WITH replacement — its refill rebinds a
+    local, so the caller's todo list stays empty).  Returns per-frame snapshots of (means3D, rgb_colors, unnorm_rotations)
+    like params2cpu (helpers.py:141-147)."""
     import random
     rnd = random.Random(seed)
     out = []
+    step = None
     for t, dataset in enumerate(datasets):
         if t == 0:
             for i in range(iters_first):
-                data = dataset[rnd.randrange(len(dataset))]
+                data = dataset[rnd.randint(0, len(dataset) - 1)]
                 loss, variables = get_loss(params, data, variables, True, fused=False, **(loss_kwargs or {}))
                 loss.backward()
                 with torch.no_grad():
@@ -795,10 +872,12 @@ def train_frames(params, variables, optimizer, datasets, iters_first=10000, iter
             variables = initialize_post_first_timestep(params, variables, optimizer, num_knn)
         else:
             params, variables = initialize_per_timestep(params, variables, optimizer)
-            step = FusedTrackingStep(params, variables, optimizer, dataset, loss_kwargs=loss_kwargs)
-            step.prepare()
-            for i in range(iters_next):
-                step.step(rnd.randrange(len(dataset)))
+            if step is None:
+                step = FusedTrackingStep(params, variables, optimizer, dataset, loss_kwargs=loss_kwargs)
+                step.prepare()
+            else:
+                step.set_targets(dataset)
+            run_frame(step, [rnd.randint(0, len(dataset) - 1) for _ in range(iters_next)])
             variables = step.variables
         out.append({k: params[k].detach().cpu().numpy().copy() for k in ('means3D', 'rgb_colors', 'unnorm_rotations')})
     return params, variables, out

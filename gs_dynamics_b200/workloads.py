@@ -43,6 +43,40 @@ def tracking_problem(G, seed=0, num_knn=20, n_cams=4, width=640, height=480):
     return dict(G=G, params=params, variables=variables, cams=cam_list, target=target, seg_colors=sc["seg_colors"])
 
 
+def tracking_problem_gpu(G, seed, device, prob=None):
+    """tracking_problem(G, seed) moved to the device and wired to the library the way train_gs.py leaves it after frame 0
+    (train_utils.py:354-374: kNN tables, frozen learning rates): returns (params, variables, optimizer, dataset, host_targets).
+    Targets are rendered by the CUDA rasterizer from S(G, seed + 1); host_targets are their pinned host copies."""
+    from . import rasterizer as R
+    from . import tracking as TR
+    prob = tracking_problem(G, seed) if prob is None else prob
+    params = {k: torch.nn.Parameter(v.to(device).contiguous()) for k, v in prob["params"].items()}
+    params["rgb_colors"].requires_grad = False
+    v = {k: (t.to(device).contiguous() if isinstance(t, torch.Tensor) else t) for k, t in prob["variables"].items()}
+    v["neighbor_indices_i32"] = v["neighbor_indices"].to(torch.int32).contiguous()
+    v["in_ptr"], v["in_edge"] = TR.build_in_edges(v["neighbor_indices_i32"])
+    v["fg_index"] = None
+    v["bg_index"] = torch.zeros(0, dtype=torch.int32, device=device)
+    TR.pack_edge_records(v)
+    opt = TR.initialize_optimizer(params, v)
+    for g in opt.param_groups:  # steady state: lrs frozen after t = 0 (train_utils.py:370-373)
+        if g["name"] in ("logit_opacities", "log_scales", "cam_m", "cam_c", "rgb_colors"):
+            g["lr"] = 0.0
+    tgt = {k: t.to(device) for k, t in prob["target"].items()}
+    ones = torch.ones_like(tgt["colors_precomp"])
+    dataset, host = [], []
+    for c in prob["cams"]:
+        cam = TR.setup_camera(c["w"], c["h"], c["k"], c["w2c"], near=1.0, far=100, device=device)
+        with torch.no_grad():
+            out, _, _, _ = R.raster_forward(cam, tgt["means3D"], tgt["opacities"], tgt["colors_precomp"], tgt["scales"],
+                                            tgt["rotations"], colors1=ones)
+        im = out[:3].clone()
+        seg = seg_target_from_mask(out[3]).contiguous()
+        dataset.append({"cam": cam, "im": im, "seg": seg, "id": c["id"]})
+        host.append((im.cpu().pin_memory(), seg.cpu().pin_memory()))
+    return params, v, opt, dataset, host
+
+
 def seg_target_from_mask(mask):
     """(seg, 0, 1-seg) colour coding of the reference's dataset loader (train_utils.py:71-75)."""
     return torch.stack((mask, torch.zeros_like(mask), 1 - mask))

@@ -80,7 +80,11 @@ typedef struct {
     void *geom_ws;
     void *binning_ws;
     void *image_ws;
-    int32_t *status; /* [GSD_STATUS_WORDS] */
+    int32_t *status; /* [GSD_STATUS_WORDS], rewritten by every forward call */
+    int32_t *sticky; /* [2] or NULL; never cleared by the library: [0] = max R over the forward calls so far, [1] = number of
+                      * forward calls that overflowed `capacity`. Lets a caller that replays a captured graph thousands of
+                      * times check ONCE per frame that no replay dropped instances (the reference sizes its buffers exactly
+                      * from num_rendered on every call, /root/reference/src/tracking/train_utils.py:178) */
 } GsdRasterFwd;
 
 typedef struct {

@@ -125,3 +125,14 @@ def analytic_one_gaussian_gradients(w=48, h=48, f=90.0, seed=0):
              scales=np.array([(a * E * dx * dx / (2 * v * v)).sum() * 2 * (f / z) ** 2 * s,
                               (a * E * dy * dy / (2 * v * v)).sum() * 2 * (f / z) ** 2 * s, 0.0]))
     return dict(cam=cam, act=act, bg=torch.tensor(bg, dtype=torch.float32), dL=torch.tensor(dL, dtype=torch.float32), grads=g)
+
+
+def pct_rel_err(a, b, q=99.9, eps_frac=1e-3):
+    """Per-element relative error |a - b| / (|b| + eps) with eps = eps_frac * max|b|, at percentile q and at the maximum:
+    unlike rel_err (max-abs error over max-abs value) this does not hide errors on small entries."""
+    a = np.asarray(a, np.float64).reshape(-1)
+    b = np.asarray(b, np.float64).reshape(-1)
+    if a.size == 0:
+        return 0.0, 0.0
+    e = np.abs(a - b) / (np.abs(b) + eps_frac * (np.abs(b).max() + 1e-30))
+    return float(np.percentile(e, q)), float(e.max())

@@ -1,0 +1,60 @@
+"""The same-box GPU baseline (baseline/upstream_structure: structural re-creation of the upstream rasterizer + the reference's
+eager get_loss) must itself be CORRECT to be a meaningful stand-in: its rasterizer is checked against the C oracle, its
+iteration against the product's fused iteration (loss 2e-4 relative; gradients 1e-3 of max — float atomics reorder sums)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import make_camera, make_scene, oracle_backward, oracle_forward, rel_err, settings_from
+
+pytestmark = pytest.mark.gpu
+
+
+def test_upstream_structure_rasterizer_vs_oracle():
+    from baseline import upstream_structure as U
+    cam = make_camera(2, 320, 240)
+    sc, act = make_scene(6000, 4, scale_boost=0.6, box_scale=0.8)
+    bg = [0.2, 0.1, 0.4]
+    dL = torch.randn(3, 240, 320, generator=torch.Generator().manual_seed(1))
+    fo = oracle_forward(act, cam, torch.tensor(bg))
+    bo = oracle_backward(act, cam, torch.tensor(bg), dL)
+    leaves = {k: v.cuda().requires_grad_(True) for k, v in act.items()}
+    m2d = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    Ras, label = U.rasterizer_module(prefer_real=False)
+    im, radii, depth = Ras(raster_settings=settings_from(cam, bg))(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
+                                                                   colors_precomp=leaves["colors_precomp"], scales=leaves["scales"],
+                                                                   rotations=leaves["rotations"])
+    (im * dL.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert np.array_equal(radii.cpu().numpy(), fo["radii"]) or (radii.cpu().numpy() != fo["radii"]).mean() < 1e-3   # compiled with FMA contraction
+    d = np.abs(im.detach().cpu().numpy() - fo["color"])
+    assert (d > 1e-4).mean() < 1e-3 and d.max() < 2e-2
+    assert np.abs(depth.cpu().numpy() - fo["depth"]).max() < 2e-2
+    for k, ko in (("means3D", "means3D"), ("colors_precomp", "colors"), ("scales", "scales"), ("rotations", "rotations")):
+        assert rel_err(leaves[k].grad.cpu(), bo[ko]) < 2e-3, k
+    assert rel_err(leaves["opacities"].grad.cpu().reshape(-1), bo["opacities"]) < 2e-3
+    assert rel_err(m2d.grad.cpu(), bo["means2D"]) < 2e-3
+
+
+def test_upstream_structure_iteration_matches_fused_iteration():
+    from baseline import upstream_structure as U
+    from gs_dynamics_b200 import tracking as TR, workloads
+    G = 20000
+    prob = workloads.tracking_problem(G, 0)
+    params, variables, opt, dataset, _ = workloads.tracking_problem_gpu(G, 0, torch.device("cuda"), prob=prob)
+    bparams = {k: torch.nn.Parameter(v.cuda().contiguous()) for k, v in prob["params"].items()}
+    bparams["rgb_colors"].requires_grad = False
+    bvars = {k: (t.cuda() if isinstance(t, torch.Tensor) else t) for k, t in prob["variables"].items()}
+    bopt = U.make_optimizer(bparams, bvars["scene_radius"])
+    Ras, _ = U.rasterizer_module(prefer_real=False)
+    step = TR.FusedTrackingStep(params, variables, opt, dataset, use_graph=False)
+    step.prepare()
+    l_ours = float(step.step(1))
+    l_base = float(U.iteration(Ras, bparams, dataset[1], bvars, bopt))
+    assert abs(l_ours - l_base) <= 2e-4 * abs(l_base)
+    for k in ("means3D", "unnorm_rotations"):
+        m_ours = opt.state[params[k]]["exp_avg"].cpu().numpy()
+        m_base = bopt.state[bparams[k]]["exp_avg"].cpu().numpy()
+        assert rel_err(m_ours, m_base) < 2e-3, k
+    assert torch.equal(variables["max_2D_radius"], bvars["max_2D_radius"]) or \
+        float((variables["max_2D_radius"] != bvars["max_2D_radius"]).float().mean()) < 1e-3

@@ -216,10 +216,7 @@ def test_tracking_step_graph_matches_eager_and_reduces_loss():
     pb, vb, ob, db = _tracking_problem(2000)
     eager = TR.TrackingStep(pa, va, oa, da, use_graph=False)
     graph = TR.TrackingStep(pb, vb, ob, db, use_graph=True)
-    eager.prepare(); graph.prepare()
-    # the graph path spent len(dataset) warm-up iterations: replay them eagerly to align the two optimisers
-    for c in range(len(da)):
-        eager.step(c)
+    eager.prepare(); graph.prepare()   # prepare() undoes its warm-up iterations: both paths start from the same state
     seq = [0, 1, 1, 0, 1, 0, 0, 1]
     le = [float(eager.step(c)) for c in seq]
     lg = [float(graph.step(c)) for c in seq]
@@ -288,8 +285,6 @@ def test_fused_tracking_step_matches_autograd_path():
     freeze(od)
     fe = TR.FusedTrackingStep(pd, vd, od, dd, use_graph=False)
     fe.prepare()
-    for c in range(len(dd)):
-        fe.step(c)  # align with the graph path's warm-up iterations
     lg = [float(fg.step(c)) for c in seq]
     l2 = [float(fe.step(c)) for c in seq]
     np.testing.assert_allclose(lg, l2, rtol=1e-4)

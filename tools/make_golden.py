@@ -181,6 +181,11 @@ paths = ["camera_1/foreground/foreground_000012.png", "camera_3/color/color_7.pn
 fout["paths_in"] = np.array(paths)
 fout["paths_seg"] = np.array([ref_tu.map_to_segmentation_path(p) for p in paths])
 fout["paths_depth"] = np.array([ref_tu.map_to_depth_path(p) for p in ["camera_1/color_12.png", "x/y/im_000003.png"]])
+import random as _random
+_random.seed(0)
+_ds, _todo = [{"id": i} for i in range(4)], []
+fout["get_batch_ids"] = np.array([ref_tu.get_batch(_todo, _ds)["id"] for _ in range(40)])   # train_utils.py:81-85 as it behaves
+assert _todo == []
 dst = os.path.join(ROOT, "tests", "golden", "formats_golden.npz")
 np.savez_compressed(dst, **fout)
 print("wrote", dst, os.path.getsize(dst), "bytes")
@@ -260,3 +265,75 @@ rout = dict(rig_X=X.numpy(), rig_Y=Y.detach().numpy(), rig_mask=qmask.numpy(), r
 dst = os.path.join(ROOT, "tests", "golden", "gnn_rigid_golden.npz")
 np.savez_compressed(dst, **rout)
 print("wrote", dst, os.path.getsize(dst), "bytes")
+
+# ------------------------------------------------------------------------------------------------------------------
+# densify_golden.npz — the reference's densify / cat_params_to_optimizer / remove_points / update_params_and_optimizer
+# (tracking/external.py:138-299) and initialize_optimizer (tracking/train_utils.py:152-164) run AS THEY ARE on the CPU (their
+# hard-coded device="cuda" dropped, torch.normal replaced by fixture noise so that the split samples are reproducible on any
+# device) through a clone / split / prune round (i = 500), the round with the big-point prune and the opacity reset
+# (i = 3000) and the remove_thresh_5k round (i = 5000).  Inputs of every round are seeded by (round, current point count).
+# ------------------------------------------------------------------------------------------------------------------
+def densify_round_inputs(rnd, n):
+    """(means2D.grad [n,3], seen [n]) of one round: shared by this generator and tests/test_densify_gpu.py."""
+    r = np.random.default_rng(1000 + rnd)
+    g = r.normal(scale=3e-4, size=(n, 3)).astype(np.float32)
+    seen = r.uniform(size=n) < 0.8
+    return g, seen
+
+
+def densify_initial_state(n=400, seed=5):
+    r = np.random.default_rng(seed)
+    p = dict(means3D=r.uniform(-0.2, 0.2, size=(n, 3)), rgb_colors=r.uniform(size=(n, 3)),
+             seg_colors=np.stack([np.ones(n), np.zeros(n), np.zeros(n)], -1), unnorm_rotations=r.normal(size=(n, 4)),
+             logit_opacities=r.normal(scale=3.0, size=(n, 1)), log_scales=np.log(r.uniform(0.01, 0.14, size=(n, 3))),
+             cam_m=np.zeros((50, 3)), cam_c=np.zeros((50, 3)))
+    v = dict(max_2D_radius=r.uniform(0, 30, size=n), means2D_gradient_accum=r.uniform(0, 0.1, size=n) * (r.uniform(size=n) < 0.9),
+             denom=np.floor(r.uniform(0, 600, size=n)) * (r.uniform(size=n) < 0.95))
+    moments = {k: (r.normal(scale=1e-3, size=a.shape), r.uniform(0, 1e-6, size=a.shape)) for k, a in p.items()}
+    noise = r.normal(size=(40 * n, 3))
+    return ({k: a.astype(np.float32) for k, a in p.items()}, {k: a.astype(np.float32) for k, a in v.items()},
+            {k: (m.astype(np.float32), s.astype(np.float32)) for k, (m, s) in moments.items()}, noise.astype(np.float32))
+
+
+dp, dv, dm, dnoise = densify_initial_state()
+params = {k: torch.nn.Parameter(torch.tensor(a).contiguous().requires_grad_(True)) for k, a in dp.items()}
+params['rgb_colors'].requires_grad = False                      # train_utils.py:132
+variables = {k: torch.tensor(a) for k, a in dv.items()}
+variables['scene_radius'] = 1.0
+optimizer = ref_tu.initialize_optimizer(params, variables)
+for k, p_ in params.items():                                     # Adam state as after some iterations
+    if p_.requires_grad:
+        optimizer.state[p_] = dict(step=torch.tensor(7.0), exp_avg=torch.tensor(dm[k][0]), exp_avg_sq=torch.tensor(dm[k][1]))
+dout = {"noise": dnoise, "scene_radius": np.float32(1.0)}
+_normal, _zeros_real = torch.normal, torch.zeros
+state = {"used": 0}
+def _fixture_normal(mean=None, std=None, **kw):
+    out = std * torch.tensor(dnoise[state["used"]:state["used"] + std.shape[0]])
+    state["used"] += std.shape[0]
+    return out
+torch.normal, torch.zeros = _fixture_normal, _zeros_cpu
+try:
+    for rnd, it in enumerate((499, 500, 3000, 5000, 5001)):
+        n_now = params['means3D'].shape[0]
+        g2d, seen = densify_round_inputs(rnd, n_now)
+        if it == 5000:   # between the opacity reset (i = 3000) and this round the optimiser has moved the opacities
+            params['logit_opacities'].data.copy_(torch.tensor(np.random.default_rng(77).normal(scale=2.0, size=(n_now, 1)).astype(np.float32)))
+        m2d = torch.zeros(n_now, 3, requires_grad=True)
+        m2d.grad = torch.tensor(g2d)
+        variables['means2D'], variables['seen'] = m2d, torch.tensor(seen)
+        with torch.no_grad():
+            params, variables, num_pts = ref_e.densify(params, variables, optimizer, it, 0.005, 0.25, 0.05)
+        dout[f"r{rnd}_iter"], dout[f"r{rnd}_n_in"], dout[f"r{rnd}_n_out"], dout[f"r{rnd}_noise_used"] = it, n_now, num_pts, state["used"]
+        for k, p_ in params.items():
+            dout[f"r{rnd}_p_{k}"] = p_.detach().numpy().copy()
+            st = optimizer.state.get(p_, None)
+            if st is not None and "exp_avg" in st:
+                dout[f"r{rnd}_m_{k}"], dout[f"r{rnd}_v_{k}"] = st["exp_avg"].numpy().copy(), st["exp_avg_sq"].numpy().copy()
+        for k in ("means2D_gradient_accum", "denom", "max_2D_radius"):
+            dout[f"r{rnd}_var_{k}"] = variables[k].numpy().copy()
+finally:
+    torch.normal, torch.zeros = _normal, _zeros_real
+assert dout["r1_n_out"] != dout["r1_n_in"] and dout["r2_n_out"] != dout["r2_n_in"]
+dst = os.path.join(ROOT, "tests", "golden", "densify_golden.npz")
+np.savez_compressed(dst, **dout)
+print("wrote", dst, os.path.getsize(dst), "bytes", {k: int(dout[k]) for k in dout if k.endswith("_n_out")})
