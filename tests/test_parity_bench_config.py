@@ -59,10 +59,24 @@ def test_six_channel_backward_vs_oracle_at_benchmark_size(G):
     _check("full      opacities", full["opacities"].cpu().reshape(-1), bo["opacities"])
 
 
+def _perturbed_problem(G):
+    """workloads.tracking_problem(G) with the current state moved 0.5 mm / 0.01 away from the points the kNN distances were
+    measured on.  At the unperturbed state the isometry residual |x_j - x_i| - d_ij is EXACTLY zero up to rounding, where the
+    prior sqrt(w r^2 + 1e-20) is non-smooth: its gradient is sign(rounding noise) * sqrt(w) — O(1e-3) per Gaussian of noise in
+    the reference as much as here (measured: the reference composition on the CPU, its eager CUDA version and this repo differ
+    from one another by that much there).  One Adam step later (lr 1.6e-4) every real run has left that point."""
+    from gs_dynamics_b200 import workloads
+    prob = workloads.tracking_problem(G, 0)
+    g = torch.Generator().manual_seed(G + 17)
+    prob["params"]["means3D"] = (prob["params"]["means3D"] + 5e-4 * torch.randn(G, 3, generator=g)).contiguous()
+    prob["params"]["unnorm_rotations"] = (prob["params"]["unnorm_rotations"] + 1e-2 * torch.randn(G, 4, generator=g)).contiguous()
+    return prob
+
+
 def _one_iteration_gpu_vs_cpu(G, use_graph):
     from gs_dynamics_b200 import tracking as TR, workloads
     from oracle import tracking_cpu
-    prob = workloads.tracking_problem(G, 0)
+    prob = _perturbed_problem(G)
     params, variables, opt, dataset, _ = workloads.tracking_problem_gpu(G, 0, torch.device("cuda"), prob=prob)
     cam_id = 2
     # the oracle side: same state, same target images (the device-rendered ones), the reference's composition on the host
