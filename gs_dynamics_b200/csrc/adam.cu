@@ -18,6 +18,8 @@ struct AdamTable {
 
 __global__ void __launch_bounds__(256)
 gsd_adam_kernel(AdamTable t) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     const long long total = t.start[t.n];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int k = 0;
@@ -38,6 +40,8 @@ gsd_adam_kernel(AdamTable t) {
     }
 }
 __global__ void gsd_adam_advance_kernel(AdamTable t) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     int k = threadIdx.x;
     if (k < t.n) *t.step[k] += 1.0f;
 }
@@ -65,14 +69,16 @@ extern "C" int gsd_adam_step(const GsdAdam *a, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     long long blocks = (off + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    gsd_adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(t);
+    gsd_launch(gsd_adam_kernel, dim3((unsigned)blocks), dim3(256), 0, st, t);
     GSD_LAUNCH_CHECK();
-    gsd_adam_advance_kernel<<<1, 32, 0, st>>>(adv);
+    gsd_launch(gsd_adam_advance_kernel, dim3(1), dim3(32), 0, st, adv);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
 
 __global__ void gsd_update_radii_kernel(int G, const int32_t *__restrict__ radii, float *__restrict__ max_r, uint8_t *__restrict__ seen) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G) return;
     int r = radii[i];
@@ -84,7 +90,7 @@ __global__ void gsd_update_radii_kernel(int G, const int32_t *__restrict__ radii
 extern "C" int gsd_track_update_radii(int32_t G, const int32_t *radii, float *max_2D_radius, uint8_t *seen, void *stream) {
     if (G < 0 || (G > 0 && (!radii || !max_2D_radius))) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
     if (G == 0) return GSD_OK;
-    gsd_update_radii_kernel<<<(G + 255) / 256, 256, 0, (cudaStream_t)stream>>>(G, radii, max_2D_radius, seen);
+    gsd_launch(gsd_update_radii_kernel, dim3((G + 255) / 256), dim3(256), 0, (cudaStream_t)stream, G, radii, max_2D_radius, seen);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
@@ -93,6 +99,8 @@ extern "C" int gsd_track_update_radii(int32_t G, const int32_t *radii, float *ma
 // steady-state fast path: F.normalize forward, and (normalize backward + gradient sum + Adam) for the two live groups
 // ------------------------------------------------------------------------------------------------------
 __global__ void gsd_normalize_rot_kernel(int G, const float4 *__restrict__ q, float4 *__restrict__ out) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G) return;
     float4 v = q[i];
@@ -103,7 +111,7 @@ __global__ void gsd_normalize_rot_kernel(int G, const float4 *__restrict__ q, fl
 extern "C" int gsd_track_normalize_rotations(int32_t G, const float *unnorm, float *rot, void *stream) {
     if (G < 0 || (G > 0 && (!unnorm || !rot))) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
     if (G == 0) return GSD_OK;
-    gsd_normalize_rot_kernel<<<(G + 255) / 256, 256, 0, (cudaStream_t)stream>>>(G, (const float4 *)unnorm, (float4 *)rot);
+    gsd_launch(gsd_normalize_rot_kernel, dim3((G + 255) / 256), dim3(256), 0, (cudaStream_t)stream, G, (const float4 *)unnorm, (float4 *)rot);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
@@ -150,6 +158,8 @@ __device__ __forceinline__ void gsd_track_update_body(const GsdTrackUpdate &u, i
 // advances the step counters (every thread has read them by then) and re-arms the counter
 __global__ void __launch_bounds__(256)
 gsd_track_update_fused_kernel(GsdTrackUpdate u) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < u.G && u.radii) {
         const int r = u.radii[i];
@@ -171,6 +181,8 @@ gsd_track_update_fused_kernel(GsdTrackUpdate u) {
     }
 }
 __global__ void gsd_track_update_advance_kernel(float *a, float *b) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     *a += 1.0f;
     if (b != a) *b += 1.0f;
 }
@@ -185,10 +197,10 @@ extern "C" int gsd_track_update(const GsdTrackUpdate *u, void *stream) {
     }
     if (u->radii && !u->max_2D_radius) { gsd_set_error("radii given without max_2D_radius"); return GSD_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    gsd_track_update_fused_kernel<<<(u->G + 255) / 256, 256, 0, st>>>(*u);
+    gsd_launch(gsd_track_update_fused_kernel, dim3((u->G + 255) / 256), dim3(256), 0, st, *u);
     GSD_LAUNCH_CHECK();
     if (!u->block_counter) {
-        gsd_track_update_advance_kernel<<<1, 1, 0, st>>>(u->step_means, u->step_rot);
+        gsd_launch(gsd_track_update_advance_kernel, dim3(1), dim3(1), 0, st, u->step_means, u->step_rot);
         GSD_LAUNCH_CHECK();
     }
     return GSD_OK;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/gsd.h"
 
@@ -60,13 +61,18 @@ struct GsdGeomWs { // per-Gaussian state
 struct GsdBinWs {
     int n_bb;            // binning blocks = ceil(G / GSD_BIN_BLOCK)
     int max_items;       // upper bound of blend work items = capacity / GSD_CHUNK + tiles
+    int max_units;       // upper bound of sort units (1024-key segments) = capacity / 1024 + tiles
     int32_t *table;      // [tiles][n_bb] per (tile, binning block) instance counts -> exclusive scan (tile-major)
-    int32_t *tile_base;  // [tiles] row totals -> exclusive scan (first slot of the tile's segment)
+    int32_t *tile_total; // [tiles] instances per tile (zero-filled by the preprocess kernel, accumulated by the histogram pass)
+    int32_t *tile_base;  // [tiles] exclusive scan of the totals (first slot of the tile's segment)
     uint2 *ranges;       // per tile [start,end) clipped to capacity
     int32_t *chunk_ptr;  // [tiles+1] exclusive scan of chunks per tile
     int32_t *item_tile;  // [max_items] tile of each work item
-    int32_t *counters;   // [8] 0: n_items, 1: tiles that need sorting
-    int32_t *sort_order; // [tiles] tiles with >= 2 instances, longest lists first (three length classes)
+    int32_t *counters;   // [8] 0: n_items, 1: sort units, 2: tiles with more than one sort unit, 3: "tile bases published" flag
+    int32_t *unit_tile;  // [max_units] tile of each sort unit
+    int32_t *unit_seg;   // [max_units] segment index of each sort unit inside its tile
+    int32_t *long_tile;  // [tiles] tiles whose list spans several sort units
+    int32_t *exec_item;  // [max_items] blend work items in execution order: chunk index major (see gsd_blend_fwd_chunk_kernel)
     uint64_t *keys;      // [capacity] (depth bits << 32 | gaussian id), grouped by tile, unsorted inside a tile
     uint64_t *keys_tmp;  // [capacity] merge-sort ping-pong buffer for tile lists that do not fit shared memory
     float4 *records;     // 4 SoA planes of [capacity] float4: packed per-instance records sorted by (tile, depth, id)
@@ -77,6 +83,7 @@ struct GsdImgWs {
     int32_t *n_contrib;
     float *chunk_state; // [max_items][5 + 3 n_sets][256]
     float *term_state;  // [tiles][4 + 3 n_sets][256]
+    int32_t *chunk_flags; // [max_items][8] "chunk composite published" per (work item, 8x4-pixel rectangle); cleared every forward
     size_t total;
 };
 size_t gsd_chunk_state_floats(int n_sets, int max_items);
@@ -94,6 +101,8 @@ struct GsdRenderParams {
     const int32_t *chunk_ptr;  // [tiles+1]
     const int32_t *item_tile;  // [n_items]
     const int32_t *n_items;    // device scalar
+    const int32_t *exec_item;  // [n_items] execution order of the forward chunk kernel
+    int32_t *chunk_flags;      // [max_items][8]
     // forward A1 gathers the per-Gaussian data by sorted key and writes the record planes
     const uint64_t *keys; const float2 *g_xy; const float4 *g_conic_o; const float2 *g_ext; const float *g_depth;
     const uint2 *g_rect; const uint32_t *g_slot_base; const float *colors0; const float *colors1;
@@ -113,6 +122,37 @@ struct GsdRenderParams {
 };
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch ------------------------------------------------------------------------------------
+// Every kernel of the tracking iteration starts with gsd_pdl_wait() (griddepcontrol.wait: all memory operations of the
+// preceding kernel are complete and visible — it is executed before ANY global-memory access, so the data dependences and
+// write-after-read hazards between consecutive launches are exactly those of ordinary stream order) followed by
+// gsd_pdl_launch() (the next kernel's CTAs may be made resident as SM slots free up).  Launched through gsd_launch() with
+// the programmatic-stream-serialization attribute, a kernel's launch latency, CTA dispatch and prologue overlap the tail of
+// its predecessor instead of following it; inside a captured CUDA graph these become programmatic edges.  GSD_NO_PDL=1 in
+// the environment turns the attribute off (plain stream order).
+__device__ __forceinline__ void gsd_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef GSD_PDL_EARLY
+#define GSD_PDL_EARLY 0
+#endif
+__device__ __forceinline__ void gsd_pdl_launch() {
+#if GSD_PDL_EARLY
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+bool gsd_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline void gsd_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = gsd_pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);   // errors are picked up by GSD_LAUNCH_CHECK (cudaGetLastError)
+}
+
 // ---- mbarrier / bulk async copy (TMA 1-D) -----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

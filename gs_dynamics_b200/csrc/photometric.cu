@@ -131,6 +131,8 @@ gsd_ssim_stats_kernel(int C, int H, int W, int seg_rows, int n_seg, int n_strip,
                       const float *__restrict__ Y, const float *__restrict__ log_scale, const float *__restrict__ shift,
                       int affine_channels, float *__restrict__ y_mu, float *__restrict__ y_s22, float *__restrict__ dmu,
                       float *__restrict__ ds11, float *__restrict__ ds12, float *__restrict__ unit_sums /* [units][2] */) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     using Gm = PhGeom<NCOL>;
     constexpr int NQ = (MODE == 0) ? 5 : (MODE == 1 ? 3 : 2); // x, xx, xy (, y, yy)   |   MODE 2: y, yy
     constexpr int NA = (MODE == 2) ? 1 : 2;                    // staged arrays: (x,) y
@@ -272,6 +274,8 @@ gsd_ssim_stats_kernel(int C, int H, int W, int seg_rows, int n_seg, int n_strip,
 __global__ void __launch_bounds__(64)
 gsd_ssim_finish_kernel(int n_sets, int blocks_per_set, const float *__restrict__ block_sums, float inv_n,
                        float w_l1, float w_ssim, float sw0, float sw1, const float *__restrict__ add, float *__restrict__ out) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     // one warp per set: lane-strided double sums, fixed butterfly -> deterministic
     __shared__ float set_loss[2];
     const int s = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -312,6 +316,8 @@ gsd_ssim_grad_kernel(int C, int H, int W, int seg_rows, int n_seg, int n_strip, 
                      int affine_channels, const float *__restrict__ dmu, const float *__restrict__ ds11,
                      const float *__restrict__ ds12, const float *__restrict__ gscale_ptr, float sw0, float sw1, float w_l1,
                      float w_ssim, float inv_n, float *__restrict__ grad) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     using Gm = PhGeom<NCOL>;
     using St = PhStream<NCOL, 3, 2>;
     __shared__ __align__(16) float ring_s[PH_WARPS][PH_D][St::SLOT];
@@ -454,10 +460,10 @@ static void ph_launch_stats(const PhPlan &pl, cudaStream_t st, int C, int H, int
                             const float *ls, const float *sh, int aff, float *y_mu, float *y_s22, float *dmu, float *ds11,
                             float *ds12, float *us) {
     if (pl.ncol == 2)
-        gsd_ssim_stats_kernel<MODE, 2><<<pl.ctas, 32 * PH_WARPS, 0, st>>>(C, H, W, pl.seg_rows, pl.n_seg, pl.n_strip, win, x, y, ls, sh,
+        gsd_launch((gsd_ssim_stats_kernel<MODE, 2>), dim3(pl.ctas), dim3(32 * PH_WARPS), 0, st, C, H, W, pl.seg_rows, pl.n_seg, pl.n_strip, win, x, y, ls, sh,
                                                                          aff, y_mu, y_s22, dmu, ds11, ds12, us);
     else
-        gsd_ssim_stats_kernel<MODE, 1><<<pl.ctas, 32 * PH_WARPS, 0, st>>>(C, H, W, pl.seg_rows, pl.n_seg, pl.n_strip, win, x, y, ls, sh,
+        gsd_launch((gsd_ssim_stats_kernel<MODE, 1>), dim3(pl.ctas), dim3(32 * PH_WARPS), 0, st, C, H, W, pl.seg_rows, pl.n_seg, pl.n_strip, win, x, y, ls, sh,
                                                                          aff, y_mu, y_s22, dmu, ds11, ds12, us);
 }
 
@@ -499,7 +505,7 @@ extern "C" int gsd_photometric_reduce(const GsdPhotometric *p, const float *add,
     const PhPlan pl = ph_plan(C, H, W);
     const int per_set_c = C / p->n_sets;
     const int units_per_set = pl.n_seg * pl.n_strip * per_set_c;
-    gsd_ssim_finish_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(p->n_sets, units_per_set, bs, 1.0f / (float)((size_t)per_set_c * H * W),
+    gsd_launch(gsd_ssim_finish_kernel, dim3(1), dim3(64), 0, (cudaStream_t)stream, p->n_sets, units_per_set, bs, 1.0f / (float)((size_t)per_set_c * H * W),
                                                                  p->w_l1, p->w_ssim, p->set_weight[0], p->set_weight[1], add, loss_out);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
@@ -542,12 +548,12 @@ extern "C" int gsd_photometric_backward(const GsdPhotometric *p, const float *gs
     const int aff = (p->affine_log_scale || p->affine_shift) ? 3 : 0;
     const float inv_n = 1.0f / (float)((size_t)per_set_c * H * W);
     if (pl.ncol == 2)
-        gsd_ssim_grad_kernel<2><<<pl.ctas, 32 * PH_WARPS, 0, st>>>(C, H, W, pl.seg_rows, pl.n_seg, pl.n_strip, win, p->x, p->y,
+        gsd_launch((gsd_ssim_grad_kernel<2>), dim3(pl.ctas), dim3(32 * PH_WARPS), 0, st, C, H, W, pl.seg_rows, pl.n_seg, pl.n_strip, win, p->x, p->y,
                                                                   p->affine_log_scale, p->affine_shift, aff, dmu, ds11, ds12,
                                                                   gscale_ptr, p->set_weight[0], p->set_weight[1], p->w_l1,
                                                                   p->w_ssim, inv_n, grad);
     else
-        gsd_ssim_grad_kernel<1><<<pl.ctas, 32 * PH_WARPS, 0, st>>>(C, H, W, pl.seg_rows, pl.n_seg, pl.n_strip, win, p->x, p->y,
+        gsd_launch((gsd_ssim_grad_kernel<1>), dim3(pl.ctas), dim3(32 * PH_WARPS), 0, st, C, H, W, pl.seg_rows, pl.n_seg, pl.n_strip, win, p->x, p->y,
                                                                   p->affine_log_scale, p->affine_shift, aff, dmu, ds11, ds12,
                                                                   gscale_ptr, p->set_weight[0], p->set_weight[1], p->w_l1,
                                                                   p->w_ssim, inv_n, grad);

@@ -1,14 +1,15 @@
 // raster_api.cu — C-ABI entry points of the rasterizer (include/gsd.h, Path A.1).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
 
 // launchers implemented in the other translation units
-int gsd_launch_preprocess(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, cudaStream_t st);
+int gsd_launch_preprocess(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, int32_t *zero_fill, int n_zero, cudaStream_t st);
 int gsd_launch_count(int G, const GsdGeomWs &g, int32_t *status, cudaStream_t st);
 int gsd_launch_mark_visible(int G, const GsdCam &cam, const float *means3D, uint8_t *vis, cudaStream_t st);
-int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, const GsdBinWs &b, cudaStream_t st);
+int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, const GsdBinWs &b, int32_t *zero_flags, int n_flags, cudaStream_t st);
 int gsd_launch_render_fwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st);
 int gsd_launch_render_bwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st);
 int gsd_launch_preprocess_bwd(int G, const GsdCam &cam, const GsdRasterBwd *a, const GsdGeomWs &g, int geom_only, cudaStream_t st);
@@ -27,6 +28,12 @@ void gsd_set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool gsd_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("GSD_NO_PDL"); on = (e && e[0] == '1') ? 0 : 1; }
+    return on == 1;
 }
 
 extern "C" const char *gsd_last_error(void) { return g_err; }
@@ -80,7 +87,7 @@ extern "C" int gsd_raster_count_instances(const GsdRasterFwd *a, void *stream) {
     GsdGeomWs g;
     if ((rc = gsd_carve_geom(a->G, a->geom_ws, &g))) return rc;
     GSD_CUDA_CHECK(cudaMemsetAsync(a->status, 0, GSD_STATUS_WORDS * 4, st));
-    if ((rc = gsd_launch_preprocess(a->G, cam, a, g, st))) return rc;
+    if ((rc = gsd_launch_preprocess(a->G, cam, a, g, nullptr, 0, st))) return rc;
     return gsd_launch_count(a->G, g, a->status, st);
 }
 
@@ -103,8 +110,8 @@ extern "C" int gsd_raster_forward(const GsdRasterFwd *a, void *stream) {
     if ((rc = gsd_carve_bin(a->G, a->capacity, tiles, a->binning_ws, &b))) return rc;
     if ((rc = gsd_carve_img(a->W, a->H, a->n_sets, b.max_items, a->image_ws, &im))) return rc;
     GSD_CUDA_CHECK(cudaMemsetAsync(a->status, 0, GSD_STATUS_WORDS * 4, st));
-    if ((rc = gsd_launch_preprocess(a->G, cam, a, g, st))) return rc;
-    if ((rc = gsd_launch_binning(a->G, cam, a, g, b, st))) return rc;
+    if ((rc = gsd_launch_preprocess(a->G, cam, a, g, b.tile_total, tiles, st))) return rc;
+    if ((rc = gsd_launch_binning(a->G, cam, a, g, b, im.chunk_flags, b.max_items * 8, st))) return rc;
     GsdRenderParams p;
     memset(&p, 0, sizeof(p));
     p.ranges = b.ranges;
@@ -121,6 +128,7 @@ extern "C" int gsd_raster_forward(const GsdRasterFwd *a, void *stream) {
     p.keys = b.keys; p.g_xy = g.xy; p.g_conic_o = g.conic_o; p.g_ext = g.ext; p.g_depth = g.depth; p.g_rect = g.rect;
     p.g_slot_base = g.slot_base; p.colors0 = a->colors0; p.colors1 = a->n_sets == 2 ? a->colors1 : nullptr;
     p.planes_w = b.records;
+    p.exec_item = b.exec_item; p.chunk_flags = im.chunk_flags;
     return gsd_launch_render_fwd(p, tiles, a->n_sets, st);
 }
 

@@ -15,6 +15,8 @@ gsd_preprocess_bwd_kernel(int G, GsdCam cam, int64_t capacity, const float *__re
                           const float4 *__restrict__ partials, float *__restrict__ dmeans3D, float *__restrict__ dmeans2D, float *__restrict__ dcolors0,
                           float *__restrict__ dcolors1, float *__restrict__ dopac, float *__restrict__ dscales,
                           float *__restrict__ drot) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     __shared__ float sVP[32];
     if (threadIdx.x < 16) sVP[threadIdx.x] = cam.view[threadIdx.x];
     else if (threadIdx.x < 32) sVP[threadIdx.x] = cam.proj[threadIdx.x - 16];
@@ -179,11 +181,11 @@ int gsd_launch_preprocess_bwd(int G, const GsdCam &cam, const GsdRasterBwd *a, c
 #define GSD_PB_ARGS G, cam, f.capacity, f.means3D, f.scales, f.rotations, f.radii, g.slot_base, g.tiles, g.conic_o, (const float4 *)a->partial_ws, \
         a->dL_dmeans3D, a->dL_dmeans2D, a->dL_dcolors0, a->dL_dcolors1, a->dL_dopacities, a->dL_dscales, a->dL_drotations
     if (geom_only) {
-        if (f.n_sets == 1) gsd_preprocess_bwd_kernel<3, true><<<blocks, 256, 0, st>>>(GSD_PB_ARGS);
-        else gsd_preprocess_bwd_kernel<6, true><<<blocks, 256, 0, st>>>(GSD_PB_ARGS);
+        if (f.n_sets == 1) gsd_launch((gsd_preprocess_bwd_kernel<3, true>), dim3(blocks), dim3(256), 0, st, GSD_PB_ARGS);
+        else gsd_launch((gsd_preprocess_bwd_kernel<6, true>), dim3(blocks), dim3(256), 0, st, GSD_PB_ARGS);
     } else {
-        if (f.n_sets == 1) gsd_preprocess_bwd_kernel<3, false><<<blocks, 256, 0, st>>>(GSD_PB_ARGS);
-        else gsd_preprocess_bwd_kernel<6, false><<<blocks, 256, 0, st>>>(GSD_PB_ARGS);
+        if (f.n_sets == 1) gsd_launch((gsd_preprocess_bwd_kernel<3, false>), dim3(blocks), dim3(256), 0, st, GSD_PB_ARGS);
+        else gsd_launch((gsd_preprocess_bwd_kernel<6, false>), dim3(blocks), dim3(256), 0, st, GSD_PB_ARGS);
     }
 #undef GSD_PB_ARGS
     GSD_LAUNCH_CHECK();

@@ -16,8 +16,12 @@ gsd_preprocess_kernel(int G, GsdCam cam, const float *__restrict__ means3D, cons
                       const float *__restrict__ scales, const float *__restrict__ rotations, float2 *__restrict__ xy,
                       float4 *__restrict__ conic_o, float2 *__restrict__ ext, float *__restrict__ depth,
                       uint2 *__restrict__ rect, uint32_t *__restrict__ tiles, uint32_t *__restrict__ slot_base,
-                      int32_t *__restrict__ radii, uint32_t *__restrict__ block_sum) {
+                      int32_t *__restrict__ radii, uint32_t *__restrict__ block_sum, int32_t *__restrict__ zero_fill, int n_zero) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     __shared__ float sVP[32];
+    // the binning histogram accumulates the per-tile totals with atomics: cleared here (one launch earlier in stream order)
+    for (int z = blockIdx.x * blockDim.x + threadIdx.x; z < n_zero; z += gridDim.x * blockDim.x) zero_fill[z] = 0;
     if (threadIdx.x < 16) sVP[threadIdx.x] = cam.view[threadIdx.x];
     else if (threadIdx.x < 32) sVP[threadIdx.x] = cam.proj[threadIdx.x - 16];
     __syncthreads();
@@ -137,6 +141,8 @@ gsd_preprocess_kernel(int G, GsdCam cam, const float *__restrict__ means3D, cons
 }
 
 __global__ void gsd_mark_visible_kernel(int G, GsdCam cam, const float *__restrict__ means3D, uint8_t *__restrict__ vis) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G) return;
     float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
@@ -148,19 +154,20 @@ __global__ void gsd_mark_visible_kernel(int G, GsdCam cam, const float *__restri
 }
 
 // block_sum[b] receives the number of tile instances of Gaussians [256 b, 256 b + 256)
-int gsd_launch_preprocess(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, cudaStream_t st) {
+int gsd_launch_preprocess(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, int32_t *zero_fill, int n_zero,
+                          cudaStream_t st) {
     if (G == 0) return GSD_OK;
     int blocks = (G + 255) / 256;
-    gsd_preprocess_kernel<<<blocks, 256, 0, st>>>(G, cam, a->means3D, a->opacities, a->scales, a->rotations, g.xy,
+    gsd_launch(gsd_preprocess_kernel, dim3(blocks), dim3(256), 0, st, G, cam, a->means3D, a->opacities, a->scales, a->rotations, g.xy,
                                                    g.conic_o, g.ext, g.depth, g.rect, g.tiles, g.slot_base, a->radii,
-                                                   g.block_sum);
+                                                   g.block_sum, zero_fill, n_zero);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
 
 int gsd_launch_mark_visible(int G, const GsdCam &cam, const float *means3D, uint8_t *vis, cudaStream_t st) {
     if (G == 0) return GSD_OK;
-    gsd_mark_visible_kernel<<<(G + 255) / 256, 256, 0, st>>>(G, cam, means3D, vis);
+    gsd_launch(gsd_mark_visible_kernel, dim3((G + 255) / 256), dim3(256), 0, st, G, cam, means3D, vis);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }

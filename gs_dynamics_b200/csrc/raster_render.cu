@@ -100,18 +100,72 @@ __device__ __forceinline__ void load_chunk(const GsdRenderParams &p, float4 (*pl
 // the earlier ones — exact termination in chunks 0/1 without A2, upper-bound skipping behind them.  In the benchmark scene 29 %
 // of the items lie behind the termination point of every pixel of their tile, but all of them at chunk index >= 4, where only a
 // sequential dependence could expose them; the phases cost more in lost occupancy (26 + 25 + 39 us) than the single launch (59 us).)
+// Execution order and look-back.  blockIdx.x is mapped to a work item through p.exec_item, which lists the items by CHUNK INDEX
+// first (all first chunks of all tiles, then all second chunks, ...): CTAs are dispatched in blockIdx order, so when a deep
+// chunk starts, the chunks in front of it have usually finished.  Every warp publishes a flag per (item, 8x4 rectangle) after
+// writing its composite; a warp of chunk c first reads the flags of the chunks in front of it, takes the contiguous published
+// prefix 0..j, rebuilds T = prod P_k (the same multiplications, in the same order, as the termination pass A2) and, where that
+// product is already below 1e-4, switches the pixel off: the reference's loop stopped in an earlier chunk, nothing of this chunk
+// is ever read for that pixel (A2 declares it dead at the same k, the combine pass breaks at the terminating chunk, the backward
+// prefix stops at n_contrib).  The look-back never waits — an unpublished predecessor just shortens the prefix — so there is no
+// forward-progress dependence between CTAs, and skipping never changes a result bit: it only removes work the sequential
+// reference would not have done either.  In the 100k benchmark scene 64 % of the (rectangle, chunk) pairs lie behind the
+// termination depth of their rectangle (53 % of the chunks behind that of their whole tile).
+__device__ __forceinline__ int ld_acquire_s32(const int32_t *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_s32(int32_t *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <int CH>
 __global__ void __launch_bounds__(GSD_CWARPS * 32, 6)
 gsd_blend_fwd_chunk_kernel(GsdRenderParams p) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     constexpr int NPL = (CH == 3) ? 3 : 4;
     using IS = ItemState<CH>;
     __shared__ __align__(128) float4 planes[NPL][GSD_CHUNK];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     ItemInfo I;
-    const int item = blockIdx.x;
+    if ((int)blockIdx.x >= *p.n_items) return;
+    const int item = p.exec_item[blockIdx.x];
     if (!item_setup(p, item, warp, lane, I)) return;
     const bool gone = !I.inside;
     float *st = p.chunk_state + (size_t)item * IS::NF * 256;
+    // look-back (issued before the gather so that its loads overlap it)
+    bool lb_dead = false;
+    if (I.chunk > 0) {
+        const int item0 = item - I.chunk;
+        const int npred = min(I.chunk, 32);
+        const int ready = lane < npred ? ld_acquire_s32(p.chunk_flags + (size_t)(item0 + lane) * GSD_CWARPS + warp) : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, ready != 0);
+        __syncwarp();   // memory ordering between the lane that acquired flag k and the lanes that read chunk k's composite
+        const int nready = min(npred, (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1));
+        float T = 1.0f;
+        bool d = gone;
+        for (int c0 = 0; c0 < nready; c0 += 8) {
+            if (__all_sync(0xffffffffu, d)) break;
+            float Pc[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                Pc[u] = (c0 + u < nready) ? __ldcg(p.chunk_state + (size_t)(item0 + c0 + u) * IS::NF * 256 + IS::P * 256 + I.pix) : 1.0f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (c0 + u < nready && !d) {
+                    const float Tn = __fmul_rn(T, Pc[u]);
+                    if (Tn < T_EPS) d = true;
+                    T = Tn;
+                }
+            }
+        }
+        lb_dead = d && !gone;
+    }
+    // the whole tile is already opaque in front of this chunk: nothing will ever composite its records; the backward only needs
+    // every instance's partial-gradient slot (it zero-fills the slots of instances that reached no pixel)
+    const bool cta_dead = I.chunk > 0 && __syncthreads_and((lb_dead || gone) ? 1 : 0);
     // gather the chunk's records by sorted key into shared memory AND into the global record planes (the backward and
     // the termination pass stream them with TMA). One record per thread; the gathers of 8 CTAs per SM overlap.
     for (int i = t; i < I.cnt; i += GSD_CWARPS * 32) {
@@ -120,6 +174,10 @@ gsd_blend_fwd_chunk_kernel(GsdRenderParams p) {
         const int minx = rc.x & 0xffff, miny = rc.x >> 16, maxx = rc.y & 0xffff;
         const int tx = I.tile % p.gx, ty = I.tile / p.gx;
         const uint32_t slot = p.g_slot_base[g] + (uint32_t)((ty - miny) * (maxx - minx) + (tx - minx));
+        if (cta_dead) {
+            p.planes_w[3 * p.plane_stride + (int64_t)I.start + i] = make_float4(__uint_as_float(slot), 0.f, 0.f, 0.f);
+            continue;
+        }
         const float2 pc = p.g_xy[g];
         const float2 e = p.g_ext[g];
         const float4 co = p.g_conic_o[g];
@@ -146,9 +204,9 @@ gsd_blend_fwd_chunk_kernel(GsdRenderParams p) {
 #pragma unroll
     for (int c = 0; c < CH; ++c) C[c] = 0.f;
     int last = 0;
-    bool off = gone;        // pixel outside the image, or (chunk 0) stopped here
-    bool stopped = false;   // chunk 0 only: the reference's "done"
-    bool dead = gone;       // nothing of this chunk can be used any more (A2 replays the terminating chunk of a pixel)
+    bool off = gone || lb_dead;   // pixel outside the image, already opaque before this chunk (look-back), or (chunk 0) stopped here
+    bool stopped = false;         // chunk 0 only: the reference's "done"
+    bool dead = off;              // nothing of this chunk can be used any more (A2 replays the terminating chunk of a pixel)
     // two instantiations of the chunk loop: only chunk 0 carries the termination rule
     auto run = [&](auto first_tag) {
         constexpr bool FIRST = decltype(first_tag)::value;
@@ -224,11 +282,20 @@ gsd_blend_fwd_chunk_kernel(GsdRenderParams p) {
         term_i[TS::CSTAR * 256 + I.pix] = stopped ? 0 : TERMINAL_NONE;
         if (stopped) T = 0.f; // later chunks see a dead pixel
     }
+    if (lb_dead) T = 0.f;   // switched off by the look-back: later chunks / passes see a dead pixel (C, D, last are still 0)
     st[IS::P * 256 + I.pix] = T;
     st[IS::D * 256 + I.pix] = D;
 #pragma unroll
     for (int c = 0; c < CH; ++c) st[(IS::C + c) * 256 + I.pix] = C[c];
     reinterpret_cast<int *>(st)[IS::LAST * 256 + I.pix] = last;
+    // publish this rectangle's composite for the look-back of the chunks behind it (2: the whole rectangle was already
+    // opaque in front of this chunk — the termination pass skips it without rebuilding T)
+    const bool rect_dead = __all_sync(0xffffffffu, lb_dead || gone);
+    __syncwarp();   // orders the lanes' composite stores before lane 0's fence + flag
+    if (lane == 0) {
+        __threadfence();
+        st_release_s32(p.chunk_flags + (size_t)item * GSD_CWARPS + warp, rect_dead && I.chunk > 0 ? 2 : 1);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -237,6 +304,8 @@ gsd_blend_fwd_chunk_kernel(GsdRenderParams p) {
 template <int CH>
 __global__ void __launch_bounds__(GSD_CWARPS * 32)
 gsd_blend_fwd_term_kernel(GsdRenderParams p) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     constexpr int NPL = (CH == 3) ? 3 : 4;
     using IS = ItemState<CH>;
     using TS = TermState<CH>;
@@ -249,7 +318,8 @@ gsd_blend_fwd_term_kernel(GsdRenderParams p) {
     const int item0 = blockIdx.x - I.chunk;
     // T_in = product of the preceding chunks' P (same order and ops in every kernel that rebuilds it)
     float T = 1.0f;
-    bool dead = !I.inside;
+    // rectangles the forward look-back found opaque in front of this chunk (flag 2): nothing to rebuild, nothing to replay
+    bool dead = !I.inside || __ldcg(p.chunk_flags + (size_t)blockIdx.x * GSD_CWARPS + warp) == 2;
     for (int c0 = 0; c0 < I.chunk && !dead; c0 += 8) {
         float Pc[8];
 #pragma unroll
@@ -335,6 +405,8 @@ gsd_blend_fwd_term_kernel(GsdRenderParams p) {
 template <int CH>
 __global__ void __launch_bounds__(GSD_CWARPS * 32)
 gsd_blend_fwd_combine_kernel(GsdRenderParams p) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     using IS = ItemState<CH>;
     using TS = TermState<CH>;
     const int tile = blockIdx.x;
@@ -407,6 +479,8 @@ gsd_blend_fwd_combine_kernel(GsdRenderParams p) {
 template <int CH>
 __global__ void __launch_bounds__(GSD_CWARPS * 32)
 gsd_blend_bwd_prefix_kernel(GsdRenderParams p) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     using IS = ItemState<CH>;
     const int tile = blockIdx.x;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -485,6 +559,8 @@ gsd_blend_bwd_prefix_kernel(GsdRenderParams p) {
 template <int CH, bool GEOM, int HALVES>
 __global__ void __launch_bounds__((GSD_CWARPS / HALVES + 1) * 32, HALVES == 2 ? 8 : 5)
 gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     constexpr int NW = GSD_CWARPS / HALVES; // consumer warps of this CTA
     constexpr int NV = GEOM ? 5 : CH + 6; // [colours,] mean2D(2), conic(3) [, opacity(1)]
     constexpr int OG = GEOM ? 0 : CH;     // offset of the geometry values inside a partial record
@@ -656,32 +732,32 @@ int gsd_launch_render_fwd(const GsdRenderParams &p, int tiles, int n_sets, cudaS
     if (tiles == 0) return GSD_OK;
     const int threads = GSD_CWARPS * 32;
     if (p.max_items > 0) {
-        if (n_sets == 1) gsd_blend_fwd_chunk_kernel<3><<<p.max_items, threads, 0, st>>>(p);
-        else gsd_blend_fwd_chunk_kernel<6><<<p.max_items, threads, 0, st>>>(p);
+        if (n_sets == 1) gsd_launch((gsd_blend_fwd_chunk_kernel<3>), dim3(p.max_items), dim3(threads), 0, st, p);
+        else gsd_launch((gsd_blend_fwd_chunk_kernel<6>), dim3(p.max_items), dim3(threads), 0, st, p);
         GSD_LAUNCH_CHECK();
-        if (n_sets == 1) gsd_blend_fwd_term_kernel<3><<<p.max_items, threads, 0, st>>>(p);
-        else gsd_blend_fwd_term_kernel<6><<<p.max_items, threads, 0, st>>>(p);
+        if (n_sets == 1) gsd_launch((gsd_blend_fwd_term_kernel<3>), dim3(p.max_items), dim3(threads), 0, st, p);
+        else gsd_launch((gsd_blend_fwd_term_kernel<6>), dim3(p.max_items), dim3(threads), 0, st, p);
         GSD_LAUNCH_CHECK();
     }
-    if (n_sets == 1) gsd_blend_fwd_combine_kernel<3><<<tiles, threads, 0, st>>>(p);
-    else gsd_blend_fwd_combine_kernel<6><<<tiles, threads, 0, st>>>(p);
+    if (n_sets == 1) gsd_launch((gsd_blend_fwd_combine_kernel<3>), dim3(tiles), dim3(threads), 0, st, p);
+    else gsd_launch((gsd_blend_fwd_combine_kernel<6>), dim3(tiles), dim3(threads), 0, st, p);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
 
 int gsd_launch_render_bwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st) {
     if (tiles == 0 || p.max_items == 0) return GSD_OK;
-    if (n_sets == 1) gsd_blend_bwd_prefix_kernel<3><<<tiles, GSD_CWARPS * 32, 0, st>>>(p);
-    else gsd_blend_bwd_prefix_kernel<6><<<tiles, GSD_CWARPS * 32, 0, st>>>(p);
+    if (n_sets == 1) gsd_launch((gsd_blend_bwd_prefix_kernel<3>), dim3(tiles), dim3(GSD_CWARPS * 32), 0, st, p);
+    else gsd_launch((gsd_blend_bwd_prefix_kernel<6>), dim3(tiles), dim3(GSD_CWARPS * 32), 0, st, p);
     GSD_LAUNCH_CHECK();
     const int threads = (GSD_CWARPS + 1) * 32;
     if (p.geom_only) {   // half-tile CTAs (see the kernel)
         const int th2 = (GSD_CWARPS / 2 + 1) * 32;
-        if (n_sets == 1) gsd_blend_bwd_chunk_kernel<3, true, 2><<<2 * p.max_items, th2, 0, st>>>(p);
-        else gsd_blend_bwd_chunk_kernel<6, true, 2><<<2 * p.max_items, th2, 0, st>>>(p);
+        if (n_sets == 1) gsd_launch((gsd_blend_bwd_chunk_kernel<3, true, 2>), dim3(2 * p.max_items), dim3(th2), 0, st, p);
+        else gsd_launch((gsd_blend_bwd_chunk_kernel<6, true, 2>), dim3(2 * p.max_items), dim3(th2), 0, st, p);
     } else {
-        if (n_sets == 1) gsd_blend_bwd_chunk_kernel<3, false, 1><<<p.max_items, threads, 0, st>>>(p);
-        else gsd_blend_bwd_chunk_kernel<6, false, 1><<<p.max_items, threads, 0, st>>>(p);
+        if (n_sets == 1) gsd_launch((gsd_blend_bwd_chunk_kernel<3, false, 1>), dim3(p.max_items), dim3(threads), 0, st, p);
+        else gsd_launch((gsd_blend_bwd_chunk_kernel<6, false, 1>), dim3(p.max_items), dim3(threads), 0, st, p);
     }
     GSD_LAUNCH_CHECK();
     return GSD_OK;

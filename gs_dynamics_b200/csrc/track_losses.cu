@@ -96,6 +96,8 @@ __device__ __forceinline__ void eval_edge(const TrackArgs &a, const float xi[3],
 #define TRK_SPLIT 4
 __global__ void __launch_bounds__(128)
 gsd_track_fg_kernel(TrackArgs a) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     __shared__ float red[4][4];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = tid / TRK_SPLIT, sub = tid % TRK_SPLIT;
@@ -217,6 +219,8 @@ gsd_track_fg_kernel(TrackArgs a) {
 // 4..16-byte loads and a quaternion product: 4x fewer L1 sectors (17.7M -> ~4.5M per call at G = 50k, K = 20).
 __global__ void __launch_bounds__(256)
 gsd_track_node_prep_kernel(TrackArgs a, float4 *__restrict__ node) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= a.Gf) return;
     const int gi = a.fg_index ? a.fg_index[f] : f;
@@ -227,6 +231,8 @@ gsd_track_node_prep_kernel(TrackArgs a, float4 *__restrict__ node) {
 
 __global__ void __launch_bounds__(128)
 gsd_track_fg_packed_kernel(TrackArgs a, const float4 *__restrict__ node, const float4 *__restrict__ edge) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     __shared__ float red[4][4];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = tid / TRK_SPLIT, sub = tid % TRK_SPLIT;
@@ -330,6 +336,8 @@ gsd_track_fg_packed_kernel(TrackArgs a, const float4 *__restrict__ node, const f
 // packs the static per-edge tables into 32-byte records (once per timestep: prev_offset changes with the frame)
 __global__ void gsd_track_pack_edges_kernel(long long n_edges, const int32_t *__restrict__ nbr, const float *__restrict__ w,
                                             const float *__restrict__ d0, const float *__restrict__ po, float4 *__restrict__ out) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
     out[2 * e] = make_float4(__int_as_float(nbr[e]), w[e], d0[e], po[3 * e]);
@@ -344,7 +352,7 @@ extern "C" int gsd_track_pack_edges(int32_t Gf, int32_t K, const int32_t *neighb
     }
     const long long n = (long long)Gf * K;
     if (n == 0) return GSD_OK;
-    gsd_track_pack_edges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, neighbor_indices, neighbor_weight,
+    gsd_launch(gsd_track_pack_edges_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, n, neighbor_indices, neighbor_weight,
                                                                                                 neighbor_dist, prev_offset, (float4 *)edge_records);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
@@ -352,6 +360,8 @@ extern "C" int gsd_track_pack_edges(int32_t Gf, int32_t K, const int32_t *neighb
 
 __global__ void __launch_bounds__(128)
 gsd_track_bg_kernel(TrackArgs a, int fg_blocks) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     __shared__ float red[4];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     float s = 0.f;
@@ -386,6 +396,8 @@ gsd_track_bg_kernel(TrackArgs a, int fg_blocks) {
 __global__ void gsd_track_finish_kernel(int nrows, const float *__restrict__ block_sums, float inv_e, float inv_f,
                                         float inv_b, float w_rigid, float w_rot, float w_iso, float w_floor, float w_bg,
                                         float *__restrict__ losses) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
     __shared__ double r[5][128];
     double v[5] = {0, 0, 0, 0, 0};
     for (int i = threadIdx.x; i < nrows; i += 128)
@@ -444,16 +456,16 @@ extern "C" int gsd_track_losses_fwd_bwd(const GsdTrackLosses *t, void *stream) {
     if (fgb > 0 && t->edge_records && t->K > 0) {
         const size_t rows = (size_t)fgb + bgb + 1;
         float4 *node = (float4 *)((char *)t->ws + gsd_align_up(rows * 5 * 4));
-        gsd_track_node_prep_kernel<<<(t->Gf + 255) / 256, 256, 0, st>>>(a, node);
+        gsd_launch(gsd_track_node_prep_kernel, dim3((t->Gf + 255) / 256), dim3(256), 0, st, a, node);
         GSD_LAUNCH_CHECK();
-        gsd_track_fg_packed_kernel<<<fgb, 128, 0, st>>>(a, node, (const float4 *)t->edge_records);
+        gsd_launch(gsd_track_fg_packed_kernel, dim3(fgb), dim3(128), 0, st, a, node, (const float4 *)t->edge_records);
         GSD_LAUNCH_CHECK();
     } else if (fgb > 0) {
-        gsd_track_fg_kernel<<<fgb, 128, 0, st>>>(a);
+        gsd_launch(gsd_track_fg_kernel, dim3(fgb), dim3(128), 0, st, a);
         GSD_LAUNCH_CHECK();
     }
-    if (bgb > 0) { gsd_track_bg_kernel<<<bgb, 128, 0, st>>>(a, fgb); GSD_LAUNCH_CHECK(); }
-    gsd_track_finish_kernel<<<1, 128, 0, st>>>(fgb + bgb, a.block_sums, t->Gf > 0 ? (float)(1.0 / ne) : 0.f,
+    if (bgb > 0) { gsd_launch(gsd_track_bg_kernel, dim3(bgb), dim3(128), 0, st, a, fgb); GSD_LAUNCH_CHECK(); }
+    gsd_launch(gsd_track_finish_kernel, dim3(1), dim3(128), 0, st, fgb + bgb, a.block_sums, t->Gf > 0 ? (float)(1.0 / ne) : 0.f,
                                                t->Gf > 0 ? 1.f / t->Gf : 0.f, t->Gb > 0 ? 1.f / t->Gb : 0.f, t->w_rigid,
                                                t->w_rot, t->w_iso, t->w_floor, t->w_bg, t->losses);
     GSD_LAUNCH_CHECK();

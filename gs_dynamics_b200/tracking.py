@@ -595,6 +595,7 @@ class FusedTrackingStep(TrackingStep):
             self.targets = [torch.cat([d['im'], d['seg']], 0).contiguous() for d in dataset]
             self.rot = torch.empty_like(params['unnorm_rotations'])
             self.tstats = [target_stats(tg) for tg in self.targets]
+        self.outputs = {}
         self.side = torch.cuda.Stream(device=params['means3D'].device)
         self.block_counter = torch.zeros(1, dtype=torch.int32, device=params['means3D'].device)   # self-resetting (gsd_track_update)
         self.lr = {g['name']: float(g['lr']) for g in optimizer.param_groups}
@@ -683,10 +684,17 @@ class FusedTrackingStep(TrackingStep):
             u.block_counter = self.block_counter.data_ptr()
             _lib.check(lib.gsd_track_update(C.byref(u), st), "gsd_track_update")
             main.wait_event(loss_done)
-            V['seen'] = seen.view(torch.bool)
-            V['prior_losses'] = parts
-            V['photometric_losses'] = ph[:7]
+            # per-camera result buffers (every captured graph writes its own): step() re-points `variables` at the ones of the
+            # camera it replayed
+            self.outputs[idx if idx is not None else cid] = {'seen': seen.view(torch.bool), 'prior_losses': parts, 'photometric_losses': ph[:7]}
+            V.update(self.outputs[idx if idx is not None else cid])
         return ph[7]
+
+    def step(self, cam_id):
+        loss = super().step(cam_id)
+        if self.use_graph:
+            self.variables.update(self.outputs[cam_id])
+        return loss
 
 
 # ----------------------------------------------------------------------------------------------------
