@@ -8,9 +8,9 @@
 // object: tens of tiles with thousands).  One CTA per tile therefore leaves most SMs idle behind a few long serial chains
 // (profiles/r1_*).  Here every tile list is cut into CHUNKS of 256 records and each (tile, chunk) is an independent work item:
 //   fwd A1  per item   local composite of the chunk (transmittance product P, colour/depth sums with T starting at 1)
-//   fwd A2  per item   exact termination: T_in = prod of the preceding chunks' P; if T_in*P < 1e-4 some Gaussian inside this
-//                      chunk is the reference's stopping point — that pixel is replayed sequentially with the true T_in
-//   fwd B   per tile   combine the chunk composites in order -> colour, depth, final_T, n_contrib
+//   fwd B   per tile   combine the chunk composites in order; the chunk in which T_in * P crosses 1e-4 holds the reference's
+//                      stopping point — that pixel's chunk is replayed sequentially with the true T_in; -> colour, depth,
+//                      final_T, n_contrib
 //   bwd B'  per tile   per chunk and pixel: T_in and Q_in = dL/dC . (colour still to come), from the stored chunk composites
 //   bwd A'  per item   gradients of the chunk's Gaussians from (T_in, Q_in): front-to-back like the forward (T rebuilt by
 //                      multiplication, not division); per-pixel partials summed across the warp with a transposed butterfly
@@ -299,64 +299,169 @@ gsd_blend_fwd_chunk_kernel(GsdRenderParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// forward A2: find the terminating chunk of each pixel and replay it with the reference's exact sequential rule
+// forward B: per tile — combine the chunk composites in order and find the chunk in which each pixel's transmittance crosses 1e-4
 // ------------------------------------------------------------------------------------------------------
+// One pass over a tile's chunk composites (round 1 rebuilt T_in = prod P of ALL preceding chunks inside every work item of the
+// termination pass: O(chunks^2) loads per tile):
+//   1. fold chunk after chunk: C += T C_c, D += T D_c, T *= P_c (the loads of four chunks are in flight at a time); the first
+//      chunk c > 0 with T * P_c < 1e-4 is the pixel's terminating chunk: the reference's loop stops somewhere inside it
+//      (chunk 0 applies the stop rule itself: its T_in = 1 is known);
+//   2. pixels that do not terminate behind chunk 0: write colour (+ T * background), depth, final T and n_contrib;
+//      pixels that do: hand (terminating chunk, incoming T, composite so far) to pass C, which replays that chunk for them with
+//      the reference's per-Gaussian test T (1 - alpha) < 1e-4 and writes their outputs.
+// (Measured and not kept: replaying inside this kernel — per-tile serialisation of up to ~20 distinct terminating chunks made it
+// 79-96 us against 47 us for the two launches it replaced; the replays are independent across items and belong in their own grid.)
 template <int CH>
 __global__ void __launch_bounds__(GSD_CWARPS * 32)
-gsd_blend_fwd_term_kernel(GsdRenderParams p) {
+gsd_blend_fwd_finish_kernel(GsdRenderParams p) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
+    using IS = ItemState<CH>;
+    using TS = TermState<CH>;
+    constexpr int NPL = (CH == 3) ? 3 : 4;
+    constexpr int BATCH = 4;
+    const int tile = blockIdx.x;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int tx = tile % p.gx, ty = tile / p.gx;
+    const int wx0 = tx * GSD_TILE + (warp & 1) * 8, wy0 = ty * GSD_TILE + (warp >> 1) * 4;
+    const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
+    const bool inside = px < p.W && py < p.H;
+    const int item0 = p.chunk_ptr[tile];
+    const int nc = min(p.chunk_ptr[tile + 1], p.max_items) - item0;
+    if (nc <= 0) {   // empty tile: background only (uniform for the CTA)
+        if (inside) {
+            const size_t pid = (size_t)py * p.W + px;
+            const size_t plane = (size_t)p.W * p.H;
+            p.final_T[pid] = 1.0f;
+            p.n_contrib[pid] = 0;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) p.out_color[c * plane + pid] = (c < 3) ? __ldg(p.bg0 + c) : (p.bg1 ? __ldg(p.bg1 + (c % 3)) : 0.f);
+            p.out_depth[pid] = 0.f;
+        }
+        return;
+    }
+    float T = 1.0f, D = 0.f;
+    float C[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) C[c] = 0.f;
+    int last = 0;
+    int cstar = -1;       // chunk (> 0) in which this pixel's T crosses 1e-4; T then holds its incoming transmittance
+    if (nc > 0 && inside) {
+        const float *ts = p.term_state + (size_t)tile * TS::NF * 256;
+        if (reinterpret_cast<const int *>(ts)[TS::CSTAR * 256 + t] == 0) {
+            // stopped inside chunk 0: A1 applied the exact rule and left the absolute values
+            const int lc = reinterpret_cast<const int *>(ts)[TS::LAST * 256 + t];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) C[k] = ts[(TS::C + k) * 256 + t];
+            D = ts[TS::D * 256 + t];
+            T = ts[TS::T * 256 + t];
+            last = lc;
+        } else {
+            bool open = true;
+            for (int c0 = 0; c0 < nc && open; c0 += BATCH) {
+                float bP[BATCH], bD[BATCH], bC[BATCH][CH];
+                int bl[BATCH];
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u) {   // independent loads in flight
+                    const bool v = c0 + u < nc;
+                    const float *st = p.chunk_state + (size_t)(item0 + (v ? c0 + u : 0)) * IS::NF * 256;
+                    bl[u] = v ? reinterpret_cast<const int *>(st)[IS::LAST * 256 + t] : 0;
+                    bP[u] = v ? st[IS::P * 256 + t] : 1.0f;
+                    bD[u] = v ? st[IS::D * 256 + t] : 0.f;
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) bC[u][k] = v ? st[(IS::C + k) * 256 + t] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u) {
+                    const int c = c0 + u;
+                    if (c < nc && open) {
+                        const float Tn = __fmul_rn(T, bP[u]);
+                        if (c > 0 && Tn < T_EPS) {   // the reference stops inside this chunk: replay it below
+                            cstar = c;
+                            open = false;
+                        } else if (bl[u] > 0) {
+#pragma unroll
+                            for (int k = 0; k < CH; ++k) C[k] += T * bC[u][k];
+                            D += T * bD[u];
+                            T = Tn;
+                            last = c * GSD_CHUNK + bl[u];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!inside) return;
+    float *tsw = p.term_state + (size_t)tile * TS::NF * 256;
+    reinterpret_cast<int *>(tsw)[TS::CSTAR * 256 + t] = cstar;     // -1, or the chunk the replay pass finishes this pixel in
+    if (cstar >= 0) {
+        // hand the pixel over to the replay of chunk cstar: incoming transmittance and the composite of the chunks in front
+        tsw[TS::T * 256 + t] = T;
+        tsw[TS::D * 256 + t] = D;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) tsw[(TS::C + k) * 256 + t] = C[k];
+        reinterpret_cast<int *>(tsw)[TS::LAST * 256 + t] = last;
+        return;
+    }
+    const size_t pid = (size_t)py * p.W + px;
+    const size_t plane = (size_t)p.W * p.H;
+    p.final_T[pid] = T;
+    p.n_contrib[pid] = last;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const float bgc = (c < 3) ? __ldg(p.bg0 + c) : (p.bg1 ? __ldg(p.bg1 + (c % 3)) : 0.f);
+        p.out_color[c * plane + pid] = C[c] + T * bgc;
+    }
+    p.out_depth[pid] = D;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// forward C: per work item — replay of a terminating chunk for the pixels that stop inside it
+// ------------------------------------------------------------------------------------------------------
+// Every pixel terminates in at most one chunk, so every output pixel has exactly one writer (pass B or one item of this pass).
+// The records arrive by one TMA bulk copy per plane; items without a terminating pixel (most) exit after one 1 KB read.
+template <int CH>
+__global__ void __launch_bounds__(GSD_CWARPS * 32)
+gsd_blend_fwd_replay_kernel(GsdRenderParams p) {
     gsd_pdl_wait();
     gsd_pdl_launch();
     constexpr int NPL = (CH == 3) ? 3 : 4;
-    using IS = ItemState<CH>;
     using TS = TermState<CH>;
     __shared__ __align__(128) float4 planes[NPL][GSD_CHUNK];
     __shared__ __align__(8) uint64_t bar;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     ItemInfo I;
     if (!item_setup(p, blockIdx.x, warp, lane, I)) return;
-    if (I.chunk == 0) return; // handled exactly by A1
-    const int item0 = blockIdx.x - I.chunk;
-    // T_in = product of the preceding chunks' P (same order and ops in every kernel that rebuilds it)
-    float T = 1.0f;
-    // rectangles the forward look-back found opaque in front of this chunk (flag 2): nothing to rebuild, nothing to replay
-    bool dead = !I.inside || __ldcg(p.chunk_flags + (size_t)blockIdx.x * GSD_CWARPS + warp) == 2;
-    for (int c0 = 0; c0 < I.chunk && !dead; c0 += 8) {
-        float Pc[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) // independent loads in flight
-            Pc[u] = (c0 + u < I.chunk) ? p.chunk_state[(size_t)(item0 + c0 + u) * IS::NF * 256 + IS::P * 256 + I.pix] : 1.0f;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (c0 + u < I.chunk && !dead) {
-                const float Tn = __fmul_rn(T, Pc[u]);
-                if (Tn < T_EPS) dead = true; // terminated in an earlier chunk
-                T = Tn;
-            }
-        }
-    }
-    const float Pme = p.chunk_state[(size_t)blockIdx.x * IS::NF * 256 + IS::P * 256 + I.pix];
-    const bool crossing = !dead && (__fmul_rn(T, Pme) < T_EPS);
-    if (!__syncthreads_or(crossing ? 1 : 0)) return;
+    if (I.chunk == 0) return; // chunk 0 applies the exact rule in pass A
+    float *ts = p.term_state + (size_t)I.tile * TS::NF * 256;
+    const bool mine = I.inside && reinterpret_cast<const int *>(ts)[TS::CSTAR * 256 + I.pix] == I.chunk;
+    if (!__syncthreads_or(mine ? 1 : 0)) return;
     if (t == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     __syncthreads();
     if (t == 0) load_chunk<NPL>(p, planes, &bar, I.start, I.cnt);
-    mbar_wait(&bar, 0);
-    if (!__any_sync(0xffffffffu, crossing)) return;
-    // sequential replay for the crossing lanes: the reference's loop (renderCUDA forward) with the true incoming T
-    const float pxf = (float)I.px, pyf = (float)I.py;
-    float D = 0.f;
+    if (!__any_sync(0xffffffffu, mine)) return;
+    float T = 1.0f, D = 0.f;
     float C[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) C[c] = 0.f;
     int last = 0;
-    bool done = !crossing;
+    if (mine) {
+        T = ts[TS::T * 256 + I.pix];
+        D = ts[TS::D * 256 + I.pix];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) C[c] = ts[(TS::C + c) * 256 + I.pix];
+        last = reinterpret_cast<const int *>(ts)[TS::LAST * 256 + I.pix];
+    }
+    mbar_wait(&bar, 0);
+    // sequential replay for the terminating lanes: the reference's loop (renderCUDA forward) with the true incoming T
+    const float pxf = (float)I.px, pyf = (float)I.py;
+    int lastl = 0;
+    bool done = !mine;
     for (int grp = 0; grp < I.cnt; grp += GSD_SUB) {
         if (__all_sync(0xffffffffu, done)) break;
         const int idx = grp + lane;
         bool pass = false;
-        if (idx < I.cnt) {
-            pass = cull_pass(planes[0][idx], planes[1][idx], I.rx0, I.rx1, I.ry0, I.ry1);
-        }
+        if (idx < I.cnt) pass = cull_pass(planes[0][idx], planes[1][idx], I.rx0, I.rx1, I.ry0, I.ry1);
         unsigned m = __ballot_sync(0xffffffffu, pass);
         while (m) {
             const int j = grp + __ffs(m) - 1;
@@ -368,7 +473,7 @@ gsd_blend_fwd_term_kernel(GsdRenderParams p) {
             if (CH == 6) g3 = planes[NPL - 1][j];
             const float power = gsd_power(g1.x, g1.y, g1.z, g0.x - pxf, g0.y - pyf);
             const float alpha = fminf(0.99f, __fmul_rn(g1.w, gsd_gauss(power)));
-            // straight-line (predicated) update, as in A1
+            // straight-line (predicated) update, as in pass A
             bool ok = (!done) && (power <= 0.0f) && (alpha >= 1.0f / 255.0f);
             const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
             const bool stop = ok && test_T < T_EPS;
@@ -385,83 +490,12 @@ gsd_blend_fwd_term_kernel(GsdRenderParams p) {
             }
             D += g2.w * w;
             T = ok ? test_T : T;
-            last = ok ? j + 1 : last;
+            lastl = ok ? j + 1 : lastl;
         }
     }
-    if (crossing) {
-        float *ts = p.term_state + (size_t)I.tile * TS::NF * 256;
-        ts[TS::T * 256 + I.pix] = T;
-        ts[TS::D * 256 + I.pix] = D;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) ts[(TS::C + c) * 256 + I.pix] = C[c];
-        reinterpret_cast<int *>(ts)[TS::LAST * 256 + I.pix] = last; // 0: nothing of this chunk contributed before the stop
-        reinterpret_cast<int *>(ts)[TS::CSTAR * 256 + I.pix] = I.chunk;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// forward B: combine the chunks of a tile in order
-// ------------------------------------------------------------------------------------------------------
-template <int CH>
-__global__ void __launch_bounds__(GSD_CWARPS * 32)
-gsd_blend_fwd_combine_kernel(GsdRenderParams p) {
-    gsd_pdl_wait();
-    gsd_pdl_launch();
-    using IS = ItemState<CH>;
-    using TS = TermState<CH>;
-    const int tile = blockIdx.x;
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int tx = tile % p.gx, ty = tile / p.gx;
-    const int px = tx * GSD_TILE + (warp & 1) * 8 + (lane & 7), py = ty * GSD_TILE + (warp >> 1) * 4 + (lane >> 3);
-    if (px >= p.W || py >= p.H) return;
-    const int item0 = p.chunk_ptr[tile];
-    const int nc = min(p.chunk_ptr[tile + 1], p.max_items) - item0;
-    float T = 1.0f, D = 0.f;
-    float C[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) C[c] = 0.f;
-    int last = 0;
-    if (nc > 0) {
-        const float *ts = p.term_state + (size_t)tile * TS::NF * 256;
-        const int cstar = reinterpret_cast<const int *>(ts)[TS::CSTAR * 256 + t];
-        // the loads of chunk c+1 are issued before chunk c is folded in (the loop is otherwise a chain of dependent L2 round trips)
-        float nP = 0.f, nD = 0.f, nC[CH];
-        int nl = 0;
-        auto fetch = [&](int c) {
-            const float *st = p.chunk_state + (size_t)(item0 + c) * IS::NF * 256;
-            nl = reinterpret_cast<const int *>(st)[IS::LAST * 256 + t];
-            nP = st[IS::P * 256 + t];
-            nD = st[IS::D * 256 + t];
-#pragma unroll
-            for (int k = 0; k < CH; ++k) nC[k] = st[(IS::C + k) * 256 + t];
-        };
-        if (cstar != 0) fetch(0);
-        for (int c = 0; c < nc; ++c) {
-            if (c == cstar) {
-                const int lc = reinterpret_cast<const int *>(ts)[TS::LAST * 256 + t];
-#pragma unroll
-                for (int k = 0; k < CH; ++k) C[k] += ts[(TS::C + k) * 256 + t];
-                D += ts[TS::D * 256 + t];
-                T = ts[TS::T * 256 + t];
-                if (lc > 0) last = c * GSD_CHUNK + lc;
-                break;
-            }
-            const float cP = nP, cD = nD;
-            const int lc = nl;
-            float cC[CH];
-#pragma unroll
-            for (int k = 0; k < CH; ++k) cC[k] = nC[k];
-            if (c + 1 < nc && c + 1 != cstar) fetch(c + 1);
-            if (lc > 0) {
-#pragma unroll
-                for (int k = 0; k < CH; ++k) C[k] += T * cC[k];
-                D += T * cD;
-                T = __fmul_rn(T, cP);
-                last = c * GSD_CHUNK + lc;
-            }
-        }
-    }
-    const size_t pid = (size_t)py * p.W + px;
+    if (!mine) return;
+    if (lastl > 0) last = I.chunk * GSD_CHUNK + lastl;   // 0: nothing of this chunk contributed before the stop
+    const size_t pid = (size_t)I.py * p.W + I.px;
     const size_t plane = (size_t)p.W * p.H;
     p.final_T[pid] = T;
     p.n_contrib[pid] = last;
@@ -472,6 +506,7 @@ gsd_blend_fwd_combine_kernel(GsdRenderParams p) {
     }
     p.out_depth[pid] = D;
 }
+
 
 // ------------------------------------------------------------------------------------------------------
 // backward B': per chunk and pixel, the incoming transmittance and Q = dL/dC . (colour composited after this point)
@@ -735,12 +770,14 @@ int gsd_launch_render_fwd(const GsdRenderParams &p, int tiles, int n_sets, cudaS
         if (n_sets == 1) gsd_launch((gsd_blend_fwd_chunk_kernel<3>), dim3(p.max_items), dim3(threads), 0, st, p);
         else gsd_launch((gsd_blend_fwd_chunk_kernel<6>), dim3(p.max_items), dim3(threads), 0, st, p);
         GSD_LAUNCH_CHECK();
-        if (n_sets == 1) gsd_launch((gsd_blend_fwd_term_kernel<3>), dim3(p.max_items), dim3(threads), 0, st, p);
-        else gsd_launch((gsd_blend_fwd_term_kernel<6>), dim3(p.max_items), dim3(threads), 0, st, p);
-        GSD_LAUNCH_CHECK();
     }
-    if (n_sets == 1) gsd_launch((gsd_blend_fwd_combine_kernel<3>), dim3(tiles), dim3(threads), 0, st, p);
-    else gsd_launch((gsd_blend_fwd_combine_kernel<6>), dim3(tiles), dim3(threads), 0, st, p);
+    if (n_sets == 1) gsd_launch((gsd_blend_fwd_finish_kernel<3>), dim3(tiles), dim3(threads), 0, st, p);
+    else gsd_launch((gsd_blend_fwd_finish_kernel<6>), dim3(tiles), dim3(threads), 0, st, p);
+    GSD_LAUNCH_CHECK();
+    if (p.max_items > 0) {
+        if (n_sets == 1) gsd_launch((gsd_blend_fwd_replay_kernel<3>), dim3(p.max_items), dim3(threads), 0, st, p);
+        else gsd_launch((gsd_blend_fwd_replay_kernel<6>), dim3(p.max_items), dim3(threads), 0, st, p);
+    }
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
