@@ -109,6 +109,7 @@ EXPORTS = [
     "gsd_track_normalize_rotations", "gsd_track_update", "gsd_photometric_target_stats",
     "gsd_gnn_edges_workspace_bytes", "gsd_gnn_build_edges", "gsd_gnn_edge_inputs", "gsd_gnn_aggregate_workspace_bytes",
     "gsd_gnn_aggregate", "gsd_gnn_aggregate_bwd_workspace_bytes", "gsd_gnn_aggregate_bwd", "gsd_gnn_edge_inputs_bwd", "gsd_fps", "gsd_tf32_pack", "gsd_skin_bone_transforms", "gsd_skin_apply", "gsd_knn",
+    "gsd_tf32_split", "gsd_linear_tf32x3", "gsd_linear_small",
 ]
 
 
@@ -154,6 +155,10 @@ def lib():
     l.gsd_tf32_pack.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_skin_bone_transforms.argtypes = [C.c_int32] + [C.c_void_p] * 7
     l.gsd_skin_apply.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 8
+    l.gsd_tf32_split.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.gsd_linear_tf32x3.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+    l.gsd_linear_small.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     l.gsd_knn.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_fps.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = l

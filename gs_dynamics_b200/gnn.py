@@ -7,8 +7,11 @@ Mirrors (same names, argument meaning, results):
   farthest_point_sampler                     dgl.geometry (call sites /root/reference/src/render/dynamics_module.py:46,65)
   fps_rad_idx_torch                          /root/reference/src/data/utils.py:50-65
 Design: edges are index lists grouped by receiver (CSR), never one-hot matrices; the relation propagator
-Linear([enc_e | h_r | h_s]) is split into W1 enc_e (once per step, cuBLAS) + W2 h_r + W3 h_s (node-level GEMM per pstep), so
-the per-pstep edge work is one fused gather + ReLU + segment-sum kernel.  Dense Linears stay on cuBLAS fp32 (no TF32).
+Linear([enc_e | h_r | h_s]) is split into W1 enc_e (once per step) + W2 h_r + W3 h_s (node-level GEMM per pstep), so the
+per-pstep edge work is one fused gather + ReLU + segment-sum kernel.  Dense layers: inference runs every F-wide nn.Linear as ONE
+hand-written tcgen05 kernel (csrc/gemm_tc.cu: error-compensated 3xTF32 with fp32-level accuracy, bias / residual / ReLU in the
+epilogue, no library GEMM); training uses the same compensation through cuBLAS TF32 GEMMs (_Linear3x); matmul="ieee" keeps
+plain fp32 SIMT GEMMs for bit-tight comparisons.
 """
 import ctypes as C
 
@@ -200,6 +203,8 @@ def edge_index_from_dense(Rr, Rs, n_heavy=0):
 # dense layers: fp32 accuracy on the tensor cores by error-compensated TF32 splitting (x = x_hi + x_lo, three TF32 GEMMs:
 # hi*hi + hi*lo + lo*hi; the dropped lo*lo term is ~2^-22 relative).  The GEMMs themselves are cuBLAS (library code);
 # "ieee" keeps plain fp32 SIMT GEMMs.
+# Inference uses the hand-written tcgen05 kernel (gsd_linear_tf32x3, csrc/gemm_tc.cu) instead: same compensation, operands split in
+# shared memory, fused epilogues.
 # ----------------------------------------------------------------------------------------------------
 def _tf32_pack(x, relu=False, add=None, want_full=False, weight=False):
     """Error-compensated TF32 operand of t = relu?(x + add) (gsd_tf32_pack): activations -> [rows, 3F] = [lo | hi | hi],
@@ -214,6 +219,44 @@ def _tf32_pack(x, relu=False, add=None, want_full=False, weight=False):
         _lib.check(_lib.lib().gsd_tf32_pack(rows, Fd, int(relu), int(weight), x.data_ptr(), add.data_ptr() if add is not None else None,
                                             full.data_ptr() if want_full else None, out.data_ptr(), _stream()), "gsd_tf32_pack")
     return out, full
+
+
+def _tc_split(w):
+    """(w_hi, w_lo): the two TF32 operands of a weight matrix for gsd_linear_tf32x3."""
+    w = w.detach().contiguous()
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.lib().gsd_tf32_split(w.numel(), w.data_ptr(), hi.data_ptr(), lo.data_ptr(), _stream()), "gsd_tf32_split")
+    return hi, lo
+
+
+def _tc_linear(x, wsplit, bias=None, res1=None, res2=None, relu=False):
+    """act(x W^T + bias + res1 + res2) on the tcgen05 tensor cores with fp32-level accuracy (gsd_linear_tf32x3: hand-written
+    sm_100a kernel, error-compensated 3xTF32, the activation split happens in shared memory).  x: [M, K] with unit column stride."""
+    w_hi, w_lo = wsplit
+    M, K = x.shape
+    N = w_hi.shape[0]
+    if x.stride(1) != 1 or x.stride(0) % 4 != 0:
+        x = x.contiguous()
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    p = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().gsd_linear_tf32x3(M, N, K, x.data_ptr(), x.stride(0), w_hi.data_ptr(), w_lo.data_ptr(), p(bias), p(res1), p(res2),
+                                                int(relu), out.data_ptr(), N, _stream()), "gsd_linear_tf32x3")
+    return out
+
+
+def _small_linear(x, W, bias, relu=False):
+    """The two layer shapes that are not tensor-core work (K <= 32 or N <= 8), plain fp32 (gsd_linear_small)."""
+    M, K = x.shape
+    N = W.shape[0]
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().gsd_linear_small(M, N, K, x.data_ptr(), x.stride(0), W.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                               int(relu), out.data_ptr(), _stream()), "gsd_linear_small")
+    return out
 
 
 class _Linear3x(torch.autograd.Function):
@@ -398,11 +441,13 @@ class ParticlePredictor(nn.Module):
 
 
 class DynamicsPredictor(nn.Module):
-    def __init__(self, model_config, device, matmul="3xtf32"):
+    def __init__(self, model_config, device, matmul="tc"):
         super().__init__()
         self.model_config = model_config
         self.device = device
-        self.matmul = matmul   # "3xtf32": error-compensated TF32 tensor-core GEMMs for the edge-row layers; "ieee": fp32 SIMT
+        # "tc": hand-written tcgen05 3xTF32 GEMMs with fused epilogues (inference) / _Linear3x (training);
+        # "3xtf32": round 1's cuBLAS path over K-concatenated packed operands (kept for A/B measurements); "ieee": fp32 SIMT
+        self.matmul = matmul
         self.nf_particle = model_config['nf_particle']
         self.nf_relation = model_config['nf_relation']
         self.nf_effect = model_config['nf_effect']
@@ -482,6 +527,47 @@ class DynamicsPredictor(nn.Module):
             self._wkey = key
         return self._wpk
 
+    def _split_weights(self):
+        """(w_hi, w_lo) of every F-wide layer for the tcgen05 path, rebuilt when a parameter changes (version counters)."""
+        ps = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, "_tckey", None) != key:
+            Fd = self.nf_effect
+            Wr, Wp = self.relation_propagator.linear.weight.detach(), self.particle_propagator.linear.weight.detach()
+            pe, re, nr = self.particle_encoder.model, self.relation_encoder.model, self.non_rigid_predictor
+            sp = _tc_split
+            self._tcw = dict(pe2=sp(pe[2].weight), pe4=sp(pe[4].weight), re2=sp(re[2].weight), re4=sp(re[4].weight),
+                             A=sp(Wr[:, :Fd]), C0=sp(Wp[:, :Fd]), W23=sp(torch.cat([Wr[:, Fd:2 * Fd], Wr[:, 2 * Fd:]], 0)),
+                             Wp2=sp(Wp[:, Fd:]), nr0=sp(nr.linear_0.weight), nr1=sp(nr.linear_1.weight))
+            self._tckey = key
+        return self._tcw
+
+    def _forward_tc(self, p_inputs, rel_inputs, edges, B, N, n_p):
+        """Inference path on the hand-written tensor-core kernels: every F-wide layer is one gsd_linear_tf32x3 launch whose
+        epilogue carries the bias, the residual adds and the ReLU (model.py:202-241 with the relation propagator's weight split
+        of DESIGN.md §4); the K = 5 / 14 input layers and the 512 -> 3 head are plain fp32 kernels.  No library GEMM, no pack
+        launches, no elementwise launches between layers."""
+        cfg, Fd = self.model_config, self.nf_effect
+        W = self._split_weights()
+        pe, re, nr = self.particle_encoder.model, self.relation_encoder.model, self.non_rigid_predictor
+        br, bp = self.relation_propagator.linear.bias, self.particle_propagator.linear.bias
+        y = _small_linear(p_inputs.reshape(B * N, -1), pe[0].weight, pe[0].bias, relu=True)
+        y = _tc_linear(y, W["pe2"], pe[2].bias, relu=True)
+        h = _tc_linear(y, W["pe4"], pe[4].bias, relu=True)                       # particle_encode
+        C0 = _tc_linear(h, W["C0"], bp)                                          # pstep-invariant node term
+        e = _small_linear(rel_inputs.reshape(B * edges.capacity, -1), re[0].weight, re[0].bias, relu=True)
+        e = _tc_linear(e, W["re2"], re[2].bias, relu=True)
+        e = _tc_linear(e, W["re4"], re[4].bias, relu=True)                       # relation_encode
+        A = _tc_linear(e, W["A"], br)                                            # pstep-invariant edge term
+        for _ in range(cfg['pstep']):
+            P = _tc_linear(h, W["W23"])                                          # [B*N, 2F]: receiver | sender projections
+            agg = _Aggregate.apply(A, P, edges)
+            h = _tc_linear(agg, W["Wp2"], None, res1=C0, res2=h, relu=True)      # relu(C0 + h + agg Wp2^T)
+        x = h if n_p == N else h.view(B, N, Fd)[:, :n_p].reshape(B * n_p, Fd)
+        x = _tc_linear(x, W["nr0"], nr.linear_0.bias, relu=True)
+        x = _tc_linear(x, W["nr1"], nr.linear_1.bias, relu=True)
+        return _small_linear(x, nr.linear_2.weight, nr.linear_2.bias).view(B, n_p, 3)
+
     def _forward_3xtf32(self, p_inputs, rel_inputs, edges, B, N, n_p):
         """Inference path: every F-wide layer is one TF32 tensor-core GEMM over the error-compensated K = 3F operands
         (gsd_tf32_pack), which also carries the ReLU / residual add between layers.  Same results as the fp32 path to ~1e-6."""
@@ -533,11 +619,13 @@ class DynamicsPredictor(nn.Module):
         try:
             p_inputs = self._particle_inputs(state, attrs, action)
             rel_inputs = edge_inputs(state, attrs, p_instance, edges)
-            if self.matmul == "3xtf32" and not torch.is_grad_enabled() and B * N >= 256 and Fd % 4 == 0:
+            if self.matmul == "tc" and not torch.is_grad_enabled() and Fd % 64 == 0:
+                pred_motion = self._forward_tc(p_inputs, rel_inputs, edges, B, N, n_p)
+            elif self.matmul == "3xtf32" and not torch.is_grad_enabled() and B * N >= 256 and Fd % 4 == 0:
                 pred_motion = self._forward_3xtf32(p_inputs, rel_inputs, edges, B, N, n_p)
             else:
                 pred_motion = self._forward_ieee(p_inputs, rel_inputs, edges, B, N, n_p,
-                                                 fast=self.matmul == "3xtf32" and torch.is_grad_enabled() and Fd % 4 == 0)
+                                                 fast=self.matmul in ("tc", "3xtf32") and torch.is_grad_enabled() and Fd % 4 == 0)
             pred_pos = state[:, -1, :n_p] + torch.clamp(pred_motion, max=self.motion_clamp, min=-self.motion_clamp)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev_tf32

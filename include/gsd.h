@@ -318,6 +318,25 @@ int gsd_skin_apply(int32_t n_particles, int32_t n_bones, const float *xyz, const
 int gsd_fps(int32_t B, int32_t N, int32_t npoints, float radius, const float *pos, const int64_t *start_idx,
             int64_t *out_idx, int32_t *count, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Path B — dense layers on the tcgen05 tensor cores, fp32-accurate (replace nn.Linear of
+ * /root/reference/src/gnn/model.py:16-22,36-47,58-67 as composed at model.py:202-241)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* w_hi = tf32(w), w_lo = tf32(w - w_hi): the two TF32 operands of a weight matrix (once per weight update). */
+int gsd_tf32_split(int64_t n, const float *w, float *w_hi, float *w_lo, void *stream);
+
+/* out[M,N] = act(A[M,K] . W[N,K]^T + bias[N] + res1[M,N] + res2[M,N]); act = ReLU if relu else identity; bias / res1 / res2 may be
+ * NULL; res1 / res2 / out share the row stride ldo, A has row stride lda (elements).  Error-compensated 3xTF32 (a_lo w_hi + a_hi w_lo
+ * + a_hi w_hi, two fp32 accumulators in tensor memory): fp32-level accuracy.  Needs K % 32 == 0, N % 64 == 0, 16-byte aligned rows. */
+int gsd_linear_tf32x3(int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *W_hi, const float *W_lo,
+                      const float *bias, const float *res1, const float *res2, int32_t relu, float *out, int64_t ldo, void *stream);
+
+/* the two layer shapes of the model that are not tensor-core work, in plain fp32: K <= 32 (first encoder layers; N % 4 == 0,
+ * dense rows, optional ReLU) or N <= 8 (the 512 -> 3 motion head; K % 4 == 0, no activation). */
+int gsd_linear_small(int64_t M, int32_t N, int32_t K, const float *x, int64_t ldx, const float *W, const float *bias, int32_t relu,
+                     float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
