@@ -691,32 +691,48 @@ def run_gnn_cpu(budget_s=8.0, n_obj=2000, seed=1):
             "sample": "%d steps in %.1f s (dense one-hot reference formulation on host cores)" % (done, dt)}
 
 
-def run_gnn_train(device, world, steps=10, warmup=3, B=64, n_obj=100, n_future=5):
+def run_gnn_train(device, world, steps=20, warmup=3, B=64, n_obj=100, n_future=5):
     """GNN training iteration (train.py:176-218 at the reference's batch_size 64 / n_future 5, nf = 512,
-    ~100 object particles, topk 5): zero_grad + 5-step unroll + backward + gradient-bucket all-reduce (N > 1) + Adam.
-    Every rank trains on its own batch (weak scaling); device time per step, max over ranks."""
+    ~100 object particles, topk 5): zero_grad + 5-step unroll + backward + gradient-bucket all-reduce (N > 1, NCCL AVG) + Adam,
+    captured in ONE CUDA graph per rank (gnn_train.GraphedTrainStep).  Every rank trains on its own batch of a shared, learnable
+    mapping (weak scaling); device time per step, max over ranks; the reported losses are means over ALL ranks."""
     import torch.distributed as dist
     from gs_dynamics_b200 import gnn, gnn_train, workloads as GO
     rank = int(os.environ.get("RANK", "0"))
     cfg = GO.sloth_cfg(512)
     model = gnn.DynamicsPredictor(dict(cfg), device).to(device).train()
     model.load_state_dict(GO.make_state_dict(cfg, 0, head_scale=0.05))
-    batch = {k: v.to(device) for k, v in GO.make_training_batch(B, n_obj, 100 + rank, "sloth", n_future).items()}
+    batch = {k: v.to(device) for k, v in GO.make_training_batch(B, n_obj, 100 + rank, "sloth", n_future, learnable=True).items()}
     batch["Rr"] = gnn.construct_edges_index(batch["state"][:, -1], 0.075, batch["state_mask"], batch["eef_mask"], topk=5, connect_all=True)
     batch["Rs"] = None
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)    # train.py's learning rate
     bucket = gnn_train.GradientBucket(model.parameters())
     funcs = gnn_train.default_loss_funcs({"mse_loss": 1.0, "length_loss": 0.05})
-    losses = []
-    for _ in range(warmup):
-        losses.append(float(gnn_train.train_iteration(model, opt, batch, n_future, funcs, bucket)[0]))
+
+    def mean_loss(l):
+        t = l.detach().double().reshape(1).clone()
+        if world > 1:
+            dist.all_reduce(t)
+        return float(t[0]) / world
+    # eager iteration time (the round-1 path) for reference, then the graphed step
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l_first = gnn_train.train_iteration(model, opt, batch, n_future, funcs, bucket)[0]
+    loss_first = mean_loss(l_first)
+    e0.record()
+    for _ in range(3):
+        gnn_train.train_iteration(model, opt, batch, n_future, funcs, bucket)
+    e1.record()
+    torch.cuda.synchronize()
+    eager_ms = e0.elapsed_time(e1) / 3
+    step = gnn_train.GraphedTrainStep(model, opt, batch, n_future, funcs, bucket, warmup=warmup)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        loss, _ = gnn_train.train_iteration(model, opt, batch, n_future, funcs, bucket)
+        loss = step.step()
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=device)
@@ -725,10 +741,11 @@ def run_gnn_train(device, world, steps=10, warmup=3, B=64, n_obj=100, n_future=5
     dt = float(t[0])
     E = int(batch["Rr"].n_edges.sum())
     return {"metric": "GNN training samples/sec", "value": world * B * steps / dt, "unit": "samples/s", "ms_per_iteration": 1e3 * dt / steps,
-            "steps": steps, "n_gpus": world, "allreduce_bytes_per_step": int(bucket.flat.numel() * 4) if world > 1 else 0,
-            "loss_first": losses[0], "loss_last": float(loss),
+            "eager_ms_per_iteration": eager_ms, "steps": steps, "n_gpus": world,
+            "allreduce_bytes_per_step": int(bucket.flat.numel() * 4) if world > 1 else 0, "allreduce_op": "NCCL AVG, captured in the step's CUDA graph",
+            "loss_first_mean_over_ranks": loss_first, "loss_last_mean_over_ranks": mean_loss(loss), "iterations_between": 4 + warmup + 1 + steps,
             "config": {"workload": "train.py iteration: batch %d x (%d particles + pad + tool), %d edges/batch, n_future %d, nf 512, "
-                                   "mse + 0.05 length loss, Adam; DP = one batch per GPU + one flat-bucket all-reduce" % (B, n_obj, E, n_future)}}
+                                   "mse + 0.05 length loss, Adam lr 1e-4; DP = one batch per GPU + one flat-bucket all-reduce; whole iteration in one CUDA graph" % (B, n_obj, E, n_future)}}
 
 
 def run_gnn_train_cpu(B=4, n_obj=100, n_future=5):

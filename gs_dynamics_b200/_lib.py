@@ -86,6 +86,22 @@ class GsdAdam(C.Structure):
     ]
 
 
+class GsdDensifyPlan(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("do_densify", C.c_int32), ("grad_thresh", C.c_float), ("clone_limit", C.c_float), ("prune_opacity", C.c_float),
+        ("prune_big", C.c_float), ("grad_accum", C.c_void_p), ("denom", C.c_void_p), ("log_scales", C.c_void_p),
+        ("logit_opacities", C.c_void_p), ("dst", C.c_void_p), ("totals", C.c_void_p),
+    ]
+
+
+class GsdDensifyApply(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("samples_scaled", C.c_int32), ("reset_opacity", C.c_int32), ("dst", C.c_void_p), ("totals", C.c_void_p),
+        ("samples", C.c_void_p), ("p_src", C.c_void_p * 6), ("m_src", C.c_void_p * 6), ("v_src", C.c_void_p * 6),
+        ("p_dst", C.c_void_p * 6), ("m_dst", C.c_void_p * 6), ("v_dst", C.c_void_p * 6), ("width", C.c_int32 * 6),
+    ]
+
+
 class GsdGnnEdges(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("N", C.c_int32), ("n_tool", C.c_int32), ("topk", C.c_int32), ("connect_all", C.c_int32),
@@ -109,7 +125,7 @@ EXPORTS = [
     "gsd_track_normalize_rotations", "gsd_track_update", "gsd_photometric_target_stats",
     "gsd_gnn_edges_workspace_bytes", "gsd_gnn_build_edges", "gsd_gnn_edge_inputs", "gsd_gnn_aggregate_workspace_bytes",
     "gsd_gnn_aggregate", "gsd_gnn_aggregate_bwd_workspace_bytes", "gsd_gnn_aggregate_bwd", "gsd_gnn_edge_inputs_bwd", "gsd_fps", "gsd_tf32_pack", "gsd_skin_bone_transforms", "gsd_skin_apply", "gsd_knn",
-    "gsd_tf32_split", "gsd_linear_tf32x3", "gsd_linear_small",
+    "gsd_tf32_split", "gsd_linear_tf32x3", "gsd_linear_small", "gsd_densify_plan", "gsd_densify_apply",
 ]
 
 
@@ -159,6 +175,8 @@ def lib():
     l.gsd_linear_tf32x3.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
     l.gsd_linear_small.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    l.gsd_densify_plan.argtypes = [C.POINTER(GsdDensifyPlan), C.c_void_p]
+    l.gsd_densify_apply.argtypes = [C.POINTER(GsdDensifyApply), C.c_void_p]
     l.gsd_knn.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_fps.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = l

@@ -54,6 +54,16 @@ def _safe_norm(d):
     return torch.where(pos, torch.sqrt(torch.where(pos, sq, torch.ones_like(sq))), torch.zeros_like(sq))
 
 
+def _edge_mean(sq, edges, kwargs):
+    """Mean over the relation rows the way train.py:66-102 takes it: F.mse_loss over [B, n_rel_padded] where the dataset pads every
+    sample's one-hot matrices to `max_nR` rows (data/dataset.py:344,491-492) and the padding rows contribute 0.  Unused edge slots
+    contribute 0 here too, so only the DENOMINATOR depends on the padding: pass max_nR=<the reference config's value> in the batch
+    dict to get the reference's loss scale with a native EdgeIndex (default: the index's own capacity — identical when the edges
+    come from the reference's dense matrices through edge_index_from_dense)."""
+    denom = int(kwargs['max_nR']) if kwargs.get('max_nR') else sq.shape[1]
+    return sq.sum() / float(sq.shape[0] * denom)
+
+
 def length_loss(pred, gt, **kwargs):
     """MSE between the edge lengths of the prediction and of the oldest history frame (train.py:66-83)."""
     n_p = pred.shape[1]
@@ -61,7 +71,7 @@ def length_loss(pred, gt, **kwargs):
     edges = _edges_of(kwargs)
     pos_r, pos_s = _endpoints(pos, edges, n_p)
     pred_r, pred_s = _endpoints(pred, edges, n_p)
-    return F.mse_loss(_safe_norm(pred_r - pred_s), _safe_norm(pos_r - pos_s))
+    return _edge_mean((_safe_norm(pred_r - pred_s) - _safe_norm(pos_r - pos_s)) ** 2, edges, kwargs)
 
 
 def local_rigid_loss(pred, gt, **kwargs):
@@ -71,7 +81,7 @@ def local_rigid_loss(pred, gt, **kwargs):
     edges = _edges_of(kwargs)
     pos_r, pos_s = _endpoints(pos, edges, n_p)
     pred_r, pred_s = _endpoints(pred, edges, n_p)
-    return F.mse_loss(_safe_norm(pred_r - pos_r), _safe_norm(pred_s - pos_s))
+    return _edge_mean((_safe_norm(pred_r - pos_r) - _safe_norm(pred_s - pos_s)) ** 2, edges, kwargs)
 
 
 def umeyama_algorithm(X, Y, mask, fixed_scale=True):
@@ -170,9 +180,14 @@ class GradientBucket:
             o += p.numel()
 
     def all_reduce_mean(self):
+        """One collective over the flat buffer.  NCCL averages inside the collective (ReduceOp.AVG, no extra pass over the
+        buffer); gloo (the CPU tests) has no AVG, so sum + scale there."""
         if gdist.world_size() > 1:
-            torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.SUM)
-            self.flat.mul_(1.0 / gdist.world_size())
+            if torch.distributed.get_backend() == "nccl":
+                torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.AVG)
+            else:
+                torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.SUM)
+                self.flat.mul_(1.0 / gdist.world_size())
 
 
 def train_iteration(model, optimizer, data, n_future, loss_funcs, bucket=None):
@@ -187,3 +202,36 @@ def train_iteration(model, optimizer, data, n_future, loss_funcs, bucket=None):
         bucket.all_reduce_mean()
     optimizer.step()
     return loss_sum.detach(), parts
+
+
+class GraphedTrainStep:
+    """train_iteration captured in ONE CUDA graph: bucket.zero, the n_future unroll, backward, the gradient all-reduce (NCCL
+    collectives are capturable) and a capturable Adam step.  The eager iteration is CPU-launch-bound (hundreds of small kernels of
+    the unroll); replaying a graph removes the launch cost and, across ranks, the skew it causes in front of the all-reduce
+    (round 1 measured 31.1 ms -> 34.0 ms per iteration from 1 to 8 GPUs for an 11.6 MB collective that takes ~30 us on NVLink).
+    `data` holds the static batch buffers: copy the next batch into them (load_batch) before each step."""
+
+    def __init__(self, model, optimizer, data, n_future, loss_funcs, bucket, warmup=3):
+        self.model, self.optimizer, self.data, self.n_future, self.funcs, self.bucket = model, optimizer, data, n_future, loss_funcs, bucket
+        for g in optimizer.param_groups:
+            if not g.get('capturable', False):
+                raise ValueError("GraphedTrainStep needs torch.optim.Adam(..., capturable=True)")
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        self.warmup_losses = []
+        with torch.cuda.stream(s):
+            for _ in range(warmup):   # real iterations (allocator + NCCL communicator warm-up); the caller counts them
+                self.warmup_losses.append(train_iteration(model, optimizer, data, n_future, loss_funcs, bucket)[0])
+        torch.cuda.current_stream().wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, _ = train_iteration(model, optimizer, data, n_future, loss_funcs, bucket)
+
+    def load_batch(self, batch):
+        for k, v in batch.items():
+            if isinstance(v, torch.Tensor) and isinstance(self.data.get(k), torch.Tensor):
+                self.data[k].copy_(v, non_blocking=True)
+
+    def step(self):
+        self.graph.replay()
+        return self.loss

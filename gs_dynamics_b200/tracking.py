@@ -763,56 +763,82 @@ def accumulate_mean2d_gradient(variables):
     return variables
 
 
-def _rotation_matrices(q):
-    q = torch.nn.functional.normalize(q)
-    r, x, y, z = q.unbind(-1)
-    return torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
-                        2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
-                        2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], -1).reshape(-1, 3, 3)
+def _install_param(optimizer, params, name, value, exp_avg, exp_avg_sq):
+    """Swap a parameter group's tensor and Adam moments for freshly built ones (no copies); the step counter is kept."""
+    g = _group(optimizer, name)
+    old = g['params'][0]
+    st = optimizer.state.pop(old, None)
+    new = torch.nn.Parameter(value, requires_grad=old.requires_grad)
+    g['params'][0] = new
+    params[name] = new
+    step = st['step'] if st is not None else torch.zeros((), dtype=torch.float32, device=new.device)
+    optimizer.state[new] = dict(step=step, exp_avg=exp_avg, exp_avg_sq=exp_avg_sq)
 
 
 @torch.no_grad()
 def densify(params, variables, optimizer, i, remove_thresh, remove_thresh_5k, scale_scene_radius, grad_thresh=0.0002, normal_sampler=None):
     """Clone / split / prune schedule of external.py:229-299 (t = 0 only): every 100 iterations for 500 <= i <= 5000 points
     with a large screen-space gradient are cloned (small) or split in two (large, sampled from the Gaussian, scale / 1.6);
-    transparent (and, after 3000, oversized) points are pruned; opacities are reset to 0.01 every 3000 iterations."""
-    if i <= 5000:
-        variables = accumulate_mean2d_gradient(variables)
-        if i >= 500 and i % 100 == 0:
-            grads = variables['means2D_gradient_accum'] / variables['denom']
-            grads[grads.isnan()] = 0.0
-            limit = scale_scene_radius * variables['scene_radius']
-            big = torch.exp(params['log_scales']).max(dim=1).values > limit
-            hot = grads >= grad_thresh
-            # clone the small hot points
-            to_clone = hot & ~big
-            params = cat_params_to_optimizer({k: params[k].detach()[to_clone] for k in PER_POINT_KEYS}, params, optimizer)
-            n_now = params['means3D'].shape[0]
-            hot_pad = torch.zeros(n_now, dtype=torch.bool, device=hot.device)
-            hot_pad[:hot.shape[0]] = hot
-            to_split = hot_pad & (torch.exp(params['log_scales']).max(dim=1).values > limit)
-            n = 2
-            new = {k: params[k].detach()[to_split].repeat(n, 1) for k in PER_POINT_KEYS}
-            stds = torch.exp(params['log_scales'].detach())[to_split].repeat(n, 1)
-            samples = torch.normal(mean=torch.zeros_like(stds), std=stds) if normal_sampler is None else normal_sampler(stds)
-            rots = _rotation_matrices(params['unnorm_rotations'].detach()[to_split]).repeat(n, 1, 1)
-            new['means3D'] = new['means3D'] + torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1)
-            new['log_scales'] = torch.log(torch.exp(new['log_scales']) / (0.8 * n))
-            params = cat_params_to_optimizer(new, params, optimizer)
-            n_now = params['means3D'].shape[0]
-            for k in ('means2D_gradient_accum', 'denom', 'max_2D_radius'):
-                variables[k] = torch.zeros(n_now, device=hot.device)
-            drop = torch.cat((to_split, torch.zeros(n * int(to_split.sum()), dtype=torch.bool, device=hot.device)))
-            params, variables = remove_points(drop, params, variables, optimizer)
-            thr = remove_thresh_5k if i == 5000 else remove_thresh
-            drop = (torch.sigmoid(params['logit_opacities']) < thr).squeeze(-1)
-            if i >= 3000:
-                drop = drop | (torch.exp(params['log_scales']).max(dim=1).values > 0.1 * variables['scene_radius'])
-            params, variables = remove_points(drop, params, variables, optimizer)
-        if i > 0 and i % 3000 == 0:
-            reset = torch.full_like(params['logit_opacities'], math.log(0.01 / 0.99))   # inverse_sigmoid(0.01)
-            params = update_params_and_optimizer({'logit_opacities': reset}, params, optimizer)
-    return params, variables, params['means3D'].shape[0]
+    transparent (and, after 3000, oversized) points are pruned; opacities are reset to 0.01 every 3000 iterations.
+    One round = two kernels (gsd_densify_plan / gsd_densify_apply: classification, stream compaction of all 18 per-point arrays
+    and the Adam-state surgery) and ONE 16-byte read of the new point count, where the reference runs ~100 eager kernels with
+    ~10 host syncs.  normal_sampler(stds) -> samples replaces torch.normal for the split copies (tests: reproducible noise)."""
+    if i > 5000:
+        return params, variables, params['means3D'].shape[0]
+    variables = accumulate_mean2d_gradient(variables)
+    do_round = i >= 500 and i % 100 == 0
+    do_reset = i > 0 and i % 3000 == 0
+    if not (do_round or do_reset):
+        return params, variables, params['means3D'].shape[0]
+    lib = _lib.lib()
+    n = params['means3D'].shape[0]
+    dev = params['means3D'].device
+    src = [params[k].detach().contiguous() for k in PER_POINT_KEYS]
+    states = [optimizer.state[_group(optimizer, k)['params'][0]] for k in PER_POINT_KEYS]
+    widths = [t.shape[1] for t in src]
+    with torch.cuda.device(dev):
+        dst = torch.empty(4 * max(n, 1), dtype=torch.int32, device=dev)
+        totals = torch.empty(4, dtype=torch.int32, device=dev)
+        pl = _lib.GsdDensifyPlan()
+        pl.n, pl.do_densify = n, int(do_round)
+        pl.grad_thresh = float(grad_thresh)
+        pl.clone_limit = float(scale_scene_radius * variables['scene_radius'])
+        pl.prune_opacity = float(remove_thresh_5k if i == 5000 else remove_thresh)
+        pl.prune_big = float(0.1 * variables['scene_radius']) if i >= 3000 else 0.0
+        accum, denom = variables['means2D_gradient_accum'].contiguous(), variables['denom'].contiguous()
+        pl.grad_accum, pl.denom = accum.data_ptr(), denom.data_ptr()
+        pl.log_scales, pl.logit_opacities = src[5].data_ptr(), src[4].data_ptr()
+        pl.dst, pl.totals = dst.data_ptr(), totals.data_ptr()
+        _lib.check(lib.gsd_densify_plan(C.byref(pl), _stream()), "gsd_densify_plan")
+        k0, k1, k2, ns = [int(v) for v in totals.tolist()]          # the one host sync of the round
+        n_out = k0 + k1 + 2 * k2
+        scaled = 0
+        if ns > 0 and normal_sampler is not None:
+            split = dst[3 * n:4 * n] >= 0
+            samples = normal_sampler(torch.exp(src[5])[split].repeat(2, 1)).contiguous()
+            scaled = 1
+        else:
+            samples = torch.randn((max(2 * ns, 1), 3), dtype=torch.float32, device=dev)
+        new_p = [torch.empty((n_out, w), dtype=torch.float32, device=dev) for w in widths]
+        new_m = [torch.empty((n_out, w), dtype=torch.float32, device=dev) for w in widths]
+        new_v = [torch.empty((n_out, w), dtype=torch.float32, device=dev) for w in widths]
+        ap = _lib.GsdDensifyApply()
+        ap.n, ap.samples_scaled, ap.reset_opacity = n, scaled, int(do_reset)
+        ap.dst, ap.totals, ap.samples = dst.data_ptr(), totals.data_ptr(), samples.data_ptr()
+        keep = []
+        for t in range(6):
+            m, v = states[t]['exp_avg'].contiguous(), states[t]['exp_avg_sq'].contiguous()
+            keep += [m, v]
+            ap.p_src[t], ap.m_src[t], ap.v_src[t] = src[t].data_ptr(), m.data_ptr(), v.data_ptr()
+            ap.p_dst[t], ap.m_dst[t], ap.v_dst[t] = new_p[t].data_ptr(), new_m[t].data_ptr(), new_v[t].data_ptr()
+            ap.width[t] = widths[t]
+        _lib.check(lib.gsd_densify_apply(C.byref(ap), _stream()), "gsd_densify_apply")
+    for t, k in enumerate(PER_POINT_KEYS):
+        _install_param(optimizer, params, k, new_p[t], new_m[t], new_v[t])
+    if do_round:   # the statistics restart after every round (external.py:275-277; pruning zeros stays zeros)
+        for k in ('means2D_gradient_accum', 'denom', 'max_2D_radius'):
+            variables[k] = torch.zeros(n_out, device=dev)
+    return params, variables, n_out
 
 
 def initialize_params_from_point_cloud(init_pt_cld, cam_centers, device="cuda", max_cams=50):

@@ -156,10 +156,13 @@ def make_graph_inputs(n_obj, seed, kind="sloth", n_his=3):
                 state_mask=torch.ones(N, dtype=torch.bool), eef_mask=torch.tensor([False] * n_obj + [True]))
 
 
-def make_training_batch(B, n_obj, seed, kind="sloth", n_future=3, n_his=3, n_pad=2):
+def make_training_batch(B, n_obj, seed, kind="sloth", n_future=3, n_his=3, n_pad=2, learnable=False):
     """Seeded training-style batch (the dict DynDataset yields, /root/reference/src/data/dataset.py:240-420, without graph
     matrices): B elements of n_obj object particles + n_pad padding particles (state_mask False, as the dataset pads to
-    max_nobj) + 1 tool particle (last).  Futures: the objects drift by a smooth seeded field, the tool advances 5 mm per step."""
+    max_nobj) + 1 tool particle (last).  Futures: the objects drift by a smooth seeded field, the tool advances 5 mm per step.
+    learnable=True makes the futures a function of the inputs (the objects follow 60 % of the tool's displacement, plus 0.1 mm of
+    noise) instead of a per-element random drift: data-parallel runs on DIFFERENT batches then share one mapping to learn, and the
+    averaged gradient lowers every rank's loss (the random drift can only be memorised batch by batch)."""
     rng = np.random.default_rng(seed)
     N = n_obj + n_pad + 1
     n_p = n_obj + n_pad
@@ -183,8 +186,12 @@ def make_training_batch(B, n_obj, seed, kind="sloth", n_future=3, n_his=3, n_pad
         emask = torch.zeros(N, dtype=torch.bool)
         emask[-1] = True
         drift = torch.tensor(rng.normal(scale=0.002, size=(n_future, 1, 3)), dtype=torch.float32).cumsum(0)
+        noise = torch.tensor(rng.normal(scale=0.0005, size=(n_future, n_obj, 3)), dtype=torch.float32)
+        if learnable:
+            drift = 0.6 * act[-1][None, None, :] * torch.arange(1, n_future + 1, dtype=torch.float32)[:, None, None]
+            noise = 0.2 * noise
         sf = torch.zeros(n_future, n_p, 3)
-        sf[:, :n_obj] = st[-1, :n_obj][None] + drift + torch.tensor(rng.normal(scale=0.0005, size=(n_future, n_obj, 3)), dtype=torch.float32)
+        sf[:, :n_obj] = st[-1, :n_obj][None] + drift + noise
         tf = torch.zeros(max(n_future - 1, 1), N, 3)
         af = torch.zeros(max(n_future - 1, 1), N, 3)
         for f in range(n_future - 1):

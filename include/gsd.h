@@ -319,6 +319,44 @@ int gsd_fps(int32_t B, int32_t N, int32_t npoints, float radius, const float *po
             int64_t *out_idx, int32_t *count, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Path A.3 — first-frame densification (replaces densify / cat_params_to_optimizer / remove_points /
+ * update_params_and_optimizer, /root/reference/src/tracking/external.py:145-299)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Classifies every point (keep / clone / split), evaluates the prune predicate of every row the round would create and assigns the
+ * destination rows in the reference's final order [kept originals | kept clones | kept split copies A | kept split copies B].
+ * dst [4][n]: row of the original, of the clone, of split copy A (copy B = + totals[2]), rank among all split candidates (-1: none).
+ * totals [4]: kept originals, kept clones, kept split candidates, all split candidates -> n_out = t0 + t1 + 2 t2.
+ * do_densify = 0 plans a plain copy (used for the opacity reset alone). */
+typedef struct {
+    int32_t n, do_densify;
+    float grad_thresh;    /* 0.0002 */
+    float clone_limit;    /* scale_scene_radius * scene_radius: clone at <=, split above */
+    float prune_opacity;  /* remove_thresh (remove_thresh_5k at i == 5000) */
+    float prune_big;      /* 0.1 * scene_radius for i >= 3000, <= 0: off */
+    const float *grad_accum, *denom;       /* [n] means2D_gradient_accum, denom */
+    const float *log_scales;               /* [n,3] */
+    const float *logit_opacities;          /* [n] */
+    int32_t *dst;                          /* [4][n] */
+    int32_t *totals;                       /* [4] */
+} GsdDensifyPlan;
+int gsd_densify_plan(const GsdDensifyPlan *p, void *stream);
+
+/* Writes the new arrays.  Tensor order: means3D(3) rgb_colors(3) seg_colors(3) unnorm_rotations(4) logit_opacities(1) log_scales(3);
+ * p = parameter, m / v = Adam exp_avg / exp_avg_sq (appended rows get zeros, kept rows carry theirs).  samples: [2 * totals[3], 3]
+ * normal draws for the split copies (row r: copy A of split rank r, row totals[3] + r: copy B); samples_scaled = 1 if they are already
+ * multiplied by exp(log_scales).  reset_opacity: every output opacity = logit(0.01) with zero moments (external.py:293-295). */
+typedef struct {
+    int32_t n, samples_scaled, reset_opacity;
+    const int32_t *dst, *totals;
+    const float *samples;
+    const float *p_src[6], *m_src[6], *v_src[6];
+    float *p_dst[6], *m_dst[6], *v_dst[6];
+    int32_t width[6];
+} GsdDensifyApply;
+int gsd_densify_apply(const GsdDensifyApply *a, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Path B — dense layers on the tcgen05 tensor cores, fp32-accurate (replace nn.Linear of
  * /root/reference/src/gnn/model.py:16-22,36-47,58-67 as composed at model.py:202-241)
  * ------------------------------------------------------------------------------------------------ */

@@ -62,7 +62,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
             fields += [re.sub(r"\[.*\]", "", r).lstrip("*").strip() for r in rest]
         structs[name] = fields
     mirrored = {n: getattr(_lib, n) for n in structs if hasattr(_lib, n)}
-    assert {"GsdRasterFwd", "GsdRasterBwd", "GsdPhotometric", "GsdTrackLosses", "GsdTrackUpdate", "GsdAdam", "GsdGnnEdges"} <= set(mirrored)
+    assert {"GsdRasterFwd", "GsdRasterBwd", "GsdPhotometric", "GsdTrackLosses", "GsdTrackUpdate", "GsdAdam", "GsdGnnEdges", "GsdDensifyPlan", "GsdDensifyApply"} <= set(mirrored)
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gsd.h"', 'int main(void) {']
     for n, cls in mirrored.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (n, n))
