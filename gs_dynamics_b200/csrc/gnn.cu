@@ -343,59 +343,58 @@ extern "C" int gsd_gnn_edge_inputs(int32_t B, int32_t N, int32_t capacity, int32
 // One warp per (receiver) row for ordinary rows; rows with many edges (the tool rows: every object is a sender) are split
 // over GNN_SPLIT CTAs writing partials that a second kernel sums in fixed order.
 // ------------------------------------------------------------------------------------------------------
-#define GNN_SPLIT 128
+#define GNN_SPLIT 32
 
+// ONE launch: CTAs [0, rows_grid) take the light rows (one warp per receiver), the others the heavy (tool) rows, GNN_SPLIT CTAs
+// per row; the last of them to finish (ticket counter) adds the partials up in FIXED order — deterministic, no second launch.
 template <int VEC_PER_LANE> // F = 128 * VEC_PER_LANE
 __global__ void __launch_bounds__(128)
-gsd_gnn_aggregate_rows_kernel(int B, int N, int cap, int n_rows_per_b, const int32_t *__restrict__ row_ptr,
-                              const int32_t *__restrict__ send, const float4 *__restrict__ A, const float4 *__restrict__ P,
-                              float4 *__restrict__ agg) {
+gsd_gnn_aggregate_kernel(int B, int N, int cap, int n_light, int n_heavy, int rows_grid, const int32_t *__restrict__ row_ptr,
+                         const int32_t *__restrict__ send, const float4 *__restrict__ A, const float4 *__restrict__ P,
+                         float4 *__restrict__ agg, float4 *__restrict__ partial /* [B*n_heavy][GNN_SPLIT][F4] */, int32_t *__restrict__ tickets) {
     constexpr int F4 = 32 * VEC_PER_LANE; // float4 per feature row
-    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * warps + warp;
-    if (row >= (long long)B * n_rows_per_b) return;
-    const int b = (int)(row / n_rows_per_b), r = (int)(row % n_rows_per_b);
-    const int32_t *rp = row_ptr + (size_t)b * (N + 1);
-    const int e0 = min(rp[r], cap), e1 = min(rp[r + 1], cap);
-    const size_t node = (size_t)b * N + r;
-    float4 pr[VEC_PER_LANE], acc[VEC_PER_LANE];
-#pragma unroll
-    for (int v = 0; v < VEC_PER_LANE; ++v) {
-        pr[v] = P[node * 2 * F4 + v * 32 + lane];
-        acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    for (int e = e0; e < e1; ++e) {
-        const size_t ge = (size_t)b * cap + e;
-        const size_t snode = (size_t)b * N + send[ge];
+    if ((int)blockIdx.x < rows_grid) {
+        const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const long long row = (long long)blockIdx.x * warps + warp;
+        if (row >= (long long)B * n_light) return;
+        const int b = (int)(row / n_light), r = (int)(row % n_light);
+        const int32_t *rp = row_ptr + (size_t)b * (N + 1);
+        const int e0 = min(rp[r], cap), e1 = min(rp[r + 1], cap);
+        const size_t node = (size_t)b * N + r;
+        float4 pr[VEC_PER_LANE], acc[VEC_PER_LANE];
 #pragma unroll
         for (int v = 0; v < VEC_PER_LANE; ++v) {
-            const float4 a4 = A[ge * F4 + v * 32 + lane];
-            const float4 s4 = P[snode * 2 * F4 + F4 + v * 32 + lane];
-            acc[v].x += fmaxf(a4.x + pr[v].x + s4.x, 0.f);
-            acc[v].y += fmaxf(a4.y + pr[v].y + s4.y, 0.f);
-            acc[v].z += fmaxf(a4.z + pr[v].z + s4.z, 0.f);
-            acc[v].w += fmaxf(a4.w + pr[v].w + s4.w, 0.f);
+            pr[v] = P[node * 2 * F4 + v * 32 + lane];
+            acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    }
+        for (int e = e0; e < e1; ++e) {
+            const size_t ge = (size_t)b * cap + e;
+            const size_t snode = (size_t)b * N + send[ge];
 #pragma unroll
-    for (int v = 0; v < VEC_PER_LANE; ++v) agg[node * F4 + v * 32 + lane] = acc[v];
-}
-
-template <int VEC_PER_LANE>
-__global__ void __launch_bounds__(128)
-gsd_gnn_aggregate_heavy_kernel(int B, int N, int cap, int first_row, int n_heavy, const int32_t *__restrict__ row_ptr,
-                               const int32_t *__restrict__ send, const float4 *__restrict__ A, const float4 *__restrict__ P,
-                               float4 *__restrict__ partial /* [B*n_heavy][GNN_SPLIT][F4] */) {
-    constexpr int F4 = 32 * VEC_PER_LANE;
-    const int hrow = blockIdx.x, split = blockIdx.y; // hrow in [0, B*n_heavy)
-    const int b = hrow / n_heavy, r = first_row + hrow % n_heavy;
+            for (int v = 0; v < VEC_PER_LANE; ++v) {
+                const float4 a4 = A[ge * F4 + v * 32 + lane];
+                const float4 s4 = P[snode * 2 * F4 + F4 + v * 32 + lane];
+                acc[v].x += fmaxf(a4.x + pr[v].x + s4.x, 0.f);
+                acc[v].y += fmaxf(a4.y + pr[v].y + s4.y, 0.f);
+                acc[v].z += fmaxf(a4.z + pr[v].z + s4.z, 0.f);
+                acc[v].w += fmaxf(a4.w + pr[v].w + s4.w, 0.f);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < VEC_PER_LANE; ++v) agg[node * F4 + v * 32 + lane] = acc[v];
+        return;
+    }
+    // ---- heavy rows
+    __shared__ int s_last;
+    const int hidx = (int)blockIdx.x - rows_grid;
+    const int hrow = hidx / GNN_SPLIT, split = hidx % GNN_SPLIT; // hrow in [0, B*n_heavy)
+    const int b = hrow / n_heavy, r = n_light + hrow % n_heavy;
     const int32_t *rp = row_ptr + (size_t)b * (N + 1);
     const int e0 = min(rp[r], cap), e1 = min(rp[r + 1], cap);
     const int n = e1 - e0;
     const int per = (n + GNN_SPLIT - 1) / GNN_SPLIT;
     const int s0 = e0 + split * per, s1 = min(e1, s0 + per);
     const size_t node = (size_t)b * N + r;
-    // 128 threads = one float4 column each for F = 512; generic: loop columns
     for (int col = threadIdx.x; col < F4; col += blockDim.x) {
         const float4 pr = P[node * 2 * F4 + col];
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -421,31 +420,20 @@ gsd_gnn_aggregate_heavy_kernel(int B, int N, int cap, int first_row, int n_heavy
         }
         partial[((size_t)hrow * GNN_SPLIT + split) * F4 + col] = acc;
     }
-}
-
-__global__ void __launch_bounds__(256)
-gsd_gnn_aggregate_heavy_finish_kernel(int N, int first_row, int n_heavy, int F4, const float4 *__restrict__ partial,
-                                      float4 *__restrict__ agg) {
-    __shared__ float4 red[8][32];
-    const int hrow = blockIdx.x;
-    const int b = hrow / n_heavy, r = first_row + hrow % n_heavy;
-    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    const int col = blockIdx.y * 32 + lane;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (col < F4) {
-#pragma unroll 4
-        for (int s = grp * (GNN_SPLIT / 8); s < (grp + 1) * (GNN_SPLIT / 8); ++s) {
-            const float4 p = partial[((size_t)hrow * GNN_SPLIT + s) * F4 + col];
-            acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
-        }
-    }
-    red[grp][lane] = acc;
+    __threadfence();
     __syncthreads();
-    if (grp == 0 && col < F4) {
+    if (threadIdx.x == 0) s_last = (atomicAdd(&tickets[hrow], 1) == GNN_SPLIT - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int col = threadIdx.x; col < F4; col += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < GNN_SPLIT; s += 8) {   // loads of 8 partials in flight, added in index order
+            float4 p[8];
 #pragma unroll
-        for (int g = 1; g < 8; ++g) { // fixed order: deterministic
-            const float4 p = red[g][lane];
-            acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+            for (int u = 0; u < 8; ++u) p[u] = __ldcg(&partial[((size_t)hrow * GNN_SPLIT + s + u) * F4 + col]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { acc.x += p[u].x; acc.y += p[u].y; acc.z += p[u].z; acc.w += p[u].w; }
         }
         agg[((size_t)b * N + r) * F4 + col] = acc;
     }
@@ -453,7 +441,8 @@ gsd_gnn_aggregate_heavy_finish_kernel(int N, int first_row, int n_heavy, int F4,
 
 extern "C" int gsd_gnn_aggregate_workspace_bytes(int32_t B, int32_t n_heavy, int32_t F, size_t *bytes) {
     if (B <= 0 || n_heavy < 0 || F <= 0 || !bytes) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
-    *bytes = gsd_align_up((size_t)B * (n_heavy > 0 ? n_heavy : 1) * GNN_SPLIT * F * 4);
+    const size_t rows = (size_t)B * (n_heavy > 0 ? n_heavy : 1);
+    *bytes = gsd_align_up(rows * GNN_SPLIT * F * 4) + gsd_align_up(rows * 4);   // partial sums, then the ticket counters
     return GSD_OK;
 }
 
@@ -469,29 +458,24 @@ extern "C" int gsd_gnn_aggregate(int32_t B, int32_t N, int32_t capacity, int32_t
     const int n_light = N - n_heavy;
     const int warps = 4;
     const long long rows = (long long)B * n_light;
-    if (rows > 0) {
-        unsigned grid = (unsigned)((rows + warps - 1) / warps);
-        // light rows of batch b are rows [0, n_light): pass n_rows_per_b = n_light
-        switch (F / 128) {
-        case 1: gsd_gnn_aggregate_rows_kernel<1><<<grid, 128, 0, st>>>(B, N, capacity, n_light, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)agg); break;
-        case 2: gsd_gnn_aggregate_rows_kernel<2><<<grid, 128, 0, st>>>(B, N, capacity, n_light, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)agg); break;
-        case 3: gsd_gnn_aggregate_rows_kernel<3><<<grid, 128, 0, st>>>(B, N, capacity, n_light, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)agg); break;
-        default: gsd_gnn_aggregate_rows_kernel<4><<<grid, 128, 0, st>>>(B, N, capacity, n_light, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)agg); break;
-        }
-        GSD_LAUNCH_CHECK();
-    }
+    const int rows_grid = (int)((rows + warps - 1) / warps);
+    const int heavy_grid = B * n_heavy * GNN_SPLIT;
+    if (rows_grid + heavy_grid == 0) return GSD_OK;
+    int32_t *tickets = nullptr;
     if (n_heavy > 0) {
-        dim3 grid(B * n_heavy, GNN_SPLIT);
-        switch (F / 128) {
-        case 1: gsd_gnn_aggregate_heavy_kernel<1><<<grid, 128, 0, st>>>(B, N, capacity, n_light, n_heavy, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)ws); break;
-        case 2: gsd_gnn_aggregate_heavy_kernel<2><<<grid, 128, 0, st>>>(B, N, capacity, n_light, n_heavy, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)ws); break;
-        case 3: gsd_gnn_aggregate_heavy_kernel<3><<<grid, 128, 0, st>>>(B, N, capacity, n_light, n_heavy, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)ws); break;
-        default: gsd_gnn_aggregate_heavy_kernel<4><<<grid, 128, 0, st>>>(B, N, capacity, n_light, n_heavy, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)ws); break;
-        }
-        GSD_LAUNCH_CHECK();
-        gsd_gnn_aggregate_heavy_finish_kernel<<<dim3(B * n_heavy, (F / 4 + 31) / 32), 256, 0, st>>>(N, n_light, n_heavy, F / 4, (const float4 *)ws, (float4 *)agg);
-        GSD_LAUNCH_CHECK();
+        tickets = (int32_t *)((char *)ws + gsd_align_up((size_t)B * n_heavy * GNN_SPLIT * F * 4));
+        GSD_CUDA_CHECK(cudaMemsetAsync(tickets, 0, (size_t)B * n_heavy * 4, st));
     }
+    const dim3 grid((unsigned)(rows_grid + heavy_grid));
+#define GSD_AGG_ARGS B, N, capacity, n_light, n_heavy, rows_grid, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)agg, (float4 *)ws, tickets
+    switch (F / 128) {
+    case 1: gsd_gnn_aggregate_kernel<1><<<grid, 128, 0, st>>>(GSD_AGG_ARGS); break;
+    case 2: gsd_gnn_aggregate_kernel<2><<<grid, 128, 0, st>>>(GSD_AGG_ARGS); break;
+    case 3: gsd_gnn_aggregate_kernel<3><<<grid, 128, 0, st>>>(GSD_AGG_ARGS); break;
+    default: gsd_gnn_aggregate_kernel<4><<<grid, 128, 0, st>>>(GSD_AGG_ARGS); break;
+    }
+#undef GSD_AGG_ARGS
+    GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
 

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib
+from . import _lib, _nvtx
 
 
 def _stream():
@@ -702,6 +702,10 @@ class GnnRollout:
         return pred
 
     def step(self, eef_delta=None):
+        with _nvtx.range("gsd.gnn_rollout_step"):
+            return self._step(eef_delta)
+
+    def _step(self, eef_delta=None):
         if eef_delta is not None:
             self.eef_delta.copy_(eef_delta)
         if not self.use_graph:

@@ -18,7 +18,7 @@ from typing import NamedTuple
 
 import torch
 
-from . import _lib
+from . import _lib, _nvtx
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -136,7 +136,8 @@ def raster_forward(settings, means3D, opacities, colors0, scales, rotations, col
         d.capacity = capacity
         d.geom_ws, d.binning_ws, d.image_ws = geom.data_ptr(), binning.data_ptr(), image.data_ptr()
         d.out_color, d.out_depth = color.data_ptr(), depth.data_ptr()
-        _lib.check(lib.gsd_raster_forward(C.byref(d), st), "gsd_raster_forward")
+        with _nvtx.range("gsd.raster_forward"):
+            _lib.check(lib.gsd_raster_forward(C.byref(d), st), "gsd_raster_forward")
 
     state = RasterState()
     state.desc = d
@@ -172,7 +173,8 @@ def raster_backward(state, grad_color, need_means2D=True, geom_only=False):
         b.dL_dmeans3D, b.dL_dmeans2D = ptr(g["means3D"]), ptr(g["means2D"])
         b.dL_dcolors0, b.dL_dcolors1 = ptr(g["colors0"]), ptr(g["colors1"])
         b.dL_dopacities, b.dL_dscales, b.dL_drotations = ptr(g["opacities"]), ptr(g["scales"]), ptr(g["rotations"])
-        _lib.check(lib.gsd_raster_backward(C.byref(b), _stream()), "gsd_raster_backward")
+        with _nvtx.range("gsd.raster_backward"):
+            _lib.check(lib.gsd_raster_backward(C.byref(b), _stream()), "gsd_raster_backward")
     return g
 
 

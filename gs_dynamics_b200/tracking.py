@@ -18,7 +18,7 @@ import math
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, _nvtx
 from . import rasterizer as R
 from .rasterizer import GaussianRasterizationSettings as Camera
 from .rasterizer import GaussianRasterizer as Renderer
@@ -179,7 +179,8 @@ def _track_priors_launch(means3D, rotations, variables, weights):
         gx = torch.empty_like(x)
         gq = torch.empty_like(q)
         t.ws, t.losses, t.grad_means3D, t.grad_rotations = ws.data_ptr(), losses.data_ptr(), gx.data_ptr(), gq.data_ptr()
-        _lib.check(lib.gsd_track_losses_fwd_bwd(C.byref(t), _stream()), "gsd_track_losses_fwd_bwd")
+        with _nvtx.range("gsd.track_priors"):
+            _lib.check(lib.gsd_track_losses_fwd_bwd(C.byref(t), _stream()), "gsd_track_losses_fwd_bwd")
     return losses, gx, gq
 
 
@@ -560,11 +561,12 @@ class TrackingStep:
         self.prepare(list(self.capacity.keys()) or None)
 
     def step(self, cam_id):
-        if self.use_graph:
-            self.graphs[cam_id].replay()
-            return self.losses[cam_id]
-        self.optimizer.zero_grad(set_to_none=True)
-        return self._iteration(self.dataset[cam_id], self.capacity.get(cam_id))
+        with _nvtx.range("gsd.tracking_iteration"):
+            if self.use_graph:
+                self.graphs[cam_id].replay()
+                return self.losses[cam_id]
+            self.optimizer.zero_grad(set_to_none=True)
+            return self._iteration(self.dataset[cam_id], self.capacity.get(cam_id))
 
 
 class FusedTrackingStep(TrackingStep):
@@ -650,7 +652,8 @@ class FusedTrackingStep(TrackingStep):
             ph = torch.empty(8, dtype=torch.float32, device=x.device)
             d = _ph_desc(color, tgt, 2, 0.8, 0.2, (self.w['weight_im'], self.w['weight_seg']), ws,
                          affine=(P['cam_m'][cid], P['cam_c'][cid]), y_stats=tst)
-            _lib.check(lib.gsd_photometric_stats(C.byref(d), st), "gsd_photometric_stats")
+            with _nvtx.range("gsd.photometric"):
+                _lib.check(lib.gsd_photometric_stats(C.byref(d), st), "gsd_photometric_stats")
             # the scalar reduction (and the addition of the prior losses: ph[7] is the iteration's loss) is not needed by the
             # gradient pass: it joins the side branch instead of sitting on the critical path
             stats_done = torch.cuda.Event()
