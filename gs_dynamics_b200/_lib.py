@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgsd_b200.so")
+LIB_PATH = os.environ.get("GSD_LIB_PATH") or os.path.join(_HERE, "libgsd_b200.so")   # GSD_LIB_PATH: a debug build of the same sources
 
 GSD_STATUS_WORDS = 8
 

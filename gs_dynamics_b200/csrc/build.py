@@ -8,6 +8,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libgsd_b200.so")
 OBJ = os.path.join(HERE, "_obj")
+# debug variants (e.g. GSD_BUILD_DEFINES="-DGSD_RACECHECK_ARRIVE_ALL" GSD_BUILD_TAG=rc): separate objects and library name,
+# loaded with GSD_LIB_PATH=<that .so>
+if os.environ.get("GSD_BUILD_TAG"):
+    LIB = os.path.join(PKG, "libgsd_b200_%s.so" % os.environ["GSD_BUILD_TAG"])
+    OBJ = os.path.join(HERE, "_obj_%s" % os.environ["GSD_BUILD_TAG"])
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -37,7 +42,7 @@ def build_lib(force=False, verbose=False):
         src = os.path.join(HERE, s)
         obj = os.path.join(OBJ, s[:-3] + ".o")
         if force or _stale(obj, [src] + headers):
-            jobs.append((s, [nvcc] + ARCH + COMMON + EXTRA.get(s, []) + ["-c", src, "-o", obj]))
+            jobs.append((s, [nvcc] + ARCH + COMMON + EXTRA.get(s, []) + os.environ.get("GSD_BUILD_DEFINES", "").split() + ["-c", src, "-o", obj]))
     logs = {}
 
     def run(job):

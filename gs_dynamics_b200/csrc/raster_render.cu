@@ -37,6 +37,15 @@ template <int CH> struct TermState {
     static constexpr int T = 0, D = 1, C = 2, LAST = 2 + CH, CSTAR = 3 + CH, NF = 4 + CH;
 };
 
+// The accumulator ring of the blend backward hands a stage over with ONE mbarrier arrival per warp (lane 0, after __syncwarp()
+// has ordered the other lanes' shared-memory accesses before it).  compute-sanitizer's racecheck attributes an arrival only to
+// the arriving thread, so it reports the other 31 lanes' accesses as hazards; -DGSD_RACECHECK_ARRIVE_ALL makes every lane arrive
+// (same protocol, 32x the arrival count) for the sanitizer run recorded in profiles/.
+#ifdef GSD_RACECHECK_ARRIVE_ALL
+#define GSD_RING_ARRIVALS 32
+#else
+#define GSD_RING_ARRIVALS 1
+#endif
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -612,7 +621,7 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
     if (t == 0) {
         mbar_init(&bar, 1);
 #pragma unroll
-        for (int s = 0; s < S; ++s) { mbar_init(&done_bar[s], NW); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(&done_bar[s], NW * GSD_RING_ARRIVALS); mbar_init(&empty[s], GSD_RING_ARRIVALS); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -656,7 +665,7 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            if (GSD_RING_ARRIVALS == 32 || lane == 0) mbar_arrive(&empty[s]);
         }
         return;
     }
@@ -755,7 +764,7 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
         }
         if (lane == 0) wmask[s][warp] = touched;
         __syncwarp();
-        if (lane == 0) mbar_arrive(&done_bar[s]);
+        if (GSD_RING_ARRIVALS == 32 || lane == 0) mbar_arrive(&done_bar[s]);
     }
 }
 
