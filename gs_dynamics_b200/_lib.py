@@ -126,6 +126,7 @@ EXPORTS = [
     "gsd_gnn_edges_workspace_bytes", "gsd_gnn_build_edges", "gsd_gnn_edge_inputs", "gsd_gnn_aggregate_workspace_bytes",
     "gsd_gnn_aggregate", "gsd_gnn_aggregate_bwd_workspace_bytes", "gsd_gnn_aggregate_bwd", "gsd_gnn_edge_inputs_bwd", "gsd_fps", "gsd_tf32_pack", "gsd_skin_bone_transforms", "gsd_skin_apply", "gsd_knn",
     "gsd_tf32_split", "gsd_linear_tf32x3", "gsd_linear_small", "gsd_densify_plan", "gsd_densify_apply",
+    "gsd_gnn_rollout_pre", "gsd_gnn_rollout_post",
 ]
 
 
@@ -171,6 +172,8 @@ def lib():
     l.gsd_tf32_pack.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_skin_bone_transforms.argtypes = [C.c_int32] + [C.c_void_p] * 7
     l.gsd_skin_apply.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 8
+    l.gsd_gnn_rollout_pre.argtypes = [C.c_int32] * 8 + [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 3
+    l.gsd_gnn_rollout_post.argtypes = [C.c_int32] * 4 + [C.c_void_p] * 3 + [C.c_int32, C.c_float, C.c_void_p, C.c_void_p]
     l.gsd_tf32_split.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_linear_tf32x3.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]

@@ -38,6 +38,10 @@ struct EdgeArgs {
     int32_t *row_count;      // [B*N]
 };
 
+// KL > 0: every lane keeps the KL smallest (distance, column) keys of ITS columns in registers while the distances are computed;
+// the row's k <= KL nearest are then k rounds of a warp arg-min over the lanes' list heads (two redux.sync each).  KL = 0: the
+// general path (bisection to a small candidate set + ranking, or k rounds of arg-min over the whole row).
+template <int KL>
 __global__ void __launch_bounds__(256)
 gsd_gnn_adjacency_kernel(EdgeArgs a) {
     // shared: positions [N*3] | per warp: candidates [GNN_CAND] u64 | per warp: row distances [N] | per warp: selected bits [words]
@@ -69,12 +73,30 @@ gsd_gnn_adjacency_kernel(EdgeArgs a) {
 
     // ---- distances of this row, cached per warp (masked pairs -> 1e10 like the reference's dis[mask] = 1e10)
     int cnt = 0; // object columns within the radius
+    constexpr int KLR = KL > 0 ? KL : 1;
+    unsigned long long best[KLR];   // ascending; key = distance bits << 32 | column (d >= 0: bit order = value order, ties -> lowest column)
+#pragma unroll
+    for (int j = 0; j < KLR; ++j) best[j] = ~0ull;
     for (int c = lane; c < a.N; c += 32) {
         float d = dist2_rn(rx, ry, rz, spos[3 * c], spos[3 * c + 1], spos[3 * c + 2]);
         const int fc = sflag[c];
         if (!(r_valid && (fc & 1)) || (r_tool && (fc & 2))) d = 1e10f;
         sd[c] = d;
-        cnt += (c < n_obj && __fsub_rn(d, thr) < 0.f) ? 1 : 0;
+        const bool in = c < n_obj && __fsub_rn(d, thr) < 0.f;
+        cnt += in ? 1 : 0;
+        if (KL > 0 && in && r < n_obj) {
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)c;
+            if (key < best[KLR - 1]) {
+                best[KLR - 1] = key;
+#pragma unroll
+                for (int j = KLR - 1; j >= 1; --j) {
+                    const unsigned long long lo = best[j - 1], hi = best[j];
+                    const bool sw = hi < lo;
+                    best[j - 1] = sw ? hi : lo;
+                    best[j] = sw ? lo : hi;
+                }
+            }
+        }
     }
     for (int w = lane; w < a.words; w += 32) selbits[w] = 0u;
     cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -86,7 +108,23 @@ gsd_gnn_adjacency_kernel(EdgeArgs a) {
     // bisection until a small candidate set (>= k columns) lies inside it, compact that set into shared memory, rank the
     // candidates against each other (ties -> lowest index) and set the bits of those ranked below k.  If bisection cannot
     // separate (hundreds of equal distances, or k larger than the buffer) fall back to k rounds of warp arg-min.
-    if (r < n_obj && cnt > 0) {
+    if (KL > 0 && r < n_obj && cnt > 0) {
+        const int k_eff = min(a.topk, a.N);   // the launcher guarantees k_eff <= KL
+        for (int it = 0; it < k_eff; ++it) {
+            const unsigned hd = (unsigned)(best[0] >> 32), hc = (unsigned)best[0];
+            const unsigned md = __reduce_min_sync(0xffffffffu, hd);
+            if (md == 0xffffffffu) break;                                   // no within-radius column left
+            const unsigned mc = __reduce_min_sync(0xffffffffu, hd == md ? hc : 0xffffffffu);
+            if (hd == md && hc == mc) {                                     // exactly one lane owns column mc
+                atomicOr(&selbits[mc >> 5], 1u << (mc & 31));
+#pragma unroll
+                for (int j = 0; j < KLR - 1; ++j) best[j] = best[j + 1];
+                best[KLR - 1] = ~0ull;
+            }
+        }
+        __syncwarp();
+    }
+    if (KL == 0 && r < n_obj && cnt > 0) {
         const int k_eff = min(a.topk, a.N);
         const int want = min(GNN_CAND, max(64, 2 * k_eff)); // candidate-set size the bisection aims below
         float t = thr;
@@ -174,56 +212,38 @@ gsd_gnn_adjacency_kernel(EdgeArgs a) {
     } // rows
 }
 
-// single block: exclusive scan of row counts per batch element -> row_ptr [B][N+1]; n_edges[b]
-__global__ void gsd_gnn_scan_rows_kernel(int B, int N, const int32_t *__restrict__ row_count, int32_t *__restrict__ row_ptr,
-                                         int32_t *__restrict__ n_edges) {
-    __shared__ int sbuf[1024];
-    __shared__ int carry;
-    for (int b = 0; b < B; ++b) {
-        if (threadIdx.x == 0) carry = 0;
-        __syncthreads();
-        for (int base = 0; base < N; base += 1024) {
-            int i = base + threadIdx.x;
-            int v = i < N ? row_count[(size_t)b * N + i] : 0;
-            sbuf[threadIdx.x] = v;
-            __syncthreads();
-            for (int o = 1; o < 1024; o <<= 1) {
-                int add = threadIdx.x >= o ? sbuf[threadIdx.x - o] : 0;
-                __syncthreads();
-                sbuf[threadIdx.x] += add;
-                __syncthreads();
-            }
-            if (i < N) row_ptr[(size_t)b * (N + 1) + i] = carry + sbuf[threadIdx.x] - v;
-            __syncthreads();
-            if (threadIdx.x == 1023) carry += sbuf[1023];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            row_ptr[(size_t)b * (N + 1) + N] = carry;
-            n_edges[b] = carry;
-        }
-        __syncthreads();
-    }
-}
-
 // one warp per row: expand adjacency bits to receiver / sender lists (row-major = adj.nonzero() order).
 // Edges of batch element b occupy [b*cap, b*cap + n_edges[b]); the remaining slots get receiver = sender = -1.
+// The exclusive scan of the row counts is folded in: every CTA sums the counts of the rows before its first one (<= N ints from
+// L2, 128 threads) instead of a separate single-CTA scan launch; the warp of row r also publishes row_ptr[r] (row N: the total).
 __global__ void __launch_bounds__(128)
-gsd_gnn_expand_kernel(int B, int N, int words, int cap, const uint32_t *__restrict__ bits, const int32_t *__restrict__ row_ptr,
-                      int32_t *__restrict__ recv, int32_t *__restrict__ send) {
+gsd_gnn_expand_kernel(int B, int N, int words, int cap, const uint32_t *__restrict__ bits, const int32_t *__restrict__ row_count,
+                      int32_t *__restrict__ row_ptr, int32_t *__restrict__ n_edges, int32_t *__restrict__ recv,
+                      int32_t *__restrict__ send) {
+    gsd_pdl_wait();
+    __shared__ int s_part[4], s_cnt[4];
     const int b = blockIdx.y;
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * warps + warp;
+    const int r0 = blockIdx.x * warps, r = r0 + warp;
+    const int32_t *rc = row_count + (size_t)b * N;
+    int part = 0;
+    for (int i = threadIdx.x; i < min(r0, N); i += blockDim.x) part += rc[i];
+    part = __reduce_add_sync(0xffffffffu, part);
+    if (lane == 0) { s_part[warp] = part; s_cnt[warp] = r < N ? rc[r] : 0; }
+    __syncthreads();
+    int off = 0;
+    for (int w = 0; w < warps; ++w) off += s_part[w] + (w < warp ? s_cnt[w] : 0);
     if (r > N) return;
-    const int32_t *rp = row_ptr + (size_t)b * (N + 1);
+    int32_t *rp = row_ptr + (size_t)b * (N + 1);
+    if (lane == 0) rp[r] = off;
     if (r == N) { // padding
-        for (int e = rp[N] + lane; e < cap; e += 32) {
+        if (lane == 0) n_edges[b] = off;
+        for (int e = off + lane; e < cap; e += 32) {
             recv[(size_t)b * cap + e] = -1;
             send[(size_t)b * cap + e] = -1;
         }
         return;
     }
-    int off = rp[r];
     const uint32_t *row = bits + ((size_t)b * N + r) * words;
     for (int w = 0; w < words; ++w) {
         const uint32_t m = row[w];
@@ -269,17 +289,21 @@ extern "C" int gsd_gnn_build_edges(const GsdGnnEdges *g, void *stream) {
                   (size_t)adj_warps * a.words * 4 + (size_t)g->N;
     static bool attr_set = false;
     if (!attr_set) {
-        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_gnn_adjacency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            GNN_MAX_SMEM_NODES * 12 + 8 + 8 * GNN_CAND * 8 + 8 * GNN_MAX_SMEM_NODES * 4 +
-                                                8 * (GNN_MAX_SMEM_NODES / 32) * 4 + GNN_MAX_SMEM_NODES));
+        const int max_smem = GNN_MAX_SMEM_NODES * 12 + 8 + 8 * GNN_CAND * 8 + 8 * GNN_MAX_SMEM_NODES * 4 +
+                             8 * (GNN_MAX_SMEM_NODES / 32) * 4 + GNN_MAX_SMEM_NODES;
+        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_gnn_adjacency_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_gnn_adjacency_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_gnn_adjacency_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set = true;
     }
-    gsd_gnn_adjacency_kernel<<<grid, adj_warps * 32, smem, st>>>(a);
-    GSD_LAUNCH_CHECK();
-    gsd_gnn_scan_rows_kernel<<<1, 1024, 0, st>>>(g->B, g->N, a.row_count, g->row_ptr, g->n_edges);
+    const int k_eff = g->topk < g->N ? g->topk : g->N;
+    if (k_eff <= 8) gsd_gnn_adjacency_kernel<8><<<grid, adj_warps * 32, smem, st>>>(a);
+    else if (k_eff <= 16) gsd_gnn_adjacency_kernel<16><<<grid, adj_warps * 32, smem, st>>>(a);
+    else gsd_gnn_adjacency_kernel<0><<<grid, adj_warps * 32, smem, st>>>(a);
     GSD_LAUNCH_CHECK();
     dim3 grid2((g->N + 1 + warps - 1) / warps, g->B);
-    gsd_gnn_expand_kernel<<<grid2, warps * 32, 0, st>>>(g->B, g->N, a.words, g->capacity, a.bits, g->row_ptr, g->receivers, g->senders);
+    gsd_launch(gsd_gnn_expand_kernel, grid2, dim3(warps * 32), 0, st, g->B, g->N, a.words, g->capacity, (const uint32_t *)a.bits,
+               (const int32_t *)a.row_count, g->row_ptr, g->n_edges, g->receivers, g->senders);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
@@ -600,6 +624,105 @@ extern "C" int gsd_tf32_pack(int64_t rows, int32_t F, int32_t relu, int32_t weig
     if (blocks > 148 * 16) blocks = 148 * 16;
     gsd_tf32_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rows, F / 4, relu, weight_layout, (const float4 *)x, (const float4 *)add,
                                                                               (float4 *)full, (float4 *)out);
+    GSD_LAUNCH_CHECK();
+    return GSD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// rollout glue: the host-side tensor plumbing around one autoregressive step as two launches.
+//   gsd_gnn_rollout_pre   action row of the tool nodes <- eef_delta (dynamics_module.py:110-111); the particle encoder's input rows
+//                         [attrs | state over history | motion over history | action] (model.py:132-160 for state_dim = 3), and a
+//                         contiguous copy of the current positions for the edge builder (dynamics_module.py:127)
+//   gsd_gnn_rollout_post  pred_pos = state[-1] + clamp(pred_motion) (model.py:241-244), the tool node advanced by eef_delta and
+//                         the history shifted by one frame (dynamics_module.py:145-158), one thread per (batch element, node)
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gsd_gnn_rollout_pre_kernel(int B, int N, int n_obj, int n_his, int attr_dim, int state_dim, int motion, int has_action,
+                           const float *__restrict__ states, const float *__restrict__ attrs, float *__restrict__ action,
+                           const float *__restrict__ eef_delta, int delta_stride, float *__restrict__ p_inputs, float *__restrict__ cur) {
+    gsd_pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * N) return;
+    const int b = i / N, n = i - b * N;
+    const int sw = state_dim * n_his;                       // state_dim 3: xyz per frame; 1: z only (model.py:144-148); 0: none
+    const int width = attr_dim + sw + (motion ? 3 * (n_his - 1) : 0) + (has_action ? 3 : 0);
+    float *o = p_inputs + (size_t)i * width;
+    for (int k = 0; k < attr_dim; ++k) o[k] = attrs[(size_t)i * attr_dim + k];
+    o += attr_dim;
+    float prev[3] = {0.f, 0.f, 0.f};
+    for (int h = 0; h < n_his; ++h) {
+        const float *s = states + (((size_t)b * n_his + h) * N + n) * 3;
+        const float x = s[0], y = s[1], z = s[2];
+        if (state_dim == 3) { o[3 * h] = x; o[3 * h + 1] = y; o[3 * h + 2] = z; }
+        else if (state_dim == 1) o[h] = z;
+        if (motion && h > 0) {
+            float *m = o + sw + 3 * (h - 1);
+            m[0] = x - prev[0]; m[1] = y - prev[1]; m[2] = z - prev[2];
+        }
+        prev[0] = x; prev[1] = y; prev[2] = z;
+    }
+    cur[(size_t)i * 3] = prev[0]; cur[(size_t)i * 3 + 1] = prev[1]; cur[(size_t)i * 3 + 2] = prev[2];
+    if (has_action) {
+        float *a = action + (size_t)i * 3;
+        float ax = a[0], ay = a[1], az = a[2];
+        if (n >= n_obj) {
+            const float *d = eef_delta + (size_t)b * delta_stride;
+            ax = d[0]; ay = d[1]; az = d[2];
+            a[0] = ax; a[1] = ay; a[2] = az;
+        }
+        float *q = o + sw + (motion ? 3 * (n_his - 1) : 0);
+        q[0] = ax; q[1] = ay; q[2] = az;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gsd_gnn_rollout_post_kernel(int B, int N, int n_obj, int n_his, float *__restrict__ states, const float *__restrict__ motion,
+                            const float *__restrict__ eef_delta, int delta_stride, float clampv, float *__restrict__ pred) {
+    gsd_pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * N) return;
+    const int b = i / N, n = i - b * N;
+    float *last = states + (((size_t)b * n_his + (n_his - 1)) * N + n) * 3;
+    float nx = last[0], ny = last[1], nz = last[2];
+    if (n < n_obj) {
+        const float *m = motion + ((size_t)b * n_obj + n) * 3;
+        nx += fminf(fmaxf(m[0], -clampv), clampv); ny += fminf(fmaxf(m[1], -clampv), clampv); nz += fminf(fmaxf(m[2], -clampv), clampv);
+        float *p = pred + ((size_t)b * n_obj + n) * 3;
+        p[0] = nx; p[1] = ny; p[2] = nz;
+    } else {
+        const float *d = eef_delta + (size_t)b * delta_stride;
+        nx += d[0]; ny += d[1]; nz += d[2];
+    }
+    for (int h = 0; h + 1 < n_his; ++h) {      // this thread owns every history entry of its node: no cross-thread hazard
+        float *dst = states + (((size_t)b * n_his + h) * N + n) * 3;
+        const float *src = dst + (size_t)N * 3;
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    }
+    last[0] = nx; last[1] = ny; last[2] = nz;
+}
+
+extern "C" int gsd_gnn_rollout_pre(int32_t B, int32_t N, int32_t n_obj, int32_t n_his, int32_t attr_dim, int32_t state_dim, int32_t motion, int32_t has_action,
+                                   const float *states, const float *attrs, float *action, const float *eef_delta, int32_t delta_stride,
+                                   float *p_inputs, float *cur, void *stream) {
+    if (B <= 0 || N <= 0 || n_obj < 0 || n_obj > N || n_his <= 0 || attr_dim < 0 || !states || (attr_dim > 0 && !attrs) || !p_inputs || !cur ||
+        (has_action && (!action || !eef_delta)) || (state_dim != 0 && state_dim != 1 && state_dim != 3)) {
+        gsd_set_error("invalid arguments");
+        return GSD_ERR_INVALID;
+    }
+    gsd_launch(gsd_gnn_rollout_pre_kernel, dim3((B * N + 255) / 256), dim3(256), 0, (cudaStream_t)stream, B, N, n_obj, n_his, attr_dim, state_dim,
+               motion, has_action, states, attrs, action, eef_delta, delta_stride, p_inputs, cur);
+    GSD_LAUNCH_CHECK();
+    return GSD_OK;
+}
+
+extern "C" int gsd_gnn_rollout_post(int32_t B, int32_t N, int32_t n_obj, int32_t n_his, float *states, const float *motion,
+                                    const float *eef_delta, int32_t delta_stride, float clampv, float *pred, void *stream) {
+    if (B <= 0 || N <= 0 || n_obj < 0 || n_obj > N || n_his <= 0 || !states || (n_obj > 0 && (!motion || !pred)) || (n_obj < N && !eef_delta)) {
+        gsd_set_error("invalid arguments");
+        return GSD_ERR_INVALID;
+    }
+    gsd_launch(gsd_gnn_rollout_post_kernel, dim3((B * N + 255) / 256), dim3(256), 0, (cudaStream_t)stream, B, N, n_obj, n_his, states, motion,
+               eef_delta, delta_stride, clampv, pred);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }

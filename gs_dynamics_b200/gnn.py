@@ -14,6 +14,7 @@ epilogue, no library GEMM); training uses the same compensation through cuBLAS T
 plain fp32 SIMT GEMMs for bit-tight comparisons.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -683,8 +684,52 @@ class GnnRollout:
             raise ValueError("Gaussian skinning follows a single rollout (batch == 1)")
         self.gs_xyz, self.gs_quat = xyz.detach().clone().float().contiguous(), quat.detach().clone().float().contiguous()
 
+    def _fused_glue_ok(self):
+        """The two glue kernels cover the reference's rollout configurations (state_dim 0 / 1 / 3, motion_dim 0 / 3, action_dim
+        0 / 3, one tool node) on the tensor-core inference path; anything else takes the torch-op path below (same results)."""
+        m, cfg = self.model, self.model.model_config
+        return (m.matmul == "tc" and m.nf_effect % 64 == 0 and cfg['state_dim'] in (0, 1, 3) and m.motion_dim in (0, 3)
+                and cfg['action_dim'] in (0, 3) and cfg['rel_attr_dim'] == self.attrs.size(2) and cfg['rel_group_dim'] == 1
+                and cfg['rel_distance_dim'] == 3 and os.environ.get("GSD_ROLLOUT_GLUE", "1") != "0")
+
+    @torch.no_grad()
+    def _step_fused(self):
+        """One step with the tensor plumbing in two kernels (gsd_gnn_rollout_pre / _post) instead of ~14 elementwise / cat /
+        copy launches: pre -> edges -> relation inputs -> dense layers + aggregation -> post."""
+        m, cfg = self.model, self.model.model_config
+        B, N, nobj, n_his = self.B, self.nobj + 1, self.nobj, cfg['n_his']
+        dev = self.states.device
+        has_action = int(cfg['action_dim'] > 0)
+        width = self.attrs.size(2) + cfg['state_dim'] * n_his + (3 * (n_his - 1) if m.motion_dim > 0 else 0) + 3 * has_action
+        lib = _lib.lib()
+        if getattr(self, "_m8", None) is None:
+            self._m8, self._t8 = self.state_mask.to(torch.uint8).contiguous(), self.eef_mask.to(torch.uint8).contiguous()
+        with torch.cuda.device(dev):
+            p_inputs = torch.empty((B * N, width), device=dev)
+            cur = torch.empty((B, N, 3), device=dev)
+            pred = torch.empty((B, nobj, 3), device=dev)
+            _lib.check(lib.gsd_gnn_rollout_pre(B, N, nobj, n_his, self.attrs.size(2), int(cfg['state_dim']), int(m.motion_dim > 0), has_action,
+                                               self.states.data_ptr(), self.attrs.data_ptr(), self.action.data_ptr(),
+                                               self.eef_delta.data_ptr(), 0 if self.eef_delta.dim() == 1 else 3,
+                                               p_inputs.data_ptr(), cur.data_ptr(), _stream()), "gsd_gnn_rollout_pre")
+            edges = construct_edges_index(cur, self.adj_thresh, self._m8, self._t8, topk=self.topk, connect_all=self.connect_all, n_tool=1)
+            rel_inputs = edge_inputs(self.states, self.attrs, self.p_instance, edges)
+            motion = m._forward_tc(p_inputs, rel_inputs, edges, B, N, nobj)
+            _lib.check(lib.gsd_gnn_rollout_post(B, N, nobj, n_his, self.states.data_ptr(), motion.data_ptr(), self.eef_delta.data_ptr(),
+                                                0 if self.eef_delta.dim() == 1 else 3, float(m.motion_clamp), pred.data_ptr(), _stream()),
+                       "gsd_gnn_rollout_post")
+        if self.gs_xyz is not None:
+            from .skinning import interpolate_motions
+            bones = cur[0, :nobj]                                          # the positions before this step
+            x, q, _ = interpolate_motions(bones, pred[0] - bones, edges, self.gs_xyz, quat=self.gs_quat, return_weights=False)
+            self.gs_xyz.copy_(x)
+            self.gs_quat.copy_(q)
+        return pred
+
     @torch.no_grad()
     def _step_impl(self):
+        if self._fused_glue_ok():
+            return self._step_fused()
         # tool moves by eef_delta; history shift of the tool row; action row of the tool
         new_eef = self.states[:, -1, self.nobj] + self.eef_delta          # [B,3]
         self.action[:, self.nobj] = self.eef_delta

@@ -260,6 +260,19 @@ int gsd_gnn_edge_inputs(int32_t B, int32_t N, int32_t capacity, int32_t n_his, i
                         int32_t n_p, const float *state, const float *attrs, const float *p_instance,
                         const int32_t *receivers, const int32_t *senders, float *rel_inputs, void *stream);
 
+/* Rollout glue (replaces the host-side tensor plumbing of one autoregressive step: /root/reference/src/render/dynamics_module.py:
+ * 104-111,127,145-158 and the particle-input concatenations of /root/reference/src/gnn/model.py:132-160).
+ * pre: action rows of the tool nodes (n >= n_obj) <- eef_delta[b * delta_stride ..+3]; p_inputs [B*N, attr_dim + state_dim n_his +
+ *      (motion ? 3 (n_his-1) : 0) + (has_action ? 3 : 0)] = [attrs | state over history (state_dim 3: xyz, 1: z, 0: none) |
+ *      frame-to-frame motion | action];
+ *      cur [B,N,3] = states[:, -1].   states: [B, n_his, N, 3].
+ * post: pred [B,n_obj,3] = states[:, -1, :n_obj] + clamp(motion, +-clampv); tool nodes advance by eef_delta; history shifts by one. */
+int gsd_gnn_rollout_pre(int32_t B, int32_t N, int32_t n_obj, int32_t n_his, int32_t attr_dim, int32_t state_dim, int32_t motion, int32_t has_action,
+                        const float *states, const float *attrs, float *action, const float *eef_delta, int32_t delta_stride,
+                        float *p_inputs, float *cur, void *stream);
+int gsd_gnn_rollout_post(int32_t B, int32_t N, int32_t n_obj, int32_t n_his, float *states, const float *motion,
+                         const float *eef_delta, int32_t delta_stride, float clampv, float *pred, void *stream);
+
 /* agg[b*N+r, :] = sum over incoming edges e of ReLU(A[b*cap+e, :] + P[b*N+r, 0:F] + P[b*N+send(e), F:2F])
  * (relation propagator epilogue + Rr^T scatter-add of model.py:212-229). The last n_heavy rows of every element
  * (tool nodes) are split over several CTAs and summed in fixed order. F multiple of 128, <= 512. */

@@ -208,6 +208,32 @@ def test_rollout_graph_matches_eager():
     assert float((pa - pb).abs().max()) <= 1e-6 and float((ra.states - rb.states).abs().max()) <= 1e-6
 
 
+@pytest.mark.parametrize("batch,kind", [(1, "sloth"), (3, "sloth"), (1, "rope")])
+def test_rollout_glue_kernels_match_torch_op_path(batch, kind, monkeypatch):
+    """gsd_gnn_rollout_pre / _post (tool action row, particle-encoder inputs, clamp + add, history shift) against the same step
+    composed from torch ops exactly as model.py:132-160 / dynamics_module.py:104-158 write it: identical states after 4 steps
+    (the arithmetic is the same fp32 adds; the dense layers see bit-identical inputs)."""
+    from gs_dynamics_b200 import gnn
+    cfg = GO.sloth_cfg(128) if kind == "sloth" else GO.rope_cfg(128)    # state_dim 1 + motion 3 + action 3 / state_dim 0 + action 3
+    m = _model(cfg, 2)
+    gi = GO.make_graph_inputs(300, 11, kind)
+    p0, eef = gi["state"][0, :, :300].cuda(), gi["state"][0, :, 300:].cuda()
+    d = torch.tensor([0.004, -0.002, 0.001], device="cuda")
+    if batch > 1:
+        d = d[None] * torch.arange(1, batch + 1, device="cuda")[:, None]
+    monkeypatch.setenv("GSD_ROLLOUT_GLUE", "0")
+    ra = gnn.GnnRollout(m, p0, eef, 0.075, 6, True, use_graph=False, batch=batch)
+    assert not ra._fused_glue_ok()
+    pa = [ra.step(d).clone() for _ in range(4)]
+    monkeypatch.setenv("GSD_ROLLOUT_GLUE", "1")
+    rb = gnn.GnnRollout(m, p0, eef, 0.075, 6, True, use_graph=False, batch=batch)
+    assert rb._fused_glue_ok()
+    pb = [rb.step(d).clone() for _ in range(4)]
+    for a, b in zip(pa, pb):
+        assert torch.equal(a, b)
+    assert torch.equal(ra.states, rb.states) and torch.equal(ra.action, rb.action)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # GNN training row (SURVEY.md §8f row 3): backward kernels, losses, the train.py unroll
 # Tolerances: gradients of a 2-3 step unroll through three propagation steps, fp32 with different summation orders:
