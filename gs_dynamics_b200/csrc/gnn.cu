@@ -38,12 +38,9 @@ struct EdgeArgs {
     int32_t *row_count;      // [B*N]
 };
 
-// KL > 0: every lane keeps the KL smallest (distance, column) keys of ITS columns in registers while the distances are computed;
-// the row's k <= KL nearest are then k rounds of a warp arg-min over the lanes' list heads (two redux.sync each).  KL = 0: the
-// general path (bisection to a small candidate set + ranking, or k rounds of arg-min over the whole row).
-template <int KL>
+// ---- general adjacency kernel (any top-k) ----
 __global__ void __launch_bounds__(256)
-gsd_gnn_adjacency_kernel(EdgeArgs a) {
+gsd_gnn_adjacency_general_kernel(EdgeArgs a) {
     // shared: positions [N*3] | per warp: candidates [GNN_CAND] u64 | per warp: row distances [N] | per warp: selected bits [words]
     // | node flags [N] (bit 0 valid, bit 1 tool)
     extern __shared__ float spos[];
@@ -73,30 +70,12 @@ gsd_gnn_adjacency_kernel(EdgeArgs a) {
 
     // ---- distances of this row, cached per warp (masked pairs -> 1e10 like the reference's dis[mask] = 1e10)
     int cnt = 0; // object columns within the radius
-    constexpr int KLR = KL > 0 ? KL : 1;
-    unsigned long long best[KLR];   // ascending; key = distance bits << 32 | column (d >= 0: bit order = value order, ties -> lowest column)
-#pragma unroll
-    for (int j = 0; j < KLR; ++j) best[j] = ~0ull;
     for (int c = lane; c < a.N; c += 32) {
         float d = dist2_rn(rx, ry, rz, spos[3 * c], spos[3 * c + 1], spos[3 * c + 2]);
         const int fc = sflag[c];
         if (!(r_valid && (fc & 1)) || (r_tool && (fc & 2))) d = 1e10f;
         sd[c] = d;
-        const bool in = c < n_obj && __fsub_rn(d, thr) < 0.f;
-        cnt += in ? 1 : 0;
-        if (KL > 0 && in && r < n_obj) {
-            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)c;
-            if (key < best[KLR - 1]) {
-                best[KLR - 1] = key;
-#pragma unroll
-                for (int j = KLR - 1; j >= 1; --j) {
-                    const unsigned long long lo = best[j - 1], hi = best[j];
-                    const bool sw = hi < lo;
-                    best[j - 1] = sw ? hi : lo;
-                    best[j] = sw ? lo : hi;
-                }
-            }
-        }
+        cnt += (c < n_obj && __fsub_rn(d, thr) < 0.f) ? 1 : 0;
     }
     for (int w = lane; w < a.words; w += 32) selbits[w] = 0u;
     cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -108,23 +87,7 @@ gsd_gnn_adjacency_kernel(EdgeArgs a) {
     // bisection until a small candidate set (>= k columns) lies inside it, compact that set into shared memory, rank the
     // candidates against each other (ties -> lowest index) and set the bits of those ranked below k.  If bisection cannot
     // separate (hundreds of equal distances, or k larger than the buffer) fall back to k rounds of warp arg-min.
-    if (KL > 0 && r < n_obj && cnt > 0) {
-        const int k_eff = min(a.topk, a.N);   // the launcher guarantees k_eff <= KL
-        for (int it = 0; it < k_eff; ++it) {
-            const unsigned hd = (unsigned)(best[0] >> 32), hc = (unsigned)best[0];
-            const unsigned md = __reduce_min_sync(0xffffffffu, hd);
-            if (md == 0xffffffffu) break;                                   // no within-radius column left
-            const unsigned mc = __reduce_min_sync(0xffffffffu, hd == md ? hc : 0xffffffffu);
-            if (hd == md && hc == mc) {                                     // exactly one lane owns column mc
-                atomicOr(&selbits[mc >> 5], 1u << (mc & 31));
-#pragma unroll
-                for (int j = 0; j < KLR - 1; ++j) best[j] = best[j + 1];
-                best[KLR - 1] = ~0ull;
-            }
-        }
-        __syncwarp();
-    }
-    if (KL == 0 && r < n_obj && cnt > 0) {
+    if (r < n_obj && cnt > 0) {
         const int k_eff = min(a.topk, a.N);
         const int want = min(GNN_CAND, max(64, 2 * k_eff)); // candidate-set size the bisection aims below
         float t = thr;
@@ -212,6 +175,210 @@ gsd_gnn_adjacency_kernel(EdgeArgs a) {
     } // rows
 }
 
+// ---- fused edge builder for top-k <= KL (every configuration of the reference: topk 5 / 6 / 10): ONE launch -----------------------
+// A CTA owns a contiguous block of receiver rows; one warp per row, ONE pass over the columns: lane l visits columns c = 32 i + l,
+// so the warp ballot of "within the radius" IS bit-word i of the row.  The (distance, column) keys of the within-radius object
+// columns are compacted into a small per-warp buffer (ballot prefix); when it fills, and at the end of the row, every lane inserts
+// ITS share of the buffer into a sorted register list of the KL smallest keys it has seen (all lanes busy; inserting inside the
+// column loop ran the ~50-instruction insertion whenever ANY lane had a hit, i.e. in ~90 % of the iterations).  The row's k nearest
+// are then k rounds of a warp arg-min over the lanes' list heads (two redux.sync each); the final bit-words are word-wise logic on
+// the radius words, the selected words and the per-graph valid / tool words and STAY IN SHARED MEMORY.  The CTA publishes its
+// edge count, sums the counts of the CTAs before it (decoupled look-back: all CTAs publish at about the same time, each reads its
+// predecessors' words in parallel), and expands its rows' bit-words straight into the receiver / sender lists: no N x N bit matrix
+// in HBM, no scan launch, no expand launch.
+#define GNN_KEYBUF 128   // keys per warp between two flushes
+__device__ __forceinline__ int gnn_ld_acquire(const int32_t *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void gnn_st_release(int32_t *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+template <int KL>
+__global__ void __launch_bounds__(256)
+gsd_gnn_edges_fused_kernel(EdgeArgs a, int rows_per_cta, int cap, int32_t *__restrict__ row_ptr, int32_t *__restrict__ n_edges,
+                           int32_t *__restrict__ recv, int32_t *__restrict__ send, int32_t *agg /* [B][gridDim.x], zeroed */) {
+    // shared: per warp key buffer | positions [3 * 32 words] | valid words | tool words | per warp selected words |
+    //         row words [rows_per_cta][words] | row counts, row offsets [rows_per_cta] | flags [32 words]
+    extern __shared__ unsigned long long skeys[];
+    __shared__ int s_red[8], s_prefix;
+    gsd_pdl_wait();
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int npad = a.words * 32;
+    float *spos = reinterpret_cast<float *>(skeys + (size_t)warps * GNN_KEYBUF);
+    uint32_t *validw = reinterpret_cast<uint32_t *>(spos + 3 * npad);
+    uint32_t *toolw = validw + a.words;
+    uint32_t *selw = toolw + a.words + (size_t)warp * a.words;
+    uint32_t *roww = toolw + a.words + (size_t)warps * a.words;
+    int *rcount = reinterpret_cast<int *>(roww + (size_t)rows_per_cta * a.words);
+    int *roff = rcount + rows_per_cta;
+    uint8_t *sflag = reinterpret_cast<uint8_t *>(roff + rows_per_cta);
+    unsigned long long *keys = skeys + (size_t)warp * GNN_KEYBUF;
+    const int b = blockIdx.y;
+    const float *st = a.states + (size_t)b * a.N * 3;
+    const uint8_t *mk = a.mask + (size_t)b * a.N, *tm = a.tool_mask + (size_t)b * a.N;
+    // staging: positions by 4-byte cp.async (all in flight at once; padding columns far away), flags by plain loads, then the
+    // valid / tool bit-words
+    for (int i = threadIdx.x; i < 3 * npad; i += blockDim.x) {
+        if (i < a.N * 3) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(spos + i)), "l"(st + i) : "memory");
+        else spos[i] = 1e18f;
+    }
+#pragma unroll 8
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) sflag[i] = i < a.N ? ((mk[i] ? 1 : 0) | (tm[i] ? 2 : 0)) : 0;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+        const int f = sflag[i];
+        const unsigned v = __ballot_sync(0xffffffffu, f & 1), t = __ballot_sync(0xffffffffu, f & 2);
+        if (lane == 0) { validw[i >> 5] = v; toolw[i >> 5] = t; }
+    }
+    __syncthreads();
+    const int n_obj = a.N - a.n_tool;
+    const float thr = a.thresh ? __fmul_rn(a.thresh[b], a.thresh[b]) : a.thresh_sq_scalar;
+    const int k_eff = min(a.topk, a.N);   // the launcher guarantees k_eff <= KL
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int row0 = blockIdx.x * rows_per_cta, row1 = min(row0 + rows_per_cta, a.N);
+    for (int r = row0 + warp; r < row1; r += warps) {
+        const float rx = spos[3 * r], ry = spos[3 * r + 1], rz = spos[3 * r + 2];
+        const bool r_valid = (validw[r >> 5] >> (r & 31)) & 1u, r_tool = (toolw[r >> 5] >> (r & 31)) & 1u, r_obj = r < n_obj;
+        uint32_t *rw = roww + (size_t)(r - row0) * a.words;
+        __syncwarp();   // the previous row's readers of selw / keys are done
+        for (int w = lane; w < a.words; w += 32) selw[w] = 0u;
+        unsigned long long best[KL];   // ascending; key = distance bits << 32 | column (d >= 0: bit order = value order, ties -> lowest column)
+#pragma unroll
+        for (int j = 0; j < KL; ++j) best[j] = ~0ull;
+        int n_keys = 0;
+        auto flush = [&]() {
+            __syncwarp();
+            for (int q = lane; q < n_keys; q += 32) {
+                const unsigned long long key = keys[q];
+                if (key < best[KL - 1]) {
+                    best[KL - 1] = key;
+#pragma unroll
+                    for (int j = KL - 1; j >= 1; --j) {
+                        const unsigned long long lo = best[j - 1], hi = best[j];
+                        const bool sw = hi < lo;
+                        best[j - 1] = sw ? hi : lo;
+                        best[j] = sw ? lo : hi;
+                    }
+                }
+            }
+            n_keys = 0;
+            __syncwarp();
+        };
+        for (int w = 0; w < a.words; ++w) {
+            const int c = w * 32 + lane;
+            // masked pairs: invalid row or column, tool-tool  (dis[mask] = 1e10, dataset.py:106-111)
+            const unsigned bad = r_valid ? (~validw[w] | (r_tool ? toolw[w] : 0u)) : 0xffffffffu;
+            float d = dist2_rn(rx, ry, rz, spos[3 * c], spos[3 * c + 1], spos[3 * c + 2]);
+            if ((bad >> lane) & 1u) d = 1e10f;
+            const bool in = __fsub_rn(d, thr) < 0.f;
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (lane == 0) rw[w] = m;
+            if (r_obj && m != 0u && w * 32 < n_obj) {
+                const bool cand = in && c < n_obj;
+                const unsigned mc = __ballot_sync(0xffffffffu, cand);
+                if (cand) keys[n_keys + __popc(mc & lt_mask)] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)c;
+                n_keys += __popc(mc);
+                if (n_keys > GNN_KEYBUF - 32) flush();
+            }
+        }
+        if (r_obj) {
+            flush();
+            for (int it = 0; it < k_eff; ++it) {
+                const unsigned hd = (unsigned)(best[0] >> 32), hc = (unsigned)best[0];
+                const unsigned md = __reduce_min_sync(0xffffffffu, hd);
+                if (md == 0xffffffffu) break;                                   // no within-radius object column left
+                const unsigned mc = __reduce_min_sync(0xffffffffu, hd == md ? hc : 0xffffffffu);
+                if (hd == md && hc == mc) {                                     // exactly one lane owns column mc
+                    atomicOr(&selw[mc >> 5], 1u << (mc & 31));
+#pragma unroll
+                    for (int j = 0; j < KL - 1; ++j) best[j] = best[j + 1];
+                    best[KL - 1] = ~0ull;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- adjacency bit-words (same order of rules as the per-bit form of the general kernel)
+        int count = 0;
+        for (int w = lane; w < a.words; w += 32) {
+            const int c0 = w * 32;
+            const unsigned objm = c0 + 32 <= n_obj ? 0xffffffffu : (c0 >= n_obj ? 0u : ((1u << (n_obj - c0)) - 1u));
+            unsigned on = rw[w];
+            if (r_obj) on = (on & ~objm) | (on & objm & selw[w]);
+            if (a.connect_all) {
+                if (r_tool) on |= validw[w];
+                if (r_valid) on |= toolw[w];
+                if (r_tool) on &= ~toolw[w];
+            }
+            rw[w] = on;
+            count += __popc(on);
+        }
+        count = __reduce_add_sync(0xffffffffu, count);
+        if (lane == 0) rcount[r - row0] = count;
+    }
+    __syncthreads();
+    // ---- this CTA's edge count -> published; exclusive prefix over the CTAs before it (look-back) and over its own rows
+    const int nrows = max(row1 - row0, 0);
+    int part = 0;
+    for (int i = threadIdx.x; i < nrows; i += blockDim.x) part += rcount[i];
+    part = __reduce_add_sync(0xffffffffu, part);
+    if (lane == 0) s_red[warp] = part;
+    __syncthreads();
+    int total = 0;
+    for (int w = 0; w < warps; ++w) total += s_red[w];
+    int32_t *ag = agg + (size_t)b * gridDim.x;
+    if (threadIdx.x == 0) gnn_st_release(ag + blockIdx.x, (total << 1) | 1);
+    int before = 0;
+    for (int j = threadIdx.x; j < (int)blockIdx.x; j += blockDim.x) {
+        int v;
+        while (((v = gnn_ld_acquire(ag + j)) & 1) == 0) __nanosleep(20);
+        before += v >> 1;
+    }
+    before = __reduce_add_sync(0xffffffffu, before);
+    __syncthreads();                       // s_red readers above are done
+    if (lane == 0) s_red[warp] = before;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int off = 0;
+        for (int w = 0; w < warps; ++w) off += s_red[w];
+        s_prefix = off;
+        for (int i = 0; i < nrows; ++i) { roff[i] = off; off += rcount[i]; }
+    }
+    __syncthreads();
+    int32_t *rp = row_ptr + (size_t)b * (a.N + 1);
+    int32_t *rv = recv + (size_t)b * cap, *sd = send + (size_t)b * cap;
+    for (int r = row0 + warp; r < row1; r += warps) {
+        const uint32_t *rw = roww + (size_t)(r - row0) * a.words;
+        int off = roff[r - row0];
+        if (lane == 0) rp[r] = off;
+        for (int w0 = 0; w0 < a.words; w0 += 32) {
+            const int w = w0 + lane;
+            uint32_t m = w < a.words ? rw[w] : 0u;
+            const int n = __popc(m);
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            int e = off + incl - n;
+            while (m) {                     // ascending columns inside the word = adj.nonzero() order
+                const int bit = __ffs(m) - 1;
+                m &= m - 1;
+                if (e < cap) { rv[e] = r; sd[e] = w * 32 + bit; }
+                ++e;
+            }
+            off += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1) {     // totals and the -1 padding of the unused slots
+        const int all = s_prefix + total;
+        if (threadIdx.x == 0) { rp[a.N] = all; n_edges[b] = all; }
+        for (int e = all + threadIdx.x; e < cap; e += blockDim.x) { rv[e] = -1; sd[e] = -1; }
+    }
+}
+
 // one warp per row: expand adjacency bits to receiver / sender lists (row-major = adj.nonzero() order).
 // Edges of batch element b occupy [b*cap, b*cap + n_edges[b]); the remaining slots get receiver = sender = -1.
 // The exclusive scan of the row counts is folded in: every CTA sums the counts of the rows before its first one (<= N ints from
@@ -227,7 +394,9 @@ gsd_gnn_expand_kernel(int B, int N, int words, int cap, const uint32_t *__restri
     const int r0 = blockIdx.x * warps, r = r0 + warp;
     const int32_t *rc = row_count + (size_t)b * N;
     int part = 0;
-    for (int i = threadIdx.x; i < min(r0, N); i += blockDim.x) part += rc[i];
+    const int lim = min(r0, N);
+#pragma unroll 8
+    for (int i = threadIdx.x; i < lim; i += blockDim.x) part += rc[i];
     part = __reduce_add_sync(0xffffffffu, part);
     if (lane == 0) { s_part[warp] = part; s_cnt[warp] = r < N ? rc[r] : 0; }
     __syncthreads();
@@ -244,17 +413,25 @@ gsd_gnn_expand_kernel(int B, int N, int words, int cap, const uint32_t *__restri
         }
         return;
     }
+    // the row's bit-words: lane l holds words l, l + 32, ... (N <= 4096: at most 4), broadcast one at a time by shuffle
     const uint32_t *row = bits + ((size_t)b * N + r) * words;
-    for (int w = 0; w < words; ++w) {
-        const uint32_t m = row[w];
-        if ((m >> lane) & 1u) {
-            const int e = off + __popc(m & ((1u << lane) - 1u));
-            if (e < cap) {
-                recv[(size_t)b * cap + e] = r;
-                send[(size_t)b * cap + e] = w * 32 + lane;
+    uint32_t wreg[GNN_MAX_SMEM_NODES / 1024];
+#pragma unroll
+    for (int j = 0; j < GNN_MAX_SMEM_NODES / 1024; ++j) wreg[j] = j * 32 + lane < words ? row[j * 32 + lane] : 0u;
+#pragma unroll
+    for (int j = 0; j < GNN_MAX_SMEM_NODES / 1024; ++j) {
+        if (j * 32 >= words) break;
+        for (int t = 0; t < 32 && j * 32 + t < words; ++t) {
+            const uint32_t m = __shfl_sync(0xffffffffu, wreg[j], t);
+            if ((m >> lane) & 1u) {
+                const int e = off + __popc(m & ((1u << lane) - 1u));
+                if (e < cap) {
+                    recv[(size_t)b * cap + e] = r;
+                    send[(size_t)b * cap + e] = (j * 32 + t) * 32 + lane;
+                }
             }
+            off += __popc(m);
         }
-        off += __popc(m);
     }
 }
 
@@ -287,19 +464,45 @@ extern "C" int gsd_gnn_build_edges(const GsdGnnEdges *g, void *stream) {
     dim3 grid(ctas, g->B);
     size_t smem = (size_t)((g->N * 3 + 1) & ~1) * 4 + (size_t)adj_warps * GNN_CAND * 8 + (size_t)adj_warps * g->N * 4 +
                   (size_t)adj_warps * a.words * 4 + (size_t)g->N;
-    static bool attr_set = false;
-    if (!attr_set) {
-        const int max_smem = GNN_MAX_SMEM_NODES * 12 + 8 + 8 * GNN_CAND * 8 + 8 * GNN_MAX_SMEM_NODES * 4 +
-                             8 * (GNN_MAX_SMEM_NODES / 32) * 4 + GNN_MAX_SMEM_NODES;
-        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_gnn_adjacency_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_gnn_adjacency_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_gnn_adjacency_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attr_set = true;
-    }
     const int k_eff = g->topk < g->N ? g->topk : g->N;
-    if (k_eff <= 8) gsd_gnn_adjacency_kernel<8><<<grid, adj_warps * 32, smem, st>>>(a);
-    else if (k_eff <= 16) gsd_gnn_adjacency_kernel<16><<<grid, adj_warps * 32, smem, st>>>(a);
-    else gsd_gnn_adjacency_kernel<0><<<grid, adj_warps * 32, smem, st>>>(a);
+    const int rows_per_cta = (g->N + ctas - 1) / ctas;
+    if (k_eff <= 16 && (size_t)rows_per_cta * a.words * 4 <= 32 * 1024 && !getenv("GSD_GNN_ADJ_GENERAL")) {
+        // fused builder: key buffers + 13 bytes per (padded) node + (2 + 1 per warp + 1 per row) words per 32 nodes (39 KB at N = 2001)
+        const size_t npad = (size_t)a.words * 32;
+        const size_t smem_fast = (size_t)adj_warps * GNN_KEYBUF * 8 + npad * 12 + (size_t)(2 + adj_warps + rows_per_cta) * a.words * 4 +
+                                 (size_t)rows_per_cta * 8 + npad;
+        static bool attr_fast = false;
+        if (!attr_fast) {
+            const int max_fast = 8 * GNN_KEYBUF * 8 + GNN_MAX_SMEM_NODES * 13 + (2 + 8) * (GNN_MAX_SMEM_NODES / 32) * 4 + 32 * 1024 + 8 * 1024;
+            GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_gnn_edges_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_fast));
+            GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_gnn_edges_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_fast));
+            attr_fast = true;
+        }
+        if (smem_fast > (size_t)(8 * GNN_KEYBUF * 8 + GNN_MAX_SMEM_NODES * 13 + (2 + 8) * (GNN_MAX_SMEM_NODES / 32) * 4 + 32 * 1024 + 8 * 1024)) {
+            gsd_set_error("edge builder: shared-memory budget exceeded");
+            return GSD_ERR_UNSUPPORTED;
+        }
+        int32_t *agg = a.row_count;       // per-CTA edge counts + ready flag (the row-count array is not needed on this path)
+        GSD_CUDA_CHECK(cudaMemsetAsync(agg, 0, (size_t)g->B * ctas * 4, st));
+        if (k_eff <= 8)
+            gsd_launch(gsd_gnn_edges_fused_kernel<8>, grid, dim3(adj_warps * 32), smem_fast, st, a, rows_per_cta, g->capacity, g->row_ptr, g->n_edges,
+                       g->receivers, g->senders, agg);
+        else
+            gsd_launch(gsd_gnn_edges_fused_kernel<16>, grid, dim3(adj_warps * 32), smem_fast, st, a, rows_per_cta, g->capacity, g->row_ptr, g->n_edges,
+                       g->receivers, g->senders, agg);
+        GSD_LAUNCH_CHECK();
+        return GSD_OK;
+    }
+    {
+        static bool attr_set = false;
+        if (!attr_set) {
+            GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_gnn_adjacency_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                GNN_MAX_SMEM_NODES * 12 + 8 + 8 * GNN_CAND * 8 + 8 * GNN_MAX_SMEM_NODES * 4 +
+                                                    8 * (GNN_MAX_SMEM_NODES / 32) * 4 + GNN_MAX_SMEM_NODES));
+            attr_set = true;
+        }
+        gsd_gnn_adjacency_general_kernel<<<grid, adj_warps * 32, smem, st>>>(a);
+    }
     GSD_LAUNCH_CHECK();
     dim3 grid2((g->N + 1 + warps - 1) / warps, g->B);
     gsd_launch(gsd_gnn_expand_kernel, grid2, dim3(warps * 32), 0, st, g->B, g->N, a.words, g->capacity, (const uint32_t *)a.bits,

@@ -51,9 +51,16 @@ def test_golden_fixture_edges_and_forward(tag):
 
 
 @pytest.mark.parametrize("kind,n_obj,topk,adj,conn", [("sloth", 2000, 8, 0.075, True), ("rope", 500, 8, 0.08, False),
-                                                       ("sloth", 37, 37, 0.2, True), ("rope", 1, 1, 0.08, True)])
-def test_edges_vs_oracle_full_size(kind, n_obj, topk, adj, conn):
+                                                       ("sloth", 37, 37, 0.2, True), ("rope", 1, 1, 0.08, True),
+                                                       ("sloth", 2000, 6, 0.075, True), ("sloth", 1000, 12, 0.09, False),
+                                                       ("sloth", 700, 20, 0.12, True)])
+@pytest.mark.parametrize("general", [False, True])
+def test_edges_vs_oracle_full_size(kind, n_obj, topk, adj, conn, general, monkeypatch):
+    """Both adjacency kernels: the single-pass register top-k kernel (topk <= 8 and <= 16 instantiations) and the general one
+    (any topk; forced with GSD_GNN_ADJ_GENERAL) — bit-exact edge lists against the oracle."""
     from gs_dynamics_b200 import gnn
+    if general:
+        monkeypatch.setenv("GSD_GNN_ADJ_GENERAL", "1")
     gi = GO.make_graph_inputs(n_obj, 5, kind)
     recv, send = GO.construct_edges(gi["state"][0, -1], adj, gi["state_mask"], gi["eef_mask"], topk, conn)
     e = gnn.construct_edges_index(gi["state"][0, -1].cuda(), adj, gi["state_mask"].cuda(), gi["eef_mask"].cuda(), topk=topk, connect_all=conn)
@@ -64,9 +71,13 @@ def test_edges_vs_oracle_full_size(kind, n_obj, topk, adj, conn):
     assert rp[-1] == E and np.array_equal(np.diff(rp), np.bincount(recv.numpy(), minlength=n_obj + 1))
 
 
-def test_edges_dense_cloud_topk_is_the_binding_constraint():
-    """every particle within the radius of every other (bisection path of the adjacency kernel): bit-exact edge list."""
+@pytest.mark.parametrize("general", [False, True])
+def test_edges_dense_cloud_topk_is_the_binding_constraint(general, monkeypatch):
+    """every particle within the radius of every other (every column a top-k candidate; bisection path of the general
+    kernel): bit-exact edge list."""
     from gs_dynamics_b200 import gnn
+    if general:
+        monkeypatch.setenv("GSD_GNN_ADJ_GENERAL", "1")
     gi = GO.make_graph_inputs(1500, 7, "sloth")
     recv, send = GO.construct_edges(gi["state"][0, -1], 5.0, gi["state_mask"], gi["eef_mask"], 8, True)
     e = gnn.construct_edges_index(gi["state"][0, -1].cuda(), 5.0, gi["state_mask"].cuda(), gi["eef_mask"].cuda(), topk=8, connect_all=True)
@@ -75,10 +86,13 @@ def test_edges_dense_cloud_topk_is_the_binding_constraint():
     assert np.array_equal(e.receivers[0, :E].cpu().numpy(), recv.numpy()) and np.array_equal(e.senders[0, :E].cpu().numpy(), send.numpy())
 
 
-def test_edges_many_equal_distances_fall_back_to_selection():
+@pytest.mark.parametrize("general", [False, True])
+def test_edges_many_equal_distances_fall_back_to_selection(general, monkeypatch):
     """600 coincident particles: all distances tie (the reference's torch.topk order is unspecified there), so only the
     degree is checked: every object row keeps exactly topk neighbours."""
     from gs_dynamics_b200 import gnn
+    if general:
+        monkeypatch.setenv("GSD_GNN_ADJ_GENERAL", "1")
     N = 601
     states = torch.zeros(N, 3)
     states[-1] = 10.0
@@ -92,8 +106,11 @@ def test_edges_many_equal_distances_fall_back_to_selection():
     assert E == 600 * 6 and int(e.senders[0, :E].max()) < 600
 
 
-def test_edges_batch_masks_and_per_element_radius():
+@pytest.mark.parametrize("general", [False, True])
+def test_edges_batch_masks_and_per_element_radius(general, monkeypatch):
     from gs_dynamics_b200 import gnn
+    if general:
+        monkeypatch.setenv("GSD_GNN_ADJ_GENERAL", "1")
     g = torch.Generator().manual_seed(3)
     B, N = 3, 64
     states = torch.rand(B, N, 3, generator=g) * 0.3
