@@ -88,6 +88,21 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float *v) {
         "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
         : "memory");
 }
+// one lane of a converged warp (the tcgen05.mma / commit issuer); everything around it stays warp-uniform so that descriptors
+// and tensor-memory addresses live in uniform registers — inside an `if (lane == 0)` region the compiler has to move every
+// operand of every MMA through an ELECT / R2UR.BROADCAST retry loop, which was measured at ~80-110 cycles per tcgen05.mma issue,
+// more than the 64 cycles a 128x128x8 TF32 product executes
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -132,11 +147,14 @@ struct GemmCfg {
     static_assert(ACC_BUFS >= 1 && STAGES * STAGE_BYTES <= 200 * 1024, "tile configuration");
     static_assert(A_COLS0 + STAGES * 2 * BLOCK_K <= 512, "tensor memory budget");
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    // the same with N = 2 * BLOCK_N: one instruction against the stacked [w_hi ; w_lo] tiles (adjacent in a stage)
+    static constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BLOCK_N) >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 };
 
 // warp 0: TMA producer; warp 1: TMEM owner + MMA issuer; warps 2-5 and 6-9: two converter groups (alternate k-blocks);
-// warps 10-13: epilogue (a warp may only read the TMEM lane quarter warp_id % 4: 10..13 -> 2, 3, 0, 1)
-constexpr int GEMM_THREADS = 448;
+// warps 10-17: epilogue (a warp may only read the TMEM lane quarter warp_id % 4; warps 10-13 take the left half of the
+// tile's columns, 14-17 the right half — the accumulators are not double-buffered at 128-wide tiles, so the epilogue is exposed)
+constexpr int GEMM_THREADS = 576, PAIR_THREADS = 448, EPI_WARPS = 8;
 // optional pipeline trace of CTA 0 (GSD_GEMM_DBG=1): globaltimer stamps per role and k-block, printed by the launcher
 __device__ long long g_gemm_trace[6 * 64];
 __device__ int g_gemm_trace_on;
@@ -147,7 +165,9 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gsd_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_wh,
                        const __grid_constant__ CUtensorMap tm_wl, int M, int N, int K, const float *__restrict__ bias,
-                       const float *__restrict__ res1, const float *__restrict__ res2, int relu, float *__restrict__ out, long long ldo) {
+                       const float *__restrict__ res1, const float *__restrict__ res2, int relu, float *__restrict__ out, long long ldo, int dbg) {
+    // dbg (GSD_GEMM_MODE, timing experiments only — results are wrong): 1 converters skip the TMEM stores, 2 converters skip all
+    // work, 4 only the big product, 8 one accumulator, 32 W tiles loaded for the first ring round only, 64 same for A
     using Cfg = GemmCfg<BLOCK_N>;
     constexpr int STAGES = Cfg::STAGES, ACC_BUFS = Cfg::ACC_BUFS;
     extern __shared__ uint8_t smem_raw[];
@@ -168,7 +188,7 @@ gsd_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&full_cvt[s], 4); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
         mbar_fence_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_wh) : "memory");
@@ -181,7 +201,10 @@ gsd_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tmem_base_slot;
+    // the allocation is the whole tensor memory (512 columns), so its base is column 0 of lane 0: a compile-time constant keeps
+    // every tensor-memory address in uniform registers
+    if (tmem_base_slot != 0u) __trap();
+    constexpr uint32_t tmem_base = 0u;
     if (threadIdx.x == 0) GEMM_TRACE(5, 1);
 
     if (warp == 0) {
@@ -194,17 +217,24 @@ gsd_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     GEMM_TRACE(0, kb + (tile != (int)blockIdx.x) * 16);
-                    mbar_expect_tx(&full_raw[stage], A_TILE_BYTES + 2 * Cfg::B_TILE_BYTES);
-                    tma_load_2d(sA(stage), &tm_a, kb * BLOCK_K, m0, &full_raw[stage]);      // rows beyond M arrive as zeros
-                    tma_load_2d(sWh(stage), &tm_wh, kb * BLOCK_K, n0, &full_raw[stage]);
-                    tma_load_2d(sWl(stage), &tm_wl, kb * BLOCK_K, n0, &full_raw[stage]);
+                    const bool first_round = tile == (int)blockIdx.x && kb < STAGES;
+                    const bool ld_w = !(dbg & 32) || first_round, ld_a = !(dbg & 64) || first_round;
+                    if (!ld_w && !ld_a) { mbar_arrive_cta(&full_raw[stage]); }
+                    else {
+                        mbar_expect_tx(&full_raw[stage], (ld_a ? A_TILE_BYTES : 0) + (ld_w ? 2 * Cfg::B_TILE_BYTES : 0));
+                        if (ld_a) tma_load_2d(sA(stage), &tm_a, kb * BLOCK_K, m0, &full_raw[stage]);      // rows beyond M arrive as zeros
+                        if (ld_w) {
+                            tma_load_2d(sWh(stage), &tm_wh, kb * BLOCK_K, n0, &full_raw[stage]);
+                            tma_load_2d(sWl(stage), &tm_wl, kb * BLOCK_K, n0, &full_raw[stage]);
+                        }
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp runs the loop (uniform control flow), one elected lane issues =====
+        {
             int stage = 0;
             uint32_t phase = 0;
             int ti = 0;
@@ -214,27 +244,39 @@ gsd_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                 // the large sum (d_big).  With ONE accumulator the result carried a systematic bias (the tensor core's fp32
                 // accumulation truncates; 192 accumulating MMAs per output instead of 64): 1.4e-6 instead of 5e-7 of the |a||w|
                 // bound, and 1.2e-4 instead of 5e-5 on the model's predicted motion — outside the stated parity tolerance.
-                const uint32_t d_small = tmem_base + (uint32_t)(ab * 2 * BLOCK_N), d_big = d_small + BLOCK_N;
+                // Layout [big | small]: w_hi and w_lo tiles are adjacent in a stage, so ONE N = 2 * BLOCK_N instruction computes
+                // a_hi . [w_hi ; w_lo]^T into both (2 instead of 3 instructions per k-step; an instruction costs ~100 cycles up to N = 128).
+                const uint32_t d_big = tmem_base + (uint32_t)(ab * 2 * BLOCK_N), d_small = d_big + BLOCK_N;
                 mbar_wait(&tmem_empty[ab], ((ti / ACC_BUFS) & 1) ^ 1);   // the epilogue has drained this accumulator set
                 tc_fence_after();
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full_cvt[stage], phase);   // TMA landed (w_hi, w_lo in shared memory) and a converter group has written a_hi / a_lo to TMEM
-                    tc_fence_after();
-                    GEMM_TRACE(3, kb + (tile != (int)blockIdx.x) * 16);
+                    if (!(dbg & 16)) tc_fence_after();
+                    if (lane == 0) GEMM_TRACE(3, kb + (tile != (int)blockIdx.x) * 16);
                     const uint32_t a_hi = tmem_base + Cfg::A_COLS0 + (uint32_t)(stage * 2 * BLOCK_K), a_lo = a_hi + BLOCK_K;
                     const uint64_t w_hi = umma_desc_sw128(sWh(stage)), w_lo = umma_desc_sw128(sWl(stage));
+                    const uint32_t acc0 = (uint32_t)(kb != 0);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t ko = (uint64_t)((k * UMMA_K * 4) >> 4);   // 32 bytes per k-step inside the 128-byte swizzle row
-                        const uint32_t kc = (uint32_t)(k * UMMA_K);              // 8 TMEM columns per k-step
-                        umma_tf32_ts(d_small, a_lo + kc, w_hi + ko, Cfg::IDESC, (kb | k) != 0);
-                        umma_tf32_ts(d_small, a_hi + kc, w_lo + ko, Cfg::IDESC, 1u);
-                        umma_tf32_ts(d_big, a_hi + kc, w_hi + ko, Cfg::IDESC, (kb | k) != 0);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t ko = (uint64_t)((k * UMMA_K * 4) >> 4);   // 32 bytes per k-step inside the 128-byte swizzle row
+                            const uint32_t kc = (uint32_t)(k * UMMA_K);              // 8 TMEM columns per k-step
+                            if (dbg & 128) {       // three N = BLOCK_N instructions per k-step (the form before the stacked-B one)
+                                umma_tf32_ts(d_big, a_hi + kc, w_hi + ko, Cfg::IDESC, k ? 1u : acc0);
+                                umma_tf32_ts(d_small, a_hi + kc, w_lo + ko, Cfg::IDESC, k ? 1u : acc0);
+                                umma_tf32_ts(d_small, a_lo + kc, w_hi + ko, Cfg::IDESC, 1u);
+                            } else {
+                                umma_tf32_ts(d_big, a_hi + kc, w_hi + ko, Cfg::IDESC2, k ? 1u : acc0);   // big += a_hi.w_hi, small += a_hi.w_lo
+                                if (!(dbg & 4)) umma_tf32_ts(d_small, a_lo + kc, w_hi + ko, Cfg::IDESC, 1u);   // small += a_lo.w_hi
+                            }
+                        }
+                        umma_commit(&empty[stage]);       // the stage returns to the producer when these MMAs have read it
+                        if (kb == kblocks - 1) umma_commit(&tmem_full[ab]);   // accumulators complete
                     }
-                    umma_commit(&empty[stage]);           // the stage returns to the producer when these MMAs have read it
+                    __syncwarp();
+                    if (lane == 0 && tile == (int)blockIdx.x) GEMM_TRACE(5, 16 + kb);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[ab]);              // accumulators complete
             }
         }
     } else if (warp < 2 + 4 * CVT_GROUPS) {
@@ -254,6 +296,7 @@ gsd_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                     // this thread's matrix row: 8 x 16-byte chunks, chunk c stored at position c ^ (row % 8) (128-byte swizzle)
                     const float4 *rowp = reinterpret_cast<const float4 *>(sA(stage) + (size_t)crow * 128);
                     float hi[32], lo[32];
+                    if (!(dbg & 2)) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         const float4 v = rowp[c ^ (crow & 7)];
@@ -261,10 +304,15 @@ gsd_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                         lo[4 * c] = round_tf32(v.x - hi[4 * c]); lo[4 * c + 1] = round_tf32(v.y - hi[4 * c + 1]);
                         lo[4 * c + 2] = round_tf32(v.z - hi[4 * c + 2]); lo[4 * c + 3] = round_tf32(v.w - hi[4 * c + 3]);
                     }
+                    }
                     const uint32_t ta = tmem_base + ((uint32_t)(cq * 32) << 16) + Cfg::A_COLS0 + (uint32_t)(stage * 2 * BLOCK_K);
-                    tmem_st32(ta, hi);
-                    tmem_st32(ta + BLOCK_K, lo);
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    if (!(dbg & 3)) {
+                        tmem_st32(ta, hi);
+                        tmem_st32(ta + BLOCK_K, lo);
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    } else if (!(dbg & 2)) {
+                        if (hi[0] + lo[31] == 123.456f) tmem_st32(ta, hi);     // keep the loads and the split alive
+                    }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cta(&full_cvt[stage]);
@@ -277,6 +325,7 @@ gsd_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
         // ===== epilogue: 4 warps = 128 accumulator rows; overlaps the next tile's main loop when there are two accumulator pairs =====
         const int quarter = warp & 3;                     // a warp may only read its own quarter of the TMEM lanes
         const int row_in_tile = quarter * 32 + lane;
+        const int chalf = (warp - (2 + 4 * CVT_GROUPS)) >> 2;          // 0: columns [0, BLOCK_N / 2), 1: the rest
         int ti = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
             const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BLOCK_N;
@@ -287,7 +336,7 @@ gsd_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
             const int row = m0 + row_in_tile;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * 2 * BLOCK_N);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            for (int c0 = chalf * (BLOCK_N / 2); c0 < (chalf + 1) * (BLOCK_N / 2); c0 += 32) {
                 float vb[32];
                 {
                     float vs[32];
@@ -334,6 +383,252 @@ gsd_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
     }
     if (threadIdx.x == 32) GEMM_TRACE(5, 2);
+}
+
+// ---- CTA-pair variant (cta_group::2) for the edge-row layers ---------------------------------------------------------------------
+// Two CTAs of a cluster (one TPC) work on one 256 x 128 tile.  Each CTA converts ITS 128 rows of A into its own tensor memory and
+// stages HALF of the W tiles (64 of the 128 weight rows); the leader CTA's single MMA thread issues tcgen05.mma.cta_group::2
+// (M = 256): one instruction drives both SMs' tensor cores, each reading its A rows from its TMEM and both B halves.  Per CTA
+// and k-block that is 32 KB instead of 48 KB through L2 -> shared memory (the single-CTA kernel sits on the L2 -> SM path:
+// 48 KB per 768 tensor cycles = 62 B/clk/SM against ~43 B/clk/SM measured chip-wide), half the B-operand shared-memory reads, and
+// half as many MMA instructions per flop (the per-instruction cost measured ~115 cycles for a 64-cycle 128x128x8 TF32 product).
+// Synchronisation: full_a (local: own A tile landed) -> own converters; full_w (leader's: both CTAs' TMA loads complete_tx on it,
+// cp.async.bulk.tensor .cta_group::2) and full_cvt (leader's: 8 converter warps of both CTAs arrive, remotely for the peer)
+// -> MMA thread; tcgen05.commit .multicast::cluster frees the stage / publishes the accumulators in BOTH CTAs; tmem_empty
+// (leader's: 8 epilogue warps of both CTAs).
+constexpr int PAIR_N = 128, PAIR_HALF_N = 64;
+constexpr uint32_t PAIR_B_BYTES = PAIR_HALF_N * BLOCK_K * 4;                       // 8 KB: this CTA's half of a W tile
+constexpr uint32_t PAIR_STAGE_BYTES = A_TILE_BYTES + 2 * PAIR_B_BYTES;             // 32 KB
+constexpr int PAIR_STAGES = 4;                                                     // tensor-memory A ring: 4 x (32 + 32) columns
+constexpr uint32_t PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024;
+constexpr uint32_t PAIR_A_COLS0 = 256, PAIR_TMEM_COLS = 512;                       // [0,128) small | [128,256) big | [256,512) A ring
+constexpr uint32_t PAIR_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(PAIR_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on a barrier of either CTA of the pair (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, int c0, int c1, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs when the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+gsd_gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_wh,
+                            const __grid_constant__ CUtensorMap tm_wl, int M, int N, int K, const float *__restrict__ bias,
+                            const float *__restrict__ res1, const float *__restrict__ res2, int relu, float *__restrict__ out, long long ldo) {
+    constexpr int STAGES = PAIR_STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_a[STAGES], full_w[STAGES], full_cvt[STAGES], empty[STAGES], tmem_full, tmem_empty;
+    __shared__ uint32_t tmem_base_slot;
+    gsd_pdl_wait();
+    gsd_pdl_launch();
+    uint8_t *ring = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int kblocks = K / BLOCK_K;
+    const int tiles_n = N / PAIR_N, tiles_m = (M + 255) / 256;
+    const int n_tiles = tiles_m * tiles_n;
+    auto sA = [&](int s) { return ring + (size_t)s * PAIR_STAGE_BYTES; };
+    auto sWh = [&](int s) { return ring + (size_t)s * PAIR_STAGE_BYTES + A_TILE_BYTES; };
+    auto sWl = [&](int s) { return ring + (size_t)s * PAIR_STAGE_BYTES + A_TILE_BYTES + PAIR_B_BYTES; };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_a[s], 1); mbar_init(&full_w[s], 1); mbar_init(&full_cvt[s], 8); mbar_init(&empty[s], 1); }
+        mbar_init(&tmem_full, 1);
+        mbar_init(&tmem_empty, 8);
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_wh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_wl) : "memory");
+    }
+    if (warp == 1) {   // tensor memory of the pair: one warp per CTA
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(PAIR_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // the peer's barriers are initialised before anything is signalled across the pair
+    tc_fence_after();
+    if (tmem_base_slot != 0u) __trap();   // the whole tensor memory was allocated: base = column 0 (keeps addresses in uniform registers)
+    constexpr uint32_t tmem_base = 0u;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own A rows -> local barrier; own half of W -> the leader's barrier =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                const int m0 = (tile / tiles_n) * 256 + (int)rank * BLOCK_M, n0 = (tile % tiles_n) * PAIR_N + (int)rank * PAIR_HALF_N;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full_a[stage], A_TILE_BYTES);
+                    tma_load_2d(sA(stage), &tm_a, kb * BLOCK_K, m0, &full_a[stage]);        // rows beyond M arrive as zeros
+                    if (rank == 0) mbar_expect_tx(&full_w[stage], 4 * PAIR_B_BYTES);        // w_hi, w_lo halves of both CTAs
+                    const uint32_t fw = mapa_u32(smem_u32(&full_w[stage]), 0);
+                    tma_load_2d_pair(sWh(stage), &tm_wh, kb * BLOCK_K, n0, fw);
+                    tma_load_2d_pair(sWl(stage), &tm_wl, kb * BLOCK_K, n0, fw);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: warp 1 of the leader CTA (uniform control flow, one elected lane issues) =====
+        if (rank == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int ti = 0;
+            const uint32_t d_small = tmem_base, d_big = tmem_base + PAIR_N;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs, ++ti) {
+                mbar_wait(&tmem_empty, (ti & 1) ^ 1);     // both CTAs' epilogues have drained the accumulators
+                tc_fence_after();
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_w[stage], phase);      // both halves of w_hi / w_lo landed (in both CTAs)
+                    mbar_wait(&full_cvt[stage], phase);    // both CTAs' converters have written a_hi / a_lo to their tensor memory
+                    tc_fence_after();
+                    const uint32_t a_hi = tmem_base + PAIR_A_COLS0 + (uint32_t)(stage * 2 * BLOCK_K), a_lo = a_hi + BLOCK_K;
+                    const uint64_t w_hi = umma_desc_sw128(sWh(stage)), w_lo = umma_desc_sw128(sWl(stage));
+                    const uint32_t acc0 = (uint32_t)(kb != 0);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t ko = (uint64_t)((k * UMMA_K * 4) >> 4);
+                            const uint32_t kc = (uint32_t)(k * UMMA_K);
+                            umma_tf32_ts_pair(d_small, a_lo + kc, w_hi + ko, PAIR_IDESC, k ? 1u : acc0);
+                            umma_tf32_ts_pair(d_small, a_hi + kc, w_lo + ko, PAIR_IDESC, 1u);
+                            umma_tf32_ts_pair(d_big, a_hi + kc, w_hi + ko, PAIR_IDESC, k ? 1u : acc0);
+                        }
+                        umma_commit_pair(&empty[stage]);
+                        if (kb == kblocks - 1) umma_commit_pair(&tmem_full);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp < 2 + 4 * CVT_GROUPS) {
+        // ===== converters (both CTAs): group g splits every CVT_GROUPS-th k-block of this CTA's A rows =====
+        const int g = (warp - 2) / 4;
+        const int cq = warp & 3;
+        const int crow = cq * 32 + lane;
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                if (it % CVT_GROUPS == g) {
+                    mbar_wait(&full_a[stage], phase);
+                    const float4 *rowp = reinterpret_cast<const float4 *>(sA(stage) + (size_t)crow * 128);
+                    float hi[32], lo[32];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 v = rowp[c ^ (crow & 7)];
+                        hi[4 * c] = round_tf32(v.x); hi[4 * c + 1] = round_tf32(v.y); hi[4 * c + 2] = round_tf32(v.z); hi[4 * c + 3] = round_tf32(v.w);
+                        lo[4 * c] = round_tf32(v.x - hi[4 * c]); lo[4 * c + 1] = round_tf32(v.y - hi[4 * c + 1]);
+                        lo[4 * c + 2] = round_tf32(v.z - hi[4 * c + 2]); lo[4 * c + 3] = round_tf32(v.w - hi[4 * c + 3]);
+                    }
+                    const uint32_t ta = tmem_base + ((uint32_t)(cq * 32) << 16) + PAIR_A_COLS0 + (uint32_t)(stage * 2 * BLOCK_K);
+                    tmem_st32(ta, hi);
+                    tmem_st32(ta + BLOCK_K, lo);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&full_cvt[stage]), 0));
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): this CTA's 128 rows of the tile =====
+        const int quarter = warp & 3;
+        const int row_in_tile = quarter * 32 + lane;
+        int ti = 0;
+        for (int tile = pair; tile < n_tiles; tile += n_pairs, ++ti) {
+            const int m0 = (tile / tiles_n) * 256 + (int)rank * BLOCK_M, n0 = (tile % tiles_n) * PAIR_N;
+            mbar_wait(&tmem_full, ti & 1);
+            tc_fence_after();
+            const int row = m0 + row_in_tile;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < PAIR_N; c0 += 32) {
+                float vb[32];
+                {
+                    float vs[32];
+                    tmem_ld32(lane_addr + (uint32_t)c0, vs);
+                    tmem_ld32(lane_addr + (uint32_t)(PAIR_N + c0), vb);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) vb[j] += vs[j];
+                }
+                if (row < M) {
+                    const int col = n0 + c0;
+                    float *o = out + (size_t)row * ldo + col;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 r = make_float4(vb[j], vb[j + 1], vb[j + 2], vb[j + 3]);
+                        if (bias) {
+                            const float4 bq = __ldg(reinterpret_cast<const float4 *>(bias + col + j));
+                            r.x += bq.x; r.y += bq.y; r.z += bq.z; r.w += bq.w;
+                        }
+                        if (res1) {
+                            const float4 q = __ldg(reinterpret_cast<const float4 *>(res1 + (size_t)row * ldo + col + j));
+                            r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+                        }
+                        if (res2) {
+                            const float4 q = __ldg(reinterpret_cast<const float4 *>(res2 + (size_t)row * ldo + col + j));
+                            r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+                        }
+                        if (relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+                        *reinterpret_cast<float4 *>(o + j) = r;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&tmem_empty), 0));
+        }
+    }
+    // ----- teardown: neither CTA may leave while the other can still signal its barriers or read its shared memory
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(PAIR_TMEM_COLS) : "memory");
+    }
 }
 
 // ---- host: tensor maps ---------------------------------------------------------------------------------------------------
@@ -384,8 +679,9 @@ int launch_gemm(long long M, int N, int K, const float *A, long long lda, const 
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const bool trace = getenv("GSD_GEMM_DBG") != nullptr;
     if (trace) { const int one = 1; cudaMemcpyToSymbol(g_gemm_trace_on, &one, 4); }
+    static const int dbg_mode = getenv("GSD_GEMM_MODE") ? atoi(getenv("GSD_GEMM_MODE")) : 0;
     gsd_launch(gsd_gemm_tf32x3_kernel<BLOCK_N>, dim3(tiles < sms ? tiles : sms), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, ta, th, tl, (int)M, N, K,
-               bias, res1, res2, relu, out, ldo);
+               bias, res1, res2, relu, out, ldo, dbg_mode);
     GSD_LAUNCH_CHECK();
     if (trace) {
         long long h[6 * 64];
@@ -395,6 +691,8 @@ int launch_gemm(long long M, int N, int K, const float *A, long long lda, const 
         fprintf(stderr, "GEMM BN=%d M=%lld N=%d grid=%d: kernel start 0, setup done %lld, end %lld (ns)\n  kb: tma_issue full_raw_seen cvt_done mma_issue\n", BLOCK_N, M, N,
                 tiles < sms ? tiles : sms, h[5 * 64 + 1] - t0, h[5 * 64 + 2] - t0);
         for (int i = 0; i < 32; ++i) fprintf(stderr, "  %2d: %6lld %6lld %6lld %6lld\n", i, h[i] - t0, h[64 + i] - t0, h[128 + i] - t0, h[192 + i] - t0);
+        fprintf(stderr, "  MMA warp, first tile: kb: issue_start  issued_and_committed\n");
+        for (int i = 0; i < 16; ++i) fprintf(stderr, "  %2d: %6lld %6lld\n", i, h[192 + i] - t0, h[5 * 64 + 16 + i] - t0);
         fprintf(stderr, "  epilogue start/end first tile: %lld %lld  last tile: %lld %lld\n", h[256] - t0, h[258] - t0, h[257] - t0, h[259] - t0);
     }
     return GSD_OK;
@@ -488,6 +786,29 @@ gsd_linear_small_n_kernel(long long M, int N, int K, const float *__restrict__ x
 
 }  // namespace
 
+int launch_gemm_pair(long long M, int N, int K, const float *A, long long lda, const float *W_hi, const float *W_lo, const float *bias,
+                     const float *res1, const float *res2, int relu, float *out, long long ldo, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_gemm_tf32x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+        attr_done = true;
+    }
+    CUtensorMap ta, th, tl;
+    int rc;
+    if ((rc = make_map(&ta, A, M, K, lda, BLOCK_M))) return rc;
+    if ((rc = make_map(&th, W_hi, N, K, K, PAIR_HALF_N))) return rc;
+    if ((rc = make_map(&tl, W_lo, N, K, K, PAIR_HALF_N))) return rc;
+    const int tiles = (int)((M + 255) / 256) * (N / PAIR_N);
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int pairs = tiles < sms / 2 ? tiles : sms / 2;
+    gsd_launch(gsd_gemm_tf32x3_pair_kernel, dim3(2 * pairs), dim3(PAIR_THREADS), PAIR_SMEM_BYTES, st, ta, th, tl, (int)M, N, K, bias, res1, res2, relu,
+               out, ldo);
+    GSD_LAUNCH_CHECK();
+    return GSD_OK;
+}
+
 extern "C" int gsd_linear_tf32x3(int64_t M, int32_t N, int32_t K, const float *A, int64_t lda, const float *W_hi, const float *W_lo,
                                  const float *bias, const float *res1, const float *res2, int32_t relu, float *out, int64_t ldo, void *stream) {
     if (M < 0 || N <= 0 || K <= 0 || (M > 0 && (!A || !W_hi || !W_lo || !out))) { gsd_set_error("invalid arguments"); return GSD_ERR_INVALID; }
@@ -506,6 +827,11 @@ extern "C" int gsd_linear_tf32x3(int64_t M, int32_t N, int32_t K, const float *A
     const long long tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
     const char *force = getenv("GSD_GEMM_BN");
     const int fbn = force ? atoi(force) : 0;
+    // GSD_GEMM_PAIR=1: CTA pairs (cta_group::2) on 256 x 128 tiles
+    const char *fp = getenv("GSD_GEMM_PAIR");
+    const int pair_mode = fp ? atoi(fp) : -1;
+    if (N % PAIR_N == 0 && fbn == 0 && pair_mode == 1)   // measured slower than the single-CTA kernel: opt-in only
+        return launch_gemm_pair(M, N, K, A, lda, W_hi, W_lo, bias, res1, res2, relu, out, ldo, st);
     if (fbn == 64) return launch_gemm<64>(M, N, K, A, lda, W_hi, W_lo, bias, res1, res2, relu, out, ldo, st);
     if (N % 128 == 0 && (fbn == 128 || tiles_m * (N / 128) >= 148)) return launch_gemm<128>(M, N, K, A, lda, W_hi, W_lo, bias, res1, res2, relu, out, ldo, st);
     return launch_gemm<64>(M, N, K, A, lda, W_hi, W_lo, bias, res1, res2, relu, out, ldo, st);
