@@ -248,34 +248,39 @@ gsd_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                 // a_hi . [w_hi ; w_lo]^T into both (2 instead of 3 instructions per k-step; an instruction costs ~100 cycles up to N = 128).
                 const uint32_t d_big = tmem_base + (uint32_t)(ab * 2 * BLOCK_N), d_small = d_big + BLOCK_N;
                 mbar_wait(&tmem_empty[ab], ((ti / ACC_BUFS) & 1) ^ 1);   // the epilogue has drained this accumulator set
+                // The wait for k-block kb + 1 is issued BETWEEN the third and the last k-step of k-block kb: the barrier poll, the
+                // fence and the descriptor arithmetic then run while the tensor pipe still has queued work instead of after it drained.
+                mbar_wait(&full_cvt[stage], phase);       // TMA landed (w_hi, w_lo in shared memory) and a converter group has written a_hi / a_lo to TMEM
                 tc_fence_after();
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full_cvt[stage], phase);   // TMA landed (w_hi, w_lo in shared memory) and a converter group has written a_hi / a_lo to TMEM
-                    if (!(dbg & 16)) tc_fence_after();
                     if (lane == 0) GEMM_TRACE(3, kb + (tile != (int)blockIdx.x) * 16);
                     const uint32_t a_hi = tmem_base + Cfg::A_COLS0 + (uint32_t)(stage * 2 * BLOCK_K), a_lo = a_hi + BLOCK_K;
-                    const uint64_t w_hi = umma_desc_sw128(sWh(stage)), w_lo = umma_desc_sw128(sWl(stage));
+                    const uint64_t w_hi = umma_desc_sw128(sWh(stage));
                     const uint32_t acc0 = (uint32_t)(kb != 0);
+                    auto issue = [&](int k) {
+                        const uint64_t ko = (uint64_t)((k * UMMA_K * 4) >> 4);   // 32 bytes per k-step inside the 128-byte swizzle row
+                        const uint32_t kc = (uint32_t)(k * UMMA_K);              // 8 TMEM columns per k-step
+                        umma_tf32_ts(d_big, a_hi + kc, w_hi + ko, Cfg::IDESC2, k ? 1u : acc0);   // big += a_hi.w_hi, small += a_hi.w_lo
+                        if (!(dbg & 4)) umma_tf32_ts(d_small, a_lo + kc, w_hi + ko, Cfg::IDESC, 1u);   // small += a_lo.w_hi
+                    };
                     if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            const uint64_t ko = (uint64_t)((k * UMMA_K * 4) >> 4);   // 32 bytes per k-step inside the 128-byte swizzle row
-                            const uint32_t kc = (uint32_t)(k * UMMA_K);              // 8 TMEM columns per k-step
-                            if (dbg & 128) {       // three N = BLOCK_N instructions per k-step (the form before the stacked-B one)
-                                umma_tf32_ts(d_big, a_hi + kc, w_hi + ko, Cfg::IDESC, k ? 1u : acc0);
-                                umma_tf32_ts(d_small, a_hi + kc, w_lo + ko, Cfg::IDESC, k ? 1u : acc0);
-                                umma_tf32_ts(d_small, a_lo + kc, w_hi + ko, Cfg::IDESC, 1u);
-                            } else {
-                                umma_tf32_ts(d_big, a_hi + kc, w_hi + ko, Cfg::IDESC2, k ? 1u : acc0);   // big += a_hi.w_hi, small += a_hi.w_lo
-                                if (!(dbg & 4)) umma_tf32_ts(d_small, a_lo + kc, w_hi + ko, Cfg::IDESC, 1u);   // small += a_lo.w_hi
-                            }
-                        }
+                        for (int k = 0; k < BLOCK_K / UMMA_K - 1; ++k) issue(k);
+                    }
+                    __syncwarp();
+                    int nstage = stage + 1;
+                    uint32_t nphase = phase;
+                    if (nstage == STAGES) { nstage = 0; nphase ^= 1; }
+                    const bool more = kb + 1 < kblocks;
+                    if (more) { mbar_wait(&full_cvt[nstage], nphase); tc_fence_after(); }
+                    if (elect_one()) {
+                        issue(BLOCK_K / UMMA_K - 1);
                         umma_commit(&empty[stage]);       // the stage returns to the producer when these MMAs have read it
-                        if (kb == kblocks - 1) umma_commit(&tmem_full[ab]);   // accumulators complete
+                        if (!more) umma_commit(&tmem_full[ab]);   // accumulators complete
                     }
                     __syncwarp();
                     if (lane == 0 && tile == (int)blockIdx.x) GEMM_TRACE(5, 16 + kb);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    stage = nstage; phase = nphase;
                 }
             }
         }
@@ -833,7 +838,10 @@ extern "C" int gsd_linear_tf32x3(int64_t M, int32_t N, int32_t K, const float *A
     if (N % PAIR_N == 0 && fbn == 0 && pair_mode == 1)   // measured slower than the single-CTA kernel: opt-in only
         return launch_gemm_pair(M, N, K, A, lda, W_hi, W_lo, bias, res1, res2, relu, out, ldo, st);
     if (fbn == 64) return launch_gemm<64>(M, N, K, A, lda, W_hi, W_lo, bias, res1, res2, relu, out, ldo, st);
-    if (N % 128 == 0 && (fbn == 128 || tiles_m * (N / 128) >= 148)) return launch_gemm<128>(M, N, K, A, lda, W_hi, W_lo, bias, res1, res2, relu, out, ldo, st);
+    // tile width: fewer waves win (a 128-wide tile costs ~1.15x a 64-wide one per k-block: both sit on the per-instruction floor)
+    const long long w64 = (tiles_m * (N / 64) + 147) / 148, w128 = N % 128 == 0 ? (tiles_m * (N / 128) + 147) / 148 : (1LL << 40);
+    if (N % 128 == 0 && (fbn == 128 || (fbn == 0 && 115 * w128 < 100 * w64)))
+        return launch_gemm<128>(M, N, K, A, lda, W_hi, W_lo, bias, res1, res2, relu, out, ldo, st);
     return launch_gemm<64>(M, N, K, A, lda, W_hi, W_lo, bias, res1, res2, relu, out, ldo, st);
 }
 

@@ -543,25 +543,50 @@ class DynamicsPredictor(nn.Module):
             self._tckey = key
         return self._tcw
 
-    def _forward_tc(self, p_inputs, rel_inputs, edges, B, N, n_p):
+    def _node_chain_tc(self, p_inputs, B, N):
+        """Particle encoder + the pstep-invariant node term + the first receiver | sender projection, launched on a SIDE stream:
+        they depend only on the particle inputs, so they run beside the edge builder and the edge-row layers (whose persistent
+        kernels leave SMs idle in their last wave) and are joined before the first aggregation.  Returns (h, C0, P, side stream)."""
+        W = self._split_weights()
+        pe, bp = self.particle_encoder.model, self.particle_propagator.linear.bias
+        main = torch.cuda.current_stream()
+        side = getattr(self, "_side", None)
+        if side is None or side.device != p_inputs.device:
+            side = self._side = torch.cuda.Stream(device=p_inputs.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            y = _small_linear(p_inputs.reshape(B * N, -1), pe[0].weight, pe[0].bias, relu=True)
+            y = _tc_linear(y, W["pe2"], pe[2].bias, relu=True)
+            h = _tc_linear(y, W["pe4"], pe[4].bias, relu=True)                   # particle_encode
+            C0 = _tc_linear(h, W["C0"], bp)                                      # pstep-invariant node term
+            P = _tc_linear(h, W["W23"])                                          # [B*N, 2F]: receiver | sender projections
+        if not torch.cuda.is_current_stream_capturing():      # eager: tell the caching allocator about the cross-stream uses
+            p_inputs.record_stream(side)
+            for t in (h, C0, P):
+                t.record_stream(main)
+        return h, C0, P, side
+
+    def _forward_tc(self, p_inputs, rel_inputs, edges, B, N, n_p, node=None):
         """Inference path on the hand-written tensor-core kernels: every F-wide layer is one gsd_linear_tf32x3 launch whose
         epilogue carries the bias, the residual adds and the ReLU (model.py:202-241 with the relation propagator's weight split
         of DESIGN.md §4); the K = 5 / 14 input layers and the 512 -> 3 head are plain fp32 kernels.  No library GEMM, no pack
-        launches, no elementwise launches between layers."""
+        launches, no elementwise launches between layers.  The node-level chain runs on a side stream (`node`: already
+        launched by the caller, e.g. before the edge builder)."""
         cfg, Fd = self.model_config, self.nf_effect
         W = self._split_weights()
-        pe, re, nr = self.particle_encoder.model, self.relation_encoder.model, self.non_rigid_predictor
-        br, bp = self.relation_propagator.linear.bias, self.particle_propagator.linear.bias
-        y = _small_linear(p_inputs.reshape(B * N, -1), pe[0].weight, pe[0].bias, relu=True)
-        y = _tc_linear(y, W["pe2"], pe[2].bias, relu=True)
-        h = _tc_linear(y, W["pe4"], pe[4].bias, relu=True)                       # particle_encode
-        C0 = _tc_linear(h, W["C0"], bp)                                          # pstep-invariant node term
+        re, nr = self.relation_encoder.model, self.non_rigid_predictor
+        br = self.relation_propagator.linear.bias
+        if node is None:
+            node = self._node_chain_tc(p_inputs, B, N)
+        h, C0, P, side = node
         e = _small_linear(rel_inputs.reshape(B * edges.capacity, -1), re[0].weight, re[0].bias, relu=True)
         e = _tc_linear(e, W["re2"], re[2].bias, relu=True)
         e = _tc_linear(e, W["re4"], re[4].bias, relu=True)                       # relation_encode
         A = _tc_linear(e, W["A"], br)                                            # pstep-invariant edge term
-        for _ in range(cfg['pstep']):
-            P = _tc_linear(h, W["W23"])                                          # [B*N, 2F]: receiver | sender projections
+        torch.cuda.current_stream().wait_stream(side)
+        for i in range(cfg['pstep']):
+            if i > 0:
+                P = _tc_linear(h, W["W23"])
             agg = _Aggregate.apply(A, P, edges)
             h = _tc_linear(agg, W["Wp2"], None, res1=C0, res2=h, relu=True)      # relu(C0 + h + agg Wp2^T)
         x = h if n_p == N else h.view(B, N, Fd)[:, :n_p].reshape(B * n_p, Fd)
@@ -712,9 +737,10 @@ class GnnRollout:
                                                self.states.data_ptr(), self.attrs.data_ptr(), self.action.data_ptr(),
                                                self.eef_delta.data_ptr(), 0 if self.eef_delta.dim() == 1 else 3,
                                                p_inputs.data_ptr(), cur.data_ptr(), _stream()), "gsd_gnn_rollout_pre")
+            node = m._node_chain_tc(p_inputs, B, N)        # side stream: beside the edge builder and the edge-row layers
             edges = construct_edges_index(cur, self.adj_thresh, self._m8, self._t8, topk=self.topk, connect_all=self.connect_all, n_tool=1)
             rel_inputs = edge_inputs(self.states, self.attrs, self.p_instance, edges)
-            motion = m._forward_tc(p_inputs, rel_inputs, edges, B, N, nobj)
+            motion = m._forward_tc(p_inputs, rel_inputs, edges, B, N, nobj, node=node)
             _lib.check(lib.gsd_gnn_rollout_post(B, N, nobj, n_his, self.states.data_ptr(), motion.data_ptr(), self.eef_delta.data_ptr(),
                                                 0 if self.eef_delta.dim() == 1 else 3, float(m.motion_clamp), pred.data_ptr(), _stream()),
                        "gsd_gnn_rollout_post")
