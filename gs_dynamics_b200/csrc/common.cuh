@@ -139,6 +139,9 @@ __device__ __forceinline__ void gsd_pdl_launch() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
+// unconditional early trigger: used by the kernels of the GNN step (one or few waves of long-lived CTAs), where letting the next
+// kernel's CTAs start their prologue on SMs as they free up hides ~2-3 us of launch latency + set-up per kernel of the chain
+__device__ __forceinline__ void gsd_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool gsd_pdl_enabled();
 template <typename... KArgs, typename... Args>
 static inline void gsd_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

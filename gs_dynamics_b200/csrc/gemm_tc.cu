@@ -173,8 +173,7 @@ gsd_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_raw[STAGES], full_cvt[STAGES], empty[STAGES], tmem_full[ACC_BUFS], tmem_empty[ACC_BUFS];
     __shared__ uint32_t tmem_base_slot;
-    gsd_pdl_wait();
-    gsd_pdl_launch();
+    gsd_pdl_trigger();           // the next kernel of the chain may set itself up while this one runs (it waits before reading)
     const bool trace_on = g_gemm_trace_on && blockIdx.x == 0;
     if (threadIdx.x == 0) GEMM_TRACE(5, 0);
     uint8_t *ring = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -205,6 +204,7 @@ gsd_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     // every tensor-memory address in uniform registers
     if (tmem_base_slot != 0u) __trap();
     constexpr uint32_t tmem_base = 0u;
+    gsd_pdl_wait();              // everything above (barriers, tensor memory, descriptor prefetch) overlapped the previous kernel
     if (threadIdx.x == 0) GEMM_TRACE(5, 1);
 
     if (warp == 0) {
@@ -340,43 +340,45 @@ gsd_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
             if (threadIdx.x == 320) GEMM_TRACE(4, (tile != (int)blockIdx.x));
             const int row = m0 + row_in_tile;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * 2 * BLOCK_N);
-#pragma unroll 1
-            for (int c0 = chalf * (BLOCK_N / 2); c0 < (chalf + 1) * (BLOCK_N / 2); c0 += 32) {
-                float vb[32];
-                {
-                    float vs[32];
-                    tmem_ld32(lane_addr + (uint32_t)c0, vs);
-                    tmem_ld32(lane_addr + (uint32_t)(BLOCK_N + c0), vb);
-                    tmem_ld_wait();
+            // this thread's BLOCK_N / 2 output columns are pulled into registers first and the accumulators handed back at once:
+            // the bias / residual loads and the stores below overlap the NEXT tile's main loop (the accumulators are not
+            // double-buffered at 128-wide tiles, so everything before the hand-back is exposed time)
+            constexpr int EC = BLOCK_N / 2;
+            float v[EC];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) vb[j] += vs[j];
-                }
-                if (row < M) {
-                    const int col = n0 + c0;
-                    float *o = out + (size_t)row * ldo + col;
+            for (int c = 0; c < EC; c += 32) {
+                float vs[32];
+                tmem_ld32(lane_addr + (uint32_t)(chalf * EC + c), v + c);
+                tmem_ld32(lane_addr + (uint32_t)(BLOCK_N + chalf * EC + c), vs);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 r = make_float4(vb[j], vb[j + 1], vb[j + 2], vb[j + 3]);
-                        if (bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + col + j));
-                            r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
-                        }
-                        if (res1) {
-                            const float4 q = __ldg(reinterpret_cast<const float4 *>(res1 + (size_t)row * ldo + col + j));
-                            r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
-                        }
-                        if (res2) {
-                            const float4 q = __ldg(reinterpret_cast<const float4 *>(res2 + (size_t)row * ldo + col + j));
-                            r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
-                        }
-                        if (relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
-                        *reinterpret_cast<float4 *>(o + j) = r;
-                    }
-                }
+                for (int j = 0; j < 32; ++j) v[c + j] += vs[j];
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(&tmem_empty[ab]);
+            if (row < M) {
+                const int col = n0 + chalf * EC;
+                float *o = out + (size_t)row * ldo + col;
+#pragma unroll
+                for (int j = 0; j < EC; j += 4) {
+                    float4 r = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    if (bias) {
+                        const float4 bq = __ldg(reinterpret_cast<const float4 *>(bias + col + j));
+                        r.x += bq.x; r.y += bq.y; r.z += bq.z; r.w += bq.w;
+                    }
+                    if (res1) {
+                        const float4 q = __ldg(reinterpret_cast<const float4 *>(res1 + (size_t)row * ldo + col + j));
+                        r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+                    }
+                    if (res2) {
+                        const float4 q = __ldg(reinterpret_cast<const float4 *>(res2 + (size_t)row * ldo + col + j));
+                        r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+                    }
+                    if (relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+                    *reinterpret_cast<float4 *>(o + j) = r;
+                }
+            }
             if (threadIdx.x == 320) GEMM_TRACE(4, 2 + (tile != (int)blockIdx.x));
         }
     }
@@ -458,8 +460,7 @@ gsd_gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __gr
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_a[STAGES], full_w[STAGES], full_cvt[STAGES], empty[STAGES], tmem_full, tmem_empty;
     __shared__ uint32_t tmem_base_slot;
-    gsd_pdl_wait();
-    gsd_pdl_launch();
+    gsd_pdl_trigger();
     uint8_t *ring = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -490,6 +491,7 @@ gsd_gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __gr
     tc_fence_after();
     if (tmem_base_slot != 0u) __trap();   // the whole tensor memory was allocated: base = column 0 (keeps addresses in uniform registers)
     constexpr uint32_t tmem_base = 0u;
+    gsd_pdl_wait();
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs): own A rows -> local barrier; own half of W -> the leader's barrier =====
@@ -721,8 +723,8 @@ constexpr int SK_ROWS = 32;
 __global__ void __launch_bounds__(256)
 gsd_linear_small_k_kernel(long long M, int N, int K, const float *__restrict__ x, const float *__restrict__ W, const float *__restrict__ bias,
                           int relu, float *__restrict__ out) {
+    gsd_pdl_trigger();
     gsd_pdl_wait();
-    gsd_pdl_launch();
     extern __shared__ float sk_smem[];          // [K][N] transposed weights, then [K][SK_ROWS] transposed inputs
     float *sWt = sk_smem, *sxT = sk_smem + (size_t)K * N;
     const long long m0 = (long long)blockIdx.x * SK_ROWS;
@@ -759,8 +761,8 @@ gsd_linear_small_k_kernel(long long M, int N, int K, const float *__restrict__ x
 __global__ void __launch_bounds__(256)
 gsd_linear_small_n_kernel(long long M, int N, int K, const float *__restrict__ x, long long ldx, const float *__restrict__ W,
                           const float *__restrict__ bias, float *__restrict__ out) {
+    gsd_pdl_trigger();
     gsd_pdl_wait();
-    gsd_pdl_launch();
     const long long m = (long long)blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
     if (m >= M) return;

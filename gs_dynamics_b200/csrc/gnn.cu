@@ -202,6 +202,7 @@ gsd_gnn_edges_fused_kernel(EdgeArgs a, int rows_per_cta, int cap, int32_t *__res
     //         row words [rows_per_cta][words] | row counts, row offsets [rows_per_cta] | flags [32 words]
     extern __shared__ unsigned long long skeys[];
     __shared__ int s_red[8], s_prefix;
+    gsd_pdl_trigger();
     gsd_pdl_wait();
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int npad = a.words * 32;
@@ -519,6 +520,8 @@ __global__ void __launch_bounds__(256)
 gsd_gnn_edge_inputs_kernel(int B, int N, int cap, int n_his, int attr_dim, int n_inst, int n_p, const float *__restrict__ state,
                            const float *__restrict__ attrs, const float *__restrict__ p_instance, const int32_t *__restrict__ recv,
                            const int32_t *__restrict__ send, float *__restrict__ out) {
+    gsd_pdl_trigger();
+    gsd_pdl_wait();
     const int width = 2 * attr_dim + 1 + 3 * n_his;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)B * cap) return;
@@ -558,8 +561,8 @@ extern "C" int gsd_gnn_edge_inputs(int32_t B, int32_t N, int32_t capacity, int32
     }
     if (capacity == 0) return GSD_OK;
     long long total = (long long)B * capacity;
-    gsd_gnn_edge_inputs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        B, N, capacity, n_his, attr_dim, n_instance, n_p, state, attrs, p_instance, receivers, senders, rel_inputs);
+    gsd_launch(gsd_gnn_edge_inputs_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, B, N, capacity, n_his,
+               attr_dim, n_instance, n_p, state, attrs, p_instance, receivers, senders, rel_inputs);
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }
@@ -579,6 +582,8 @@ __global__ void __launch_bounds__(128)
 gsd_gnn_aggregate_kernel(int B, int N, int cap, int n_light, int n_heavy, int rows_grid, const int32_t *__restrict__ row_ptr,
                          const int32_t *__restrict__ send, const float4 *__restrict__ A, const float4 *__restrict__ P,
                          float4 *__restrict__ agg, float4 *__restrict__ partial /* [B*n_heavy][GNN_SPLIT][F4] */, int32_t *__restrict__ tickets) {
+    gsd_pdl_trigger();
+    gsd_pdl_wait();
     constexpr int F4 = 32 * VEC_PER_LANE; // float4 per feature row
     if ((int)blockIdx.x < rows_grid) {
         const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -649,7 +654,10 @@ gsd_gnn_aggregate_kernel(int B, int N, int cap, int n_light, int n_heavy, int ro
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&tickets[hrow], 1) == GNN_SPLIT - 1);
+    if (threadIdx.x == 0) {
+        s_last = (atomicAdd(&tickets[hrow], 1) == GNN_SPLIT - 1);
+        if (s_last) tickets[hrow] = 0;      // self-cleaning: the counters are zero again when the kernel ends (no memset per call)
+    }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
@@ -690,16 +698,15 @@ extern "C" int gsd_gnn_aggregate(int32_t B, int32_t N, int32_t capacity, int32_t
     if (rows_grid + heavy_grid == 0) return GSD_OK;
     int32_t *tickets = nullptr;
     if (n_heavy > 0) {
-        tickets = (int32_t *)((char *)ws + gsd_align_up((size_t)B * n_heavy * GNN_SPLIT * F * 4));
-        GSD_CUDA_CHECK(cudaMemsetAsync(tickets, 0, (size_t)B * n_heavy * 4, st));
+        tickets = (int32_t *)((char *)ws + gsd_align_up((size_t)B * n_heavy * GNN_SPLIT * F * 4));   // zero on entry, zero on exit
     }
     const dim3 grid((unsigned)(rows_grid + heavy_grid));
 #define GSD_AGG_ARGS B, N, capacity, n_light, n_heavy, rows_grid, row_ptr, senders, (const float4 *)A, (const float4 *)P, (float4 *)agg, (float4 *)ws, tickets
     switch (F / 128) {
-    case 1: gsd_gnn_aggregate_kernel<1><<<grid, 128, 0, st>>>(GSD_AGG_ARGS); break;
-    case 2: gsd_gnn_aggregate_kernel<2><<<grid, 128, 0, st>>>(GSD_AGG_ARGS); break;
-    case 3: gsd_gnn_aggregate_kernel<3><<<grid, 128, 0, st>>>(GSD_AGG_ARGS); break;
-    default: gsd_gnn_aggregate_kernel<4><<<grid, 128, 0, st>>>(GSD_AGG_ARGS); break;
+    case 1: gsd_launch(gsd_gnn_aggregate_kernel<1>, grid, dim3(128), 0, st, GSD_AGG_ARGS); break;
+    case 2: gsd_launch(gsd_gnn_aggregate_kernel<2>, grid, dim3(128), 0, st, GSD_AGG_ARGS); break;
+    case 3: gsd_launch(gsd_gnn_aggregate_kernel<3>, grid, dim3(128), 0, st, GSD_AGG_ARGS); break;
+    default: gsd_launch(gsd_gnn_aggregate_kernel<4>, grid, dim3(128), 0, st, GSD_AGG_ARGS); break;
     }
 #undef GSD_AGG_ARGS
     GSD_LAUNCH_CHECK();
@@ -843,6 +850,7 @@ __global__ void __launch_bounds__(256)
 gsd_gnn_rollout_pre_kernel(int B, int N, int n_obj, int n_his, int attr_dim, int state_dim, int motion, int has_action,
                            const float *__restrict__ states, const float *__restrict__ attrs, float *__restrict__ action,
                            const float *__restrict__ eef_delta, int delta_stride, float *__restrict__ p_inputs, float *__restrict__ cur) {
+    gsd_pdl_trigger();
     gsd_pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * N) return;
@@ -881,6 +889,7 @@ gsd_gnn_rollout_pre_kernel(int B, int N, int n_obj, int n_his, int attr_dim, int
 __global__ void __launch_bounds__(256)
 gsd_gnn_rollout_post_kernel(int B, int N, int n_obj, int n_his, float *__restrict__ states, const float *__restrict__ motion,
                             const float *__restrict__ eef_delta, int delta_stride, float clampv, float *__restrict__ pred) {
+    gsd_pdl_trigger();
     gsd_pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * N) return;

@@ -357,6 +357,9 @@ def edge_inputs(state, attrs, p_instance, edges, attr_dim_used=True, group=True)
     return _EdgeInputs.apply(state, attrs.contiguous(), p_instance.contiguous(), edges)
 
 
+_AGG_WS = {}
+
+
 class _Aggregate(torch.autograd.Function):
     """agg[node] = sum_e ReLU(A[e] + P[node,:F] + P[send(e),F:]).  Backward (GNN training): gsd_gnn_aggregate_bwd recomputes
     the pre-activation sign, so the forward saves nothing but its inputs."""
@@ -371,7 +374,11 @@ class _Aggregate(torch.autograd.Function):
         nbytes = C.c_size_t()
         _lib.check(lib.gsd_gnn_aggregate_workspace_bytes(B, edges.n_tool, Fd, C.byref(nbytes)), "gsd_gnn_aggregate_workspace_bytes")
         with torch.cuda.device(A.device):
-            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=A.device)
+            # zero-filled once, self-cleaning afterwards (include/gsd.h); the calls sharing it are issued in stream order
+            key = (A.device, B, edges.n_tool, Fd)
+            ws = _AGG_WS.get(key)
+            if ws is None:
+                ws = _AGG_WS[key] = torch.zeros(max(int(nbytes.value), 16), dtype=torch.uint8, device=A.device)
             agg = torch.empty((B * N, Fd), dtype=torch.float32, device=A.device)
             _lib.check(lib.gsd_gnn_aggregate(B, N, cap, Fd, edges.n_tool, edges.row_ptr.data_ptr(), edges.senders.data_ptr(),
                                              A.data_ptr(), P.data_ptr(), ws.data_ptr(), agg.data_ptr(), _stream()), "gsd_gnn_aggregate")

@@ -275,7 +275,9 @@ int gsd_gnn_rollout_post(int32_t B, int32_t N, int32_t n_obj, int32_t n_his, flo
 
 /* agg[b*N+r, :] = sum over incoming edges e of ReLU(A[b*cap+e, :] + P[b*N+r, 0:F] + P[b*N+send(e), F:2F])
  * (relation propagator epilogue + Rr^T scatter-add of model.py:212-229). The last n_heavy rows of every element
- * (tool nodes) are split over several CTAs and summed in fixed order. F multiple of 128, <= 512. */
+ * (tool nodes) are split over several CTAs and summed in fixed order. F multiple of 128, <= 512.
+ * ws: gsd_gnn_aggregate_workspace_bytes() bytes, ZERO-FILLED ONCE by the caller before its first use; the call leaves the
+ * counters it holds at zero again, so the same workspace serves any number of calls issued in stream order (no memset per call). */
 int gsd_gnn_aggregate_workspace_bytes(int32_t B, int32_t n_heavy, int32_t F, size_t *bytes);
 int gsd_gnn_aggregate(int32_t B, int32_t N, int32_t capacity, int32_t F, int32_t n_heavy, const int32_t *row_ptr,
                       const int32_t *senders, const float *A, const float *P, void *ws, float *agg, void *stream);
