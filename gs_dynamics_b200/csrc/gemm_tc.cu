@@ -727,32 +727,38 @@ gsd_linear_small_k_kernel(long long M, int N, int K, const float *__restrict__ x
     gsd_pdl_wait();
     extern __shared__ float sk_smem[];          // [K][N] transposed weights, then [K][SK_ROWS] transposed inputs
     float *sWt = sk_smem, *sxT = sk_smem + (size_t)K * N;
-    const long long m0 = (long long)blockIdx.x * SK_ROWS;
+    // persistent CTAs: the transposed weights (strided, uncoalesced reads) are staged ONCE per CTA, then it walks its row blocks
+    // (staging them per 32-row block cost as much as the block's arithmetic: 23 us for the 20 000 edge rows)
     for (int i = threadIdx.x; i < N * K; i += 256) { const int k = i / N, n = i % N; sWt[i] = __ldg(W + (size_t)n * K + k); }   // conflict-free stores
-    for (int i = threadIdx.x; i < SK_ROWS * K; i += 256) { const int r = i / K, k = i % K; const long long m = m0 + r; sxT[k * SK_ROWS + r] = m < M ? x[m * K + k] : 0.f; }
-    __syncthreads();
     const int n4 = N / 4;
     const int rg = threadIdx.x / 32;             // 8 row groups of 4 rows
-    for (int c = threadIdx.x % 32; c < n4; c += 32) {
-        const float4 b = bias ? __ldg(reinterpret_cast<const float4 *>(bias) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 acc[4] = {b, b, b, b};
-        for (int k = 0; k < K; ++k) {
-            const float4 w = *reinterpret_cast<const float4 *>(sWt + (size_t)k * N + 4 * c);
-            const float4 xv = *reinterpret_cast<const float4 *>(sxT + k * SK_ROWS + 4 * rg);
-            const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+    const long long blocks = (M + SK_ROWS - 1) / SK_ROWS;
+    for (long long blk = blockIdx.x; blk < blocks; blk += gridDim.x) {
+        const long long m0 = blk * SK_ROWS;
+        __syncthreads();                         // the previous block's readers of sxT are done (and sWt is staged)
+        for (int i = threadIdx.x; i < SK_ROWS * K; i += 256) { const int r = i / K, k = i % K; const long long m = m0 + r; sxT[k * SK_ROWS + r] = m < M ? x[m * K + k] : 0.f; }
+        __syncthreads();
+        for (int c = threadIdx.x % 32; c < n4; c += 32) {
+            const float4 b = bias ? __ldg(reinterpret_cast<const float4 *>(bias) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 acc[4] = {b, b, b, b};
+            for (int k = 0; k < K; ++k) {
+                const float4 w = *reinterpret_cast<const float4 *>(sWt + (size_t)k * N + 4 * c);
+                const float4 xv = *reinterpret_cast<const float4 *>(sxT + k * SK_ROWS + 4 * rg);
+                const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    acc[r].x = fmaf(xr[r], w.x, acc[r].x); acc[r].y = fmaf(xr[r], w.y, acc[r].y);
+                    acc[r].z = fmaf(xr[r], w.z, acc[r].z); acc[r].w = fmaf(xr[r], w.w, acc[r].w);
+                }
+            }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                acc[r].x = fmaf(xr[r], w.x, acc[r].x); acc[r].y = fmaf(xr[r], w.y, acc[r].y);
-                acc[r].z = fmaf(xr[r], w.z, acc[r].z); acc[r].w = fmaf(xr[r], w.w, acc[r].w);
+                const long long m = m0 + 4 * rg + r;
+                if (m >= M) break;
+                float4 v = acc[r];
+                if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                reinterpret_cast<float4 *>(out + m * N)[c] = v;
             }
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const long long m = m0 + 4 * rg + r;
-            if (m >= M) break;
-            float4 v = acc[r];
-            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            reinterpret_cast<float4 *>(out + m * N)[c] = v;
         }
     }
 }
@@ -867,7 +873,9 @@ extern "C" int gsd_linear_small(int64_t M, int32_t N, int32_t K, const float *x,
             GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_linear_small_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             attr_done = true;
         }
-        gsd_launch(gsd_linear_small_k_kernel, dim3((unsigned)((M + SK_ROWS - 1) / SK_ROWS)), dim3(256), smem, st, (long long)M, N, K, x, W, bias, relu, out);
+        const long long blocks = (M + SK_ROWS - 1) / SK_ROWS;
+        const unsigned grid = (unsigned)(blocks < 2 * 148 ? blocks : 2 * 148);      // two CTAs per SM (30 KB of shared memory each at N = 512, K = 14)
+        gsd_launch(gsd_linear_small_k_kernel, dim3(grid), dim3(256), smem, st, (long long)M, N, K, x, W, bias, relu, out);
     } else if (N <= 8 && K % 4 == 0 && ldx % 4 == 0 && !relu) {
         gsd_launch(gsd_linear_small_n_kernel, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, st, (long long)M, N, K, x, (long long)ldx, W, bias, out);
     } else {
