@@ -410,6 +410,9 @@ gsd_blend_fwd_finish_kernel(GsdRenderParams p) {
 #pragma unroll
         for (int k = 0; k < CH; ++k) tsw[(TS::C + k) * 256 + t] = C[k];
         reinterpret_cast<int *>(tsw)[TS::LAST * 256 + t] = last;
+        // work list of the replay pass: flag 3 on (item, rectangle).  The look-back flags of pass A are dead by now (this kernel
+        // runs after it); several lanes may store the same value to the same word.
+        p.chunk_flags[(size_t)(item0 + cstar) * GSD_CWARPS + warp] = 3;
         return;
     }
     const size_t pid = (size_t)py * p.W + px;
@@ -440,15 +443,19 @@ gsd_blend_fwd_replay_kernel(GsdRenderParams p) {
     __shared__ __align__(8) uint64_t bar;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     ItemInfo I;
-    if (!item_setup(p, blockIdx.x, warp, lane, I)) return;
-    if (I.chunk == 0) return; // chunk 0 applies the exact rule in pass A
+    if ((int)blockIdx.x >= *p.n_items) return;
+    // pass B flagged the (item, rectangle) pairs that hold a terminating pixel: one 32-byte read tells every warp whether the
+    // item has work at all (most do not) and whether its own rectangle has
+    const int fl = lane < GSD_CWARPS ? p.chunk_flags[(size_t)blockIdx.x * GSD_CWARPS + lane] : 0;
+    const unsigned live = __ballot_sync(0xffffffffu, fl == 3);
+    if (live == 0u) return;
+    item_setup(p, blockIdx.x, warp, lane, I);
     float *ts = p.term_state + (size_t)I.tile * TS::NF * 256;
-    const bool mine = I.inside && reinterpret_cast<const int *>(ts)[TS::CSTAR * 256 + I.pix] == I.chunk;
-    if (!__syncthreads_or(mine ? 1 : 0)) return;
     if (t == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     __syncthreads();
     if (t == 0) load_chunk<NPL>(p, planes, &bar, I.start, I.cnt);
-    if (!__any_sync(0xffffffffu, mine)) return;
+    if (!((live >> warp) & 1u)) return;
+    const bool mine = I.inside && reinterpret_cast<const int *>(ts)[TS::CSTAR * 256 + I.pix] == I.chunk;
     float T = 1.0f, D = 0.f;
     float C[CH];
 #pragma unroll
