@@ -67,7 +67,7 @@ struct GsdBinWs {
     int32_t *tile_base;  // [tiles] exclusive scan of the totals (first slot of the tile's segment)
     uint2 *ranges;       // per tile [start,end) clipped to capacity
     int32_t *chunk_ptr;  // [tiles+1] exclusive scan of chunks per tile
-    int32_t *item_tile;  // [max_items] tile of each work item
+    int4 *item_tile;     // [max_items] work item -> (tile, chunk index in the tile, first record, record count): one 16-byte read per CTA
     int32_t *counters;   // [8] 0: n_items, 1: sort units, 2: tiles with more than one sort unit, 3: "tile bases published" flag
     int32_t *unit_tile;  // [max_units] tile of each sort unit
     int32_t *unit_seg;   // [max_units] segment index of each sort unit inside its tile
@@ -99,7 +99,7 @@ struct GsdRenderParams {
     int64_t plane_stride;
     int W, H, gx, n_tiles;
     const int32_t *chunk_ptr;  // [tiles+1]
-    const int32_t *item_tile;  // [n_items]
+    const int4 *item_tile;     // [n_items] (tile, chunk, first record, record count)
     const int32_t *n_items;    // device scalar
     const int32_t *exec_item;  // [n_items] execution order of the forward chunk kernel
     int32_t *chunk_flags;      // [max_items][8]

@@ -59,7 +59,7 @@ int gsd_carve_bin(int G, int64_t capacity, int tiles, void *base, GsdBinWs *ws) 
     ws->tile_base = (int32_t *)take((size_t)tiles * 4);
     ws->ranges = (uint2 *)take((size_t)tiles * sizeof(uint2));
     ws->chunk_ptr = (int32_t *)take((size_t)(tiles + 1) * 4);
-    ws->item_tile = (int32_t *)take((size_t)ws->max_items * 4);
+    ws->item_tile = (int4 *)take((size_t)ws->max_items * 16);
     ws->counters = (int32_t *)take(8 * 4);
     ws->unit_tile = (int32_t *)take((size_t)ws->max_units * 4);
     ws->unit_seg = (int32_t *)take((size_t)ws->max_units * 4);
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 gsd_bin_scan_kernel(int n_pre_blocks, int n_tiles, int n_bb, int64_t capacity, int max_items, int max_units,
                     const uint32_t *__restrict__ block_sum, uint32_t *__restrict__ block_base, const int32_t *__restrict__ tile_total,
                     int32_t *__restrict__ tile_base, uint2 *__restrict__ ranges, int32_t *__restrict__ chunk_ptr,
-                    int32_t *__restrict__ item_tile, int32_t *__restrict__ counters, int32_t *__restrict__ unit_tile,
+                    int4 *__restrict__ item_tile, int32_t *__restrict__ counters, int32_t *__restrict__ unit_tile,
                     int32_t *__restrict__ unit_seg, int32_t *__restrict__ long_tile, int32_t *__restrict__ exec_item,
                     int32_t *__restrict__ table, int32_t *__restrict__ status, int32_t *__restrict__ sticky) {
     gsd_pdl_wait();
@@ -259,7 +259,15 @@ gsd_bin_scan_kernel(int n_pre_blocks, int n_tiles, int n_bb, int64_t capacity, i
         for (int i = t; i < n_tiles; i += SCAN_THREADS) {
             const int c0 = s_x[i], c1 = c0 + (s_n[i] + GSD_CHUNK - 1) / GSD_CHUNK;
             chunk_ptr[i] = c0;
-            for (int c = c0; c < c1 && c < max_items; ++c) item_tile[c] = i;
+            // everything a blend CTA needs to know about its item in one 16-byte record (was: item -> tile -> chunk_ptr / ranges,
+            // three dependent loads in front of the first TMA of every CTA)
+            long long s = tile_base[i];
+            if (s > capacity) s = capacity;
+            const int rx = (int)s, ry = rx + s_n[i];
+            for (int c = c0; c < c1 && c < max_items; ++c) {
+                const int start = rx + (c - c0) * GSD_CHUNK;
+                item_tile[c] = make_int4(i, c - c0, start, min(GSD_CHUNK, ry - start));
+            }
         }
         return;
     }

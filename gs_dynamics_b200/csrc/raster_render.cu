@@ -79,11 +79,11 @@ struct ItemInfo { int tile, chunk, start, cnt, px, py, pix; bool inside; float r
 
 __device__ __forceinline__ bool item_setup(const GsdRenderParams &p, int item, int warp, int lane, ItemInfo &I) {
     if (item >= *p.n_items) return false;
-    I.tile = p.item_tile[item];
-    I.chunk = item - p.chunk_ptr[I.tile];
-    const uint2 r = p.ranges[I.tile];
-    I.start = (int)r.x + I.chunk * GSD_CHUNK;
-    I.cnt = min(GSD_CHUNK, (int)r.y - I.start);
+    const int4 rec = p.item_tile[item];
+    I.tile = rec.x;
+    I.chunk = rec.y;
+    I.start = rec.z;
+    I.cnt = rec.w;
     const int tx = I.tile % p.gx, ty = I.tile / p.gx;
     const int wx0 = tx * GSD_TILE + (warp & 1) * 8, wy0 = ty * GSD_TILE + (warp >> 1) * 4;
     I.px = wx0 + (lane & 7);
