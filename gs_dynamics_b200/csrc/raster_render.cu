@@ -78,8 +78,9 @@ __device__ __forceinline__ bool cull_pass(const float4 g0, const float4 g1, floa
 struct ItemInfo { int tile, chunk, start, cnt, px, py, pix; bool inside; float rx0, rx1, ry0, ry1; };
 
 __device__ __forceinline__ bool item_setup(const GsdRenderParams &p, int item, int warp, int lane, ItemInfo &I) {
-    if (item >= *p.n_items) return false;
+    const int n_items = *p.n_items;            // the two loads are independent (item < max_items: in bounds): issued together
     const int4 rec = p.item_tile[item];
+    if (item >= n_items) return false;
     I.tile = rec.x;
     I.chunk = rec.y;
     I.start = rec.z;
@@ -139,8 +140,9 @@ gsd_blend_fwd_chunk_kernel(GsdRenderParams p) {
     __shared__ __align__(128) float4 planes[NPL][GSD_CHUNK];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     ItemInfo I;
-    if ((int)blockIdx.x >= *p.n_items) return;
+    const int n_items_l = *p.n_items;          // independent of the next load (exec_item is max_items long): issued together
     const int item = p.exec_item[blockIdx.x];
+    if ((int)blockIdx.x >= n_items_l) return;
     if (!item_setup(p, item, warp, lane, I)) return;
     const bool gone = !I.inside;
     float *st = p.chunk_state + (size_t)item * IS::NF * 256;
