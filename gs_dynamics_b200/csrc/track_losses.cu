@@ -12,9 +12,11 @@
 // summation order (the reference materialises ~15 such temporaries and scatters with index_put atomics).
 // Algorithmic bytes: 56*G*K + 72*G per call; node data is L2-resident.
 #include "common.cuh"
+#include <cstdlib>
 
 struct TrackArgs {
     int Gf, K, Gb;
+    unsigned div_magic; int div_shift;   // e / K == (e * div_magic) >> div_shift for every 31-bit e
     const float *x;        // [G,3] means3D
     const float *q;        // [G,4] normalised rotations
     const int32_t *fg_index; // [Gf] or null (identity)
@@ -63,6 +65,14 @@ __device__ __forceinline__ Quat load_q(const float *p, int i) {
 
 struct EdgeOut { float g_off[3]; float dLde[3]; float g_rel[4]; float s1, s2, s3; };
 
+// MUFU.RSQ: every argument below is >= 1e-20 (normal range), error 2 ulp.  The IEEE sqrtf / division sequences this replaces were
+// 7 x ~15 instructions (+ slow-path calls) of a ~190-instruction edge evaluation; sqrt(a) = a * rsqrt(a), w / sqrt(a) = w * rsqrt(a).
+__device__ __forceinline__ float trk_rsqrt(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // evaluates one edge i -> j; g_off = dL/d(x_j - x_i), dLde = dL/d(R_i^T off - prev), g_rel = dL/d rel_j (= -dL/d rel_i)
 __device__ __forceinline__ void eval_edge(const TrackArgs &a, const float xi[3], const float Ri[3][3], Quat rel_i,
                                           const float xj[3], Quat rel_j, float w, float d0, const float po[3],
@@ -71,29 +81,47 @@ __device__ __forceinline__ void eval_edge(const TrackArgs &a, const float xi[3],
     float e[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) e[c] = Ri[0][c] * off[0] + Ri[1][c] * off[1] + Ri[2][c] * off[2] - po[c];
-    float s1 = sqrtf(w * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) + 1e-20f);
-    float cr = a.c_rigid * w / s1;
+    const float a1 = w * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) + 1e-20f;
+    const float r1 = trk_rsqrt(a1);
+    const float cr = a.c_rigid * w * r1;
 #pragma unroll
     for (int c = 0; c < 3; ++c) o.dLde[c] = cr * e[c];
 #pragma unroll
     for (int b = 0; b < 3; ++b) o.g_off[b] = Ri[b][0] * o.dLde[0] + Ri[b][1] * o.dLde[1] + Ri[b][2] * o.dLde[2];
     float d[4] = {rel_j.w - rel_i.w, rel_j.x - rel_i.x, rel_j.y - rel_i.y, rel_j.z - rel_i.z};
-    float s2 = sqrtf(w * (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]) + 1e-20f);
-    float crot = a.c_rot * w / s2;
+    const float a2 = w * (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]) + 1e-20f;
+    const float r2 = trk_rsqrt(a2);
+    const float crot = a.c_rot * w * r2;
 #pragma unroll
     for (int c = 0; c < 4; ++c) o.g_rel[c] = crot * d[c];
-    float m = sqrtf(off[0] * off[0] + off[1] * off[1] + off[2] * off[2] + 1e-20f);
-    float dm = m - d0;
-    float s3 = sqrtf(w * dm * dm + 1e-20f);
-    float ciso = a.c_iso * w * dm / (s3 * m);
+    const float m2 = off[0] * off[0] + off[1] * off[1] + off[2] * off[2] + 1e-20f;
+    const float rm = trk_rsqrt(m2);
+    const float dm = m2 * rm - d0;
+    const float a3 = w * dm * dm + 1e-20f;
+    const float r3 = trk_rsqrt(a3);
+    const float ciso = a.c_iso * w * dm * r3 * rm;
 #pragma unroll
     for (int c = 0; c < 3; ++c) o.g_off[c] += ciso * off[c];
-    o.s1 = s1; o.s2 = s2; o.s3 = s3;
+    o.s1 = a1 * r1; o.s2 = a2 * r2; o.s3 = a3 * r3;
 }
 
 // 4 lanes per foreground point (each takes every 4th out-/in-edge, fixed-order quad reduction): 4x more warps in flight and
 // 4x shorter serial gather chains than one thread per point — the kernel is latency-bound on dependent gathers.
 #define TRK_SPLIT 4
+// Gathers in flight per lane (out-edges / in-edges) and resident CTAs per SM, measured inside the tracking iteration at 100k
+// (tools/step_ablate.py; the kernel runs on a side branch of the iteration's graph and competes with the render branch):
+// (5, 3, 4 CTAs: 112 registers) 334.7 us per iteration, (5, 2, 6) 329.1, (3, 2, 7) 327.0, (2, 2, 8) 326.1, (3, 2, 8: 64 registers,
+// 36 bytes of spills) 325.8 — occupancy beats loads in flight once each record is one load instruction.
+#ifndef TRK_UO
+#define TRK_UO 3
+#endif
+#ifndef TRK_UI
+#define TRK_UI 2
+#endif
+#ifndef TRK_MIN_CTAS
+#define TRK_MIN_CTAS 8
+#endif
+#define GSD_PRIORS_CTAS_PER_SM_DEFAULT 0
 __global__ void __launch_bounds__(128)
 gsd_track_fg_kernel(TrackArgs a) {
     gsd_pdl_wait();
@@ -215,8 +243,20 @@ gsd_track_fg_kernel(TrackArgs a) {
 // ---- packed variant -----------------------------------------------------------------------------------------------
 // Per iteration a tiny kernel writes one 32-byte record per foreground point: (x, y, z, 0 | rel = q (x) prev_inv_q); the static
 // per-edge tables are packed once per timestep into 32-byte records (neighbour id, weight, rest distance, previous offset).
-// Every edge evaluation is then two sector-aligned float4 pairs (edge record + neighbour record) instead of ~10 scattered
-// 4..16-byte loads and a quaternion product: 4x fewer L1 sectors (17.7M -> ~4.5M per call at G = 50k, K = 20).
+// Every edge evaluation is then two 32-byte-aligned 256-bit loads (edge record + node record) instead of ~10 scattered 4..16-byte
+// loads and a quaternion product.  The kernel is bound by the L1 tag stage — a gather instruction costs one pass per distinct
+// 128-byte line its lanes touch (ncu: L1/TEX throughput 89 %, DRAM 16 %, issue slots 27 %) — so what counts is the number of
+// load INSTRUCTIONS per edge: one LDG.256 per record (two LDG.128 per record + a 64-byte node record with the rotation matrix
+// precomputed measured 65-72 us whatever the occupancy or the number of loads in flight).
+struct F8 { float4 a, b; };
+__device__ __forceinline__ F8 ldg256(const float4 *p) {   // p 32-byte aligned; read-only data
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+                 : "l"(p));
+    return r;
+}
+
 __global__ void __launch_bounds__(256)
 gsd_track_node_prep_kernel(TrackArgs a, float4 *__restrict__ node) {
     gsd_pdl_wait();
@@ -229,12 +269,18 @@ gsd_track_node_prep_kernel(TrackArgs a, float4 *__restrict__ node) {
     node[2 * (size_t)f + 1] = make_float4(rel.w, rel.x, rel.y, rel.z);
 }
 
-__global__ void __launch_bounds__(128)
-gsd_track_fg_packed_kernel(TrackArgs a, const float4 *__restrict__ node, const float4 *__restrict__ edge) {
+__global__ void __launch_bounds__(128, TRK_MIN_CTAS)
+gsd_track_fg_packed_kernel(TrackArgs a, const float4 *__restrict__ node, const float4 *__restrict__ edge, int n_vblocks) {
     gsd_pdl_wait();
     gsd_pdl_launch();
     __shared__ float red[4][4];
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    // the grid may be smaller than the number of 128-thread blocks of work (see gsd_track_losses_fwd_bwd): a CTA then walks a
+    // CONTIGUOUS run of virtual blocks (consecutive blocks are neighbours on the Morton curve: the node records one block pulled
+    // into L1 are the next block's neighbours too); sums are kept per virtual block (fixed order, grid-independent)
+    const int vb_per = (n_vblocks + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int vb_end = min(n_vblocks, ((int)blockIdx.x + 1) * vb_per);
+    for (int vb = blockIdx.x * vb_per; vb < vb_end; ++vb) {
+    const int tid = vb * blockDim.x + threadIdx.x;
     const int f = tid / TRK_SPLIT, sub = tid % TRK_SPLIT;
     float s_rigid = 0.f, s_rot = 0.f, s_iso = 0.f, s_floor = 0.f;
     const bool active = f < a.Gf;
@@ -244,51 +290,75 @@ gsd_track_fg_packed_kernel(TrackArgs a, const float4 *__restrict__ node, const f
     float gx[3] = {0.f, 0.f, 0.f}, grel[4] = {0.f, 0.f, 0.f, 0.f};
     float Gm[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
     if (active) {
-        const float4 n0 = node[2 * (size_t)f], n1 = node[2 * (size_t)f + 1];
-        xi[0] = n0.x; xi[1] = n0.y; xi[2] = n0.z;
-        const Quat rel_i = {n1.x, n1.y, n1.z, n1.w};
-        inv_n = rsqrtf(rel_i.w * rel_i.w + rel_i.x * rel_i.x + rel_i.y * rel_i.y + rel_i.z * rel_i.z);
+        const F8 n0 = ldg256(node + 2 * (size_t)f);
+        xi[0] = n0.a.x; xi[1] = n0.a.y; xi[2] = n0.a.z;
+        const Quat rel_i = {n0.b.x, n0.b.y, n0.b.z, n0.b.w};
+        inv_n = trk_rsqrt(rel_i.w * rel_i.w + rel_i.x * rel_i.x + rel_i.y * rel_i.y + rel_i.z * rel_i.z);
         n_i = Quat{rel_i.w * inv_n, rel_i.x * inv_n, rel_i.y * inv_n, rel_i.z * inv_n};
         float Ri[3][3];
         rot_from_unit(n_i, Ri);
-        for (int k = sub; k < a.K; k += TRK_SPLIT) {
-            const size_t e = (size_t)f * a.K + k;
-            const float4 e0 = edge[2 * e], e1 = edge[2 * e + 1];
-            const int j = __float_as_int(e0.x);
-            const float4 m0 = node[2 * (size_t)j], m1 = node[2 * (size_t)j + 1];
-            const float xj[3] = {m0.x, m0.y, m0.z};
-            const float po[3] = {e0.w, e1.x, e1.y};
-            EdgeOut o;
-            eval_edge(a, xi, Ri, rel_i, xj, Quat{m1.x, m1.y, m1.z, m1.w}, e0.y, e0.z, po, o);
-            const float off[3] = {xj[0] - xi[0], xj[1] - xi[1], xj[2] - xi[2]};
+        // The loads of TRK_UO / TRK_UI edges are issued together, then the arithmetic runs.  Slots past the end re-read a valid
+        // record and are skipped in the arithmetic.
+        for (int k0 = sub; k0 < a.K; k0 += TRK_SPLIT * TRK_UO) {
+            F8 E[TRK_UO], M[TRK_UO];
 #pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                gx[b] -= o.g_off[b];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) Gm[b][c] += off[b] * o.dLde[c];
+            for (int u = 0; u < TRK_UO; ++u) {
+                const int k = k0 + TRK_SPLIT * u;
+                E[u] = ldg256(edge + 2 * ((size_t)f * a.K + (k < a.K ? k : k0)));
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) grel[c] -= o.g_rel[c];
-            s_rigid += o.s1; s_rot += o.s2; s_iso += o.s3;
+            for (int u = 0; u < TRK_UO; ++u) M[u] = ldg256(node + 2 * (size_t)__float_as_int(E[u].a.x));
+#pragma unroll
+            for (int u = 0; u < TRK_UO; ++u) {
+                if (k0 + TRK_SPLIT * u >= a.K) break;
+                const float xj[3] = {M[u].a.x, M[u].a.y, M[u].a.z};
+                const float po[3] = {E[u].a.w, E[u].b.x, E[u].b.y};
+                EdgeOut o;
+                eval_edge(a, xi, Ri, rel_i, xj, Quat{M[u].b.x, M[u].b.y, M[u].b.z, M[u].b.w}, E[u].a.y, E[u].a.z, po, o);
+                const float off[3] = {xj[0] - xi[0], xj[1] - xi[1], xj[2] - xi[2]};
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    gx[b] -= o.g_off[b];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) Gm[b][c] += off[b] * o.dLde[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) grel[c] -= o.g_rel[c];
+                s_rigid += o.s1; s_rot += o.s2; s_iso += o.s3;
+            }
         }
         const int t0 = a.in_ptr[f], t1 = a.in_ptr[f + 1];
-        for (int t = t0 + sub; t < t1; t += TRK_SPLIT) {
-            const int e = a.in_edge[t];
-            const int i2 = e / a.K;
-            const float4 e0 = edge[2 * (size_t)e], e1 = edge[2 * (size_t)e + 1];
-            const float4 m0 = node[2 * (size_t)i2], m1 = node[2 * (size_t)i2 + 1];
-            const float x2[3] = {m0.x, m0.y, m0.z};
-            const Quat rel_2 = {m1.x, m1.y, m1.z, m1.w};
-            const float n2 = rsqrtf(rel_2.w * rel_2.w + rel_2.x * rel_2.x + rel_2.y * rel_2.y + rel_2.z * rel_2.z);
-            float R2[3][3];
-            rot_from_unit(Quat{rel_2.w * n2, rel_2.x * n2, rel_2.y * n2, rel_2.z * n2}, R2);
-            const float po[3] = {e0.w, e1.x, e1.y};
-            EdgeOut o;
-            eval_edge(a, x2, R2, rel_2, xi, rel_i, e0.y, e0.z, po, o);
+        for (int tb = t0 + sub; tb < t1; tb += TRK_SPLIT * TRK_UI) {
+            int Ei[TRK_UI];
+            F8 E[TRK_UI], M[TRK_UI];
 #pragma unroll
-            for (int b = 0; b < 3; ++b) gx[b] += o.g_off[b];
+            for (int u = 0; u < TRK_UI; ++u) {
+                const int t = tb + TRK_SPLIT * u;
+                Ei[u] = a.in_edge[t < t1 ? t : tb];
+            }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) grel[c] += o.g_rel[c];
+            for (int u = 0; u < TRK_UI; ++u) {
+                // e / K by multiplication (exact for every 31-bit e: magic = ceil(2^shift / K) < 2^32 and e K < 2^shift)
+                const int i2 = (int)(((unsigned long long)(unsigned)Ei[u] * a.div_magic) >> a.div_shift);
+                E[u] = ldg256(edge + 2 * (size_t)Ei[u]);
+                M[u] = ldg256(node + 2 * (size_t)i2);
+            }
+#pragma unroll
+            for (int u = 0; u < TRK_UI; ++u) {
+                if (tb + TRK_SPLIT * u >= t1) break;
+                const float x2[3] = {M[u].a.x, M[u].a.y, M[u].a.z};
+                const Quat rel_2 = {M[u].b.x, M[u].b.y, M[u].b.z, M[u].b.w};
+                const float n2 = trk_rsqrt(rel_2.w * rel_2.w + rel_2.x * rel_2.x + rel_2.y * rel_2.y + rel_2.z * rel_2.z);
+                float R2[3][3];
+                rot_from_unit(Quat{rel_2.w * n2, rel_2.x * n2, rel_2.y * n2, rel_2.z * n2}, R2);
+                const float po[3] = {E[u].a.w, E[u].b.x, E[u].b.y};
+                EdgeOut o;
+                eval_edge(a, x2, R2, rel_2, xi, rel_i, E[u].a.y, E[u].a.z, po, o);
+#pragma unroll
+                for (int b = 0; b < 3; ++b) gx[b] += o.g_off[b];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) grel[c] += o.g_rel[c];
+            }
         }
     }
 #pragma unroll
@@ -329,8 +399,10 @@ gsd_track_fg_packed_kernel(TrackArgs a, const float4 *__restrict__ node, const f
 #pragma unroll
         for (int c = 0; c < 4; ++c) red[threadIdx.x >> 5][c] = v[c];
     __syncthreads();
-    if (threadIdx.x < 4) a.block_sums[5 * (size_t)blockIdx.x + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
-    if (threadIdx.x == 4) a.block_sums[5 * (size_t)blockIdx.x + 4] = 0.f;
+    if (threadIdx.x < 4) a.block_sums[5 * (size_t)vb + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    if (threadIdx.x == 4) a.block_sums[5 * (size_t)vb + 4] = 0.f;
+    __syncthreads();   // red[] is reused by the next virtual block
+    }
 }
 
 // packs the static per-edge tables into 32-byte records (once per timestep: prev_offset changes with the frame)
@@ -436,10 +508,18 @@ extern "C" int gsd_track_losses_fwd_bwd(const GsdTrackLosses *t, void *stream) {
     }
     if (t->Gb > 0 && (!t->bg_index || !t->init_bg_pts || !t->init_bg_rot)) { gsd_set_error("null background input"); return GSD_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    GSD_CUDA_CHECK(cudaMemsetAsync(t->grad_means3D, 0, (size_t)t->G * 3 * 4, st));
-    GSD_CUDA_CHECK(cudaMemsetAsync(t->grad_rotations, 0, (size_t)t->G * 4 * 4, st));
+    if ((long long)t->Gf + t->Gb != t->G) {   // foreground + background cover every Gaussian (is_fg / ~is_fg): each row is written once below
+        GSD_CUDA_CHECK(cudaMemsetAsync(t->grad_means3D, 0, (size_t)t->G * 3 * 4, st));
+        GSD_CUDA_CHECK(cudaMemsetAsync(t->grad_rotations, 0, (size_t)t->G * 4 * 4, st));
+    }
     TrackArgs a;
     a.Gf = t->Gf; a.K = t->K; a.Gb = t->Gb;
+    {
+        int lg = 0;
+        while ((1ll << lg) < (long long)(t->K > 0 ? t->K : 1)) ++lg;
+        a.div_shift = 31 + lg;
+        a.div_magic = (unsigned)(((1ull << a.div_shift) + (unsigned long long)(t->K > 0 ? t->K : 1) - 1) / (unsigned long long)(t->K > 0 ? t->K : 1));
+    }
     a.x = t->means3D; a.q = t->rotations; a.fg_index = t->fg_index; a.prev_inv = t->prev_inv_rot;
     a.nbr = t->neighbor_indices; a.nbr_w = t->neighbor_weight; a.nbr_d = t->neighbor_dist; a.prev_off = t->prev_offset;
     a.in_ptr = t->in_ptr; a.in_edge = t->in_edge;
@@ -458,7 +538,14 @@ extern "C" int gsd_track_losses_fwd_bwd(const GsdTrackLosses *t, void *stream) {
         float4 *node = (float4 *)((char *)t->ws + gsd_align_up(rows * 5 * 4));
         gsd_launch(gsd_track_node_prep_kernel, dim3((t->Gf + 255) / 256), dim3(256), 0, st, a, node);
         GSD_LAUNCH_CHECK();
-        gsd_launch(gsd_track_fg_packed_kernel, dim3(fgb), dim3(128), 0, st, a, node, (const float4 *)t->edge_records);
+        // Optional resident-CTA cap (a grid of SMs x cap CTAs walking contiguous runs of the work).  Measured inside the tracking
+        // iteration, where this kernel runs on a side branch beside the render branch: every cap is slower than the plain grid
+        // (cap 1 / 2 / 4 / 6 / 8: +90 / +55 / +10 / +6 / +1 us per iteration) — the kernel's cost to the iteration is its own
+        // machine time, not the placement of the other branch's CTAs.  Kept as a tuning switch, off by default.
+        const char *cap_env = getenv("GSD_PRIORS_CTAS_PER_SM");   // tuning override (tools/step_ablate.py)
+        const int cap = cap_env ? atoi(cap_env) : GSD_PRIORS_CTAS_PER_SM_DEFAULT;
+        const int grid = cap > 0 ? (fgb < 148 * cap ? fgb : 148 * cap) : fgb;
+        gsd_launch(gsd_track_fg_packed_kernel, dim3(grid), dim3(128), 0, st, a, node, (const float4 *)t->edge_records, fgb);
         GSD_LAUNCH_CHECK();
     } else if (fgb > 0) {
         gsd_launch(gsd_track_fg_kernel, dim3(fgb), dim3(128), 0, st, a);

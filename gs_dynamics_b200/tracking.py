@@ -167,8 +167,14 @@ def _track_priors_launch(means3D, rotations, variables, weights):
     t.neighbor_dist, t.prev_offset = ptr(v["neighbor_dist"]), ptr(v["prev_offset"])
     t.in_ptr, t.in_edge = ptr(v["in_ptr"]), ptr(v["in_edge"])
     er = v.get("edge_records")
-    if er is not None and er.get("src") is v["prev_offset"] and er.get("ver") == v["prev_offset"]._version:
+    if (er is not None and er.get("src") is v["prev_offset"] and er.get("ver") == v["prev_offset"]._version
+            and er.get("src_inv") is v["prev_inv_rot_fg"] and er.get("ver_inv") == v["prev_inv_rot_fg"]._version
+            and er["layout"]["src"] is v["neighbor_indices_i32"]):
+        # packed tables: the foreground set re-numbered along a Morton curve (see _priors_layout)
+        lay = er["layout"]
         t.edge_records = er["data"].data_ptr()
+        t.fg_index, t.prev_inv_rot = ptr(lay["fg_index"]), ptr(lay["prev_inv"])
+        t.in_ptr, t.in_edge = ptr(lay["in_ptr"]), ptr(lay["in_edge"])
     t.bg_index, t.init_bg_pts, t.init_bg_rot = ptr(bg), ptr(v.get("init_bg_pts")), ptr(v.get("init_bg_rot"))
     t.w_rigid, t.w_rot, t.w_iso, t.w_floor, t.w_bg = [float(w) for w in weights]
     nbytes = C.c_size_t()
@@ -198,21 +204,69 @@ class _TrackPriors(torch.autograd.Function):
         return gx * g_total, gq * g_total, None, None
 
 
-def pack_edge_records(variables):
-    """Packs the per-edge tables into 32-byte records for the priors kernel. Call after prev_offset changed (once per
-    timestep); a stale pack is detected (tensor identity + version) and ignored.  The record buffer is reused across calls."""
+def _morton_order(pts):
+    """Permutation that sorts points along a 30-bit Morton curve of their bounding box (10 bits per axis)."""
+    lo, hi = pts.min(0).values, pts.max(0).values
+    q = ((pts - lo) / (hi - lo).clamp_min(1e-12) * 1023.0).long().clamp_(0, 1023)
+
+    def spread(x):
+        x = (x | (x << 16)) & 0x030000FF
+        x = (x | (x << 8)) & 0x0300F00F
+        x = (x | (x << 4)) & 0x030C30C3
+        x = (x | (x << 2)) & 0x09249249
+        return x
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+    return torch.argsort(code, stable=True)
+
+
+def _priors_layout(v, positions):
+    """Static part of the packed priors tables (the kNN graph never changes after frame 0, train_utils.py:354-368): the foreground
+    points re-numbered along a Morton curve.  The priors kernel is bound by the gathers of its neighbours' records; in curve
+    order a warp's points share most of their neighbours, so those gathers hit L1 / the same L2 sectors (the Gaussians
+    themselves keep the caller's order: the kernel reads and writes them through fg_index)."""
+    nbr = v["neighbor_indices_i32"]
+    lay = v.get("priors_layout")
+    if lay is not None and lay["src"] is nbr and lay["ver"] == nbr._version:
+        return lay
+    Gf, K = nbr.shape
+    dev = nbr.device
+    fg = v.get("fg_index")
+    fg_l = torch.arange(Gf, device=dev) if fg is None else fg.long()
+    if positions is None:
+        positions = v.get("prev_pts")
+    if Gf > 0 and positions is not None and torch.is_tensor(positions) and positions.is_cuda and positions.shape[0] > int(fg_l.max()):
+        perm = _morton_order(positions.detach()[fg_l].float())
+    else:
+        perm = torch.arange(Gf, device=dev)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(Gf, device=dev)
+    nbr_p = inv[nbr.long()[perm]].to(torch.int32).contiguous()          # row f' = old row perm[f'], entries renamed
+    in_ptr, in_edge = build_in_edges(nbr_p)
+    lay = dict(src=nbr, ver=nbr._version, perm=perm, nbr=nbr_p, w=v["neighbor_weight"][perm].contiguous(),
+               d=v["neighbor_dist"][perm].contiguous(), fg_index=fg_l[perm].to(torch.int32).contiguous(), in_ptr=in_ptr, in_edge=in_edge,
+               prev_offset=torch.empty((Gf, K, 3), dtype=torch.float32, device=dev),
+               prev_inv=torch.empty((Gf, 4), dtype=torch.float32, device=dev),
+               data=torch.empty((Gf * K, 8), dtype=torch.float32, device=dev))
+    v["priors_layout"] = lay
+    return lay
+
+
+def pack_edge_records(variables, positions=None):
+    """Packs the per-edge tables into 32-byte records for the priors kernel, in the Morton order of `positions` ([G,3] means;
+    default variables['prev_pts']; neither: caller's order).  Call after prev_offset / prev_inv_rot_fg changed (once per
+    timestep); a stale pack is detected (tensor identity + version) and ignored.  All buffers are reused across calls (a captured
+    CUDA graph keeps reading them on the following frames)."""
     v = variables
     Gf, K = v["neighbor_indices_i32"].shape
-    old = v.get("edge_records")
-    if old is not None and old["data"].shape == (Gf * K, 8) and old["data"].device == v["prev_offset"].device:
-        out = old["data"]   # in place: a captured CUDA graph keeps reading this buffer on the following frames
-    else:
-        out = torch.empty((Gf * K, 8), dtype=torch.float32, device=v["prev_offset"].device)
+    lay = _priors_layout(v, positions)
+    torch.index_select(v["prev_offset"], 0, lay["perm"], out=lay["prev_offset"])
+    torch.index_select(v["prev_inv_rot_fg"], 0, lay["perm"], out=lay["prev_inv"])
+    out = lay["data"]
     with torch.cuda.device(out.device):
-        _lib.check(_lib.lib().gsd_track_pack_edges(Gf, K, v["neighbor_indices_i32"].data_ptr(), v["neighbor_weight"].data_ptr(),
-                                                   v["neighbor_dist"].data_ptr(), v["prev_offset"].data_ptr(), out.data_ptr(),
-                                                   _stream()), "gsd_track_pack_edges")
-    v["edge_records"] = dict(data=out, src=v["prev_offset"], ver=v["prev_offset"]._version)
+        _lib.check(_lib.lib().gsd_track_pack_edges(Gf, K, lay["nbr"].data_ptr(), lay["w"].data_ptr(), lay["d"].data_ptr(),
+                                                   lay["prev_offset"].data_ptr(), out.data_ptr(), _stream()), "gsd_track_pack_edges")
+    v["edge_records"] = dict(data=out, src=v["prev_offset"], ver=v["prev_offset"]._version, src_inv=v["prev_inv_rot_fg"],
+                             ver_inv=v["prev_inv_rot_fg"]._version, layout=lay)
     return v
 
 
@@ -540,7 +594,7 @@ class TrackingStep:
         for c in cam_ids:
             g = torch.cuda.CUDAGraph()
             self.optimizer.zero_grad(set_to_none=True)
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=getattr(self, 'capture_stream', None)):
                 self.losses[c] = self._iteration(self.dataset[c], self.capacity[c])
             self.graphs[c] = g
         self.sticky.zero_()
@@ -599,6 +653,7 @@ class FusedTrackingStep(TrackingStep):
             self.tstats = [target_stats(tg) for tg in self.targets]
         self.outputs = {}
         self.side = torch.cuda.Stream(device=params['means3D'].device)
+        self.priors_fork = 'start'   # where the priors branch forks off the render branch: 'start' | 'after_forward'
         self.block_counter = torch.zeros(1, dtype=torch.int32, device=params['means3D'].device)   # self-resetting (gsd_track_update)
         self.lr = {g['name']: float(g['lr']) for g in optimizer.param_groups}
 
@@ -634,20 +689,28 @@ class FusedTrackingStep(TrackingStep):
             # the physical priors depend only on the parameters, not on the render: they run on a side stream concurrently
             # with binning / sorting / blending (fork-join, captured as parallel branches of the CUDA graph)
             main = torch.cuda.current_stream()
-            fork = torch.cuda.Event()
-            fork.record(main)
-            with torch.cuda.stream(self.side):
-                self.side.wait_event(fork)
-                parts, gx_p, gq_p = _track_priors_launch(x.detach(), self.rot, V, (self.w['weight_rigid'], self.w['weight_rot'],
-                                                         self.w['weight_iso'], FLOOR_WEIGHT, self.w['weight_bg']))
-                prior = parts[5]
-                join = torch.cuda.Event()
-                join.record(self.side)
-            for tns in (prior, parts, gx_p, gq_p):
-                tns.record_stream(main)
+
+            def launch_priors():
+                fork = torch.cuda.Event()
+                fork.record(main)
+                with torch.cuda.stream(self.side):
+                    self.side.wait_event(fork)
+                    parts, gx_p, gq_p = _track_priors_launch(x.detach(), self.rot, V, (self.w['weight_rigid'], self.w['weight_rot'],
+                                                             self.w['weight_iso'], FLOOR_WEIGHT, self.w['weight_bg']))
+                    join = torch.cuda.Event()
+                    join.record(self.side)
+                for tns in (parts, gx_p, gq_p):
+                    tns.record_stream(main)
+                return parts, gx_p, gq_p, join
+
+            if self.priors_fork == 'start':
+                parts, gx_p, gq_p, join = launch_priors()
             color, radii, _, state = R.raster_forward(data['cam'], x.detach(), self.opac, self.rgb, self.scales, self.rot,
                                                       colors1=self.seg, capacity=capacity,
                                                       sticky=self.sticky if capacity is not None else None)
+            if self.priors_fork == 'after_forward':
+                parts, gx_p, gq_p, join = launch_priors()
+            prior = parts[5]
             ws = _ph_workspace(color)
             ph = torch.empty(8, dtype=torch.float32, device=x.device)
             d = _ph_desc(color, tgt, 2, 0.8, 0.2, (self.w['weight_im'], self.w['weight_seg']), ws,

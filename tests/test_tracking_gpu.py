@@ -111,11 +111,18 @@ def test_priors_packed_edge_records_match_unpacked_tables():
     t0.backward()
     gx0, gq0 = x.grad.clone(), q.grad.clone()
     x.grad = None; q.grad = None
-    TR.pack_edge_records(v)
-    t1, p1 = TR.track_prior_losses(x, q, v, 200.0, 4.0, 1000.0, 200.0)
-    t1.backward()
-    assert float((p1 - p0).abs().max()) <= 1e-6 * float(p0.abs().max())
-    assert rel_err(x.grad.cpu(), gx0.cpu()) < 1e-5 and rel_err(q.grad.cpu(), gq0.cpu()) < 1e-5
+    # packed tables in the caller's order, then re-numbered along the Morton curve of the means (what the episode loop uses)
+    for positions in (None, x.detach()):
+        v.pop("priors_layout", None)
+        TR.pack_edge_records(v, positions=positions)
+        lay = v["edge_records"]["layout"]
+        ident = bool((lay["perm"] == torch.arange(lay["perm"].numel(), device="cuda")).all())
+        assert ident == (positions is None)
+        x.grad = None; q.grad = None
+        t1, p1 = TR.track_prior_losses(x, q, v, 200.0, 4.0, 1000.0, 200.0)
+        t1.backward()
+        assert float((p1 - p0).abs().max()) <= 2e-6 * float(p0.abs().max())
+        assert rel_err(x.grad.cpu(), gx0.cpu()) < 1e-5 and rel_err(q.grad.cpu(), gq0.cpu()) < 1e-5
     # a stale pack (prev_offset modified afterwards) must not be used
     v["prev_offset"].mul_(1.0)
     assert v["edge_records"]["ver"] != v["prev_offset"]._version
