@@ -3,6 +3,7 @@
 // (/root/reference/src/tracking/train_utils.py:152-164, train_gs.py:38-39) and the boolean-mask indexing of
 // train_utils.py:243-245 (which forces host syncs).  HBM-bound: 16 B read + 12 B written per parameter.
 #include "common.cuh"
+#include "track_update.cuh"
 
 struct AdamTable {
     float *param[GSD_ADAM_MAX_TENSORS];
@@ -116,44 +117,6 @@ extern "C" int gsd_track_normalize_rotations(int32_t G, const float *unnorm, flo
     return GSD_OK;
 }
 
-__device__ __forceinline__ float adam_1(float p, float g, float &m, float &v, float b1, float b2, float eps, float lr_bc1, float inv_sqrt_bc2) {
-    m = b1 * m + (1.f - b1) * g;
-    v = b2 * v + (1.f - b2) * g * g;
-    return p - lr_bc1 * (m / (sqrtf(v) * inv_sqrt_bc2 + eps));
-}
-
-__device__ __forceinline__ void gsd_track_update_body(const GsdTrackUpdate &u, int i) {
-    if (i >= u.G) return;
-    const float sm = *u.step_means + 1.f, sr = *u.step_rot + 1.f;
-    const float lrm = u.lr_means / (1.f - powf(u.beta1, sm)), ism = 1.f / sqrtf(1.f - powf(u.beta2, sm));
-    const float lrr = u.lr_rot / (1.f - powf(u.beta1, sr)), isr = 1.f / sqrtf(1.f - powf(u.beta2, sr));
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const size_t k = 3 * (size_t)i + c;
-        float g = u.g_means_a[k] + (u.g_means_b ? u.g_means_b[k] : 0.f);
-        float m = u.m_means[k], v = u.v_means[k];
-        u.means3D[k] = adam_1(u.means3D[k], g, m, v, u.beta1, u.beta2, u.eps, lrm, ism);
-        u.m_means[k] = m; u.v_means[k] = v;
-    }
-    float4 q = reinterpret_cast<const float4 *>(u.unnorm_rotations)[i];
-    float4 ga = reinterpret_cast<const float4 *>(u.g_rot_a)[i];
-    if (u.g_rot_b) {
-        float4 gb = reinterpret_cast<const float4 *>(u.g_rot_b)[i];
-        ga.x += gb.x; ga.y += gb.y; ga.z += gb.z; ga.w += gb.w;
-    }
-    const float n = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
-    const float4 qn = make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
-    const float dot = qn.x * ga.x + qn.y * ga.y + qn.z * ga.z + qn.w * ga.w;
-    const float gq[4] = {(ga.x - qn.x * dot) / n, (ga.y - qn.y * dot) / n, (ga.z - qn.z * dot) / n, (ga.w - qn.w * dot) / n};
-    float4 m4 = reinterpret_cast<float4 *>(u.m_rot)[i], v4 = reinterpret_cast<float4 *>(u.v_rot)[i];
-    float qo[4] = {q.x, q.y, q.z, q.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) qo[c] = adam_1(qo[c], gq[c], mm[c], vv[c], u.beta1, u.beta2, u.eps, lrr, isr);
-    reinterpret_cast<float4 *>(u.unnorm_rotations)[i] = make_float4(qo[0], qo[1], qo[2], qo[3]);
-    reinterpret_cast<float4 *>(u.m_rot)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
-    reinterpret_cast<float4 *>(u.v_rot)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-}
-
 // the per-Gaussian update + (optionally) the radii bookkeeping and the step advance in ONE launch: the last CTA to retire
 // advances the step counters (every thread has read them by then) and re-arms the counter
 __global__ void __launch_bounds__(256)
@@ -161,24 +124,9 @@ gsd_track_update_fused_kernel(GsdTrackUpdate u) {
     gsd_pdl_wait();
     gsd_pdl_launch();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < u.G && u.radii) {
-        const int r = u.radii[i];
-        const bool s = r > 0;
-        if (u.seen) u.seen[i] = s ? 1 : 0;
-        if (s) u.max_2D_radius[i] = fmaxf((float)r, u.max_2D_radius[i]);
-    }
+    gsd_track_update_radii_1(u, i);
     gsd_track_update_body(u, i);
-    if (u.block_counter) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            if (atomicAdd(u.block_counter, 1u) == gridDim.x - 1) {
-                *u.step_means += 1.0f;
-                if (u.step_rot != u.step_means) *u.step_rot += 1.0f;
-                *u.block_counter = 0u;
-            }
-        }
-    }
+    gsd_track_update_advance(u);
 }
 __global__ void gsd_track_update_advance_kernel(float *a, float *b) {
     gsd_pdl_wait();

@@ -13,6 +13,7 @@ int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const Gs
 int gsd_launch_render_fwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st);
 int gsd_launch_render_bwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st);
 int gsd_launch_preprocess_bwd(int G, const GsdCam &cam, const GsdRasterBwd *a, const GsdGeomWs &g, int geom_only, cudaStream_t st);
+int gsd_launch_preprocess_bwd_update(int G, const GsdCam &cam, const GsdRasterBwd *a, const GsdGeomWs &g, const GsdTrackUpdate &u, cudaStream_t st);
 
 #include <atomic>
 static thread_local char g_err[512] = "";
@@ -132,21 +133,38 @@ extern "C" int gsd_raster_forward(const GsdRasterFwd *a, void *stream) {
     return gsd_launch_render_fwd(p, tiles, a->n_sets, st);
 }
 
-static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages);
+static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages, const GsdTrackUpdate *fused = nullptr);
 extern "C" int gsd_raster_backward(const GsdRasterBwd *a, void *stream) { return raster_backward_impl(a, stream, 3); }
+// steady-state tracking: blend backward (geometry-only) + ONE per-Gaussian kernel that turns the partial records into the
+// gradients of means3D / rotations and applies gsd_track_update to them in registers (no gradient arrays, one launch less)
+extern "C" int gsd_track_backward_update(const GsdRasterBwd *a, const GsdTrackUpdate *u, void *stream) {
+    if (!a || !u) { gsd_set_error("null descriptor"); return GSD_ERR_INVALID; }
+    if (a->dL_dcolors0 || a->dL_dcolors1 || a->dL_dopacities || a->dL_dmeans2D) {
+        gsd_set_error("gsd_track_backward_update is the geometry-only backward: colour / opacity / means2D gradient outputs must be NULL");
+        return GSD_ERR_INVALID;
+    }
+    if (u->G != a->fwd.G) { gsd_set_error("GsdTrackUpdate.G differs from the rasterizer's G"); return GSD_ERR_INVALID; }
+    if (u->G > 0 && (!u->means3D || !u->unnorm_rotations || !u->m_means || !u->v_means || !u->m_rot || !u->v_rot || !u->step_means ||
+                     !u->step_rot || !u->block_counter)) {
+        gsd_set_error("null pointer in GsdTrackUpdate (block_counter is required by the fused kernel)");
+        return GSD_ERR_INVALID;
+    }
+    if (u->radii && !u->max_2D_radius) { gsd_set_error("radii given without max_2D_radius"); return GSD_ERR_INVALID; }
+    return raster_backward_impl(a, stream, 3, u);
+}
 // stage 1: blend backward only (the dominant kernel, timed alone for the roofline); stage 2: per-Gaussian backward only
 extern "C" int gsd_raster_backward_stage(const GsdRasterBwd *a, int32_t stage, void *stream) {
     if (stage != 1 && stage != 2) { gsd_set_error("stage must be 1 or 2"); return GSD_ERR_INVALID; }
     return raster_backward_impl(a, stream, stage);
 }
-static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages) {
+static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages, const GsdTrackUpdate *fused) {
     if (!a) { gsd_set_error("null descriptor"); return GSD_ERR_INVALID; }
     const GsdRasterFwd *f = &a->fwd;
     GsdCam cam;
     int rc;
     if ((rc = make_cam(f, &cam))) return rc;
     if (!f->geom_ws || !f->binning_ws || !f->image_ws || !a->partial_ws || !a->dL_dcolor ||
-        ((stages & 2) && f->G > 0 && (!a->dL_dmeans3D || !a->dL_dscales || !a->dL_drotations))) {
+        ((stages & 2) && !fused && f->G > 0 && (!a->dL_dmeans3D || !a->dL_dscales || !a->dL_drotations))) {
         gsd_set_error("null workspace/output pointer");
         return GSD_ERR_INVALID;
     }
@@ -176,6 +194,7 @@ static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages)
     p.geom_only = geom_only;
     if ((stages & 1) && f->G > 0 && f->capacity > 0)
         if ((rc = gsd_launch_render_bwd(p, tiles, f->n_sets, st))) return rc;
+    if ((stages & 2) && fused) return gsd_launch_preprocess_bwd_update(f->G, cam, a, g, *fused, st);
     if (stages & 2) return gsd_launch_preprocess_bwd(f->G, cam, a, g, geom_only, st);
     return GSD_OK;
 }

@@ -5,18 +5,20 @@
 // gradients returned as the reference's autograd consumes them (/root/reference/src/tracking/train_gs.py:31,
 // means2D.grad at /root/reference/src/tracking/external.py:138-142). dL/ddepth is ignored as upstream does.
 #include "common.cuh"
+#include "track_update.cuh"
 
-template <int CH, bool GEOM>
-__global__ void __launch_bounds__(256)
-gsd_preprocess_bwd_kernel(int G, GsdCam cam, int64_t capacity, const float *__restrict__ means3D,
-                          const float *__restrict__ scales, const float *__restrict__ rotations,
-                          const int32_t *__restrict__ radii, const uint32_t *__restrict__ slot_base,
-                          const uint32_t *__restrict__ tiles, const float4 *__restrict__ conic_o,
-                          const float4 *__restrict__ partials, float *__restrict__ dmeans3D, float *__restrict__ dmeans2D, float *__restrict__ dcolors0,
-                          float *__restrict__ dcolors1, float *__restrict__ dopac, float *__restrict__ dscales,
-                          float *__restrict__ drot) {
-    gsd_pdl_wait();
-    gsd_pdl_launch();
+// FUSE (steady-state tracking, geometry-only): the gradients do not go to memory — the thread applies normalize backward +
+// gradient sum + Adam to its Gaussian right here (track_update.cuh), with the radii bookkeeping and the step advance of
+// gsd_track_update: one launch and a 28-byte gradient round trip per Gaussian less per iteration.
+template <int CH, bool GEOM, bool FUSE>
+__device__ __forceinline__ void
+preprocess_bwd_body(int G, const GsdCam &cam, int64_t capacity, const float *__restrict__ means3D,
+                    const float *__restrict__ scales, const float *__restrict__ rotations,
+                    const int32_t *__restrict__ radii, const uint32_t *__restrict__ slot_base,
+                    const uint32_t *__restrict__ tiles, const float4 *__restrict__ conic_o,
+                    const float4 *__restrict__ partials, float *__restrict__ dmeans3D, float *__restrict__ dmeans2D, float *__restrict__ dcolors0,
+                    float *__restrict__ dcolors1, float *__restrict__ dopac, float *__restrict__ dscales,
+                    float *__restrict__ drot, const GsdTrackUpdate &u) {
     __shared__ float sVP[32];
     if (threadIdx.x < 16) sVP[threadIdx.x] = cam.view[threadIdx.x];
     else if (threadIdx.x < 32) sVP[threadIdx.x] = cam.proj[threadIdx.x - 16];
@@ -165,6 +167,11 @@ gsd_preprocess_bwd_kernel(int G, GsdCam cam, int64_t capacity, const float *__re
         dq[2] = 2.f * (-2.f * y * g[0][0] + x * g[0][1] + r * g[0][2] + x * g[1][0] + z * g[1][2] - r * g[2][0] + z * g[2][1] - 2.f * y * g[2][2]);
         dq[3] = 2.f * (-2.f * z * g[0][0] - r * g[0][1] + x * g[0][2] + r * g[1][0] - 2.f * z * g[1][1] + y * g[1][2] + x * g[2][0] + y * g[2][1]);
     }
+    if (FUSE) {
+        gsd_track_update_radii_1(u, i);
+        gsd_track_update_apply(u, i, dmean, make_float4(dq[0], dq[1], dq[2], dq[3]));
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         dmeans3D[3 * i + k] = dmean[k];
@@ -172,6 +179,51 @@ gsd_preprocess_bwd_kernel(int G, GsdCam cam, int64_t capacity, const float *__re
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) drot[4 * i + k] = dq[k];
+}
+
+template <int CH, bool GEOM>
+__global__ void __launch_bounds__(256)
+gsd_preprocess_bwd_kernel(int G, GsdCam cam, int64_t capacity, const float *__restrict__ means3D,
+                          const float *__restrict__ scales, const float *__restrict__ rotations,
+                          const int32_t *__restrict__ radii, const uint32_t *__restrict__ slot_base,
+                          const uint32_t *__restrict__ tiles, const float4 *__restrict__ conic_o,
+                          const float4 *__restrict__ partials, float *__restrict__ dmeans3D, float *__restrict__ dmeans2D, float *__restrict__ dcolors0,
+                          float *__restrict__ dcolors1, float *__restrict__ dopac, float *__restrict__ dscales,
+                          float *__restrict__ drot) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
+    GsdTrackUpdate none;
+    preprocess_bwd_body<CH, GEOM, false>(G, cam, capacity, means3D, scales, rotations, radii, slot_base, tiles, conic_o, partials, dmeans3D, dmeans2D,
+                                         dcolors0, dcolors1, dopac, dscales, drot, none);
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256)
+gsd_preprocess_bwd_update_kernel(int G, GsdCam cam, int64_t capacity, const float *__restrict__ means3D,
+                                 const float *__restrict__ scales, const float *__restrict__ rotations,
+                                 const int32_t *__restrict__ radii, const uint32_t *__restrict__ slot_base,
+                                 const uint32_t *__restrict__ tiles, const float4 *__restrict__ conic_o,
+                                 const float4 *__restrict__ partials, GsdTrackUpdate u) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
+    preprocess_bwd_body<CH, true, true>(G, cam, capacity, means3D, scales, rotations, radii, slot_base, tiles, conic_o, partials, nullptr, nullptr,
+                                        nullptr, nullptr, nullptr, nullptr, nullptr, u);
+    gsd_track_update_advance(u);
+}
+
+// per-Gaussian backward fused with the tracker's update (gsd_track_backward_update): geometry-only, no gradient outputs
+int gsd_launch_preprocess_bwd_update(int G, const GsdCam &cam, const GsdRasterBwd *a, const GsdGeomWs &g, const GsdTrackUpdate &u, cudaStream_t st) {
+    if (G == 0) return GSD_OK;
+    const GsdRasterFwd &f = a->fwd;
+    int blocks = (G + 255) / 256;
+    if (f.n_sets == 1)
+        gsd_launch((gsd_preprocess_bwd_update_kernel<3>), dim3(blocks), dim3(256), 0, st, G, cam, f.capacity, f.means3D, f.scales, f.rotations, f.radii,
+                   g.slot_base, g.tiles, g.conic_o, (const float4 *)a->partial_ws, u);
+    else
+        gsd_launch((gsd_preprocess_bwd_update_kernel<6>), dim3(blocks), dim3(256), 0, st, G, cam, f.capacity, f.means3D, f.scales, f.rotations, f.radii,
+                   g.slot_base, g.tiles, g.conic_o, (const float4 *)a->partial_ws, u);
+    GSD_LAUNCH_CHECK();
+    return GSD_OK;
 }
 
 int gsd_launch_preprocess_bwd(int G, const GsdCam &cam, const GsdRasterBwd *a, const GsdGeomWs &g, int geom_only, cudaStream_t st) {

@@ -122,6 +122,7 @@ __device__ __forceinline__ void eval_edge(const TrackArgs &a, const float xi[3],
 #define TRK_MIN_CTAS 8
 #endif
 #define GSD_PRIORS_CTAS_PER_SM_DEFAULT 0
+#define GSD_PRIORS_CARVEOUT_DEFAULT (-1)
 __global__ void __launch_bounds__(128)
 gsd_track_fg_kernel(TrackArgs a) {
     gsd_pdl_wait();
@@ -542,6 +543,15 @@ extern "C" int gsd_track_losses_fwd_bwd(const GsdTrackLosses *t, void *stream) {
         // iteration, where this kernel runs on a side branch beside the render branch: every cap is slower than the plain grid
         // (cap 1 / 2 / 4 / 6 / 8: +90 / +55 / +10 / +6 / +1 us per iteration) — the kernel's cost to the iteration is its own
         // machine time, not the placement of the other branch's CTAs.  Kept as a tuning switch, off by default.
+        {   // shared-memory carveout of the SMs this kernel runs on (see below); GSD_PRIORS_CARVEOUT: tuning override, -1 = driver default
+            static int carve_set = -2;
+            const char *ce = getenv("GSD_PRIORS_CARVEOUT");
+            const int carve = ce ? atoi(ce) : GSD_PRIORS_CARVEOUT_DEFAULT;
+            if (carve != carve_set) {
+                GSD_CUDA_CHECK(cudaFuncSetAttribute(gsd_track_fg_packed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+                carve_set = carve;
+            }
+        }
         const char *cap_env = getenv("GSD_PRIORS_CTAS_PER_SM");   // tuning override (tools/step_ablate.py)
         const int cap = cap_env ? atoi(cap_env) : GSD_PRIORS_CTAS_PER_SM_DEFAULT;
         const int grid = cap > 0 ? (fgb < 148 * cap ? fgb : 148 * cap) : fgb;

@@ -147,9 +147,11 @@ def raster_forward(settings, means3D, opacities, colors0, scales, rotations, col
     return color, radii, depth, state
 
 
-def raster_backward(state, grad_color, need_means2D=True, geom_only=False):
+def raster_backward(state, grad_color, need_means2D=True, geom_only=False, fused_update=None):
     """Runs the backward kernels. Returns dict of gradients (float32 CUDA tensors). geom_only: colours and opacities are
-    frozen (steady-state tracking) — their gradients are not produced and the blend backward reduces 5 values per instance."""
+    frozen (steady-state tracking) — their gradients are not produced and the blend backward reduces 5 values per instance.
+    fused_update (a filled _lib.GsdTrackUpdate; implies geom_only, no means2D): the per-Gaussian backward kernel applies the
+    tracker's update itself (gsd_track_backward_update) and nothing is returned."""
     lib = _lib.lib()
     G, n_sets = state.G, state.n_sets
     dev = grad_color.device
@@ -159,6 +161,13 @@ def raster_backward(state, grad_color, need_means2D=True, geom_only=False):
     with torch.cuda.device(dev):
         sz = _workspace_bytes(G, state.W, state.H, n_sets, state.capacity)
         partial = torch.empty(sz[3], dtype=torch.uint8, device=dev)
+        b = _lib.GsdRasterBwd()
+        b.fwd = state.desc
+        b.dL_dcolor, b.partial_ws = grad_color.data_ptr(), partial.data_ptr()
+        if fused_update is not None:
+            with _nvtx.range("gsd.raster_backward_update"):
+                _lib.check(lib.gsd_track_backward_update(C.byref(b), C.byref(fused_update), _stream()), "gsd_track_backward_update")
+            return None
         g = dict(means3D=torch.empty((G, 3), dtype=torch.float32, device=dev),
                  means2D=torch.empty((G, 3), dtype=torch.float32, device=dev) if need_means2D else None,
                  colors0=torch.empty((G, 3), dtype=torch.float32, device=dev) if not geom_only else None,
@@ -166,9 +175,6 @@ def raster_backward(state, grad_color, need_means2D=True, geom_only=False):
                  opacities=torch.empty((G, 1), dtype=torch.float32, device=dev) if not geom_only else None,
                  scales=torch.empty((G, 3), dtype=torch.float32, device=dev),
                  rotations=torch.empty((G, 4), dtype=torch.float32, device=dev))
-        b = _lib.GsdRasterBwd()
-        b.fwd = state.desc
-        b.dL_dcolor, b.partial_ws = grad_color.data_ptr(), partial.data_ptr()
         ptr = lambda t: t.data_ptr() if t is not None else None
         b.dL_dmeans3D, b.dL_dmeans2D = ptr(g["means3D"]), ptr(g["means2D"])
         b.dL_dcolors0, b.dL_dcolors1 = ptr(g["colors0"]), ptr(g["colors1"])

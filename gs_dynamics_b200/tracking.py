@@ -653,6 +653,10 @@ class FusedTrackingStep(TrackingStep):
             self.tstats = [target_stats(tg) for tg in self.targets]
         self.outputs = {}
         self.side = torch.cuda.Stream(device=params['means3D'].device)
+        # the render branch is captured on a high-priority stream: when the side branch's CTAs fill the machine, the block scheduler
+        # hands freed slots to the render branch first (tools/graph_timeline.py: preprocess starts 12 us earlier; -3 us per iteration)
+        self.capture_stream = torch.cuda.Stream(device=params['means3D'].device, priority=-1)
+        self.fuse_update = True      # rasterizer backward + update in one per-Gaussian kernel (False: gsd_raster_backward, gsd_track_update)
         self.priors_fork = 'start'   # where the priors branch forks off the render branch: 'start' | 'after_forward'
         self.block_counter = torch.zeros(1, dtype=torch.int32, device=params['means3D'].device)   # self-resetting (gsd_track_update)
         self.lr = {g['name']: float(g['lr']) for g in optimizer.param_groups}
@@ -731,7 +735,6 @@ class FusedTrackingStep(TrackingStep):
                 tns.record_stream(self.side)
             dL = torch.empty_like(color)
             _lib.check(lib.gsd_photometric_backward(C.byref(d), None, dL.data_ptr(), st), "gsd_photometric_backward")
-            g = R.raster_backward(state, dL, need_means2D=False, geom_only=True)
             main.wait_event(join)
             u = _lib.GsdTrackUpdate()
             u.G = G
@@ -739,8 +742,7 @@ class FusedTrackingStep(TrackingStep):
             u.lr_means, u.lr_rot = self.lr['means3D'], self.lr['unnorm_rotations']
             sm, sr = self.optimizer.state[x], self.optimizer.state[uq]
             u.means3D, u.unnorm_rotations = x.data_ptr(), uq.data_ptr()
-            u.g_means_a, u.g_means_b = g['means3D'].data_ptr(), gx_p.data_ptr()
-            u.g_rot_a, u.g_rot_b = g['rotations'].data_ptr(), gq_p.data_ptr()
+            u.g_means_b, u.g_rot_b = gx_p.data_ptr(), gq_p.data_ptr()
             u.m_means, u.v_means = sm['exp_avg'].data_ptr(), sm['exp_avg_sq'].data_ptr()
             u.m_rot, u.v_rot = sr['exp_avg'].data_ptr(), sr['exp_avg_sq'].data_ptr()
             u.step_means, u.step_rot = sm['step'].data_ptr(), sr['step'].data_ptr()
@@ -748,7 +750,13 @@ class FusedTrackingStep(TrackingStep):
             seen = torch.empty(G, dtype=torch.uint8, device=x.device)
             u.radii, u.max_2D_radius, u.seen = radii.data_ptr(), V['max_2D_radius'].data_ptr(), seen.data_ptr()
             u.block_counter = self.block_counter.data_ptr()
-            _lib.check(lib.gsd_track_update(C.byref(u), st), "gsd_track_update")
+            if self.fuse_update:
+                # the rasterizer's per-Gaussian backward applies the update in registers: no gradient arrays, one launch less
+                R.raster_backward(state, dL, fused_update=u)
+            else:
+                g = R.raster_backward(state, dL, need_means2D=False, geom_only=True)
+                u.g_means_a, u.g_rot_a = g['means3D'].data_ptr(), g['rotations'].data_ptr()
+                _lib.check(lib.gsd_track_update(C.byref(u), st), "gsd_track_update")
             main.wait_event(loss_done)
             # per-camera result buffers (every captured graph writes its own): step() re-points `variables` at the ones of the
             # camera it replayed

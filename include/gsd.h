@@ -223,6 +223,11 @@ typedef struct {
     uint32_t *block_counter;              /* optional, see above */
 } GsdTrackUpdate;
 int gsd_track_update(const GsdTrackUpdate *u, void *stream);
+/* gsd_raster_backward (geometry-only: dL_dcolors0/1, dL_dopacities, dL_dmeans2D must be NULL; dL_dmeans3D / dL_dscales /
+ * dL_drotations are not written and may be NULL) with gsd_track_update applied inside its per-Gaussian kernel: replaces
+ * loss.backward() + optimizer.step() of train_gs.py:31-39 for t > 0.  u->g_means_a / g_rot_a are ignored (the rasterizer's
+ * gradients stay in registers); u->g_means_b / g_rot_b (the priors' gradients) are added; u->block_counter is required. */
+int gsd_track_backward_update(const GsdRasterBwd *a, const GsdTrackUpdate *u, void *stream);
 
 /* bookkeeping of get_loss (train_utils.py:243-245): seen = radii > 0; max_2D_radius = max(radii, max_2D_radius)[seen] */
 int gsd_track_update_radii(int32_t G, const int32_t *radii, float *max_2D_radius, uint8_t *seen, void *stream);

@@ -297,6 +297,33 @@ def test_fused_tracking_step_matches_autograd_path():
     np.testing.assert_allclose(lg, l2, rtol=1e-4)
 
 
+def test_fused_backward_update_kernel_equals_backward_plus_update():
+    """gsd_track_backward_update (per-Gaussian rasterizer backward with the Adam update applied in registers) against the two
+    launches it replaces (gsd_raster_backward + gsd_track_update): same parameters, Adam moments, step counters, radii bookkeeping."""
+    from gs_dynamics_b200 import tracking as TR
+    runs = []
+    for fuse in (True, False):
+        p, v, o, d = _tracking_problem(3000)
+        for g in o.param_groups:
+            if g['name'] not in ('means3D', 'unnorm_rotations'):
+                g['lr'] = 0.0
+        st = TR.FusedTrackingStep(p, v, o, d, use_graph=False)
+        st.fuse_update = fuse
+        st.prepare()
+        losses = [float(st.step(c)) for c in (0, 1, 1, 0, 1)]
+        runs.append((p, o, v, losses))
+    (pa, oa, va, la), (pb, ob, vb, lb) = runs
+    # same arithmetic, compiled in two kernels (FMA contraction may differ by an ulp per step): 1e-5 after five iterations
+    np.testing.assert_allclose(la, lb, rtol=1e-5)
+    for k in ('means3D', 'unnorm_rotations'):
+        a, b = pa[k].detach(), pb[k].detach()
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()), k
+        sa, sb = oa.state[pa[k]], ob.state[pb[k]]
+        assert float(sa['step']) == float(sb['step']) == 5.0
+        assert rel_err(sa['exp_avg'].cpu(), sb['exp_avg'].cpu()) < 1e-5 and rel_err(sa['exp_avg_sq'].cpu(), sb['exp_avg_sq'].cpu()) < 1e-5
+    assert torch.equal(va['max_2D_radius'], vb['max_2D_radius']) and torch.equal(va['seen'], vb['seen'])
+
+
 def test_t0_densification_surgery_and_short_episode():
     """A9/A12 + episode loop: densify bookkeeping (clone / split / prune, Adam state surgery) and a 2-frame episode."""
     from gs_dynamics_b200 import tracking as TR, scenes, rasterizer as R

@@ -19,7 +19,11 @@ dev = torch.device("cuda")
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
 
-def measure(label, patch=None, fork='start', hi_prio=False, cap=None):
+def measure(label, patch=None, fork='start', hi_prio=False, cap=None, carve=None):
+    if carve is None:
+        os.environ.pop('GSD_PRIORS_CARVEOUT', None)
+    else:
+        os.environ['GSD_PRIORS_CARVEOUT'] = str(carve)
     if cap is None:
         os.environ.pop('GSD_PRIORS_CTAS_PER_SM', None)
     else:
@@ -100,5 +104,14 @@ for vname in variants:
         measure("main_hi_prio", hi_prio=True)
     elif vname == "both":
         measure("after_fwd+hi_prio", fork='after_forward', hi_prio=True)
+    elif vname == "no_morton":   # packed priors tables in the caller's (random) order
+        orig_m = TR._morton_order
+        TR._morton_order = lambda pts: torch.arange(pts.shape[0], device=pts.device)
+        measure("no_morton")
+        TR._morton_order = orig_m
+    elif vname.startswith("hi_carve"):      # render branch on a high-priority stream + shared-memory carveout of the priors kernel
+        measure(vname, hi_prio=True, carve=int(vname[8:]))
+    elif vname.startswith("carve"):
+        measure(vname, carve=int(vname[5:]))
     elif vname.startswith("cap"):
         measure(vname, cap=int(vname[3:]))
