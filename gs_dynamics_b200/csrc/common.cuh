@@ -56,7 +56,9 @@ struct GsdGeomWs { // per-Gaussian state
     uint32_t *block_base;// [ceil(G/256)] exclusive scan of block_sum
     size_t total;
 };
+#ifndef GSD_CHUNK
 #define GSD_CHUNK 128      // records per blend work item (tile lists are split into chunks processed in parallel)
+#endif
 #define GSD_BIN_BLOCK 1024 // Gaussians per binning block
 struct GsdBinWs {
     int n_bb;            // binning blocks = ceil(G / GSD_BIN_BLOCK)
