@@ -188,6 +188,7 @@ static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages,
     p.final_T = im.final_T;
     p.n_contrib = im.n_contrib;
     p.dL_dcolor = a->dL_dcolor;
+    p.exec_item = b.exec_item;
     p.partials = (float *)a->partial_ws;
     // colours and opacities frozen (no output requested): geometry-only partials
     const int geom_only = (!a->dL_dcolors0 && !a->dL_dcolors1 && !a->dL_dopacities) ? 1 : 0;

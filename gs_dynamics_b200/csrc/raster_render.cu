@@ -625,7 +625,12 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
     __shared__ __align__(8) uint64_t bar, done_bar[S], empty[S];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     ItemInfo I;
-    const int item = blockIdx.x / HALVES, half = blockIdx.x % HALVES;
+    // heavy items first: the forward's chunk-index-major order is also longest-work-first for this kernel (front chunks touch
+    // every pixel, deep chunks lie mostly behind the pixels' last contributor and leave early), so the grid's tail is made of
+    // light items instead of whatever tile happens to come last
+    const int half = blockIdx.x % HALVES;
+    if ((int)(blockIdx.x / HALVES) >= *p.n_items) return;
+    const int item = p.exec_item[blockIdx.x / HALVES];
     if (!item_setup(p, item, half * NW + (warp < NW ? warp : 0), lane, I)) return;
     if (t == 0) {
         mbar_init(&bar, 1);
