@@ -123,9 +123,12 @@ __global__ void __launch_bounds__(256)
 gsd_track_update_fused_kernel(GsdTrackUpdate u) {
     gsd_pdl_wait();
     gsd_pdl_launch();
+    __shared__ GsdAdamCoef coef;
+    if (threadIdx.x == 0) gsd_track_update_coef(u, &coef);
+    __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     gsd_track_update_radii_1(u, i);
-    gsd_track_update_body(u, i);
+    gsd_track_update_body(u, coef, i);
     gsd_track_update_advance(u);
 }
 __global__ void gsd_track_update_advance_kernel(float *a, float *b) {

@@ -70,7 +70,7 @@ struct GsdBinWs {
     uint2 *ranges;       // per tile [start,end) clipped to capacity
     int32_t *chunk_ptr;  // [tiles+1] exclusive scan of chunks per tile
     int4 *item_tile;     // [max_items] work item -> (tile, chunk index in the tile, first record, record count): one 16-byte read per CTA
-    int32_t *counters;   // [8] 0: n_items, 1: sort units, 2: tiles with more than one sort unit, 3: "tile bases published" flag
+    int32_t *counters;   // [8] 0: n_items, 1: sort units, 2: tiles with more than one sort unit, 3: "tile bases published" flag, 4: replay pairs of the blend forward
     int32_t *unit_tile;  // [max_units] tile of each sort unit
     int32_t *unit_seg;   // [max_units] segment index of each sort unit inside its tile
     int32_t *long_tile;  // [tiles] tiles whose list spans several sort units
@@ -104,7 +104,8 @@ struct GsdRenderParams {
     const int4 *item_tile;     // [n_items] (tile, chunk, first record, record count)
     const int32_t *n_items;    // device scalar
     const int32_t *exec_item;  // [n_items] execution order of the forward chunk kernel
-    int32_t *chunk_flags;      // [max_items][8]
+    int32_t *chunk_flags;      // [max_items][8] pass A: look-back flags; pass B -> C: list of (item * 8 + rectangle) replay pairs
+    int32_t *replay_count;     // device scalar: entries of that list (cleared by the histogram pass of every forward)
     // forward A1 gathers the per-Gaussian data by sorted key and writes the record planes
     const uint64_t *keys; const float2 *g_xy; const float4 *g_conic_o; const float2 *g_ext; const float *g_depth;
     const uint2 *g_rect; const uint32_t *g_slot_base; const float *colors0; const float *colors1;

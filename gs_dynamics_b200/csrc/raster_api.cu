@@ -129,7 +129,7 @@ extern "C" int gsd_raster_forward(const GsdRasterFwd *a, void *stream) {
     p.keys = b.keys; p.g_xy = g.xy; p.g_conic_o = g.conic_o; p.g_ext = g.ext; p.g_depth = g.depth; p.g_rect = g.rect;
     p.g_slot_base = g.slot_base; p.colors0 = a->colors0; p.colors1 = a->n_sets == 2 ? a->colors1 : nullptr;
     p.planes_w = b.records;
-    p.exec_item = b.exec_item; p.chunk_flags = im.chunk_flags;
+    p.exec_item = b.exec_item; p.chunk_flags = im.chunk_flags; p.replay_count = b.counters + 4;
     return gsd_launch_render_fwd(p, tiles, a->n_sets, st);
 }
 

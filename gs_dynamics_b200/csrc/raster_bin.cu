@@ -105,7 +105,7 @@ gsd_bin_kernel(int G, int gx, int n_tiles, int n_bb, const uint32_t *__restrict_
     for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) bins[i] = 0;
     if (!SCATTER)   // the "published" flags of the blend work items, cleared for this forward pass
         for (int z = bb * GSD_BIN_BLOCK + threadIdx.x; z < n_zero; z += gridDim.x * GSD_BIN_BLOCK) zero_fill[z] = 0;
-    if (!SCATTER && bb == 0 && threadIdx.x == 0) counters[3] = 0;   // "tile bases published" flag of the scan launch
+    if (!SCATTER && bb == 0 && threadIdx.x == 0) { counters[3] = 0; counters[4] = 0; }   // "tile bases published" flag of the scan launch; replay-pair count of the blend forward
     __syncthreads();
     const int i = bb * GSD_BIN_BLOCK + threadIdx.x;
     if (i < G) {

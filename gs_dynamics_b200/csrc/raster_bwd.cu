@@ -20,8 +20,10 @@ preprocess_bwd_body(int G, const GsdCam &cam, int64_t capacity, const float *__r
                     float *__restrict__ dcolors1, float *__restrict__ dopac, float *__restrict__ dscales,
                     float *__restrict__ drot, const GsdTrackUpdate &u) {
     __shared__ float sVP[32];
+    __shared__ GsdAdamCoef coef;
     if (threadIdx.x < 16) sVP[threadIdx.x] = cam.view[threadIdx.x];
     else if (threadIdx.x < 32) sVP[threadIdx.x] = cam.proj[threadIdx.x - 16];
+    if (FUSE && threadIdx.x == 32) gsd_track_update_coef(u, &coef);
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G) return;
@@ -32,18 +34,39 @@ preprocess_bwd_body(int G, const GsdCam &cam, int64_t capacity, const float *__r
     if (vis) {
         uint32_t nt = tiles[i];
         int64_t s0 = (int64_t)slot_base[i];
-        for (uint32_t k = 0; k < nt; ++k) {
-            int64_t s = s0 + k;
-            if (s >= capacity) break;
-            const float4 *r = partials + s * 4;
-            float4 a = r[0], b = r[1];
-            if (GEOM) {   // two half-tile partial sums per record: floats [0,5) and [8,13), added in fixed order
-                const float4 c = r[2], d = r[3];
-                a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; b.x += d.x;
+        if (GEOM) {
+            // two half-tile partial sums per record: floats [0,5) and [8,13), added in fixed order.  The trip count is data dependent,
+            // so the compiler does not overlap the iterations: the loads of four records are issued together (the kernel is one wave;
+            // its time is the slowest thread's chain of record loads), the sums keep the record order
+            for (uint32_t k0 = 0; k0 < nt; k0 += 4) {
+                float4 A[4], Cc[4];
+                float B[4], D[4];
+                bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t sidx = s0 + k0 + u;
+                    ok[u] = (k0 + u < nt) && sidx < capacity;
+                    const float *r = reinterpret_cast<const float *>(partials + (ok[u] ? sidx : 0) * 4);
+                    A[u] = *reinterpret_cast<const float4 *>(r);
+                    B[u] = r[4];
+                    Cc[u] = *reinterpret_cast<const float4 *>(r + 8);
+                    D[u] = r[12];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (!ok[u]) continue;
+                    acc[0] += A[u].x + Cc[u].x; acc[1] += A[u].y + Cc[u].y; acc[2] += A[u].z + Cc[u].z; acc[3] += A[u].w + Cc[u].w;
+                    acc[4] += B[u] + D[u];
+                }
             }
-            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-            if (!GEOM) {
+        } else {
+            for (uint32_t k = 0; k < nt; ++k) {
+                int64_t s = s0 + k;
+                if (s >= capacity) break;
+                const float4 *r = partials + s * 4;
+                float4 a = r[0], b = r[1];
+                acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+                acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
                 float4 c = r[2];
                 acc[8] += c.x; acc[9] += c.y; acc[10] += c.z; acc[11] += c.w;
             }
@@ -169,7 +192,7 @@ preprocess_bwd_body(int G, const GsdCam &cam, int64_t capacity, const float *__r
     }
     if (FUSE) {
         gsd_track_update_radii_1(u, i);
-        gsd_track_update_apply(u, i, dmean, make_float4(dq[0], dq[1], dq[2], dq[3]));
+        gsd_track_update_apply(u, coef, i, dmean, make_float4(dq[0], dq[1], dq[2], dq[3]));
         return;
     }
 #pragma unroll

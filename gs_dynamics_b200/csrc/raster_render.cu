@@ -402,6 +402,17 @@ gsd_blend_fwd_finish_kernel(GsdRenderParams p) {
             }
         }
     }
+    // work list of the replay pass: one entry per (work item, rectangle) that holds a terminating pixel — a rectangle is this
+    // warp, so the lanes that share a terminating chunk elect one of them to append.  The list lives in the look-back flag
+    // array of pass A, which is dead by now (this kernel runs after it; the next forward clears it again).
+    {
+        const bool term = inside && cstar >= 0;
+        const unsigned tm = __ballot_sync(0xffffffffu, term);
+        if (term) {
+            const unsigned same = __match_any_sync(tm, cstar);
+            if (lane == __ffs(same) - 1) p.chunk_flags[atomicAdd(p.replay_count, 1)] = (item0 + cstar) * GSD_CWARPS + warp;
+        }
+    }
     if (!inside) return;
     float *tsw = p.term_state + (size_t)tile * TS::NF * 256;
     reinterpret_cast<int *>(tsw)[TS::CSTAR * 256 + t] = cstar;     // -1, or the chunk the replay pass finishes this pixel in
@@ -412,9 +423,6 @@ gsd_blend_fwd_finish_kernel(GsdRenderParams p) {
 #pragma unroll
         for (int k = 0; k < CH; ++k) tsw[(TS::C + k) * 256 + t] = C[k];
         reinterpret_cast<int *>(tsw)[TS::LAST * 256 + t] = last;
-        // work list of the replay pass: flag 3 on (item, rectangle).  The look-back flags of pass A are dead by now (this kernel
-        // runs after it); several lanes may store the same value to the same word.
-        p.chunk_flags[(size_t)(item0 + cstar) * GSD_CWARPS + warp] = 3;
         return;
     }
     const size_t pid = (size_t)py * p.W + px;
@@ -430,10 +438,13 @@ gsd_blend_fwd_finish_kernel(GsdRenderParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// forward C: per work item — replay of a terminating chunk for the pixels that stop inside it
+// forward C: replay of a terminating chunk for the pixels of one 8x4 rectangle that stop inside it
 // ------------------------------------------------------------------------------------------------------
-// Every pixel terminates in at most one chunk, so every output pixel has exactly one writer (pass B or one item of this pass).
-// The records arrive by one TMA bulk copy per plane; items without a terminating pixel (most) exit after one 1 KB read.
+// Every pixel terminates in at most one chunk, so every output pixel has exactly one writer (pass B or one warp of this pass).
+// One WARP per (work item, rectangle) pair of pass B's list (~1.5 pairs per rectangle of a saturated tile): warps are independent
+// (their own 2 KB shared-memory stage for the 32 records of a cull group, no block barrier, no TMA), so every resident warp has
+// work.  (Round 2's first version ran one CTA per work item with the chunk staged by TMA: one to three live warps per 8-warp
+// CTA, SMSPs active 56 % of the elapsed cycles, 24 us; the order of the list is arbitrary and never affects a result.)
 template <int CH>
 __global__ void __launch_bounds__(GSD_CWARPS * 32)
 gsd_blend_fwd_replay_kernel(GsdRenderParams p) {
@@ -441,22 +452,16 @@ gsd_blend_fwd_replay_kernel(GsdRenderParams p) {
     gsd_pdl_launch();
     constexpr int NPL = (CH == 3) ? 3 : 4;
     using TS = TermState<CH>;
-    __shared__ __align__(128) float4 planes[NPL][GSD_CHUNK];
-    __shared__ __align__(8) uint64_t bar;
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    __shared__ __align__(16) float4 stage[GSD_CWARPS][NPL][GSD_SUB];
+    const int t = threadIdx.x, wid = t >> 5, lane = t & 31;
+    const int n_pairs = *p.replay_count;
+    const int pi = blockIdx.x * GSD_CWARPS + wid;
+    if (pi >= n_pairs) return;
+    const int pair = p.chunk_flags[pi];
+    const int item = pair / GSD_CWARPS, rect = pair % GSD_CWARPS;
     ItemInfo I;
-    if ((int)blockIdx.x >= *p.n_items) return;
-    // pass B flagged the (item, rectangle) pairs that hold a terminating pixel: one 32-byte read tells every warp whether the
-    // item has work at all (most do not) and whether its own rectangle has
-    const int fl = lane < GSD_CWARPS ? p.chunk_flags[(size_t)blockIdx.x * GSD_CWARPS + lane] : 0;
-    const unsigned live = __ballot_sync(0xffffffffu, fl == 3);
-    if (live == 0u) return;
-    item_setup(p, blockIdx.x, warp, lane, I);
+    if (!item_setup(p, item, rect, lane, I)) return;
     float *ts = p.term_state + (size_t)I.tile * TS::NF * 256;
-    if (t == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-    __syncthreads();
-    if (t == 0) load_chunk<NPL>(p, planes, &bar, I.start, I.cnt);
-    if (!((live >> warp) & 1u)) return;
     const bool mine = I.inside && reinterpret_cast<const int *>(ts)[TS::CSTAR * 256 + I.pix] == I.chunk;
     float T = 1.0f, D = 0.f;
     float C[CH];
@@ -470,25 +475,37 @@ gsd_blend_fwd_replay_kernel(GsdRenderParams p) {
         for (int c = 0; c < CH; ++c) C[c] = ts[(TS::C + c) * 256 + I.pix];
         last = reinterpret_cast<const int *>(ts)[TS::LAST * 256 + I.pix];
     }
-    mbar_wait(&bar, 0);
     // sequential replay for the terminating lanes: the reference's loop (renderCUDA forward) with the true incoming T
     const float pxf = (float)I.px, pyf = (float)I.py;
+    const float4 *src = p.planes + I.start;
+    float4 (*st)[GSD_SUB] = stage[wid];
     int lastl = 0;
     bool done = !mine;
+    // lane l holds record grp + l of every plane (coalesced 512-byte reads, next group in flight during the current one)
+    float4 r[NPL];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) r[k] = lane < I.cnt ? src[(int64_t)k * p.plane_stride + lane] : zero4;
     for (int grp = 0; grp < I.cnt; grp += GSD_SUB) {
         if (__all_sync(0xffffffffu, done)) break;
         const int idx = grp + lane;
-        bool pass = false;
-        if (idx < I.cnt) pass = cull_pass(planes[0][idx], planes[1][idx], I.rx0, I.rx1, I.ry0, I.ry1);
+        const bool pass = idx < I.cnt && cull_pass(r[0], r[1], I.rx0, I.rx1, I.ry0, I.ry1);
+        __syncwarp();      // the previous group's survivors have been read by every lane
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) st[k][lane] = r[k];
+        const int nidx = idx + GSD_SUB;
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) r[k] = nidx < I.cnt ? src[(int64_t)k * p.plane_stride + nidx] : zero4;
+        __syncwarp();      // stage stores visible to the whole warp
         unsigned m = __ballot_sync(0xffffffffu, pass);
         while (m) {
-            const int j = grp + __ffs(m) - 1;
+            const int jl = __ffs(m) - 1;
             m &= m - 1;
-            const float4 g0 = planes[0][j];
-            const float4 g1 = planes[1][j];
-            const float4 g2 = planes[2][j];
-            float4 g3 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (CH == 6) g3 = planes[NPL - 1][j];
+            const float4 g0 = st[0][jl];
+            const float4 g1 = st[1][jl];
+            const float4 g2 = st[2][jl];
+            float4 g3 = zero4;
+            if (CH == 6) g3 = st[NPL - 1][jl];
             const float power = gsd_power(g1.x, g1.y, g1.z, g0.x - pxf, g0.y - pyf);
             const float alpha = fminf(0.99f, __fmul_rn(g1.w, gsd_gauss(power)));
             // straight-line (predicated) update, as in pass A
@@ -508,7 +525,7 @@ gsd_blend_fwd_replay_kernel(GsdRenderParams p) {
             }
             D += g2.w * w;
             T = ok ? test_T : T;
-            lastl = ok ? j + 1 : lastl;
+            lastl = ok ? grp + jl + 1 : lastl;
         }
     }
     if (!mine) return;

@@ -11,11 +11,18 @@ __device__ __forceinline__ float adam_1(float p, float g, float &m, float &v, fl
 }
 
 // ga_m[3] / ga_q: the rasterizer's gradients w.r.t. means3D / the NORMALISED rotation, in registers
-__device__ __forceinline__ void gsd_track_update_apply(const GsdTrackUpdate &u, int i, const float ga_m[3], float4 ga) {
-    if (i >= u.G) return;
+// Adam's bias-corrected step sizes of the two groups: uniform over the launch (four powf + divisions, ~400 instructions behind a
+// dependent load of the step counter) — one thread per CTA computes them at kernel entry, the others read shared memory
+struct GsdAdamCoef { float lrm, ism, lrr, isr; };
+__device__ __forceinline__ void gsd_track_update_coef(const GsdTrackUpdate &u, GsdAdamCoef *c) {
     const float sm = *u.step_means + 1.f, sr = *u.step_rot + 1.f;
-    const float lrm = u.lr_means / (1.f - powf(u.beta1, sm)), ism = 1.f / sqrtf(1.f - powf(u.beta2, sm));
-    const float lrr = u.lr_rot / (1.f - powf(u.beta1, sr)), isr = 1.f / sqrtf(1.f - powf(u.beta2, sr));
+    c->lrm = u.lr_means / (1.f - powf(u.beta1, sm)); c->ism = 1.f / sqrtf(1.f - powf(u.beta2, sm));
+    c->lrr = u.lr_rot / (1.f - powf(u.beta1, sr)); c->isr = 1.f / sqrtf(1.f - powf(u.beta2, sr));
+}
+
+__device__ __forceinline__ void gsd_track_update_apply(const GsdTrackUpdate &u, const GsdAdamCoef &k4, int i, const float ga_m[3], float4 ga) {
+    if (i >= u.G) return;
+    const float lrm = k4.lrm, ism = k4.ism, lrr = k4.lrr, isr = k4.isr;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const size_t k = 3 * (size_t)i + c;
@@ -42,10 +49,10 @@ __device__ __forceinline__ void gsd_track_update_apply(const GsdTrackUpdate &u, 
     reinterpret_cast<float4 *>(u.v_rot)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
 }
 
-__device__ __forceinline__ void gsd_track_update_body(const GsdTrackUpdate &u, int i) {
+__device__ __forceinline__ void gsd_track_update_body(const GsdTrackUpdate &u, const GsdAdamCoef &k4, int i) {
     if (i >= u.G) return;
     const float ga_m[3] = {u.g_means_a[3 * (size_t)i], u.g_means_a[3 * (size_t)i + 1], u.g_means_a[3 * (size_t)i + 2]};
-    gsd_track_update_apply(u, i, ga_m, reinterpret_cast<const float4 *>(u.g_rot_a)[i]);
+    gsd_track_update_apply(u, k4, i, ga_m, reinterpret_cast<const float4 *>(u.g_rot_a)[i]);
 }
 
 // radii bookkeeping of get_loss (train_utils.py:243-245)
