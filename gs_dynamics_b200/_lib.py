@@ -26,7 +26,7 @@ class GsdRasterFwd(C.Structure):
         ("colors0", C.c_void_p), ("colors1", C.c_void_p),
         ("out_color", C.c_void_p), ("out_depth", C.c_void_p), ("radii", C.c_void_p),
         ("geom_ws", C.c_void_p), ("binning_ws", C.c_void_p), ("image_ws", C.c_void_p), ("status", C.c_void_p),
-        ("sticky", C.c_void_p),
+        ("sticky", C.c_void_p), ("unnorm_rotations", C.c_void_p),
     ]
 
 
@@ -53,6 +53,7 @@ class GsdTrackLosses(C.Structure):
         ("init_bg_pts", C.c_void_p), ("init_bg_rot", C.c_void_p),
         ("w_rigid", C.c_float), ("w_rot", C.c_float), ("w_iso", C.c_float), ("w_floor", C.c_float), ("w_bg", C.c_float),
         ("ws", C.c_void_p), ("losses", C.c_void_p), ("grad_means3D", C.c_void_p), ("grad_rotations", C.c_void_p),
+        ("rotations_unnormalized", C.c_int32),
     ]
 
 

@@ -104,9 +104,7 @@ __global__ void gsd_normalize_rot_kernel(int G, const float4 *__restrict__ q, fl
     gsd_pdl_launch();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G) return;
-    float4 v = q[i];
-    float n = fmaxf(sqrtf(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w), 1e-12f); // F.normalize eps
-    out[i] = make_float4(v.x / n, v.y / n, v.z / n, v.w / n);
+    out[i] = gsd_quat_normalize(q[i]);
 }
 
 extern "C" int gsd_track_normalize_rotations(int32_t G, const float *unnorm, float *rot, void *stream) {

@@ -133,6 +133,20 @@ struct GsdRenderParams {
 // the programmatic-stream-serialization attribute, a kernel's launch latency, CTA dispatch and prologue overlap the tail of
 // its predecessor instead of following it; inside a captured CUDA graph these become programmatic edges.  GSD_NO_PDL=1 in
 // the environment turns the attribute off (plain stream order).
+// F.normalize of a quaternion (helpers.py:40; eps 1e-12), written with explicit roundings so that every kernel that normalises
+// on the fly (preprocess, the priors' node records, the update's normalize-backward) gets the same bits whatever its -fmad setting
+__device__ __forceinline__ float gsd_quat_norm(float4 v) {
+    float s = __fmul_rn(v.x, v.x);
+    s = __fmaf_rn(v.y, v.y, s);
+    s = __fmaf_rn(v.z, v.z, s);
+    s = __fmaf_rn(v.w, v.w, s);
+    return fmaxf(__fsqrt_rn(s), 1e-12f);
+}
+__device__ __forceinline__ float4 gsd_quat_normalize(float4 v) {
+    const float n = gsd_quat_norm(v);
+    return make_float4(__fdiv_rn(v.x, n), __fdiv_rn(v.y, n), __fdiv_rn(v.z, n), __fdiv_rn(v.w, n));
+}
+
 __device__ __forceinline__ void gsd_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #ifndef GSD_PDL_EARLY
 #define GSD_PDL_EARLY 0

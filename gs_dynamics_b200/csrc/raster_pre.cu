@@ -16,7 +16,8 @@ gsd_preprocess_kernel(int G, GsdCam cam, const float *__restrict__ means3D, cons
                       const float *__restrict__ scales, const float *__restrict__ rotations, float2 *__restrict__ xy,
                       float4 *__restrict__ conic_o, float2 *__restrict__ ext, float *__restrict__ depth,
                       uint2 *__restrict__ rect, uint32_t *__restrict__ tiles, uint32_t *__restrict__ slot_base,
-                      int32_t *__restrict__ radii, uint32_t *__restrict__ block_sum, int32_t *__restrict__ zero_fill, int n_zero) {
+                      int32_t *__restrict__ radii, uint32_t *__restrict__ block_sum, int32_t *__restrict__ zero_fill, int n_zero,
+                      const float4 *__restrict__ unnorm, float4 *__restrict__ rot_out) {
     gsd_pdl_wait();
     gsd_pdl_launch();
     __shared__ float sVP[32];
@@ -27,6 +28,13 @@ gsd_preprocess_kernel(int G, GsdCam cam, const float *__restrict__ means3D, cons
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = i < G;
+    // steady-state tracking: the quaternions arrive un-normalised (params['unnorm_rotations']); F.normalize is applied here and the
+    // result written for the backward (one launch less in front of every iteration)
+    float4 qn = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (in_range) {
+        if (unnorm) { qn = gsd_quat_normalize(unnorm[i]); rot_out[i] = qn; }
+        else qn = *reinterpret_cast<const float4 *>(rotations + 4 * (size_t)i);
+    }
     int rad_out = 0;
     uint32_t tiles_out = 0;
     uint2 rect_out = make_uint2(0u, 0u);
@@ -42,7 +50,7 @@ gsd_preprocess_kernel(int G, GsdCam cam, const float *__restrict__ means3D, cons
         float ndcx = hx * pw, ndcy = hy * pw;
 
         // Sigma = R diag((mod*s)^2) R^T
-        float r = rotations[4 * i], x = rotations[4 * i + 1], y = rotations[4 * i + 2], z = rotations[4 * i + 3];
+        float r = qn.x, x = qn.y, y = qn.z, z = qn.w;
         float R[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
                          {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
                          {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
@@ -160,7 +168,8 @@ int gsd_launch_preprocess(int G, const GsdCam &cam, const GsdRasterFwd *a, const
     int blocks = (G + 255) / 256;
     gsd_launch(gsd_preprocess_kernel, dim3(blocks), dim3(256), 0, st, G, cam, a->means3D, a->opacities, a->scales, a->rotations, g.xy,
                                                    g.conic_o, g.ext, g.depth, g.rect, g.tiles, g.slot_base, a->radii,
-                                                   g.block_sum, zero_fill, n_zero);
+                                                   g.block_sum, zero_fill, n_zero, (const float4 *)a->unnorm_rotations,
+                                                   (float4 *)const_cast<float *>(a->rotations));
     GSD_LAUNCH_CHECK();
     return GSD_OK;
 }

@@ -16,6 +16,7 @@
 
 struct TrackArgs {
     int Gf, K, Gb;
+    int unnorm;            // q holds un-normalised quaternions: F.normalize on the fly
     unsigned div_magic; int div_shift;   // e / K == (e * div_magic) >> div_shift for every 31-bit e
     const float *x;        // [G,3] means3D
     const float *q;        // [G,4] normalised rotations
@@ -60,6 +61,12 @@ __device__ __forceinline__ void rot_from_unit(Quat n, float R[3][3]) {
 }
 __device__ __forceinline__ Quat load_q(const float *p, int i) {
     float4 v = *reinterpret_cast<const float4 *>(p + 4 * (size_t)i);
+    return Quat{v.x, v.y, v.z, v.w};
+}
+// the current rotation of Gaussian gi as the reference's get_loss sees it: F.normalize(unnorm_rotations) (helpers.py:40)
+__device__ __forceinline__ Quat load_rot(const TrackArgs &a, int gi) {
+    float4 v = *reinterpret_cast<const float4 *>(a.q + 4 * (size_t)gi);
+    if (a.unnorm) v = gsd_quat_normalize(v);
     return Quat{v.x, v.y, v.z, v.w};
 }
 
@@ -141,7 +148,7 @@ gsd_track_fg_kernel(TrackArgs a) {
     if (active) {
         gi = a.fg_index ? a.fg_index[f] : f;
         xi[0] = a.x[3 * (size_t)gi]; xi[1] = a.x[3 * (size_t)gi + 1]; xi[2] = a.x[3 * (size_t)gi + 2];
-        Quat qi = load_q(a.q, gi);
+        Quat qi = load_rot(a, gi);
         pi = load_q(a.prev_inv, f);
         Quat rel_i = qmul(qi, pi);
         float nrm = sqrtf(rel_i.w * rel_i.w + rel_i.x * rel_i.x + rel_i.y * rel_i.y + rel_i.z * rel_i.z);
@@ -155,7 +162,7 @@ gsd_track_fg_kernel(TrackArgs a) {
             const int j = a.nbr[e];
             const int gj = a.fg_index ? a.fg_index[j] : j;
             float xj[3] = {a.x[3 * (size_t)gj], a.x[3 * (size_t)gj + 1], a.x[3 * (size_t)gj + 2]};
-            Quat rel_j = qmul(load_q(a.q, gj), load_q(a.prev_inv, j));
+            Quat rel_j = qmul(load_rot(a, gj), load_q(a.prev_inv, j));
             float po[3] = {a.prev_off[3 * e], a.prev_off[3 * e + 1], a.prev_off[3 * e + 2]};
             EdgeOut o;
             eval_edge(a, xi, Ri, rel_i, xj, rel_j, a.nbr_w[e], a.nbr_d[e], po, o);
@@ -177,7 +184,7 @@ gsd_track_fg_kernel(TrackArgs a) {
             const int i2 = e / a.K;
             const int g2 = a.fg_index ? a.fg_index[i2] : i2;
             float x2[3] = {a.x[3 * (size_t)g2], a.x[3 * (size_t)g2 + 1], a.x[3 * (size_t)g2 + 2]};
-            Quat rel_2 = qmul(load_q(a.q, g2), load_q(a.prev_inv, i2));
+            Quat rel_2 = qmul(load_rot(a, g2), load_q(a.prev_inv, i2));
             float n2 = rsqrtf(rel_2.w * rel_2.w + rel_2.x * rel_2.x + rel_2.y * rel_2.y + rel_2.z * rel_2.z);
             Quat u2 = {rel_2.w * n2, rel_2.x * n2, rel_2.y * n2, rel_2.z * n2};
             float R2[3][3];
@@ -265,7 +272,7 @@ gsd_track_node_prep_kernel(TrackArgs a, float4 *__restrict__ node) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= a.Gf) return;
     const int gi = a.fg_index ? a.fg_index[f] : f;
-    const Quat rel = qmul(load_q(a.q, gi), load_q(a.prev_inv, f));
+    const Quat rel = qmul(load_rot(a, gi), load_q(a.prev_inv, f));
     node[2 * (size_t)f] = make_float4(a.x[3 * (size_t)gi], a.x[3 * (size_t)gi + 1], a.x[3 * (size_t)gi + 2], 0.f);
     node[2 * (size_t)f + 1] = make_float4(rel.w, rel.x, rel.y, rel.z);
 }
@@ -446,9 +453,11 @@ gsd_track_bg_kernel(TrackArgs a, int fg_blocks) {
             s += fabsf(d);
             a.grad_x[3 * (size_t)gi + c] = a.c_bg * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
         }
+        const Quat qb = load_rot(a, gi);
+        const float qv[4] = {qb.w, qb.x, qb.y, qb.z};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            float d = a.q[4 * (size_t)gi + c] - a.bg_q0[4 * (size_t)b + c];
+            float d = qv[c] - a.bg_q0[4 * (size_t)b + c];
             s += fabsf(d);
             a.grad_q[4 * (size_t)gi + c] = a.c_bg * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
         }
@@ -515,6 +524,7 @@ extern "C" int gsd_track_losses_fwd_bwd(const GsdTrackLosses *t, void *stream) {
     }
     TrackArgs a;
     a.Gf = t->Gf; a.K = t->K; a.Gb = t->Gb;
+    a.unnorm = t->rotations_unnormalized;
     {
         int lg = 0;
         while ((1ll << lg) < (long long)(t->K > 0 ? t->K : 1)) ++lg;

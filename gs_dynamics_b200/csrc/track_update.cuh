@@ -36,8 +36,8 @@ __device__ __forceinline__ void gsd_track_update_apply(const GsdTrackUpdate &u, 
         float4 gb = reinterpret_cast<const float4 *>(u.g_rot_b)[i];
         ga.x += gb.x; ga.y += gb.y; ga.z += gb.z; ga.w += gb.w;
     }
-    const float n = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
-    const float4 qn = make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
+    const float n = gsd_quat_norm(q);
+    const float4 qn = make_float4(__fdiv_rn(q.x, n), __fdiv_rn(q.y, n), __fdiv_rn(q.z, n), __fdiv_rn(q.w, n));
     const float dot = qn.x * ga.x + qn.y * ga.y + qn.z * ga.z + qn.w * ga.w;
     const float gq[4] = {(ga.x - qn.x * dot) / n, (ga.y - qn.y * dot) / n, (ga.z - qn.z * dot) / n, (ga.w - qn.w * dot) / n};
     float4 m4 = reinterpret_cast<float4 *>(u.m_rot)[i], v4 = reinterpret_cast<float4 *>(u.v_rot)[i];

@@ -68,13 +68,16 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def raster_forward(settings, means3D, opacities, colors0, scales, rotations, colors1=None, bg1=None, capacity=None, sticky=None):
+def raster_forward(settings, means3D, opacities, colors0, scales, rotations, colors1=None, bg1=None, capacity=None, sticky=None,
+                   unnorm_rotations=None):
     """Runs the forward kernels. Returns (color [3*n_sets,H,W], radii [G] int32, depth [1,H,W], state).
 
     capacity=None reproduces upstream behaviour: the instance count R is read back once (one D2H sync, what
     upstream's num_rendered copy does) and buffers are sized exactly.  Passing a capacity >= R makes the call
     fully asynchronous; state.status[1] is set on the device if it was too small, and `sticky` (int32[2] CUDA tensor, zeroed
-    by the caller) accumulates max R / number of overflowed calls across calls (read it once per frame, not per call)."""
+    by the caller) accumulates max R / number of overflowed calls across calls (read it once per frame, not per call).
+    unnorm_rotations ([G,4]): `rotations` is then an OUTPUT buffer — the preprocess kernel writes F.normalize(unnorm_rotations)
+    into it and renders with it (params2rendervar without a separate normalisation launch)."""
     lib = _lib.lib()
     means3D = _f32c(means3D, "means3D")
     dev = means3D.device
@@ -101,6 +104,10 @@ def raster_forward(settings, means3D, opacities, colors0, scales, rotations, col
     if bg1 is not None:
         bg1 = _f32c(bg1, "bg1").reshape(-1)
 
+    if unnorm_rotations is not None:
+        unnorm_rotations = _f32c(unnorm_rotations, "unnorm_rotations")
+        if unnorm_rotations.shape != (G, 4):
+            raise ValueError("unnorm_rotations must be [G,4]")
     with torch.cuda.device(dev):
         st = _stream()
         status = torch.empty(_lib.GSD_STATUS_WORDS, dtype=torch.int32, device=dev)   # zeroed by the library (memset node)
@@ -112,6 +119,7 @@ def raster_forward(settings, means3D, opacities, colors0, scales, rotations, col
         d.bg1 = bg1.data_ptr() if bg1 is not None else None
         d.means3D, d.opacities, d.scales, d.rotations = means3D.data_ptr(), opacities.data_ptr(), scales.data_ptr(), rotations.data_ptr()
         d.colors0 = colors0.data_ptr()
+        d.unnorm_rotations = unnorm_rotations.data_ptr() if unnorm_rotations is not None else None
         d.colors1 = colors1.data_ptr() if colors1 is not None else None
         d.radii, d.status = radii.data_ptr(), status.data_ptr()
         if sticky is not None:
@@ -141,7 +149,7 @@ def raster_forward(settings, means3D, opacities, colors0, scales, rotations, col
 
     state = RasterState()
     state.desc = d
-    state.keep = (means3D, opacities, colors0, colors1, scales, rotations, view, proj, bg0, bg1, geom, binning, image,
+    state.keep = (means3D, opacities, colors0, colors1, scales, rotations, unnorm_rotations, view, proj, bg0, bg1, geom, binning, image,
                   color, depth, radii, status, sticky)
     state.capacity, state.G, state.W, state.H, state.n_sets, state.status = capacity, G, W, H, n_sets, status
     return color, radii, depth, state

@@ -145,9 +145,10 @@ def calc_psnr(img1, img2):
 # ----------------------------------------------------------------------------------------------------
 # physical priors (rigid / rot / iso / floor / bg)
 # ----------------------------------------------------------------------------------------------------
-def _track_priors_launch(means3D, rotations, variables, weights):
+def _track_priors_launch(means3D, rotations, variables, weights, unnormalized=False):
     """One launch of gsd_track_losses_fwd_bwd: returns (losses[6] = rigid, rot, iso, floor, bg, weighted total; dL/dmeans3D;
-    dL/drotations).  Plain function: the autograd wrapper below and the fused step both call it (no shared state)."""
+    dL/drotations).  Plain function: the autograd wrapper below and the fused step both call it (no shared state).
+    unnormalized: `rotations` is params['unnorm_rotations']; the kernels normalise on the fly (gradient w.r.t. the normalised)."""
     lib = _lib.lib()
     x = R._f32c(means3D, "means3D")
     q = R._f32c(rotations, "rotations")
@@ -159,6 +160,7 @@ def _track_priors_launch(means3D, rotations, variables, weights):
     K = int(v["neighbor_indices_i32"].shape[1]) if Gf > 0 else 0
     Gb = int(bg.shape[0]) if bg is not None else 0
     t.G, t.Gf, t.K, t.Gb = G, Gf, K, Gb
+    t.rotations_unnormalized = 1 if unnormalized else 0
     ptr = lambda tt: tt.data_ptr() if tt is not None and tt.numel() > 0 else None
     t.means3D, t.rotations = x.data_ptr(), q.data_ptr()
     t.fg_index = ptr(fg)
@@ -689,7 +691,8 @@ class FusedTrackingStep(TrackingStep):
         tst = self.tstats[idx] if idx is not None else None
         with torch.cuda.device(x.device):
             st = _stream()
-            _lib.check(lib.gsd_track_normalize_rotations(G, uq.data_ptr(), self.rot.data_ptr(), st), "gsd_track_normalize_rotations")
+            # F.normalize(unnorm_rotations) (params2rendervar) happens inside the consumers: the rasterizer's preprocess kernel
+            # writes self.rot for the backward, the priors' kernels normalise on the fly — no launch in front of the fork
             # the physical priors depend only on the parameters, not on the render: they run on a side stream concurrently
             # with binning / sorting / blending (fork-join, captured as parallel branches of the CUDA graph)
             main = torch.cuda.current_stream()
@@ -699,8 +702,8 @@ class FusedTrackingStep(TrackingStep):
                 fork.record(main)
                 with torch.cuda.stream(self.side):
                     self.side.wait_event(fork)
-                    parts, gx_p, gq_p = _track_priors_launch(x.detach(), self.rot, V, (self.w['weight_rigid'], self.w['weight_rot'],
-                                                             self.w['weight_iso'], FLOOR_WEIGHT, self.w['weight_bg']))
+                    parts, gx_p, gq_p = _track_priors_launch(x.detach(), uq.detach(), V, (self.w['weight_rigid'], self.w['weight_rot'],
+                                                             self.w['weight_iso'], FLOOR_WEIGHT, self.w['weight_bg']), unnormalized=True)
                     join = torch.cuda.Event()
                     join.record(self.side)
                 for tns in (parts, gx_p, gq_p):
@@ -711,7 +714,7 @@ class FusedTrackingStep(TrackingStep):
                 parts, gx_p, gq_p, join = launch_priors()
             color, radii, _, state = R.raster_forward(data['cam'], x.detach(), self.opac, self.rgb, self.scales, self.rot,
                                                       colors1=self.seg, capacity=capacity,
-                                                      sticky=self.sticky if capacity is not None else None)
+                                                      sticky=self.sticky if capacity is not None else None, unnorm_rotations=uq.detach())
             if self.priors_fork == 'after_forward':
                 parts, gx_p, gq_p, join = launch_priors()
             prior = parts[5]

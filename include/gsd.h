@@ -85,6 +85,10 @@ typedef struct {
                       * forward calls that overflowed `capacity`. Lets a caller that replays a captured graph thousands of
                       * times check ONCE per frame that no replay dropped instances (the reference sizes its buffers exactly
                       * from num_rendered on every call, /root/reference/src/tracking/train_utils.py:178) */
+    const float *unnorm_rotations; /* [G,4] or NULL.  When set, `rotations` is an OUTPUT: the preprocess kernel computes
+                      * rotations = F.normalize(unnorm_rotations) (params2rendervar, helpers.py:40) on the fly, uses it and writes
+                      * it to `rotations` (a writable [G,4] buffer) for the backward — the tracker's iteration then needs no
+                      * separate normalisation launch */
 } GsdRasterFwd;
 
 typedef struct {
@@ -176,6 +180,8 @@ typedef struct {
     float *losses;                  /* [6] rigid, rot, iso, floor, bg (unweighted means), weighted total */
     float *grad_means3D;            /* [G,3] d(weighted total)/d means3D, fully overwritten */
     float *grad_rotations;          /* [G,4] d(weighted total)/d rotations, fully overwritten */
+    int32_t rotations_unnormalized; /* != 0: `rotations` holds params['unnorm_rotations']; F.normalize is applied on the fly (the
+                                     * gradient is still w.r.t. the NORMALISED rotations, as gsd_track_update expects) */
 } GsdTrackLosses;
 int gsd_track_losses_workspace_bytes(int32_t Gf, int32_t Gb, size_t *bytes);
 /* packs (neighbour id, weight, rest distance, previous offset) of every edge into one 32-byte record; call once per

@@ -33,16 +33,9 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         torch.cuda.synchronize()
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "gsd_" in e.name]
 ev.sort(key=lambda e: e.time_range.start)
-# split into replays at the first kernel of the iteration
-first = ev[0].name
-its, cur = [], []
-for e in ev:
-    if e.name == first and cur:
-        its.append(cur)
-        cur = []
-    cur.append(e)
-its.append(cur)
-its = [it for it in its if len(it) == len(its[0])]
+# split into replays: every replay launches the same kernels; the torch.cuda.synchronize() between replays separates them in time
+per = len(ev) // n
+its = [sorted(ev[k * per:(k + 1) * per], key=lambda e: e.time_range.start) for k in range(n)] if per * n == len(ev) else [ev]
 print("# %d replays of %d kernels, G = %d; start offset / duration in us (mean over replays); '|' marks the side branch" % (len(its), len(its[0]), G))
 nk = len(its[0])
 t_end = 0.0
