@@ -36,7 +36,7 @@ class GsdRasterBwd(C.Structure):
         ("dL_dcolor", C.c_void_p), ("partial_ws", C.c_void_p),
         ("dL_dmeans3D", C.c_void_p), ("dL_dmeans2D", C.c_void_p), ("dL_dcolors0", C.c_void_p),
         ("dL_dcolors1", C.c_void_p), ("dL_dopacities", C.c_void_p), ("dL_dscales", C.c_void_p),
-        ("dL_drotations", C.c_void_p),
+        ("dL_drotations", C.c_void_p), ("prefix_done", C.c_int32),
     ]
 
 

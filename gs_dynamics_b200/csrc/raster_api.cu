@@ -11,7 +11,7 @@ int gsd_launch_count(int G, const GsdGeomWs &g, int32_t *status, cudaStream_t st
 int gsd_launch_mark_visible(int G, const GsdCam &cam, const float *means3D, uint8_t *vis, cudaStream_t st);
 int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const GsdGeomWs &g, const GsdBinWs &b, int32_t *zero_flags, int n_flags, cudaStream_t st);
 int gsd_launch_render_fwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st);
-int gsd_launch_render_bwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st);
+int gsd_launch_render_bwd(const GsdRenderParams &p, int tiles, int n_sets, int which, cudaStream_t st);
 int gsd_launch_preprocess_bwd(int G, const GsdCam &cam, const GsdRasterBwd *a, const GsdGeomWs &g, int geom_only, cudaStream_t st);
 int gsd_launch_preprocess_bwd_update(int G, const GsdCam &cam, const GsdRasterBwd *a, const GsdGeomWs &g, const GsdTrackUpdate &u, cudaStream_t st);
 
@@ -153,8 +153,10 @@ extern "C" int gsd_track_backward_update(const GsdRasterBwd *a, const GsdTrackUp
     return raster_backward_impl(a, stream, 3, u);
 }
 // stage 1: blend backward only (the dominant kernel, timed alone for the roofline); stage 2: per-Gaussian backward only
+// stage 4: the per-chunk prefix pass of the blend backward alone — it needs only the forward's state (no dL_dcolor, no partial_ws),
+// so a caller can run it on another stream while the image gradient is still being computed, and set prefix_done for the rest
 extern "C" int gsd_raster_backward_stage(const GsdRasterBwd *a, int32_t stage, void *stream) {
-    if (stage != 1 && stage != 2) { gsd_set_error("stage must be 1 or 2"); return GSD_ERR_INVALID; }
+    if (stage != 1 && stage != 2 && stage != 4) { gsd_set_error("stage must be 1, 2 or 4"); return GSD_ERR_INVALID; }
     return raster_backward_impl(a, stream, stage);
 }
 static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages, const GsdTrackUpdate *fused) {
@@ -163,7 +165,7 @@ static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages,
     GsdCam cam;
     int rc;
     if ((rc = make_cam(f, &cam))) return rc;
-    if (!f->geom_ws || !f->binning_ws || !f->image_ws || !a->partial_ws || !a->dL_dcolor ||
+    if (!f->geom_ws || !f->binning_ws || !f->image_ws || (stages != 4 && (!a->partial_ws || !a->dL_dcolor)) ||
         ((stages & 2) && !fused && f->G > 0 && (!a->dL_dmeans3D || !a->dL_dscales || !a->dL_drotations))) {
         gsd_set_error("null workspace/output pointer");
         return GSD_ERR_INVALID;
@@ -193,8 +195,9 @@ static int raster_backward_impl(const GsdRasterBwd *a, void *stream, int stages,
     // colours and opacities frozen (no output requested): geometry-only partials
     const int geom_only = (!a->dL_dcolors0 && !a->dL_dcolors1 && !a->dL_dopacities) ? 1 : 0;
     p.geom_only = geom_only;
+    if (stages == 4) return (f->G > 0 && f->capacity > 0) ? gsd_launch_render_bwd(p, tiles, f->n_sets, 1, st) : GSD_OK;
     if ((stages & 1) && f->G > 0 && f->capacity > 0)
-        if ((rc = gsd_launch_render_bwd(p, tiles, f->n_sets, st))) return rc;
+        if ((rc = gsd_launch_render_bwd(p, tiles, f->n_sets, a->prefix_done ? 2 : 3, st))) return rc;
     if ((stages & 2) && fused) return gsd_launch_preprocess_bwd_update(f->G, cam, a, g, *fused, st);
     if (stages & 2) return gsd_launch_preprocess_bwd(f->G, cam, a, g, geom_only, st);
     return GSD_OK;

@@ -28,9 +28,9 @@
 #define T_EPS 0.0001f
 #define TERMINAL_NONE (-1)
 
-// per-item state (floats, SoA over the 256 pixels): P, D, C[CH], last(int) | bwd: T_in, Q_in
+// per-item state (floats, SoA over the 256 pixels): P, D, C[CH], last(int) | bwd: T_in, Cpre[CH] (colour composited in front of the item)
 template <int CH> struct ItemState {
-    static constexpr int P = 0, D = 1, C = 2, LAST = 2 + CH, TIN = 3 + CH, QIN = 4 + CH, NF = 5 + CH;
+    static constexpr int P = 0, D = 1, C = 2, LAST = 2 + CH, TIN = 3 + CH, CPRE = 4 + CH, NF = 4 + 2 * CH;
 };
 // per-tile terminal record (written by the one chunk that terminates a pixel): T_stop, D_abs, C_abs[CH], last(int), cstar(int)
 template <int CH> struct TermState {
@@ -544,8 +544,12 @@ gsd_blend_fwd_replay_kernel(GsdRenderParams p) {
 
 
 // ------------------------------------------------------------------------------------------------------
-// backward B': per chunk and pixel, the incoming transmittance and Q = dL/dC . (colour composited after this point)
+// backward B': per chunk and pixel, the incoming transmittance and the colour composited in front of the chunk
 // ------------------------------------------------------------------------------------------------------
+// Depends only on the forward's results (chunk composites, n_contrib) — NOT on dL/dcolour: the tracking iteration runs it on a side
+// branch while the photometric kernels compute the image gradient, and the chunk kernel forms
+// Q_in = dL/dC . (colour still to come) = dL/dC . (C_final - T_final bg - C_pre) itself.  (Round 2's first version folded
+// dL/dC in here — one scalar per chunk and pixel instead of CH — and therefore sat on the critical path behind the SSIM gradient.)
 template <int CH>
 __global__ void __launch_bounds__(GSD_CWARPS * 32)
 gsd_blend_bwd_prefix_kernel(GsdRenderParams p) {
@@ -560,25 +564,11 @@ gsd_blend_bwd_prefix_kernel(GsdRenderParams p) {
     const int nc = min(p.chunk_ptr[tile + 1], p.max_items) - item0;
     if (nc <= 0) return;
     const bool inside = px < p.W && py < p.H;
-    float dLdC[CH];
-    float Q = 0.f;
-    int last = 0;
-    if (inside) {
-        const size_t pid = (size_t)py * p.W + px;
-        const size_t plane = (size_t)p.W * p.H;
-        const float Tfin = p.final_T[pid];
-        last = p.n_contrib[pid];
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            const float bgc = (c < 3) ? __ldg(p.bg0 + c) : (p.bg1 ? __ldg(p.bg1 + (c % 3)) : 0.f);
-            dLdC[c] = p.dL_dcolor[c * plane + pid];
-            Q += dLdC[c] * (p.out_color[c * plane + pid] - Tfin * bgc);
-        }
-    } else {
-#pragma unroll
-        for (int c = 0; c < CH; ++c) dLdC[c] = 0.f;
-    }
+    const int last = inside ? p.n_contrib[(size_t)py * p.W + px] : 0;
     float T = 1.0f;
+    float Cp[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) Cp[k] = 0.f;
     float nP = 0.f, nC[CH];
     int nl = 0;
     auto fetch = [&](int c) {
@@ -592,13 +582,10 @@ gsd_blend_bwd_prefix_kernel(GsdRenderParams p) {
     for (int c = 0; c < nc; ++c) {
         float *st = p.chunk_state + (size_t)(item0 + c) * IS::NF * 256;
         st[IS::TIN * 256 + t] = T;
-        st[IS::QIN * 256 + t] = Q;
-        if (c * GSD_CHUNK >= last) { // nothing of this or later chunks contributed to the pixel
-            for (int c2 = c + 1; c2 < nc; ++c2) {
-                float *s2 = p.chunk_state + (size_t)(item0 + c2) * IS::NF * 256;
-                s2[IS::TIN * 256 + t] = 0.f;
-                s2[IS::QIN * 256 + t] = 0.f;
-            }
+#pragma unroll
+        for (int k = 0; k < CH; ++k) st[(IS::CPRE + k) * 256 + t] = Cp[k];
+        if (c * GSD_CHUNK >= last) { // nothing of this or later chunks contributed to the pixel (the chunk kernel skips them by n_contrib)
+            for (int c2 = c + 1; c2 < nc; ++c2) p.chunk_state[(size_t)(item0 + c2) * IS::NF * 256 + IS::TIN * 256 + t] = 0.f;
             break;
         }
         const float cP = nP;
@@ -607,11 +594,9 @@ gsd_blend_bwd_prefix_kernel(GsdRenderParams p) {
 #pragma unroll
         for (int k = 0; k < CH; ++k) cC[k] = nC[k];
         if (c + 1 < nc) fetch(c + 1);
-        if (lc > 0) {
-            float cd = 0.f;
+        if (lc > 0) {   // the same fold as the forward's pass B
 #pragma unroll
-            for (int k = 0; k < CH; ++k) cd += dLdC[k] * cC[k];
-            Q -= T * cd;
+            for (int k = 0; k < CH; ++k) Cp[k] += T * cC[k];
             T = __fmul_rn(T, cP);
         }
     }
@@ -712,15 +697,16 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
         const size_t plane = (size_t)p.W * p.H;
         const float *st = p.chunk_state + (size_t)item * IS::NF * 256;
         T = st[IS::TIN * 256 + I.pix];
-        Q = st[IS::QIN * 256 + I.pix];
         last = p.n_contrib[pid];
         const float Tfin = p.final_T[pid];
         float bgdot = 0.f;
+        // Q = dL/dC . (colour composited behind the front of this chunk) = dL/dC . (C_final - T_final bg - C_pre)
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             const float bgc = (c < 3) ? __ldg(p.bg0 + c) : (p.bg1 ? __ldg(p.bg1 + (c % 3)) : 0.f);
             dLdC[c] = p.dL_dcolor[c * plane + pid];
             bgdot += bgc * dLdC[c];
+            Q += dLdC[c] * ((p.out_color[c * plane + pid] - Tfin * bgc) - st[(IS::CPRE + c) * 256 + I.pix]);
         }
         tail = Tfin * bgdot;
     } else {
@@ -800,7 +786,7 @@ gsd_blend_bwd_chunk_kernel(GsdRenderParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-size_t gsd_chunk_state_floats(int n_sets, int max_items) { return (size_t)(5 + 3 * n_sets) * 256 * (size_t)max_items; }
+size_t gsd_chunk_state_floats(int n_sets, int max_items) { return (size_t)(4 + 6 * n_sets) * 256 * (size_t)max_items; }
 size_t gsd_term_state_floats(int n_sets, int tiles) { return (size_t)(4 + 3 * n_sets) * 256 * (size_t)tiles; }
 
 int gsd_launch_render_fwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st) {
@@ -822,11 +808,15 @@ int gsd_launch_render_fwd(const GsdRenderParams &p, int tiles, int n_sets, cudaS
     return GSD_OK;
 }
 
-int gsd_launch_render_bwd(const GsdRenderParams &p, int tiles, int n_sets, cudaStream_t st) {
+// which: 1 = the per-chunk prefix pass (needs only the forward's state), 2 = the chunk kernel, 3 = both
+int gsd_launch_render_bwd(const GsdRenderParams &p, int tiles, int n_sets, int which, cudaStream_t st) {
     if (tiles == 0 || p.max_items == 0) return GSD_OK;
-    if (n_sets == 1) gsd_launch((gsd_blend_bwd_prefix_kernel<3>), dim3(tiles), dim3(GSD_CWARPS * 32), 0, st, p);
-    else gsd_launch((gsd_blend_bwd_prefix_kernel<6>), dim3(tiles), dim3(GSD_CWARPS * 32), 0, st, p);
-    GSD_LAUNCH_CHECK();
+    if (which & 1) {
+        if (n_sets == 1) gsd_launch((gsd_blend_bwd_prefix_kernel<3>), dim3(tiles), dim3(GSD_CWARPS * 32), 0, st, p);
+        else gsd_launch((gsd_blend_bwd_prefix_kernel<6>), dim3(tiles), dim3(GSD_CWARPS * 32), 0, st, p);
+        GSD_LAUNCH_CHECK();
+    }
+    if (!(which & 2)) return GSD_OK;
     const int threads = (GSD_CWARPS + 1) * 32;
     if (p.geom_only) {   // half-tile CTAs (see the kernel)
         const int th2 = (GSD_CWARPS / 2 + 1) * 32;

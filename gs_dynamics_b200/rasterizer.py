@@ -155,7 +155,17 @@ def raster_forward(settings, means3D, opacities, colors0, scales, rotations, col
     return color, radii, depth, state
 
 
-def raster_backward(state, grad_color, need_means2D=True, geom_only=False, fused_update=None):
+def raster_backward_prepare(state):
+    """The blend backward's per-chunk prefix pass (incoming transmittance / colour in front of every chunk).  It depends only on
+    the forward's state, so it can run on a side stream while the image gradient is computed; pass prefix_done=True to
+    raster_backward afterwards (the caller orders the two with events)."""
+    b = _lib.GsdRasterBwd()
+    b.fwd = state.desc
+    with torch.cuda.device(state.status.device):
+        _lib.check(_lib.lib().gsd_raster_backward_stage(C.byref(b), 4, _stream()), "gsd_raster_backward_stage")
+
+
+def raster_backward(state, grad_color, need_means2D=True, geom_only=False, fused_update=None, prefix_done=False):
     """Runs the backward kernels. Returns dict of gradients (float32 CUDA tensors). geom_only: colours and opacities are
     frozen (steady-state tracking) — their gradients are not produced and the blend backward reduces 5 values per instance.
     fused_update (a filled _lib.GsdTrackUpdate; implies geom_only, no means2D): the per-Gaussian backward kernel applies the
@@ -172,6 +182,7 @@ def raster_backward(state, grad_color, need_means2D=True, geom_only=False, fused
         b = _lib.GsdRasterBwd()
         b.fwd = state.desc
         b.dL_dcolor, b.partial_ws = grad_color.data_ptr(), partial.data_ptr()
+        b.prefix_done = 1 if prefix_done else 0
         if fused_update is not None:
             with _nvtx.range("gsd.raster_backward_update"):
                 _lib.check(lib.gsd_track_backward_update(C.byref(b), C.byref(fused_update), _stream()), "gsd_track_backward_update")

@@ -658,6 +658,7 @@ class FusedTrackingStep(TrackingStep):
         # the render branch is captured on a high-priority stream: when the side branch's CTAs fill the machine, the block scheduler
         # hands freed slots to the render branch first (tools/graph_timeline.py: preprocess starts 12 us earlier; -3 us per iteration)
         self.capture_stream = torch.cuda.Stream(device=params['means3D'].device, priority=-1)
+        self.prefix_on_side = True   # blend backward's prefix pass on the side branch, beside the photometric kernels
         self.fuse_update = True      # rasterizer backward + update in one per-Gaussian kernel (False: gsd_raster_backward, gsd_track_update)
         self.priors_fork = 'start'   # where the priors branch forks off the render branch: 'start' | 'after_forward'
         self.block_counter = torch.zeros(1, dtype=torch.int32, device=params['means3D'].device)   # self-resetting (gsd_track_update)
@@ -717,6 +718,16 @@ class FusedTrackingStep(TrackingStep):
                                                       sticky=self.sticky if capacity is not None else None, unnorm_rotations=uq.detach())
             if self.priors_fork == 'after_forward':
                 parts, gx_p, gq_p, join = launch_priors()
+            # the blend backward's per-chunk prefix pass needs only the forward's state: side branch, beside the photometric kernels
+            prefix_ev = None
+            if self.prefix_on_side:
+                fwd_done = torch.cuda.Event()
+                fwd_done.record(main)
+                with torch.cuda.stream(self.side):
+                    self.side.wait_event(fwd_done)
+                    R.raster_backward_prepare(state)
+                    prefix_ev = torch.cuda.Event()
+                    prefix_ev.record(self.side)
             prior = parts[5]
             ws = _ph_workspace(color)
             ph = torch.empty(8, dtype=torch.float32, device=x.device)
@@ -753,11 +764,13 @@ class FusedTrackingStep(TrackingStep):
             seen = torch.empty(G, dtype=torch.uint8, device=x.device)
             u.radii, u.max_2D_radius, u.seen = radii.data_ptr(), V['max_2D_radius'].data_ptr(), seen.data_ptr()
             u.block_counter = self.block_counter.data_ptr()
+            if prefix_ev is not None:
+                main.wait_event(prefix_ev)
             if self.fuse_update:
                 # the rasterizer's per-Gaussian backward applies the update in registers: no gradient arrays, one launch less
-                R.raster_backward(state, dL, fused_update=u)
+                R.raster_backward(state, dL, fused_update=u, prefix_done=prefix_ev is not None)
             else:
-                g = R.raster_backward(state, dL, need_means2D=False, geom_only=True)
+                g = R.raster_backward(state, dL, need_means2D=False, geom_only=True, prefix_done=prefix_ev is not None)
                 u.g_means_a, u.g_rot_a = g['means3D'].data_ptr(), g['rotations'].data_ptr()
                 _lib.check(lib.gsd_track_update(C.byref(u), st), "gsd_track_update")
             main.wait_event(loss_done)

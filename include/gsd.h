@@ -104,6 +104,8 @@ typedef struct {
                            * backward (colours / opacities frozen): 5 instead of 9-12 partials per instance */
     float *dL_dscales;    /* [G,3] */
     float *dL_drotations; /* [G,4] */
+    int32_t prefix_done;  /* != 0: gsd_raster_backward_stage(a, 4, other_stream) already ran the per-chunk prefix pass on this forward
+                           * state (and the caller ordered this call behind it) */
 } GsdRasterBwd;
 
 /* out[0] geom_ws, out[1] binning_ws, out[2] image_ws, out[3] partial_ws (backward scratch) — bytes */
@@ -119,7 +121,8 @@ int gsd_raster_forward(const GsdRasterFwd *a, void *stream);
 /* blend backward (deterministic, atomic-free) -> cov2D/projection/cov3D backward */
 int gsd_raster_backward(const GsdRasterBwd *a, void *stream);
 
-/* one stage of the backward alone (1 = blend backward, 2 = per-Gaussian backward); bench.py times stage 1 for the roofline */
+/* one stage of the backward alone (1 = blend backward, 2 = per-Gaussian backward; bench.py times stage 1 for the roofline;
+ * 4 = only the blend backward's per-chunk prefix pass, which needs the forward's state but neither dL_dcolor nor partial_ws) */
 int gsd_raster_backward_stage(const GsdRasterBwd *a, int32_t stage, void *stream);
 
 /* replaces _C.mark_visible: visible[g] = (view-space z > 0.2) */
