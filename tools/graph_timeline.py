@@ -37,18 +37,25 @@ ev.sort(key=lambda e: e.time_range.start)
 per = len(ev) // n
 its = [sorted(ev[k * per:(k + 1) * per], key=lambda e: e.time_range.start) for k in range(n)] if per * n == len(ev) else [ev]
 print("# %d replays of %d kernels, G = %d; start offset / duration in us (mean over replays); '|' marks the side branch" % (len(its), len(its[0]), G))
-nk = len(its[0])
+# kernels are matched by NAME across replays (every kernel of the iteration occurs once; concurrent branches may start in a
+# different order from replay to replay), rows are ordered by mean start
 t_end = 0.0
 rows = []
-for k in range(nk):
-    st = sum(it[k].time_range.start - it[0].time_range.start for it in its) / len(its)
-    du = sum(it[k].time_range.end - it[k].time_range.start for it in its) / len(its)
-    name = re.sub(r"\(.*", "", its[0][k].name).replace("void ", "")
-    rows.append((st, du, name))
+names = [re.sub(r"\(.*", "", e.name).replace("void ", "") for e in its[0]]
+for nm in names:
+    st = du = 0.0
+    for it in its:
+        t0 = min(e.time_range.start for e in it)
+        e = next(e for e in it if re.sub(r"\(.*", "", e.name).replace("void ", "") == nm)
+        st += e.time_range.start - t0
+        du += e.time_range.end - e.time_range.start
+    st /= len(its); du /= len(its)
+    rows.append((st, du, nm))
     t_end = max(t_end, st + du)
+rows.sort()
 prev_end = 0.0
 for st, du, name in rows:
-    side = any(s in name for s in ("gsd_track_node_prep", "gsd_track_fg", "gsd_track_bg", "gsd_track_finish", "gsd_ssim_finish"))
+    side = any(s in name for s in ("gsd_track_node_prep", "gsd_track_fg", "gsd_track_bg", "gsd_track_finish", "gsd_ssim_finish", "gsd_blend_bwd_prefix"))
     gap = "" if side else "  (gap %5.1f)" % (st - prev_end)
     if not side:
         prev_end = st + du

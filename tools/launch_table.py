@@ -7,7 +7,7 @@ import sys
 
 def main():
     rows = list(csv.reader(open(sys.argv[1])))
-    first = sys.argv[2] if len(sys.argv) > 2 else "normalize_rot"
+    first = sys.argv[2] if len(sys.argv) > 2 else "track_node_prep"
     for i, r in enumerate(rows):
         if "Kernel Name" in r:
             h, st = r, i + 1

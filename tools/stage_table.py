@@ -6,7 +6,7 @@ profiles/roofline_traffic.json from ONE ncu pass over an eager steady-state iter
 
   python tools/stage_table.py gpurun_out/stages_100k.csv 100000 [hbm_gbs]
 
-The LAST complete iteration of the list is used (from one gsd_track_normalize launch to the next).  Per launch: device time
+The LAST complete iteration of the list is used (from one gsd_track_node_prep launch to the next).  Per launch: device time
 (cold-cache, serialised: compare SHARES), DRAM bytes, warp instructions, and the two fractions that matter: DRAM bytes / time
 against the measured HBM peak, warp instructions / time against the issue-slot peak (148 SMs x 4 schedulers x SM clock)."""
 import csv
@@ -40,7 +40,9 @@ def main():
         except ValueError:
             pass
     L = [launches[i] for i in order]
-    idx = [i for i, l in enumerate(L) if "normalize_rot" in l["kernel"]]
+    # first launch of an eager iteration: the priors' node-record kernel (side branch, launched first by the host); older builds
+    # started with the rotation normalisation kernel
+    idx = [i for i, l in enumerate(L) if "track_node_prep" in l["kernel"]] or [i for i, l in enumerate(L) if "normalize_rot" in l["kernel"]]
     if len(idx) < 2:
         raise SystemExit("need at least two iterations in the launch list")
     it = L[idx[-2]:idx[-1]]
