@@ -123,7 +123,7 @@ EXPORTS = [
     "gsd_photometric_workspace_bytes", "gsd_photometric_forward", "gsd_photometric_backward", "gsd_photometric_stats",
     "gsd_photometric_reduce",
     "gsd_track_losses_workspace_bytes", "gsd_track_losses_fwd_bwd", "gsd_track_pack_edges", "gsd_adam_step", "gsd_track_update_radii",
-    "gsd_track_normalize_rotations", "gsd_track_update", "gsd_track_backward_update", "gsd_photometric_target_stats",
+    "gsd_track_normalize_rotations", "gsd_track_update", "gsd_track_backward_update", "gsd_photometric_target_stats", "gsd_track_unpack_target_u8",
     "gsd_gnn_edges_workspace_bytes", "gsd_gnn_build_edges", "gsd_gnn_edge_inputs", "gsd_gnn_aggregate_workspace_bytes",
     "gsd_gnn_aggregate", "gsd_gnn_aggregate_bwd_workspace_bytes", "gsd_gnn_aggregate_bwd", "gsd_gnn_edge_inputs_bwd", "gsd_fps", "gsd_tf32_pack", "gsd_skin_bone_transforms", "gsd_skin_apply", "gsd_knn",
     "gsd_tf32_split", "gsd_linear_tf32x3", "gsd_linear_small", "gsd_densify_plan", "gsd_densify_apply",
@@ -155,6 +155,7 @@ def lib():
     l.gsd_photometric_reduce.argtypes = [C.POINTER(GsdPhotometric), C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_photometric_backward.argtypes = [C.POINTER(GsdPhotometric), C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_photometric_target_stats.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.gsd_track_unpack_target_u8.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_track_normalize_rotations.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     l.gsd_track_update.argtypes = [C.POINTER(GsdTrackUpdate), C.c_void_p]
     l.gsd_track_backward_update.argtypes = [C.POINTER(GsdRasterBwd), C.POINTER(GsdTrackUpdate), C.c_void_p]

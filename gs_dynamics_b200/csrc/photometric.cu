@@ -530,6 +530,39 @@ extern "C" int gsd_photometric_target_stats(int32_t C, int32_t H, int32_t W, con
     return GSD_OK;
 }
 
+// ---- targets as they are at rest ----------------------------------------------------------------------------------------
+// The reference's dataset is PNG files: an 8-bit RGB(A) image and an 8-bit segmentation mask per camera and frame
+// (train_utils.py:66-75: `torch.tensor(im).float().cuda().permute(2, 0, 1) / 255`, `torch.stack((seg, zeros, 1 - seg))`).  It converts
+// to float32 on the HOST and uploads 6 float planes (7.4 MB per 640x480 camera); uploading the bytes (1.2 MB) and converting here
+// gives bit-identical planes (uint8 -> float is exact, the division is IEEE) for a sixth of the PCIe traffic.
+__global__ void __launch_bounds__(256)
+gsd_unpack_target_u8_kernel(int n_px, int cin, const uint8_t *__restrict__ im, const uint8_t *__restrict__ seg, float *__restrict__ out) {
+    gsd_pdl_wait();
+    gsd_pdl_launch();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_px) return;
+    const uint8_t *px = im + (size_t)i * cin;
+    out[i] = __fdiv_rn((float)px[0], 255.0f);
+    out[(size_t)n_px + i] = __fdiv_rn((float)px[1], 255.0f);
+    out[2 * (size_t)n_px + i] = __fdiv_rn((float)px[2], 255.0f);
+    const float sg = (float)seg[i];
+    out[3 * (size_t)n_px + i] = sg;
+    out[4 * (size_t)n_px + i] = 0.0f;
+    out[5 * (size_t)n_px + i] = 1.0f - sg;
+}
+
+extern "C" int gsd_track_unpack_target_u8(int32_t H, int32_t W, int32_t im_channels, const uint8_t *im_hwc, const uint8_t *seg,
+                                          float *target6, void *stream) {
+    if (H <= 0 || W <= 0 || (im_channels != 3 && im_channels != 4) || !im_hwc || !seg || !target6) {
+        gsd_set_error("invalid arguments (im_channels must be 3 or 4)");
+        return GSD_ERR_INVALID;
+    }
+    const int n = H * W;
+    gsd_launch(gsd_unpack_target_u8_kernel, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, n, im_channels, im_hwc, seg, target6);
+    GSD_LAUNCH_CHECK();
+    return GSD_OK;
+}
+
 // grad = (gscale_ptr ? *gscale_ptr : 1) * set_weight[set] * d loss_set / d rendered
 extern "C" int gsd_photometric_backward(const GsdPhotometric *p, const float *gscale_ptr, float *grad, void *stream) {
     int rc;

@@ -128,6 +128,9 @@ __device__ __forceinline__ void eval_edge(const TrackArgs &a, const float xi[3],
 #ifndef TRK_MIN_CTAS
 #define TRK_MIN_CTAS 8
 #endif
+#ifndef TRK_THREADS
+#define TRK_THREADS 128   // threads per CTA of the packed kernel (a multiple of 128)
+#endif
 #define GSD_PRIORS_CTAS_PER_SM_DEFAULT 0
 #define GSD_PRIORS_CARVEOUT_DEFAULT (-1)
 __global__ void __launch_bounds__(128)
@@ -277,21 +280,28 @@ gsd_track_node_prep_kernel(TrackArgs a, float4 *__restrict__ node) {
     node[2 * (size_t)f + 1] = make_float4(rel.w, rel.x, rel.y, rel.z);
 }
 
-__global__ void __launch_bounds__(128, TRK_MIN_CTAS)
+__global__ void __launch_bounds__(TRK_THREADS, TRK_MIN_CTAS)
 gsd_track_fg_packed_kernel(TrackArgs a, const float4 *__restrict__ node, const float4 *__restrict__ edge, int n_vblocks) {
     gsd_pdl_wait();
     gsd_pdl_launch();
-    __shared__ float red[4][4];
+    constexpr int NG = TRK_THREADS / 128;   // virtual blocks (128 threads = 32 points, one row of block_sums each) side by side in a CTA
+    __shared__ float red_all[NG][4][4];
+    float (*red)[4] = red_all[threadIdx.x >> 7];
+    const int tg = threadIdx.x & 127;
     // the grid may be smaller than the number of 128-thread blocks of work (see gsd_track_losses_fwd_bwd): a CTA then walks a
     // CONTIGUOUS run of virtual blocks (consecutive blocks are neighbours on the Morton curve: the node records one block pulled
     // into L1 are the next block's neighbours too); sums are kept per virtual block (fixed order, grid-independent)
-    const int vb_per = (n_vblocks + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int vb_end = min(n_vblocks, ((int)blockIdx.x + 1) * vb_per);
-    for (int vb = blockIdx.x * vb_per; vb < vb_end; ++vb) {
-    const int tid = vb * blockDim.x + threadIdx.x;
+    const int n_grp = (int)gridDim.x * NG;
+    const int my_grp = (int)blockIdx.x * NG + (int)(threadIdx.x >> 7);
+    const int vb_per = (n_vblocks + n_grp - 1) / n_grp;
+    const int vb_end = min(n_vblocks, (my_grp + 1) * vb_per);
+    for (int it = 0; it < vb_per; ++it) {     // uniform trip count over the CTA (block barriers inside); surplus groups idle
+    const int vb = my_grp * vb_per + it;
+    const bool vb_ok = vb < vb_end;
+    const int tid = vb * 128 + tg;
     const int f = tid / TRK_SPLIT, sub = tid % TRK_SPLIT;
     float s_rigid = 0.f, s_rot = 0.f, s_iso = 0.f, s_floor = 0.f;
-    const bool active = f < a.Gf;
+    const bool active = vb_ok && f < a.Gf;
     float xi[3] = {0.f, 0.f, 0.f};
     Quat n_i = {1.f, 0.f, 0.f, 0.f};
     float inv_n = 1.f;
@@ -403,12 +413,12 @@ gsd_track_fg_packed_kernel(TrackArgs a, const float4 *__restrict__ node, const f
     for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
-    if ((threadIdx.x & 31) == 0)
+    if ((tg & 31) == 0)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) red[threadIdx.x >> 5][c] = v[c];
+        for (int c = 0; c < 4; ++c) red[tg >> 5][c] = v[c];
     __syncthreads();
-    if (threadIdx.x < 4) a.block_sums[5 * (size_t)vb + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
-    if (threadIdx.x == 4) a.block_sums[5 * (size_t)vb + 4] = 0.f;
+    if (vb_ok && tg < 4) a.block_sums[5 * (size_t)vb + tg] = red[0][tg] + red[1][tg] + red[2][tg] + red[3][tg];
+    if (vb_ok && tg == 4) a.block_sums[5 * (size_t)vb + 4] = 0.f;
     __syncthreads();   // red[] is reused by the next virtual block
     }
 }
@@ -564,8 +574,10 @@ extern "C" int gsd_track_losses_fwd_bwd(const GsdTrackLosses *t, void *stream) {
         }
         const char *cap_env = getenv("GSD_PRIORS_CTAS_PER_SM");   // tuning override (tools/step_ablate.py)
         const int cap = cap_env ? atoi(cap_env) : GSD_PRIORS_CTAS_PER_SM_DEFAULT;
-        const int grid = cap > 0 ? (fgb < 148 * cap ? fgb : 148 * cap) : fgb;
-        gsd_launch(gsd_track_fg_packed_kernel, dim3(grid), dim3(128), 0, st, a, node, (const float4 *)t->edge_records, fgb);
+        const int ng = TRK_THREADS / 128;
+        const int ctas = (fgb + ng - 1) / ng;
+        const int grid = cap > 0 ? (ctas < 148 * cap ? ctas : 148 * cap) : ctas;
+        gsd_launch(gsd_track_fg_packed_kernel, dim3(grid), dim3(TRK_THREADS), 0, st, a, node, (const float4 *)t->edge_records, fgb);
         GSD_LAUNCH_CHECK();
     } else if (fgb > 0) {
         gsd_launch(gsd_track_fg_kernel, dim3(fgb), dim3(128), 0, st, a);

@@ -654,6 +654,7 @@ class FusedTrackingStep(TrackingStep):
             self.rot = torch.empty_like(params['unnorm_rotations'])
             self.tstats = [target_stats(tg) for tg in self.targets]
         self.outputs = {}
+        self._u8_stage = {}
         self.side = torch.cuda.Stream(device=params['means3D'].device)
         # the render branch is captured on a high-priority stream: when the side branch's CTAs fill the machine, the block scheduler
         # hands freed slots to the render branch first (tools/graph_timeline.py: preprocess starts 12 us earlier; -3 us per iteration)
@@ -679,6 +680,28 @@ class FusedTrackingStep(TrackingStep):
         with torch.cuda.device(tg.device):
             _lib.check(_lib.lib().gsd_photometric_target_stats(6, tg.shape[1], tg.shape[2], tg.data_ptr(), mu.data_ptr(),
                                                                s22.data_ptr(), _stream()), "gsd_photometric_target_stats")
+
+    def set_target_u8(self, cam_id, im_hwc_u8, seg_u8):
+        """Like set_target, from the dataset's bytes: im_hwc_u8 [H,W,3|4] uint8 (a PIL image as np.array gives it) and seg_u8 [H,W]
+        uint8, e.g. pinned host tensors.  One sixth of set_target's host-to-device traffic; the float planes are built on the
+        device exactly as train_utils.py:66-75 builds them on the host (im / 255; seg, 0, 1 - seg)."""
+        tg = self.targets[cam_id]
+        H, W = tg.shape[1], tg.shape[2]
+        if im_hwc_u8.dtype != torch.uint8 or seg_u8.dtype != torch.uint8 or im_hwc_u8.dim() != 3 or im_hwc_u8.shape[:2] != (H, W) \
+                or im_hwc_u8.shape[2] not in (3, 4) or seg_u8.shape != (H, W):
+            raise ValueError("set_target_u8 expects uint8 im [H,W,3|4] and seg [H,W] of the camera's size")
+        st = self._u8_stage.get(cam_id)
+        if st is None or st[0].shape != im_hwc_u8.shape:
+            st = (torch.empty(im_hwc_u8.shape, dtype=torch.uint8, device=tg.device), torch.empty((H, W), dtype=torch.uint8, device=tg.device))
+            self._u8_stage[cam_id] = st
+        st[0].copy_(im_hwc_u8, non_blocking=True)
+        st[1].copy_(seg_u8, non_blocking=True)
+        mu, s22 = self.tstats[cam_id]
+        with torch.cuda.device(tg.device):
+            _lib.check(_lib.lib().gsd_track_unpack_target_u8(H, W, im_hwc_u8.shape[2], st[0].data_ptr(), st[1].data_ptr(), tg.data_ptr(),
+                                                             _stream()), "gsd_track_unpack_target_u8")
+            _lib.check(_lib.lib().gsd_photometric_target_stats(6, H, W, tg.data_ptr(), mu.data_ptr(), s22.data_ptr(), _stream()),
+                       "gsd_photometric_target_stats")
 
     @torch.no_grad()
     def _iteration(self, data, capacity):

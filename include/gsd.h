@@ -156,6 +156,10 @@ int gsd_photometric_stats(const GsdPhotometric *p, void *stream);
 int gsd_photometric_reduce(const GsdPhotometric *p, const float *add, float *loss_out, void *stream);
 /* conv(y), conv(y*y) with the SSIM window: constant per target image, computed once per camera and frame */
 int gsd_photometric_target_stats(int32_t C, int32_t H, int32_t W, const float *y, float *y_mu, float *y_s22, void *stream);
+/* target planes from the dataset's bytes (train_utils.py:66-75): im_hwc [H,W,im_channels] uint8 (PIL layout, 3 or 4 channels),
+ * seg [H,W] uint8 -> target6 [6,H,W] float = (im / 255 | seg, 0, 1 - seg): what the reference builds on the host before its upload */
+int gsd_track_unpack_target_u8(int32_t H, int32_t W, int32_t im_channels, const uint8_t *im_hwc, const uint8_t *seg, float *target6,
+                               void *stream);
 /* grad = (gscale_ptr ? *gscale_ptr : 1) * set_weight[set] * d loss_set / d x_rendered (before the affine) */
 int gsd_photometric_backward(const GsdPhotometric *p, const float *gscale_ptr, float *grad, void *stream);
 

@@ -324,6 +324,34 @@ def test_fused_backward_update_kernel_equals_backward_plus_update():
     assert torch.equal(va['max_2D_radius'], vb['max_2D_radius']) and torch.equal(va['seen'], vb['seen'])
 
 
+def test_set_target_u8_builds_the_reference_planes():
+    """set_target_u8 (bytes up, float planes built on the device) == set_target with the planes train_utils.py:66-75 builds on the host."""
+    from gs_dynamics_b200 import tracking as TR
+    p, v, o, d = _tracking_problem(2000)
+    for g in o.param_groups:
+        if g['name'] not in ('means3D', 'unnorm_rotations'):
+            g['lr'] = 0.0
+    st = TR.FusedTrackingStep(p, v, o, d, use_graph=False)
+    st.prepare()
+    H, W = d[0]['im'].shape[1:]
+    gen = torch.Generator().manual_seed(3)
+    for cin in (3, 4):
+        im_u8 = torch.randint(0, 256, (H, W, cin), dtype=torch.uint8, generator=gen)
+        seg_u8 = torch.randint(0, 2, (H, W), dtype=torch.uint8, generator=gen)
+        im = (torch.tensor(im_u8.numpy()).float().permute(2, 0, 1)[:3].contiguous() / 255)          # the reference's host code
+        seg = torch.tensor(seg_u8.numpy().astype(np.float32)).float()
+        seg_col = torch.stack((seg, torch.zeros_like(seg), 1 - seg))
+        st.set_target(0, im.cuda(), seg_col.cuda())
+        ref_t, ref_mu, ref_s = st.targets[0].clone(), st.tstats[0][0].clone(), st.tstats[0][1].clone()
+        st.targets[0].zero_()
+        st.set_target_u8(0, im_u8.pin_memory(), seg_u8.pin_memory())
+        torch.cuda.synchronize()
+        assert torch.equal(st.targets[0], ref_t)
+        assert torch.equal(st.tstats[0][0], ref_mu) and torch.equal(st.tstats[0][1], ref_s)
+    with pytest.raises(ValueError):
+        st.set_target_u8(0, torch.zeros((H, W, 2), dtype=torch.uint8), torch.zeros((H, W), dtype=torch.uint8))
+
+
 def test_t0_densification_surgery_and_short_episode():
     """A9/A12 + episode loop: densify bookkeeping (clone / split / prune, Adam state surgery) and a 2-frame episode."""
     from gs_dynamics_b200 import tracking as TR, scenes, rasterizer as R
