@@ -11,11 +11,14 @@
 //   fwd B   per tile   combine the chunk composites in order; the chunk in which T_in * P crosses 1e-4 holds the reference's
 //                      stopping point — that pixel's chunk is replayed sequentially with the true T_in; -> colour, depth,
 //                      final_T, n_contrib
-//   bwd B'  per tile   per chunk and pixel: T_in and Q_in = dL/dC . (colour still to come), from the stored chunk composites
-//   bwd A'  per item   gradients of the chunk's Gaussians from (T_in, Q_in): front-to-back like the forward (T rebuilt by
+//   bwd B'  per tile   per chunk and pixel: T_in and C_pre (the colour composited in front of the chunk), from the stored chunk
+//                      composites — independent of dL/dC, so it can run beside the loss kernels
+//   bwd A'  per item   gradients of the chunk's Gaussians from T_in and Q_in = dL/dC . (C_final - T_final bg - C_pre), the colour
+//                      still to come: front-to-back like the forward (T rebuilt by
 //                      multiplication, not division); per-pixel partials summed across the warp with a transposed butterfly
 //                      (13 shuffles for 12 values), across warps in fixed order by a flusher warp, one 64-byte record per
 //                      instance: no atomics, bit-reproducible gradients
+// fwd C   per pair   the crossing chunk replayed for one 8x4 rectangle by one warp (list of (item, rectangle) pairs from pass B)
 // Inside an item the chunk's records are one TMA bulk copy per SoA plane (cp.async.bulk + mbarrier); 8 warps own 8x4 pixel
 // rectangles; every 32 records the lanes test one record each against the rectangle (conservative extents of the
 // alpha >= 1/255 ellipse) and only ballot survivors are blended, GSD_ILP at a time.

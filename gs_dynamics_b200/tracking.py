@@ -630,10 +630,12 @@ class FusedTrackingStep(TrackingStep):
     unnorm_rotations have a non-zero learning rate (train_utils.py:370-373), so opacities / scales / colours are constants
     and the whole iteration is
 
-        normalize -> rasterize (RGB+seg, one pass) -> photometric (both sets, affine colour fix fused) -> priors
-                  -> rasterize backward -> (normalize backward + gradient sum + Adam) for the two live groups
+        render branch:  rasterize (RGB+seg in one pass; the preprocess kernel normalises the rotations) -> photometric (both sets,
+                        affine colour fix fused) -> blend backward -> per-Gaussian backward with normalize-backward + gradient
+                        sum + Adam applied in registers (the two live groups)
+        side branch:    priors (rigid / rot / iso / floor / bg + gradients) | blend backward's prefix pass | scalar loss reduction
 
-    = ~24 launches of this library.  Same loss and parameter trajectory as get_loss + backward + FusedAdam.step (frozen groups
+    = 17 launches of this library.  Same loss and parameter trajectory as get_loss + backward + FusedAdam.step (frozen groups
     are skipped: their values cannot change; their unused Adam moments are not advanced).  Requires every group other than
     means3D / unnorm_rotations to have lr == 0; use TrackingStep otherwise."""
 
