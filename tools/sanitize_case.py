@@ -26,6 +26,13 @@ params, variables, opt, dataset, _ = workloads.tracking_problem_gpu(3000, 0, dev
 step = TR.FusedTrackingStep(params, variables, opt, dataset, use_graph=False)
 step.prepare([0])
 step.step(0)
+# targets from bytes (unpack kernel) and the two-launch variant of the backward (gsd_raster_backward + gsd_track_update)
+H, W = dataset[0]['im'].shape[1:]
+step.set_target_u8(0, torch.randint(0, 256, (H, W, 3), dtype=torch.uint8).pin_memory(), torch.randint(0, 2, (H, W), dtype=torch.uint8).pin_memory())
+step.step(0)
+step.fuse_update = False
+step.prefix_on_side = False
+step.step(0)
 # tcgen05 GEMM, both tile widths
 for M, N in ((300, 128), (700, 512)):
     x = torch.randn(M, 64, device=dev); w = torch.randn(N, 64, device=dev)
