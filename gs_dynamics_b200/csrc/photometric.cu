@@ -412,21 +412,23 @@ static PhPlan ph_plan(int C, int H, int W) {
     PhPlan pl;
     pl.ncol = env_ncol == 1 || env_ncol == 2 ? env_ncol : 2;
     pl.n_strip = (W + 32 * pl.ncol - 1) / (32 * pl.ncol);
-    // One warp per unit, all units resident at once.  Pick the number of row segments that maximises
-    //   (SM load balance) x (useful rows / streamed rows: 10 halo rows are recomputed per segment)
-    // among the choices that keep 7..16 warps per SM (fewer: the per-warp dependency chains are exposed; measured).
+    // One warp per unit (single-warp CTAs), all units resident at once.  An SM's time is that of its fullest scheduler: with w warps
+    // per SM, ceil(w / 4) units of (seg + 10) streamed rows each (10 halo rows are recomputed per segment).  Pick the number of
+    // row segments that minimises it among the choices that keep 7..16 warps per SM (fewer: the per-warp dependency chains are
+    // exposed; measured).  640x480, 6 planes: 19 segments = 1 140 warps = 8 per SM (two per scheduler) x 36 rows; the 17 segments
+    // of the first version (7 per SM: schedulers loaded 2-2-2-1, 39 rows) cost 3.6 us more per iteration.
     const int n_sm = 148;
     int best_seg = H;
-    double best = -1.0;
+    double best = 1e30;
     for (int n_seg = 1; n_seg <= (H + PH_MIN_SEG - 1) / PH_MIN_SEG; ++n_seg) {
         const int seg = (H + n_seg - 1) / n_seg;
         if ((H + seg - 1) / seg != n_seg) continue;
         const long long units = (long long)C * pl.n_strip * n_seg;
-        const int waves = (int)((units + n_sm - 1) / n_sm);
-        double eff = ((double)units / n_sm / waves) * ((double)seg / (seg + 2 * PH_R));
-        if (waves < 7) eff *= waves / 7.0;
-        if (waves > 16) eff *= 16.0 / waves;
-        if (eff > best) { best = eff; best_seg = seg; }
+        const int per_sm = (int)((units + n_sm - 1) / n_sm);
+        double cost = (double)((per_sm + 3) / 4) * (seg + 2 * PH_R);
+        if (per_sm < 7) cost *= 7.0 / per_sm;
+        if (per_sm > 16) cost *= per_sm / 16.0;
+        if (cost < best) { best = cost; best_seg = seg; }
     }
     int seg = env_seg > 0 ? env_seg : best_seg;
     if (seg < PH_MIN_SEG) seg = PH_MIN_SEG;
