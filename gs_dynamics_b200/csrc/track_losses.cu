@@ -133,6 +133,7 @@ __device__ __forceinline__ void eval_edge(const TrackArgs &a, const float xi[3],
 #endif
 #define GSD_PRIORS_CTAS_PER_SM_DEFAULT 0
 #define GSD_PRIORS_CARVEOUT_DEFAULT (-1)
+#define GSD_PRIORS_PIECES_DEFAULT 1
 __global__ void __launch_bounds__(128)
 gsd_track_fg_kernel(TrackArgs a) {
     gsd_pdl_wait();
@@ -281,7 +282,7 @@ gsd_track_node_prep_kernel(TrackArgs a, float4 *__restrict__ node) {
 }
 
 __global__ void __launch_bounds__(TRK_THREADS, TRK_MIN_CTAS)
-gsd_track_fg_packed_kernel(TrackArgs a, const float4 *__restrict__ node, const float4 *__restrict__ edge, int n_vblocks) {
+gsd_track_fg_packed_kernel(TrackArgs a, const float4 *__restrict__ node, const float4 *__restrict__ edge, int vb_first, int n_vblocks) {
     gsd_pdl_wait();
     gsd_pdl_launch();
     constexpr int NG = TRK_THREADS / 128;   // virtual blocks (128 threads = 32 points, one row of block_sums each) side by side in a CTA
@@ -296,8 +297,8 @@ gsd_track_fg_packed_kernel(TrackArgs a, const float4 *__restrict__ node, const f
     const int vb_per = (n_vblocks + n_grp - 1) / n_grp;
     const int vb_end = min(n_vblocks, (my_grp + 1) * vb_per);
     for (int it = 0; it < vb_per; ++it) {     // uniform trip count over the CTA (block barriers inside); surplus groups idle
-    const int vb = my_grp * vb_per + it;
-    const bool vb_ok = vb < vb_end;
+    const int vb = vb_first + my_grp * vb_per + it;
+    const bool vb_ok = my_grp * vb_per + it < vb_end;
     const int tid = vb * 128 + tg;
     const int f = tid / TRK_SPLIT, sub = tid % TRK_SPLIT;
     float s_rigid = 0.f, s_rot = 0.f, s_iso = 0.f, s_floor = 0.f;
@@ -574,10 +575,22 @@ extern "C" int gsd_track_losses_fwd_bwd(const GsdTrackLosses *t, void *stream) {
         }
         const char *cap_env = getenv("GSD_PRIORS_CTAS_PER_SM");   // tuning override (tools/step_ablate.py)
         const int cap = cap_env ? atoi(cap_env) : GSD_PRIORS_CTAS_PER_SM_DEFAULT;
+        // The work is launched in `pieces` consecutive kernels of at most one wave of CTAs each: a grid with a backlog of pending
+        // CTAs refills every slot a retiring CTA frees, so the render branch's 1 024-thread binning CTAs (same graph, other branch,
+        // higher priority) could not be placed until the backlog was gone; between two pieces whole SMs drain and go to them.
+        const char *sp_env = getenv("GSD_PRIORS_PIECES");
+        const int pieces_req = sp_env ? atoi(sp_env) : GSD_PRIORS_PIECES_DEFAULT;
+        const int pieces = pieces_req > 1 ? pieces_req : 1;
         const int ng = TRK_THREADS / 128;
-        const int ctas = (fgb + ng - 1) / ng;
-        const int grid = cap > 0 ? (ctas < 148 * cap ? ctas : 148 * cap) : ctas;
-        gsd_launch(gsd_track_fg_packed_kernel, dim3(grid), dim3(TRK_THREADS), 0, st, a, node, (const float4 *)t->edge_records, fgb);
+        const int per_piece = (fgb + pieces - 1) / pieces;
+        for (int pc = 0; pc < pieces; ++pc) {
+            const int vb0 = pc * per_piece, nvb = (fgb - vb0 < per_piece) ? fgb - vb0 : per_piece;
+            if (nvb <= 0) break;
+            const int ctas = (nvb + ng - 1) / ng;
+            const int grid = cap > 0 ? (ctas < 148 * cap ? ctas : 148 * cap) : ctas;
+            gsd_launch(gsd_track_fg_packed_kernel, dim3(grid), dim3(TRK_THREADS), 0, st, a, node, (const float4 *)t->edge_records, vb0, nvb);
+            GSD_LAUNCH_CHECK();
+        }
         GSD_LAUNCH_CHECK();
     } else if (fgb > 0) {
         gsd_launch(gsd_track_fg_kernel, dim3(fgb), dim3(128), 0, st, a);

@@ -114,3 +114,35 @@ def test_first_frame_step_refuses_graph_capture():
     with pytest.raises(ValueError, match="use_graph=False"):
         TR.TrackingStep({}, {}, None, [], is_initial_timestep=True, use_graph=True)
     TR.TrackingStep({}, {}, None, [], is_initial_timestep=True, use_graph=False)
+
+
+def test_morton_order_is_a_locality_preserving_permutation():
+    """Host side of the priors' packed tables (tracking._morton_order): a permutation whose consecutive points are close."""
+    from gs_dynamics_b200 import tracking as TR
+    g = torch.Generator().manual_seed(0)
+    pts = torch.rand(20000, 3, generator=g) * torch.tensor([0.5, 0.5, 0.1])
+    perm = TR._morton_order(pts)
+    assert sorted(perm.tolist()) == list(range(20000))
+    d_curve = (pts[perm][1:] - pts[perm][:-1]).norm(dim=1).mean()
+    d_rand = (pts[1:] - pts[:-1]).norm(dim=1).mean()
+    assert d_curve < 0.2 * d_rand
+    # degenerate clouds (all points equal / a single point) must not divide by zero
+    assert TR._morton_order(torch.zeros(5, 3)).tolist() == [0, 1, 2, 3, 4]
+    assert TR._morton_order(torch.ones(1, 3)).tolist() == [0]
+
+
+def test_edge_id_division_by_multiplication_is_exact():
+    """track_losses.cu replaces e / K by (e * magic) >> shift with magic = ceil(2^shift / K), shift = 31 + ceil(log2 K): exact for
+    every 31-bit edge id (same arithmetic restated with Python integers)."""
+    rng = np.random.default_rng(0)
+    for K in (1, 2, 3, 5, 7, 16, 17, 20, 31, 32, 33, 100, 1000, 65535):
+        lg = 0
+        while (1 << lg) < K:
+            lg += 1
+        shift = 31 + lg
+        magic = ((1 << shift) + K - 1) // K
+        assert magic < (1 << 32)
+        es = np.concatenate([rng.integers(0, 2 ** 31, size=2000), np.arange(0, 4 * K), 2 ** 31 - 1 - np.arange(0, 4 * K),
+                             np.arange(1, 50) * K, np.arange(1, 50) * K - 1])
+        for e in es.tolist():
+            assert (e * magic) >> shift == e // K, (K, e)

@@ -19,7 +19,11 @@ dev = torch.device("cuda")
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
 
-def measure(label, patch=None, fork='start', hi_prio=False, cap=None, carve=None):
+def measure(label, patch=None, fork='start', hi_prio=False, cap=None, carve=None, pieces=None):
+    if pieces is None:
+        os.environ.pop('GSD_PRIORS_PIECES', None)
+    else:
+        os.environ['GSD_PRIORS_PIECES'] = str(pieces)
     if carve is None:
         os.environ.pop('GSD_PRIORS_CARVEOUT', None)
     else:
@@ -113,5 +117,7 @@ for vname in variants:
         measure(vname, hi_prio=True, carve=int(vname[8:]))
     elif vname.startswith("carve"):
         measure(vname, carve=int(vname[5:]))
+    elif vname.startswith("pieces"):        # the priors kernel launched in N consecutive pieces
+        measure(vname, pieces=int(vname[6:]))
     elif vname.startswith("cap"):
         measure(vname, cap=int(vname[3:]))
