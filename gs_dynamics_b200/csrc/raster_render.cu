@@ -333,7 +333,7 @@ gsd_blend_fwd_finish_kernel(GsdRenderParams p) {
     using IS = ItemState<CH>;
     using TS = TermState<CH>;
     constexpr int NPL = (CH == 3) ? 3 : 4;
-    constexpr int BATCH = 4;
+    constexpr int BATCH = 4;   // chunks whose composites are in flight at once (8: 124 registers, 7.0 -> 9.5 us)
     const int tile = blockIdx.x;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int tx = tile % p.gx, ty = tile / p.gx;
