@@ -92,8 +92,15 @@ int gsd_carve_img(int W, int H, int n_sets, int max_items, void *base, GsdImgWs 
 }
 
 // ---- hist / scatter: one CTA per GSD_BIN_BLOCK Gaussians ------------------------------------------------------
+// BIN_THREADS threads per CTA walk the block's Gaussians (the shared-memory histogram stays per GSD_BIN_BLOCK Gaussians).  Smaller
+// CTAs would be placed sooner when the tracking iteration's side branch fills the SMs (a 1 024-thread CTA needs a whole SM's worth
+// of thread slots to come free at once; DESIGN.md "priors kernel"), but 256 threads walking four Gaussians each measured
+// +12 us per iteration: one thread per Gaussian stays.
+#ifndef BIN_THREADS
+#define BIN_THREADS 1024
+#endif
 template <bool SCATTER>
-__global__ void __launch_bounds__(GSD_BIN_BLOCK)
+__global__ void __launch_bounds__(BIN_THREADS)
 gsd_bin_kernel(int G, int gx, int n_tiles, int n_bb, const uint32_t *__restrict__ tiles, const uint2 *__restrict__ rect,
                const float *__restrict__ depth, int32_t *__restrict__ table, const uint2 *__restrict__ ranges,
                uint64_t *__restrict__ keys, uint32_t *__restrict__ slot_base, const uint32_t *__restrict__ block_base,
@@ -104,10 +111,11 @@ gsd_bin_kernel(int G, int gx, int n_tiles, int n_bb, const uint32_t *__restrict_
     const int bb = blockIdx.x;
     for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) bins[i] = 0;
     if (!SCATTER)   // the "published" flags of the blend work items, cleared for this forward pass
-        for (int z = bb * GSD_BIN_BLOCK + threadIdx.x; z < n_zero; z += gridDim.x * GSD_BIN_BLOCK) zero_fill[z] = 0;
+        for (int z = bb * BIN_THREADS + threadIdx.x; z < n_zero; z += gridDim.x * BIN_THREADS) zero_fill[z] = 0;
     if (!SCATTER && bb == 0 && threadIdx.x == 0) { counters[3] = 0; counters[4] = 0; }   // "tile bases published" flag of the scan launch; replay-pair count of the blend forward
     __syncthreads();
-    const int i = bb * GSD_BIN_BLOCK + threadIdx.x;
+    for (int gi = threadIdx.x; gi < GSD_BIN_BLOCK; gi += BIN_THREADS) {
+    const int i = bb * GSD_BIN_BLOCK + gi;
     if (i < G) {
         const uint32_t n = tiles[i];
         if (SCATTER) slot_base[i] += block_base[i >> 8]; // block-local offset -> global slot
@@ -126,6 +134,7 @@ gsd_bin_kernel(int G, int gx, int n_tiles, int n_bb, const uint32_t *__restrict_
                     }
                 }
         }
+    }
     }
     if (!SCATTER) {
         __syncthreads();
@@ -565,7 +574,7 @@ int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const Gs
     const size_t smem = (size_t)tiles * 4;
     // tile totals are accumulated with atomics by the histogram pass: the preprocess kernel zero-fills them (G > 0)
     if (G > 0) {
-        gsd_launch((gsd_bin_kernel<false>), dim3(b.n_bb), dim3(GSD_BIN_BLOCK), smem, st, G, cam.gx, tiles, b.n_bb, g.tiles, g.rect, g.depth, b.table,
+        gsd_launch((gsd_bin_kernel<false>), dim3(b.n_bb), dim3(BIN_THREADS), smem, st, G, cam.gx, tiles, b.n_bb, g.tiles, g.rect, g.depth, b.table,
                                                                     b.ranges, b.keys, g.slot_base, g.block_base, b.tile_total, b.counters, zero_flags, n_flags);
         GSD_LAUNCH_CHECK();
     } else {
@@ -578,7 +587,7 @@ int gsd_launch_binning(int G, const GsdCam &cam, const GsdRasterFwd *a, const Gs
         b.item_tile, b.counters, b.unit_tile, b.unit_seg, b.long_tile, b.exec_item, b.table, a->status, a->sticky);
     GSD_LAUNCH_CHECK();
     if (G == 0 || cap == 0) return GSD_OK;
-    gsd_launch((gsd_bin_kernel<true>), dim3(b.n_bb), dim3(GSD_BIN_BLOCK), smem, st, G, cam.gx, tiles, b.n_bb, g.tiles, g.rect, g.depth, b.table, b.ranges,
+    gsd_launch((gsd_bin_kernel<true>), dim3(b.n_bb), dim3(BIN_THREADS), smem, st, G, cam.gx, tiles, b.n_bb, g.tiles, g.rect, g.depth, b.table, b.ranges,
                                                                b.keys, g.slot_base, g.block_base, b.tile_total, b.counters, nullptr, 0);
     GSD_LAUNCH_CHECK();
     gsd_launch(gsd_tile_sort_kernel, dim3(148 * 2), dim3(MERGE_THREADS), LONG_SORT_SMEM, st, b.ranges, b.keys, b.keys_tmp, b.unit_tile, b.unit_seg, b.long_tile,
