@@ -177,6 +177,37 @@ def test_backward_is_bit_reproducible():
         assert torch.equal(outs[0][k], outs[1][k]) and torch.equal(outs[0][k], outs[2][k]), k
 
 
+def test_backward_prefix_pass_on_another_stream_gives_the_same_gradients():
+    """gsd_raster_backward_stage(.., 4, ..) (the blend backward's per-chunk prefix pass, which needs only the forward's state) run
+    ahead on a side stream + prefix_done == the plain backward, bit for bit, in both modes; and the unnormalised-rotations input
+    of the forward (F.normalize inside the preprocess kernel) renders what the pre-normalised input renders."""
+    from gs_dynamics_b200 import rasterizer as R
+    cam = make_camera(1, 640, 480)
+    sc, act = make_scene(40000, 4)
+    a = _to_cuda(act)
+    st = settings_from(cam, [0.1, 0.0, 0.2])
+    seg = sc["seg_colors"].cuda()
+    c, r, d, s = R.raster_forward(st, a["means3D"], a["opacities"], a["colors_precomp"], a["scales"], a["rotations"], colors1=seg)
+    dL = torch.randn_like(c)
+    side = torch.cuda.Stream()
+    for geom in (False, True):
+        ref = R.raster_backward(s, dL, need_means2D=not geom, geom_only=geom)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            R.raster_backward_prepare(s)
+        torch.cuda.current_stream().wait_stream(side)
+        got = R.raster_backward(s, dL, need_means2D=not geom, geom_only=geom, prefix_done=True)
+        for k, v in ref.items():
+            if v is not None:
+                assert torch.equal(v, got[k]), (geom, k)
+    unnorm = (a["rotations"] * torch.linspace(0.3, 3.0, a["rotations"].shape[0], device="cuda")[:, None]).contiguous()
+    rot_out = torch.empty_like(unnorm)
+    c2, r2, d2, s2 = R.raster_forward(st, a["means3D"], a["opacities"], a["colors_precomp"], a["scales"], rot_out, colors1=seg,
+                                      unnorm_rotations=unnorm)
+    assert rel_err(rot_out.cpu(), torch.nn.functional.normalize(unnorm).cpu()) < 1e-6
+    assert float((c2 - c).abs().max()) < 1e-4 and float((r2 - r).abs().float().max()) <= 1.0   # a 1-ulp quaternion may move a radius by one
+
+
 def test_forward_is_bit_reproducible_under_lookback_skipping():
     """The forward chunk kernel skips rectangles that its look-back finds already opaque; WHICH rectangles are skipped depends
     on CTA timing, the result must not: repeated renders of the 100k benchmark scene are bit-identical (and so are the backward
