@@ -306,10 +306,87 @@ class _Linear3x(torch.autograd.Function):
         return gx, gW, gb
 
 
+# hi / lo splits of the weights inside ONE training iteration (forward + backward of the unroll: the weights are constant until
+# the optimiser step, and every unroll step / the backward would split them again).  Only valid inside split_scope(): CUDA-graph
+# replays change the weights without touching their version counters, so nothing may outlive the iteration.  Entries keep their
+# source tensor alive (its address cannot be recycled while cached).
+_SPLIT_CACHE = None
+
+
+class split_scope:
+    def __enter__(self):
+        global _SPLIT_CACHE
+        self.prev, _SPLIT_CACHE = _SPLIT_CACHE, {}
+        return self
+
+    def __exit__(self, *exc):
+        global _SPLIT_CACHE
+        _SPLIT_CACHE = self.prev
+        return False
+
+
+def _train_split(W, transposed):
+    key = (W.data_ptr(), tuple(W.shape), tuple(W.stride()), transposed)
+    if _SPLIT_CACHE is not None and key in _SPLIT_CACHE:
+        return _SPLIT_CACHE[key][1]
+    ws = _tc_split(W.detach().t().contiguous() if transposed else W)
+    if _SPLIT_CACHE is not None:
+        _SPLIT_CACHE[key] = (W, ws)
+    return ws
+
+
+class _LinearTC(torch.autograd.Function):
+    """y = x W^T + b for GNN training with the hand-written tcgen05 kernel (gsd_linear_tf32x3: error-compensated 3xTF32, operands
+    split on chip) in the forward AND the grad-input product (gx = gy W = gsd_linear_tf32x3(gy, split(W^T))): no packed copy of
+    the activations in front of either.  grad-weight contracts over the rows (gW = gy^T x), which the kernel's K-major operand
+    layout does not cover: it stays three TF32 library GEMMs on the hi / lo halves of the packed operands, as in _Linear3x."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        y = _tc_linear(x, _train_split(W, False), b)
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W = ctx.saved_tensors
+        K, O = W.shape[1], W.shape[0]
+        gy = gy.contiguous()
+        gx = gW = None
+        if ctx.needs_input_grad[0]:
+            gx = _tc_linear(gy, _train_split(W, True))
+        if ctx.needs_input_grad[1]:
+            xp, _ = _tf32_pack(x)                                        # [rows, 3K] = [lo | hi | hi]
+            gp, _ = _tf32_pack(gy)                                       # [rows, 3O] = [lo | hi | hi]
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True
+            try:
+                g_lo, g_hi = gp[:, :O], gp[:, O:2 * O]
+                x_lo, x_hi = xp[:, :K], xp[:, K:2 * K]
+                gW = g_lo.t() @ x_hi
+                gW.addmm_(g_hi.t(), x_lo)
+                gW.addmm_(g_hi.t(), x_hi)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+        gb = gy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return gx, gW, gb
+
+
+# training GEMMs: "cublas" = library TF32 GEMMs over packed operands (_Linear3x), "tc" = the hand-written kernel for forward +
+# grad-input (_LinearTC).  Measured on B200 (bench.py's gnn_train iteration, batch 64 x n_future 5, one CUDA graph): cublas
+# 27.5 ms, tc 28.5 ms (eager: 35.9 / 34.6 ms) — the library's single K = 3 x 512 GEMM per product still beats the hand-written
+# kernel's ~60 % of the TF32 peak by more than its pack kernel costs, so the library path stays the default; GSD_TRAIN_GEMM=tc
+# (or gnn.TRAIN_GEMM = "tc") selects the hand-written one.  Both are covered by the gradient-parity tests.
+TRAIN_GEMM = os.environ.get("GSD_TRAIN_GEMM", "cublas")
+
+
 def _linear(x, W, b, fast):
-    """F.linear, or its 3xTF32 tensor-core twin when `fast` and the shape suits the pack kernel."""
+    """F.linear, or its 3xTF32 tensor-core twin when `fast` and the shape suits the kernels."""
     if fast and x.is_cuda and x.dim() == 2 and x.shape[0] >= 256 and W.shape[1] % 4 == 0 and W.shape[1] >= 128 and W.shape[0] % 4 == 0 \
             and W.shape[0] >= 128:
+        if TRAIN_GEMM == "tc" and W.shape[1] % 32 == 0 and W.shape[0] % 64 == 0 and W.shape[1] % 64 == 0:
+            return _LinearTC.apply(x.contiguous(), W, b)
         return _Linear3x.apply(x, W, b)
     return F.linear(x, W, b)
 

@@ -12,7 +12,7 @@ import torch
 import torch.nn.functional as F
 
 from . import dist as gdist
-from .gnn import EdgeIndex, edge_index_from_dense
+from .gnn import EdgeIndex, edge_index_from_dense, split_scope as gnn_split_scope
 
 
 def mse_loss(pred, gt, **kwargs):
@@ -196,8 +196,9 @@ def train_iteration(model, optimizer, data, n_future, loss_funcs, bucket=None):
         bucket.zero()
     else:
         optimizer.zero_grad()
-    loss_sum, parts = unrolled_loss(model, data, n_future, loss_funcs)
-    loss_sum.backward()
+    with gnn_split_scope():      # the weights' hi / lo splits are shared by the unroll steps and the backward of this iteration
+        loss_sum, parts = unrolled_loss(model, data, n_future, loss_funcs)
+        loss_sum.backward()
     if bucket is not None:
         bucket.all_reduce_mean()
     optimizer.step()

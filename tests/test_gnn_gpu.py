@@ -313,11 +313,14 @@ def test_edge_inputs_backward_kernel_vs_torch():
     assert _rel(st.grad.cpu(), st2.grad.cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("gemm", ["cublas", "tc"])
 @pytest.mark.parametrize("tag", ["sloth", "rope"])
-def test_training_unroll_gradients_match_reference(tag):
+def test_training_unroll_gradients_match_reference(tag, gemm, monkeypatch):
     """train.py:183-211 through gnn_train.unrolled_loss on the CUDA kernels vs the fixture generated from the reference's
-    model and loss functions; both calling conventions (dense Rr/Rs of the dataset, EdgeIndex)."""
+    model and loss functions; both calling conventions (dense Rr/Rs of the dataset, EdgeIndex); both training GEMM paths (library
+    TF32 GEMMs over packed operands / the hand-written tcgen05 kernel for forward + grad-input)."""
     from gs_dynamics_b200 import gnn, gnn_train
+    monkeypatch.setattr(gnn, "TRAIN_GEMM", gemm)
     B, n_obj, topk, adj, conn, seed, n_future = TGOLD[f"{tag}_cfg"]
     B, n_obj, topk, seed, n_future = int(B), int(n_obj), int(topk), int(seed), int(n_future)
     cfg = GO.sloth_cfg(128) if tag == "sloth" else GO.rope_cfg(128)
