@@ -59,7 +59,9 @@ struct GsdGeomWs { // per-Gaussian state
 #ifndef GSD_CHUNK
 #define GSD_CHUNK 128      // records per blend work item (tile lists are split into chunks processed in parallel)
 #endif
+#ifndef GSD_BIN_BLOCK
 #define GSD_BIN_BLOCK 1024 // Gaussians per binning block
+#endif
 struct GsdBinWs {
     int n_bb;            // binning blocks = ceil(G / GSD_BIN_BLOCK)
     int max_items;       // upper bound of blend work items = capacity / GSD_CHUNK + tiles

@@ -95,9 +95,9 @@ int gsd_carve_img(int W, int H, int n_sets, int max_items, void *base, GsdImgWs 
 // BIN_THREADS threads per CTA walk the block's Gaussians (the shared-memory histogram stays per GSD_BIN_BLOCK Gaussians).  Smaller
 // CTAs would be placed sooner when the tracking iteration's side branch fills the SMs (a 1 024-thread CTA needs a whole SM's worth
 // of thread slots to come free at once; DESIGN.md "priors kernel"), but 256 threads walking four Gaussians each measured
-// +12 us per iteration: one thread per Gaussian stays.
+// +12 us per iteration, and 256- / 512-Gaussian blocks with one thread per Gaussian (GSD_BIN_BLOCK) +3.5 / -0.5 us: 1 024 stays.
 #ifndef BIN_THREADS
-#define BIN_THREADS 1024
+#define BIN_THREADS GSD_BIN_BLOCK
 #endif
 template <bool SCATTER>
 __global__ void __launch_bounds__(BIN_THREADS)
